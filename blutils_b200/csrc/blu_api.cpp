@@ -1,0 +1,823 @@
+// blu_api.cpp -- C ABI (include/blu_consensus.h): context, taxonomy upload, chunked streaming of the outfmt-6
+// text through the CUDA kernels, result download/decoding and the reference-compatible writer.
+//
+// There is deliberately NO CPU implementation of the consensus here: everything that computes goes through
+// blu_kernels.cu; without a CUDA device every compute entry point fails with BLU_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+#include <filesystem>
+#include <fstream>
+#include <memory>
+#include <random>
+#include <string>
+#include <string_view>
+#include <thread>
+#include <unordered_set>
+#include <vector>
+
+#include "../../include/blu_consensus.h"
+#include "blu_decode.h"
+#include "blu_json.h"
+#include "blu_kernels.h"
+#include "blu_taxonomy.h"
+
+using namespace blu;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct CudaErr : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+struct UnsupportedErr : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define CK(expr)                                                                                        \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) throw CudaErr(std::string(#expr) + ": " + cudaGetErrorString(_e));       \
+    } while (0)
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+    void ensure(size_t n) {
+        if (n <= cap) return;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        CK(cudaMalloc((void**)&p, n * sizeof(T)));
+        cap = n;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+}  // namespace
+
+struct blu_ctx {
+    blu_opts opts{};
+    Cutoffs cut;
+    int device = 0;
+    int sms = 148;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev[6]{};
+    cudaEvent_t ev_h2d[2]{}, ev_free[2]{};
+    std::shared_ptr<HostTaxonomy> tax;
+    // device taxonomy
+    DevBuf<uint32_t> d_lin_off, d_lvl, d_bean, d_irank;
+    DevBuf<double> d_cut;
+    DevBuf<uint16_t> d_rcls, d_acls;
+    DevBuf<uint8_t> d_linok;
+    DevBuf<HashSlot> d_slots;
+    LinTables dT{};
+    // run buffers
+    DevBuf<uint8_t> d_text[2];
+    DevBuf<blu_record> d_rec;
+    DevBuf<blu_bean> d_beans;
+    DevBuf<blu_acc> d_accs;
+    DevBuf<uint64_t> d_defer;
+    DevBuf<uint8_t> d_pool;
+    DevBuf<unsigned long long> d_dup;
+    Counters* d_ctr = nullptr;
+    Counters* h_ctr = nullptr;  // pinned
+    std::vector<PinnedBuf> pinned_free;
+    std::string err;
+    blu_timings tm{};
+    uint64_t carry_bytes = 64ull << 20;
+
+    PinnedBuf acquire(size_t bytes) {
+        size_t best = SIZE_MAX;
+        for (size_t i = 0; i < pinned_free.size(); i++)
+            if (pinned_free[i].cap >= bytes && (best == SIZE_MAX || pinned_free[i].cap < pinned_free[best].cap)) best = i;
+        if (best != SIZE_MAX) {
+            PinnedBuf b = pinned_free[best];
+            pinned_free.erase(pinned_free.begin() + best);
+            return b;
+        }
+        PinnedBuf b;
+        size_t cap = std::max<size_t>(bytes, 4096);
+        CK(cudaHostAlloc(&b.p, cap, cudaHostAllocDefault));
+        b.cap = cap;
+        return b;
+    }
+    void release(PinnedBuf b) {
+        if (!b.p) return;
+        if (pinned_free.size() >= 16) {
+            cudaFreeHost(b.p);
+            return;
+        }
+        pinned_free.push_back(b);
+    }
+};
+
+struct blu_result {
+    blu_ctx* ctx = nullptr;
+    std::shared_ptr<HostTaxonomy> tax;
+    Cutoffs cut;
+    PinnedBuf b_rec, b_beans, b_accs, b_pool;
+    uint64_t n_rec = 0, n_slots = 0, pool_len = 0, n_rows = 0;
+    std::vector<std::string> hitless;  // NoConsensusFound (mod.rs:84-102)
+    const blu_record* rec() const { return (const blu_record*)b_rec.p; }
+    const blu_bean* beans() const { return (const blu_bean*)b_beans.p; }
+    const blu_acc* accs() const { return (const blu_acc*)b_accs.p; }
+    const char* pool() const { return (const char*)b_pool.p; }
+};
+
+namespace {
+
+ResultView make_view(const blu_result* r) {
+    ResultView v;
+    v.tax = r->tax.get();
+    v.cut = r->cut;
+    v.rec_ = r->rec();
+    v.beans_ = r->beans();
+    v.accs_ = r->accs();
+    v.pool_ = r->pool();
+    v.n_rec = r->n_rec;
+    v.hitless_ = &r->hitless;
+    return v;
+}
+
+int fail(blu_ctx* ctx, int code, const std::string& msg) {
+    if (ctx)
+        ctx->err = msg;
+    else
+        g_create_error = msg;
+    return code;
+}
+
+template <class F>
+int guarded(blu_ctx* ctx, F&& f) {
+    try {
+        f();
+        if (ctx) ctx->err.clear();
+        return BLU_OK;
+    } catch (const IoErr& e) {
+        return fail(ctx, BLU_ERR_IO, e.what());
+    } catch (const DataErr& e) {
+        return fail(ctx, BLU_ERR_DATA, e.what());
+    } catch (const CudaErr& e) {
+        return fail(ctx, BLU_ERR_CUDA, e.what());
+    } catch (const UnsupportedErr& e) {
+        return fail(ctx, BLU_ERR_UNSUPPORTED, e.what());
+    } catch (const std::invalid_argument& e) {
+        return fail(ctx, BLU_ERR_UNSUPPORTED, e.what());
+    } catch (const std::bad_alloc&) {
+        return fail(ctx, BLU_ERR_INTERNAL, "out of host memory");
+    } catch (const std::exception& e) {
+        return fail(ctx, BLU_ERR_INTERNAL, e.what());
+    }
+}
+
+const char* dev_err_text(uint32_t e) {
+    switch (e) {
+        case DE_BAD_FIELD_COUNT: return "row does not have 13 tab-separated fields";
+        case DE_BAD_NUMBER: return "malformed numeric field";
+        case DE_EMPTY_STRING: return "empty qseqid / saccver";
+        case DE_QUOTE_OR_CR: return "'\"' or '\\r' byte in the blast output (not supported)";
+        case DE_UNMAPPED_TAXID: return "subject taxid of a top bit-score hit has no lineage in the taxonomy file (reference: panic on `null` lineage)";
+        case DE_BAD_LINEAGE: return "Unexpected error on parse taxonomy (lineage of a top bit-score hit)";
+        case DE_EMPTY_ADJUSTED: return "No taxonomy found for result (single match below every identity cutoff)";
+        case DE_ROOT_DISAGREE: return "top hits disagree at the first lineage level (reference: index underflow panic)";
+        case DE_BITS_RANGE: return "bit score outside the i64 range";
+        case DE_NUM_UNSUPPORTED: return "number outside the exactly-parsed range (more than 19 significant digits or |exponent| > 22)";
+        case DE_TOPGROUP_TOO_BIG: return "top bit-score group larger than 1024 rows";
+        case DE_CARRY_TOO_BIG: return "a single row does not fit the 60 KB window";
+        default: return "internal device error";
+    }
+}
+
+void upload_taxonomy(blu_ctx* c) {
+    HostTaxonomy& T = *c->tax;
+    auto up = [&](auto& dbuf, const auto& vec) {
+        dbuf.ensure(std::max<size_t>(vec.size(), 1));
+        if (!vec.empty()) CK(cudaMemcpy(dbuf.p, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice));
+    };
+    up(c->d_lin_off, T.lin_off);
+    up(c->d_lvl, T.lvl_key);
+    up(c->d_bean, T.bean_key);
+    up(c->d_irank, T.ident_rank);
+    up(c->d_cut, T.cut);
+    up(c->d_rcls, T.rank_cls);
+    up(c->d_acls, T.allowed_cls);
+    up(c->d_linok, T.lin_ok);
+    up(c->d_slots, T.slots);
+    c->dT.lin_off = c->d_lin_off.p;
+    c->dT.lvl_key = c->d_lvl.p;
+    c->dT.bean_key = c->d_bean.p;
+    c->dT.ident_rank = c->d_irank.p;
+    c->dT.cut = c->d_cut.p;
+    c->dT.rank_cls = c->d_rcls.p;
+    c->dT.allowed_cls = c->d_acls.p;
+    c->dT.lin_ok = c->d_linok.p;
+    c->dT.slots = c->d_slots.p;
+    c->dT.hash_mask = T.hash_mask;
+    c->dT.n_lin = (uint32_t)T.n_lin();
+}
+
+struct Caps {
+    size_t rec, slots, defer, pool;
+};
+
+Caps initial_caps(uint64_t n_bytes) {
+    Caps c;
+    c.rec = n_bytes / 160 + 4096;
+    c.slots = n_bytes / 96 + 8192;
+    c.defer = c.rec;
+    c.pool = n_bytes / 24 + 65536;
+    return c;
+}
+
+void ensure_out(blu_ctx* c, const Caps& k) {
+    c->d_rec.ensure(k.rec);
+    c->d_beans.ensure(k.slots);
+    c->d_accs.ensure(k.slots);
+    c->d_defer.ensure(k.defer);
+    c->d_pool.ensure(k.pool);
+}
+
+void check_device_error(blu_ctx*, const Counters& h, uint64_t stream_base) {
+    if (!h.err_code) return;
+    std::string m = std::string(dev_err_text(h.err_code)) + " (near byte " + std::to_string(stream_base + h.err_off) + " of the blast output)";
+    if (h.err_code >= DE_INTERNAL) throw std::runtime_error(m);
+    if (h.err_code >= DE_NUM_UNSUPPORTED) throw UnsupportedErr(m);
+    throw DataErr(m);
+}
+
+// Runs the kernels on one resident chunk.  rec_begin = number of records before this chunk.
+void launch_chunk(blu_ctx* c, const uint8_t* dtext, uint64_t begin, uint64_t end, bool final_chunk, const Caps& k, cudaStream_t s,
+                  uint32_t rec_begin_hint, bool time_it) {
+    RunParams p{};
+    p.text = dtext;
+    p.begin = begin;
+    p.end = end;
+    p.final_chunk = final_chunk ? 1 : 0;
+    p.strategy = c->opts.strategy;
+    p.T = c->dT;
+    p.records = c->d_rec.p;
+    p.rec_cap = (uint32_t)std::min<size_t>(k.rec, 0xFFFFFFFFu);
+    p.beans = c->d_beans.p;
+    p.accs = c->d_accs.p;
+    p.slot_cap = (uint32_t)std::min<size_t>(k.slots, 0xFFFFFFFFu);
+    p.defer = c->d_defer.p;
+    p.defer_cap = (uint32_t)std::min<size_t>(k.defer, 0xFFFFFFFFu);
+    p.ctr = c->d_ctr;
+    (void)rec_begin_hint;
+    if (time_it) CK(cudaEventRecord(c->ev[0], s));
+    CK(launch_tile_kernel(p, tile_kernel_grid(c->device), s));
+    if (time_it) CK(cudaEventRecord(c->ev[1], s));
+    CK(launch_longrun_kernel(p, c->sms, s));
+    if (time_it) CK(cudaEventRecord(c->ev[2], s));
+    c->tm.n_kernel_launches += 2;
+}
+
+void reset_counters_async(blu_ctx* c, cudaStream_t s, bool whole) {
+    if (whole) {
+        CK(cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), s));
+    } else {
+        // per chunk: n_defer, work_ticket back to zero; keep the output counters
+        CK(cudaMemsetAsync(&c->d_ctr->n_defer, 0, sizeof(unsigned), s));
+        CK(cudaMemsetAsync(&c->d_ctr->work_ticket, 0, sizeof(unsigned), s));
+    }
+    CK(cudaMemsetAsync(&c->d_ctr->tail_start, 0xFF, sizeof(unsigned long long), s));
+}
+
+void finish_result(blu_ctx* c, const Counters& h, cudaStream_t s, blu_result* r) {
+    r->n_rec = h.n_rec;
+    r->n_slots = h.n_slots;
+    r->pool_len = h.pool_used;
+    r->n_rows = h.n_rows;
+    r->b_rec = c->acquire(std::max<size_t>(r->n_rec * sizeof(blu_record), 64));
+    r->b_beans = c->acquire(std::max<size_t>(r->n_slots * sizeof(blu_bean), 64));
+    r->b_accs = c->acquire(std::max<size_t>(r->n_slots * sizeof(blu_acc), 64));
+    r->b_pool = c->acquire(std::max<size_t>(r->pool_len, 64));
+    if (r->n_rec) CK(cudaMemcpyAsync(r->b_rec.p, c->d_rec.p, r->n_rec * sizeof(blu_record), cudaMemcpyDeviceToHost, s));
+    if (r->n_slots) {
+        CK(cudaMemcpyAsync(r->b_beans.p, c->d_beans.p, r->n_slots * sizeof(blu_bean), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(r->b_accs.p, c->d_accs.p, r->n_slots * sizeof(blu_acc), cudaMemcpyDeviceToHost, s));
+    }
+    if (r->pool_len) CK(cudaMemcpyAsync(r->b_pool.p, c->d_pool.p, r->pool_len, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    c->tm.d2h_bytes += r->n_rec * sizeof(blu_record) + r->n_slots * (sizeof(blu_bean) + sizeof(blu_acc)) + r->pool_len + sizeof(Counters);
+    c->tm.result_bytes = r->n_rec * sizeof(blu_record) + r->n_slots * (sizeof(blu_bean) + sizeof(blu_acc));
+    c->tm.n_queries = r->n_rec;
+    c->tm.n_rows = r->n_rows;
+}
+
+float ev_ms(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+}
+
+// Post-pass on all records of the run: string gather for [rec_begin, rec_end) + (at the end) duplicate check.
+void launch_gather(blu_ctx* c, const uint8_t* dtext, uint32_t rec_begin, uint32_t rec_end, const Caps& k, cudaStream_t s) {
+    GatherParams g{};
+    g.text = dtext;
+    g.records = c->d_rec.p;
+    g.accs = c->d_accs.p;
+    g.rec_begin = rec_begin;
+    g.rec_end = rec_end;
+    g.pool = c->d_pool.p;
+    g.pool_cap = k.pool;
+    g.ctr = c->d_ctr;
+    CK(launch_gather_kernel(g, s));
+    if (rec_end > rec_begin) c->tm.n_kernel_launches += 1;
+}
+
+void launch_dup(blu_ctx* c, uint32_t n_rec, cudaStream_t s) {
+    if (!n_rec) return;
+    size_t cap = 1024;
+    while (cap < 2ull * n_rec) cap <<= 1;
+    c->d_dup.ensure(cap);
+    CK(cudaMemsetAsync(c->d_dup.p, 0, cap * sizeof(unsigned long long), s));
+    DupParams d{};
+    d.records = c->d_rec.p;
+    d.n_rec = n_rec;
+    d.pool = c->d_pool.p;
+    d.table = c->d_dup.p;
+    d.mask = (uint32_t)(cap - 1);
+    d.ctr = c->d_ctr;
+    CK(launch_dup_kernel(d, s));
+    c->tm.n_kernel_launches += 1;
+}
+
+void read_counters(blu_ctx* c, cudaStream_t s) {
+    CK(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+}
+
+bool grow_caps(const Counters& h, Caps& k, uint64_t defer_seen) {
+    bool grew = false;
+    if (h.n_rec > k.rec) k.rec = (size_t)h.n_rec + h.n_rec / 8 + 1024, grew = true;
+    if (h.n_slots > k.slots) k.slots = (size_t)h.n_slots + h.n_slots / 8 + 1024, grew = true;
+    if (defer_seen > k.defer) k.defer = (size_t)defer_seen + defer_seen / 8 + 1024, grew = true;
+    if (h.pool_used > k.pool) k.pool = (size_t)h.pool_used + h.pool_used / 8 + 4096, grew = true;
+    if (!grew) {  // overflow flagged but counts look fine (reservation raced past the cap): grow everything
+        k.rec *= 2, k.slots *= 2, k.defer *= 2, k.pool *= 2;
+    }
+    return true;
+}
+
+void require_ready(blu_ctx* c) {
+    if (!c->tax) throw std::invalid_argument("no taxonomy loaded (call blu_taxonomy_load_json first)");
+}
+
+// --- text resident on the device ------------------------------------------------------------------------------
+void run_device(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStream_t s, blu_result* r) {
+    require_ready(c);
+    if (n == 0) throw DataErr("empty blast output (the reference's CsvReader fails on an empty file)");
+    if (((uintptr_t)dtext & 15) != 0) throw std::invalid_argument("device text must be 16-byte aligned");
+    c->tm = blu_timings{};
+    Caps k = initial_caps(n);
+    for (int attempt = 0; attempt < 6; attempt++) {
+        ensure_out(c, k);
+        reset_counters_async(c, s, true);
+        launch_chunk(c, dtext, 0, n, true, k, s, 0, true);
+        // gather needs n_rec: read it from the device counters inside the kernel launch geometry -> one sync
+        read_counters(c, s);
+        Counters h = *c->h_ctr;
+        if (h.cap_overflow || h.n_rec > k.rec || h.n_slots > k.slots || h.n_defer > k.defer) {
+            grow_caps(h, k, h.n_defer);
+            continue;
+        }
+        check_device_error(c, h, 0);
+        CK(cudaEventRecord(c->ev[3], s));
+        launch_gather(c, dtext, 0, h.n_rec, k, s);
+        launch_dup(c, h.n_rec, s);
+        CK(cudaEventRecord(c->ev[4], s));
+        read_counters(c, s);
+        h = *c->h_ctr;
+        if (h.cap_overflow || h.pool_used > k.pool) {
+            grow_caps(h, k, h.n_defer);
+            continue;
+        }
+        check_device_error(c, h, 0);
+        if (h.dup_found)
+            throw UnsupportedErr("a query id occurs in two non-adjacent groups of rows; non-contiguous hit tables are not supported yet");
+        if (h.n_rec == 0) throw DataErr("the blast output holds no rows");
+        c->tm.ms_tile_kernel = ev_ms(c->ev[0], c->ev[1]);
+        c->tm.ms_longrun_kernel = ev_ms(c->ev[1], c->ev[2]);
+        c->tm.ms_gather_kernel = ev_ms(c->ev[3], c->ev[4]);
+        c->tm.ms_total_device = c->tm.ms_tile_kernel + c->tm.ms_longrun_kernel + c->tm.ms_gather_kernel;
+        c->tm.text_bytes = n;
+        c->tm.taxonomy_bytes = c->tax->device_bytes();
+        c->tm.n_deferred_runs = h.n_defer;
+        finish_result(c, h, s, r);
+        return;
+    }
+    throw std::runtime_error("output capacity did not converge");
+}
+
+// --- text on the host: chunked, double-buffered H2D overlapped with the kernels --------------------------------
+void run_host(blu_ctx* c, const char* text, uint64_t n, blu_result* r) {
+    require_ready(c);
+    if (n == 0) throw DataErr("empty blast output (the reference's CsvReader fails on an empty file)");
+    c->tm = blu_timings{};
+    const uint64_t chunk = c->opts.chunk_bytes ? ((c->opts.chunk_bytes + 127) & ~127ull) : (256ull << 20);
+    const uint64_t carry = c->carry_bytes;
+    const uint64_t n_chunks = (n + chunk - 1) / chunk;
+    const bool single = n_chunks == 1;
+    const uint64_t buf_bytes = (single ? 0 : carry) + std::min(chunk, n) + 256;
+    const uint64_t text_off = single ? 0 : carry;  // where H2D data lands inside a buffer
+    c->d_text[0].ensure(buf_bytes);
+    if (!single) c->d_text[1].ensure(buf_bytes);
+    Caps k = initial_caps(n);
+    cudaStream_t s = c->stream, cs = c->copy_stream;
+    auto t0 = std::chrono::steady_clock::now();
+    for (int attempt = 0; attempt < 6; attempt++) {
+        ensure_out(c, k);
+        reset_counters_async(c, s, true);
+        bool retry = false;
+        uint64_t tail_len = 0;           // bytes carried from the previous chunk
+        uint32_t rec_done = 0;           // records already gathered
+        uint64_t defer_total = 0;
+        double ms_tile = 0, ms_long = 0, ms_gather = 0;
+        auto issue_h2d = [&](uint64_t ci) {
+            const uint64_t off = ci * chunk, len = std::min(chunk, n - off);
+            CK(cudaMemcpyAsync(c->d_text[ci & 1].p + text_off, text + off, len, cudaMemcpyHostToDevice, cs));
+            CK(cudaEventRecord(c->ev_h2d[ci & 1], cs));
+            c->tm.h2d_bytes += len;
+        };
+        issue_h2d(0);
+        for (uint64_t ci = 0; ci < n_chunks && !retry; ci++) {
+            const uint64_t off = ci * chunk, len = std::min(chunk, n - off);
+            const bool final_chunk = ci + 1 == n_chunks;
+            uint8_t* buf = c->d_text[ci & 1].p;
+            CK(cudaStreamWaitEvent(s, c->ev_h2d[ci & 1], 0));
+            if (tail_len) {
+                // the unfinished last query of the previous chunk goes in front of this chunk's text
+                const uint8_t* prev = c->d_text[(ci - 1) & 1].p;
+                const uint64_t prev_end = text_off + std::min(chunk, n - (ci - 1) * chunk);
+                CK(cudaMemcpyAsync(buf + text_off - tail_len, prev + prev_end - tail_len, tail_len, cudaMemcpyDeviceToDevice, s));
+            }
+            CK(cudaEventRecord(c->ev_free[(ci + 1) & 1], s));  // previous buffer no longer read after this point
+            if (!final_chunk) {
+                CK(cudaStreamWaitEvent(cs, c->ev_free[(ci + 1) & 1], 0));
+                issue_h2d(ci + 1);
+            }
+            if (ci) reset_counters_async(c, s, false);
+            const uint64_t begin = text_off - tail_len, end = text_off + len;
+            launch_chunk(c, buf, begin, end, final_chunk, k, s, rec_done, true);
+            read_counters(c, s);
+            Counters h = *c->h_ctr;
+            ms_tile += ev_ms(c->ev[0], c->ev[1]);
+            ms_long += ev_ms(c->ev[1], c->ev[2]);
+            defer_total = std::max<uint64_t>(defer_total, h.n_defer);
+            if (h.cap_overflow || h.n_rec > k.rec || h.n_slots > k.slots || h.n_defer > k.defer) {
+                grow_caps(h, k, h.n_defer);
+                retry = true;
+                break;
+            }
+            check_device_error(c, h, off - text_off);  // err_off is in buffer coordinates
+            CK(cudaEventRecord(c->ev[3], s));
+            launch_gather(c, buf, rec_done, h.n_rec, k, s);
+            CK(cudaEventRecord(c->ev[4], s));
+            rec_done = h.n_rec;
+            if (!final_chunk) {
+                if (h.tail_start == ~0ull)
+                    tail_len = 0;
+                else {
+                    tail_len = end - h.tail_start;
+                    if (tail_len > carry) throw UnsupportedErr("a single query spans more than the 64 MiB carry buffer between streamed chunks");
+                }
+            }
+            CK(cudaStreamSynchronize(s));  // gather must finish before this buffer is overwritten two chunks later
+            ms_gather += ev_ms(c->ev[3], c->ev[4]);
+            c->tm.n_deferred_runs += h.n_defer;
+        }
+        if (retry) {
+            CK(cudaStreamSynchronize(cs));
+            CK(cudaStreamSynchronize(s));
+            c->tm = blu_timings{};
+            continue;
+        }
+        launch_dup(c, rec_done, s);
+        read_counters(c, s);
+        Counters h = *c->h_ctr;
+        if (h.cap_overflow || h.pool_used > k.pool) {
+            grow_caps(h, k, defer_total);
+            c->tm = blu_timings{};
+            continue;
+        }
+        check_device_error(c, h, 0);
+        if (h.dup_found)
+            throw UnsupportedErr("a query id occurs in two non-adjacent groups of rows; non-contiguous hit tables are not supported yet");
+        if (h.n_rec == 0) throw DataErr("the blast output holds no rows");
+        c->tm.ms_tile_kernel = ms_tile;
+        c->tm.ms_longrun_kernel = ms_long;
+        c->tm.ms_gather_kernel = ms_gather;
+        c->tm.text_bytes = n;
+        c->tm.taxonomy_bytes = c->tax->device_bytes();
+        finish_result(c, h, s, r);
+        c->tm.ms_total_device = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        return;
+    }
+    throw std::runtime_error("output capacity did not converge");
+}
+
+}  // namespace
+
+// =================================================================================================================
+// C ABI
+// =================================================================================================================
+extern "C" {
+
+int blu_abi_version(void) { return BLU_ABI_VERSION; }
+
+const char* blu_last_error(const blu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int blu_ctx_create(const blu_opts* opts, blu_ctx** out) {
+    if (!opts || !out) return fail(nullptr, BLU_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (opts->taxon < 0 || opts->taxon > 3) return fail(nullptr, BLU_ERR_ARG, "bad taxon");
+    if (opts->strategy < 0 || opts->strategy > 1) return fail(nullptr, BLU_ERR_ARG, "bad strategy");
+    if (opts->taxon == BLU_TAXON_CUSTOM && !opts->has_custom)
+        return fail(nullptr, BLU_ERR_DATA, "Custom taxon values are required when the custom taxon option is selected.");
+    auto c = std::make_unique<blu_ctx>();
+    c->opts = *opts;
+    c->cut.taxon = opts->taxon;
+    c->cut.has_custom = opts->has_custom != 0;
+    for (int i = 0; i < 8; i++) c->cut.custom[i] = opts->custom[i];
+    c->device = opts->device;
+    int rc = guarded(nullptr, [&] {
+        make_backbone(c->cut);  // validates the custom values
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0) throw CudaErr(std::string("no CUDA device available: ") + cudaGetErrorString(e));
+        if (c->device < 0 || c->device >= n) throw CudaErr("device ordinal out of range");
+        CK(cudaSetDevice(c->device));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, c->device));
+        if (prop.major < 10) throw CudaErr(std::string("device '") + prop.name + "' is not sm_100-class; this library only carries sm_100a code");
+        c->sms = prop.multiProcessorCount;
+        CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (auto& e2 : c->ev) CK(cudaEventCreate(&e2));
+        for (auto& e2 : c->ev_h2d) CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+        for (auto& e2 : c->ev_free) CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+        CK(cudaMalloc((void**)&c->d_ctr, sizeof(Counters)));
+        CK(cudaHostAlloc((void**)&c->h_ctr, sizeof(Counters), cudaHostAllocDefault));
+        CK(kernels_set_attributes());
+    });
+    if (rc != BLU_OK) {
+        std::string msg = g_create_error;
+        blu_ctx_destroy(c.release());
+        g_create_error = msg;
+        return rc;
+    }
+    *out = c.release();
+    return BLU_OK;
+}
+
+void blu_ctx_destroy(blu_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    c->d_lin_off.release(), c->d_lvl.release(), c->d_bean.release(), c->d_irank.release(), c->d_cut.release();
+    c->d_rcls.release(), c->d_acls.release(), c->d_linok.release(), c->d_slots.release();
+    c->d_text[0].release(), c->d_text[1].release(), c->d_rec.release(), c->d_beans.release(), c->d_accs.release();
+    c->d_defer.release(), c->d_pool.release(), c->d_dup.release();
+    if (c->d_ctr) cudaFree(c->d_ctr);
+    if (c->h_ctr) cudaFreeHost(c->h_ctr);
+    for (auto& b : c->pinned_free) cudaFreeHost(b.p);
+    for (auto& e : c->ev)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : c->ev_h2d)
+        if (e) cudaEventDestroy(e);
+    for (auto& e : c->ev_free)
+        if (e) cudaEventDestroy(e);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    delete c;
+}
+
+int blu_custom_cutoffs_from_file(const char* path, blu_opts* opts, char* err, size_t errlen) {
+    if (!path || !opts) return BLU_ERR_ARG;
+    try {
+        Cutoffs c;
+        read_custom_cutoffs(path, c);
+        opts->has_custom = 1;
+        for (int i = 0; i < 8; i++) opts->custom[i] = c.custom[i];
+        return BLU_OK;
+    } catch (const std::exception& e) {
+        if (err && errlen) snprintf(err, errlen, "%s", e.what());
+        return BLU_ERR_DATA;  // the reference panics on every failure of CustomTaxon::from_file
+    }
+}
+
+int blu_taxonomy_load_arrays(blu_ctx* c, const int64_t* taxids, const uint64_t* off, const char* blob, uint64_t n) {
+    if (!c || (n && (!taxids || !off || !blob))) return fail(c, BLU_ERR_ARG, "null argument");
+    return guarded(c, [&] {
+        CK(cudaSetDevice(c->device));
+        auto T = std::make_shared<HostTaxonomy>();
+        static const uint64_t zero = 0;
+        build_taxonomy(taxids, n ? off : &zero, blob, n, c->cut, *T);
+        c->tax = T;
+        upload_taxonomy(c);
+    });
+}
+
+int blu_taxonomy_load_json(blu_ctx* c, const char* path) {
+    if (!c || !path) return fail(c, BLU_ERR_ARG, "null argument");
+    std::vector<int64_t> ids;
+    std::vector<uint64_t> off;
+    std::string blob;
+    int rc = guarded(c, [&] { read_taxonomy_json(path, c->opts.use_taxid != 0, ids, off, blob); });
+    if (rc != BLU_OK) return rc;
+    return blu_taxonomy_load_arrays(c, ids.data(), off.data(), blob.data(), ids.size());
+}
+
+int blu_consensus_run_device(blu_ctx* c, const void* dtext, uint64_t n, void* stream, blu_result** out) {
+    if (!c || !out || (!dtext && n)) return fail(c, BLU_ERR_ARG, "null argument");
+    *out = nullptr;
+    auto r = std::make_unique<blu_result>();
+    r->ctx = c;
+    int rc = guarded(c, [&] {
+        CK(cudaSetDevice(c->device));
+        r->tax = c->tax;
+        r->cut = c->cut;
+        run_device(c, (const uint8_t*)dtext, n, stream ? (cudaStream_t)stream : c->stream, r.get());
+    });
+    if (rc != BLU_OK) {
+        blu_result_free(r.release());
+        return rc;
+    }
+    *out = r.release();
+    return BLU_OK;
+}
+
+int blu_consensus_run_host(blu_ctx* c, const char* text, uint64_t n, blu_result** out) {
+    if (!c || !out || (!text && n)) return fail(c, BLU_ERR_ARG, "null argument");
+    *out = nullptr;
+    auto r = std::make_unique<blu_result>();
+    r->ctx = c;
+    int rc = guarded(c, [&] {
+        CK(cudaSetDevice(c->device));
+        r->tax = c->tax;
+        r->cut = c->cut;
+        run_host(c, text, n, r.get());
+    });
+    if (rc != BLU_OK) {
+        blu_result_free(r.release());
+        return rc;
+    }
+    *out = r.release();
+    return BLU_OK;
+}
+
+int blu_consensus_run_file(blu_ctx* c, const char* path, blu_result** out) {
+    if (!c || !path || !out) return fail(c, BLU_ERR_ARG, "null argument");
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return fail(c, BLU_ERR_IO, "Unexpected error occurred on load table.");  // mod.rs:357-364
+    f.seekg(0, std::ios::end);
+    std::streamoff n = f.tellg();
+    f.seekg(0);
+    void* pinned = nullptr;
+    if (n > 0) {
+        cudaSetDevice(c->device);
+        if (cudaHostAlloc(&pinned, (size_t)n, cudaHostAllocDefault) != cudaSuccess) return fail(c, BLU_ERR_CUDA, "cudaHostAlloc failed");
+        if (!f.read((char*)pinned, n)) {
+            cudaFreeHost(pinned);
+            return fail(c, BLU_ERR_IO, "Unexpected error occurred on load table.");
+        }
+    }
+    int rc = blu_consensus_run_host(c, (const char*)pinned, (uint64_t)n, out);
+    if (pinned) cudaFreeHost(pinned);
+    return rc;
+}
+
+int blu_result_add_headers(blu_result* r, const char* headers_nl, uint64_t len) {
+    if (!r) return BLU_ERR_ARG;
+    std::unordered_set<std::string_view> have;
+    have.reserve(r->n_rec * 2);
+    for (uint64_t i = 0; i < r->n_rec; i++) have.insert(std::string_view(r->pool() + r->rec()[i].query_off, r->rec()[i].query_len));
+    const char* p = headers_nl;
+    const char* e = headers_nl + len;
+    while (p < e) {
+        const char* nl = (const char*)memchr(p, '\n', e - p);
+        const char* le = nl ? nl : e;
+        std::string_view h(p, le - p);
+        if (!have.count(h)) r->hitless.emplace_back(h);  // duplicates in `headers` stay duplicated, as in the reference
+        p = le + 1;
+    }
+    return BLU_OK;
+}
+
+uint64_t blu_result_num_queries(const blu_result* r) { return r ? r->n_rec + r->hitless.size() : 0; }
+uint64_t blu_result_num_rows(const blu_result* r) { return r ? r->n_rows : 0; }
+const blu_record* blu_result_records(const blu_result* r) { return r ? r->rec() : nullptr; }
+const blu_bean* blu_result_beans(const blu_result* r) { return r ? r->beans() : nullptr; }
+const blu_acc* blu_result_accessions(const blu_result* r) { return r ? r->accs() : nullptr; }
+const char* blu_result_pool(const blu_result* r, uint64_t* len) {
+    if (len) *len = r ? r->pool_len : 0;
+    return r ? r->pool() : nullptr;
+}
+
+uint64_t blu_result_checksum(const blu_result* r) {
+    if (!r) return 0;
+    ResultView v = make_view(r);
+    return view_checksum(&v);
+}
+
+int blu_result_to_jsonl(const blu_result* r, char** out, uint64_t* len) {
+    if (!r || !out || !len) return BLU_ERR_ARG;
+    try {
+        ResultView v = make_view(r);
+        std::string s = view_to_jsonl(&v);
+        char* buf = (char*)malloc(s.size() + 1);
+        if (!buf) return BLU_ERR_INTERNAL;
+        memcpy(buf, s.data(), s.size());
+        buf[s.size()] = 0;
+        *out = buf;
+        *len = s.size();
+        return BLU_OK;
+    } catch (const std::exception&) {
+        return BLU_ERR_INTERNAL;
+    }
+}
+
+int blu_result_write(const blu_result* r, const char* path, int format, const char* run_id_in) {
+    if (!r || format < 0 || format > 2) return BLU_ERR_ARG;
+    try {
+        ResultView v = make_view(r);
+        return view_write(&v, path, format, run_id_in);
+    } catch (const std::exception&) {
+        return BLU_ERR_INTERNAL;
+    }
+}
+
+void blu_result_free(blu_result* r) {
+    if (!r) return;
+    if (r->ctx) {
+        r->ctx->release(r->b_rec);
+        r->ctx->release(r->b_beans);
+        r->ctx->release(r->b_accs);
+        r->ctx->release(r->b_pool);
+    }
+    delete r;
+}
+
+void blu_free(void* p) { free(p); }
+
+int blu_ctx_last_timings(const blu_ctx* c, blu_timings* out) {
+    if (!c || !out) return BLU_ERR_ARG;
+    *out = c->tm;
+    return BLU_OK;
+}
+
+int blu_ctx_measure_h2d(blu_ctx* c, uint64_t bytes, double* gbps) {
+    if (!c || !gbps || !bytes) return BLU_ERR_ARG;
+    return guarded(c, [&] {
+        CK(cudaSetDevice(c->device));
+        void* h = nullptr;
+        void* d = nullptr;
+        CK(cudaHostAlloc(&h, bytes, cudaHostAllocDefault));
+        if (cudaMalloc(&d, bytes) != cudaSuccess) {
+            cudaFreeHost(h);
+            throw CudaErr("cudaMalloc failed");
+        }
+        memset(h, 1, bytes);
+        double best = 0;
+        for (int i = 0; i < 5; i++) {
+            cudaEventRecord(c->ev[0], c->stream);
+            cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream);
+            cudaEventRecord(c->ev[1], c->stream);
+            cudaStreamSynchronize(c->stream);
+            double ms = ev_ms(c->ev[0], c->ev[1]);
+            if (ms > 0) best = std::max(best, bytes / ms / 1e6);
+        }
+        cudaFree(d);
+        cudaFreeHost(h);
+        *gbps = best;
+    });
+}
+
+void* blu_host_alloc(uint64_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    return p;
+}
+void blu_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

@@ -1,0 +1,581 @@
+// blu_core.cuh -- per-row parsing and per-query consensus logic shared by the CUDA kernels.
+//
+// Everything here is `__host__ __device__` so that tests/csrc/sim_harness.cpp can compile the *same* code
+// with g++ and check it against the oracle without a GPU.  The product library only ever calls these from
+// device code (blu_kernels.cu); there is no CPU execution path in libblu_consensus.so.
+//
+// Reference semantics restated (paths relative to /root/reference):
+//   row fields / truncation ......... core/src/use_cases/build_consensus_identities/mod.rs:147-209,226-244
+//   top bit-score group ............. find_single_query_consensus.rs:28-64
+//   single match .................... find_single_query_consensus.rs:74-150
+//   multi match (sort, level walk) .. find_multi_taxa_consensus.rs:39-214
+//   rank selection / filtering ...... build_blast_consensus_identity.rs:9-105, linnaean_ranks.rs:174-212
+//   bean folding .................... consensus_result.rs:65-88
+#pragma once
+#include <stdint.h>
+
+#include "../../include/blu_consensus.h"
+
+#if defined(__CUDACC__)
+#define BLU_HD __host__ __device__ __forceinline__
+#define BLU_HD_NOINLINE __host__ __device__ __noinline__
+#else
+#define BLU_HD inline
+#define BLU_HD_NOINLINE inline
+#endif
+
+namespace blu {
+
+// ---- device-side error codes (first error wins; host maps them to BLU_ERR_*) ------------------------------
+enum DevErr : uint32_t {
+    DE_NONE = 0,
+    DE_BAD_FIELD_COUNT = 1,   // row does not have 13 fields            -> DATA
+    DE_BAD_NUMBER = 2,        // numeric grammar violated               -> DATA
+    DE_EMPTY_STRING = 3,      // empty qseqid / saccver                 -> DATA
+    DE_QUOTE_OR_CR = 4,       // '"' or '\r' byte                       -> DATA
+    DE_UNMAPPED_TAXID = 5,    // top-group row whose taxid has no lineage -> DATA (fsqc.rs:59)
+    DE_BAD_LINEAGE = 6,       // top-group lineage failed parse_taxonomy  -> DATA
+    DE_EMPTY_ADJUSTED = 7,    // single match, no rank passes the cutoff  -> DATA (fsqc.rs:113-119)
+    DE_ROOT_DISAGREE = 8,     // level 0 disagreement (index-1 underflow) -> DATA (fmtc.rs:181)
+    DE_BITS_RANGE = 9,        // bit score outside i64                  -> DATA
+    DE_NUM_UNSUPPORTED = 32,  // number outside the exact fast path     -> UNSUPPORTED
+    DE_TOPGROUP_TOO_BIG = 33, // top group larger than the block path handles -> UNSUPPORTED
+    DE_CARRY_TOO_BIG = 34,    // a single query larger than the carry buffer  -> UNSUPPORTED
+    DE_INTERNAL = 64
+};
+
+// ---- lineage tables in HBM (built by blu_taxonomy.cpp) ------------------------------------------------------
+struct HashSlot {
+    int64_t key;
+    uint32_t val;   // lineage index
+    uint32_t used;  // 0 = empty
+};
+
+struct LinTables {
+    const uint32_t* lin_off;     // [n_lin+1] CSR offsets into the per-position arrays
+    const uint32_t* lvl_key;     // id of rank.to_string()+identifier        (fmtc.rs:153-157)
+    const uint32_t* bean_key;    // id of "{rank}__{identifier}"             (consensus_result.rs:70-73)
+    const uint32_t* ident_rank;  // bytewise order rank of the identifier    (bbci.rs:50-60)
+    const double* cut;           // interpolated cutoff                      (linnaean_ranks.rs:220-383)
+    const uint16_t* rank_cls;    // equality class of the position's LinnaeanRank
+    const uint16_t* allowed_cls; // equality class of the rank get_rank_adjusted_by_identity would return here
+    const uint8_t* lin_ok;       // [n_lin] 1 = lineage parsed; 0 = parse_taxonomy would fail
+    const HashSlot* slots;
+    uint32_t hash_mask;
+    uint32_t n_lin;
+};
+
+BLU_HD uint64_t mix64(uint64_t x) {
+    x ^= x >> 33;
+    x *= 0xff51afd7ed558ccdULL;
+    x ^= x >> 33;
+    x *= 0xc4ceb9fe1a85ec53ULL;
+    x ^= x >> 33;
+    return x;
+}
+
+// taxid -> lineage index (left join on subject_taxid == taxid, mod.rs:72-76).  0xFFFFFFFF = no match.
+BLU_HD uint32_t probe_taxid(const LinTables& T, int64_t taxid) {
+    uint32_t h = (uint32_t)mix64((uint64_t)taxid) & T.hash_mask;
+    for (uint32_t i = 0; i <= T.hash_mask; i++) {
+        HashSlot s = T.slots[h];
+        if (!s.used) return 0xFFFFFFFFu;
+        if (s.key == taxid) return s.val;
+        h = (h + 1) & T.hash_mask;
+    }
+    return 0xFFFFFFFFu;
+}
+
+// ---- numbers --------------------------------------------------------------------------------------------------
+// int := -?[0-9]{1,18}
+BLU_HD bool parse_i64(const uint8_t* p, int len, int64_t& v) {
+    int i = 0;
+    bool neg = false;
+    if (len > 0 && p[0] == '-') {
+        neg = true;
+        i = 1;
+    }
+    int nd = len - i;
+    if (nd < 1 || nd > 18) return false;
+    int64_t x = 0;
+    for (; i < len; i++) {
+        uint32_t d = (uint32_t)p[i] - '0';
+        if (d > 9) return false;
+        x = x * 10 + d;
+    }
+    v = neg ? -x : x;
+    return true;
+}
+
+// float := -?([0-9]+(\.[0-9]*)?|\.[0-9]+)([eE][+-]?[0-9]+)?
+// Returns DE_NONE, DE_BAD_NUMBER (grammar) or DE_NUM_UNSUPPORTED (valid, but not exactly computable here:
+// more than 19 significant digits, mantissa >= 2^53 or |decimal exponent| > 22).
+// Exact path (Clinger): m and 10^|e| are both exact doubles, so one IEEE multiply/divide is correctly rounded.
+#if defined(__CUDA_ARCH__)
+__device__ __constant__ double kPow10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                                             1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+#else
+static const double kPow10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                                  1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+#endif
+
+BLU_HD uint32_t parse_f64(const uint8_t* p, int len, double& v) {
+    int i = 0;
+    bool neg = false;
+    if (i < len && p[i] == '-') {
+        neg = true;
+        i++;
+    }
+    uint64_t mant = 0;
+    int sig = 0, nint = 0, nfrac = 0;
+    bool unsupported = false;
+    while (i < len) {
+        uint32_t d = (uint32_t)p[i] - '0';
+        if (d > 9) break;
+        if (sig > 0 || d != 0) {
+            if (sig < 19) mant = mant * 10 + d;
+            sig++;
+        }
+        nint++;
+        i++;
+    }
+    if (i < len && p[i] == '.') {
+        i++;
+        while (i < len) {
+            uint32_t d = (uint32_t)p[i] - '0';
+            if (d > 9) break;
+            if (sig > 0 || d != 0) {
+                if (sig < 19) mant = mant * 10 + d;
+                sig++;
+            }
+            nfrac++;
+            i++;
+        }
+        if (nint == 0 && nfrac == 0) return DE_BAD_NUMBER;
+    } else if (nint == 0)
+        return DE_BAD_NUMBER;
+    int ex = 0;
+    if (i < len && (p[i] == 'e' || p[i] == 'E')) {
+        i++;
+        bool eneg = false;
+        if (i < len && (p[i] == '+' || p[i] == '-')) {
+            eneg = p[i] == '-';
+            i++;
+        }
+        int nd = 0;
+        while (i < len) {
+            uint32_t d = (uint32_t)p[i] - '0';
+            if (d > 9) break;
+            if (ex < 100000) ex = ex * 10 + (int)d;
+            nd++;
+            i++;
+        }
+        if (nd == 0) return DE_BAD_NUMBER;
+        if (eneg) ex = -ex;
+    }
+    if (i != len) return DE_BAD_NUMBER;
+    if (sig > 19) unsupported = true;
+    int e10 = ex - nfrac;
+    double r;
+    if (mant == 0 && !unsupported) {
+        r = 0.0;
+    } else {
+        if (unsupported || mant >= (1ULL << 53) || e10 > 22 || e10 < -22) return DE_NUM_UNSUPPORTED;
+        r = (double)mant;
+        if (e10 >= 0)
+            r = r * kPow10[e10];
+        else
+            r = r / kPow10[-e10];
+    }
+    v = neg ? -r : r;
+    return DE_NONE;
+}
+
+// Grammar-only DFA for the numeric columns nobody reads (7 of 13 columns are parsed and dropped
+// by the reference, but a malformed one still aborts it).  class: 0 digit, 1 '.', 2 e/E, 3 '+', 4 '-', 5 other.
+BLU_HD int num_class(uint32_t c) {
+    if (c - '0' <= 9u) return 0;
+    if (c == '.') return 1;
+    if ((c | 0x20) == 'e') return 2;
+    if (c == '+') return 3;
+    if (c == '-') return 4;
+    return 5;
+}
+// float DFA states: 0 start, 1 sign, 2 int digits*, 3 "d." *, 4 frac digits*, 5 "." (needs digit), 6 e, 7 e sign,
+// 8 exp digits*, 9 error.  (* accepting)
+BLU_HD int float_dfa_next(int s, int cls) {
+    switch (s) {
+        case 0: return cls == 0 ? 2 : cls == 4 ? 1 : cls == 1 ? 5 : 9;
+        case 1: return cls == 0 ? 2 : cls == 1 ? 5 : 9;
+        case 2: return cls == 0 ? 2 : cls == 1 ? 3 : cls == 2 ? 6 : 9;
+        case 3: return cls == 0 ? 4 : cls == 2 ? 6 : 9;
+        case 4: return cls == 0 ? 4 : cls == 2 ? 6 : 9;
+        case 5: return cls == 0 ? 4 : 9;
+        case 6: return cls == 0 ? 8 : (cls == 3 || cls == 4) ? 7 : 9;
+        case 7: return cls == 0 ? 8 : 9;
+        case 8: return cls == 0 ? 8 : 9;
+        default: return 9;
+    }
+}
+BLU_HD bool float_dfa_accept(int s) { return s == 2 || s == 3 || s == 4 || s == 8; }
+
+BLU_HD bool check_float(const uint8_t* p, int len) {
+    int s = 0;
+    for (int i = 0; i < len; i++) s = float_dfa_next(s, num_class(p[i]));
+    return float_dfa_accept(s);
+}
+BLU_HD bool check_int(const uint8_t* p, int len) {
+    int i = (len > 0 && p[0] == '-') ? 1 : 0;
+    int nd = len - i;
+    if (nd < 1 || nd > 18) return false;
+    for (; i < len; i++)
+        if ((uint32_t)p[i] - '0' > 9u) return false;
+    return true;
+}
+
+// ---- one row, all 13 fields ----------------------------------------------------------------------------------
+struct LightRow {
+    int64_t bits;     // trunc(bitscore)
+    uint16_t q_len;   // length of qseqid
+    uint32_t err;     // DevErr
+};
+
+// Validates the whole row (field count, grammar of the 11 numeric columns, non-empty strings, no '"'/'\r')
+// and extracts what every row needs: the truncated bit score and the qseqid length.
+// Columns: 0 qseqid 1 saccver 2 staxid 3 pident 4 length 5 mismatch 6 gapopen 7 qstart 8 qend 9 sstart
+// 10 send 11 evalue 12 bitscore (core/src/domain/dtos/blast_builder.rs:87).
+BLU_HD LightRow light_parse_row(const uint8_t* p, int len) {
+    LightRow r;
+    r.bits = 0;
+    r.q_len = 0;
+    r.err = DE_NONE;
+    int f = 0, fs = 0;
+    int st = 0;        // DFA state of the current float field
+    bool bad = false;  // current int field has a non-digit
+    uint32_t err = DE_NONE;
+    int last_start = 0;
+    for (int i = 0; i <= len; i++) {
+        uint32_t c = i < len ? p[i] : '\t';
+        if (c == '\t') {
+            int flen = i - fs;
+            if (f <= 1) {
+                if (flen == 0 && !err) err = DE_EMPTY_STRING;
+                if (f == 0) r.q_len = (uint16_t)(flen > 65535 ? 65535 : flen);
+            } else if (f == 3 || f == 11 || f == 12) {
+                if (!float_dfa_accept(st) && !err) err = DE_BAD_NUMBER;
+                if (f == 12) last_start = fs;
+            } else if (f < 13) {
+                int nd = flen - ((flen > 0 && p[fs] == '-') ? 1 : 0);
+                if ((bad || nd < 1 || nd > 18) && !err) err = DE_BAD_NUMBER;
+            }
+            f++;
+            fs = i + 1;
+            st = 0;
+            bad = false;
+            continue;
+        }
+        if ((c == '"' || c == '\r') && !err) err = DE_QUOTE_OR_CR;
+        if (f == 3 || f == 11 || f == 12) {
+            st = float_dfa_next(st, num_class(c));
+        } else if (f >= 2) {
+            if (c - '0' > 9u && !(c == '-' && i == fs)) bad = true;
+        }
+    }
+    if (f != 13 && !err) err = DE_BAD_FIELD_COUNT;
+    if (!err) {
+        double d;
+        uint32_t e = parse_f64(p + last_start, len - last_start, d);
+        if (e)
+            err = e;
+        else if (!(d > -9223372036854775808.0 && d < 9223372036854775808.0))
+            err = DE_BITS_RANGE;
+        else
+            r.bits = (int64_t)d;  // truncation toward zero
+    }
+    r.err = err;
+    return r;
+}
+
+// ---- top-group rows ---------------------------------------------------------------------------------------------
+struct TopRow {
+    double pident;
+    int64_t alnlen;
+    uint64_t acc_off;   // absolute offset of saccver in the text buffer
+    uint32_t lin;       // lineage index
+    uint16_t acc_len;
+    uint16_t lin_len;   // number of lineage positions
+};
+
+// Fields 1..4 of an already validated row: saccver bounds, staxid -> lineage, pident, length.
+BLU_HD uint32_t heavy_parse_row(const uint8_t* p, int len, uint64_t row_abs_off, const LinTables& T, TopRow& out) {
+    int tabs[5];
+    int nt = 0;
+    for (int i = 0; i < len && nt < 5; i++)
+        if (p[i] == '\t') tabs[nt++] = i;
+    if (nt < 5) return DE_BAD_FIELD_COUNT;
+    out.acc_off = row_abs_off + (uint64_t)tabs[0] + 1;
+    int alen = tabs[1] - tabs[0] - 1;
+    if (alen > 65535) return DE_NUM_UNSUPPORTED;
+    out.acc_len = (uint16_t)alen;
+    int64_t taxid;
+    if (!parse_i64(p + tabs[1] + 1, tabs[2] - tabs[1] - 1, taxid)) return DE_BAD_NUMBER;
+    uint32_t e = parse_f64(p + tabs[2] + 1, tabs[3] - tabs[2] - 1, out.pident);
+    if (e) return e;
+    if (!parse_i64(p + tabs[3] + 1, tabs[4] - tabs[3] - 1, out.alnlen)) return DE_BAD_NUMBER;
+    uint32_t lin = probe_taxid(T, taxid);
+    if (lin == 0xFFFFFFFFu) return DE_UNMAPPED_TAXID;
+    if (!T.lin_ok[lin]) return DE_BAD_LINEAGE;
+    out.lin = lin;
+    out.lin_len = (uint16_t)(T.lin_off[lin + 1] - T.lin_off[lin]);
+    return DE_NONE;
+}
+
+// ---- consensus --------------------------------------------------------------------------------------------------
+// Where the per-query output goes.  `beans`/`accs` point at this query's reserved slots (g of each).
+struct QueryOut {
+    blu_record* rec;
+    blu_bean* beans;
+    blu_acc* accs;
+};
+
+BLU_HD int bytes_cmp(const uint8_t* a, int la, const uint8_t* b, int lb) {
+    int n = la < lb ? la : lb;
+    for (int i = 0; i < n; i++) {
+        int d = (int)a[i] - (int)b[i];
+        if (d) return d;
+    }
+    return la - lb;
+}
+
+// rank selection for a reference lineage (build_blast_consensus_identity.rs:22-37,66-95)
+BLU_HD void apply_cutoffs(const LinTables& T, uint32_t ref_lin, double identity, bool whole_filter, int idx, blu_record* rec) {
+    const uint32_t o = T.lin_off[ref_lin];
+    const int k = (int)(T.lin_off[ref_lin + 1] - o);
+    int allowed = -1;
+    for (int j = 0; j < k; j++)
+        if (!(identity > T.cut[o + j])) {  // skip_while(identity > cut) linnaean_ranks.rs:182-189
+            allowed = j;
+            break;
+        }
+    uint64_t mask = 0;
+    int kept = 0, last = -1;
+    for (int j = 0; j < k; j++)
+        if (identity >= T.cut[o + j]) {  // linnaean_ranks.rs:208
+            if (whole_filter || kept <= idx) {  // enumerate AFTER the filter, take_while(index <= bean_index)
+                mask |= 1ULL << j;
+                last = j;
+            }
+            kept++;
+        }
+    rec->keep_mask = mask;
+    rec->allowed_pos = (int8_t)allowed;
+    rec->reached_pos = (int8_t)(last >= 0 ? last : idx);  // adjusted_taxonomy.last().unwrap_or(_bean)
+    rec->mutated = (allowed >= 0 && T.rank_cls[o + idx] != T.allowed_cls[o + allowed]) ? 1 : 0;
+}
+
+// |G| == 1 (find_single_query_consensus.rs:74-150)
+BLU_HD uint32_t consensus_single(const TopRow& r, const LinTables& T, QueryOut out) {
+    const uint32_t o = T.lin_off[r.lin];
+    const int k = r.lin_len;
+    uint64_t mask = 0;
+    int last = -1;
+    for (int j = 0; j < k; j++)
+        if (r.pident >= T.cut[o + j]) {
+            mask |= 1ULL << j;
+            last = j;
+        }
+    if (last < 0) return DE_EMPTY_ADJUSTED;
+    blu_record* rec = out.rec;
+    rec->keep_mask = mask;
+    rec->perc_identity = r.pident;
+    rec->ref_lineage = r.lin;
+    rec->n_beans = 1;
+    rec->n_accessions = 1;
+    rec->status = 1;
+    rec->single_match = 1;
+    rec->mutated = 0;
+    rec->reached_pos = (int8_t)last;
+    rec->allowed_pos = -1;
+    rec->bean_level = (int8_t)last;
+    out.beans[0].first_lineage = r.lin;
+    out.beans[0].occurrences = 1;
+    out.beans[0].acc_begin = 0;
+    out.beans[0].n_acc = 1;
+    out.accs[0].off = r.acc_off;
+    out.accs[0].len = r.acc_len;
+    out.accs[0].pad = 0;
+    return DE_NONE;
+}
+
+// sort comparator of find_multi_taxa_consensus.rs:41-54, made total by the file order (stable sort)
+BLU_HD bool row_less(const TopRow* rows, const uint8_t* text, int a, int b) {
+    const TopRow& x = rows[a];
+    const TopRow& y = rows[b];
+    if (x.lin_len != y.lin_len) return x.lin_len < y.lin_len;
+    if (x.pident < y.pident) return true;
+    if (x.pident > y.pident) return false;
+    if (x.alnlen != y.alnlen) return x.alnlen < y.alnlen;
+    int c = bytes_cmp(text + x.acc_off, x.acc_len, text + y.acc_off, y.acc_len);
+    if (c) return c < 0;
+    return a < b;
+}
+
+// |G| > 1 (find_multi_taxa_consensus.rs:22-217 + build_blast_consensus_identity.rs).
+// rows[0..g) in file order; `text` is the base the acc_off offsets are relative to (generic pointer).
+// scratch: order[g], bean_of[g], bean_first[g], bean_cnt[g], bean_ord[g]  (uint16_t each, caller-provided).
+BLU_HD_NOINLINE uint32_t consensus_multi(const TopRow* rows, int g, const uint8_t* text, const LinTables& T, int strategy,
+                                         uint16_t* scratch, QueryOut out) {
+    uint16_t* order = scratch;
+    uint16_t* bean_of = scratch + g;
+    uint16_t* bean_first = scratch + 2 * g;
+    uint16_t* bean_cnt = scratch + 3 * g;
+    uint16_t* bean_ord = scratch + 4 * g;
+    // S = stable sort (insertion sort for small g, heap-free shell otherwise: comparator is total)
+    for (int i = 0; i < g; i++) order[i] = (uint16_t)i;
+    if (g <= 64) {
+        for (int i = 1; i < g; i++) {
+            uint16_t v = order[i];
+            int j = i - 1;
+            while (j >= 0 && row_less(rows, text, v, order[j])) {
+                order[j + 1] = order[j];
+                j--;
+            }
+            order[j + 1] = v;
+        }
+    } else {
+        // heap sort (total order => stability is irrelevant)
+        auto sift = [&](int start, int end) {
+            int root = start;
+            while (2 * root + 1 <= end) {
+                int child = 2 * root + 1, sw = root;
+                if (row_less(rows, text, order[sw], order[child])) sw = child;
+                if (child + 1 <= end && row_less(rows, text, order[sw], order[child + 1])) sw = child + 1;
+                if (sw == root) return;
+                uint16_t t = order[root];
+                order[root] = order[sw];
+                order[sw] = t;
+                root = sw;
+            }
+        };
+        for (int s = (g - 2) / 2; s >= 0; s--) sift(s, g - 1);
+        for (int e = g - 1; e > 0; e--) {
+            uint16_t t = order[e];
+            order[e] = order[0];
+            order[0] = t;
+            sift(0, e - 1);
+        }
+    }
+    const TopRow& ref = rows[strategy == BLU_STRATEGY_CAUTIOUS ? order[0] : order[g - 1]];  // fmtc.rs:60-63
+    const int m = rows[order[0]].lin_len;  // shortest lineage; levels >= m are skipped (take_while + continue)
+    // level walk (fmtc.rs:137-214): first level where the level keys disagree
+    int diverge = -1;
+    double max_pident = 0.0;
+    for (int i = 0; i < m; i++) {
+        uint32_t k0 = T.lvl_key[T.lin_off[rows[0].lin] + i];
+        bool same = true;
+        for (int r = 1; r < g; r++)
+            if (T.lvl_key[T.lin_off[rows[r].lin] + i] != k0) {
+                same = false;
+                break;
+            }
+        if (!same) {
+            diverge = i;
+            break;
+        }
+    }
+    int idx, level;
+    bool single;
+    double identity;
+    if (diverge == 0) return DE_ROOT_DISAGREE;
+    if (diverge > 0) {
+        for (int r = 0; r < g; r++)
+            if (rows[r].pident > max_pident) max_pident = rows[r].pident;  // fold from 0.0 (fmtc.rs:182-185)
+        idx = diverge - 1;
+        level = diverge;
+        single = false;
+        identity = max_pident;
+    } else {
+        idx = m - 1;
+        level = m - 1;
+        single = true;
+        identity = ref.pident;
+    }
+    // fold beans at `level` in S order (consensus_result.rs:65-88)
+    int nb = 0;
+    for (int s = 0; s < g; s++) {
+        const TopRow& r = rows[order[s]];
+        uint32_t key = T.bean_key[T.lin_off[r.lin] + level];
+        int b = -1;
+        for (int j = 0; j < nb; j++)
+            if (T.bean_key[T.lin_off[rows[bean_first[j]].lin] + level] == key) {
+                b = j;
+                break;
+            }
+        if (b < 0) {
+            b = nb++;
+            bean_first[b] = order[s];
+            bean_cnt[b] = 0;
+        }
+        bean_cnt[b]++;
+        bean_of[s] = (uint16_t)b;
+    }
+    // sort beans: occurrences desc, identifier asc (bbci.rs:50-60); deterministic tie-break on the key id
+    for (int j = 0; j < nb; j++) bean_ord[j] = (uint16_t)j;
+    for (int i = 1; i < nb; i++) {
+        uint16_t v = bean_ord[i];
+        int j = i - 1;
+        while (j >= 0) {
+            uint16_t w = bean_ord[j];
+            bool less;
+            if (bean_cnt[v] != bean_cnt[w])
+                less = bean_cnt[v] > bean_cnt[w];
+            else {
+                uint32_t pv = T.lin_off[rows[bean_first[v]].lin] + level, pw = T.lin_off[rows[bean_first[w]].lin] + level;
+                if (T.ident_rank[pv] != T.ident_rank[pw])
+                    less = T.ident_rank[pv] < T.ident_rank[pw];
+                else
+                    less = T.bean_key[pv] < T.bean_key[pw];
+            }
+            if (!less) break;
+            bean_ord[j + 1] = w;
+            j--;
+        }
+        bean_ord[j + 1] = v;
+    }
+    // emit beans + accession lists (S order, consecutive duplicates removed: Vec::dedup)
+    uint32_t na = 0;
+    for (int bi = 0; bi < nb; bi++) {
+        int b = bean_ord[bi];
+        uint32_t begin = na;
+        int prev = -1;
+        for (int s = 0; s < g; s++) {
+            if (bean_of[s] != b) continue;
+            const TopRow& r = rows[order[s]];
+            if (prev >= 0) {
+                const TopRow& q = rows[prev];
+                if (q.acc_len == r.acc_len && bytes_cmp(text + q.acc_off, q.acc_len, text + r.acc_off, r.acc_len) == 0) continue;
+            }
+            out.accs[na].off = r.acc_off;
+            out.accs[na].len = r.acc_len;
+            out.accs[na].pad = 0;
+            na++;
+            prev = order[s];
+        }
+        out.beans[bi].first_lineage = rows[bean_first[b]].lin;
+        out.beans[bi].occurrences = bean_cnt[b];
+        out.beans[bi].acc_begin = begin;
+        out.beans[bi].n_acc = na - begin;
+    }
+    blu_record* rec = out.rec;
+    rec->perc_identity = ref.pident;
+    rec->ref_lineage = ref.lin;
+    rec->n_beans = (uint32_t)nb;
+    rec->n_accessions = na;
+    rec->status = 1;
+    rec->single_match = 0;
+    rec->bean_level = (int8_t)level;
+    apply_cutoffs(T, ref.lin, identity, single && nb == 1, idx, rec);
+    return DE_NONE;
+}
+
+}  // namespace blu

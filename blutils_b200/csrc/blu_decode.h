@@ -1,0 +1,514 @@
+// blu_decode.h -- host-side decoding of the binary consensus records into the reference's result objects and
+// the writer of `write_blutils_output` (reference core/src/use_cases/write_blutils_output.rs:33-250).
+// Header-only so that the C ABI (blu_api.cpp) and the test-only host simulation (tests/csrc) share it.
+#pragma once
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <filesystem>
+#include <random>
+#include <string>
+#include <string_view>
+#include <thread>
+#include <vector>
+
+#include "../../include/blu_consensus.h"
+#include "blu_json.h"
+#include "blu_taxonomy.h"
+
+namespace blu {
+
+// Non-owning view of one result set.
+struct ResultView {
+    const HostTaxonomy* tax = nullptr;
+    Cutoffs cut;
+    const blu_record* rec_ = nullptr;
+    const blu_bean* beans_ = nullptr;
+    const blu_acc* accs_ = nullptr;
+    const char* pool_ = nullptr;
+    uint64_t n_rec = 0;
+    const std::vector<std::string>* hitless_ = nullptr;
+    const blu_record* rec() const { return rec_; }
+    const blu_bean* beans() const { return beans_; }
+    const blu_acc* accs() const { return accs_; }
+    const char* pool() const { return pool_; }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// decoding: records -> the reference's JSON objects
+// ---------------------------------------------------------------------------------------------------------------
+inline std::string_view rec_query(const ResultView* r, const blu_record& rc) { return std::string_view(r->pool() + rc.query_off, rc.query_len); }
+
+// serde form of Option<LinnaeanRank> for max_allowed_rank (bbci.rs:22-30): DefaultRank -> the enum variant,
+// NonDefaultRank(name) -> Other(name) where name = rank.to_string()
+inline void append_allowed_rank(std::string& o, const HostTaxonomy& T, const std::vector<uint8_t>& in_bb, uint32_t pos) {
+    const RankInfo& ri = T.ranks[T.pos_rank[pos]];
+    json_escape(o, in_bb[T.pos_rank[pos]] ? ri.full : ri.display);
+}
+
+struct Decoder {
+    const ResultView* r;
+    const HostTaxonomy& T;
+    std::vector<uint8_t> in_bb;  // per rank id: default rank present in the cutoff backbone
+    Decoder(const ResultView* res) : r(res), T(*res->tax) {
+        const Cutoffs& cut = res->cut;
+        auto bb = make_backbone(cut);
+        in_bb.resize(T.ranks.size());
+        for (size_t i = 0; i < T.ranks.size(); i++) {
+            in_bb[i] = 0;
+            if (T.ranks[i].def >= 0)
+                for (auto& b : bb)
+                    if (b.def == T.ranks[i].def) in_bb[i] = 1;
+        }
+    }
+    // `"taxon":{...}` object body (TaxonomyBean, taxonomy_bean.rs:5-17) in compact or pretty layout
+    void taxon(std::string& o, const blu_record& rc, bool pretty, int ind) const {
+        const uint32_t lo = T.lin_off[rc.ref_lineage];
+        auto nl = [&](int extra) {
+            if (!pretty) return;
+            o.push_back('\n');
+            o.append((size_t)(ind + extra) * 2, ' ');
+        };
+        const char* colon = pretty ? ": " : ":";
+        o.push_back('{');
+        nl(1);
+        o += "\"reachedRank\"";
+        o += colon;
+        json_escape(o, T.ranks[T.pos_rank[lo + rc.reached_pos]].full);
+        o.push_back(',');
+        nl(1);
+        o += "\"maxAllowedRank\"";
+        o += colon;
+        if (rc.allowed_pos < 0)
+            o += "null";
+        else
+            append_allowed_rank(o, T, in_bb, lo + rc.allowed_pos);
+        o.push_back(',');
+        nl(1);
+        o += "\"identifier\"";
+        o += colon;
+        json_escape(o, T.idents[T.pos_ident[lo + rc.reached_pos]]);
+        o.push_back(',');
+        nl(1);
+        o += "\"percIdentity\"";
+        o += colon;
+        json_f64(o, rc.perc_identity);
+        o.push_back(',');
+        nl(1);
+        o += "\"bitScore\"";
+        o += colon;
+        json_f64(o, (double)rc.bit_score);
+        o.push_back(',');
+        nl(1);
+        o += "\"taxonomy\"";
+        o += colon;
+        {
+            std::string t;
+            bool first = true;
+            const int k = T.lin_len(rc.ref_lineage);
+            for (int j = 0; j < k; j++)
+                if (rc.keep_mask >> j & 1) {
+                    if (!first) t.push_back(';');
+                    first = false;
+                    T.append_bean(t, lo + j);
+                }
+            json_escape(o, t);
+        }
+        o.push_back(',');
+        nl(1);
+        o += "\"mutated\"";
+        o += colon;
+        o += rc.mutated ? "true" : "false";
+        o.push_back(',');
+        nl(1);
+        o += "\"singleMatch\"";
+        o += colon;
+        o += rc.single_match ? "true" : "false";
+        o.push_back(',');
+        nl(1);
+        o += "\"consensusBeans\"";
+        o += colon;
+        o.push_back('[');
+        std::string lineage;
+        for (uint32_t b = 0; b < rc.n_beans; b++) {
+            const blu_bean& bn = r->beans()[rc.slot_base + b];
+            const uint32_t bp = T.lin_off[bn.first_lineage] + rc.bean_level;
+            if (b) o.push_back(',');
+            nl(2);
+            o.push_back('{');
+            nl(3);
+            o += "\"rank\"";
+            o += colon;
+            json_escape(o, T.ranks[T.pos_rank[bp]].full);
+            o.push_back(',');
+            nl(3);
+            o += "\"identifier\"";
+            o += colon;
+            json_escape(o, T.idents[T.pos_ident[bp]]);
+            o.push_back(',');
+            nl(3);
+            o += "\"occurrences\"";
+            o += colon;
+            o += std::to_string(bn.occurrences);
+            o.push_back(',');
+            nl(3);
+            o += "\"taxonomy\"";
+            o += colon;
+            lineage.clear();
+            T.append_lineage(lineage, bn.first_lineage);
+            json_escape(o, lineage);
+            o.push_back(',');
+            nl(3);
+            o += "\"accessions\"";
+            o += colon;
+            o.push_back('[');
+            for (uint32_t a = 0; a < bn.n_acc; a++) {
+                const blu_acc& ac = r->accs()[rc.slot_base + bn.acc_begin + a];
+                if (a) o.push_back(',');
+                nl(4);
+                json_escape(o, std::string_view(r->pool() + ac.off, ac.len));
+            }
+            if (bn.n_acc) nl(3);
+            o.push_back(']');
+            nl(2);
+            o.push_back('}');
+        }
+        if (rc.n_beans) nl(1);
+        o.push_back(']');
+        nl(0);
+        o.push_back('}');
+    }
+    // one QueryWithConsensus object (consensus_result.rs:7-13); run_id empty -> field omitted (canonical form)
+    void object(std::string& o, std::string_view query, const blu_record* rc, const char* run_id, bool pretty, int ind) const {
+        auto nl = [&](int extra) {
+            if (!pretty) return;
+            o.push_back('\n');
+            o.append((size_t)(ind + extra) * 2, ' ');
+        };
+        const char* colon = pretty ? ": " : ":";
+        o.push_back('{');
+        if (run_id) {
+            nl(1);
+            o += "\"runId\"";
+            o += colon;
+            json_escape(o, run_id);
+            o.push_back(',');
+        }
+        nl(1);
+        o += "\"query\"";
+        o += colon;
+        json_escape(o, query);
+        o.push_back(',');
+        nl(1);
+        o += "\"taxon\"";
+        o += colon;
+        if (rc)
+            taxon(o, *rc, pretty, ind + 1);
+        else
+            o += "null";
+        nl(0);
+        o.push_back('}');
+    }
+};
+
+struct Entry {
+    std::string_view query;
+    const blu_record* rec;  // nullptr = NoConsensusFound
+};
+
+// write_blutils_output.rs:87-111: flatten + sort by query (bytewise)
+inline std::vector<Entry> sorted_entries(const ResultView* r) {
+    std::vector<Entry> v;
+    v.reserve(r->n_rec + (r->hitless_ ? r->hitless_->size() : 0));
+    for (uint64_t i = 0; i < r->n_rec; i++) v.push_back({rec_query(r, r->rec()[i]), &r->rec()[i]});
+    if (r->hitless_)
+        for (auto& h : *r->hitless_) v.push_back({std::string_view(h), nullptr});
+    std::stable_sort(v.begin(), v.end(), [](const Entry& a, const Entry& b) { return a.query < b.query; });
+    return v;
+}
+
+inline unsigned host_threads() {
+    unsigned n = std::thread::hardware_concurrency();
+    return n ? std::min(n, 32u) : 4u;
+}
+
+template <class F>
+void parallel_ranges(size_t n, F&& f) {
+    unsigned nt = (unsigned)std::min<size_t>(host_threads(), std::max<size_t>(1, n / 4096));
+    if (nt <= 1) {
+        f(0, 0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++) th.emplace_back([&, t] { f(t, n * t / nt, n * (t + 1) / nt); });
+    for (auto& x : th) x.join();
+}
+
+inline std::string uuid_v4() {
+    std::random_device rd;
+    uint8_t b[16];
+    for (int i = 0; i < 16; i += 4) {
+        uint32_t x = rd();
+        memcpy(b + i, &x, 4);
+    }
+    b[6] = (b[6] & 0x0F) | 0x40;
+    b[8] = (b[8] & 0x3F) | 0x80;
+    char s[40];
+    snprintf(s, sizeof s, "%02x%02x%02x%02x-%02x%02x-%02x%02x-%02x%02x-%02x%02x%02x%02x%02x%02x", b[0], b[1], b[2], b[3], b[4], b[5], b[6], b[7],
+             b[8], b[9], b[10], b[11], b[12], b[13], b[14], b[15]);
+    return s;
+}
+
+// serde_yaml 0.9 scalar rules needed for this schema (strings that would not round-trip as plain scalars are
+// single-quoted; everything else plain)
+inline void yaml_str(std::string& o, std::string_view s) {
+    auto plain_ok = [&]() {
+        if (s.empty()) return false;
+        static const char* special[] = {"null", "Null", "NULL", "~", "true", "True", "TRUE", "false", "False", "FALSE", "y", "Y", "n", "N",
+                                        "yes", "Yes", "YES", "no", "No", "NO", "on", "On", "ON", "off", "Off", "OFF"};
+        for (auto sp : special)
+            if (s == sp) return false;
+        char c0 = s[0];
+        if (strchr("-?:,[]{}#&*!|>'\"%@` ", c0)) return false;
+        if (s.back() == ' ' || s.back() == ':') return false;
+        bool numeric = true;
+        for (char ch : s)
+            if (!((ch >= '0' && ch <= '9') || ch == '.' || ch == '-' || ch == '+' || ch == 'e' || ch == 'E' || ch == '_')) numeric = false;
+        if (numeric) return false;
+        for (size_t i = 0; i < s.size(); i++) {
+            unsigned char ch = (unsigned char)s[i];
+            if (ch < 0x20 || ch == 0x7f) return false;
+            if (ch == ':' && i + 1 < s.size() && s[i + 1] == ' ') return false;
+            if (ch == '#' && i > 0 && s[i - 1] == ' ') return false;
+        }
+        return true;
+    };
+    if (plain_ok()) {
+        o.append(s);
+        return;
+    }
+    bool ctl = false;
+    for (unsigned char ch : s) ctl |= ch < 0x20 || ch == 0x7f;
+    if (!ctl) {
+        o.push_back('\'');
+        for (char ch : s) {
+            if (ch == '\'') o.push_back('\'');
+            o.push_back(ch);
+        }
+        o.push_back('\'');
+        return;
+    }
+    o.push_back('"');
+    for (unsigned char ch : s) {
+        switch (ch) {
+            case '"': o += "\\\""; break;
+            case '\\': o += "\\\\"; break;
+            case '\n': o += "\\n"; break;
+            case '\t': o += "\\t"; break;
+            case '\r': o += "\\r"; break;
+            default:
+                if (ch < 0x20 || ch == 0x7f) {
+                    char b[8];
+                    snprintf(b, sizeof b, "\\x%02x", ch);
+                    o += b;
+                } else
+                    o.push_back((char)ch);
+        }
+    }
+    o.push_back('"');
+}
+
+inline void yaml_f64(std::string& o, double v) {  // serde_yaml: ryu, but integers print without ".0"?  No: serde_yaml keeps ryu's output
+    json_f64(o, v);
+}
+
+inline uint64_t view_checksum(const ResultView* r) {
+    Decoder d(r);
+    std::atomic<uint64_t> total{0};
+    auto fnv = [](const std::string& s) {
+        uint64_t h = 0xcbf29ce484222325ull;
+        for (unsigned char ch : s) {
+            h ^= ch;
+            h *= 0x100000001b3ull;
+        }
+        return h;
+    };
+    parallel_ranges(r->n_rec, [&](unsigned, size_t a, size_t b) {
+        std::string line;
+        uint64_t sum = 0;
+        for (size_t i = a; i < b; i++) {
+            line.clear();
+            d.object(line, rec_query(r, r->rec()[i]), &r->rec()[i], nullptr, false, 0);
+            sum += fnv(line);
+        }
+        total += sum;
+    });
+    if (r->hitless_)
+    for (auto& h : *r->hitless_) {
+        std::string line;
+        d.object(line, h, nullptr, nullptr, false, 0);
+        total += fnv(line);
+    }
+    return total.load();
+}
+
+
+inline std::string view_to_jsonl(const ResultView* r) {
+    Decoder d(r);
+    auto ent = sorted_entries(r);
+    std::vector<std::string> parts(host_threads());
+    parallel_ranges(ent.size(), [&](unsigned t, size_t a, size_t b) {
+        std::string& o = parts[t];
+        for (size_t i = a; i < b; i++) {
+            d.object(o, ent[i].query, ent[i].rec, nullptr, false, 0);
+            o.push_back('\n');
+        }
+    });
+    size_t tot = 0;
+    for (auto& p : parts) tot += p.size();
+    std::string out;
+    out.reserve(tot);
+    for (auto& p : parts) out += p;
+    return out;
+}
+
+inline int view_write(const ResultView* r, const char* path, int format, const char* run_id_in) {
+    {
+        Decoder d(r);
+        auto ent = sorted_entries(r);
+        const std::string run_id = run_id_in ? std::string(run_id_in) : uuid_v4();
+        std::string target;
+        FILE* f = stdout;
+        if (path) {
+            // write_blutils_output.rs:42-52: the extension is forced to match the format
+            target = path;
+            size_t slash = target.find_last_of('/');
+            size_t dot = target.find_last_of('.');
+            if (dot != std::string::npos && (slash == std::string::npos || dot > slash)) target.resize(dot);
+            target += format == BLU_FORMAT_JSON ? ".json" : format == BLU_FORMAT_JSONL ? ".jsonl" : ".yaml";
+            {
+                std::error_code ec;
+                auto parent = std::filesystem::path(target).parent_path();
+                if (!parent.empty()) std::filesystem::create_directories(parent, ec);  // write_blutils_output.rs:64-73
+            }
+            f = fopen(target.c_str(), "wb");
+            if (!f) return BLU_ERR_IO;
+        }
+        const bool pretty = format == BLU_FORMAT_JSON && path != nullptr;  // to_string_pretty to a file, compact to stdout
+        std::string o;
+        auto flush = [&](bool force) {
+            if (o.size() > (8u << 20) || force) {
+                fwrite(o.data(), 1, o.size(), f);
+                o.clear();
+            }
+        };
+        if (format == BLU_FORMAT_JSON) {
+            o += pretty ? "{\n  \"results\": [" : "{\"results\":[";
+            for (size_t i = 0; i < ent.size(); i++) {
+                if (i) o.push_back(',');
+                if (pretty) o += "\n    ";
+                d.object(o, ent[i].query, ent[i].rec, run_id.c_str(), pretty, 2);
+                flush(false);
+            }
+            if (pretty)
+                o += ent.empty() ? "],\n  \"config\": null\n}" : "\n  ],\n  \"config\": null\n}";
+            else
+                o += "],\"config\":null}";
+        } else if (format == BLU_FORMAT_JSONL) {
+            o += "null\n";  // serde_json::to_string(&config) with config = None
+            for (size_t i = 0; i < ent.size(); i++) {
+                d.object(o, ent[i].query, ent[i].rec, run_id.c_str(), false, 0);
+                o.push_back('\n');
+                flush(false);
+            }
+        } else {
+            // serde_yaml 0.9 block style of BlutilsOutput{results, config}
+            const HostTaxonomy& T = *r->tax;
+            if (ent.empty())
+                o += "results: []\n";
+            else
+                o += "results:\n";
+            std::string tmp;
+            for (auto& en : ent) {
+                o += "- runId: ";
+                o += run_id;
+                o += "\n  query: ";
+                yaml_str(o, en.query);
+                if (!en.rec) {
+                    o += "\n  taxon: null\n";
+                    continue;
+                }
+                const blu_record& rc = *en.rec;
+                const uint32_t lo = T.lin_off[rc.ref_lineage];
+                o += "\n  taxon:\n    reachedRank: ";
+                yaml_str(o, T.ranks[T.pos_rank[lo + rc.reached_pos]].full);
+                o += "\n    maxAllowedRank: ";
+                if (rc.allowed_pos < 0)
+                    o += "null";
+                else {
+                    const RankInfo& ri = T.ranks[T.pos_rank[lo + rc.allowed_pos]];
+                    yaml_str(o, d.in_bb[T.pos_rank[lo + rc.allowed_pos]] ? ri.full : ri.display);
+                }
+                o += "\n    identifier: ";
+                yaml_str(o, T.idents[T.pos_ident[lo + rc.reached_pos]]);
+                o += "\n    percIdentity: ";
+                yaml_f64(o, rc.perc_identity);
+                o += "\n    bitScore: ";
+                yaml_f64(o, (double)rc.bit_score);
+                o += "\n    taxonomy: ";
+                tmp.clear();
+                {
+                    bool first = true;
+                    for (int j = 0; j < T.lin_len(rc.ref_lineage); j++)
+                        if (rc.keep_mask >> j & 1) {
+                            if (!first) tmp.push_back(';');
+                            first = false;
+                            T.append_bean(tmp, lo + j);
+                        }
+                }
+                yaml_str(o, tmp);
+                o += rc.mutated ? "\n    mutated: true" : "\n    mutated: false";
+                o += rc.single_match ? "\n    singleMatch: true" : "\n    singleMatch: false";
+                if (!rc.n_beans)
+                    o += "\n    consensusBeans: []\n";
+                else
+                    o += "\n    consensusBeans:\n";
+                for (uint32_t b = 0; b < rc.n_beans; b++) {
+                    const blu_bean& bn = r->beans()[rc.slot_base + b];
+                    const uint32_t bp = T.lin_off[bn.first_lineage] + rc.bean_level;
+                    o += "    - rank: ";
+                    yaml_str(o, T.ranks[T.pos_rank[bp]].full);
+                    o += "\n      identifier: ";
+                    yaml_str(o, T.idents[T.pos_ident[bp]]);
+                    o += "\n      occurrences: " + std::to_string(bn.occurrences);
+                    o += "\n      taxonomy: ";
+                    tmp.clear();
+                    T.append_lineage(tmp, bn.first_lineage);
+                    yaml_str(o, tmp);
+                    if (!bn.n_acc)
+                        o += "\n      accessions: []\n";
+                    else
+                        o += "\n      accessions:\n";
+                    for (uint32_t a = 0; a < bn.n_acc; a++) {
+                        const blu_acc& ac = r->accs()[rc.slot_base + bn.acc_begin + a];
+                        o += "      - ";
+                        yaml_str(o, std::string_view(r->pool() + ac.off, ac.len));
+                        o.push_back('\n');
+                    }
+                }
+                flush(false);
+            }
+            o += "config: null\n";
+        }
+        flush(true);
+        if (path)
+            fclose(f);
+        else
+            fflush(stdout);
+        return BLU_OK;
+    }
+}
+
+
+}  // namespace blu

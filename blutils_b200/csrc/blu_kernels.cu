@@ -1,0 +1,851 @@
+// blu_kernels.cu -- hand-written sm_100a kernels of the consensus-identity path.
+//
+//   tile_kernel    : the dominant, HBM-bound kernel.  One CTA stages a ~61 KB window of outfmt-6 text into shared
+//                    memory with TMA bulk copies (cp.async.bulk + mbarrier), builds the row index with 16-byte
+//                    SIMD-in-register newline masks + warp prefix sums, validates/parses every row, finds query
+//                    runs and their top bit-score group, joins the top rows with the lineage tables (taxid hash
+//                    probe in HBM/L2) and emits one consensus record per query.  Text is read from HBM once;
+//                    nothing per-row is ever written back to HBM.
+//   longrun_kernel : block-per-query path for queries that do not fit a tile window (long-tail / straddlers),
+//                    whose top group exceeds one warp, or that touch the end of a streamed chunk.
+//   gather_kernel  : copies query ids and accessions of finished queries into the result's string pool.
+//   dup_kernel     : detects a query id that occurs in two separate runs (non-contiguous input).
+//
+// Reference semantics: see blu_core.cuh.  Geometry and roofline accounting: DESIGN.md.
+#include <cuda_runtime.h>
+
+#include "blu_kernels.h"
+
+namespace blu {
+
+namespace {
+
+constexpr int kWarps = kTileThreads / 32;
+constexpr int kRowCap = kWin / 26 + 16;   // a valid row is >= 26 bytes (13 one-byte fields, 12 tabs, '\n')
+constexpr int kMaxRuns = kRowCap;           // owned heads <= rows in the window
+constexpr int kLongTopCap = 1024;         // largest top bit-score group the block path sorts
+constexpr int kLongThreads = 256;
+constexpr int kLongWarps = kLongThreads / 32;
+
+// ---------------------------------------------------------------------------------------------------------------
+// small PTX wrappers (TMA 1-D bulk copy + mbarrier)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void report(Counters* ctr, uint32_t err, unsigned long long off) {
+    if (atomicCAS(&ctr->err_code, 0u, err) == 0u) ctr->err_off = off;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// shared-memory window + row index (used by both kernels)
+// ---------------------------------------------------------------------------------------------------------------
+struct WindowIndex {
+    alignas(128) uint8_t win[kWin + 128];
+    uint16_t row_s[kRowCap];
+    uint16_t row_e[kRowCap + 1];
+    alignas(8) unsigned long long mbar;
+    int n_starts, n_ends;
+    int warp_cnt[16];
+};
+
+struct WinGeom {
+    unsigned long long lo;  // absolute offset of win[0]
+    int rb;                 // begin - lo (may be negative)
+    int re;                 // end - lo   (may exceed the window)
+    int loaded;             // bytes staged
+    int L;                  // bytes scanned (text end + optional virtual newline)
+    bool covers_eof;        // the window contains the end of the text
+};
+
+// Stage [lo, lo+bytes) of the text into the window with TMA bulk copies.  All threads call; returns when the
+// bytes are visible.  `phase` is the barrier parity, flipped by the caller after every use.
+__device__ __forceinline__ void load_window(WindowIndex& W, const uint8_t* text, unsigned long long lo, int bytes, uint32_t& phase) {
+    __syncthreads();  // everyone is done with the previous contents
+    if (threadIdx.x == 0) {
+        fence_proxy_async();
+        mbar_expect_tx(&W.mbar, (uint32_t)bytes);
+        for (int o = 0; o < bytes; o += 16384) {
+            int n = bytes - o < 16384 ? bytes - o : 16384;
+            tma_bulk_g2s(W.win + o, text + lo + o, (uint32_t)n, &W.mbar);
+        }
+    }
+    while (!mbar_try_wait(&W.mbar, phase)) {
+    }
+    phase ^= 1;
+}
+
+// Window geometry for text [begin, end) seen through a window starting at `lo` of at most `max_bytes`.
+__device__ __forceinline__ WinGeom make_geom(unsigned long long lo, int max_bytes, unsigned long long begin, unsigned long long end) {
+    WinGeom g;
+    g.lo = lo;
+    unsigned long long up = (end + 15ull) & ~15ull;
+    unsigned long long hi = lo + (unsigned long long)max_bytes;
+    if (hi > up) hi = up;
+    g.loaded = hi > lo ? (int)(hi - lo) : 0;
+    g.rb = begin >= lo ? (int)((begin - lo) > 0x7fffffffull ? 0x7fffffff : (begin - lo)) : -1;
+    long long re = (long long)end - (long long)lo;
+    g.re = re > (long long)kWin + 64 ? kWin + 64 : (int)re;
+    g.covers_eof = end <= lo + (unsigned long long)g.loaded;
+    g.L = g.re < g.loaded ? g.re : g.loaded;
+    return g;
+}
+
+// 16-bit mask of bytes equal to `c` in a 16-byte chunk
+__device__ __forceinline__ uint32_t eq_mask16(const uint4& v, uint32_t c4) {
+    uint32_t a = (__vcmpeq4(v.x, c4) & 0x01010101u) * 0x01020408u >> 24;
+    uint32_t b = (__vcmpeq4(v.y, c4) & 0x01010101u) * 0x01020408u >> 24;
+    uint32_t c = (__vcmpeq4(v.z, c4) & 0x01010101u) * 0x01020408u >> 24;
+    uint32_t d = (__vcmpeq4(v.w, c4) & 0x01010101u) * 0x01020408u >> 24;
+    return (a & 15u) | ((b & 15u) << 4) | ((c & 15u) << 8) | ((d & 15u) << 12);
+}
+
+__device__ __forceinline__ uint32_t range_mask16(int pos0, int lo, int hi) {  // bits k with lo <= pos0+k < hi
+    int a = lo - pos0, b = hi - pos0;
+    a = a < 0 ? 0 : (a > 16 ? 16 : a);
+    b = b < 0 ? 0 : (b > 16 ? 16 : b);
+    if (b <= a) return 0;
+    return ((1u << b) - 1u) & ~((1u << a) - 1u);
+}
+
+// row starts / row ends inside chunk c (see DESIGN.md "row index")
+__device__ __forceinline__ void chunk_masks(const WindowIndex& W, const WinGeom& g, int c, uint32_t& start, uint32_t& end) {
+    const int pos0 = c << 4;
+    const uint4 v = *reinterpret_cast<const uint4*>(W.win + pos0);
+    const int rb = g.rb < 0 ? 0 : g.rb;
+    uint32_t nl = eq_mask16(v, 0x0A0A0A0Au) & range_mask16(pos0, rb, g.L);
+    uint32_t carry;
+    if (g.rb >= 0 && pos0 == g.rb)
+        carry = 1;  // virtual newline in front of the text
+    else if (pos0 > rb)
+        carry = W.win[pos0 - 1] == '\n';
+    else
+        carry = 0;  // unknown predecessor (window starts mid-text) or before the text
+    uint32_t prev = ((nl << 1) | carry) & 0xFFFFu;
+    if (g.rb > pos0 && g.rb < pos0 + 16) prev |= 1u << (g.rb - pos0);
+    start = prev & ~nl & range_mask16(pos0, rb, g.re < g.loaded ? g.re : g.loaded);
+    end = nl & ~prev;
+}
+
+// Builds row_s / row_e for the staged window.  Returns false (uniformly) when the row table would overflow,
+// which can only happen when some row is shorter than 26 bytes, i.e. malformed.
+template <int NWARPS>
+__device__ bool scan_rows(WindowIndex& W, const WinGeom& g) {
+    const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int nchunks = (g.L + 15) >> 4;
+    const int cpw = (nchunks + NWARPS - 1) / NWARPS;
+    const int c0 = w * cpw;
+    const int c1 = c0 + cpw < nchunks ? c0 + cpw : nchunks;
+    int cnt = 0;
+    for (int base = c0; base < c1; base += 32) {
+        int c = base + lane;
+        if (c < c1) {
+            uint32_t s, e;
+            chunk_masks(W, g, c, s, e);
+            cnt += __popc(s) | (__popc(e) << 16);
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
+    if (lane == 0) W.warp_cnt[w] = cnt;
+    __syncthreads();
+    int so = 0, eo = 0, ts = 0, te = 0;
+#pragma unroll
+    for (int i = 0; i < NWARPS; i++) {
+        int v = W.warp_cnt[i];
+        if (i < w) {
+            so += v & 0xFFFF;
+            eo += v >> 16;
+        }
+        ts += v & 0xFFFF;
+        te += v >> 16;
+    }
+    if (tid == 0) {
+        W.n_starts = ts;
+        W.n_ends = te;
+    }
+    if (ts > kRowCap || te > kRowCap) {
+        __syncthreads();
+        return false;
+    }
+    for (int base = c0; base < c1; base += 32) {
+        int c = base + lane;
+        uint32_t s = 0, e = 0;
+        if (c < c1) chunk_masks(W, g, c, s, e);
+        int mine = __popc(s) | (__popc(e) << 16);
+        int inc = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        int tot = __shfl_sync(0xffffffffu, inc, 31);
+        int ex = inc - mine;
+        int os = so + (ex & 0xFFFF), oe = eo + (ex >> 16);
+        const int pos0 = c << 4;
+        while (s) {
+            int k = __ffs(s) - 1;
+            s &= s - 1;
+            W.row_s[os++] = (uint16_t)(pos0 + k);
+        }
+        while (e) {
+            int k = __ffs(e) - 1;
+            e &= e - 1;
+            W.row_e[oe++] = (uint16_t)(pos0 + k);
+        }
+        so += tot & 0xFFFF;
+        eo += tot >> 16;
+    }
+    __syncthreads();
+    return true;
+}
+
+// Writes the virtual newline that terminates an unterminated last row (final chunk only) and fixes g.L.
+__device__ __forceinline__ void finish_geom(WindowIndex& W, WinGeom& g, bool final_chunk) {
+    if (final_chunk && g.covers_eof && g.re > 0 && g.re <= g.loaded) {
+        bool needs = (g.re - 1 >= 0) && W.win[g.re - 1] != '\n' && (g.rb < 0 || g.re - 1 >= g.rb);
+        if (needs) {
+            __syncthreads();
+            if (threadIdx.x == 0) W.win[g.re] = '\n';  // win has 128 spare bytes
+            g.L = g.re + 1;
+            __syncthreads();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// tile kernel
+// ---------------------------------------------------------------------------------------------------------------
+struct WarpScratch {
+    TopRow rows[32];
+    uint16_t idx[32];
+    uint16_t tmp[5 * 32];
+};
+
+struct TileSmem {
+    WindowIndex W;
+    int32_t bits[kRowCap];
+    uint8_t flags[kRowCap];  // bit0: head of a run, bit1: bit score does not fit int32
+    uint16_t runs[kMaxRuns];
+    WarpScratch ws[kWarps];
+    int n_runs;
+};
+
+static_assert(sizeof(TileSmem) <= 113 * 1024, "two tile CTAs must fit one SM");
+
+__device__ __forceinline__ void push_defer(const RunParams& p, unsigned long long off, unsigned check_prev) {
+    unsigned i = atomicAdd(&p.ctr->n_defer, 1u);
+    if (i < p.defer_cap)
+        p.defer[i] = (off << 1) | check_prev;
+    else
+        p.ctr->cap_overflow = 1;
+}
+
+__global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(const __grid_constant__ RunParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    TileSmem& S = *reinterpret_cast<TileSmem*>(smem_raw);
+    WindowIndex& W = S.W;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) mbar_init(&W.mbar, 1);
+    __syncthreads();
+    uint32_t phase = 0;
+
+    const unsigned long long first_tile = p.begin / kTile;
+    const unsigned long long n_tiles = p.end > p.begin ? (p.end + kTile - 1) / kTile - first_tile : 0;
+
+    for (unsigned long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const unsigned long long base = (first_tile + t) * (unsigned long long)kTile;
+        unsigned long long lo = base >= (unsigned long long)kBack ? base - kBack : 0;
+        const unsigned long long b16 = p.begin & ~15ull;
+        if (lo < b16) lo = b16;
+        const int max_bytes = (int)(base + kTile + kFwd - lo);
+        WinGeom g = make_geom(lo, max_bytes, p.begin, p.end);
+        if (g.loaded <= 0) continue;
+        load_window(W, p.text, lo, g.loaded, phase);
+        finish_geom(W, g, p.final_chunk != 0);
+        if (tid == 0) S.n_runs = 0;
+        if (!scan_rows<kWarps>(W, g)) {
+            if (tid == 0) report(p.ctr, DE_BAD_FIELD_COUNT, lo);
+            continue;
+        }
+        const int n_starts = W.n_starts, n_ends = W.n_ends;
+        const int eskip = (n_ends > 0 && (n_starts == 0 || W.row_e[0] < W.row_s[0])) ? 1 : 0;
+        const int ncomplete = n_starts < n_ends - eskip ? n_starts : n_ends - eskip;
+        const bool has_partial = n_starts > ncomplete;
+        const unsigned long long own_lo = base, own_hi = base + kTile;
+
+        // ---- phase B: every complete row: validate, bit score, head flag ----------------------------------
+        for (int r = tid; r < ncomplete; r += kTileThreads) {
+            const int s = W.row_s[r];
+            const int len = (int)W.row_e[r + eskip] - s;
+            const uint8_t* q = W.win + s;
+            LightRow lr = light_parse_row(q, len);
+            if (lr.err) report(p.ctr, lr.err, lo + s);
+            uint8_t fl = 0;
+            int32_t b32 = (int32_t)lr.bits;
+            if ((int64_t)b32 != lr.bits) fl |= 2;
+            if (r == 0) {
+                if (g.rb >= 0 && s == g.rb) fl |= 1;  // first row of the text
+            } else {
+                const uint8_t* pq = W.win + W.row_s[r - 1];
+                const int plen = (int)W.row_e[r - 1 + eskip] - (int)W.row_s[r - 1];
+                const int n = len < plen ? len : plen;
+                bool same = false;
+                for (int i = 0; i < n; i++) {
+                    uint8_t a = q[i];
+                    if (a != pq[i]) break;
+                    if (a == '\t') {
+                        same = true;
+                        break;
+                    }
+                }
+                if (!same) fl |= 1;
+            }
+            S.bits[r] = b32;
+            S.flags[r] = fl;
+        }
+        __syncthreads();
+        // ---- phase C: runs owned by this tile ------------------------------------------------------------------
+        for (int r = tid; r < ncomplete; r += kTileThreads) {
+            const unsigned long long abs = lo + W.row_s[r];
+            const bool owned = abs >= own_lo && abs < own_hi;
+            if (!owned) continue;
+            if (S.flags[r] & 1) {
+                int i = atomicAdd(&S.n_runs, 1);
+                S.runs[i] = (uint16_t)r;
+            } else if (r == 0) {
+                push_defer(p, abs, 1);  // predecessor not in the window: the block path decides whether it is a head
+            }
+        }
+        if (tid == 0 && has_partial) {
+            const unsigned long long abs = lo + W.row_s[ncomplete];
+            if (abs >= own_lo && abs < own_hi) push_defer(p, abs, 1);  // unterminated row: the block path sorts it out
+        }
+        __syncthreads();
+        // ---- phase D: one warp per run ----------------------------------------------------------------------------
+        const int n_runs = S.n_runs;
+        WarpScratch& ws = S.ws[warp];
+        for (int ri = warp; ri < n_runs; ri += kWarps) {
+            const int h = S.runs[ri];
+            // end of the run = next head among the complete rows
+            int e = -1;
+            for (int b = h + 1; b < ncomplete; b += 32) {
+                int r = b + lane;
+                bool hd = r < ncomplete && (S.flags[r] & 1);
+                unsigned bal = __ballot_sync(0xffffffffu, hd);
+                if (bal) {
+                    e = b + __ffs(bal) - 1;
+                    break;
+                }
+            }
+            const unsigned long long h_abs = lo + W.row_s[h];
+            if (e < 0) {
+                if (p.final_chunk && g.covers_eof && !has_partial)
+                    e = ncomplete;
+                else {
+                    if (lane == 0) push_defer(p, h_abs, 0);
+                    continue;
+                }
+            }
+            // max bit score of the run
+            int mx = INT32_MIN;
+            bool ovf = false;
+            for (int r = h + lane; r < e; r += 32) {
+                int b = S.bits[r];
+                mx = b > mx ? b : mx;
+                ovf |= (S.flags[r] & 2) != 0;
+            }
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                int o = __shfl_xor_sync(0xffffffffu, mx, d);
+                mx = o > mx ? o : mx;
+            }
+            ovf = __any_sync(0xffffffffu, ovf);
+            // rows of the top group, in file order
+            int gcount = 0;
+            for (int b = h; b < e; b += 32) {
+                int r = b + lane;
+                bool top = r < e && S.bits[r] == mx;
+                unsigned bal = __ballot_sync(0xffffffffu, top);
+                int pos = gcount + __popc(bal & ((1u << lane) - 1u));
+                if (top && pos < 32) ws.idx[pos] = (uint16_t)r;
+                gcount += __popc(bal);
+            }
+            __syncwarp();
+            if (ovf || gcount > 32) {
+                if (lane == 0) push_defer(p, h_abs, 0);
+                continue;
+            }
+            // reserve output
+            unsigned rec_i = 0, slot = 0;
+            if (lane == 0) {
+                rec_i = atomicAdd(&p.ctr->n_rec, 1u);
+                slot = atomicAdd(&p.ctr->n_slots, (unsigned)gcount);
+                atomicAdd(&p.ctr->n_rows, (unsigned long long)(e - h));
+            }
+            rec_i = __shfl_sync(0xffffffffu, rec_i, 0);
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            if (rec_i >= p.rec_cap || slot + (unsigned)gcount > p.slot_cap) {
+                if (lane == 0) p.ctr->cap_overflow = 1;
+                continue;
+            }
+            // join: each lane parses one top row and probes the taxid table
+            uint32_t err = 0;
+            if (lane < gcount) {
+                const int r = ws.idx[lane];
+                const int s = W.row_s[r];
+                err = heavy_parse_row(W.win + s, (int)W.row_e[r + eskip] - s, lo + s, p.T, ws.rows[lane]);
+                if (err) report(p.ctr, err, lo + s);
+            }
+            err = __any_sync(0xffffffffu, err != 0);
+            __syncwarp();
+            if (err) continue;
+            if (lane == 0) {
+                blu_record* rec = p.records + rec_i;
+                QueryOut out{rec, p.beans + slot, p.accs + slot};
+                const uint8_t* q = W.win + W.row_s[h];
+                const uint32_t qmax = (uint32_t)((int)W.row_e[h + eskip] - (int)W.row_s[h]);
+                uint32_t ql = 0;
+                while (ql < qmax && q[ql] != '\t') ql++;
+                rec->query_off = h_abs;
+                rec->query_len = ql;
+                rec->n_rows = (uint32_t)(e - h);
+                rec->bit_score = (int64_t)mx;
+                rec->slot_base = slot;
+                rec->pad[0] = rec->pad[1] = 0;
+                uint32_t ce = gcount == 1 ? consensus_single(ws.rows[0], p.T, out)
+                                          : consensus_multi(ws.rows, gcount, p.text, p.T, p.strategy, ws.tmp, out);
+                if (ce) report(p.ctr, ce, h_abs);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// long-run kernel: one CTA per deferred run
+// ---------------------------------------------------------------------------------------------------------------
+struct LongSmem {
+    WindowIndex W;
+    long long bits[kRowCap];
+    uint8_t same[kRowCap];
+    TopRow top[kLongTopCap];
+    uint16_t tmp[5 * kLongTopCap];
+    long long red_max[kLongWarps];
+    int red_cnt[kLongWarps];
+    int red_first[kLongWarps];
+    int bcast[8];
+    unsigned long long bcast64[4];
+};
+
+static_assert(sizeof(LongSmem) <= 227 * 1024, "long-run CTA exceeds shared memory");
+
+__device__ __forceinline__ bool same_query(const uint8_t* a, int alen, const uint8_t* text, unsigned long long s, unsigned long long end) {
+    // compares the first field of row `a` (window) with the first field of the row at absolute offset s (global)
+    for (int i = 0; i < alen; i++) {
+        if (s + i >= end) return false;
+        uint8_t b = text[s + i];
+        if (a[i] != b) return false;
+        if (b == '\t') return true;
+    }
+    return false;
+}
+
+struct LongScan {
+    int ncomplete, eskip, d;     // d = first row that does not belong to the run (== ncomplete when none)
+    unsigned long long next;     // where the next window starts
+    bool at_end;                 // no more text after this window
+    bool giant;                  // a row does not fit the window
+};
+
+// Stages the window that starts at `cur`, indexes and parses its rows, and marks which rows belong to the run
+// whose first row starts at absolute offset `s`.
+__device__ LongScan long_scan(LongSmem& S, const RunParams& p, unsigned long long s, unsigned long long cur, uint32_t& phase) {
+    WindowIndex& W = S.W;
+    LongScan r;
+    const unsigned long long lo = cur & ~15ull;
+    WinGeom g = make_geom(lo, kWin, cur, p.end);
+    load_window(W, p.text, lo, g.loaded, phase);
+    finish_geom(W, g, p.final_chunk != 0);
+    r.giant = false;
+    if (!scan_rows<kLongWarps>(W, g)) {
+        if (threadIdx.x == 0) report(p.ctr, DE_BAD_FIELD_COUNT, lo);
+        r.ncomplete = 0, r.eskip = 0, r.d = 0, r.next = p.end, r.at_end = true;
+        return r;
+    }
+    const int n_starts = W.n_starts, n_ends = W.n_ends;
+    r.eskip = (n_ends > 0 && (n_starts == 0 || W.row_e[0] < W.row_s[0])) ? 1 : 0;
+    r.ncomplete = n_starts < n_ends - r.eskip ? n_starts : n_ends - r.eskip;
+    int first_other = r.ncomplete;
+    for (int i = threadIdx.x; i < r.ncomplete; i += kLongThreads) {
+        const int st = W.row_s[i];
+        const int len = (int)W.row_e[i + r.eskip] - st;
+        LightRow lr = light_parse_row(W.win + st, len);
+        bool sm = same_query(W.win + st, len, p.text, s, p.end);
+        if (lr.err && sm) report(p.ctr, lr.err, lo + st);
+        S.bits[i] = lr.bits;
+        S.same[i] = sm;
+        if (!sm && i < first_other) first_other = i;
+    }
+#pragma unroll
+    for (int dd = 16; dd > 0; dd >>= 1) {
+        int o = __shfl_xor_sync(0xffffffffu, first_other, dd);
+        first_other = o < first_other ? o : first_other;
+    }
+    if ((threadIdx.x & 31) == 0) S.red_first[threadIdx.x >> 5] = first_other;
+    __syncthreads();
+    int d = r.ncomplete;
+    for (int i = 0; i < kLongWarps; i++) d = S.red_first[i] < d ? S.red_first[i] : d;
+    r.d = d;
+    if (n_starts > r.ncomplete) {
+        r.next = lo + W.row_s[r.ncomplete];
+        r.at_end = false;
+        if (r.ncomplete == 0) r.giant = !g.covers_eof || !p.final_chunk;  // partial row only: too long, or chunk tail
+        if (g.covers_eof) r.at_end = true;
+    } else {
+        r.next = r.ncomplete > 0 ? lo + W.row_e[r.ncomplete - 1 + r.eskip] + 1 : p.end;
+        r.at_end = g.covers_eof || r.next >= p.end;
+    }
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(kLongThreads, 1) longrun_kernel(const __grid_constant__ RunParams p) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    LongSmem& S = *reinterpret_cast<LongSmem*>(smem_raw);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) mbar_init(&S.W.mbar, 1);
+    __syncthreads();
+    uint32_t phase = 0;
+    const unsigned n_defer = p.ctr->n_defer < p.defer_cap ? p.ctr->n_defer : p.defer_cap;
+
+    while (true) {
+        __syncthreads();
+        if (tid == 0) S.bcast[0] = (int)atomicAdd(&p.ctr->work_ticket, 1u);
+        __syncthreads();
+        const unsigned wi = (unsigned)S.bcast[0];
+        if (wi >= n_defer) break;
+        const unsigned long long entry = p.defer[wi];
+        const unsigned long long s = entry >> 1;
+        // ---- is it really the first row of a run? ------------------------------------------------------------
+        if (entry & 1) {
+            if (tid == 0) {
+                int head = 1;
+                if (s > p.begin) {
+                    long long q = (long long)s - 1;
+                    while (q >= (long long)p.begin && p.text[q] == '\n') q--;  // skip the newline(s) before s
+                    if (q >= (long long)p.begin) {
+                        long long st = q;
+                        while (st > (long long)p.begin && p.text[st - 1] != '\n') st--;
+                        // compare first fields of rows at st and s
+                        head = 0;
+                        for (unsigned long long i = 0;; i++) {
+                            if (s + i >= p.end || (unsigned long long)st + i > (unsigned long long)q) {
+                                head = 1;
+                                break;
+                            }
+                            uint8_t a = p.text[st + i], b = p.text[s + i];
+                            if (a != b) {
+                                head = 1;
+                                break;
+                            }
+                            if (a == '\t') break;
+                        }
+                    }
+                }
+                S.bcast[1] = head;
+            }
+            __syncthreads();
+            if (!S.bcast[1]) continue;
+        }
+        // ---- pass A: extent, max bit score, size of the top group -------------------------------------------
+        long long mx = LLONG_MIN;
+        long long cnt = 0, nrows = 0;
+        unsigned long long cur = s;
+        bool ended = false, hit_end = false, fail = false;
+        while (true) {
+            LongScan sc = long_scan(S, p, s, cur, phase);
+            if (sc.giant && sc.d == 0 && sc.ncomplete == 0) {
+                // an unterminated row: either the chunk tail (carried over) or a row longer than the window
+                if (!sc.at_end || p.final_chunk) {
+                    if (tid == 0) report(p.ctr, DE_CARRY_TOO_BIG, cur);
+                    fail = true;
+                }
+                hit_end = true;
+                break;
+            }
+            long long lm = LLONG_MIN;
+            int lc = 0;
+            for (int i = tid; i < sc.d; i += kLongThreads) {
+                long long b = S.bits[i];
+                if (b > lm) {
+                    lm = b;
+                    lc = 1;
+                } else if (b == lm)
+                    lc++;
+            }
+#pragma unroll
+            for (int dd = 16; dd > 0; dd >>= 1) {
+                long long om = __shfl_xor_sync(0xffffffffu, lm, dd);
+                int oc = __shfl_xor_sync(0xffffffffu, lc, dd);
+                if (om > lm) {
+                    lm = om;
+                    lc = oc;
+                } else if (om == lm)
+                    lc += oc;
+            }
+            if (lane == 0) {
+                S.red_max[warp] = lm;
+                S.red_cnt[warp] = lc;
+            }
+            __syncthreads();
+            long long wm = LLONG_MIN;
+            long long wc = 0;
+            for (int i = 0; i < kLongWarps; i++) {
+                if (S.red_max[i] > wm) {
+                    wm = S.red_max[i];
+                    wc = S.red_cnt[i];
+                } else if (S.red_max[i] == wm)
+                    wc += S.red_cnt[i];
+            }
+            if (sc.d > 0) {
+                if (wm > mx) {
+                    mx = wm;
+                    cnt = wc;
+                } else if (wm == mx)
+                    cnt += wc;
+            }
+            nrows += sc.d;
+            if (sc.d < sc.ncomplete) {
+                ended = true;
+                break;
+            }
+            if (sc.at_end) {
+                hit_end = true;
+                break;
+            }
+            cur = sc.next;
+        }
+        if (fail) continue;
+        if (!ended && hit_end && !p.final_chunk) {
+            if (tid == 0) atomicMin(&p.ctr->tail_start, s);  // carried into the next chunk
+            continue;
+        }
+        if (nrows == 0) continue;
+        if (cnt > kLongTopCap) {
+            if (tid == 0) report(p.ctr, DE_TOPGROUP_TOO_BIG, s);
+            continue;
+        }
+        const int gcount = (int)cnt;
+        if (tid == 0) {
+            unsigned rec_i = atomicAdd(&p.ctr->n_rec, 1u);
+            unsigned slot = atomicAdd(&p.ctr->n_slots, (unsigned)gcount);
+            atomicAdd(&p.ctr->n_rows, (unsigned long long)nrows);
+            S.bcast[2] = (int)rec_i;
+            S.bcast[3] = (int)slot;
+        }
+        __syncthreads();
+        const unsigned rec_i = (unsigned)S.bcast[2], slot = (unsigned)S.bcast[3];
+        if (rec_i >= p.rec_cap || slot + (unsigned)gcount > p.slot_cap) {
+            if (tid == 0) p.ctr->cap_overflow = 1;
+            continue;
+        }
+        // ---- pass B: collect + join the top rows, in file order ----------------------------------------------
+        cur = s;
+        int filled = 0;
+        int any_err = 0;
+        while (filled < gcount) {
+            LongScan sc = long_scan(S, p, s, cur, phase);
+            const unsigned long long lo = cur & ~15ull;
+            for (int b = 0; b < sc.d; b += kLongThreads) {
+                const int i = b + tid;
+                const bool top = i < sc.d && S.bits[i] == mx;
+                const unsigned bal = __ballot_sync(0xffffffffu, top);
+                if (lane == 0) S.red_cnt[warp] = __popc(bal);
+                __syncthreads();
+                int before = filled;
+                for (int k = 0; k < warp; k++) before += S.red_cnt[k];
+                int total = 0;
+                for (int k = 0; k < kLongWarps; k++) total += S.red_cnt[k];
+                if (top) {
+                    int pos = before + __popc(bal & ((1u << lane) - 1u));
+                    if (pos >= kLongTopCap) pos = kLongTopCap - 1;  // cannot happen (cnt was checked); keeps smem safe
+                    const int st = S.W.row_s[i];
+                    uint32_t err = heavy_parse_row(S.W.win + st, (int)S.W.row_e[i + sc.eskip] - st, lo + st, p.T, S.top[pos]);
+                    if (err) {
+                        report(p.ctr, err, lo + st);
+                        any_err = 1;
+                    }
+                }
+                filled += total;
+                __syncthreads();
+            }
+            if (sc.d < sc.ncomplete || sc.at_end) break;
+            cur = sc.next;
+        }
+        any_err = __syncthreads_or(any_err);
+        if (any_err || filled != gcount) {
+            if (!any_err && tid == 0) report(p.ctr, DE_INTERNAL, s);
+            continue;
+        }
+        if (tid == 0) {
+            blu_record* rec = p.records + rec_i;
+            QueryOut out{rec, p.beans + slot, p.accs + slot};
+            uint32_t ql = 0;
+            while (s + ql < p.end && p.text[s + ql] != '\t') ql++;
+            rec->query_off = s;
+            rec->query_len = ql;
+            rec->n_rows = (uint32_t)nrows;
+            rec->bit_score = mx;
+            rec->slot_base = slot;
+            rec->pad[0] = rec->pad[1] = 0;
+            uint32_t ce = gcount == 1 ? consensus_single(S.top[0], p.T, out)
+                                      : consensus_multi(S.top, gcount, p.text, p.T, p.strategy, S.tmp, out);
+            if (ce) report(p.ctr, ce, s);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// gather: query ids + accessions -> string pool
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_kernel(const GatherParams p) {
+    __shared__ unsigned long long warp_tot[8];
+    __shared__ unsigned long long base_sh;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned i = p.rec_begin + blockIdx.x * blockDim.x + tid;
+    const bool live = i < p.rec_end;
+    unsigned long long bytes = 0;
+    blu_record* rec = nullptr;
+    if (live) {
+        rec = p.records + i;
+        bytes = rec->query_len;
+        for (unsigned a = 0; a < rec->n_accessions; a++) bytes += p.accs[rec->slot_base + a].len;
+    }
+    unsigned long long inc = bytes;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    unsigned long long before = 0, total = 0;
+    for (int k = 0; k < 8; k++) {
+        if (k < warp) before += warp_tot[k];
+        total += warp_tot[k];
+    }
+    if (tid == 0) base_sh = total ? atomicAdd(&p.ctr->pool_used, total) : 0ull;
+    __syncthreads();
+    if (!live) return;
+    unsigned long long o = base_sh + before + inc - bytes;
+    if (base_sh + total > p.pool_cap) {
+        p.ctr->cap_overflow = 1;
+        return;
+    }
+    const uint8_t* src = p.text + rec->query_off;
+    for (unsigned k = 0; k < rec->query_len; k++) p.pool[o + k] = src[k];
+    rec->query_off = o;
+    o += rec->query_len;
+    for (unsigned a = 0; a < rec->n_accessions; a++) {
+        blu_acc& ac = p.accs[rec->slot_base + a];
+        const uint8_t* sa = p.text + ac.off;
+        for (unsigned k = 0; k < ac.len; k++) p.pool[o + k] = sa[k];
+        ac.off = o;
+        o += ac.len;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// duplicate query detection (reference groups by a HashMap<String,_>, mod.rs:145,192: rows of one query need
+// not be contiguous).  A repeated id means the fast contiguous path is not applicable.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dup_kernel(const DupParams p) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.n_rec) return;
+    const blu_record& r = p.records[i];
+    unsigned long long h = 0xcbf29ce484222325ull;
+    const uint8_t* q = p.pool + r.query_off;
+    for (unsigned k = 0; k < r.query_len; k++) {
+        h ^= q[k];
+        h *= 0x100000001b3ull;
+    }
+    h = mix64(h ^ r.query_len);
+    if (h == 0) h = 1;
+    unsigned slot = (unsigned)h & p.mask;
+    for (unsigned n = 0; n <= p.mask; n++) {
+        unsigned long long old = atomicCAS(p.table + slot, 0ull, h);
+        if (old == 0ull) return;
+        if (old == h) {
+            p.ctr->dup_found = 1;
+            return;
+        }
+        slot = (slot + 1) & p.mask;
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------------------------
+cudaError_t kernels_set_attributes() {
+    cudaError_t e = cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(longrun_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LongSmem));
+}
+
+int tile_kernel_grid(int device) {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    return 2 * sms;  // two resident CTAs per SM (~100 KB of shared memory each)
+}
+
+cudaError_t launch_tile_kernel(const RunParams& p, int grid, cudaStream_t s) {
+    tile_kernel<<<grid, kTileThreads, sizeof(TileSmem), s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_longrun_kernel(const RunParams& p, int grid, cudaStream_t s) {
+    longrun_kernel<<<grid, kLongThreads, sizeof(LongSmem), s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_gather_kernel(const GatherParams& p, cudaStream_t s) {
+    if (p.rec_end <= p.rec_begin) return cudaSuccess;
+    unsigned n = p.rec_end - p.rec_begin;
+    gather_kernel<<<(n + 255) / 256, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dup_kernel(const DupParams& p, cudaStream_t s) {
+    if (p.n_rec == 0) return cudaSuccess;
+    dup_kernel<<<(p.n_rec + 255) / 256, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+}  // namespace blu

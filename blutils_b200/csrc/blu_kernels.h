@@ -1,0 +1,75 @@
+// blu_kernels.h -- launch interface between the host runtime (blu_api.cpp) and the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "blu_core.cuh"
+
+namespace blu {
+
+// Device-side counters of one run (zeroed by the host before the first chunk).
+struct Counters {
+    unsigned int n_rec;        // records reserved
+    unsigned int n_slots;      // bean/accession slots reserved
+    unsigned int n_defer;      // deferred runs of the current chunk
+    unsigned int err_code;     // first DevErr
+    unsigned long long err_off;    // byte offset (in the current device buffer) of the first error
+    unsigned long long tail_start; // !final chunks: start of the last (unfinished) run
+    unsigned long long pool_used;  // bytes of the string pool in use
+    unsigned long long n_rows;     // hit rows seen in finished runs
+    unsigned int dup_found;    // a query id occurs in two separate runs
+    unsigned int cap_overflow; // some output capacity was exceeded (host grows and retries)
+    unsigned int work_ticket;  // dynamic work distribution of the long-run kernel
+    unsigned int pad;
+};
+
+struct RunParams {
+    const uint8_t* text;   // device buffer (16-byte aligned, padded to a multiple of 128 bytes)
+    uint64_t begin, end;   // valid text is [begin, end)
+    int final_chunk;       // 1: `end` is the end of the input; 0: the run touching `end` is carried over
+    int strategy;
+    LinTables T;
+    blu_record* records;
+    uint32_t rec_cap;
+    blu_bean* beans;
+    blu_acc* accs;
+    uint32_t slot_cap;
+    uint64_t* defer;       // (offset << 1) | check_prev
+    uint32_t defer_cap;
+    Counters* ctr;
+};
+
+struct GatherParams {
+    const uint8_t* text;
+    blu_record* records;
+    blu_acc* accs;
+    uint32_t rec_begin, rec_end;  // records produced by the current chunk
+    uint8_t* pool;
+    uint64_t pool_cap;
+    Counters* ctr;
+};
+
+struct DupParams {
+    const blu_record* records;
+    uint32_t n_rec;
+    const uint8_t* pool;
+    unsigned long long* table;  // open addressing, 0 = empty
+    uint32_t mask;
+    Counters* ctr;
+};
+
+// Tile geometry of the fused kernel
+constexpr int kTile = 49152;   // bytes owned by one tile
+constexpr int kBack = 1024;    // look-behind so the tile's first row can be compared with its predecessor
+constexpr int kFwd = 12288;    // look-ahead so a query that starts in the tile can finish in the window
+constexpr int kWin = kBack + kTile + kFwd;
+constexpr int kTileThreads = 256;
+
+int tile_kernel_grid(int device);
+cudaError_t launch_tile_kernel(const RunParams& p, int grid, cudaStream_t s);
+cudaError_t launch_longrun_kernel(const RunParams& p, int grid, cudaStream_t s);
+cudaError_t launch_gather_kernel(const GatherParams& p, cudaStream_t s);
+cudaError_t launch_dup_kernel(const DupParams& p, cudaStream_t s);
+cudaError_t kernels_set_attributes();
+
+}  // namespace blu

@@ -13,9 +13,7 @@
 //
 // Accepted input grammar (anything else -> data error == "reference aborts or is unpinned"):
 //   int   := -?[0-9]{1,18}
-//   float := -?([0-9]+(\.[0-9]*)?|\.[0-9]+)([eE][+-]?[0-9]{1,4})?
-//            used columns (pident, bitscore) additionally: <= 19 significant digits, mantissa < 2^53,
-//            |decimal exponent| <= 22 (exactly representable fast path).
+//   float := -?([0-9]+(\.[0-9]*)?|\.[0-9]+)([eE][+-]?[0-9]+)?   (value: strtod, correctly rounded)
 //   rows '\n'-terminated (last newline optional), 13 '\t'-separated fields, empty lines skipped,
 //   no '"' and no '\r' bytes, non-empty qseqid/saccver.
 //
@@ -325,22 +323,12 @@ static int parse_float(const char* p, const char* e, bool need_value, double& v)
             nd++;
             p++;
         }
-        if (nd == 0 || nd > 4) return 1;
+        if (nd == 0) return 1;
         if (eneg) ex = -ex;
     }
     if (p != e) return 1;
     if (!need_value) return 0;
-    if (sig > 19) return 2;
-    // exactness conditions of the supported path
-    unsigned __int128 mant = 0;
-    {
-        const char* q = s;
-        if (*q == '-') q++;
-        for (; q < e && *q != 'e' && *q != 'E'; q++)
-            if (*q != '.') mant = mant * 10 + (unsigned)(*q - '0');
-    }
-    long e10 = ex - nfrac;
-    if (mant != 0 && (mant >= ((unsigned __int128)1 << 53) || e10 > 22 || e10 < -22)) return 2;
+    (void)sig;  // any number of digits: strtod is correctly rounded (the CUDA path reports BLU_ERR_UNSUPPORTED beyond its exact range)
     std::string tmp(s, e);
     v = strtod(tmp.c_str(), nullptr);  // correctly rounded; independent of the GPU's Clinger arithmetic
     return 0;
@@ -833,6 +821,26 @@ int blu_oracle_run(void* h, const char* text, uint64_t n, int threads, const cha
 }
 
 void blu_oracle_free(char* p) { free(p); }
+
+// order-independent checksum of a JSONL buffer: sum over lines of FNV-1a-64(line without '\n')
+// (same definition as blu_result_checksum in include/blu_consensus.h)
+uint64_t blu_oracle_checksum_jsonl(const char* js, uint64_t n) {
+    uint64_t total = 0;
+    const char* p = js;
+    const char* e = js + n;
+    while (p < e) {
+        const char* nl = (const char*)memchr(p, '\n', e - p);
+        const char* le = nl ? nl : e;
+        uint64_t h = 0xcbf29ce484222325ull;
+        for (const char* c = p; c < le; c++) {
+            h ^= (unsigned char)*c;
+            h *= 0x100000001b3ull;
+        }
+        total += h;
+        p = le + 1;
+    }
+    return total;
+}
 
 // interpolation only, for known-answer tests: ranks = '\n'-separated rank strings
 int blu_oracle_interpolate(const char* ranks_nl, int taxon, const int* custom8, double* out, int cap) {

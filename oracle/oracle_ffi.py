@@ -41,6 +41,8 @@ def lib():
         l.blu_oracle_run.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_char_p, C.c_uint64, C.POINTER(C.c_void_p),
                                      C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_char_p, C.c_int]
         l.blu_oracle_free.argtypes = [C.c_void_p]
+        l.blu_oracle_checksum_jsonl.restype = C.c_uint64
+        l.blu_oracle_checksum_jsonl.argtypes = [C.c_char_p, C.c_uint64]
         l.blu_oracle_interpolate.restype = C.c_int
         l.blu_oracle_interpolate.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.POINTER(C.c_double), C.c_int]
         _lib = l
@@ -141,3 +143,7 @@ def interpolate(ranks: Sequence[str], taxon: str, custom: Optional[dict] = None)
     if n < 0:
         raise OracleDataError("interpolate failed")
     return [out[i] for i in range(n)]
+
+
+def checksum_jsonl(js: bytes) -> int:
+    return lib().blu_oracle_checksum_jsonl(js, len(js))

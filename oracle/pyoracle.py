@@ -19,9 +19,7 @@ Third-party behaviour restated from published semantics (not in /root/reference)
     `try_extract().unwrap()`, mod.rs:174-184,371).  Accepted grammar here (anything else is
     a DataError, i.e. "the reference aborts or its behaviour is unpinned"):
         int   := -?[0-9]{1,18}
-        float := -?([0-9]+(\\.[0-9]*)?|\\.[0-9]+)([eE][+-]?[0-9]+)?   (<= 19 significant
-                 digits, decimal exponent such that the value is exactly m*10^e or m/10^-e
-                 with m < 2^53, |e| <= 22 for the two columns that are used)
+        float := -?([0-9]+(\\.[0-9]*)?|\\.[0-9]+)([eE][+-]?[0-9]+)?   (correctly rounded)
     Empty lines are skipped; a '"' or '\r' byte anywhere is a DataError (polars quoting /
     CRLF handling not restated).
   * slugify 0.1 `slugify!` (linnaean_ranks.rs:69): ASCII only here.
@@ -250,27 +248,11 @@ def check_float(b: bytes) -> None:
 
 
 def parse_float(b: bytes) -> float:
-    """Correctly rounded decimal->f64 restricted to the exact (Clinger) fast path."""
+    """Correctly rounded decimal->f64 (the CUDA path reports BLU_ERR_UNSUPPORTED outside its exact range)."""
     mt = _FLT.match(b)
     if not mt:
         raise DataError(f"bad float field {b!r}")
-    neg, ip, fp, fp2, ex = mt.groups()
-    ip = ip or b""
-    frac = fp if fp is not None else (fp2 or b"")
-    digits = (ip + frac).lstrip(b"0")
-    nfrac = len(frac)
-    e10 = (int(ex) if ex else 0) - nfrac
-    if ex and len(ex.lstrip(b"+-")) > 4:
-        raise DataError("float exponent too long")
-    if len(digits) > 19:
-        raise DataError("float with more than 19 significant digits (unsupported)")
-    mant = int(digits) if digits else 0
-    if mant == 0:
-        return -0.0 if neg else 0.0
-    if mant >= 2**53 or abs(e10) > 22:
-        raise DataError("float outside the exact fast path (unsupported)")
-    v = float(mant) * (10.0 ** e10) if e10 >= 0 else float(mant) / (10.0 ** (-e10))
-    return -v if neg else v
+    return float(b)  # Python float(): correctly rounded, any number of digits
 
 
 @dataclass

@@ -1,0 +1,215 @@
+// TEST INFRASTRUCTURE ONLY -- host simulation of the device-side logic.
+// Compiles blutils_b200/csrc/blu_core.cuh (the `__host__ __device__` parsing / join / consensus code the CUDA
+// kernels call), blu_taxonomy.cpp and blu_decode.h with g++ and drives them with a trivial sequential loop, so
+// that the per-row and per-query logic can be checked against the oracle on a machine without a GPU.
+// It is NOT linked into libblu_consensus.so and is not a fallback: the kernel-side control flow (windows, row
+// index, run ownership, deferral, streaming) only exists in blu_kernels.cu and is tested on the GPU.
+#include <cstring>
+#include <string>
+#include <unordered_set>
+#include <vector>
+
+#include "../../blutils_b200/csrc/blu_core.cuh"
+#include "../../blutils_b200/csrc/blu_decode.h"
+#include "../../blutils_b200/csrc/blu_taxonomy.h"
+
+using namespace blu;
+
+static int map_err(uint32_t e) {
+    if (e == DE_NONE) return BLU_OK;
+    if (e >= DE_INTERNAL) return BLU_ERR_INTERNAL;
+    if (e >= DE_NUM_UNSUPPORTED) return BLU_ERR_UNSUPPORTED;
+    return BLU_ERR_DATA;
+}
+
+extern "C" int blu_sim_run(const int64_t* taxids, const uint64_t* off, const char* blob, uint64_t n, int taxon, int has_custom,
+                           const int32_t* custom8, int strategy, const char* text, uint64_t nbytes, const char* headers_nl, uint64_t headers_len,
+                           char** out, uint64_t* out_len, char* err, int errlen) {
+    try {
+        Cutoffs cut;
+        cut.taxon = taxon;
+        cut.has_custom = has_custom != 0;
+        if (has_custom)
+            for (int i = 0; i < 8; i++) cut.custom[i] = custom8[i];
+        HostTaxonomy T;
+        build_taxonomy(taxids, off, blob, n, cut, T);
+        LinTables L{};
+        L.lin_off = T.lin_off.data();
+        L.lvl_key = T.lvl_key.data();
+        L.bean_key = T.bean_key.data();
+        L.ident_rank = T.ident_rank.data();
+        L.cut = T.cut.data();
+        L.rank_cls = T.rank_cls.data();
+        L.allowed_cls = T.allowed_cls.data();
+        L.lin_ok = T.lin_ok.data();
+        L.slots = T.slots.data();
+        L.hash_mask = T.hash_mask;
+        L.n_lin = (uint32_t)T.n_lin();
+        if (nbytes == 0) throw DataErr("empty blast output");
+        const uint8_t* tx = (const uint8_t*)text;
+        struct R {
+            uint64_t s;
+            int len;
+            int64_t bits;
+            int qlen;
+        };
+        std::vector<R> rows;
+        for (uint64_t p = 0; p < nbytes;) {
+            const void* nl = memchr(tx + p, '\n', nbytes - p);
+            uint64_t e = nl ? (uint64_t)((const uint8_t*)nl - tx) : nbytes;
+            if (e > p) {
+                LightRow lr = light_parse_row(tx + p, (int)(e - p));
+                if (lr.err) {
+                    snprintf(err, errlen, "device error %u at byte %llu", lr.err, (unsigned long long)p);
+                    return map_err(lr.err);
+                }
+                rows.push_back({p, (int)(e - p), lr.bits, lr.q_len});
+            }
+            p = e + 1;
+        }
+        if (rows.empty()) throw DataErr("no rows");
+        std::vector<blu_record> recs;
+        std::vector<blu_bean> beans;
+        std::vector<blu_acc> accs;
+        std::unordered_set<std::string> seen;
+        std::vector<TopRow> top;
+        std::vector<uint16_t> scratch;
+        for (size_t h = 0; h < rows.size();) {
+            size_t e = h + 1;
+            while (e < rows.size() && rows[e].qlen == rows[h].qlen && !memcmp(tx + rows[e].s, tx + rows[h].s, rows[h].qlen)) e++;
+            if (!seen.insert(std::string((const char*)tx + rows[h].s, rows[h].qlen)).second) {
+                snprintf(err, errlen, "non-contiguous query");
+                return BLU_ERR_UNSUPPORTED;
+            }
+            int64_t mx = rows[h].bits;
+            for (size_t r = h; r < e; r++) mx = std::max(mx, rows[r].bits);
+            top.clear();
+            for (size_t r = h; r < e; r++)
+                if (rows[r].bits == mx) {
+                    TopRow t;
+                    uint32_t er = heavy_parse_row(tx + rows[r].s, rows[r].len, rows[r].s, L, t);
+                    if (er) {
+                        snprintf(err, errlen, "device error %u at byte %llu", er, (unsigned long long)rows[r].s);
+                        return map_err(er);
+                    }
+                    top.push_back(t);
+                }
+            const size_t g = top.size();
+            if (g > 1024) return BLU_ERR_UNSUPPORTED;
+            blu_record rec;
+            memset(&rec, 0, sizeof rec);
+            rec.query_off = rows[h].s;
+            rec.query_len = (uint32_t)rows[h].qlen;
+            rec.n_rows = (uint32_t)(e - h);
+            rec.bit_score = mx;
+            rec.slot_base = (uint32_t)beans.size();
+            beans.resize(beans.size() + g);
+            accs.resize(accs.size() + g);
+            scratch.assign(5 * g, 0);
+            QueryOut qo{&rec, beans.data() + rec.slot_base, accs.data() + rec.slot_base};
+            uint32_t ce = g == 1 ? consensus_single(top[0], L, qo) : consensus_multi(top.data(), (int)g, tx, L, strategy, scratch.data(), qo);
+            if (ce) {
+                snprintf(err, errlen, "device error %u in query at byte %llu", ce, (unsigned long long)rows[h].s);
+                return map_err(ce);
+            }
+            recs.push_back(rec);
+            h = e;
+        }
+        std::vector<std::string> hitless;
+        if (headers_nl) {
+            std::unordered_set<std::string> have;
+            for (auto& rc : recs) have.insert(std::string(text + rc.query_off, rc.query_len));
+            const char* p = headers_nl;
+            const char* e = headers_nl + headers_len;
+            while (p < e) {
+                const char* nl = (const char*)memchr(p, '\n', e - p);
+                const char* le = nl ? nl : e;
+                std::string hd(p, le - p);
+                if (!have.count(hd)) hitless.push_back(hd);
+                p = le + 1;
+            }
+        }
+        ResultView v;
+        v.tax = &T;
+        v.cut = cut;
+        v.rec_ = recs.data();
+        v.beans_ = beans.data();
+        v.accs_ = accs.data();
+        v.pool_ = text;
+        v.n_rec = recs.size();
+        v.hitless_ = &hitless;
+        std::string js = view_to_jsonl(&v);
+        *out = (char*)malloc(js.size() + 1);
+        memcpy(*out, js.data(), js.size());
+        (*out)[js.size()] = 0;
+        *out_len = js.size();
+        return BLU_OK;
+    } catch (const DataErr& e) {
+        snprintf(err, errlen, "%s", e.what());
+        return BLU_ERR_DATA;
+    } catch (const std::invalid_argument& e) {
+        snprintf(err, errlen, "%s", e.what());
+        return BLU_ERR_UNSUPPORTED;
+    } catch (const std::exception& e) {
+        snprintf(err, errlen, "%s", e.what());
+        return BLU_ERR_INTERNAL;
+    }
+}
+
+extern "C" void blu_sim_free(char* p) { free(p); }
+
+// interpolation of the product's taxonomy encoder, for the KAT vectors
+extern "C" int blu_sim_interpolate(const char* ranks_nl, int taxon, int has_custom, const int32_t* custom8, double* out, int cap) {
+    try {
+        Cutoffs cut;
+        cut.taxon = taxon;
+        cut.has_custom = has_custom != 0;
+        if (has_custom)
+            for (int i = 0; i < 8; i++) cut.custom[i] = custom8[i];
+        auto bb = make_backbone(cut);
+        std::vector<RankInfo> rk;
+        std::string s(ranks_nl);
+        size_t pos = 0;
+        while (true) {
+            size_t k = s.find('\n', pos);
+            rk.push_back(rank_from_str(s.substr(pos, k == std::string::npos ? std::string::npos : k - pos)));
+            if (k == std::string::npos) break;
+            pos = k + 1;
+        }
+        std::vector<const RankInfo*> ptr;
+        for (auto& r : rk) ptr.push_back(&r);
+        auto v = interpolate_cutoffs(ptr, bb);
+        if ((int)v.size() > cap) return -1;
+        for (size_t i = 0; i < v.size(); i++) out[i] = v[i];
+        return (int)v.size();
+    } catch (...) {
+        return -2;
+    }
+}
+
+// custom cutoff file parser of the product
+extern "C" int blu_sim_custom_cutoffs(const char* path, int32_t* out8, char* err, int errlen) {
+    try {
+        Cutoffs c;
+        read_custom_cutoffs(path, c);
+        for (int i = 0; i < 8; i++) out8[i] = c.custom[i];
+        return 0;
+    } catch (const std::exception& e) {
+        snprintf(err, errlen, "%s", e.what());
+        return 2;
+    }
+}
+
+// taxonomy JSON reader of the product: returns number of taxa, or -1 (I/O class error)
+extern "C" long long blu_sim_read_taxonomy_json(const char* path, int use_taxid, char* err, int errlen) {
+    try {
+        std::vector<int64_t> ids;
+        std::vector<uint64_t> off;
+        std::string blob;
+        read_taxonomy_json(path, use_taxid != 0, ids, off, blob);
+        return (long long)ids.size();
+    } catch (const std::exception& e) {
+        snprintf(err, errlen, "%s", e.what());
+        return -1;
+    }
+}
