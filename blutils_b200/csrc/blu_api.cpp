@@ -13,6 +13,7 @@
 #include <filesystem>
 #include <fstream>
 #include <memory>
+#include <mutex>
 #include <random>
 #include <string>
 #include <string_view>
@@ -69,6 +70,52 @@ struct PinnedBuf {
     size_t cap = 0;
 };
 
+// Pinned result buffers are recycled between runs.  The pool is shared by the context and every result it
+// produced, so a result may be freed after its context.
+struct PinnedPool {
+    std::mutex mu;
+    std::vector<PinnedBuf> free_list;
+    bool closed = false;
+    PinnedBuf acquire(size_t bytes) {
+        {
+            std::lock_guard<std::mutex> g(mu);
+            size_t best = SIZE_MAX;
+            for (size_t i = 0; i < free_list.size(); i++)
+                if (free_list[i].cap >= bytes && (best == SIZE_MAX || free_list[i].cap < free_list[best].cap)) best = i;
+            if (best != SIZE_MAX) {
+                PinnedBuf b = free_list[best];
+                free_list.erase(free_list.begin() + best);
+                return b;
+            }
+        }
+        PinnedBuf b;
+        size_t cap = std::max<size_t>(bytes + bytes / 8, 4096);
+        CK(cudaHostAlloc(&b.p, cap, cudaHostAllocDefault));
+        b.cap = cap;
+        return b;
+    }
+    void release(PinnedBuf b) {
+        if (!b.p) return;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            if (!closed && free_list.size() < 16) {
+                free_list.push_back(b);
+                return;
+            }
+        }
+        cudaFreeHost(b.p);
+    }
+    void close() {
+        std::vector<PinnedBuf> v;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            closed = true;
+            v.swap(free_list);
+        }
+        for (auto& b : v) cudaFreeHost(b.p);
+    }
+};
+
 }  // namespace
 
 struct blu_ctx {
@@ -97,38 +144,16 @@ struct blu_ctx {
     DevBuf<unsigned long long> d_dup;
     Counters* d_ctr = nullptr;
     Counters* h_ctr = nullptr;  // pinned
-    std::vector<PinnedBuf> pinned_free;
+    std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
     std::string err;
     blu_timings tm{};
     uint64_t carry_bytes = 64ull << 20;
 
-    PinnedBuf acquire(size_t bytes) {
-        size_t best = SIZE_MAX;
-        for (size_t i = 0; i < pinned_free.size(); i++)
-            if (pinned_free[i].cap >= bytes && (best == SIZE_MAX || pinned_free[i].cap < pinned_free[best].cap)) best = i;
-        if (best != SIZE_MAX) {
-            PinnedBuf b = pinned_free[best];
-            pinned_free.erase(pinned_free.begin() + best);
-            return b;
-        }
-        PinnedBuf b;
-        size_t cap = std::max<size_t>(bytes, 4096);
-        CK(cudaHostAlloc(&b.p, cap, cudaHostAllocDefault));
-        b.cap = cap;
-        return b;
-    }
-    void release(PinnedBuf b) {
-        if (!b.p) return;
-        if (pinned_free.size() >= 16) {
-            cudaFreeHost(b.p);
-            return;
-        }
-        pinned_free.push_back(b);
-    }
+    PinnedBuf acquire(size_t bytes) { return pool->acquire(bytes); }
 };
 
 struct blu_result {
-    blu_ctx* ctx = nullptr;
+    std::shared_ptr<PinnedPool> pinned;
     std::shared_ptr<HostTaxonomy> tax;
     Cutoffs cut;
     PinnedBuf b_rec, b_beans, b_accs, b_pool;
@@ -598,7 +623,7 @@ void blu_ctx_destroy(blu_ctx* c) {
     c->d_defer.release(), c->d_pool.release(), c->d_dup.release();
     if (c->d_ctr) cudaFree(c->d_ctr);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
-    for (auto& b : c->pinned_free) cudaFreeHost(b.p);
+    c->pool->close();
     for (auto& e : c->ev)
         if (e) cudaEventDestroy(e);
     for (auto& e : c->ev_h2d)
@@ -650,7 +675,7 @@ int blu_consensus_run_device(blu_ctx* c, const void* dtext, uint64_t n, void* st
     if (!c || !out || (!dtext && n)) return fail(c, BLU_ERR_ARG, "null argument");
     *out = nullptr;
     auto r = std::make_unique<blu_result>();
-    r->ctx = c;
+    r->pinned = c->pool;
     int rc = guarded(c, [&] {
         CK(cudaSetDevice(c->device));
         r->tax = c->tax;
@@ -669,7 +694,7 @@ int blu_consensus_run_host(blu_ctx* c, const char* text, uint64_t n, blu_result*
     if (!c || !out || (!text && n)) return fail(c, BLU_ERR_ARG, "null argument");
     *out = nullptr;
     auto r = std::make_unique<blu_result>();
-    r->ctx = c;
+    r->pinned = c->pool;
     int rc = guarded(c, [&] {
         CK(cudaSetDevice(c->device));
         r->tax = c->tax;
@@ -767,11 +792,11 @@ int blu_result_write(const blu_result* r, const char* path, int format, const ch
 
 void blu_result_free(blu_result* r) {
     if (!r) return;
-    if (r->ctx) {
-        r->ctx->release(r->b_rec);
-        r->ctx->release(r->b_beans);
-        r->ctx->release(r->b_accs);
-        r->ctx->release(r->b_pool);
+    if (r->pinned) {
+        r->pinned->release(r->b_rec);
+        r->pinned->release(r->b_beans);
+        r->pinned->release(r->b_accs);
+        r->pinned->release(r->b_pool);
     }
     delete r;
 }
