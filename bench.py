@@ -220,12 +220,12 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
 
     # ---------------- device-resident arm -------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()  # spans warm-up + timed region; the median is taken over samples under load
     for _ in range(args.warmup):
         eng.run_device(dbuf.data_ptr(), nbytes, stream).close()
-    sampler = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
-        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tile_ms, long_ms, gather_ms, launches = [], [], [], 0
     nq = 0

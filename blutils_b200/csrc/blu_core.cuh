@@ -296,6 +296,99 @@ BLU_HD LightRow light_parse_row(const uint8_t* p, int len) {
     return r;
 }
 
+// ---- one row, through the byte-class bitmasks -----------------------------------------------------------------
+// The row scan classifies every byte of the window once (tab / digit bitmasks, bit i = byte i of the window);
+// a row is then validated with bit operations in a 13-iteration loop that every lane walks in lockstep (field k of
+// all 32 rows at the same time), instead of a data-dependent per-byte state machine.
+// `tabw` / `digw` must be readable one word past the row.
+BLU_HD int blu_ctz64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __ffsll((long long)x) - 1;
+#else
+    return __builtin_ctzll(x);
+#endif
+}
+
+// first tab at position >= cur and < e, or e
+BLU_HD int next_tab(const uint64_t* tabw, int cur, int e) {
+    int w = cur >> 6;
+    uint64_t bits = tabw[w] >> (cur & 63);
+    if (bits) {
+        int p = cur + blu_ctz64(bits);
+        return p < e ? p : e;
+    }
+    for (w++; (w << 6) < e; w++) {
+        bits = tabw[w];
+        if (bits) {
+            int p = (w << 6) + blu_ctz64(bits);
+            return p < e ? p : e;
+        }
+    }
+    return e;
+}
+
+// bytes [a, a+len) are all ASCII digits (1 <= len <= 32)
+BLU_HD bool all_digits(const uint64_t* digw, int a, int len) {
+    const int sh = a & 63;
+    uint64_t x = digw[a >> 6] >> sh;
+    if (sh > 32) x |= digw[(a >> 6) + 1] << (64 - sh);
+    const uint32_t m = len >= 32 ? 0xFFFFFFFFu : ((1u << len) - 1u);
+    return ((uint32_t)x & m) == m;
+}
+
+BLU_HD LightRow parse_row_masked(const uint8_t* win, const uint64_t* tabw, const uint64_t* digw, int s, int e) {
+    LightRow r;
+    r.bits = 0;
+    r.q_len = 0;
+    uint32_t err = DE_NONE;
+    int cur = s;
+    for (int k = 0; k < 13; k++) {
+        const int t = k < 12 ? next_tab(tabw, cur, e) : e;
+        if (k < 12 && t >= e) {  // ran out of tabs
+            if (!err) err = DE_BAD_FIELD_COUNT;
+            break;
+        }
+        const int len = t - cur;
+        if (k <= 1) {
+            if (len == 0 && !err) err = DE_EMPTY_STRING;
+            if (k == 0) r.q_len = (uint16_t)(len > 65535 ? 65535 : len);
+        } else if (k == 3 || k == 11) {
+            // pident / evalue: grammar only here (pident's value is parsed again for the top rows)
+            if (!check_float(win + cur, len) && !err) err = DE_BAD_NUMBER;
+        } else if (k == 12) {
+            if (next_tab(tabw, cur, e) < e) {  // a 14th field
+                if (!err) err = DE_BAD_FIELD_COUNT;
+            } else {
+                double d;
+                uint32_t pe = parse_f64(win + cur, len, d);
+                if (pe) {
+                    if (!err) err = pe;
+                } else if (!(d > -9223372036854775808.0 && d < 9223372036854775808.0)) {
+                    if (!err) err = DE_BITS_RANGE;
+                } else
+                    r.bits = (int64_t)d;
+            }
+        } else {
+            // integer column: the common case is 1..18 digits, checked on the digit mask
+            const bool fast = len >= 1 && len <= 18 && all_digits(digw, cur, len);
+            if (!fast && !check_int(win + cur, len) && !err) err = DE_BAD_NUMBER;
+        }
+        cur = t + 1;
+    }
+    r.err = err;
+    return r;
+}
+
+// first fields (qseqid) of the rows starting at a and b are equal; both rows are known to contain a tab
+BLU_HD bool same_first_field(const uint8_t* win, const uint64_t* tabw, int a, int ea, int b, int eb) {
+    const int la = next_tab(tabw, a, ea) - a;
+    const int lb = next_tab(tabw, b, eb) - b;
+    if (la != lb) return false;
+    for (int i = 0; i < la; i++)
+        if (win[a + i] != win[b + i]) return false;
+    return true;
+}
+
 // ---- top-group rows ---------------------------------------------------------------------------------------------
 struct TopRow {
     double pident;

@@ -14,6 +14,8 @@
 // Reference semantics: see blu_core.cuh.  Geometry and roofline accounting: DESIGN.md.
 #include <cuda_runtime.h>
 
+#include <climits>
+
 #include "blu_kernels.h"
 
 namespace blu {
@@ -64,12 +66,18 @@ __device__ __forceinline__ void report(Counters* ctr, uint32_t err, unsigned lon
 // ---------------------------------------------------------------------------------------------------------------
 // shared-memory window + row index (used by both kernels)
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int kChunks = (kWin + 128) / 16;  // 16-byte chunks of the window (incl. the spare tail)
+
 struct WindowIndex {
     alignas(128) uint8_t win[kWin + 128];
+    // byte-class bitmasks, one bit per window byte (u16 per 16-byte chunk; read back as 64-bit words)
+    alignas(8) uint16_t tabm[kChunks + 8];
+    alignas(8) uint16_t digm[kChunks + 8];
     uint16_t row_s[kRowCap];
     uint16_t row_e[kRowCap + 1];
     alignas(8) unsigned long long mbar;
     int n_starts, n_ends;
+    int bad_byte;  // window offset of the first '"' / '\r' byte inside [qlo, qhi), or INT_MAX
     int warp_cnt[16];
 };
 
@@ -80,6 +88,7 @@ struct WinGeom {
     int loaded;             // bytes staged
     int L;                  // bytes scanned (text end + optional virtual newline)
     bool covers_eof;        // the window contains the end of the text
+    int qlo, qhi;           // window range in which a '"' / '\r' byte is this CTA's to report
 };
 
 // Stage [lo, lo+bytes) of the text into the window with TMA bulk copies.  All threads call; returns when the
@@ -112,16 +121,25 @@ __device__ __forceinline__ WinGeom make_geom(unsigned long long lo, int max_byte
     g.re = re > (long long)kWin + 64 ? kWin + 64 : (int)re;
     g.covers_eof = end <= lo + (unsigned long long)g.loaded;
     g.L = g.re < g.loaded ? g.re : g.loaded;
+    g.qlo = g.rb < 0 ? 0 : g.rb;
+    g.qhi = g.L;
     return g;
 }
 
-// 16-bit mask of bytes equal to `c` in a 16-byte chunk
-__device__ __forceinline__ uint32_t eq_mask16(const uint4& v, uint32_t c4) {
-    uint32_t a = (__vcmpeq4(v.x, c4) & 0x01010101u) * 0x01020408u >> 24;
-    uint32_t b = (__vcmpeq4(v.y, c4) & 0x01010101u) * 0x01020408u >> 24;
-    uint32_t c = (__vcmpeq4(v.z, c4) & 0x01010101u) * 0x01020408u >> 24;
-    uint32_t d = (__vcmpeq4(v.w, c4) & 0x01010101u) * 0x01020408u >> 24;
-    return (a & 15u) | ((b & 15u) << 4) | ((c & 15u) << 8) | ((d & 15u) << 12);
+// SIMD-in-register byte classification: 0x80 in every byte of the result where the predicate holds
+__device__ __forceinline__ uint32_t bytes_eq(uint32_t x, uint32_t c4) {
+    uint32_t t = x ^ c4;  // zero byte <=> equal
+    return ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u;
+}
+__device__ __forceinline__ uint32_t bytes_digit(uint32_t x) {
+    uint32_t t = x ^ 0x30303030u;  // '0'..'9' -> 0..9
+    return ~(((t & 0x7F7F7F7Fu) + 0x76767676u) | t) & 0x80808080u;
+}
+// gathers the four 0x80 flags of a word into its low nibble
+__device__ __forceinline__ uint32_t pack4(uint32_t m) { return ((m >> 7) * 0x01020408u) >> 24; }
+
+__device__ __forceinline__ uint32_t pack16(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    return (pack4(a) & 15u) | ((pack4(b) & 15u) << 4) | ((pack4(c) & 15u) << 8) | ((pack4(d) & 15u) << 12);
 }
 
 __device__ __forceinline__ uint32_t range_mask16(int pos0, int lo, int hi) {  // bits k with lo <= pos0+k < hi
@@ -132,12 +150,27 @@ __device__ __forceinline__ uint32_t range_mask16(int pos0, int lo, int hi) {  //
     return ((1u << b) - 1u) & ~((1u << a) - 1u);
 }
 
-// row starts / row ends inside chunk c (see DESIGN.md "row index")
-__device__ __forceinline__ void chunk_masks(const WindowIndex& W, const WinGeom& g, int c, uint32_t& start, uint32_t& end) {
+// Classifies chunk c: row starts / row ends (see DESIGN.md "row index"); when STORE, also publishes the tab and
+// digit masks of the chunk and flags '"' / '\r' bytes.
+template <bool STORE>
+__device__ __forceinline__ void chunk_masks(WindowIndex& W, const WinGeom& g, int c, uint32_t& start, uint32_t& end) {
     const int pos0 = c << 4;
     const uint4 v = *reinterpret_cast<const uint4*>(W.win + pos0);
     const int rb = g.rb < 0 ? 0 : g.rb;
-    uint32_t nl = eq_mask16(v, 0x0A0A0A0Au) & range_mask16(pos0, rb, g.L);
+    const uint32_t valid = range_mask16(pos0, rb, g.L);
+    uint32_t nl = pack16(bytes_eq(v.x, 0x0A0A0A0Au), bytes_eq(v.y, 0x0A0A0A0Au), bytes_eq(v.z, 0x0A0A0A0Au), bytes_eq(v.w, 0x0A0A0A0Au)) & valid;
+    if (STORE) {
+        W.tabm[c] = (uint16_t)pack16(bytes_eq(v.x, 0x09090909u), bytes_eq(v.y, 0x09090909u), bytes_eq(v.z, 0x09090909u), bytes_eq(v.w, 0x09090909u));
+        W.digm[c] = (uint16_t)pack16(bytes_digit(v.x), bytes_digit(v.y), bytes_digit(v.z), bytes_digit(v.w));
+        const uint32_t q = (bytes_eq(v.x, 0x22222222u) | bytes_eq(v.x, 0x0D0D0D0Du)) | (bytes_eq(v.y, 0x22222222u) | bytes_eq(v.y, 0x0D0D0D0Du)) |
+                           (bytes_eq(v.z, 0x22222222u) | bytes_eq(v.z, 0x0D0D0D0Du)) | (bytes_eq(v.w, 0x22222222u) | bytes_eq(v.w, 0x0D0D0D0Du));
+        if (q) {
+            const uint32_t qm = pack16(bytes_eq(v.x, 0x22222222u) | bytes_eq(v.x, 0x0D0D0D0Du), bytes_eq(v.y, 0x22222222u) | bytes_eq(v.y, 0x0D0D0D0Du),
+                                       bytes_eq(v.z, 0x22222222u) | bytes_eq(v.z, 0x0D0D0D0Du), bytes_eq(v.w, 0x22222222u) | bytes_eq(v.w, 0x0D0D0D0Du)) &
+                                range_mask16(pos0, g.qlo, g.qhi);
+            if (qm) atomicMin(&W.bad_byte, pos0 + __ffs(qm) - 1);
+        }
+    }
     uint32_t carry;
     if (g.rb >= 0 && pos0 == g.rb)
         carry = 1;  // virtual newline in front of the text
@@ -165,7 +198,7 @@ __device__ bool scan_rows(WindowIndex& W, const WinGeom& g) {
         int c = base + lane;
         if (c < c1) {
             uint32_t s, e;
-            chunk_masks(W, g, c, s, e);
+            chunk_masks<true>(W, g, c, s, e);
             cnt += __popc(s) | (__popc(e) << 16);
         }
     }
@@ -195,7 +228,7 @@ __device__ bool scan_rows(WindowIndex& W, const WinGeom& g) {
     for (int base = c0; base < c1; base += 32) {
         int c = base + lane;
         uint32_t s = 0, e = 0;
-        if (c < c1) chunk_masks(W, g, c, s, e);
+        if (c < c1) chunk_masks<false>(W, g, c, s, e);
         int mine = __popc(s) | (__popc(e) << 16);
         int inc = mine;
 #pragma unroll
@@ -253,6 +286,8 @@ struct TileSmem {
     uint16_t runs[kMaxRuns];
     WarpScratch ws[kWarps];
     int n_runs;
+    int first_head;  // lowest row index that heads a run owned by this tile
+    int fwd_limit;   // first head at/after the end of the tile (rows from there on belong to the next tile)
 };
 
 static_assert(sizeof(TileSmem) <= 113 * 1024, "two tile CTAs must fit one SM");
@@ -285,9 +320,19 @@ __global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(const __grid_cons
         const int max_bytes = (int)(base + kTile + kFwd - lo);
         WinGeom g = make_geom(lo, max_bytes, p.begin, p.end);
         if (g.loaded <= 0) continue;
+        if (tid == 0) {
+            W.bad_byte = INT_MAX;
+            S.n_runs = 0;
+            S.first_head = 0x7fffffff;
+            S.fwd_limit = 0x7fffffff;
+        }
+        const unsigned long long own_lo = base, own_hi = base + kTile;
+        // every text byte lies in exactly one tile's [own_lo, own_hi): that tile reports a '"' / '\r' in it
+        g.qlo = own_lo > lo ? (int)(own_lo - lo) : 0;
+        if (g.rb > g.qlo) g.qlo = g.rb;
+        g.qhi = (int)(own_hi - lo) < g.L ? (int)(own_hi - lo) : g.L;
         load_window(W, p.text, lo, g.loaded, phase);
         finish_geom(W, g, p.final_chunk != 0);
-        if (tid == 0) S.n_runs = 0;
         if (!scan_rows<kWarps>(W, g)) {
             if (tid == 0) report(p.ctr, DE_BAD_FIELD_COUNT, lo);
             continue;
@@ -296,54 +341,53 @@ __global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(const __grid_cons
         const int eskip = (n_ends > 0 && (n_starts == 0 || W.row_e[0] < W.row_s[0])) ? 1 : 0;
         const int ncomplete = n_starts < n_ends - eskip ? n_starts : n_ends - eskip;
         const bool has_partial = n_starts > ncomplete;
-        const unsigned long long own_lo = base, own_hi = base + kTile;
+        const uint64_t* tabw = reinterpret_cast<const uint64_t*>(W.tabm);
+        const uint64_t* digw = reinterpret_cast<const uint64_t*>(W.digm);
+        if (W.bad_byte != INT_MAX && tid == 0) report(p.ctr, DE_QUOTE_OR_CR, lo + (unsigned)W.bad_byte);
 
-        // ---- phase B: every complete row: validate, bit score, head flag ----------------------------------
+        // ---- phase B0: head flags of the rows at/after the tile start; run list ------------------------------
+        // (rows before own_lo belong to runs of the previous tile; only the last one is needed, as predecessor)
         for (int r = tid; r < ncomplete; r += kTileThreads) {
             const int s = W.row_s[r];
-            const int len = (int)W.row_e[r + eskip] - s;
-            const uint8_t* q = W.win + s;
-            LightRow lr = light_parse_row(q, len);
-            if (lr.err) report(p.ctr, lr.err, lo + s);
+            const unsigned long long abs = lo + s;
             uint8_t fl = 0;
-            int32_t b32 = (int32_t)lr.bits;
-            if ((int64_t)b32 != lr.bits) fl |= 2;
-            if (r == 0) {
-                if (g.rb >= 0 && s == g.rb) fl |= 1;  // first row of the text
-            } else {
-                const uint8_t* pq = W.win + W.row_s[r - 1];
-                const int plen = (int)W.row_e[r - 1 + eskip] - (int)W.row_s[r - 1];
-                const int n = len < plen ? len : plen;
-                bool same = false;
-                for (int i = 0; i < n; i++) {
-                    uint8_t a = q[i];
-                    if (a != pq[i]) break;
-                    if (a == '\t') {
-                        same = true;
-                        break;
-                    }
+            if (abs >= own_lo) {
+                bool head;
+                if (r == 0)
+                    head = g.rb >= 0 && s == g.rb;  // first row of the text (else: predecessor not in the window)
+                else
+                    head = !same_first_field(W.win, tabw, W.row_s[r - 1], W.row_e[r - 1 + eskip], s, W.row_e[r + eskip]);
+                if (head) {
+                    fl = 1;
+                    if (abs < own_hi) {
+                        int i = atomicAdd(&S.n_runs, 1);
+                        S.runs[i] = (uint16_t)r;
+                        atomicMin(&S.first_head, r);
+                    } else
+                        atomicMin(&S.fwd_limit, r);  // first run of the next tile: nothing beyond it is ours
+                } else if (r == 0 && abs < own_hi) {
+                    push_defer(p, abs, 1);  // predecessor not in the window: the block path decides whether it is a head
                 }
-                if (!same) fl |= 1;
             }
-            S.bits[r] = b32;
             S.flags[r] = fl;
-        }
-        __syncthreads();
-        // ---- phase C: runs owned by this tile ------------------------------------------------------------------
-        for (int r = tid; r < ncomplete; r += kTileThreads) {
-            const unsigned long long abs = lo + W.row_s[r];
-            const bool owned = abs >= own_lo && abs < own_hi;
-            if (!owned) continue;
-            if (S.flags[r] & 1) {
-                int i = atomicAdd(&S.n_runs, 1);
-                S.runs[i] = (uint16_t)r;
-            } else if (r == 0) {
-                push_defer(p, abs, 1);  // predecessor not in the window: the block path decides whether it is a head
-            }
         }
         if (tid == 0 && has_partial) {
             const unsigned long long abs = lo + W.row_s[ncomplete];
             if (abs >= own_lo && abs < own_hi) push_defer(p, abs, 1);  // unterminated row: the block path sorts it out
+        }
+        __syncthreads();
+        // ---- phase B1: validate + bit score of the rows of the runs this tile owns ----------------------------
+        {
+            const int r1 = S.fwd_limit < ncomplete ? S.fwd_limit : ncomplete;
+            const int r0 = S.first_head < r1 ? S.first_head : r1;  // no owned head: nothing to do
+            for (int r = r0 + tid; r < r1; r += kTileThreads) {
+                const int s = W.row_s[r];
+                LightRow lr = parse_row_masked(W.win, tabw, digw, s, W.row_e[r + eskip]);
+                if (lr.err) report(p.ctr, lr.err, lo + s);
+                const int32_t b32 = (int32_t)lr.bits;
+                if ((int64_t)b32 != lr.bits) S.flags[r] |= 2;
+                S.bits[r] = b32;
+            }
         }
         __syncthreads();
         // ---- phase D: one warp per run ----------------------------------------------------------------------------
@@ -437,8 +481,10 @@ __global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(const __grid_cons
                 rec->bit_score = (int64_t)mx;
                 rec->slot_base = slot;
                 rec->pad[0] = rec->pad[1] = 0;
+                // accession bytes are read from the shared-memory window (generic pointer rebased to buffer offsets)
+                const uint8_t* win_as_text = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(W.win) - (uintptr_t)lo);
                 uint32_t ce = gcount == 1 ? consensus_single(ws.rows[0], p.T, out)
-                                          : consensus_multi(ws.rows, gcount, p.text, p.T, p.strategy, ws.tmp, out);
+                                          : consensus_multi(ws.rows, gcount, win_as_text, p.T, p.strategy, ws.tmp, out);
                 if (ce) report(p.ctr, ce, h_abs);
             }
             __syncwarp();
@@ -489,6 +535,7 @@ __device__ LongScan long_scan(LongSmem& S, const RunParams& p, unsigned long lon
     LongScan r;
     const unsigned long long lo = cur & ~15ull;
     WinGeom g = make_geom(lo, kWin, cur, p.end);
+    if (threadIdx.x == 0) W.bad_byte = INT_MAX;
     load_window(W, p.text, lo, g.loaded, phase);
     finish_geom(W, g, p.final_chunk != 0);
     r.giant = false;
@@ -504,7 +551,7 @@ __device__ LongScan long_scan(LongSmem& S, const RunParams& p, unsigned long lon
     for (int i = threadIdx.x; i < r.ncomplete; i += kLongThreads) {
         const int st = W.row_s[i];
         const int len = (int)W.row_e[i + r.eskip] - st;
-        LightRow lr = light_parse_row(W.win + st, len);
+        LightRow lr = parse_row_masked(W.win, reinterpret_cast<const uint64_t*>(W.tabm), reinterpret_cast<const uint64_t*>(W.digm), st, st + len);
         bool sm = same_query(W.win + st, len, p.text, s, p.end);
         if (lr.err && sm) report(p.ctr, lr.err, lo + st);
         S.bits[i] = lr.bits;
@@ -521,6 +568,11 @@ __device__ LongScan long_scan(LongSmem& S, const RunParams& p, unsigned long lon
     int d = r.ncomplete;
     for (int i = 0; i < kLongWarps; i++) d = S.red_first[i] < d ? S.red_first[i] : d;
     r.d = d;
+    if (W.bad_byte != INT_MAX && threadIdx.x == 0) {
+        // only bytes of this run's rows are ours to report
+        const int run_end = d < r.ncomplete ? (int)W.row_s[d] : (n_starts > r.ncomplete ? (int)W.row_s[r.ncomplete] : g.L);
+        if (W.bad_byte < run_end) report(p.ctr, DE_QUOTE_OR_CR, lo + (unsigned)W.bad_byte);
+    }
     if (n_starts > r.ncomplete) {
         r.next = lo + W.row_s[r.ncomplete];
         r.at_end = false;

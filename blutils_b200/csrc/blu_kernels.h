@@ -59,7 +59,7 @@ struct DupParams {
 };
 
 // Tile geometry of the fused kernel
-constexpr int kTile = 49152;   // bytes owned by one tile
+constexpr int kTile = 40960;   // bytes owned by one tile
 constexpr int kBack = 1024;    // look-behind so the tile's first row can be compared with its predecessor
 constexpr int kFwd = 12288;    // look-ahead so a query that starts in the tile can finish in the window
 constexpr int kWin = kBack + kTile + kFwd;

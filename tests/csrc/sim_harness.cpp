@@ -54,11 +54,27 @@ extern "C" int blu_sim_run(const int64_t* taxids, const uint64_t* off, const cha
             int qlen;
         };
         std::vector<R> rows;
+        // byte-class bitmasks exactly as the row scan of the kernels publishes them (bit i = byte i)
+        std::vector<uint64_t> tabw(nbytes / 64 + 3, 0), digw(nbytes / 64 + 3, 0);
+        for (uint64_t i = 0; i < nbytes; i++) {
+            if (tx[i] == '\t') tabw[i >> 6] |= 1ull << (i & 63);
+            if (tx[i] >= '0' && tx[i] <= '9') digw[i >> 6] |= 1ull << (i & 63);
+            if (tx[i] == '"' || tx[i] == '\r') {
+                snprintf(err, errlen, "device error %u at byte %llu", (unsigned)DE_QUOTE_OR_CR, (unsigned long long)i);
+                return map_err(DE_QUOTE_OR_CR);
+            }
+        }
+        if (nbytes > 0x7fffff00ull) throw std::invalid_argument("sim: text too large");
         for (uint64_t p = 0; p < nbytes;) {
             const void* nl = memchr(tx + p, '\n', nbytes - p);
             uint64_t e = nl ? (uint64_t)((const uint8_t*)nl - tx) : nbytes;
             if (e > p) {
-                LightRow lr = light_parse_row(tx + p, (int)(e - p));
+                LightRow lr = parse_row_masked(tx, tabw.data(), digw.data(), (int)p, (int)e);
+                LightRow l2 = light_parse_row(tx + p, (int)(e - p));  // byte-wise variant must agree
+                if ((lr.err != 0) != (l2.err != 0) || (!lr.err && (lr.bits != l2.bits || lr.q_len != l2.q_len))) {
+                    snprintf(err, errlen, "masked and byte-wise row parsers disagree at byte %llu", (unsigned long long)p);
+                    return BLU_ERR_INTERNAL;
+                }
                 if (lr.err) {
                     snprintf(err, errlen, "device error %u at byte %llu", lr.err, (unsigned long long)p);
                     return map_err(lr.err);
@@ -76,7 +92,9 @@ extern "C" int blu_sim_run(const int64_t* taxids, const uint64_t* off, const cha
         std::vector<uint16_t> scratch;
         for (size_t h = 0; h < rows.size();) {
             size_t e = h + 1;
-            while (e < rows.size() && rows[e].qlen == rows[h].qlen && !memcmp(tx + rows[e].s, tx + rows[h].s, rows[h].qlen)) e++;
+            while (e < rows.size() && same_first_field(tx, tabw.data(), (int)rows[e - 1].s, (int)rows[e - 1].s + rows[e - 1].len, (int)rows[e].s,
+                                                       (int)rows[e].s + rows[e].len))
+                e++;
             if (!seen.insert(std::string((const char*)tx + rows[h].s, rows[h].qlen)).second) {
                 snprintf(err, errlen, "non-contiguous query");
                 return BLU_ERR_UNSUPPORTED;
