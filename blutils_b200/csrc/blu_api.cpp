@@ -139,6 +139,7 @@ struct blu_ctx {
     DevBuf<blu_record> d_rec;
     DevBuf<blu_bean> d_beans;
     DevBuf<blu_acc> d_accs;
+    DevBuf<TopRow> d_top;
     DevBuf<uint64_t> d_defer;
     DevBuf<uint8_t> d_pool;
     DevBuf<unsigned long long> d_dup;
@@ -261,6 +262,9 @@ struct Caps {
     size_t rec, slots, defer, pool;
 };
 
+inline uint64_t n_rec_of(const Counters& h) { return h.rec_slots >> 32; }
+inline uint64_t n_slots_of(const Counters& h) { return h.rec_slots & 0xFFFFFFFFull; }
+
 Caps initial_caps(uint64_t n_bytes) {
     Caps c;
     c.rec = n_bytes / 160 + 4096;
@@ -274,6 +278,7 @@ void ensure_out(blu_ctx* c, const Caps& k) {
     c->d_rec.ensure(k.rec);
     c->d_beans.ensure(k.slots);
     c->d_accs.ensure(k.slots);
+    c->d_top.ensure(k.slots);
     c->d_defer.ensure(k.defer);
     c->d_pool.ensure(k.pool);
 }
@@ -300,6 +305,7 @@ void launch_chunk(blu_ctx* c, const uint8_t* dtext, uint64_t begin, uint64_t end
     p.rec_cap = (uint32_t)std::min<size_t>(k.rec, 0xFFFFFFFFu);
     p.beans = c->d_beans.p;
     p.accs = c->d_accs.p;
+    p.toprows = c->d_top.p;
     p.slot_cap = (uint32_t)std::min<size_t>(k.slots, 0xFFFFFFFFu);
     p.defer = c->d_defer.p;
     p.defer_cap = (uint32_t)std::min<size_t>(k.defer, 0xFFFFFFFFu);
@@ -325,10 +331,9 @@ void reset_counters_async(blu_ctx* c, cudaStream_t s, bool whole) {
 }
 
 void finish_result(blu_ctx* c, const Counters& h, cudaStream_t s, blu_result* r) {
-    r->n_rec = h.n_rec;
-    r->n_slots = h.n_slots;
+    r->n_rec = n_rec_of(h);
+    r->n_slots = n_slots_of(h);
     r->pool_len = h.pool_used;
-    r->n_rows = h.n_rows;
     r->b_rec = c->acquire(std::max<size_t>(r->n_rec * sizeof(blu_record), 64));
     r->b_beans = c->acquire(std::max<size_t>(r->n_slots * sizeof(blu_bean), 64));
     r->b_accs = c->acquire(std::max<size_t>(r->n_slots * sizeof(blu_acc), 64));
@@ -340,6 +345,12 @@ void finish_result(blu_ctx* c, const Counters& h, cudaStream_t s, blu_result* r)
     }
     if (r->pool_len) CK(cudaMemcpyAsync(r->b_pool.p, c->d_pool.p, r->pool_len, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    {
+        uint64_t rows = 0;
+        const blu_record* rc = r->rec();
+        for (uint64_t i = 0; i < r->n_rec; i++) rows += rc[i].n_rows;
+        r->n_rows = rows;
+    }
     c->tm.d2h_bytes += r->n_rec * sizeof(blu_record) + r->n_slots * (sizeof(blu_bean) + sizeof(blu_acc)) + r->pool_len + sizeof(Counters);
     c->tm.result_bytes = r->n_rec * sizeof(blu_record) + r->n_slots * (sizeof(blu_bean) + sizeof(blu_acc));
     c->tm.n_queries = r->n_rec;
@@ -354,6 +365,22 @@ float ev_ms(cudaEvent_t a, cudaEvent_t b) {
 
 // Post-pass on all records of the run: string gather for [rec_begin, rec_end) + (at the end) duplicate check.
 void launch_gather(blu_ctx* c, const uint8_t* dtext, uint32_t rec_begin, uint32_t rec_end, const Caps& k, cudaStream_t s) {
+    {
+        // warp-per-query consensus over the top-row table the tile kernel produced for these records
+        ConsParams q{};
+        q.records = c->d_rec.p;
+        q.rec_begin = rec_begin;
+        q.rec_end = rec_end;
+        q.toprows = c->d_top.p;
+        q.beans = c->d_beans.p;
+        q.accs = c->d_accs.p;
+        q.text = dtext;
+        q.T = c->dT;
+        q.strategy = c->opts.strategy;
+        q.ctr = c->d_ctr;
+        CK(launch_consensus_kernel(q, s));
+        if (rec_end > rec_begin) c->tm.n_kernel_launches += 1;
+    }
     GatherParams g{};
     g.text = dtext;
     g.records = c->d_rec.p;
@@ -391,8 +418,8 @@ void read_counters(blu_ctx* c, cudaStream_t s) {
 
 bool grow_caps(const Counters& h, Caps& k, uint64_t defer_seen) {
     bool grew = false;
-    if (h.n_rec > k.rec) k.rec = (size_t)h.n_rec + h.n_rec / 8 + 1024, grew = true;
-    if (h.n_slots > k.slots) k.slots = (size_t)h.n_slots + h.n_slots / 8 + 1024, grew = true;
+    if (n_rec_of(h) > k.rec) k.rec = (size_t)n_rec_of(h) + n_rec_of(h) / 8 + 1024, grew = true;
+    if (n_slots_of(h) > k.slots) k.slots = (size_t)n_slots_of(h) + n_slots_of(h) / 8 + 1024, grew = true;
     if (defer_seen > k.defer) k.defer = (size_t)defer_seen + defer_seen / 8 + 1024, grew = true;
     if (h.pool_used > k.pool) k.pool = (size_t)h.pool_used + h.pool_used / 8 + 4096, grew = true;
     if (!grew) {  // overflow flagged but counts look fine (reservation raced past the cap): grow everything
@@ -419,14 +446,14 @@ void run_device(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStream_t s, bl
         // gather needs n_rec: read it from the device counters inside the kernel launch geometry -> one sync
         read_counters(c, s);
         Counters h = *c->h_ctr;
-        if (h.cap_overflow || h.n_rec > k.rec || h.n_slots > k.slots || h.n_defer > k.defer) {
+        if (h.cap_overflow || n_rec_of(h) > k.rec || n_slots_of(h) > k.slots || h.n_defer > k.defer) {
             grow_caps(h, k, h.n_defer);
             continue;
         }
         check_device_error(c, h, 0);
         CK(cudaEventRecord(c->ev[3], s));
-        launch_gather(c, dtext, 0, h.n_rec, k, s);
-        launch_dup(c, h.n_rec, s);
+        launch_gather(c, dtext, 0, n_rec_of(h), k, s);
+        launch_dup(c, n_rec_of(h), s);
         CK(cudaEventRecord(c->ev[4], s));
         read_counters(c, s);
         h = *c->h_ctr;
@@ -437,7 +464,7 @@ void run_device(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStream_t s, bl
         check_device_error(c, h, 0);
         if (h.dup_found)
             throw UnsupportedErr("a query id occurs in two non-adjacent groups of rows; non-contiguous hit tables are not supported yet");
-        if (h.n_rec == 0) throw DataErr("the blast output holds no rows");
+        if (n_rec_of(h) == 0) throw DataErr("the blast output holds no rows");
         c->tm.ms_tile_kernel = ev_ms(c->ev[0], c->ev[1]);
         c->tm.ms_longrun_kernel = ev_ms(c->ev[1], c->ev[2]);
         c->tm.ms_gather_kernel = ev_ms(c->ev[3], c->ev[4]);
@@ -506,16 +533,16 @@ void run_host(blu_ctx* c, const char* text, uint64_t n, blu_result* r) {
             ms_tile += ev_ms(c->ev[0], c->ev[1]);
             ms_long += ev_ms(c->ev[1], c->ev[2]);
             defer_total = std::max<uint64_t>(defer_total, h.n_defer);
-            if (h.cap_overflow || h.n_rec > k.rec || h.n_slots > k.slots || h.n_defer > k.defer) {
+            if (h.cap_overflow || n_rec_of(h) > k.rec || n_slots_of(h) > k.slots || h.n_defer > k.defer) {
                 grow_caps(h, k, h.n_defer);
                 retry = true;
                 break;
             }
             check_device_error(c, h, off - text_off);  // err_off is in buffer coordinates
             CK(cudaEventRecord(c->ev[3], s));
-            launch_gather(c, buf, rec_done, h.n_rec, k, s);
+            launch_gather(c, buf, rec_done, n_rec_of(h), k, s);
             CK(cudaEventRecord(c->ev[4], s));
-            rec_done = h.n_rec;
+            rec_done = n_rec_of(h);
             if (!final_chunk) {
                 if (h.tail_start == ~0ull)
                     tail_len = 0;
@@ -545,7 +572,7 @@ void run_host(blu_ctx* c, const char* text, uint64_t n, blu_result* r) {
         check_device_error(c, h, 0);
         if (h.dup_found)
             throw UnsupportedErr("a query id occurs in two non-adjacent groups of rows; non-contiguous hit tables are not supported yet");
-        if (h.n_rec == 0) throw DataErr("the blast output holds no rows");
+        if (n_rec_of(h) == 0) throw DataErr("the blast output holds no rows");
         c->tm.ms_tile_kernel = ms_tile;
         c->tm.ms_longrun_kernel = ms_long;
         c->tm.ms_gather_kernel = ms_gather;
@@ -620,7 +647,7 @@ void blu_ctx_destroy(blu_ctx* c) {
     c->d_lin_off.release(), c->d_lvl.release(), c->d_bean.release(), c->d_irank.release(), c->d_cut.release();
     c->d_rcls.release(), c->d_acls.release(), c->d_linok.release(), c->d_slots.release();
     c->d_text[0].release(), c->d_text[1].release(), c->d_rec.release(), c->d_beans.release(), c->d_accs.release();
-    c->d_defer.release(), c->d_pool.release(), c->d_dup.release();
+    c->d_defer.release(), c->d_pool.release(), c->d_dup.release(), c->d_top.release();
     if (c->d_ctr) cudaFree(c->d_ctr);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
     c->pool->close();

@@ -93,8 +93,9 @@ struct WinGeom {
 
 // Stage [lo, lo+bytes) of the text into the window with TMA bulk copies.  All threads call; returns when the
 // bytes are visible.  `phase` is the barrier parity, flipped by the caller after every use.
-__device__ __forceinline__ void load_window(WindowIndex& W, const uint8_t* text, unsigned long long lo, int bytes, uint32_t& phase) {
-    __syncthreads();  // everyone is done with the previous contents
+__device__ __forceinline__ void load_window(WindowIndex& W, const uint8_t* text, unsigned long long lo, int bytes, uint32_t& phase,
+                                            bool synced = false) {
+    if (!synced) __syncthreads();  // everyone is done with the previous contents
     if (threadIdx.x == 0) {
         fence_proxy_async();
         mbar_expect_tx(&W.mbar, (uint32_t)bytes);
@@ -274,9 +275,7 @@ __device__ __forceinline__ void finish_geom(WindowIndex& W, WinGeom& g, bool fin
 // tile kernel
 // ---------------------------------------------------------------------------------------------------------------
 struct WarpScratch {
-    TopRow rows[32];
     uint16_t idx[32];
-    uint16_t tmp[5 * 32];
 };
 
 struct TileSmem {
@@ -286,6 +285,7 @@ struct TileSmem {
     uint16_t runs[kMaxRuns];
     WarpScratch ws[kWarps];
     int n_runs;
+    int next_run;    // dynamic distribution of the runs over the warps
     int first_head;  // lowest row index that heads a run owned by this tile
     int fwd_limit;   // first head at/after the end of the tile (rows from there on belong to the next tile)
 };
@@ -320,9 +320,12 @@ __global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(const __grid_cons
         const int max_bytes = (int)(base + kTile + kFwd - lo);
         WinGeom g = make_geom(lo, max_bytes, p.begin, p.end);
         if (g.loaded <= 0) continue;
+        __syncthreads();  // every warp is done with the previous tile (window, row tables, run queue)
         if (tid == 0) {
+            // published to the other threads by the mbarrier arrive (release) / wait (acquire) of the load below
             W.bad_byte = INT_MAX;
             S.n_runs = 0;
+            S.next_run = 0;
             S.first_head = 0x7fffffff;
             S.fwd_limit = 0x7fffffff;
         }
@@ -331,7 +334,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(const __grid_cons
         g.qlo = own_lo > lo ? (int)(own_lo - lo) : 0;
         if (g.rb > g.qlo) g.qlo = g.rb;
         g.qhi = (int)(own_hi - lo) < g.L ? (int)(own_hi - lo) : g.L;
-        load_window(W, p.text, lo, g.loaded, phase);
+        load_window(W, p.text, lo, g.loaded, phase, true);
         finish_geom(W, g, p.final_chunk != 0);
         if (!scan_rows<kWarps>(W, g)) {
             if (tid == 0) report(p.ctr, DE_BAD_FIELD_COUNT, lo);
@@ -393,7 +396,11 @@ __global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(const __grid_cons
         // ---- phase D: one warp per run ----------------------------------------------------------------------------
         const int n_runs = S.n_runs;
         WarpScratch& ws = S.ws[warp];
-        for (int ri = warp; ri < n_runs; ri += kWarps) {
+        while (true) {
+            int ri = 0;
+            if (lane == 0) ri = atomicAdd(&S.next_run, 1);
+            ri = __shfl_sync(0xffffffffu, ri, 0);
+            if (ri >= n_runs) break;
             const int h = S.runs[ri];
             // end of the run = next head among the complete rows
             int e = -1;
@@ -444,50 +451,40 @@ __global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(const __grid_cons
                 if (lane == 0) push_defer(p, h_abs, 0);
                 continue;
             }
-            // reserve output
-            unsigned rec_i = 0, slot = 0;
-            if (lane == 0) {
-                rec_i = atomicAdd(&p.ctr->n_rec, 1u);
-                slot = atomicAdd(&p.ctr->n_slots, (unsigned)gcount);
-                atomicAdd(&p.ctr->n_rows, (unsigned long long)(e - h));
-            }
-            rec_i = __shfl_sync(0xffffffffu, rec_i, 0);
-            slot = __shfl_sync(0xffffffffu, slot, 0);
+            // reserve one record + gcount top-row slots with a single packed atomic
+            unsigned long long rs = 0;
+            if (lane == 0) rs = atomicAdd(&p.ctr->rec_slots, (1ull << 32) | (unsigned long long)gcount);
+            rs = __shfl_sync(0xffffffffu, rs, 0);
+            const unsigned rec_i = (unsigned)(rs >> 32), slot = (unsigned)rs;
             if (rec_i >= p.rec_cap || slot + (unsigned)gcount > p.slot_cap) {
                 if (lane == 0) p.ctr->cap_overflow = 1;
                 continue;
             }
-            // join: each lane parses one top row and probes the taxid table
+            // join: each lane parses one top row and probes the taxid table; the rows go to the top-row table
             uint32_t err = 0;
             if (lane < gcount) {
                 const int r = ws.idx[lane];
                 const int s = W.row_s[r];
-                err = heavy_parse_row(W.win + s, (int)W.row_e[r + eskip] - s, lo + s, p.T, ws.rows[lane]);
-                if (err) report(p.ctr, err, lo + s);
+                TopRow tr;
+                err = heavy_parse_row(W.win + s, (int)W.row_e[r + eskip] - s, lo + s, p.T, tr);
+                if (err)
+                    report(p.ctr, err, lo + s);
+                else
+                    p.toprows[slot + lane] = tr;
             }
             err = __any_sync(0xffffffffu, err != 0);
-            __syncwarp();
-            if (err) continue;
             if (lane == 0) {
                 blu_record* rec = p.records + rec_i;
-                QueryOut out{rec, p.beans + slot, p.accs + slot};
-                const uint8_t* q = W.win + W.row_s[h];
-                const uint32_t qmax = (uint32_t)((int)W.row_e[h + eskip] - (int)W.row_s[h]);
-                uint32_t ql = 0;
-                while (ql < qmax && q[ql] != '\t') ql++;
                 rec->query_off = h_abs;
-                rec->query_len = ql;
+                rec->query_len = (uint32_t)(next_tab(tabw, W.row_s[h], W.row_e[h + eskip]) - (int)W.row_s[h]);
                 rec->n_rows = (uint32_t)(e - h);
                 rec->bit_score = (int64_t)mx;
                 rec->slot_base = slot;
+                rec->n_accessions = (uint32_t)gcount;  // size of the top group until the consensus kernel overwrites it
+                rec->n_beans = 0;
+                rec->status = err ? 0 : 2;             // 2 = waiting for the consensus kernel
                 rec->pad[0] = rec->pad[1] = 0;
-                // accession bytes are read from the shared-memory window (generic pointer rebased to buffer offsets)
-                const uint8_t* win_as_text = reinterpret_cast<const uint8_t*>(reinterpret_cast<uintptr_t>(W.win) - (uintptr_t)lo);
-                uint32_t ce = gcount == 1 ? consensus_single(ws.rows[0], p.T, out)
-                                          : consensus_multi(ws.rows, gcount, win_as_text, p.T, p.strategy, ws.tmp, out);
-                if (ce) report(p.ctr, ce, h_abs);
             }
-            __syncwarp();
         }
     }
 }
@@ -535,8 +532,9 @@ __device__ LongScan long_scan(LongSmem& S, const RunParams& p, unsigned long lon
     LongScan r;
     const unsigned long long lo = cur & ~15ull;
     WinGeom g = make_geom(lo, kWin, cur, p.end);
+    __syncthreads();
     if (threadIdx.x == 0) W.bad_byte = INT_MAX;
-    load_window(W, p.text, lo, g.loaded, phase);
+    load_window(W, p.text, lo, g.loaded, phase, true);
     finish_geom(W, g, p.final_chunk != 0);
     r.giant = false;
     if (!scan_rows<kLongWarps>(W, g)) {
@@ -714,11 +712,9 @@ __global__ void __launch_bounds__(kLongThreads, 1) longrun_kernel(const __grid_c
         }
         const int gcount = (int)cnt;
         if (tid == 0) {
-            unsigned rec_i = atomicAdd(&p.ctr->n_rec, 1u);
-            unsigned slot = atomicAdd(&p.ctr->n_slots, (unsigned)gcount);
-            atomicAdd(&p.ctr->n_rows, (unsigned long long)nrows);
-            S.bcast[2] = (int)rec_i;
-            S.bcast[3] = (int)slot;
+            unsigned long long rs = atomicAdd(&p.ctr->rec_slots, (1ull << 32) | (unsigned long long)gcount);
+            S.bcast[2] = (int)(unsigned)(rs >> 32);
+            S.bcast[3] = (int)(unsigned)rs;
         }
         __syncthreads();
         const unsigned rec_i = (unsigned)S.bcast[2], slot = (unsigned)S.bcast[3];
@@ -779,6 +775,280 @@ __global__ void __launch_bounds__(kLongThreads, 1) longrun_kernel(const __grid_c
                                       : consensus_multi(S.top, gcount, p.text, p.T, p.strategy, S.tmp, out);
             if (ce) report(p.ctr, ce, s);
         }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// consensus kernel: one warp per query, lanes = rows of the top bit-score group (<= 32)
+//   find_multi_taxa_consensus.rs:39-214 + build_blast_consensus_identity.rs:9-105 + consensus_result.rs:65-88
+//   (same semantics as the serial consensus_multi() in blu_core.cuh, which the block path and the host tests use)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int cmp_u64(unsigned long long a, unsigned long long b) { return a < b ? -1 : (a > b ? 1 : 0); }
+
+// bytewise comparison of two accessions given their first 16 bytes as big-endian keys (zero padded)
+__device__ __forceinline__ int cmp_acc(unsigned long long a0, unsigned long long a1, unsigned alen, unsigned long long aoff, unsigned long long b0,
+                                       unsigned long long b1, unsigned blen, unsigned long long boff, const uint8_t* text) {
+    int c = cmp_u64(a0, b0);
+    if (c) return c;
+    c = cmp_u64(a1, b1);
+    if (c) return c;
+    if (alen > 16 && blen > 16) {
+        const unsigned n = alen < blen ? alen : blen;
+        for (unsigned i = 16; i < n; i++) {
+            int d = (int)text[aoff + i] - (int)text[boff + i];
+            if (d) return d;
+        }
+    }
+    return (int)alen - (int)blen;
+}
+
+// rank selection for the reference lineage, lanes = lineage positions (two rounds cover the 64-position limit)
+__device__ __forceinline__ void warp_apply_cutoffs(const LinTables& T, uint32_t ref_lin, uint32_t o, int k, double identity, bool whole, int idx,
+                                                   blu_record* rec, int lane) {
+    unsigned long long ge = 0, notgt = 0;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int j = lane + 32 * h;
+        double c = 0.0;
+        const bool in = j < k;
+        if (in) c = T.cut[o + j];
+        const unsigned b_ge = __ballot_sync(0xffffffffu, in && identity >= c);     // linnaean_ranks.rs:208
+        const unsigned b_ng = __ballot_sync(0xffffffffu, in && !(identity > c));   // linnaean_ranks.rs:188
+        ge |= (unsigned long long)b_ge << (32 * h);
+        notgt |= (unsigned long long)b_ng << (32 * h);
+    }
+    if (lane == 0) {
+        const int allowed = notgt ? (__ffsll((long long)notgt) - 1) : -1;
+        unsigned long long mask = ge;
+        if (!whole) {
+            // keep the first idx+1 survivors: enumerate AFTER the filter, take_while(index <= bean_index)
+            unsigned long long m = 0, rest = ge;
+            for (int n = 0; n <= idx && rest; n++) {
+                unsigned long long low = rest & (~rest + 1);
+                m |= low;
+                rest ^= low;
+            }
+            mask = m;
+        }
+        const int last = mask ? 63 - __clzll((long long)mask) : -1;
+        rec->keep_mask = mask;
+        rec->allowed_pos = (int8_t)allowed;
+        rec->reached_pos = (int8_t)(last >= 0 ? last : idx);
+        rec->mutated = (allowed >= 0 && T.rank_cls[o + idx] != T.allowed_cls[o + allowed]) ? 1 : 0;
+        rec->ref_lineage = ref_lin;
+    }
+}
+
+__global__ void __launch_bounds__(256) consensus_kernel(const ConsParams p) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned qi = p.rec_begin + (blockIdx.x * blockDim.x + threadIdx.x) / 32;
+    if (qi >= p.rec_end) return;
+    blu_record* rec = p.records + qi;
+    if (rec->status != 2) return;
+    const LinTables& T = p.T;
+    const int g = (int)rec->n_accessions;
+    const unsigned slot = rec->slot_base;
+    const bool on = lane < g;
+    const unsigned act = g >= 32 ? FULL : ((1u << g) - 1u);
+    TopRow r;
+    r.pident = 0.0, r.alnlen = 0, r.acc_off = 0, r.lin = 0, r.acc_len = 0, r.lin_len = 0;
+    uint32_t pos0 = 0;
+    if (on) {
+        r = p.toprows[slot + lane];
+        pos0 = T.lin_off[r.lin];
+    }
+    __syncwarp();
+    if (g == 1) {
+        // single match (find_single_query_consensus.rs:74-150)
+        const uint32_t o = __shfl_sync(FULL, pos0, 0);
+        const int k = __shfl_sync(FULL, (int)r.lin_len, 0);
+        const double pid = __shfl_sync(FULL, r.pident, 0);
+        unsigned long long mask = 0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int j = lane + 32 * h;
+            const bool in = j < k;
+            double c = 0.0;
+            if (in) c = T.cut[o + j];
+            mask |= (unsigned long long)__ballot_sync(FULL, in && pid >= c) << (32 * h);
+        }
+        if (lane == 0) {
+            if (!mask) {
+                report(p.ctr, DE_EMPTY_ADJUSTED, rec->query_off);
+                rec->status = 0;
+                return;
+            }
+            const int last = 63 - __clzll((long long)mask);
+            rec->keep_mask = mask;
+            rec->perc_identity = r.pident;
+            rec->ref_lineage = r.lin;
+            rec->n_beans = 1;
+            rec->n_accessions = 1;
+            rec->single_match = 1;
+            rec->mutated = 0;
+            rec->reached_pos = (int8_t)last;
+            rec->allowed_pos = -1;
+            rec->bean_level = (int8_t)last;
+            blu_bean b;
+            b.first_lineage = r.lin, b.occurrences = 1, b.acc_begin = 0, b.n_acc = 1;
+            p.beans[slot] = b;
+            blu_acc a;
+            a.off = r.acc_off, a.len = r.acc_len, a.pad = 0;
+            p.accs[slot] = a;
+            rec->status = 1;
+        }
+        return;
+    }
+    // ---- first 16 accession bytes as big-endian keys ---------------------------------------------------------------
+    unsigned long long k0 = 0, k1 = 0;
+    if (on) {
+        const uint8_t* a = p.text + r.acc_off;
+        const unsigned n = r.acc_len;
+#pragma unroll
+        for (unsigned b = 0; b < 8; b++) k0 = (k0 << 8) | (b < n ? a[b] : 0u);
+#pragma unroll
+        for (unsigned b = 8; b < 16; b++) k1 = (k1 << 8) | (b < n ? a[b] : 0u);
+    }
+    // ---- S = stable sort by (lineage length, pident, align length, accession)   fmtc.rs:39-54 ----------------------
+    int rank = 0;
+    for (int j = 0; j < g; j++) {
+        const int len_j = __shfl_sync(FULL, (int)r.lin_len, j);
+        const double pid_j = __shfl_sync(FULL, r.pident, j);
+        const long long aln_j = __shfl_sync(FULL, (long long)r.alnlen, j);
+        const unsigned long long k0_j = __shfl_sync(FULL, k0, j), k1_j = __shfl_sync(FULL, k1, j);
+        const unsigned alen_j = __shfl_sync(FULL, (unsigned)r.acc_len, j);
+        const unsigned long long off_j = __shfl_sync(FULL, (unsigned long long)r.acc_off, j);
+        bool lt;
+        if (len_j != (int)r.lin_len)
+            lt = len_j < (int)r.lin_len;
+        else if (pid_j < r.pident)
+            lt = true;
+        else if (pid_j > r.pident)
+            lt = false;
+        else if (aln_j != (long long)r.alnlen)
+            lt = aln_j < (long long)r.alnlen;
+        else {
+            const int c = on ? cmp_acc(k0_j, k1_j, alen_j, off_j, k0, k1, r.acc_len, r.acc_off, p.text) : 0;
+            lt = c < 0 || (c == 0 && j < lane);
+        }
+        if (on && j != lane && lt) rank++;
+    }
+    // move row of rank s into lane s
+    int src = lane;
+    for (int j = 0; j < g; j++) {
+        const int rj = __shfl_sync(FULL, rank, j);
+        if (rj == lane) src = j;
+    }
+    r.pident = __shfl_sync(FULL, r.pident, src);
+    r.alnlen = __shfl_sync(FULL, (long long)r.alnlen, src);
+    r.acc_off = __shfl_sync(FULL, (unsigned long long)r.acc_off, src);
+    r.lin = __shfl_sync(FULL, r.lin, src);
+    r.acc_len = (uint16_t)__shfl_sync(FULL, (unsigned)r.acc_len, src);
+    r.lin_len = (uint16_t)__shfl_sync(FULL, (unsigned)r.lin_len, src);
+    pos0 = __shfl_sync(FULL, pos0, src);
+    k0 = __shfl_sync(FULL, k0, src);
+    k1 = __shfl_sync(FULL, k1, src);
+    // ---- reference row + level walk (fmtc.rs:60-63,137-214) ----------------------------------------------------------
+    const int ref_lane = p.strategy == BLU_STRATEGY_CAUTIOUS ? 0 : g - 1;
+    const int m = __shfl_sync(FULL, (int)r.lin_len, 0);  // shortest lineage
+    const uint32_t lin0 = __shfl_sync(FULL, r.lin, 0);
+    int diverge = -1;
+    if (__ballot_sync(FULL, on && r.lin != lin0)) {
+        for (int i = 0; i < m; i++) {
+            uint32_t key = 0;
+            if (on) key = T.lvl_key[pos0 + i];
+            const uint32_t key0 = __shfl_sync(FULL, key, 0);
+            if (__ballot_sync(FULL, on && key != key0)) {
+                diverge = i;
+                break;
+            }
+        }
+    }
+    if (diverge == 0) {
+        if (lane == 0) {
+            report(p.ctr, DE_ROOT_DISAGREE, rec->query_off);
+            rec->status = 0;
+        }
+        return;
+    }
+    double identity;
+    int idx, level;
+    bool single;
+    const double ref_pid = __shfl_sync(FULL, r.pident, ref_lane);
+    if (diverge > 0) {
+        double mx = on ? r.pident : 0.0;  // fold from 0.0 (fmtc.rs:182-185)
+        if (!(mx > 0.0)) mx = 0.0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const double o = __shfl_xor_sync(FULL, mx, d);
+            mx = o > mx ? o : mx;
+        }
+        identity = mx, idx = diverge - 1, level = diverge, single = false;
+    } else {
+        identity = ref_pid, idx = m - 1, level = m - 1, single = true;
+    }
+    // ---- fold beans at `level` in S order (consensus_result.rs:65-88) -----------------------------------------------
+    uint32_t bkey = 0xFFFFFF00u + (uint32_t)lane, irank = 0;
+    if (on) {
+        bkey = T.bean_key[pos0 + level];
+        irank = T.ident_rank[pos0 + level];
+    }
+    const unsigned grp = __match_any_sync(FULL, bkey) & act;
+    const unsigned below = grp & ((1u << lane) - 1u);
+    const bool leader = on && below == 0;
+    const int occ = __popc(grp);
+    // Vec::dedup: an accession equal to its predecessor in the bean's S-ordered list is dropped
+    const int pl = below ? 31 - __clz(below) : lane;
+    const unsigned long long pk0 = __shfl_sync(FULL, k0, pl), pk1 = __shfl_sync(FULL, k1, pl);
+    const unsigned plen = __shfl_sync(FULL, (unsigned)r.acc_len, pl);
+    const unsigned long long poff = __shfl_sync(FULL, (unsigned long long)r.acc_off, pl);
+    bool dropped = false;
+    if (on && below) dropped = plen == r.acc_len && cmp_acc(pk0, pk1, plen, poff, k0, k1, r.acc_len, r.acc_off, p.text) == 0;
+    const unsigned kept = __ballot_sync(FULL, on && !dropped);
+    const int nacc_bean = __popc(grp & kept);
+    const int my_idx = __popc(grp & kept & ((1u << lane) - 1u));
+    // sort beans: occurrences desc, identifier asc (bbci.rs:50-60); deterministic tie-break on the key id
+    const unsigned lm = __ballot_sync(FULL, leader);
+    int brank = 0, acc_begin = 0;
+    for (unsigned rest = lm; rest;) {
+        const int j = __ffs(rest) - 1;
+        rest &= rest - 1;
+        const int occ_j = __shfl_sync(FULL, occ, j);
+        const uint32_t ir_j = __shfl_sync(FULL, irank, j), bk_j = __shfl_sync(FULL, bkey, j);
+        const int na_j = __shfl_sync(FULL, nacc_bean, j);
+        if (leader && j != lane) {
+            const bool better = occ_j != occ ? occ_j > occ : (ir_j != irank ? ir_j < irank : bk_j < bkey);
+            if (better) {
+                brank++;
+                acc_begin += na_j;
+            }
+        }
+    }
+    if (leader) {
+        blu_bean b;
+        b.first_lineage = r.lin, b.occurrences = (uint32_t)occ, b.acc_begin = (uint32_t)acc_begin, b.n_acc = (uint32_t)nacc_bean;
+        p.beans[slot + brank] = b;
+    }
+    const int my_begin = __shfl_sync(FULL, acc_begin, grp ? __ffs(grp) - 1 : 0);
+    if (on && !dropped) {
+        blu_acc a;
+        a.off = r.acc_off, a.len = r.acc_len, a.pad = 0;
+        p.accs[slot + my_begin + my_idx] = a;
+    }
+    const int nb = __popc(lm);
+    // ---- rank selection on the reference lineage (bbci.rs:22-37,66-95) -----------------------------------------------
+    const uint32_t ref_lin = __shfl_sync(FULL, r.lin, ref_lane);
+    const uint32_t ref_o = __shfl_sync(FULL, pos0, ref_lane);
+    const int ref_k = __shfl_sync(FULL, (int)r.lin_len, ref_lane);
+    warp_apply_cutoffs(T, ref_lin, ref_o, ref_k, identity, single && nb == 1, idx, rec, lane);
+    if (lane == 0) {
+        rec->perc_identity = ref_pid;
+        rec->n_beans = (uint32_t)nb;
+        rec->n_accessions = (uint32_t)__popc(kept);
+        rec->single_match = 0;
+        rec->bean_level = (int8_t)level;
+        rec->status = 1;
     }
 }
 
@@ -884,6 +1154,13 @@ cudaError_t launch_tile_kernel(const RunParams& p, int grid, cudaStream_t s) {
 
 cudaError_t launch_longrun_kernel(const RunParams& p, int grid, cudaStream_t s) {
     longrun_kernel<<<grid, kLongThreads, sizeof(LongSmem), s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_consensus_kernel(const ConsParams& p, cudaStream_t s) {
+    if (p.rec_end <= p.rec_begin) return cudaSuccess;
+    const unsigned n = p.rec_end - p.rec_begin;  // one warp per record, 8 per CTA
+    consensus_kernel<<<(n + 7) / 8, 256, 0, s>>>(p);
     return cudaGetLastError();
 }
 

@@ -9,18 +9,16 @@ namespace blu {
 
 // Device-side counters of one run (zeroed by the host before the first chunk).
 struct Counters {
-    unsigned int n_rec;        // records reserved
-    unsigned int n_slots;      // bean/accession slots reserved
+    unsigned long long rec_slots;  // packed reservation counter: records << 32 | top-row slots
     unsigned int n_defer;      // deferred runs of the current chunk
     unsigned int err_code;     // first DevErr
     unsigned long long err_off;    // byte offset (in the current device buffer) of the first error
     unsigned long long tail_start; // !final chunks: start of the last (unfinished) run
     unsigned long long pool_used;  // bytes of the string pool in use
-    unsigned long long n_rows;     // hit rows seen in finished runs
     unsigned int dup_found;    // a query id occurs in two separate runs
     unsigned int cap_overflow; // some output capacity was exceeded (host grows and retries)
     unsigned int work_ticket;  // dynamic work distribution of the long-run kernel
-    unsigned int pad;
+    unsigned int pad[3];
 };
 
 struct RunParams {
@@ -33,9 +31,22 @@ struct RunParams {
     uint32_t rec_cap;
     blu_bean* beans;
     blu_acc* accs;
+    TopRow* toprows;       // top bit-score rows of every query (joined with the lineage tables), slot-indexed
     uint32_t slot_cap;
     uint64_t* defer;       // (offset << 1) | check_prev
     uint32_t defer_cap;
+    Counters* ctr;
+};
+
+struct ConsParams {
+    blu_record* records;
+    uint32_t rec_begin, rec_end;
+    const TopRow* toprows;
+    blu_bean* beans;
+    blu_acc* accs;
+    const uint8_t* text;
+    LinTables T;
+    int strategy;
     Counters* ctr;
 };
 
@@ -68,6 +79,7 @@ constexpr int kTileThreads = 256;
 int tile_kernel_grid(int device);
 cudaError_t launch_tile_kernel(const RunParams& p, int grid, cudaStream_t s);
 cudaError_t launch_longrun_kernel(const RunParams& p, int grid, cudaStream_t s);
+cudaError_t launch_consensus_kernel(const ConsParams& p, cudaStream_t s);
 cudaError_t launch_gather_kernel(const GatherParams& p, cudaStream_t s);
 cudaError_t launch_dup_kernel(const DupParams& p, cudaStream_t s);
 cudaError_t kernels_set_attributes();
