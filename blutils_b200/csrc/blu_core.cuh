@@ -379,6 +379,155 @@ BLU_HD LightRow parse_row_masked(const uint8_t* win, const uint64_t* tabw, const
     return r;
 }
 
+// ---- fast path: the whole row in registers -----------------------------------------------------------------------
+// Rows of up to 96 bytes (every BLAST row in practice) are validated from three 32-bit words of the tab mask and
+// three of the digit mask, with popcount / find-first-set / count-leading-zeros instead of per-byte loops.  The fast
+// path only ACCEPTS shapes it fully understands (digits-only integers, `digits[.digits]` floats without exponent in
+// pident / bitscore); anything else -- including every malformed row -- returns false and is re-examined by
+// parse_row_masked(), which implements the complete grammar.  So the fast path can never change a result or an
+// error decision, only skip work.
+BLU_HD uint32_t blu_funnel_r(uint32_t lo, uint32_t hi, uint32_t sh) {  // (hi:lo) >> sh, 0 <= sh < 32
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, sh);
+#else
+    return sh ? (lo >> sh) | (hi << (32 - sh)) : lo;
+#endif
+}
+BLU_HD int blu_ffs32(uint32_t x) {  // index of the lowest set bit; x != 0
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)x) - 1;
+#else
+    return __builtin_ctz(x);
+#endif
+}
+BLU_HD int blu_clz32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __clz((int)x);
+#else
+    return x ? __builtin_clz(x) : 32;
+#endif
+}
+BLU_HD int blu_popc32(uint32_t x) {
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+
+// 32 mask bits starting at (window) bit position `pos`
+BLU_HD uint32_t bits_at(const uint32_t* w, int pos) { return blu_funnel_r(w[pos >> 5], w[(pos >> 5) + 1], (uint32_t)pos & 31u); }
+
+// tabw32 / digw32: the byte-class masks viewed as 32-bit words (readable 4 words past the row start).
+// Returns true and fills bits / q_len when the row is valid AND of the common shape.
+BLU_HD bool parse_row_fast(const uint8_t* win, const uint32_t* tabw32, const uint32_t* digw32, int s, int e, int64_t& bits, int& q_len) {
+    const int len = e - s;
+    if (len > 96 || len < 25) return false;
+    const int wi = s >> 5;
+    const uint32_t sh = (uint32_t)s & 31u;
+    uint32_t t0 = blu_funnel_r(tabw32[wi], tabw32[wi + 1], sh), t1 = blu_funnel_r(tabw32[wi + 1], tabw32[wi + 2], sh),
+             t2 = blu_funnel_r(tabw32[wi + 2], tabw32[wi + 3], sh);
+    // clear the bits at/after the end of the row
+    if (len <= 32) {
+        t0 &= len == 32 ? 0xFFFFFFFFu : ((1u << len) - 1u);
+        t1 = 0;
+        t2 = 0;
+    } else if (len <= 64) {
+        t1 &= len == 64 ? 0xFFFFFFFFu : ((1u << (len - 32)) - 1u);
+        t2 = 0;
+    } else {
+        t2 &= len == 96 ? 0xFFFFFFFFu : ((1u << (len - 64)) - 1u);
+    }
+    if (blu_popc32(t0) + blu_popc32(t1) + blu_popc32(t2) != 12) return false;
+    // first four tabs must lie in the first 64 bytes
+    uint64_t lo64 = (uint64_t)t0 | ((uint64_t)t1 << 32);
+    if (!lo64) return false;
+    const int p1 = blu_ctz64(lo64);
+    lo64 &= lo64 - 1;
+    if (!lo64) return false;
+    const int p2 = blu_ctz64(lo64);
+    lo64 &= lo64 - 1;
+    if (!lo64) return false;
+    const int p3 = blu_ctz64(lo64);
+    lo64 &= lo64 - 1;
+    if (!lo64) return false;
+    const int p4 = blu_ctz64(lo64);
+    // last two tabs
+    int p12, p11;
+    {
+        uint32_t a = t2, b = t1, c = t0;
+        int base = 64;
+        if (!a) {
+            a = b, b = c, c = 0, base = 32;
+            if (!a) a = b, b = 0, base = 0;
+        }
+        p12 = base + 31 - blu_clz32(a);
+        a &= ~(1u << (p12 - base));
+        if (!a) {
+            a = b, base -= 32;
+            if (!a) a = c, base -= 32;  // (cannot run out: there are 12 tabs)
+        }
+        p11 = base + 31 - blu_clz32(a);
+    }
+    // field lengths (relative positions within the row)
+    const int l_q = p1, l_acc = p2 - p1 - 1, l_tax = p3 - p2 - 1, l_pid = p4 - p3 - 1, l_ints = p11 - p4 - 1, l_ev = p12 - p11 - 1,
+              l_bits = len - p12 - 1;
+    if (l_q < 1 || l_acc < 1 || l_tax < 1 || l_tax > 18 || l_pid < 1 || l_pid > 32 || l_ints < 13 || l_ints > 30 || l_ev < 1 || l_ev > 32 ||
+        l_bits < 1 || l_bits > 32)
+        return false;
+    // "other" = neither digit nor tab
+    // taxid: digits only
+    {
+        const uint32_t d = bits_at(digw32, s + p2 + 1);
+        const uint32_t m = (1u << l_tax) - 1u;
+        if ((d & m) != m) return false;
+    }
+    // length .. send: seven non-empty digit-only fields separated by single tabs
+    {
+        const uint32_t d = bits_at(digw32, s + p4 + 1), t = bits_at(tabw32, s + p4 + 1);
+        const uint32_t m = (1u << l_ints) - 1u;
+        if (((d | t) & m) != m) return false;
+        const uint32_t tt = t & m;
+        if (blu_popc32(tt) != 6 || (tt & (tt << 1)) || (tt & 1u) || (tt >> (l_ints - 1))) return false;
+    }
+    // pident / evalue: digits with at most one '.', at least one digit
+    {
+        const uint32_t m = l_pid == 32 ? 0xFFFFFFFFu : ((1u << l_pid) - 1u);
+        const uint32_t o = ~bits_at(digw32, s + p3 + 1) & m;
+        if (o) {
+            if (o & (o - 1)) return false;
+            if (l_pid < 2 || win[s + p3 + 1 + blu_ffs32(o)] != '.') return false;
+        }
+    }
+    {
+        const uint32_t m = l_ev == 32 ? 0xFFFFFFFFu : ((1u << l_ev) - 1u);
+        const uint32_t o = ~bits_at(digw32, s + p11 + 1) & m;
+        if (o) {
+            const bool one_dot = !(o & (o - 1)) && l_ev >= 2 && win[s + p11 + 1 + blu_ffs32(o)] == '.';
+            if (!one_dot && !check_float(win + s + p11 + 1, l_ev)) return false;
+        }
+    }
+    // bit score: digits[.digits] with at most 15 digits in total -> trunc(value) is the integer part, exactly
+    {
+        const uint32_t m = l_bits == 32 ? 0xFFFFFFFFu : ((1u << l_bits) - 1u);
+        const uint32_t o = ~bits_at(digw32, s + p12 + 1) & m;
+        int n_int = l_bits;
+        if (o) {
+            if (o & (o - 1)) return false;
+            n_int = blu_ffs32(o);
+            if (l_bits < 2 || win[s + p12 + 1 + n_int] != '.') return false;
+            if (l_bits - 1 > 15) return false;
+        } else if (l_bits > 15)
+            return false;
+        int64_t v = 0;
+        const uint8_t* b = win + s + p12 + 1;
+        for (int i = 0; i < n_int; i++) v = v * 10 + (int64_t)(b[i] - '0');
+        bits = v;
+    }
+    q_len = l_q;
+    return true;
+}
+
 // first fields (qseqid) of the rows starting at a and b are equal; both rows are known to contain a tab
 BLU_HD bool same_first_field(const uint8_t* win, const uint64_t* tabw, int a, int ea, int b, int eb) {
     const int la = next_tab(tabw, a, ea) - a;

@@ -73,6 +73,8 @@ struct WindowIndex {
     // byte-class bitmasks, one bit per window byte (u16 per 16-byte chunk; read back as 64-bit words)
     alignas(8) uint16_t tabm[kChunks + 8];
     alignas(8) uint16_t digm[kChunks + 8];
+    uint16_t startm[kChunks + 8];  // row starts / row ends per chunk (pass 1 of the row scan -> pass 2)
+    uint16_t endm[kChunks + 8];
     uint16_t row_s[kRowCap];
     uint16_t row_e[kRowCap + 1];
     alignas(8) unsigned long long mbar;
@@ -151,38 +153,36 @@ __device__ __forceinline__ uint32_t range_mask16(int pos0, int lo, int hi) {  //
     return ((1u << b) - 1u) & ~((1u << a) - 1u);
 }
 
-// Classifies chunk c: row starts / row ends (see DESIGN.md "row index"); when STORE, also publishes the tab and
-// digit masks of the chunk and flags '"' / '\r' bytes.
-template <bool STORE>
-__device__ __forceinline__ void chunk_masks(WindowIndex& W, const WinGeom& g, int c, uint32_t& start, uint32_t& end) {
+// Row scan, pass 1: classifies one 16-byte chunk (newline / tab / digit / quote-or-CR) with SIMD-in-register byte
+// tests, publishes the tab and digit masks, and derives the row-start / row-end masks of the chunk
+// (DESIGN.md "row index").  `carry` = the byte in front of the chunk is a newline.
+__device__ __forceinline__ void classify_chunk(WindowIndex& W, const WinGeom& g, int c, uint32_t carry, uint32_t& nl_out, uint32_t& start,
+                                               uint32_t& end) {
     const int pos0 = c << 4;
     const uint4 v = *reinterpret_cast<const uint4*>(W.win + pos0);
     const int rb = g.rb < 0 ? 0 : g.rb;
-    const uint32_t valid = range_mask16(pos0, rb, g.L);
-    uint32_t nl = pack16(bytes_eq(v.x, 0x0A0A0A0Au), bytes_eq(v.y, 0x0A0A0A0Au), bytes_eq(v.z, 0x0A0A0A0Au), bytes_eq(v.w, 0x0A0A0A0Au)) & valid;
-    if (STORE) {
-        W.tabm[c] = (uint16_t)pack16(bytes_eq(v.x, 0x09090909u), bytes_eq(v.y, 0x09090909u), bytes_eq(v.z, 0x09090909u), bytes_eq(v.w, 0x09090909u));
-        W.digm[c] = (uint16_t)pack16(bytes_digit(v.x), bytes_digit(v.y), bytes_digit(v.z), bytes_digit(v.w));
-        const uint32_t q = (bytes_eq(v.x, 0x22222222u) | bytes_eq(v.x, 0x0D0D0D0Du)) | (bytes_eq(v.y, 0x22222222u) | bytes_eq(v.y, 0x0D0D0D0Du)) |
-                           (bytes_eq(v.z, 0x22222222u) | bytes_eq(v.z, 0x0D0D0D0Du)) | (bytes_eq(v.w, 0x22222222u) | bytes_eq(v.w, 0x0D0D0D0Du));
-        if (q) {
-            const uint32_t qm = pack16(bytes_eq(v.x, 0x22222222u) | bytes_eq(v.x, 0x0D0D0D0Du), bytes_eq(v.y, 0x22222222u) | bytes_eq(v.y, 0x0D0D0D0Du),
-                                       bytes_eq(v.z, 0x22222222u) | bytes_eq(v.z, 0x0D0D0D0Du), bytes_eq(v.w, 0x22222222u) | bytes_eq(v.w, 0x0D0D0D0Du)) &
-                                range_mask16(pos0, g.qlo, g.qhi);
-            if (qm) atomicMin(&W.bad_byte, pos0 + __ffs(qm) - 1);
-        }
+    const int tend = g.re < g.loaded ? g.re : g.loaded;  // end of the text inside the window
+    uint32_t nl = pack16(bytes_eq(v.x, 0x0A0A0A0Au), bytes_eq(v.y, 0x0A0A0A0Au), bytes_eq(v.z, 0x0A0A0A0Au), bytes_eq(v.w, 0x0A0A0A0Au));
+    W.tabm[c] = (uint16_t)pack16(bytes_eq(v.x, 0x09090909u), bytes_eq(v.y, 0x09090909u), bytes_eq(v.z, 0x09090909u), bytes_eq(v.w, 0x09090909u));
+    W.digm[c] = (uint16_t)pack16(bytes_digit(v.x), bytes_digit(v.y), bytes_digit(v.z), bytes_digit(v.w));
+    const uint32_t qx = bytes_eq(v.x, 0x22222222u) | bytes_eq(v.x, 0x0D0D0D0Du), qy = bytes_eq(v.y, 0x22222222u) | bytes_eq(v.y, 0x0D0D0D0Du),
+                   qz = bytes_eq(v.z, 0x22222222u) | bytes_eq(v.z, 0x0D0D0D0Du), qw = bytes_eq(v.w, 0x22222222u) | bytes_eq(v.w, 0x0D0D0D0Du);
+    if (qx | qy | qz | qw) {
+        const uint32_t qm = pack16(qx, qy, qz, qw) & range_mask16(pos0, g.qlo, g.qhi);
+        if (qm) atomicMin(&W.bad_byte, pos0 + __ffs(qm) - 1);
     }
-    uint32_t carry;
-    if (g.rb >= 0 && pos0 == g.rb)
-        carry = 1;  // virtual newline in front of the text
-    else if (pos0 > rb)
-        carry = W.win[pos0 - 1] == '\n';
-    else
-        carry = 0;  // unknown predecessor (window starts mid-text) or before the text
+    uint32_t tmask = 0xFFFFu;
+    if (pos0 < rb || pos0 + 16 > tend) {  // chunk on the edge of the text (first / last chunk only)
+        nl &= range_mask16(pos0, rb, g.L);
+        tmask = range_mask16(pos0, rb, tend);
+    }
+    if (g.rb >= 0 && pos0 == g.rb) carry = 1;  // virtual newline in front of the text
+    if (pos0 < rb) carry = 0;
     uint32_t prev = ((nl << 1) | carry) & 0xFFFFu;
     if (g.rb > pos0 && g.rb < pos0 + 16) prev |= 1u << (g.rb - pos0);
-    start = prev & ~nl & range_mask16(pos0, rb, g.re < g.loaded ? g.re : g.loaded);
+    start = prev & ~nl & tmask;
     end = nl & ~prev;
+    nl_out = nl;
 }
 
 // Builds row_s / row_e for the staged window.  Returns false (uniformly) when the row table would overflow,
@@ -191,15 +191,42 @@ template <int NWARPS>
 __device__ bool scan_rows(WindowIndex& W, const WinGeom& g) {
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
     const int nchunks = (g.L + 15) >> 4;
-    const int cpw = (nchunks + NWARPS - 1) / NWARPS;
+    const int cpw = (((nchunks + NWARPS - 1) / NWARPS) + 31) & ~31;  // chunks per warp, whole 32-lane rounds
     const int c0 = w * cpw;
     const int c1 = c0 + cpw < nchunks ? c0 + cpw : nchunks;
+    const int rb = g.rb < 0 ? 0 : g.rb;
+    // ---- pass 1: classify, count ---------------------------------------------------------------------------------
     int cnt = 0;
+    uint32_t carry_in = 0;
+    if (c0 < c1 && (c0 << 4) > rb) carry_in = W.win[(c0 << 4) - 1] == '\n';
     for (int base = c0; base < c1; base += 32) {
-        int c = base + lane;
-        if (c < c1) {
-            uint32_t s, e;
-            chunk_masks<true>(W, g, c, s, e);
+        const int c = base + lane;
+        uint32_t nl = 0, s = 0, e = 0;
+        const bool live = c < c1;
+        // the newline status of the byte in front of the chunk comes from the neighbouring lane
+        uint32_t v_nl = 0;
+        if (live) {
+            // cheap pre-classification of the last byte of the previous chunk is not available yet: classify with a
+            // provisional carry of 0 and patch bit 0 below
+            classify_chunk(W, g, c, 0u, nl, s, e);
+            v_nl = nl;
+        }
+        uint32_t up = __shfl_up_sync(0xffffffffu, v_nl, 1);
+        uint32_t carry = lane == 0 ? carry_in : (up >> 15) & 1u;
+        carry_in = (__shfl_sync(0xffffffffu, v_nl, 31) >> 15) & 1u;
+        if (live && carry) {
+            const int pos0 = c << 4;
+            if (pos0 >= rb && !(g.rb >= 0 && pos0 == g.rb)) {
+                // byte 0 of the chunk follows a newline: it starts a row unless it is a newline itself, and a newline
+                // there does not end a row (empty line)
+                const int tend = g.re < g.loaded ? g.re : g.loaded;
+                if (!(nl & 1u) && pos0 < tend) s |= 1u;
+                e &= ~1u;
+            }
+        }
+        if (live) {
+            W.startm[c] = (uint16_t)s;
+            W.endm[c] = (uint16_t)e;
             cnt += __popc(s) | (__popc(e) << 16);
         }
     }
@@ -226,10 +253,15 @@ __device__ bool scan_rows(WindowIndex& W, const WinGeom& g) {
         __syncthreads();
         return false;
     }
+    // ---- pass 2: positions ---------------------------------------------------------------------------------------------
     for (int base = c0; base < c1; base += 32) {
-        int c = base + lane;
+        const int c = base + lane;
         uint32_t s = 0, e = 0;
-        if (c < c1) chunk_masks<false>(W, g, c, s, e);
+        if (c < c1) {
+            s = W.startm[c];
+            e = W.endm[c];
+        }
+        if (!__ballot_sync(0xffffffffu, (s | e) != 0)) continue;
         int mine = __popc(s) | (__popc(e) << 16);
         int inc = mine;
 #pragma unroll
@@ -286,8 +318,7 @@ struct TileSmem {
     WarpScratch ws[kWarps];
     int n_runs;
     int next_run;    // dynamic distribution of the runs over the warps
-    int first_head;  // lowest row index that heads a run owned by this tile
-    int fwd_limit;   // first head at/after the end of the tile (rows from there on belong to the next tile)
+    int first_fwd;   // index of the first row of the look-ahead region (start >= own_hi)
 };
 
 static_assert(sizeof(TileSmem) <= 113 * 1024, "two tile CTAs must fit one SM");
@@ -326,8 +357,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(const __grid_cons
             W.bad_byte = INT_MAX;
             S.n_runs = 0;
             S.next_run = 0;
-            S.first_head = 0x7fffffff;
-            S.fwd_limit = 0x7fffffff;
+            S.first_fwd = 0x7fffffff;
         }
         const unsigned long long own_lo = base, own_hi = base + kTile;
         // every text byte lies in exactly one tile's [own_lo, own_hi): that tile reports a '"' / '\r' in it
@@ -348,10 +378,15 @@ __global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(const __grid_cons
         const uint64_t* digw = reinterpret_cast<const uint64_t*>(W.digm);
         if (W.bad_byte != INT_MAX && tid == 0) report(p.ctr, DE_QUOTE_OR_CR, lo + (unsigned)W.bad_byte);
 
-        // ---- phase B0: head flags of the rows at/after the tile start; run list ------------------------------
-        // (rows before own_lo belong to runs of the previous tile; only the last one is needed, as predecessor)
+        const uint32_t* tabw32 = reinterpret_cast<const uint32_t*>(W.tabm);
+        const uint32_t* digw32 = reinterpret_cast<const uint32_t*>(W.digm);
+        // ---- phase P: one thread per row at/after the tile start --------------------------------------------------
+        //   head flag (first field differs from the previous row's), run list, and -- for the rows inside the tile --
+        //   validation + truncated bit score.  Rows of the look-ahead region are parsed lazily by the warp that
+        //   owns their run (phase D); rows before own_lo belong to runs of the previous tile.
         for (int r = tid; r < ncomplete; r += kTileThreads) {
             const int s = W.row_s[r];
+            const int e = W.row_e[r + eskip];
             const unsigned long long abs = lo + s;
             uint8_t fl = 0;
             if (abs >= own_lo) {
@@ -359,17 +394,28 @@ __global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(const __grid_cons
                 if (r == 0)
                     head = g.rb >= 0 && s == g.rb;  // first row of the text (else: predecessor not in the window)
                 else
-                    head = !same_first_field(W.win, tabw, W.row_s[r - 1], W.row_e[r - 1 + eskip], s, W.row_e[r + eskip]);
-                if (head) {
-                    fl = 1;
-                    if (abs < own_hi) {
+                    head = !same_first_field(W.win, tabw, W.row_s[r - 1], W.row_e[r - 1 + eskip], s, e);
+                if (abs < own_hi) {
+                    if (head) {
+                        fl = 1;
                         int i = atomicAdd(&S.n_runs, 1);
                         S.runs[i] = (uint16_t)r;
-                        atomicMin(&S.first_head, r);
-                    } else
-                        atomicMin(&S.fwd_limit, r);  // first run of the next tile: nothing beyond it is ours
-                } else if (r == 0 && abs < own_hi) {
-                    push_defer(p, abs, 1);  // predecessor not in the window: the block path decides whether it is a head
+                    } else if (r == 0) {
+                        push_defer(p, abs, 1);  // predecessor not in the window: the block path decides whether it is a head
+                    }
+                    int64_t bits;
+                    int ql;
+                    if (!parse_row_fast(W.win, tabw32, digw32, s, e, bits, ql)) {
+                        LightRow lr = parse_row_masked(W.win, tabw, digw, s, e);
+                        if (lr.err) report(p.ctr, lr.err, abs);
+                        bits = lr.bits;
+                    }
+                    const int32_t b32 = (int32_t)bits;
+                    if ((int64_t)b32 != bits) fl |= 2;
+                    S.bits[r] = b32;
+                } else {
+                    if (head) fl = 1;
+                    if (r == 0 || lo + W.row_s[r - 1] < own_hi) S.first_fwd = r;  // first row of the look-ahead region
                 }
             }
             S.flags[r] = fl;
@@ -377,20 +423,6 @@ __global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(const __grid_cons
         if (tid == 0 && has_partial) {
             const unsigned long long abs = lo + W.row_s[ncomplete];
             if (abs >= own_lo && abs < own_hi) push_defer(p, abs, 1);  // unterminated row: the block path sorts it out
-        }
-        __syncthreads();
-        // ---- phase B1: validate + bit score of the rows of the runs this tile owns ----------------------------
-        {
-            const int r1 = S.fwd_limit < ncomplete ? S.fwd_limit : ncomplete;
-            const int r0 = S.first_head < r1 ? S.first_head : r1;  // no owned head: nothing to do
-            for (int r = r0 + tid; r < r1; r += kTileThreads) {
-                const int s = W.row_s[r];
-                LightRow lr = parse_row_masked(W.win, tabw, digw, s, W.row_e[r + eskip]);
-                if (lr.err) report(p.ctr, lr.err, lo + s);
-                const int32_t b32 = (int32_t)lr.bits;
-                if ((int64_t)b32 != lr.bits) S.flags[r] |= 2;
-                S.bits[r] = b32;
-            }
         }
         __syncthreads();
         // ---- phase D: one warp per run ----------------------------------------------------------------------------
@@ -421,6 +453,26 @@ __global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(const __grid_cons
                     if (lane == 0) push_defer(p, h_abs, 0);
                     continue;
                 }
+            }
+            // rows of this run that lie in the look-ahead region have not been parsed yet
+            {
+                int f0 = S.first_fwd > h ? S.first_fwd : h;
+                if (f0 > e) f0 = e;  // (first_fwd is INT_MAX when the window has no look-ahead rows)
+                for (int r = f0 + lane; r < e; r += 32) {
+                    const int s = W.row_s[r];
+                    const int re = W.row_e[r + eskip];
+                    int64_t bits;
+                    int ql;
+                    if (!parse_row_fast(W.win, tabw32, digw32, s, re, bits, ql)) {
+                        LightRow lr = parse_row_masked(W.win, tabw, digw, s, re);
+                        if (lr.err) report(p.ctr, lr.err, lo + s);
+                        bits = lr.bits;
+                    }
+                    const int32_t b32 = (int32_t)bits;
+                    if ((int64_t)b32 != bits) S.flags[r] |= 2;
+                    S.bits[r] = b32;
+                }
+                __syncwarp();
             }
             // max bit score of the run
             int mx = INT32_MIN;
@@ -549,7 +601,15 @@ __device__ LongScan long_scan(LongSmem& S, const RunParams& p, unsigned long lon
     for (int i = threadIdx.x; i < r.ncomplete; i += kLongThreads) {
         const int st = W.row_s[i];
         const int len = (int)W.row_e[i + r.eskip] - st;
-        LightRow lr = parse_row_masked(W.win, reinterpret_cast<const uint64_t*>(W.tabm), reinterpret_cast<const uint64_t*>(W.digm), st, st + len);
+        LightRow lr;
+        {
+            int64_t fb;
+            int fq;
+            if (parse_row_fast(W.win, reinterpret_cast<const uint32_t*>(W.tabm), reinterpret_cast<const uint32_t*>(W.digm), st, st + len, fb, fq)) {
+                lr.bits = fb, lr.q_len = (uint16_t)fq, lr.err = DE_NONE;
+            } else
+                lr = parse_row_masked(W.win, reinterpret_cast<const uint64_t*>(W.tabm), reinterpret_cast<const uint64_t*>(W.digm), st, st + len);
+        }
         bool sm = same_query(W.win + st, len, p.text, s, p.end);
         if (lr.err && sm) report(p.ctr, lr.err, lo + st);
         S.bits[i] = lr.bits;

@@ -4,6 +4,7 @@
 // that the per-row and per-query logic can be checked against the oracle on a machine without a GPU.
 // It is NOT linked into libblu_consensus.so and is not a fallback: the kernel-side control flow (windows, row
 // index, run ownership, deferral, streaming) only exists in blu_kernels.cu and is tested on the GPU.
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <unordered_set>
@@ -54,6 +55,7 @@ extern "C" int blu_sim_run(const int64_t* taxids, const uint64_t* off, const cha
             int qlen;
         };
         std::vector<R> rows;
+        long n_fast = 0;
         // byte-class bitmasks exactly as the row scan of the kernels publishes them (bit i = byte i)
         std::vector<uint64_t> tabw(nbytes / 64 + 3, 0), digw(nbytes / 64 + 3, 0);
         for (uint64_t i = 0; i < nbytes; i++) {
@@ -70,6 +72,19 @@ extern "C" int blu_sim_run(const int64_t* taxids, const uint64_t* off, const cha
             uint64_t e = nl ? (uint64_t)((const uint8_t*)nl - tx) : nbytes;
             if (e > p) {
                 LightRow lr = parse_row_masked(tx, tabw.data(), digw.data(), (int)p, (int)e);
+                {
+                    // the register fast path may only accept rows the full parser accepts, with identical outputs
+                    int64_t fb = 0;
+                    int fq = 0;
+                    if (parse_row_fast(tx, reinterpret_cast<const uint32_t*>(tabw.data()), reinterpret_cast<const uint32_t*>(digw.data()), (int)p, (int)e,
+                                       fb, fq)) {
+                        n_fast++;
+                        if (lr.err || fb != lr.bits || fq != lr.q_len) {
+                            snprintf(err, errlen, "fast row parser disagrees with the full parser at byte %llu", (unsigned long long)p);
+                            return BLU_ERR_INTERNAL;
+                        }
+                    }
+                }
                 LightRow l2 = light_parse_row(tx + p, (int)(e - p));  // byte-wise variant must agree
                 if ((lr.err != 0) != (l2.err != 0) || (!lr.err && (lr.bits != l2.bits || lr.q_len != l2.q_len))) {
                     snprintf(err, errlen, "masked and byte-wise row parsers disagree at byte %llu", (unsigned long long)p);
@@ -84,6 +99,7 @@ extern "C" int blu_sim_run(const int64_t* taxids, const uint64_t* off, const cha
             p = e + 1;
         }
         if (rows.empty()) throw DataErr("no rows");
+        if (getenv("BLU_SIM_VERBOSE")) fprintf(stderr, "sim: %zu rows, %ld through the fast row parser\n", rows.size(), n_fast);
         std::vector<blu_record> recs;
         std::vector<blu_bean> beans;
         std::vector<blu_acc> accs;
