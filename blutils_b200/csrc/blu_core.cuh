@@ -418,6 +418,30 @@ BLU_HD int blu_popc32(uint32_t x) {
 // 32 mask bits starting at (window) bit position `pos`
 BLU_HD uint32_t bits_at(const uint32_t* w, int pos) { return blu_funnel_r(w[pos >> 5], w[(pos >> 5) + 1], (uint32_t)pos & 31u); }
 
+// Non-negative float of the shapes D+[.D*][e[+-]D+] / .D+..., decided from the positions of its non-digit bytes
+// (`o` = non-digit mask of the field, bit i = byte i; o != 0).  false = "not one of these shapes" (caller falls back
+// to the full DFA), never a wrong accept.
+BLU_HD bool float_shape_ok(const uint8_t* f, int len, uint32_t o) {
+    const int k = blu_popc32(o);
+    if (k > 3) return false;
+    const int i1 = blu_ffs32(o);
+    const uint8_t c1 = f[i1];
+    if (k == 1) {
+        if (c1 == '.') return len >= 2;
+        return (c1 | 0x20) == 'e' && i1 >= 1 && i1 <= len - 2;
+    }
+    const uint32_t o2 = o & (o - 1);
+    const int i2 = blu_ffs32(o2);
+    const uint8_t c2 = f[i2];
+    if (k == 2) {
+        if (c1 == '.') return (c2 | 0x20) == 'e' && i2 >= 2 && i2 <= len - 2;
+        return (c1 | 0x20) == 'e' && (c2 == '-' || c2 == '+') && i2 == i1 + 1 && i1 >= 1 && i2 <= len - 2;
+    }
+    const int i3 = blu_ffs32(o2 & (o2 - 1));
+    const uint8_t c3 = f[i3];
+    return c1 == '.' && (c2 | 0x20) == 'e' && (c3 == '-' || c3 == '+') && i3 == i2 + 1 && i2 >= 2 && i3 <= len - 2;
+}
+
 // tabw32 / digw32: the byte-class masks viewed as 32-bit words (readable 4 words past the row start).
 // Returns true and fills bits / q_len when the row is valid AND of the common shape.
 BLU_HD bool parse_row_fast(const uint8_t* win, const uint32_t* tabw32, const uint32_t* digw32, int s, int e, int64_t& bits, int& q_len) {
@@ -502,10 +526,7 @@ BLU_HD bool parse_row_fast(const uint8_t* win, const uint32_t* tabw32, const uin
     {
         const uint32_t m = l_ev == 32 ? 0xFFFFFFFFu : ((1u << l_ev) - 1u);
         const uint32_t o = ~bits_at(digw32, s + p11 + 1) & m;
-        if (o) {
-            const bool one_dot = !(o & (o - 1)) && l_ev >= 2 && win[s + p11 + 1 + blu_ffs32(o)] == '.';
-            if (!one_dot && !check_float(win + s + p11 + 1, l_ev)) return false;
-        }
+        if (o && !float_shape_ok(win + s + p11 + 1, l_ev, o) && !check_float(win + s + p11 + 1, l_ev)) return false;
     }
     // bit score: digits[.digits] with at most 15 digits in total -> trunc(value) is the integer part, exactly
     {
@@ -564,6 +585,31 @@ BLU_HD uint32_t heavy_parse_row(const uint8_t* p, int len, uint64_t row_abs_off,
     uint32_t e = parse_f64(p + tabs[2] + 1, tabs[3] - tabs[2] - 1, out.pident);
     if (e) return e;
     if (!parse_i64(p + tabs[3] + 1, tabs[4] - tabs[3] - 1, out.alnlen)) return DE_BAD_NUMBER;
+    uint32_t lin = probe_taxid(T, taxid);
+    if (lin == 0xFFFFFFFFu) return DE_UNMAPPED_TAXID;
+    if (!T.lin_ok[lin]) return DE_BAD_LINEAGE;
+    out.lin = lin;
+    out.lin_len = (uint16_t)(T.lin_off[lin + 1] - T.lin_off[lin]);
+    return DE_NONE;
+}
+
+// Same as heavy_parse_row, with the field boundaries taken from the tab mask.  `lo` = absolute offset of win[0].
+BLU_HD uint32_t heavy_parse_row_masked(const uint8_t* win, const uint64_t* tabw, int s, int e, uint64_t lo, const LinTables& T, TopRow& out) {
+    const int t0 = next_tab(tabw, s, e);
+    const int t1 = t0 < e ? next_tab(tabw, t0 + 1, e) : e;
+    const int t2 = t1 < e ? next_tab(tabw, t1 + 1, e) : e;
+    const int t3 = t2 < e ? next_tab(tabw, t2 + 1, e) : e;
+    const int t4 = t3 < e ? next_tab(tabw, t3 + 1, e) : e;
+    if (t4 >= e) return DE_BAD_FIELD_COUNT;
+    out.acc_off = lo + (uint64_t)t0 + 1;
+    const int alen = t1 - t0 - 1;
+    if (alen > 65535) return DE_NUM_UNSUPPORTED;
+    out.acc_len = (uint16_t)alen;
+    int64_t taxid;
+    if (!parse_i64(win + t1 + 1, t2 - t1 - 1, taxid)) return DE_BAD_NUMBER;
+    uint32_t er = parse_f64(win + t2 + 1, t3 - t2 - 1, out.pident);
+    if (er) return er;
+    if (!parse_i64(win + t3 + 1, t4 - t3 - 1, out.alnlen)) return DE_BAD_NUMBER;
     uint32_t lin = probe_taxid(T, taxid);
     if (lin == 0xFFFFFFFFu) return DE_UNMAPPED_TAXID;
     if (!T.lin_ok[lin]) return DE_BAD_LINEAGE;

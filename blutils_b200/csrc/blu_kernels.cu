@@ -321,7 +321,7 @@ struct TileSmem {
     int first_fwd;   // index of the first row of the look-ahead region (start >= own_hi)
 };
 
-static_assert(sizeof(TileSmem) <= 113 * 1024, "two tile CTAs must fit one SM");
+static_assert(sizeof(TileSmem) * kTileCtasPerSm + 1024 * kTileCtasPerSm <= 227 * 1024, "tile CTAs must fit one SM");
 
 __device__ __forceinline__ void push_defer(const RunParams& p, unsigned long long off, unsigned check_prev) {
     unsigned i = atomicAdd(&p.ctr->n_defer, 1u);
@@ -331,7 +331,7 @@ __device__ __forceinline__ void push_defer(const RunParams& p, unsigned long lon
         p.ctr->cap_overflow = 1;
 }
 
-__global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(const __grid_constant__ RunParams p) {
+__global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(const __grid_constant__ RunParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     TileSmem& S = *reinterpret_cast<TileSmem*>(smem_raw);
     WindowIndex& W = S.W;
@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) tile_kernel(const __grid_cons
                 const int r = ws.idx[lane];
                 const int s = W.row_s[r];
                 TopRow tr;
-                err = heavy_parse_row(W.win + s, (int)W.row_e[r + eskip] - s, lo + s, p.T, tr);
+                err = heavy_parse_row_masked(W.win, tabw, s, W.row_e[r + eskip], lo, p.T, tr);
                 if (err)
                     report(p.ctr, err, lo + s);
                 else
@@ -1204,7 +1204,7 @@ cudaError_t kernels_set_attributes() {
 int tile_kernel_grid(int device) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    return 2 * sms;  // two resident CTAs per SM (~100 KB of shared memory each)
+    return kTileCtasPerSm * sms;  // resident CTAs per SM (~70 KB of shared memory each)
 }
 
 cudaError_t launch_tile_kernel(const RunParams& p, int grid, cudaStream_t s) {

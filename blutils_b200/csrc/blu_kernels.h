@@ -70,11 +70,12 @@ struct DupParams {
 };
 
 // Tile geometry of the fused kernel
-constexpr int kTile = 40960;   // bytes owned by one tile
+constexpr int kTile = 24576;   // bytes owned by one tile
 constexpr int kBack = 1024;    // look-behind so the tile's first row can be compared with its predecessor
-constexpr int kFwd = 12288;    // look-ahead so a query that starts in the tile can finish in the window
+constexpr int kFwd = 10240;    // look-ahead so a query that starts in the tile can finish in the window
 constexpr int kWin = kBack + kTile + kFwd;
 constexpr int kTileThreads = 256;
+constexpr int kTileCtasPerSm = 3;
 
 int tile_kernel_grid(int device);
 cudaError_t launch_tile_kernel(const RunParams& p, int grid, cudaStream_t s);

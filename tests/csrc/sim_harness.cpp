@@ -121,7 +121,16 @@ extern "C" int blu_sim_run(const int64_t* taxids, const uint64_t* off, const cha
             for (size_t r = h; r < e; r++)
                 if (rows[r].bits == mx) {
                     TopRow t;
-                    uint32_t er = heavy_parse_row(tx + rows[r].s, rows[r].len, rows[r].s, L, t);
+                    uint32_t er = heavy_parse_row_masked(tx, tabw.data(), (int)rows[r].s, (int)rows[r].s + rows[r].len, 0, L, t);
+                    {
+                        TopRow t2;
+                        uint32_t er2 = heavy_parse_row(tx + rows[r].s, rows[r].len, rows[r].s, L, t2);
+                        if (er != er2 || (!er && (t.acc_off != t2.acc_off || t.acc_len != t2.acc_len || t.lin != t2.lin || t.pident != t2.pident ||
+                                                  t.alnlen != t2.alnlen || t.lin_len != t2.lin_len))) {
+                            snprintf(err, errlen, "masked and byte-wise top-row parsers disagree at byte %llu", (unsigned long long)rows[r].s);
+                            return BLU_ERR_INTERNAL;
+                        }
+                    }
                     if (er) {
                         snprintf(err, errlen, "device error %u at byte %llu", er, (unsigned long long)rows[r].s);
                         return map_err(er);
