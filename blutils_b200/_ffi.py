@@ -32,7 +32,7 @@ class blu_timings(C.Structure):
     _fields_ = [("ms_total_device", C.c_double), ("ms_tile_kernel", C.c_double), ("ms_longrun_kernel", C.c_double),
                 ("ms_gather_kernel", C.c_double), ("ms_other", C.c_double), ("text_bytes", C.c_uint64), ("result_bytes", C.c_uint64),
                 ("taxonomy_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_queries", C.c_uint64),
-                ("n_rows", C.c_uint64), ("n_deferred_runs", C.c_uint64), ("n_kernel_launches", C.c_uint64), ("reserved", C.c_uint64 * 4)]
+                ("n_rows", C.c_uint64), ("n_deferred_runs", C.c_uint64), ("n_kernel_launches", C.c_uint64), ("n_regrouped", C.c_uint64), ("reserved", C.c_uint64 * 3)]
 
 
 # every symbol include/blu_consensus.h declares: (name, restype, argtypes)
@@ -61,6 +61,7 @@ SYMBOLS = [
     ("blu_free", None, [C.c_void_p]),
     ("blu_ctx_last_timings", C.c_int, [C.c_void_p, C.POINTER(blu_timings)]),
     ("blu_ctx_measure_h2d", C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_double)]),
+    ("blu_shard_cuts", C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]),
     ("blu_host_alloc", C.c_void_p, [C.c_uint64]),
     ("blu_host_free", None, [C.c_void_p]),
 ]

@@ -305,6 +305,19 @@ class ConsensusEngine:
             pass
 
 
+def shard_cuts(text: Union[bytes, int], n_shards: int, nbytes: Optional[int] = None) -> List[int]:
+    """Byte offsets that split a (contiguous) hit table into n_shards query-aligned ranges.  Host-only."""
+    cuts = (C.c_uint64 * (n_shards + 1))()
+    if isinstance(text, (bytes, bytearray)):
+        buf = C.create_string_buffer(bytes(text), len(text)) if len(text) else C.create_string_buffer(1)
+        rc = _ffi.lib().blu_shard_cuts(C.addressof(buf), len(text), n_shards, cuts)
+    else:
+        rc = _ffi.lib().blu_shard_cuts(int(text), int(nbytes), n_shards, cuts)
+    if rc != 0:
+        raise ValueError("blu_shard_cuts failed")
+    return list(cuts)
+
+
 def build_consensus_identities(blast_output: ParallelBlastOutput, taxonomies_file: str, taxon: Taxon, strategy: ConsensusStrategy,
                                use_taxid: Optional[bool] = None, custom_taxon_values: Optional[CustomTaxon] = None, *,
                                device: int = 0) -> ConsensusOutput:

@@ -18,6 +18,7 @@
 #include <string>
 #include <string_view>
 #include <thread>
+#include <unordered_map>
 #include <unordered_set>
 #include <vector>
 
@@ -432,6 +433,50 @@ void require_ready(blu_ctx* c) {
     if (!c->tax) throw std::invalid_argument("no taxonomy loaded (call blu_taxonomy_load_json first)");
 }
 
+// Non-contiguous hit tables (the reference groups rows through a HashMap<String, Vec<_>>, mod.rs:145,192, so the
+// rows of one query need not be adjacent).  Rare (BLAST emits queries contiguously, blutils appends whole chunks),
+// so it is handled by data movement only: rows are regrouped by query id -- first-appearance order of the queries,
+// file order inside a query, which is all the consensus depends on -- and the GPU pipeline runs on the regrouped
+// text.  No consensus arithmetic happens on the host.
+std::string regroup_by_query(const char* text, uint64_t n) {
+    struct Row {
+        uint64_t off;
+        uint32_t len;
+    };
+    std::unordered_map<std::string_view, uint32_t> gid;
+    std::vector<std::vector<Row>> groups;
+    for (uint64_t p = 0; p < n;) {
+        const char* nl = (const char*)memchr(text + p, '\n', n - p);
+        const uint64_t e = nl ? (uint64_t)(nl - text) : n;
+        if (e > p) {
+            const char* tab = (const char*)memchr(text + p, '\t', e - p);
+            std::string_view q(text + p, tab ? (size_t)(tab - (text + p)) : (size_t)(e - p));
+            auto it = gid.find(q);
+            uint32_t g;
+            if (it == gid.end()) {
+                g = (uint32_t)groups.size();
+                gid.emplace(q, g);
+                groups.emplace_back();
+            } else
+                g = it->second;
+            groups[g].push_back({p, (uint32_t)(e - p)});
+        }
+        p = e + 1;
+    }
+    std::string out;
+    out.reserve(n + 1);
+    for (auto& g : groups)
+        for (auto& r : g) {
+            out.append(text + r.off, r.len);
+            out.push_back('\n');
+        }
+    return out;
+}
+
+struct NonContiguous : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
 // --- text resident on the device ------------------------------------------------------------------------------
 void run_device(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStream_t s, blu_result* r) {
     require_ready(c);
@@ -462,8 +507,7 @@ void run_device(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStream_t s, bl
             continue;
         }
         check_device_error(c, h, 0);
-        if (h.dup_found)
-            throw UnsupportedErr("a query id occurs in two non-adjacent groups of rows; non-contiguous hit tables are not supported yet");
+        if (h.dup_found) throw NonContiguous("a query id occurs in two non-adjacent groups of rows");
         if (n_rec_of(h) == 0) throw DataErr("the blast output holds no rows");
         c->tm.ms_tile_kernel = ev_ms(c->ev[0], c->ev[1]);
         c->tm.ms_longrun_kernel = ev_ms(c->ev[1], c->ev[2]);
@@ -570,8 +614,7 @@ void run_host(blu_ctx* c, const char* text, uint64_t n, blu_result* r) {
             continue;
         }
         check_device_error(c, h, 0);
-        if (h.dup_found)
-            throw UnsupportedErr("a query id occurs in two non-adjacent groups of rows; non-contiguous hit tables are not supported yet");
+        if (h.dup_found) throw NonContiguous("a query id occurs in two non-adjacent groups of rows");
         if (n_rec_of(h) == 0) throw DataErr("the blast output holds no rows");
         c->tm.ms_tile_kernel = ms_tile;
         c->tm.ms_longrun_kernel = ms_long;
@@ -707,7 +750,18 @@ int blu_consensus_run_device(blu_ctx* c, const void* dtext, uint64_t n, void* st
         CK(cudaSetDevice(c->device));
         r->tax = c->tax;
         r->cut = c->cut;
-        run_device(c, (const uint8_t*)dtext, n, stream ? (cudaStream_t)stream : c->stream, r.get());
+        try {
+            run_device(c, (const uint8_t*)dtext, n, stream ? (cudaStream_t)stream : c->stream, r.get());
+        } catch (const NonContiguous&) {
+            // regroup on the host (data movement only), then the normal streamed path
+            std::string host(n, '\0');
+            CK(cudaMemcpy(host.data(), dtext, n, cudaMemcpyDeviceToHost));
+            std::string re = regroup_by_query(host.data(), n);
+            host.clear();
+            host.shrink_to_fit();
+            run_host(c, re.data(), re.size(), r.get());
+            c->tm.n_regrouped = 1;
+        }
     });
     if (rc != BLU_OK) {
         blu_result_free(r.release());
@@ -726,7 +780,13 @@ int blu_consensus_run_host(blu_ctx* c, const char* text, uint64_t n, blu_result*
         CK(cudaSetDevice(c->device));
         r->tax = c->tax;
         r->cut = c->cut;
-        run_host(c, text, n, r.get());
+        try {
+            run_host(c, text, n, r.get());
+        } catch (const NonContiguous&) {
+            std::string re = regroup_by_query(text, n);
+            run_host(c, re.data(), re.size(), r.get());
+            c->tm.n_regrouped = 1;
+        }
     });
     if (rc != BLU_OK) {
         blu_result_free(r.release());
@@ -861,6 +921,51 @@ int blu_ctx_measure_h2d(blu_ctx* c, uint64_t bytes, double* gbps) {
         cudaFreeHost(h);
         *gbps = best;
     });
+}
+
+int blu_shard_cuts(const char* text, uint64_t n, int n_shards, uint64_t* cuts) {
+    if (!cuts || n_shards < 1 || (!text && n)) return BLU_ERR_ARG;
+    auto first_field = [&](uint64_t p) {
+        const char* e = (const char*)memchr(text + p, '\n', n - p);
+        const uint64_t re = e ? (uint64_t)(e - text) : n;
+        const char* t = (const char*)memchr(text + p, '\t', re - p);
+        return std::string_view(text + p, t ? (size_t)(t - (text + p)) : (size_t)(re - p));
+    };
+    auto next_row = [&](uint64_t p) {  // start of the next non-empty row after the row containing p
+        const char* e = (const char*)memchr(text + p, '\n', n - p);
+        uint64_t q = e ? (uint64_t)(e - text) + 1 : n;
+        while (q < n && text[q] == '\n') q++;
+        return q;
+    };
+    cuts[0] = 0;
+    cuts[n_shards] = n;
+    for (int k = 1; k < n_shards; k++) {
+        uint64_t p = std::max<uint64_t>(cuts[k - 1], n / (uint64_t)n_shards * (uint64_t)k);
+        if (p >= n) {
+            cuts[k] = n;
+            continue;
+        }
+        // first row start at/after p
+        if (p > 0 && text[p - 1] != '\n') p = next_row(p);
+        while (p < n && text[p] == '\n') p++;
+        if (p >= n) {
+            cuts[k] = n;
+            continue;
+        }
+        // previous non-empty row
+        if (p > 0) {
+            uint64_t q = p - 1;
+            while (q > 0 && text[q] == '\n') q--;
+            if (text[q] != '\n') {
+                uint64_t st = q;
+                while (st > 0 && text[st - 1] != '\n') st--;
+                const std::string_view run = first_field(st);
+                while (p < n && first_field(p) == run) p = next_row(p);  // never split a query
+            }
+        }
+        cuts[k] = p;
+    }
+    return BLU_OK;
 }
 
 void* blu_host_alloc(uint64_t bytes) {

@@ -83,7 +83,7 @@ typedef struct blu_record {
     int8_t allowed_pos;     /* lineage position of maxAllowedRank, -1 = null */
     int8_t bean_level;      /* lineage position the consensus beans were taken at */
     uint8_t pad[2];
-} blu_record; /* 72 bytes */
+} blu_record; /* 64 bytes */
 
 typedef struct blu_bean {
     uint32_t first_lineage; /* lineage of the first (sorted) row carrying this bean: its `taxonomy` string */
@@ -108,7 +108,8 @@ typedef struct blu_timings {
     uint64_t text_bytes, result_bytes, taxonomy_bytes;
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t n_queries, n_rows, n_deferred_runs, n_kernel_launches;
-    uint64_t reserved[4];
+    uint64_t n_regrouped; /* 1 when the table was non-contiguous and had to be regrouped by query first */
+    uint64_t reserved[3];
 } blu_timings;
 
 /* ---- context ------------------------------------------------------------------------------------------- */
@@ -158,6 +159,12 @@ void blu_free(void* p);
 int blu_ctx_last_timings(const blu_ctx* ctx, blu_timings* out);
 /* Measured pinned host->device copy bandwidth (GB/s) on ctx's device, for the end-to-end ceiling. */
 int blu_ctx_measure_h2d(blu_ctx* ctx, uint64_t bytes, double* gbps);
+
+/* Multi-GPU sharding: byte offsets cuts[0..n_shards] that split the table into n_shards ranges of
+ * roughly equal size without ever splitting a query (cuts move forward to the next query boundary).  Valid for
+ * contiguous tables (every query's rows adjacent), which is what BLAST and blutils' chunked appends
+ * (run_parallel_blast.rs:97,146-151) produce.  Host-only; needs no GPU. */
+int blu_shard_cuts(const char* text, uint64_t n_bytes, int n_shards, uint64_t* cuts);
 
 /* Pinned host buffers (cudaHostAlloc) so callers can stage text for blu_consensus_run_host. */
 void* blu_host_alloc(uint64_t bytes);

@@ -164,14 +164,45 @@ def test_reference_abort_cases(bad):
     eng.close()
 
 
-def test_noncontiguous_is_loud():
-    from blutils_b200 import Unsupported
+@pytest.mark.parametrize("seed", range(6))
+def test_noncontiguous_tables(seed):
+    """Rows of one query scattered over the file (legal for the reference's HashMap grouping, mod.rs:145,192):
+    detected on the GPU (dup_kernel), regrouped by query, then the normal path."""
+    rng = random.Random(300 + seed)
+    units = random_taxonomy(rng, n_leaves=30)
+    text = random_blast(rng, units, n_queries=40, contiguous=False)
+    lin = [u["textLineage"] for u in units]
+    ids = [u["taxid"] for u in units]
+    from oracle_ffi import OracleDataError
 
+    try:
+        want = _oracle(ids, lin, "fungi", "relaxed").run_raw(text)[0]
+    except OracleDataError:
+        pytest.skip("generated case hits a reference abort")
+    eng = _engine("fungi", "relaxed")
+    eng.load_taxonomy_arrays(ids, lin)
+    out = eng.run_host(text)
+    assert out.jsonl() == want
+    assert int(eng.timings()["n_regrouped"]) in (0, 1)
+    eng.close()
+
+
+def test_sharded_equals_whole():
+    """query-range shards (blu_shard_cuts) processed independently and concatenated == the whole table."""
+    from blutils_b200 import shard_cuts
+
+    ids, lin, text = _synth_case(3000, 3000, 50, seed=21)
     eng = _engine("bacteria", "cautious")
-    eng.load_taxonomy_arrays([1], ["d__a;p__b"])
-    text = (_row("q1", "a", 1, "99.0", 10, "50") + _row("q2", "a", 1, "99.0", 10, "50") + _row("q1", "b", 1, "99.0", 10, "50")).encode()
-    with pytest.raises(Unsupported):
-        eng.run_host(text)
+    eng.load_taxonomy_arrays(ids, lin)
+    whole = eng.run_host(text).jsonl()
+    for n in (2, 3, 8):
+        cuts = shard_cuts(text, n)
+        assert cuts[0] == 0 and cuts[-1] == len(text) and cuts == sorted(cuts)
+        parts = []
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            if b > a:
+                parts += eng.run_host(text[a:b]).jsonl().decode().splitlines()
+        assert "\n".join(sorted(parts, key=lambda l: l.encode())) + "\n" == whole.decode()
     eng.close()
 
 
