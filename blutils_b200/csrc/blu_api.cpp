@@ -140,7 +140,7 @@ struct blu_ctx {
     DevBuf<blu_record> d_rec;
     DevBuf<blu_bean> d_beans;
     DevBuf<blu_acc> d_accs;
-    DevBuf<TopRow> d_top;
+    DevBuf<TopRowRaw> d_top;
     DevBuf<uint64_t> d_defer;
     DevBuf<uint8_t> d_pool;
     DevBuf<unsigned long long> d_dup;

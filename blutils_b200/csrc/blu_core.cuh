@@ -593,6 +593,50 @@ BLU_HD uint32_t heavy_parse_row(const uint8_t* p, int len, uint64_t row_abs_off,
     return DE_NONE;
 }
 
+// A top-group row as the tile kernel emits it: numbers parsed, lineage not joined yet (the consensus kernel probes
+// the taxid table, where full occupancy hides the lookup latency).
+struct TopRowRaw {
+    double pident;
+    int64_t alnlen;
+    uint64_t acc_off;  // absolute offset of saccver in the text buffer
+    int64_t taxid;
+    uint32_t acc_len;
+    uint32_t pad;
+};
+
+BLU_HD uint32_t split_top_row(const uint8_t* win, const uint64_t* tabw, int s, int e, uint64_t lo, TopRowRaw& out) {
+    const int t0 = next_tab(tabw, s, e);
+    const int t1 = t0 < e ? next_tab(tabw, t0 + 1, e) : e;
+    const int t2 = t1 < e ? next_tab(tabw, t1 + 1, e) : e;
+    const int t3 = t2 < e ? next_tab(tabw, t2 + 1, e) : e;
+    const int t4 = t3 < e ? next_tab(tabw, t3 + 1, e) : e;
+    if (t4 >= e) return DE_BAD_FIELD_COUNT;
+    out.acc_off = lo + (uint64_t)t0 + 1;
+    const int alen = t1 - t0 - 1;
+    if (alen > 65535) return DE_NUM_UNSUPPORTED;
+    out.acc_len = (uint32_t)alen;
+    out.pad = 0;
+    if (!parse_i64(win + t1 + 1, t2 - t1 - 1, out.taxid)) return DE_BAD_NUMBER;
+    uint32_t er = parse_f64(win + t2 + 1, t3 - t2 - 1, out.pident);
+    if (er) return er;
+    if (!parse_i64(win + t3 + 1, t4 - t3 - 1, out.alnlen)) return DE_BAD_NUMBER;
+    return DE_NONE;
+}
+
+// the join: taxid -> lineage (mod.rs:72-76); a miss / unparsable lineage in a top group is what makes the reference panic
+BLU_HD uint32_t join_top_row(const TopRowRaw& raw, const LinTables& T, TopRow& out) {
+    out.pident = raw.pident;
+    out.alnlen = raw.alnlen;
+    out.acc_off = raw.acc_off;
+    out.acc_len = (uint16_t)raw.acc_len;
+    const uint32_t lin = probe_taxid(T, raw.taxid);
+    if (lin == 0xFFFFFFFFu) return DE_UNMAPPED_TAXID;
+    if (!T.lin_ok[lin]) return DE_BAD_LINEAGE;
+    out.lin = lin;
+    out.lin_len = (uint16_t)(T.lin_off[lin + 1] - T.lin_off[lin]);
+    return DE_NONE;
+}
+
 // Same as heavy_parse_row, with the field boundaries taken from the tab mask.  `lo` = absolute offset of win[0].
 BLU_HD uint32_t heavy_parse_row_masked(const uint8_t* win, const uint64_t* tabw, int s, int e, uint64_t lo, const LinTables& T, TopRow& out) {
     const int t0 = next_tab(tabw, s, e);

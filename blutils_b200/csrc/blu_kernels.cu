@@ -25,6 +25,8 @@ namespace {
 constexpr int kWarps = kTileThreads / 32;
 constexpr int kRowCap = kWin / 26 + 16;   // a valid row is >= 26 bytes (13 one-byte fields, 12 tabs, '\n')
 constexpr int kMaxRuns = kRowCap;           // owned heads <= rows in the window
+constexpr int kTopList = 768;             // top rows a tile can queue (beyond: block path)
+constexpr int kTileQ = 384;               // queries a tile can queue (beyond: block path)
 constexpr int kLongTopCap = 1024;         // largest top bit-score group the block path sorts
 constexpr int kLongThreads = 256;
 constexpr int kLongWarps = kLongThreads / 32;
@@ -138,11 +140,17 @@ __device__ __forceinline__ uint32_t bytes_digit(uint32_t x) {
     uint32_t t = x ^ 0x30303030u;  // '0'..'9' -> 0..9
     return ~(((t & 0x7F7F7F7Fu) + 0x76767676u) | t) & 0x80808080u;
 }
-// gathers the four 0x80 flags of a word into its low nibble
-__device__ __forceinline__ uint32_t pack4(uint32_t m) { return ((m >> 7) * 0x01020408u) >> 24; }
-
+// bytes below 0x23 ('#'): control characters, space, '!' and '"'.  In clean BLAST text only tab and newline are.
+__device__ __forceinline__ uint32_t bytes_below_23(uint32_t x) {
+    uint32_t t = (x | 0x80808080u) - 0x23232323u;  // no borrow between bytes; bit 7 survives iff (x & 0x7f) >= 0x23
+    return ~t & ~x & 0x80808080u;
+}
+// Gathers the sixteen 0x80 flags of four words into a 16-bit mask with four dot products:
+// a flag byte is 0x80 = 128, so dp4a(flags, weights) = 128 * (sum of the weights of the set bytes).
 __device__ __forceinline__ uint32_t pack16(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    return (pack4(a) & 15u) | ((pack4(b) & 15u) << 4) | ((pack4(c) & 15u) << 8) | ((pack4(d) & 15u) << 12);
+    const uint32_t lo = __dp4a(a, 0x08040201u, __dp4a(b, 0x80402010u, 0u));
+    const uint32_t hi = __dp4a(c, 0x08040201u, __dp4a(d, 0x80402010u, 0u));
+    return (lo >> 7) | (hi << 1);
 }
 
 __device__ __forceinline__ uint32_t range_mask16(int pos0, int lo, int hi) {  // bits k with lo <= pos0+k < hi
@@ -162,13 +170,18 @@ __device__ __forceinline__ void classify_chunk(WindowIndex& W, const WinGeom& g,
     const uint4 v = *reinterpret_cast<const uint4*>(W.win + pos0);
     const int rb = g.rb < 0 ? 0 : g.rb;
     const int tend = g.re < g.loaded ? g.re : g.loaded;  // end of the text inside the window
-    uint32_t nl = pack16(bytes_eq(v.x, 0x0A0A0A0Au), bytes_eq(v.y, 0x0A0A0A0Au), bytes_eq(v.z, 0x0A0A0A0Au), bytes_eq(v.w, 0x0A0A0A0Au));
-    W.tabm[c] = (uint16_t)pack16(bytes_eq(v.x, 0x09090909u), bytes_eq(v.y, 0x09090909u), bytes_eq(v.z, 0x09090909u), bytes_eq(v.w, 0x09090909u));
+    const uint32_t nx = bytes_eq(v.x, 0x0A0A0A0Au), ny = bytes_eq(v.y, 0x0A0A0A0Au), nz = bytes_eq(v.z, 0x0A0A0A0Au), nw = bytes_eq(v.w, 0x0A0A0A0Au);
+    const uint32_t tx = bytes_eq(v.x, 0x09090909u), ty = bytes_eq(v.y, 0x09090909u), tz = bytes_eq(v.z, 0x09090909u), tw = bytes_eq(v.w, 0x09090909u);
+    uint32_t nl = pack16(nx, ny, nz, nw);
+    W.tabm[c] = (uint16_t)pack16(tx, ty, tz, tw);
     W.digm[c] = (uint16_t)pack16(bytes_digit(v.x), bytes_digit(v.y), bytes_digit(v.z), bytes_digit(v.w));
-    const uint32_t qx = bytes_eq(v.x, 0x22222222u) | bytes_eq(v.x, 0x0D0D0D0Du), qy = bytes_eq(v.y, 0x22222222u) | bytes_eq(v.y, 0x0D0D0D0Du),
-                   qz = bytes_eq(v.z, 0x22222222u) | bytes_eq(v.z, 0x0D0D0D0Du), qw = bytes_eq(v.w, 0x22222222u) | bytes_eq(v.w, 0x0D0D0D0Du);
-    if (qx | qy | qz | qw) {
-        const uint32_t qm = pack16(qx, qy, qz, qw) & range_mask16(pos0, g.qlo, g.qhi);
+    // any byte below 0x23 that is neither tab nor newline is suspicious; only then look for '"' / '\r' exactly
+    const uint32_t sus = (bytes_below_23(v.x) & ~(nx | tx)) | (bytes_below_23(v.y) & ~(ny | ty)) | (bytes_below_23(v.z) & ~(nz | tz)) |
+                         (bytes_below_23(v.w) & ~(nw | tw));
+    if (sus) {
+        const uint32_t qm = pack16(bytes_eq(v.x, 0x22222222u) | bytes_eq(v.x, 0x0D0D0D0Du), bytes_eq(v.y, 0x22222222u) | bytes_eq(v.y, 0x0D0D0D0Du),
+                                   bytes_eq(v.z, 0x22222222u) | bytes_eq(v.z, 0x0D0D0D0Du), bytes_eq(v.w, 0x22222222u) | bytes_eq(v.w, 0x0D0D0D0Du)) &
+                            range_mask16(pos0, g.qlo, g.qhi);
         if (qm) atomicMin(&W.bad_byte, pos0 + __ffs(qm) - 1);
     }
     uint32_t tmask = 0xFFFFu;
@@ -196,24 +209,20 @@ __device__ bool scan_rows(WindowIndex& W, const WinGeom& g) {
     const int c1 = c0 + cpw < nchunks ? c0 + cpw : nchunks;
     const int rb = g.rb < 0 ? 0 : g.rb;
     // ---- pass 1: classify, count ---------------------------------------------------------------------------------
-    int cnt = 0;
+    // A valid row is >= 26 bytes, so a 16-byte chunk holds at most one row start and one row end; a chunk with more
+    // proves a malformed (too short) row and is reported as such.  That makes the row index a matter of ballots.
+    int ns = 0, ne = 0;
+    bool crowded = false;
     uint32_t carry_in = 0;
     if (c0 < c1 && (c0 << 4) > rb) carry_in = W.win[(c0 << 4) - 1] == '\n';
     for (int base = c0; base < c1; base += 32) {
         const int c = base + lane;
         uint32_t nl = 0, s = 0, e = 0;
         const bool live = c < c1;
-        // the newline status of the byte in front of the chunk comes from the neighbouring lane
-        uint32_t v_nl = 0;
-        if (live) {
-            // cheap pre-classification of the last byte of the previous chunk is not available yet: classify with a
-            // provisional carry of 0 and patch bit 0 below
-            classify_chunk(W, g, c, 0u, nl, s, e);
-            v_nl = nl;
-        }
-        uint32_t up = __shfl_up_sync(0xffffffffu, v_nl, 1);
-        uint32_t carry = lane == 0 ? carry_in : (up >> 15) & 1u;
-        carry_in = (__shfl_sync(0xffffffffu, v_nl, 31) >> 15) & 1u;
+        if (live) classify_chunk(W, g, c, 0u, nl, s, e);  // provisional carry 0, bit 0 is patched below
+        const uint32_t up = __shfl_up_sync(0xffffffffu, nl, 1);
+        const uint32_t carry = lane == 0 ? carry_in : (up >> 15) & 1u;
+        carry_in = (__shfl_sync(0xffffffffu, nl, 31) >> 15) & 1u;
         if (live && carry) {
             const int pos0 = c << 4;
             if (pos0 >= rb && !(g.rb >= 0 && pos0 == g.rb)) {
@@ -227,33 +236,37 @@ __device__ bool scan_rows(WindowIndex& W, const WinGeom& g) {
         if (live) {
             W.startm[c] = (uint16_t)s;
             W.endm[c] = (uint16_t)e;
-            cnt += __popc(s) | (__popc(e) << 16);
+            crowded |= (s & (s - 1)) != 0 || (e & (e - 1)) != 0;
         }
+        ns += __popc(__ballot_sync(0xffffffffu, s != 0));
+        ne += __popc(__ballot_sync(0xffffffffu, e != 0));
     }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, d);
-    if (lane == 0) W.warp_cnt[w] = cnt;
+    crowded = __any_sync(0xffffffffu, crowded);
+    if (lane == 0) W.warp_cnt[w] = ns | (ne << 16) | (crowded ? 0x80000000 : 0);
     __syncthreads();
     int so = 0, eo = 0, ts = 0, te = 0;
+    bool any_crowded = false;
 #pragma unroll
     for (int i = 0; i < NWARPS; i++) {
-        int v = W.warp_cnt[i];
+        const int v = W.warp_cnt[i];
+        any_crowded |= v < 0;
         if (i < w) {
             so += v & 0xFFFF;
-            eo += v >> 16;
+            eo += (v >> 16) & 0x7FFF;
         }
         ts += v & 0xFFFF;
-        te += v >> 16;
+        te += (v >> 16) & 0x7FFF;
     }
     if (tid == 0) {
         W.n_starts = ts;
         W.n_ends = te;
     }
-    if (ts > kRowCap || te > kRowCap) {
+    if (any_crowded || ts > kRowCap || te > kRowCap) {
         __syncthreads();
         return false;
     }
     // ---- pass 2: positions ---------------------------------------------------------------------------------------------
+    const uint32_t lt = (1u << lane) - 1u;
     for (int base = c0; base < c1; base += 32) {
         const int c = base + lane;
         uint32_t s = 0, e = 0;
@@ -261,30 +274,12 @@ __device__ bool scan_rows(WindowIndex& W, const WinGeom& g) {
             s = W.startm[c];
             e = W.endm[c];
         }
-        if (!__ballot_sync(0xffffffffu, (s | e) != 0)) continue;
-        int mine = __popc(s) | (__popc(e) << 16);
-        int inc = mine;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            int t = __shfl_up_sync(0xffffffffu, inc, d);
-            if (lane >= d) inc += t;
-        }
-        int tot = __shfl_sync(0xffffffffu, inc, 31);
-        int ex = inc - mine;
-        int os = so + (ex & 0xFFFF), oe = eo + (ex >> 16);
+        const uint32_t bs = __ballot_sync(0xffffffffu, s != 0), be = __ballot_sync(0xffffffffu, e != 0);
         const int pos0 = c << 4;
-        while (s) {
-            int k = __ffs(s) - 1;
-            s &= s - 1;
-            W.row_s[os++] = (uint16_t)(pos0 + k);
-        }
-        while (e) {
-            int k = __ffs(e) - 1;
-            e &= e - 1;
-            W.row_e[oe++] = (uint16_t)(pos0 + k);
-        }
-        so += tot & 0xFFFF;
-        eo += tot >> 16;
+        if (s) W.row_s[so + __popc(bs & lt)] = (uint16_t)(pos0 + __ffs(s) - 1);
+        if (e) W.row_e[eo + __popc(be & lt)] = (uint16_t)(pos0 + __ffs(e) - 1);
+        so += __popc(bs);
+        eo += __popc(be);
     }
     __syncthreads();
     return true;
@@ -310,12 +305,24 @@ struct WarpScratch {
     uint16_t idx[32];
 };
 
+struct TileQuery {
+    uint16_t head;    // row index of the query's first row
+    uint16_t n_rows;
+    uint16_t g;       // size of the top bit-score group
+    uint16_t top0;    // first entry in top_row[]
+    int32_t bits;     // truncated top bit score
+};
+
 struct TileSmem {
     WindowIndex W;
     int32_t bits[kRowCap];
     uint8_t flags[kRowCap];  // bit0: head of a run, bit1: bit score does not fit int32
     uint16_t runs[kMaxRuns];
     WarpScratch ws[kWarps];
+    uint16_t top_row[kTopList];   // row indices of the top bit-score rows of the tile's queries
+    TileQuery q[kTileQ];          // the tile's finished queries
+    unsigned long long rs_base;   // packed (first record, first slot) reserved for this tile
+    int n_top, n_q;
     int n_runs;
     int next_run;    // dynamic distribution of the runs over the warps
     int first_fwd;   // index of the first row of the look-ahead region (start >= own_hi)
@@ -357,6 +364,8 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
             W.bad_byte = INT_MAX;
             S.n_runs = 0;
             S.next_run = 0;
+            S.n_top = 0;
+            S.n_q = 0;
             S.first_fwd = 0x7fffffff;
         }
         const unsigned long long own_lo = base, own_hi = base + kTile;
@@ -425,12 +434,15 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
             if (abs >= own_lo && abs < own_hi) push_defer(p, abs, 1);  // unterminated row: the block path sorts it out
         }
         __syncthreads();
-        // ---- phase D: one warp per run ----------------------------------------------------------------------------
+        // ---- phase D: one warp per run: extent, top bit-score group (shared memory only) -----------------------------
+        // D and E repeat in batches when a tile holds more queries / top rows than its queues (tables with one or two
+        // hits per query); a warp only claims a run while every warp could still queue a full 32-row top group.
         const int n_runs = S.n_runs;
         WarpScratch& ws = S.ws[warp];
+        for (bool more = n_runs > 0; more;) {
         while (true) {
-            int ri = 0;
-            if (lane == 0) ri = atomicAdd(&S.next_run, 1);
+            int ri = n_runs;
+            if (lane == 0 && S.n_q <= kTileQ - kWarps && S.n_top <= kTopList - 32 * kWarps) ri = atomicAdd(&S.next_run, 1);
             ri = __shfl_sync(0xffffffffu, ri, 0);
             if (ri >= n_runs) break;
             const int h = S.runs[ri];
@@ -503,40 +515,92 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
                 if (lane == 0) push_defer(p, h_abs, 0);
                 continue;
             }
-            // reserve one record + gcount top-row slots with a single packed atomic
-            unsigned long long rs = 0;
-            if (lane == 0) rs = atomicAdd(&p.ctr->rec_slots, (1ull << 32) | (unsigned long long)gcount);
-            rs = __shfl_sync(0xffffffffu, rs, 0);
-            const unsigned rec_i = (unsigned)(rs >> 32), slot = (unsigned)rs;
-            if (rec_i >= p.rec_cap || slot + (unsigned)gcount > p.slot_cap) {
-                if (lane == 0) p.ctr->cap_overflow = 1;
-                continue;
-            }
-            // join: each lane parses one top row and probes the taxid table; the rows go to the top-row table
-            uint32_t err = 0;
-            if (lane < gcount) {
-                const int r = ws.idx[lane];
-                const int s = W.row_s[r];
-                TopRow tr;
-                err = heavy_parse_row_masked(W.win, tabw, s, W.row_e[r + eskip], lo, p.T, tr);
-                if (err)
-                    report(p.ctr, err, lo + s);
-                else
-                    p.toprows[slot + lane] = tr;
-            }
-            err = __any_sync(0xffffffffu, err != 0);
+            // queue the query and its top rows for phase E (tile-local positions; global slots are reserved once per tile)
+            int qi = 0, tpos = 0;
             if (lane == 0) {
-                blu_record* rec = p.records + rec_i;
-                rec->query_off = h_abs;
-                rec->query_len = (uint32_t)(next_tab(tabw, W.row_s[h], W.row_e[h + eskip]) - (int)W.row_s[h]);
-                rec->n_rows = (uint32_t)(e - h);
-                rec->bit_score = (int64_t)mx;
-                rec->slot_base = slot;
-                rec->n_accessions = (uint32_t)gcount;  // size of the top group until the consensus kernel overwrites it
-                rec->n_beans = 0;
-                rec->status = err ? 0 : 2;             // 2 = waiting for the consensus kernel
-                rec->pad[0] = rec->pad[1] = 0;
+                qi = atomicAdd(&S.n_q, 1);
+                tpos = atomicAdd(&S.n_top, gcount);
             }
+            qi = __shfl_sync(0xffffffffu, qi, 0);
+            tpos = __shfl_sync(0xffffffffu, tpos, 0);
+            if (lane < gcount) S.top_row[tpos + lane] = ws.idx[lane];
+            if (lane == 0) {
+                TileQuery& q = S.q[qi];
+                q.head = (uint16_t)h;
+                q.n_rows = (uint16_t)(e - h);
+                q.g = (uint16_t)gcount;
+                q.top0 = (uint16_t)tpos;
+                q.bits = mx;
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+        // ---- phase E: one reservation per tile, then one thread per top row / per query writes to HBM ----------------
+        const int n_q = S.n_q, n_top = S.n_top;
+        if (tid == 0 && n_q > 0) S.rs_base = atomicAdd(&p.ctr->rec_slots, ((unsigned long long)n_q << 32) | (unsigned long long)n_top);
+        // field split + number parse of the top rows overlaps the latency of the atomic
+        TopRowRaw tr[(kTopList + kTileThreads - 1) / kTileThreads];
+        uint32_t terr = 0;
+#pragma unroll
+        for (int k = 0; k < (kTopList + kTileThreads - 1) / kTileThreads; k++) {
+            const int i = tid + k * kTileThreads;
+            if (i < n_top) {
+                const int r = S.top_row[i];
+                const int s = W.row_s[r];
+                const uint32_t er = split_top_row(W.win, tabw, s, W.row_e[r + eskip], lo, tr[k]);
+                if (er) {
+                    report(p.ctr, er, lo + s);
+                    terr = er;
+                }
+            }
+        }
+        __syncthreads();
+        if (n_q > 0) {
+            const unsigned long long rs = S.rs_base;
+            const unsigned rec0 = (unsigned)(rs >> 32), slot0 = (unsigned)rs;
+            if (rec0 + (unsigned)n_q > p.rec_cap || slot0 + (unsigned)n_top > p.slot_cap) {
+                if (tid == 0) p.ctr->cap_overflow = 1;
+            } else {
+#pragma unroll
+                for (int k = 0; k < (kTopList + kTileThreads - 1) / kTileThreads; k++) {
+                    const int i = tid + k * kTileThreads;
+                    if (i < n_top) p.toprows[slot0 + i] = tr[k];
+                }
+                for (int j = tid; j < n_q; j += kTileThreads) {
+                    const TileQuery q = S.q[j];
+                    const int s = W.row_s[q.head];
+                    blu_record rec;
+                    rec.query_off = lo + s;
+                    rec.query_len = (uint32_t)(next_tab(tabw, s, W.row_e[q.head + eskip]) - s);
+                    rec.n_rows = q.n_rows;
+                    rec.keep_mask = 0;
+                    rec.perc_identity = 0.0;
+                    rec.bit_score = (int64_t)q.bits;
+                    rec.ref_lineage = 0;
+                    rec.slot_base = slot0 + q.top0;
+                    rec.n_beans = 0;
+                    rec.n_accessions = q.g;  // size of the top group until the consensus kernel overwrites it
+                    rec.status = 2;          // waiting for the consensus kernel
+                    rec.single_match = 0;
+                    rec.mutated = 0;
+                    rec.reached_pos = 0;
+                    rec.allowed_pos = -1;
+                    rec.bean_level = 0;
+                    rec.pad[0] = rec.pad[1] = 0;
+                    p.records[rec0 + j] = rec;
+                }
+            }
+        }
+        (void)terr;
+        more = S.next_run < n_runs;  // stable since the barrier that ended phase D (next_run may overshoot n_runs)
+        if (more) {                  // rare: start the next batch with empty queues
+            __syncthreads();
+            if (tid == 0) {
+                S.n_q = 0;
+                S.n_top = 0;
+            }
+            __syncthreads();
+        }
         }
     }
 }
@@ -914,11 +978,20 @@ __global__ void __launch_bounds__(256) consensus_kernel(const ConsParams p) {
     TopRow r;
     r.pident = 0.0, r.alnlen = 0, r.acc_off = 0, r.lin = 0, r.acc_len = 0, r.lin_len = 0;
     uint32_t pos0 = 0;
+    uint32_t jerr = 0;
     if (on) {
-        r = p.toprows[slot + lane];
-        pos0 = T.lin_off[r.lin];
+        // the join (left_join on subject_taxid == taxid, mod.rs:72-76): probe the taxid table
+        const TopRowRaw raw = p.toprows[slot + lane];
+        jerr = join_top_row(raw, T, r);
+        if (jerr)
+            report(p.ctr, jerr, raw.acc_off);
+        else
+            pos0 = T.lin_off[r.lin];
     }
-    __syncwarp();
+    if (__any_sync(FULL, jerr != 0)) {
+        if (lane == 0) rec->status = 0;
+        return;
+    }
     if (g == 1) {
         // single match (find_single_query_consensus.rs:74-150)
         const uint32_t o = __shfl_sync(FULL, pos0, 0);

@@ -31,7 +31,7 @@ struct RunParams {
     uint32_t rec_cap;
     blu_bean* beans;
     blu_acc* accs;
-    TopRow* toprows;       // top bit-score rows of every query (joined with the lineage tables), slot-indexed
+    TopRowRaw* toprows;    // top bit-score rows of every query (numbers parsed, lineage not joined yet), slot-indexed
     uint32_t slot_cap;
     uint64_t* defer;       // (offset << 1) | check_prev
     uint32_t defer_cap;
@@ -41,7 +41,7 @@ struct RunParams {
 struct ConsParams {
     blu_record* records;
     uint32_t rec_begin, rec_end;
-    const TopRow* toprows;
+    const TopRowRaw* toprows;
     blu_bean* beans;
     blu_acc* accs;
     const uint8_t* text;

@@ -71,7 +71,8 @@ def _synth_case(n_taxa, n_queries, hits, zipf=False, seed=11):
     return ids.tolist(), lin, text
 
 
-@pytest.mark.parametrize("n_queries,hits,zipf", [(300, 50, False), (4000, 50, False), (2000, 100, False), (600, 5000, True)])
+@pytest.mark.parametrize("n_queries,hits,zipf", [(300, 50, False), (4000, 50, False), (2000, 100, False), (600, 5000, True),
+                                                 (40000, 1, False), (30000, 2, False), (3000, 200, False)])
 def test_synth_vs_oracle(n_queries, hits, zipf):
     """Multi-tile inputs (0.1 - 30 MB): windows, ownership, look-ahead, long-run path (Zipf up to 5000 hits)."""
     ids, lin, text = _synth_case(5000, n_queries, hits, zipf)
