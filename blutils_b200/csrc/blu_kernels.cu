@@ -319,10 +319,6 @@ struct TileSmem {
     uint8_t flags[kRowCap];  // bit0: head of a run, bit1: bit score does not fit int32
     uint16_t runs[kMaxRuns];
     WarpScratch ws[kWarps];
-    uint16_t top_row[kTopList];   // row indices of the top bit-score rows of the tile's queries
-    TileQuery q[kTileQ];          // the tile's finished queries
-    unsigned long long rs_base;   // packed (first record, first slot) reserved for this tile
-    int n_top, n_q;
     int n_runs;
     int next_run;    // dynamic distribution of the runs over the warps
     int first_fwd;   // index of the first row of the look-ahead region (start >= own_hi)
@@ -364,8 +360,6 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
             W.bad_byte = INT_MAX;
             S.n_runs = 0;
             S.next_run = 0;
-            S.n_top = 0;
-            S.n_q = 0;
             S.first_fwd = 0x7fffffff;
         }
         const unsigned long long own_lo = base, own_hi = base + kTile;
@@ -434,15 +428,12 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
             if (abs >= own_lo && abs < own_hi) push_defer(p, abs, 1);  // unterminated row: the block path sorts it out
         }
         __syncthreads();
-        // ---- phase D: one warp per run: extent, top bit-score group (shared memory only) -----------------------------
-        // D and E repeat in batches when a tile holds more queries / top rows than its queues (tables with one or two
-        // hits per query); a warp only claims a run while every warp could still queue a full 32-row top group.
+        // ---- phase D: one warp per run: extent, top bit-score group, top rows + record header to HBM ------------------
         const int n_runs = S.n_runs;
         WarpScratch& ws = S.ws[warp];
-        for (bool more = n_runs > 0; more;) {
         while (true) {
-            int ri = n_runs;
-            if (lane == 0 && S.n_q <= kTileQ - kWarps && S.n_top <= kTopList - 32 * kWarps) ri = atomicAdd(&S.next_run, 1);
+            int ri = 0;
+            if (lane == 0) ri = atomicAdd(&S.next_run, 1);
             ri = __shfl_sync(0xffffffffu, ri, 0);
             if (ri >= n_runs) break;
             const int h = S.runs[ri];
@@ -515,92 +506,47 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
                 if (lane == 0) push_defer(p, h_abs, 0);
                 continue;
             }
-            // queue the query and its top rows for phase E (tile-local positions; global slots are reserved once per tile)
-            int qi = 0, tpos = 0;
-            if (lane == 0) {
-                qi = atomicAdd(&S.n_q, 1);
-                tpos = atomicAdd(&S.n_top, gcount);
-            }
-            qi = __shfl_sync(0xffffffffu, qi, 0);
-            tpos = __shfl_sync(0xffffffffu, tpos, 0);
-            if (lane < gcount) S.top_row[tpos + lane] = ws.idx[lane];
-            if (lane == 0) {
-                TileQuery& q = S.q[qi];
-                q.head = (uint16_t)h;
-                q.n_rows = (uint16_t)(e - h);
-                q.g = (uint16_t)gcount;
-                q.top0 = (uint16_t)tpos;
-                q.bits = mx;
-            }
-            __syncwarp();
-        }
-        __syncthreads();
-        // ---- phase E: one reservation per tile, then one thread per top row / per query writes to HBM ----------------
-        const int n_q = S.n_q, n_top = S.n_top;
-        if (tid == 0 && n_q > 0) S.rs_base = atomicAdd(&p.ctr->rec_slots, ((unsigned long long)n_q << 32) | (unsigned long long)n_top);
-        // field split + number parse of the top rows overlaps the latency of the atomic
-        TopRowRaw tr[(kTopList + kTileThreads - 1) / kTileThreads];
-        uint32_t terr = 0;
-#pragma unroll
-        for (int k = 0; k < (kTopList + kTileThreads - 1) / kTileThreads; k++) {
-            const int i = tid + k * kTileThreads;
-            if (i < n_top) {
-                const int r = S.top_row[i];
+            // reserve one record + gcount top-row slots with a single packed atomic; its latency is covered by the field
+            // split / number parse of the top rows (lanes = top rows), which does not need the result
+            unsigned long long rs = 0;
+            if (lane == 0) rs = atomicAdd(&p.ctr->rec_slots, (1ull << 32) | (unsigned long long)gcount);
+            TopRowRaw tr;
+            uint32_t err = 0;
+            if (lane < gcount) {
+                const int r = ws.idx[lane];
                 const int s = W.row_s[r];
-                const uint32_t er = split_top_row(W.win, tabw, s, W.row_e[r + eskip], lo, tr[k]);
-                if (er) {
-                    report(p.ctr, er, lo + s);
-                    terr = er;
-                }
+                err = split_top_row(W.win, tabw, s, W.row_e[r + eskip], lo, tr);
+                if (err) report(p.ctr, err, lo + s);
             }
-        }
-        __syncthreads();
-        if (n_q > 0) {
-            const unsigned long long rs = S.rs_base;
-            const unsigned rec0 = (unsigned)(rs >> 32), slot0 = (unsigned)rs;
-            if (rec0 + (unsigned)n_q > p.rec_cap || slot0 + (unsigned)n_top > p.slot_cap) {
-                if (tid == 0) p.ctr->cap_overflow = 1;
-            } else {
-#pragma unroll
-                for (int k = 0; k < (kTopList + kTileThreads - 1) / kTileThreads; k++) {
-                    const int i = tid + k * kTileThreads;
-                    if (i < n_top) p.toprows[slot0 + i] = tr[k];
-                }
-                for (int j = tid; j < n_q; j += kTileThreads) {
-                    const TileQuery q = S.q[j];
-                    const int s = W.row_s[q.head];
-                    blu_record rec;
-                    rec.query_off = lo + s;
-                    rec.query_len = (uint32_t)(next_tab(tabw, s, W.row_e[q.head + eskip]) - s);
-                    rec.n_rows = q.n_rows;
-                    rec.keep_mask = 0;
-                    rec.perc_identity = 0.0;
-                    rec.bit_score = (int64_t)q.bits;
-                    rec.ref_lineage = 0;
-                    rec.slot_base = slot0 + q.top0;
-                    rec.n_beans = 0;
-                    rec.n_accessions = q.g;  // size of the top group until the consensus kernel overwrites it
-                    rec.status = 2;          // waiting for the consensus kernel
-                    rec.single_match = 0;
-                    rec.mutated = 0;
-                    rec.reached_pos = 0;
-                    rec.allowed_pos = -1;
-                    rec.bean_level = 0;
-                    rec.pad[0] = rec.pad[1] = 0;
-                    p.records[rec0 + j] = rec;
-                }
+            const int qlen = next_tab(tabw, W.row_s[h], W.row_e[h + eskip]) - (int)W.row_s[h];
+            rs = __shfl_sync(0xffffffffu, rs, 0);
+            const unsigned rec_i = (unsigned)(rs >> 32), slot = (unsigned)rs;
+            if (rec_i >= p.rec_cap || slot + (unsigned)gcount > p.slot_cap) {
+                if (lane == 0) p.ctr->cap_overflow = 1;
+                continue;
             }
-        }
-        (void)terr;
-        more = S.next_run < n_runs;  // stable since the barrier that ended phase D (next_run may overshoot n_runs)
-        if (more) {                  // rare: start the next batch with empty queues
-            __syncthreads();
-            if (tid == 0) {
-                S.n_q = 0;
-                S.n_top = 0;
+            if (lane < gcount && !err) p.toprows[slot + lane] = tr;
+            if (lane == 0) {
+                blu_record rec;
+                rec.query_off = h_abs;
+                rec.query_len = (uint32_t)qlen;
+                rec.n_rows = (uint32_t)(e - h);
+                rec.keep_mask = 0;
+                rec.perc_identity = 0.0;
+                rec.bit_score = (int64_t)mx;
+                rec.ref_lineage = 0;
+                rec.slot_base = slot;
+                rec.n_beans = 0;
+                rec.n_accessions = (uint32_t)gcount;  // size of the top group until the consensus kernel overwrites it
+                rec.status = 2;                       // waiting for the consensus kernel
+                rec.single_match = 0;
+                rec.mutated = 0;
+                rec.reached_pos = 0;
+                rec.allowed_pos = -1;
+                rec.bean_level = 0;
+                rec.pad[0] = rec.pad[1] = 0;
+                p.records[rec_i] = rec;
             }
-            __syncthreads();
-        }
         }
     }
 }
