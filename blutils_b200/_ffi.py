@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libblu_consensus.so")
+LIB_PATH = os.environ.get("BLU_CONSENSUS_LIB") or os.path.join(_HERE, "libblu_consensus.so")  # (override: tuning builds)
 SYNTH_PATH = os.path.join(_HERE, "libblu_synth.so")
 
 BLU_OK, BLU_ERR_IO, BLU_ERR_DATA, BLU_ERR_CUDA, BLU_ERR_ARG, BLU_ERR_UNSUPPORTED, BLU_ERR_INTERNAL = range(7)

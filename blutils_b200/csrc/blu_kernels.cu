@@ -75,14 +75,16 @@ struct WindowIndex {
     // byte-class bitmasks, one bit per window byte (u16 per 16-byte chunk; read back as 64-bit words)
     alignas(8) uint16_t tabm[kChunks + 8];
     alignas(8) uint16_t digm[kChunks + 8];
-    uint16_t startm[kChunks + 8];  // row starts / row ends per chunk (pass 1 of the row scan -> pass 2)
+    // row starts / row ends per chunk (pass 1 of the row scan -> pass 2).  Dead once the row table exists: the tile
+    // kernel re-uses the space for the per-row bit scores.
+    alignas(8) uint16_t startm[kChunks + 8];
     uint16_t endm[kChunks + 8];
     uint16_t row_s[kRowCap];
     uint16_t row_e[kRowCap + 1];
     alignas(8) unsigned long long mbar;
     int n_starts, n_ends;
     int bad_byte;  // window offset of the first '"' / '\r' byte inside [qlo, qhi), or INT_MAX
-    int warp_cnt[16];
+    int warp_cnt[32];
 };
 
 struct WinGeom {
@@ -313,9 +315,11 @@ struct TileQuery {
     int32_t bits;     // truncated top bit score
 };
 
+static_assert(kWin + 128 < 65536, "window offsets are 16-bit");
+static_assert(2 * (kChunks + 8) * sizeof(uint16_t) >= kRowCap * sizeof(int32_t), "bit scores alias the start/end masks");
+
 struct TileSmem {
     WindowIndex W;
-    int32_t bits[kRowCap];
     uint8_t flags[kRowCap];  // bit0: head of a run, bit1: bit score does not fit int32
     uint16_t runs[kMaxRuns];
     WarpScratch ws[kWarps];
@@ -338,6 +342,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
     extern __shared__ __align__(128) uint8_t smem_raw[];
     TileSmem& S = *reinterpret_cast<TileSmem*>(smem_raw);
     WindowIndex& W = S.W;
+    int32_t* const row_bits = reinterpret_cast<int32_t*>(W.startm);  // valid between the row scan and the next load
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) mbar_init(&W.mbar, 1);
     __syncthreads();
@@ -415,7 +420,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
                     }
                     const int32_t b32 = (int32_t)bits;
                     if ((int64_t)b32 != bits) fl |= 2;
-                    S.bits[r] = b32;
+                    row_bits[r] = b32;
                 } else {
                     if (head) fl = 1;
                     if (r == 0 || lo + W.row_s[r - 1] < own_hi) S.first_fwd = r;  // first row of the look-ahead region
@@ -473,7 +478,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
                     }
                     const int32_t b32 = (int32_t)bits;
                     if ((int64_t)b32 != bits) S.flags[r] |= 2;
-                    S.bits[r] = b32;
+                    row_bits[r] = b32;
                 }
                 __syncwarp();
             }
@@ -481,7 +486,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
             int mx = INT32_MIN;
             bool ovf = false;
             for (int r = h + lane; r < e; r += 32) {
-                int b = S.bits[r];
+                int b = row_bits[r];
                 mx = b > mx ? b : mx;
                 ovf |= (S.flags[r] & 2) != 0;
             }
@@ -495,7 +500,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
             int gcount = 0;
             for (int b = h; b < e; b += 32) {
                 int r = b + lane;
-                bool top = r < e && S.bits[r] == mx;
+                bool top = r < e && row_bits[r] == mx;
                 unsigned bal = __ballot_sync(0xffffffffu, top);
                 int pos = gcount + __popc(bal & ((1u << lane) - 1u));
                 if (top && pos < 32) ws.idx[pos] = (uint16_t)r;

@@ -70,12 +70,24 @@ struct DupParams {
 };
 
 // Tile geometry of the fused kernel
-constexpr int kTile = 24576;   // bytes owned by one tile
-constexpr int kBack = 1024;    // look-behind so the tile's first row can be compared with its predecessor
-constexpr int kFwd = 10240;    // look-ahead so a query that starts in the tile can finish in the window
+#ifndef BLU_TILE_BYTES
+#define BLU_TILE_BYTES 49152
+#endif
+#ifndef BLU_FWD_BYTES
+#define BLU_FWD_BYTES 10240
+#endif
+#ifndef BLU_TILE_CTAS
+#define BLU_TILE_CTAS 2
+#endif
+#ifndef BLU_TILE_THREADS
+#define BLU_TILE_THREADS 384
+#endif
+constexpr int kTile = BLU_TILE_BYTES;   // bytes owned by one tile
+constexpr int kBack = 1024;             // look-behind so the tile's first row can be compared with its predecessor
+constexpr int kFwd = BLU_FWD_BYTES;     // look-ahead so a query that starts in the tile can finish in the window
 constexpr int kWin = kBack + kTile + kFwd;
-constexpr int kTileThreads = 256;
-constexpr int kTileCtasPerSm = 3;
+constexpr int kTileThreads = BLU_TILE_THREADS;
+constexpr int kTileCtasPerSm = BLU_TILE_CTAS;
 
 int tile_kernel_grid(int device);
 cudaError_t launch_tile_kernel(const RunParams& p, int grid, cudaStream_t s);
