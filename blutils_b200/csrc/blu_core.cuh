@@ -464,18 +464,24 @@ BLU_HD bool parse_row_fast(const uint8_t* win, const uint32_t* tabw32, const uin
     }
     if (blu_popc32(t0) + blu_popc32(t1) + blu_popc32(t2) != 12) return false;
     // first four tabs must lie in the first 64 bytes
-    uint64_t lo64 = (uint64_t)t0 | ((uint64_t)t1 << 32);
-    if (!lo64) return false;
-    const int p1 = blu_ctz64(lo64);
-    lo64 &= lo64 - 1;
-    if (!lo64) return false;
-    const int p2 = blu_ctz64(lo64);
-    lo64 &= lo64 - 1;
-    if (!lo64) return false;
-    const int p3 = blu_ctz64(lo64);
-    lo64 &= lo64 - 1;
-    if (!lo64) return false;
-    const int p4 = blu_ctz64(lo64);
+    int p1, p2, p3, p4;
+    {
+        uint32_t a = t0, b = t1;
+        int base = 0;
+#define BLU_POP_TAB(dst)            \
+    if (!a) {                       \
+        a = b, b = 0, base += 32;   \
+        if (!a) return false;       \
+    }                               \
+    dst = base + blu_ffs32(a);      \
+    a &= a - 1;
+        BLU_POP_TAB(p1)
+        BLU_POP_TAB(p2)
+        BLU_POP_TAB(p3)
+        BLU_POP_TAB(p4)
+#undef BLU_POP_TAB
+        if (base >= 64) return false;
+    }
     // last two tabs
     int p12, p11;
     {
@@ -549,12 +555,28 @@ BLU_HD bool parse_row_fast(const uint8_t* win, const uint32_t* tabw32, const uin
     return true;
 }
 
-// first fields (qseqid) of the rows starting at a and b are equal; both rows are known to contain a tab
+// first fields (qseqid) of the rows starting at a and b are equal
+BLU_HD uint32_t load_u32_unaligned(const uint8_t* win, int pos) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(win + (pos & ~3));
+    return __funnelshift_r(w[0], w[1], (uint32_t)(pos & 3) * 8u);
+#else
+    return (uint32_t)win[pos] | ((uint32_t)win[pos + 1] << 8) | ((uint32_t)win[pos + 2] << 16) | ((uint32_t)win[pos + 3] << 24);
+#endif
+}
+
 BLU_HD bool same_first_field(const uint8_t* win, const uint64_t* tabw, int a, int ea, int b, int eb) {
-    const int la = next_tab(tabw, a, ea) - a;
-    const int lb = next_tab(tabw, b, eb) - b;
+    const uint32_t* tabw32 = reinterpret_cast<const uint32_t*>(tabw);
+    // length of the first field: first tab within the first 32 bytes (the common case), else the general search
+    uint32_t ta = bits_at(tabw32, a), tb = bits_at(tabw32, b);
+    int la = ta ? blu_ffs32(ta) : 32, lb = tb ? blu_ffs32(tb) : 32;
+    if (la >= 32 || a + la > ea) la = next_tab(tabw, a, ea) - a;
+    if (lb >= 32 || b + lb > eb) lb = next_tab(tabw, b, eb) - b;
     if (la != lb) return false;
-    for (int i = 0; i < la; i++)
+    int i = 0;
+    for (; i + 4 <= la; i += 4)  // (reads stay inside the rows: i + 4 <= la)
+        if (load_u32_unaligned(win, a + i) != load_u32_unaligned(win, b + i)) return false;
+    for (; i < la; i++)
         if (win[a + i] != win[b + i]) return false;
     return true;
 }

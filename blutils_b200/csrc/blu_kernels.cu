@@ -210,9 +210,11 @@ __device__ bool scan_rows(WindowIndex& W, const WinGeom& g) {
     const int c0 = w * cpw;
     const int c1 = c0 + cpw < nchunks ? c0 + cpw : nchunks;
     const int rb = g.rb < 0 ? 0 : g.rb;
-    // ---- pass 1: classify, count ---------------------------------------------------------------------------------
+    // ---- pass 1: classify; every warp compacts the row starts / ends of its chunk range ------------------------------
     // A valid row is >= 26 bytes, so a 16-byte chunk holds at most one row start and one row end; a chunk with more
-    // proves a malformed (too short) row and is reported as such.  That makes the row index a matter of ballots.
+    // proves a malformed (too short) row and is reported as such.  So a warp's k-th row start can be parked at index
+    // c0 + k of the (chunk-indexed) scratch array: it never overtakes the chunk it came from.
+    const uint32_t lt = (1u << lane) - 1u;
     int ns = 0, ne = 0;
     bool crowded = false;
     uint32_t carry_in = 0;
@@ -225,23 +227,22 @@ __device__ bool scan_rows(WindowIndex& W, const WinGeom& g) {
         const uint32_t up = __shfl_up_sync(0xffffffffu, nl, 1);
         const uint32_t carry = lane == 0 ? carry_in : (up >> 15) & 1u;
         carry_in = (__shfl_sync(0xffffffffu, nl, 31) >> 15) & 1u;
-        if (live && carry) {
-            const int pos0 = c << 4;
-            if (pos0 >= rb && !(g.rb >= 0 && pos0 == g.rb)) {
-                // byte 0 of the chunk follows a newline: it starts a row unless it is a newline itself, and a newline
-                // there does not end a row (empty line)
-                const int tend = g.re < g.loaded ? g.re : g.loaded;
-                if (!(nl & 1u) && pos0 < tend) s |= 1u;
-                e &= ~1u;
-            }
+        const int pos0 = c << 4;
+        if (live && carry && pos0 >= rb && !(g.rb >= 0 && pos0 == g.rb)) {
+            // byte 0 of the chunk follows a newline: it starts a row unless it is a newline itself, and a newline
+            // there does not end a row (empty line)
+            const int tend = g.re < g.loaded ? g.re : g.loaded;
+            if (!(nl & 1u) && pos0 < tend) s |= 1u;
+            e &= ~1u;
         }
-        if (live) {
-            W.startm[c] = (uint16_t)s;
-            W.endm[c] = (uint16_t)e;
-            crowded |= (s & (s - 1)) != 0 || (e & (e - 1)) != 0;
-        }
-        ns += __popc(__ballot_sync(0xffffffffu, s != 0));
-        ne += __popc(__ballot_sync(0xffffffffu, e != 0));
+        crowded |= (s & (s - 1)) != 0 || (e & (e - 1)) != 0;
+        const uint32_t bs = __ballot_sync(0xffffffffu, s != 0), be = __ballot_sync(0xffffffffu, e != 0);
+        // (all chunks of this round are classified before anything is parked: the parking slots c0+ns.. lie at or
+        // below the chunks of this round, whose own masks are not needed any more)
+        if (s) W.startm[c0 + ns + __popc(bs & lt)] = (uint16_t)(pos0 + __ffs(s) - 1);
+        if (e) W.endm[c0 + ne + __popc(be & lt)] = (uint16_t)(pos0 + __ffs(e) - 1);
+        ns += __popc(bs);
+        ne += __popc(be);
     }
     crowded = __any_sync(0xffffffffu, crowded);
     if (lane == 0) W.warp_cnt[w] = ns | (ne << 16) | (crowded ? 0x80000000 : 0);
@@ -267,22 +268,9 @@ __device__ bool scan_rows(WindowIndex& W, const WinGeom& g) {
         __syncthreads();
         return false;
     }
-    // ---- pass 2: positions ---------------------------------------------------------------------------------------------
-    const uint32_t lt = (1u << lane) - 1u;
-    for (int base = c0; base < c1; base += 32) {
-        const int c = base + lane;
-        uint32_t s = 0, e = 0;
-        if (c < c1) {
-            s = W.startm[c];
-            e = W.endm[c];
-        }
-        const uint32_t bs = __ballot_sync(0xffffffffu, s != 0), be = __ballot_sync(0xffffffffu, e != 0);
-        const int pos0 = c << 4;
-        if (s) W.row_s[so + __popc(bs & lt)] = (uint16_t)(pos0 + __ffs(s) - 1);
-        if (e) W.row_e[eo + __popc(be & lt)] = (uint16_t)(pos0 + __ffs(e) - 1);
-        so += __popc(bs);
-        eo += __popc(be);
-    }
+    // ---- pass 2: move every warp's compacted positions to their place in the row table -------------------------------
+    for (int i = lane; i < ns; i += 32) W.row_s[so + i] = W.startm[c0 + i];
+    for (int i = lane; i < ne; i += 32) W.row_e[eo + i] = W.endm[c0 + i];
     __syncthreads();
     return true;
 }

@@ -1,0 +1,29 @@
+"""Instruction / stall-sample breakdown of an ncu source dump by function (line ranges found in the sources)."""
+import csv, sys
+src = sys.argv[1]
+def num(x):
+    try: return int(x)
+    except Exception: return 0
+cur=None; hdr=None; agg={}
+for row in csv.reader(open(src)):
+    if not row: continue
+    if row[0]=='File Path': cur=row[1].split('/')[-1]; continue
+    if row[0]=='Function Name': continue
+    if row[0]=='Line No': hdr=row; continue
+    if hdr and row[0].strip().isdigit():
+        d=dict(zip(hdr,row)); agg[(cur,int(row[0]))]=(num(d['Instructions Executed']), num(d['# Samples']), num(d['Thread Instructions Executed']))
+def line_of(pat, f):
+    for i,l in enumerate(open('/root/repo/blutils_b200/csrc/'+f),1):
+        if pat in l: return i
+    return None
+K='blu_kernels.cu'; C='blu_core.cuh'
+marks={K:[('load_window','void load_window'),('make_geom','WinGeom make_geom'),('byte tests/pack','uint32_t bytes_eq'),('classify_chunk','void classify_chunk'),('scan_rows','bool scan_rows'),('finish_geom','void finish_geom'),('tile prologue',') tile_kernel('),('phase P','---- phase P'),('phase D','---- phase D'),('longrun','struct LongSmem')],
+       C:[('probe','uint32_t probe_taxid'),('parse_i64','bool parse_i64'),('parse_f64','uint32_t parse_f64'),('num_class/dfa','int num_class'),('light_parse_row','LightRow light_parse_row'),('ctz/next_tab/all_digits','int blu_ctz64'),('parse_row_masked','LightRow parse_row_masked'),('fast helpers','uint32_t blu_funnel_r'),('float_shape_ok','bool float_shape_ok'),('parse_row_fast','bool parse_row_fast'),('same_first_field','bool same_first_field'),('TopRow/heavy','struct TopRow'),('split_top_row','uint32_t split_top_row'),('join/heavy_masked','uint32_t join_top_row'),('consensus','struct QueryOut')]}
+ti=sum(v[0] for v in agg.values()) or 1; ts=sum(v[1] for v in agg.values()) or 1
+print('total warp-inst',ti,'samples',ts)
+for f,ms in marks.items():
+    ms=[(n,line_of(p,f)) for n,p in ms]; ms=[m for m in ms if m[1]]
+    for (n,a),(n2,b) in zip(ms, ms[1:]+[('end',10**9)]):
+        i=sum(v[0] for k,v in agg.items() if k[0]==f and a<=k[1]<b); s=sum(v[1] for k,v in agg.items() if k[0]==f and a<=k[1]<b); t=sum(v[2] for k,v in agg.items() if k[0]==f and a<=k[1]<b)
+        if i: print(f"{f:15s} {n:26s} inst {100*i/ti:5.1f}%  samples {100*s/ts:5.1f}%  thr/inst {t/max(i,1):5.1f}")
+oth=sum(v[0] for k,v in agg.items() if k[0] not in (K,C)); print('other files inst %.1f%%'%(100*oth/ti))
