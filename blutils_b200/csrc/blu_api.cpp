@@ -346,12 +346,7 @@ void finish_result(blu_ctx* c, const Counters& h, cudaStream_t s, blu_result* r)
     }
     if (r->pool_len) CK(cudaMemcpyAsync(r->b_pool.p, c->d_pool.p, r->pool_len, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    {
-        uint64_t rows = 0;
-        const blu_record* rc = r->rec();
-        for (uint64_t i = 0; i < r->n_rec; i++) rows += rc[i].n_rows;
-        r->n_rows = rows;
-    }
+    r->n_rows = h.n_rows;
     c->tm.d2h_bytes += r->n_rec * sizeof(blu_record) + r->n_slots * (sizeof(blu_bean) + sizeof(blu_acc)) + r->pool_len + sizeof(Counters);
     c->tm.result_bytes = r->n_rec * sizeof(blu_record) + r->n_slots * (sizeof(blu_bean) + sizeof(blu_acc));
     c->tm.n_queries = r->n_rec;

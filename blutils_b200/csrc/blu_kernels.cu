@@ -60,6 +60,10 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
                  : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+// asks the TMA unit to pull [src, src+bytes) into L2 (no destination): the tile after the current one
+__device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 
 __device__ __forceinline__ void report(Counters* ctr, uint32_t err, unsigned long long off) {
     if (atomicCAS(&ctr->err_code, 0u, err) == 0u) ctr->err_off = off;
@@ -361,6 +365,15 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
         if (g.rb > g.qlo) g.qlo = g.rb;
         g.qhi = (int)(own_hi - lo) < g.L ? (int)(own_hi - lo) : g.L;
         load_window(W, p.text, lo, g.loaded, phase, true);
+        if (tid == 32 && t + gridDim.x < n_tiles) {
+            // next tile of this CTA: start moving its owned bytes from HBM to L2 while this one is processed
+            const unsigned long long nb = (first_tile + t + gridDim.x) * (unsigned long long)kTile;
+            const unsigned long long up = (p.end + 15ull) & ~15ull;
+            if (nb < up) {
+                const unsigned long long n = up - nb < (unsigned long long)(kTile + kFwd) ? up - nb : (unsigned long long)(kTile + kFwd);
+                tma_prefetch_l2(p.text + nb, (uint32_t)n);
+            }
+        }
         finish_geom(W, g, p.final_chunk != 0);
         if (!scan_rows<kWarps>(W, g)) {
             if (tid == 0) report(p.ctr, DE_BAD_FIELD_COUNT, lo);
@@ -1135,8 +1148,10 @@ __global__ void __launch_bounds__(256) gather_kernel(const GatherParams p) {
     const bool live = i < p.rec_end;
     unsigned long long bytes = 0;
     blu_record* rec = nullptr;
+    unsigned rows = 0;
     if (live) {
         rec = p.records + i;
+        rows = rec->n_rows;
         bytes = rec->query_len;
         for (unsigned a = 0; a < rec->n_accessions; a++) bytes += p.accs[rec->slot_base + a].len;
     }
@@ -1147,6 +1162,9 @@ __global__ void __launch_bounds__(256) gather_kernel(const GatherParams p) {
         if (lane >= d) inc += t;
     }
     if (lane == 31) warp_tot[warp] = inc;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) rows += __shfl_xor_sync(0xffffffffu, rows, d);
+    if (lane == 0 && rows) atomicAdd(&p.ctr->n_rows, (unsigned long long)rows);
     __syncthreads();
     unsigned long long before = 0, total = 0;
     for (int k = 0; k < 8; k++) {

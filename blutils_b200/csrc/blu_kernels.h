@@ -18,7 +18,8 @@ struct Counters {
     unsigned int dup_found;    // a query id occurs in two separate runs
     unsigned int cap_overflow; // some output capacity was exceeded (host grows and retries)
     unsigned int work_ticket;  // dynamic work distribution of the long-run kernel
-    unsigned int pad[3];
+    unsigned int pad;
+    unsigned long long n_rows; // hit rows of the finished queries (summed by the gather kernel)
 };
 
 struct RunParams {
