@@ -271,6 +271,13 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "B200_PROFILING.md fallback 6650 GB/s"
     algo_bytes = nbytes + res_bytes + tax_bytes  # B_text + B_out + B_tax per GPU
+    # DRAM traffic of one launch from the committed `ncu --set full` capture of this same workload (else null)
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_tile_kernel_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if int(tj.get("text_bytes", -1)) == int(nbytes):
+            traffic = int(tj["dram_read_bytes"] + tj["dram_write_bytes"])
     tile_avg = sum(tile_ms) / len(tile_ms)
     achieved = algo_bytes / (tile_avg * 1e-3) / 1e9 if tile_avg > 0 else 0.0
 
@@ -290,7 +297,7 @@ def main():
                     "hit_rows_per_s": total_rows / e2e_s},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(algo_bytes),
+                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(algo_bytes),
                          "ms_per_launch": tile_avg, "kernel_share_of_step": tile_avg / dev_ms if dev_ms else None,
                          "ms_longrun_kernel": sum(long_ms) / len(long_ms), "ms_gather_dup_kernels": sum(gather_ms) / len(gather_ms)},
             "cpu_baseline": cpu, "clocks": clocks,
