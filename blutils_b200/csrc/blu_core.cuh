@@ -546,10 +546,16 @@ BLU_HD bool parse_row_fast(const uint8_t* win, const uint32_t* tabw32, const uin
             if (l_bits - 1 > 15) return false;
         } else if (l_bits > 15)
             return false;
-        int64_t v = 0;
         const uint8_t* b = win + s + p12 + 1;
-        for (int i = 0; i < n_int; i++) v = v * 10 + (int64_t)(b[i] - '0');
-        bits = v;
+        if (n_int <= 9) {  // the usual case: 32-bit arithmetic
+            uint32_t v = 0;
+            for (int i = 0; i < n_int; i++) v = v * 10u + (uint32_t)(b[i] - '0');
+            bits = (int64_t)v;
+        } else {
+            int64_t v = 0;
+            for (int i = 0; i < n_int; i++) v = v * 10 + (int64_t)(b[i] - '0');
+            bits = v;
+        }
     }
     q_len = l_q;
     return true;
@@ -626,6 +632,42 @@ struct TopRowRaw {
     uint32_t pad;
 };
 
+// digits-only unsigned integer of at most 9 digits (the common staxid / length): 32-bit arithmetic
+BLU_HD bool parse_u32_short(const uint8_t* p, int len, int64_t& v) {
+    if (len < 1 || len > 9) return false;
+    uint32_t x = 0;
+    for (int i = 0; i < len; i++) {
+        const uint32_t d = (uint32_t)p[i] - '0';
+        if (d > 9u) return false;
+        x = x * 10u + d;
+    }
+    v = (int64_t)x;
+    return true;
+}
+
+// `ddd[.ddd]` with at most 9 digits in total: exact Clinger path (mantissa < 2^53, one IEEE divide) without the
+// generic parser's 64-bit bookkeeping.  false = some other shape (caller uses parse_f64).
+BLU_HD bool parse_f64_short(const uint8_t* p, int len, double& v) {
+    if (len < 1 || len > 10) return false;
+    uint32_t m = 0;
+    int nd = 0, frac = -1;
+    for (int i = 0; i < len; i++) {
+        const uint32_t c = p[i];
+        const uint32_t d = c - '0';
+        if (d <= 9u) {
+            m = m * 10u + d;
+            nd++;
+            if (frac >= 0) frac++;
+        } else if (c == '.' && frac < 0)
+            frac = 0;
+        else
+            return false;
+    }
+    if (nd == 0 || nd > 9) return false;
+    v = frac > 0 ? (double)m / kPow10[frac] : (double)m;
+    return true;
+}
+
 BLU_HD uint32_t split_top_row(const uint8_t* win, const uint64_t* tabw, int s, int e, uint64_t lo, TopRowRaw& out) {
     const int t0 = next_tab(tabw, s, e);
     const int t1 = t0 < e ? next_tab(tabw, t0 + 1, e) : e;
@@ -638,10 +680,12 @@ BLU_HD uint32_t split_top_row(const uint8_t* win, const uint64_t* tabw, int s, i
     if (alen > 65535) return DE_NUM_UNSUPPORTED;
     out.acc_len = (uint32_t)alen;
     out.pad = 0;
-    if (!parse_i64(win + t1 + 1, t2 - t1 - 1, out.taxid)) return DE_BAD_NUMBER;
-    uint32_t er = parse_f64(win + t2 + 1, t3 - t2 - 1, out.pident);
-    if (er) return er;
-    if (!parse_i64(win + t3 + 1, t4 - t3 - 1, out.alnlen)) return DE_BAD_NUMBER;
+    if (!parse_u32_short(win + t1 + 1, t2 - t1 - 1, out.taxid) && !parse_i64(win + t1 + 1, t2 - t1 - 1, out.taxid)) return DE_BAD_NUMBER;
+    if (!parse_f64_short(win + t2 + 1, t3 - t2 - 1, out.pident)) {
+        uint32_t er = parse_f64(win + t2 + 1, t3 - t2 - 1, out.pident);
+        if (er) return er;
+    }
+    if (!parse_u32_short(win + t3 + 1, t4 - t3 - 1, out.alnlen) && !parse_i64(win + t3 + 1, t4 - t3 - 1, out.alnlen)) return DE_BAD_NUMBER;
     return DE_NONE;
 }
 

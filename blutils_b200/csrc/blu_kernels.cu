@@ -167,6 +167,14 @@ __device__ __forceinline__ uint32_t range_mask16(int pos0, int lo, int hi) {  //
     return ((1u << b) - 1u) & ~((1u << a) - 1u);
 }
 
+// Rare path of the row scan: some byte below 0x23 is neither tab nor newline -- look for '"' / '\r' exactly.
+__device__ __noinline__ void quote_check(WindowIndex& W, const WinGeom& g, const uint4 v, int pos0) {
+    const uint32_t qm = pack16(bytes_eq(v.x, 0x22222222u) | bytes_eq(v.x, 0x0D0D0D0Du), bytes_eq(v.y, 0x22222222u) | bytes_eq(v.y, 0x0D0D0D0Du),
+                               bytes_eq(v.z, 0x22222222u) | bytes_eq(v.z, 0x0D0D0D0Du), bytes_eq(v.w, 0x22222222u) | bytes_eq(v.w, 0x0D0D0D0Du)) &
+                        range_mask16(pos0, g.qlo, g.qhi);
+    if (qm) atomicMin(&W.bad_byte, pos0 + __ffs(qm) - 1);
+}
+
 // Row scan, pass 1: classifies one 16-byte chunk (newline / tab / digit / quote-or-CR) with SIMD-in-register byte
 // tests, publishes the tab and digit masks, and derives the row-start / row-end masks of the chunk
 // (DESIGN.md "row index").  `carry` = the byte in front of the chunk is a newline.
@@ -184,23 +192,22 @@ __device__ __forceinline__ void classify_chunk(WindowIndex& W, const WinGeom& g,
     // any byte below 0x23 that is neither tab nor newline is suspicious; only then look for '"' / '\r' exactly
     const uint32_t sus = (bytes_below_23(v.x) & ~(nx | tx)) | (bytes_below_23(v.y) & ~(ny | ty)) | (bytes_below_23(v.z) & ~(nz | tz)) |
                          (bytes_below_23(v.w) & ~(nw | tw));
-    if (sus) {
-        const uint32_t qm = pack16(bytes_eq(v.x, 0x22222222u) | bytes_eq(v.x, 0x0D0D0D0Du), bytes_eq(v.y, 0x22222222u) | bytes_eq(v.y, 0x0D0D0D0Du),
-                                   bytes_eq(v.z, 0x22222222u) | bytes_eq(v.z, 0x0D0D0D0Du), bytes_eq(v.w, 0x22222222u) | bytes_eq(v.w, 0x0D0D0D0Du)) &
-                            range_mask16(pos0, g.qlo, g.qhi);
-        if (qm) atomicMin(&W.bad_byte, pos0 + __ffs(qm) - 1);
-    }
-    uint32_t tmask = 0xFFFFu;
-    if (pos0 < rb || pos0 + 16 > tend) {  // chunk on the edge of the text (first / last chunk only)
+    if (__builtin_expect(sus != 0, 0)) quote_check(W, g, v, pos0);
+    if (__builtin_expect(pos0 <= rb || pos0 + 16 > tend, 0)) {
+        // chunk on an edge of the text (the first / last chunk of the whole text only)
         nl &= range_mask16(pos0, rb, g.L);
-        tmask = range_mask16(pos0, rb, tend);
+        const uint32_t tmask = range_mask16(pos0, rb, tend);
+        if (g.rb >= 0 && pos0 == g.rb) carry = 1;  // virtual newline in front of the text
+        if (pos0 < rb) carry = 0;
+        uint32_t prev = ((nl << 1) | carry) & 0xFFFFu;
+        if (g.rb > pos0 && g.rb < pos0 + 16) prev |= 1u << (g.rb - pos0);
+        start = prev & ~nl & tmask;
+        end = nl & ~prev;
+    } else {
+        const uint32_t prev = ((nl << 1) | carry) & 0xFFFFu;
+        start = prev & ~nl;
+        end = nl & ~prev;
     }
-    if (g.rb >= 0 && pos0 == g.rb) carry = 1;  // virtual newline in front of the text
-    if (pos0 < rb) carry = 0;
-    uint32_t prev = ((nl << 1) | carry) & 0xFFFFu;
-    if (g.rb > pos0 && g.rb < pos0 + 16) prev |= 1u << (g.rb - pos0);
-    start = prev & ~nl & tmask;
-    end = nl & ~prev;
     nl_out = nl;
 }
 
@@ -389,43 +396,55 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
 
         const uint32_t* tabw32 = reinterpret_cast<const uint32_t*>(W.tabm);
         const uint32_t* digw32 = reinterpret_cast<const uint32_t*>(W.digm);
-        // ---- phase P: one thread per row at/after the tile start --------------------------------------------------
-        //   head flag (first field differs from the previous row's), run list, and -- for the rows inside the tile --
-        //   validation + truncated bit score.  Rows of the look-ahead region are parsed lazily by the warp that
-        //   owns their run (phase D); rows before own_lo belong to runs of the previous tile.
-        for (int r = tid; r < ncomplete; r += kTileThreads) {
+        // ---- phase P: one thread per row of the tile -----------------------------------------------------------------
+        //   head flag (first field differs from the previous row's), run list, validation + truncated bit score.
+        //   Rows before own_lo belong to runs of the previous tile; rows of the look-ahead region only get their head
+        //   flag here and are parsed lazily by the warp that owns their run (phase D).
+        int r_lo, r_hi;  // rows [r_lo, r_hi) start inside [own_lo, own_hi)
+        {
+            const int k_lo = own_lo > lo ? (int)(own_lo - lo) : 0, k_hi = (int)(own_hi - lo);
+            int a = 0, b = ncomplete;
+            while (a < b) {
+                const int m = (a + b) >> 1;
+                if ((int)W.row_s[m] < k_lo) a = m + 1; else b = m;
+            }
+            r_lo = a;
+            b = ncomplete;
+            while (a < b) {
+                const int m = (a + b) >> 1;
+                if ((int)W.row_s[m] < k_hi) a = m + 1; else b = m;
+            }
+            r_hi = a;
+        }
+        if (tid == 0) S.first_fwd = r_hi < ncomplete ? r_hi : 0x7fffffff;
+        for (int r = tid; r < r_lo; r += kTileThreads) S.flags[r] = 0;
+        for (int r = r_lo + tid; r < ncomplete; r += kTileThreads) {
             const int s = W.row_s[r];
             const int e = W.row_e[r + eskip];
             const unsigned long long abs = lo + s;
-            uint8_t fl = 0;
-            if (abs >= own_lo) {
-                bool head;
-                if (r == 0)
-                    head = g.rb >= 0 && s == g.rb;  // first row of the text (else: predecessor not in the window)
-                else
-                    head = !same_first_field(W.win, tabw, W.row_s[r - 1], W.row_e[r - 1 + eskip], s, e);
-                if (abs < own_hi) {
-                    if (head) {
-                        fl = 1;
-                        int i = atomicAdd(&S.n_runs, 1);
-                        S.runs[i] = (uint16_t)r;
-                    } else if (r == 0) {
-                        push_defer(p, abs, 1);  // predecessor not in the window: the block path decides whether it is a head
-                    }
-                    int64_t bits;
-                    int ql;
-                    if (!parse_row_fast(W.win, tabw32, digw32, s, e, bits, ql)) {
-                        LightRow lr = parse_row_masked(W.win, tabw, digw, s, e);
-                        if (lr.err) report(p.ctr, lr.err, abs);
-                        bits = lr.bits;
-                    }
-                    const int32_t b32 = (int32_t)bits;
-                    if ((int64_t)b32 != bits) fl |= 2;
-                    row_bits[r] = b32;
-                } else {
-                    if (head) fl = 1;
-                    if (r == 0 || lo + W.row_s[r - 1] < own_hi) S.first_fwd = r;  // first row of the look-ahead region
+            bool head;
+            if (r == 0)
+                head = g.rb >= 0 && s == g.rb;  // first row of the text (else: predecessor not in the window)
+            else
+                head = !same_first_field(W.win, tabw, W.row_s[r - 1], W.row_e[r - 1 + eskip], s, e);
+            uint8_t fl = head ? 1 : 0;
+            if (r < r_hi) {
+                if (head) {
+                    int i = atomicAdd(&S.n_runs, 1);
+                    S.runs[i] = (uint16_t)r;
+                } else if (r == 0) {
+                    push_defer(p, abs, 1);  // predecessor not in the window: the block path decides whether it is a head
                 }
+                int64_t bits;
+                int ql;
+                if (!parse_row_fast(W.win, tabw32, digw32, s, e, bits, ql)) {
+                    LightRow lr = parse_row_masked(W.win, tabw, digw, s, e);
+                    if (lr.err) report(p.ctr, lr.err, abs);
+                    bits = lr.bits;
+                }
+                const int32_t b32 = (int32_t)bits;
+                if ((int64_t)b32 != bits) fl |= 2;
+                row_bits[r] = b32;
             }
             S.flags[r] = fl;
         }

@@ -121,7 +121,10 @@ extern "C" int blu_sim_run(const int64_t* taxids, const uint64_t* off, const cha
             for (size_t r = h; r < e; r++)
                 if (rows[r].bits == mx) {
                     TopRow t;
-                    uint32_t er = heavy_parse_row_masked(tx, tabw.data(), (int)rows[r].s, (int)rows[r].s + rows[r].len, 0, L, t);
+                    // the kernels' path: field split + number parse (tile kernel), then the taxid join (consensus kernel)
+                    TopRowRaw raw;
+                    uint32_t er = split_top_row(tx, tabw.data(), (int)rows[r].s, (int)rows[r].s + rows[r].len, 0, raw);
+                    if (!er) er = join_top_row(raw, L, t);
                     {
                         TopRow t2;
                         uint32_t er2 = heavy_parse_row(tx + rows[r].s, rows[r].len, rows[r].s, L, t2);
