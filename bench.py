@@ -117,7 +117,11 @@ def cpu_reference(w, lineages, q_sample: int, hits: int, steps: int, warmup: int
 
     ids, off, blob = lineages
     lin = [bytes(blob[int(off[i]):int(off[i + 1])]).decode() for i in range(len(ids))]
-    cores = os.cpu_count() or 1
+    try:
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))  # the CPU arm may use every core of the box
+    except OSError:
+        pass
+    cores = len(os.sched_getaffinity(0))
     orc = Oracle(ids.tolist(), lin, "custom", "relaxed", CUSTOM, threads=cores)
     text = w.hits(q_begin, q_sample, hits)
     times = []
@@ -177,6 +181,15 @@ def main():
     from blutils_b200 import ConsensusEngine, ConsensusStrategy, CustomTaxon, Taxon
 
     torch.cuda.set_device(local_rank)
+    # keep this rank's threads and its pinned staging memory on the NUMA node of its GPU (one PCIe link per GPU)
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        config["cpu_affinity"] = f"{len(os.sched_getaffinity(0))} cpus (NVML ideal affinity of GPU {local_rank})"
+    except Exception as ex:  # noqa: BLE001
+        config["cpu_affinity"] = f"not set ({type(ex).__name__})"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
