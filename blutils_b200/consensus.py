@@ -209,6 +209,13 @@ class ConsensusOutput:
         if rc != 0:
             raise MappedErrors("could not write the blutils output")
 
+    def write_tabular(self, output_file: Optional[str], run_id: Optional[str] = None) -> None:
+        """parse_consensus_as_tabular (parse_consensus_as_tabular/mod.rs:15-173) from the binary records."""
+        rc = _ffi.lib().blu_result_write_tabular(self._h, None if output_file is None else os.fspath(output_file).encode(),
+                                                 None if run_id is None else run_id.encode())
+        if rc != 0:
+            raise MappedErrors("could not write the tabular output")
+
     def close(self) -> None:
         if self._h:
             _ffi.lib().blu_result_free(self._h)

@@ -872,6 +872,16 @@ int blu_result_write(const blu_result* r, const char* path, int format, const ch
     }
 }
 
+int blu_result_write_tabular(const blu_result* r, const char* path, const char* run_id) {
+    if (!r) return BLU_ERR_ARG;
+    try {
+        ResultView v = make_view(r);
+        return view_write_tabular(&v, path, run_id);
+    } catch (const std::exception&) {
+        return BLU_ERR_INTERNAL;
+    }
+}
+
 void blu_result_free(blu_result* r) {
     if (!r) return;
     if (r->pinned) {

@@ -511,4 +511,106 @@ inline int view_write(const ResultView* r, const char* path, int format, const c
 }
 
 
+// parse_consensus_as_tabular (reference core/src/use_cases/parse_consensus_as_tabular/mod.rs:15-173), emitted
+// straight from the binary records instead of re-reading the JSON.  Byte-exact quirks kept:
+//   * to stdout every piece goes through println! (one '\n' each), so a query without taxon, whose piece already ends
+//     in '\n', is followed by an empty line;
+//   * to a file the pieces are written as they are -- the reference never adds the line breaks there (mod.rs:58-66 +
+//     shared/write_file_or_stdout.rs), so only the taxon-less pieces end a line;
+//   * floats use Rust's Display (845.0 -> "845").
+inline int view_write_tabular(const ResultView* r, const char* path, const char* run_id_in) {
+    Decoder d(r);
+    const HostTaxonomy& T = *r->tax;
+    auto ent = sorted_entries(r);
+    const std::string run_id = run_id_in ? std::string(run_id_in) : uuid_v4();
+    const bool to_stdout = path == nullptr;
+    FILE* f = stdout;
+    if (path) {
+        std::string target = path;
+        size_t slash = target.find_last_of('/');
+        size_t dot = target.find_last_of('.');
+        if (dot != std::string::npos && (slash == std::string::npos || dot > slash)) target.resize(dot);
+        target += ".tsv";
+        std::remove(target.c_str());
+        f = fopen(target.c_str(), "ab");
+        if (!f) return BLU_ERR_IO;
+    }
+    std::string o;
+    auto piece_done = [&]() {
+        if (to_stdout) o.push_back('\n');
+        if (o.size() > (8u << 20)) {
+            fwrite(o.data(), 1, o.size(), f);
+            o.clear();
+        }
+    };
+    o += "run-id\tquery\ttype\trank\tidentifier\tperc-identity\tbit-score\ttaxonomy\tmutated\tsingle-match\toccurrences\taccessions";
+    piece_done();
+    std::string tmp;
+    for (auto& en : ent) {
+        if (!en.rec) {
+            o.append(en.query);
+            o += "\tnull\n";
+            piece_done();
+            continue;
+        }
+        const blu_record& rc = *en.rec;
+        const uint32_t lo = T.lin_off[rc.ref_lineage];
+        o += run_id;
+        o.push_back('\t');
+        o.append(en.query);
+        o += "\tconsensus\t";
+        o += T.ranks[T.pos_rank[lo + rc.reached_pos]].full;
+        o.push_back('\t');
+        o += T.idents[T.pos_ident[lo + rc.reached_pos]];
+        o.push_back('\t');
+        rust_display_f64(o, rc.perc_identity);
+        o.push_back('\t');
+        rust_display_f64(o, (double)rc.bit_score);
+        o.push_back('\t');
+        {
+            bool first = true;
+            for (int j = 0; j < T.lin_len(rc.ref_lineage); j++)
+                if (rc.keep_mask >> j & 1) {
+                    if (!first) o.push_back(';');
+                    first = false;
+                    T.append_bean(o, lo + j);
+                }
+        }
+        o += rc.mutated ? "\ttrue" : "\tfalse";
+        o += rc.single_match ? "\ttrue" : "\tfalse";
+        o += "\tnull\tnull";
+        piece_done();
+        for (uint32_t b = 0; b < rc.n_beans; b++) {
+            const blu_bean& bn = r->beans()[rc.slot_base + b];
+            const uint32_t bp = T.lin_off[bn.first_lineage] + rc.bean_level;
+            o += run_id;
+            o.push_back('\t');
+            o.append(en.query);
+            o += "\tblast-match\t";
+            o += T.ranks[T.pos_rank[bp]].full;
+            o.push_back('\t');
+            o += T.idents[T.pos_ident[bp]];
+            o += "\tnull\t";
+            rust_display_f64(o, (double)rc.bit_score);
+            o.push_back('\t');
+            T.append_lineage(o, bn.first_lineage);
+            o += "\tnull\tnull\t";
+            o += std::to_string(bn.occurrences);
+            o.push_back('\t');
+            for (uint32_t a = 0; a < bn.n_acc; a++) {
+                const blu_acc& ac = r->accs()[rc.slot_base + bn.acc_begin + a];
+                if (a) o += ", ";
+                o.append(r->pool() + ac.off, ac.len);
+            }
+            piece_done();
+        }
+    }
+    fwrite(o.data(), 1, o.size(), f);
+    if (path)
+        fclose(f);
+    else
+        fflush(stdout);
+    return BLU_OK;
+}
+
 }  // namespace blu

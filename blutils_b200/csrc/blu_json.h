@@ -271,4 +271,46 @@ inline void json_f64(std::string& o, double v) {
     }
 }
 
+// Rust `format!("{}", f64)`: shortest round-trip digits, positional notation, no exponent, no trailing ".0"
+// (used by parse_consensus_as_tabular, reference core/src/use_cases/parse_consensus_as_tabular/mod.rs:133-134)
+inline void rust_display_f64(std::string& o, double v) {
+    if (std::isnan(v)) {
+        o += "NaN";
+        return;
+    }
+    if (std::isinf(v)) {
+        o += v < 0 ? "-inf" : "inf";
+        return;
+    }
+    if (v == 0) {
+        o += std::signbit(v) ? "-0" : "0";
+        return;
+    }
+    char buf[48];
+    auto r = std::to_chars(buf, buf + sizeof buf, std::fabs(v), std::chars_format::scientific);
+    const char* ep = buf;
+    while (ep < r.ptr && *ep != 'e') ep++;
+    int ex = 0;
+    std::from_chars(ep + (ep[1] == '+' ? 2 : 1), r.ptr, ex);
+    char dg[24];
+    int n = 0;
+    for (const char* c = buf; c < ep; c++)
+        if (*c != '.') dg[n++] = *c;
+    while (n > 1 && dg[n - 1] == '0') n--;
+    const int kk = ex + 1;  // digits before the decimal point
+    if (std::signbit(v)) o.push_back('-');
+    if (kk <= 0) {
+        o += "0.";
+        o.append((size_t)(-kk), '0');
+        o.append(dg, n);
+    } else if (kk >= n) {
+        o.append(dg, n);
+        o.append((size_t)(kk - n), '0');
+    } else {
+        o.append(dg, kk);
+        o.push_back('.');
+        o.append(dg + kk, n - kk);
+    }
+}
+
 }  // namespace blu

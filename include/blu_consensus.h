@@ -153,6 +153,11 @@ int blu_result_to_jsonl(const blu_result* res, char** out, uint64_t* len);
 /* write_blutils_output (write_blutils_output.rs:33-250): path NULL -> stdout; run_id NULL -> fresh UUIDv4;
  * config is always `null` on this path (ports/cli/src/cmds/blast/mod.rs:139). */
 int blu_result_write(const blu_result* res, const char* path, int format, const char* run_id);
+/* parse_consensus_as_tabular (parse_consensus_as_tabular/mod.rs:15-173) straight from the binary records: the
+ * 12-column TSV of `blu blastn build-tabular` (one `consensus` row + one `blast-match` row per bean); path NULL ->
+ * stdout, else the extension is forced to `.tsv`.  Reproduces the reference byte for byte, including its quirk of
+ * not writing line breaks between pieces in file mode. */
+int blu_result_write_tabular(const blu_result* res, const char* path, const char* run_id);
 void blu_result_free(blu_result* res);
 void blu_free(void* p);
 

@@ -567,3 +567,43 @@ def results_to_jsonl(results: List[dict], run_id: Optional[str] = None) -> str:
         o["taxon"] = r["taxon"]
         lines.append(to_json_compact(o))
     return "\n".join(lines) + ("\n" if lines else "")
+
+
+# --------------------------------------------------------------------------------------
+# parse_consensus_as_tabular (core/src/use_cases/parse_consensus_as_tabular/mod.rs:15-173)
+# --------------------------------------------------------------------------------------
+def rust_display_f64(v: float) -> str:
+    """Rust `format!("{}", f64)`: shortest round-trip digits, positional, no trailing '.0'."""
+    from decimal import Decimal
+
+    if v != v:
+        return "NaN"
+    if v in (math.inf, -math.inf):
+        return "inf" if v > 0 else "-inf"
+    s = format(Decimal(repr(v)), "f")
+    if "." in s:
+        s = s.rstrip("0").rstrip(".")
+    return s
+
+
+def results_to_tabular(results: List[dict], run_id: str, to_stdout: bool) -> str:
+    """The byte stream the reference produces: println! per piece on stdout, raw pieces in a file (mod.rs:58-170,
+    shared/write_file_or_stdout.rs:3-22)."""
+    end = "\n" if to_stdout else ""
+    out = ["\t".join(["run-id", "query", "type", "rank", "identifier", "perc-identity", "bit-score", "taxonomy", "mutated",
+                      "single-match", "occurrences", "accessions"]) + end]
+    for r in results:
+        t = r["taxon"]
+        if t is None:
+            out.append(f"{r['query']}\tnull\n" + end)
+            continue
+        b = "true" if t["mutated"] else "false"
+        sm = "true" if t["singleMatch"] else "false"
+        out.append("\t".join([run_id, r["query"], "consensus", t["reachedRank"], t["identifier"], rust_display_f64(t["percIdentity"]),
+                              rust_display_f64(t["bitScore"]), t["taxonomy"] if t["taxonomy"] is not None else "null", b, sm, "null",
+                              "null"]) + end)
+        for c in t["consensusBeans"] or []:
+            out.append("\t".join([run_id, r["query"], "blast-match", c["rank"], c["identifier"], "null", rust_display_f64(t["bitScore"]),
+                                  c["taxonomy"] if c["taxonomy"] is not None else "null", "null", "null", str(c["occurrences"]),
+                                  ", ".join(c["accessions"])]) + end)
+    return "".join(out)

@@ -232,6 +232,9 @@ def test_file_api_headers_and_writer(tmp_path):
     run_id = doc["results"][0]["runId"]
     exp = {"results": [dict([("runId", run_id)] + list(r.items())) for r in want], "config": None}
     assert got == po.to_json_pretty(exp)
+    # build-tabular straight from the records (parse_consensus_as_tabular), file mode keeps the reference's missing line breaks
+    res.write_tabular(str(tmp_path / "tab.txt"), run_id)
+    assert (tmp_path / "tab.tsv").read_text() == po.results_to_tabular(want, run_id, to_stdout=False)
     write_blutils_output(res, None, str(tmp_path / "out2"), OutputFormat.Jsonl)
     lines = (tmp_path / "out2.jsonl").read_text().splitlines()
     assert lines[0] == "null" and len(lines) == 1 + len(want)
