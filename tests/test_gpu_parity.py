@@ -239,3 +239,73 @@ def test_file_api_headers_and_writer(tmp_path):
     lines = (tmp_path / "out2.jsonl").read_text().splitlines()
     assert lines[0] == "null" and len(lines) == 1 + len(want)
     assert [json.loads(l)["query"] for l in lines[1:]] == [r["query"] for r in want]
+
+
+def test_tile_and_window_edges():
+    """Texts cut at every kind of position relative to the 48 KiB tile grid, with and without a trailing newline,
+    with empty lines, through both the host path and tiny streaming chunks."""
+    ids, lin, text = _synth_case(2000, 2600, 50, seed=31)
+    rows = text.split(b"\n")
+    rows = [r for r in rows if r]
+    orc = _oracle(ids, lin, "bacteria", "relaxed")
+    eng = _engine("bacteria", "relaxed")
+    eng.load_taxonomy_arrays(ids, lin)
+    eng_small = _engine("bacteria", "relaxed", chunk_bytes=96 << 10)
+    eng_small.load_taxonomy_arrays(ids, lin)
+    # prefix lengths (in rows) that put the end of the text just before / at / after tile and window borders
+    sizes = []
+    acc = 0
+    marks = [49152, 49152 + 10240, 2 * 49152, 3 * 49152 + 1024]
+    for i, r in enumerate(rows):
+        acc += len(r) + 1
+        for m in marks:
+            if abs(acc - m) <= 80:
+                sizes.append(i + 1)
+    sizes = sorted(set(sizes))[:12] + [1, 2, 51]
+    for n in sizes:
+        for tail in (b"\n", b"", b"\n\n\n"):
+            t = b"\n".join(rows[:n]) + tail
+            want = orc.run_raw(t)[0]
+            assert eng.run_host(t).jsonl() == want, (n, tail)
+            assert eng_small.run_host(t).jsonl() == want, (n, tail, "streamed")
+    # empty lines sprinkled between rows
+    t = b"\n\n".join(rows[:700]) + b"\n"
+    want = orc.run_raw(t)[0]
+    assert eng.run_host(t).jsonl() == want
+    assert eng_small.run_host(t).jsonl() == want
+    eng.close()
+    eng_small.close()
+
+
+def test_long_rows():
+    """Rows whose first field is longer than the 1 KiB look-behind (predecessor not in the window -> block path),
+    and a row longer than the whole window (documented limit: loud BLU_ERR_UNSUPPORTED)."""
+    from blutils_b200 import Unsupported
+
+    lin = ["d__bac;p__p1;c__c1;o__o1;f__f1;g__g1;s__s1", "d__bac;p__p1;c__c1;o__o1;f__f1;g__g1;s__s2"]
+    ids = [11, 12]
+    rows = []
+    for q in range(120):
+        name = f"q{q:04d}_" + "x" * (1500 if q % 3 == 0 else 20)
+        for h in range(30):
+            rows.append(_row(name, f"ACC{h % 5}.1", ids[(q + h) % 2], "99.5" if h < 3 else "90.1", 400, "700" if h < 3 else "300"))
+    text = "".join(rows).encode()
+    want = _oracle(ids, lin, "bacteria", "cautious").run_raw(text)[0]
+    eng = _engine("bacteria", "cautious")
+    eng.load_taxonomy_arrays(ids, lin)
+    assert eng.run_host(text).jsonl() == want
+    big = (_row("q_small", "A.1", 11, "99.0", 10, "50") + _row("q" + "y" * 70000, "A.1", 11, "99.0", 10, "50")).encode()
+    with pytest.raises(Unsupported):
+        eng.run_host(big)
+    eng.close()
+
+
+def test_streamed_chunk_sizes_zipf():
+    """Carry-over logic under stress: chunk sizes from 64 KiB up, long-tail (Zipf) queries of up to ~380 KB."""
+    ids, lin, text = _synth_case(3000, 250, 5000, zipf=True, seed=17)
+    want = _oracle(ids, lin, "bacteria", "relaxed").run_raw(text)[0]
+    for chunk in (512 << 10, 1 << 20, (1 << 20) + 4096 + 128):
+        eng = _engine("bacteria", "relaxed", chunk_bytes=chunk)
+        eng.load_taxonomy_arrays(ids, lin)
+        assert eng.run_host(text).jsonl() == want, chunk
+        eng.close()
