@@ -241,6 +241,7 @@ def main():
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tile_ms, long_ms, gather_ms, launches = [], [], [], 0
+    tile_launches = 1
     nq = 0
     res_bytes = tax_bytes = 0
     e0.record()
@@ -251,6 +252,7 @@ def main():
         long_ms.append(t["ms_longrun_kernel"])
         gather_ms.append(t["ms_gather_kernel"])
         launches += int(t["n_kernel_launches"])
+        tile_launches = max(1, int(t["n_tile_launches"]))
         nq = len(out)
         res_bytes, tax_bytes = int(t["result_bytes"]), int(t["taxonomy_bytes"])
         out.close()
@@ -289,8 +291,8 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "r01_tile_kernel_traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
-        if int(tj.get("text_bytes", -1)) == int(nbytes):
-            traffic = int(tj["dram_read_bytes"] + tj["dram_write_bytes"])
+        if int(tj.get("text_bytes", -1)) == int(nbytes) and int(tj.get("launches_per_step", 1)) == tile_launches:
+            traffic = int(tj["dram_read_bytes"] + tj["dram_write_bytes"])  # of ONE launch, like `achieved`
     tile_avg = sum(tile_ms) / len(tile_ms)
     achieved = algo_bytes / (tile_avg * 1e-3) / 1e9 if tile_avg > 0 else 0.0
 
@@ -310,8 +312,9 @@ def main():
                     "hit_rows_per_s": total_rows / e2e_s},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(algo_bytes),
-                         "ms_per_launch": tile_avg, "kernel_share_of_step": tile_avg / dev_ms if dev_ms else None,
+                         "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(algo_bytes // tile_launches),
+                         "ms_per_launch": tile_avg / tile_launches, "launches_per_step": tile_launches,
+                         "ms_per_step_all_launches": tile_avg, "kernel_share_of_step": tile_avg / dev_ms if dev_ms else None,
                          "ms_longrun_kernel": sum(long_ms) / len(long_ms), "ms_gather_dup_kernels": sum(gather_ms) / len(gather_ms)},
             "cpu_baseline": cpu, "clocks": clocks,
         }

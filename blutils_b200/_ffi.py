@@ -32,7 +32,7 @@ class blu_timings(C.Structure):
     _fields_ = [("ms_total_device", C.c_double), ("ms_tile_kernel", C.c_double), ("ms_longrun_kernel", C.c_double),
                 ("ms_gather_kernel", C.c_double), ("ms_other", C.c_double), ("text_bytes", C.c_uint64), ("result_bytes", C.c_uint64),
                 ("taxonomy_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("n_queries", C.c_uint64),
-                ("n_rows", C.c_uint64), ("n_deferred_runs", C.c_uint64), ("n_kernel_launches", C.c_uint64), ("n_regrouped", C.c_uint64), ("reserved", C.c_uint64 * 3)]
+                ("n_rows", C.c_uint64), ("n_deferred_runs", C.c_uint64), ("n_kernel_launches", C.c_uint64), ("n_regrouped", C.c_uint64), ("n_tile_launches", C.c_uint64), ("reserved", C.c_uint64 * 2)]
 
 
 # every symbol include/blu_consensus.h declares: (name, restype, argtypes)

@@ -124,7 +124,7 @@ struct blu_ctx {
     Cutoffs cut;
     int device = 0;
     int sms = 148;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaStream_t stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t ev[6]{};
     cudaEvent_t ev_h2d[2]{}, ev_free[2]{};
     std::shared_ptr<HostTaxonomy> tax;
@@ -331,27 +331,71 @@ void reset_counters_async(blu_ctx* c, cudaStream_t s, bool whole) {
     CK(cudaMemsetAsync(&c->d_ctr->tail_start, 0xFF, sizeof(unsigned long long), s));
 }
 
-void finish_result(blu_ctx* c, const Counters& h, cudaStream_t s, blu_result* r) {
-    r->n_rec = n_rec_of(h);
-    r->n_slots = n_slots_of(h);
-    r->pool_len = h.pool_used;
-    r->b_rec = c->acquire(std::max<size_t>(r->n_rec * sizeof(blu_record), 64));
-    r->b_beans = c->acquire(std::max<size_t>(r->n_slots * sizeof(blu_bean), 64));
-    r->b_accs = c->acquire(std::max<size_t>(r->n_slots * sizeof(blu_acc), 64));
-    r->b_pool = c->acquire(std::max<size_t>(r->pool_len, 64));
-    if (r->n_rec) CK(cudaMemcpyAsync(r->b_rec.p, c->d_rec.p, r->n_rec * sizeof(blu_record), cudaMemcpyDeviceToHost, s));
-    if (r->n_slots) {
-        CK(cudaMemcpyAsync(r->b_beans.p, c->d_beans.p, r->n_slots * sizeof(blu_bean), cudaMemcpyDeviceToHost, s));
-        CK(cudaMemcpyAsync(r->b_accs.p, c->d_accs.p, r->n_slots * sizeof(blu_acc), cudaMemcpyDeviceToHost, s));
+// Incremental download of the finished part of the result arrays on the context's download stream, so that the
+// device->host copies of one range / chunk run under the kernels (and host->device copies) of the next one.
+struct Downloader {
+    blu_ctx* c;
+    blu_result* r;
+    uint64_t rec_done = 0, slot_done = 0, pool_done = 0;
+    uint64_t bytes = 0;
+
+    Downloader(blu_ctx* ctx, blu_result* res) : c(ctx), r(res) {}
+
+    static void grow(blu_ctx* c, PinnedBuf& b, size_t need, size_t keep, cudaStream_t ds) {
+        if (b.cap >= need && b.p) return;
+        PinnedBuf nb = c->acquire(std::max<size_t>(need, 64));
+        if (keep) {
+            CK(cudaStreamSynchronize(ds));  // the prefix may still be in flight
+            memcpy(nb.p, b.p, keep);
+        }
+        if (b.p) c->pool->release(b);
+        b = nb;
     }
-    if (r->pool_len) CK(cudaMemcpyAsync(r->b_pool.p, c->d_pool.p, r->pool_len, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    r->n_rows = h.n_rows;
-    c->tm.d2h_bytes += r->n_rec * sizeof(blu_record) + r->n_slots * (sizeof(blu_bean) + sizeof(blu_acc)) + r->pool_len + sizeof(Counters);
-    c->tm.result_bytes = r->n_rec * sizeof(blu_record) + r->n_slots * (sizeof(blu_bean) + sizeof(blu_acc));
-    c->tm.n_queries = r->n_rec;
-    c->tm.n_rows = r->n_rows;
-}
+    // capacity for at least these totals (called with estimates first, exact numbers at the end)
+    void reserve(uint64_t rec, uint64_t slots, uint64_t pool) {
+        cudaStream_t ds = c->d2h_stream;
+        grow(c, r->b_rec, rec * sizeof(blu_record), rec_done * sizeof(blu_record), ds);
+        grow(c, r->b_beans, slots * sizeof(blu_bean), slot_done * sizeof(blu_bean), ds);
+        grow(c, r->b_accs, slots * sizeof(blu_acc), slot_done * sizeof(blu_acc), ds);
+        grow(c, r->b_pool, pool, pool_done, ds);
+    }
+    // everything up to the counters in `h` is final on the device (the compute stream has been synchronised)
+    void push(const Counters& h) {
+        cudaStream_t ds = c->d2h_stream;
+        const uint64_t rec = n_rec_of(h), slots = n_slots_of(h), pool = h.pool_used;
+        reserve(rec, slots, pool);
+        if (rec > rec_done)
+            CK(cudaMemcpyAsync((blu_record*)r->b_rec.p + rec_done, c->d_rec.p + rec_done, (rec - rec_done) * sizeof(blu_record),
+                               cudaMemcpyDeviceToHost, ds));
+        if (slots > slot_done) {
+            CK(cudaMemcpyAsync((blu_bean*)r->b_beans.p + slot_done, c->d_beans.p + slot_done, (slots - slot_done) * sizeof(blu_bean),
+                               cudaMemcpyDeviceToHost, ds));
+            CK(cudaMemcpyAsync((blu_acc*)r->b_accs.p + slot_done, c->d_accs.p + slot_done, (slots - slot_done) * sizeof(blu_acc),
+                               cudaMemcpyDeviceToHost, ds));
+        }
+        if (pool > pool_done)
+            CK(cudaMemcpyAsync((char*)r->b_pool.p + pool_done, c->d_pool.p + pool_done, pool - pool_done, cudaMemcpyDeviceToHost, ds));
+        bytes += (rec - rec_done) * sizeof(blu_record) + (slots - slot_done) * (sizeof(blu_bean) + sizeof(blu_acc)) + (pool - pool_done);
+        rec_done = rec, slot_done = slots, pool_done = pool;
+    }
+    void finish(const Counters& h) {
+        push(h);
+        CK(cudaStreamSynchronize(c->d2h_stream));
+        r->n_rec = rec_done;
+        r->n_slots = slot_done;
+        r->pool_len = pool_done;
+        r->n_rows = h.n_rows;
+        c->tm.d2h_bytes += bytes + sizeof(Counters);
+        c->tm.result_bytes = r->n_rec * sizeof(blu_record) + r->n_slots * (sizeof(blu_bean) + sizeof(blu_acc));
+        c->tm.n_queries = r->n_rec;
+        c->tm.n_rows = r->n_rows;
+    }
+    void abandon() {  // retry with larger device capacities: drop what was downloaded
+        cudaStreamSynchronize(c->d2h_stream);
+        rec_done = slot_done = pool_done = 0;
+        bytes = 0;
+    }
+};
 
 float ev_ms(cudaEvent_t a, cudaEvent_t b) {
     float ms = 0;
@@ -479,39 +523,83 @@ void run_device(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStream_t s, bl
     if (((uintptr_t)dtext & 15) != 0) throw std::invalid_argument("device text must be 16-byte aligned");
     c->tm = blu_timings{};
     Caps k = initial_caps(n);
+    // Large resident tables are processed in a few query-aligned ranges so that the download of one range's records
+    // overlaps the kernels of the next (the unfinished last query of a range simply starts the next range: the
+    // buffer is contiguous, nothing is copied).
+    const uint64_t n_ranges = n >= (512ull << 20) ? 4 : (n >= (128ull << 20) ? 2 : 1);
+    const uint64_t range_bytes = ((n + n_ranges - 1) / n_ranges + (uint64_t)kTile - 1) / (uint64_t)kTile * (uint64_t)kTile;
+    Downloader dl(c, r);
     for (int attempt = 0; attempt < 6; attempt++) {
         ensure_out(c, k);
         reset_counters_async(c, s, true);
-        launch_chunk(c, dtext, 0, n, true, k, s, 0, true);
-        // gather needs n_rec: read it from the device counters inside the kernel launch geometry -> one sync
-        read_counters(c, s);
-        Counters h = *c->h_ctr;
-        if (h.cap_overflow || n_rec_of(h) > k.rec || n_slots_of(h) > k.slots || h.n_defer > k.defer) {
-            grow_caps(h, k, h.n_defer);
+        bool retry = false;
+        uint64_t begin = 0;
+        uint32_t rec_done = 0;
+        uint64_t defer_total = 0;
+        double ms_tile = 0, ms_long = 0, ms_post = 0;
+        uint64_t launches = 0;
+        Counters h{};
+        for (uint64_t ri = 0; ri < n_ranges && !retry; ri++) {
+            const bool final_range = ri + 1 == n_ranges;
+            const uint64_t end = final_range ? n : std::min<uint64_t>(n, (ri + 1) * range_bytes);
+            if (end <= begin && !final_range) continue;
+            if (ri) reset_counters_async(c, s, false);
+            launch_chunk(c, dtext, begin, end, final_range, k, s, rec_done, true);
+            launches++;
+            read_counters(c, s);
+            h = *c->h_ctr;
+            ms_tile += ev_ms(c->ev[0], c->ev[1]);
+            ms_long += ev_ms(c->ev[1], c->ev[2]);
+            defer_total = std::max<uint64_t>(defer_total, h.n_defer);
+            c->tm.n_deferred_runs += h.n_defer;
+            if (h.cap_overflow || n_rec_of(h) > k.rec || n_slots_of(h) > k.slots || h.n_defer > k.defer) {
+                grow_caps(h, k, h.n_defer);
+                retry = true;
+                break;
+            }
+            check_device_error(c, h, 0);
+            CK(cudaEventRecord(c->ev[3], s));
+            launch_gather(c, dtext, rec_done, (uint32_t)n_rec_of(h), k, s);
+            if (final_range) launch_dup(c, (uint32_t)n_rec_of(h), s);
+            CK(cudaEventRecord(c->ev[4], s));
+            rec_done = (uint32_t)n_rec_of(h);
+            read_counters(c, s);
+            h = *c->h_ctr;
+            ms_post += ev_ms(c->ev[3], c->ev[4]);
+            if (h.cap_overflow || h.pool_used > k.pool) {
+                grow_caps(h, k, defer_total);
+                retry = true;
+                break;
+            }
+            check_device_error(c, h, 0);
+            if (!final_range) {
+                if (ri == 0 && end > 0) {
+                    // size the pinned result buffers from the density of the first range
+                    const double f = 1.15 * (double)n / (double)end;
+                    dl.reserve((uint64_t)(n_rec_of(h) * f) + 4096, (uint64_t)(n_slots_of(h) * f) + 8192, (uint64_t)(h.pool_used * f) + 65536);
+                }
+                dl.push(h);  // runs on the download stream under the next range's kernels
+                begin = h.tail_start != ~0ull ? h.tail_start : end;
+            }
+        }
+        if (retry) {
+            dl.abandon();
+            c->tm = blu_timings{};
             continue;
         }
-        check_device_error(c, h, 0);
-        CK(cudaEventRecord(c->ev[3], s));
-        launch_gather(c, dtext, 0, n_rec_of(h), k, s);
-        launch_dup(c, n_rec_of(h), s);
-        CK(cudaEventRecord(c->ev[4], s));
-        read_counters(c, s);
-        h = *c->h_ctr;
-        if (h.cap_overflow || h.pool_used > k.pool) {
-            grow_caps(h, k, h.n_defer);
-            continue;
+        if (h.dup_found) {
+            dl.abandon();
+            throw NonContiguous("a query id occurs in two non-adjacent groups of rows");
         }
-        check_device_error(c, h, 0);
-        if (h.dup_found) throw NonContiguous("a query id occurs in two non-adjacent groups of rows");
         if (n_rec_of(h) == 0) throw DataErr("the blast output holds no rows");
-        c->tm.ms_tile_kernel = ev_ms(c->ev[0], c->ev[1]);
-        c->tm.ms_longrun_kernel = ev_ms(c->ev[1], c->ev[2]);
-        c->tm.ms_gather_kernel = ev_ms(c->ev[3], c->ev[4]);
-        c->tm.ms_total_device = c->tm.ms_tile_kernel + c->tm.ms_longrun_kernel + c->tm.ms_gather_kernel;
+        c->tm.ms_tile_kernel = ms_tile;
+        c->tm.ms_longrun_kernel = ms_long;
+        c->tm.ms_gather_kernel = ms_post;
+        c->tm.ms_total_device = ms_tile + ms_long + ms_post;
         c->tm.text_bytes = n;
         c->tm.taxonomy_bytes = c->tax->device_bytes();
-        c->tm.n_deferred_runs = h.n_defer;
-        finish_result(c, h, s, r);
+        c->tm.n_tile_launches = launches;
+        dl.finish(h);
         return;
     }
     throw std::runtime_error("output capacity did not converge");
@@ -532,6 +620,7 @@ void run_host(blu_ctx* c, const char* text, uint64_t n, blu_result* r) {
     if (!single) c->d_text[1].ensure(buf_bytes);
     Caps k = initial_caps(n);
     cudaStream_t s = c->stream, cs = c->copy_stream;
+    Downloader dl(c, r);
     auto t0 = std::chrono::steady_clock::now();
     for (int attempt = 0; attempt < 6; attempt++) {
         ensure_out(c, k);
@@ -541,6 +630,7 @@ void run_host(blu_ctx* c, const char* text, uint64_t n, blu_result* r) {
         uint32_t rec_done = 0;           // records already gathered
         uint64_t defer_total = 0;
         double ms_tile = 0, ms_long = 0, ms_gather = 0;
+        uint64_t launches = 0;
         auto issue_h2d = [&](uint64_t ci) {
             const uint64_t off = ci * chunk, len = std::min(chunk, n - off);
             CK(cudaMemcpyAsync(c->d_text[ci & 1].p + text_off, text + off, len, cudaMemcpyHostToDevice, cs));
@@ -590,13 +680,28 @@ void run_host(blu_ctx* c, const char* text, uint64_t n, blu_result* r) {
                     if (tail_len > carry) throw UnsupportedErr("a single query spans more than the 64 MiB carry buffer between streamed chunks");
                 }
             }
-            CK(cudaStreamSynchronize(s));  // gather must finish before this buffer is overwritten two chunks later
+            read_counters(c, s);  // (also: gather must finish before this buffer is overwritten two chunks later)
             ms_gather += ev_ms(c->ev[3], c->ev[4]);
             c->tm.n_deferred_runs += h.n_defer;
+            launches++;
+            if (!final_chunk) {
+                const Counters hg = *c->h_ctr;
+                if (hg.cap_overflow || hg.pool_used > k.pool) {
+                    grow_caps(hg, k, defer_total);
+                    retry = true;
+                    break;
+                }
+                if (ci == 0) {
+                    const double f = 1.15 * (double)n / (double)len;
+                    dl.reserve((uint64_t)(n_rec_of(hg) * f) + 4096, (uint64_t)(n_slots_of(hg) * f) + 8192, (uint64_t)(hg.pool_used * f) + 65536);
+                }
+                dl.push(hg);  // result download of this chunk runs beside the next chunks' host->device copies
+            }
         }
         if (retry) {
             CK(cudaStreamSynchronize(cs));
             CK(cudaStreamSynchronize(s));
+            dl.abandon();
             c->tm = blu_timings{};
             continue;
         }
@@ -605,18 +710,23 @@ void run_host(blu_ctx* c, const char* text, uint64_t n, blu_result* r) {
         Counters h = *c->h_ctr;
         if (h.cap_overflow || h.pool_used > k.pool) {
             grow_caps(h, k, defer_total);
+            dl.abandon();
             c->tm = blu_timings{};
             continue;
         }
         check_device_error(c, h, 0);
-        if (h.dup_found) throw NonContiguous("a query id occurs in two non-adjacent groups of rows");
+        if (h.dup_found) {
+            dl.abandon();
+            throw NonContiguous("a query id occurs in two non-adjacent groups of rows");
+        }
         if (n_rec_of(h) == 0) throw DataErr("the blast output holds no rows");
         c->tm.ms_tile_kernel = ms_tile;
         c->tm.ms_longrun_kernel = ms_long;
         c->tm.ms_gather_kernel = ms_gather;
         c->tm.text_bytes = n;
         c->tm.taxonomy_bytes = c->tax->device_bytes();
-        finish_result(c, h, s, r);
+        c->tm.n_tile_launches = launches;
+        dl.finish(h);
         c->tm.ms_total_device = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
         return;
     }
@@ -660,6 +770,7 @@ int blu_ctx_create(const blu_opts* opts, blu_ctx** out) {
         c->sms = prop.multiProcessorCount;
         CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
         for (auto& e2 : c->ev) CK(cudaEventCreate(&e2));
         for (auto& e2 : c->ev_h2d) CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
         for (auto& e2 : c->ev_free) CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
@@ -682,6 +793,7 @@ void blu_ctx_destroy(blu_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
+    if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
     c->d_lin_off.release(), c->d_lvl.release(), c->d_bean.release(), c->d_irank.release(), c->d_cut.release();
     c->d_rcls.release(), c->d_acls.release(), c->d_linok.release(), c->d_slots.release();
     c->d_text[0].release(), c->d_text[1].release(), c->d_rec.release(), c->d_beans.release(), c->d_accs.release();
@@ -697,6 +809,7 @@ void blu_ctx_destroy(blu_ctx* c) {
         if (e) cudaEventDestroy(e);
     if (c->stream) cudaStreamDestroy(c->stream);
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->d2h_stream) cudaStreamDestroy(c->d2h_stream);
     delete c;
 }
 
