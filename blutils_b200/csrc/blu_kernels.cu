@@ -28,7 +28,7 @@ constexpr int kMaxRuns = kRowCap;           // owned heads <= rows in the window
 constexpr int kTopList = 768;             // top rows a tile can queue (beyond: block path)
 constexpr int kTileQ = 384;               // queries a tile can queue (beyond: block path)
 constexpr int kLongTopCap = 1024;         // largest top bit-score group the block path sorts
-constexpr int kLongThreads = 256;
+constexpr int kLongThreads = 512;
 constexpr int kLongWarps = kLongThreads / 32;
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -579,12 +579,17 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
 // ---------------------------------------------------------------------------------------------------------------
 // long-run kernel: one CTA per deferred run
 // ---------------------------------------------------------------------------------------------------------------
+constexpr int kQidCache = 256;  // bytes of the run's query id kept in shared memory
+
 struct LongSmem {
     WindowIndex W;
     long long bits[kRowCap];
     uint8_t same[kRowCap];
+    unsigned long long cand_off[kLongTopCap];  // rows whose bit score equals the running maximum, in file order
+    uint32_t cand_len[kLongTopCap];
     TopRow top[kLongTopCap];
     uint16_t tmp[5 * kLongTopCap];
+    uint8_t qid[kQidCache];  // first field (+ its tab) of the run's first row
     long long red_max[kLongWarps];
     int red_cnt[kLongWarps];
     int red_first[kLongWarps];
@@ -593,6 +598,14 @@ struct LongSmem {
 };
 
 static_assert(sizeof(LongSmem) <= 227 * 1024, "long-run CTA exceeds shared memory");
+
+// first field of window row `a` == the run's query id (`qid` holds the id and its terminating tab, qn bytes)
+__device__ __forceinline__ bool same_query_cached(const uint8_t* a, int alen, const uint8_t* qid, int qn) {
+    if (alen < qn) return false;
+    for (int i = 0; i < qn; i++)
+        if (a[i] != qid[i]) return false;
+    return true;
+}
 
 __device__ __forceinline__ bool same_query(const uint8_t* a, int alen, const uint8_t* text, unsigned long long s, unsigned long long end) {
     // compares the first field of row `a` (window) with the first field of the row at absolute offset s (global)
@@ -614,7 +627,7 @@ struct LongScan {
 
 // Stages the window that starts at `cur`, indexes and parses its rows, and marks which rows belong to the run
 // whose first row starts at absolute offset `s`.
-__device__ LongScan long_scan(LongSmem& S, const RunParams& p, unsigned long long s, unsigned long long cur, uint32_t& phase) {
+__device__ LongScan long_scan(LongSmem& S, const RunParams& p, unsigned long long s, unsigned long long cur, uint32_t& phase, int qn) {
     WindowIndex& W = S.W;
     LongScan r;
     const unsigned long long lo = cur & ~15ull;
@@ -622,6 +635,12 @@ __device__ LongScan long_scan(LongSmem& S, const RunParams& p, unsigned long lon
     __syncthreads();
     if (threadIdx.x == 0) W.bad_byte = INT_MAX;
     load_window(W, p.text, lo, g.loaded, phase, true);
+    if (threadIdx.x == 32) {
+        // a long run continues right behind this window: pull the next one into L2 meanwhile
+        const unsigned long long nb = lo + (unsigned long long)g.loaded;
+        const unsigned long long up = (p.end + 15ull) & ~15ull;
+        if (nb < up) tma_prefetch_l2(p.text + nb, (uint32_t)(up - nb < (unsigned long long)kWin ? up - nb : (unsigned long long)kWin));
+    }
     finish_geom(W, g, p.final_chunk != 0);
     r.giant = false;
     if (!scan_rows<kLongWarps>(W, g)) {
@@ -645,7 +664,7 @@ __device__ LongScan long_scan(LongSmem& S, const RunParams& p, unsigned long lon
             } else
                 lr = parse_row_masked(W.win, reinterpret_cast<const uint64_t*>(W.tabm), reinterpret_cast<const uint64_t*>(W.digm), st, st + len);
         }
-        bool sm = same_query(W.win + st, len, p.text, s, p.end);
+        const bool sm = qn > 0 ? same_query_cached(W.win + st, len, S.qid, qn) : same_query(W.win + st, len, p.text, s, p.end);
         if (lr.err && sm) report(p.ctr, lr.err, lo + st);
         S.bits[i] = lr.bits;
         S.same[i] = sm;
@@ -727,13 +746,25 @@ __global__ void __launch_bounds__(kLongThreads, 1) longrun_kernel(const __grid_c
             __syncthreads();
             if (!S.bcast[1]) continue;
         }
-        // ---- pass A: extent, max bit score, size of the top group -------------------------------------------
+        // ---- the run's query id (with its tab) is compared against every row: keep it in shared memory ---------------
+        if (tid == 0) {
+            int qn = 0;
+            while (qn < kQidCache && s + qn < p.end) {
+                const uint8_t b = p.text[s + qn];
+                S.qid[qn++] = b;
+                if (b == '\t') break;
+            }
+            S.bcast[4] = (qn > 0 && S.qid[qn - 1] == '\t') ? qn : 0;  // 0: id longer than the cache -> compare in global memory
+        }
+        __syncthreads();
+        const int qn = S.bcast[4];
+        // ---- single pass: extent, max bit score, and the rows that carry it (candidate list reset on a new maximum) --
         long long mx = LLONG_MIN;
         long long cnt = 0, nrows = 0;
         unsigned long long cur = s;
         bool ended = false, hit_end = false, fail = false;
         while (true) {
-            LongScan sc = long_scan(S, p, s, cur, phase);
+            LongScan sc = long_scan(S, p, s, cur, phase, qn);
             if (sc.giant && sc.d == 0 && sc.ncomplete == 0) {
                 // an unterminated row: either the chunk tail (carried over) or a row longer than the window
                 if (!sc.at_end || p.final_chunk) {
@@ -743,46 +774,48 @@ __global__ void __launch_bounds__(kLongThreads, 1) longrun_kernel(const __grid_c
                 hit_end = true;
                 break;
             }
+            const unsigned long long lo = cur & ~15ull;
+            // maximum of this window's rows of the run
             long long lm = LLONG_MIN;
-            int lc = 0;
             for (int i = tid; i < sc.d; i += kLongThreads) {
-                long long b = S.bits[i];
-                if (b > lm) {
-                    lm = b;
-                    lc = 1;
-                } else if (b == lm)
-                    lc++;
+                const long long b = S.bits[i];
+                lm = b > lm ? b : lm;
             }
 #pragma unroll
             for (int dd = 16; dd > 0; dd >>= 1) {
-                long long om = __shfl_xor_sync(0xffffffffu, lm, dd);
-                int oc = __shfl_xor_sync(0xffffffffu, lc, dd);
-                if (om > lm) {
-                    lm = om;
-                    lc = oc;
-                } else if (om == lm)
-                    lc += oc;
+                const long long om = __shfl_xor_sync(0xffffffffu, lm, dd);
+                lm = om > lm ? om : lm;
             }
-            if (lane == 0) {
-                S.red_max[warp] = lm;
-                S.red_cnt[warp] = lc;
-            }
+            if (lane == 0) S.red_max[warp] = lm;
             __syncthreads();
             long long wm = LLONG_MIN;
-            long long wc = 0;
-            for (int i = 0; i < kLongWarps; i++) {
-                if (S.red_max[i] > wm) {
-                    wm = S.red_max[i];
-                    wc = S.red_cnt[i];
-                } else if (S.red_max[i] == wm)
-                    wc += S.red_cnt[i];
+            for (int i = 0; i < kLongWarps; i++) wm = S.red_max[i] > wm ? S.red_max[i] : wm;
+            if (sc.d > 0 && wm > mx) {
+                mx = wm;
+                cnt = 0;  // earlier candidates are beaten
             }
-            if (sc.d > 0) {
-                if (wm > mx) {
-                    mx = wm;
-                    cnt = wc;
-                } else if (wm == mx)
-                    cnt += wc;
+            // append this window's rows with bits == mx, in file order
+            for (int b0 = 0; b0 < sc.d; b0 += kLongThreads) {
+                const int i = b0 + tid;
+                const bool top = i < sc.d && S.bits[i] == mx;
+                const unsigned bal = __ballot_sync(0xffffffffu, top);
+                if (lane == 0) S.red_cnt[warp] = __popc(bal);
+                __syncthreads();
+                long long before = cnt;
+                int total = 0;
+                for (int k = 0; k < kLongWarps; k++) {
+                    if (k < warp) before += S.red_cnt[k];
+                    total += S.red_cnt[k];
+                }
+                if (top) {
+                    const long long pos = before + __popc(bal & ((1u << lane) - 1u));
+                    if (pos < kLongTopCap) {
+                        S.cand_off[pos] = lo + S.W.row_s[i];
+                        S.cand_len[pos] = (uint32_t)((int)S.W.row_e[i + sc.eskip] - (int)S.W.row_s[i]);
+                    }
+                }
+                cnt += total;
+                __syncthreads();
             }
             nrows += sc.d;
             if (sc.d < sc.ncomplete) {
@@ -811,48 +844,24 @@ __global__ void __launch_bounds__(kLongThreads, 1) longrun_kernel(const __grid_c
             S.bcast[2] = (int)(unsigned)(rs >> 32);
             S.bcast[3] = (int)(unsigned)rs;
         }
-        __syncthreads();
+        // ---- join the top rows (read back from the text; they are few) -----------------------------------------------
+        int any_err = 0;
+        for (int i = tid; i < gcount; i += kLongThreads) {
+            const unsigned long long off = S.cand_off[i];
+            uint32_t err = heavy_parse_row(p.text + off, (int)S.cand_len[i], off, p.T, S.top[i]);
+            if (err) {
+                report(p.ctr, err, off);
+                any_err = 1;
+            }
+        }
+        any_err = __syncthreads_or(any_err);
         const unsigned rec_i = (unsigned)S.bcast[2], slot = (unsigned)S.bcast[3];
         if (rec_i >= p.rec_cap || slot + (unsigned)gcount > p.slot_cap) {
             if (tid == 0) p.ctr->cap_overflow = 1;
             continue;
         }
-        // ---- pass B: collect + join the top rows, in file order ----------------------------------------------
-        cur = s;
-        int filled = 0;
-        int any_err = 0;
-        while (filled < gcount) {
-            LongScan sc = long_scan(S, p, s, cur, phase);
-            const unsigned long long lo = cur & ~15ull;
-            for (int b = 0; b < sc.d; b += kLongThreads) {
-                const int i = b + tid;
-                const bool top = i < sc.d && S.bits[i] == mx;
-                const unsigned bal = __ballot_sync(0xffffffffu, top);
-                if (lane == 0) S.red_cnt[warp] = __popc(bal);
-                __syncthreads();
-                int before = filled;
-                for (int k = 0; k < warp; k++) before += S.red_cnt[k];
-                int total = 0;
-                for (int k = 0; k < kLongWarps; k++) total += S.red_cnt[k];
-                if (top) {
-                    int pos = before + __popc(bal & ((1u << lane) - 1u));
-                    if (pos >= kLongTopCap) pos = kLongTopCap - 1;  // cannot happen (cnt was checked); keeps smem safe
-                    const int st = S.W.row_s[i];
-                    uint32_t err = heavy_parse_row(S.W.win + st, (int)S.W.row_e[i + sc.eskip] - st, lo + st, p.T, S.top[pos]);
-                    if (err) {
-                        report(p.ctr, err, lo + st);
-                        any_err = 1;
-                    }
-                }
-                filled += total;
-                __syncthreads();
-            }
-            if (sc.d < sc.ncomplete || sc.at_end) break;
-            cur = sc.next;
-        }
-        any_err = __syncthreads_or(any_err);
-        if (any_err || filled != gcount) {
-            if (!any_err && tid == 0) report(p.ctr, DE_INTERNAL, s);
+        if (any_err) {
+            if (tid == 0) p.records[rec_i].status = 0, p.records[rec_i].n_rows = 0, p.records[rec_i].query_len = 0, p.records[rec_i].n_accessions = 0;
             continue;
         }
         if (tid == 0) {
