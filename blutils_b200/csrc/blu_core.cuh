@@ -561,6 +561,97 @@ BLU_HD bool parse_row_fast(const uint8_t* win, const uint32_t* tabw32, const uin
     return true;
 }
 
+// ---- lean path: the numeric tail of the row in two 64-bit masks -----------------------------------------------------
+// The streaming tile kernel's per-row parser.  The first two tabs (qseqid, saccver) are taken from the first 64 bytes
+// of the row; the 11 numeric columns behind them ("tail", at most 64 bytes) are validated with a handful of 64-bit
+// mask operations on the tab / digit masks re-aligned to the tail: tab count, no empty field, non-digit bytes only
+// inside pident / evalue / bitscore and of the accepted shapes.  Like parse_row_fast() it only ACCEPTS rows it fully
+// understands and returns false for everything else (the caller then runs parse_row_masked(), the complete grammar),
+// so it can never change a result or an error decision.
+BLU_HD int blu_popc64(uint64_t x) {
+#if defined(__CUDA_ARCH__)
+    return __popcll(x);
+#else
+    return __builtin_popcountll(x);
+#endif
+}
+BLU_HD int blu_clz64(uint64_t x) {  // x != 0
+#if defined(__CUDA_ARCH__)
+    return __clzll((long long)x);
+#else
+    return __builtin_clzll(x);
+#endif
+}
+// 64 mask bits starting at (window) bit position `pos` (reads words pos/32 .. pos/32+2)
+BLU_HD uint64_t bits64_at(const uint32_t* w, int pos) {
+    const int i = pos >> 5;
+    const uint32_t sh = (uint32_t)pos & 31u;
+    const uint32_t a = w[i], b = w[i + 1], c = w[i + 2];
+    return (uint64_t)blu_funnel_r(a, b, sh) | ((uint64_t)blu_funnel_r(b, c, sh) << 32);
+}
+
+BLU_HD bool parse_row_lean(const uint8_t* win, const uint32_t* tabw32, const uint32_t* digw32, int s, int e, int64_t& bits, int& q_len) {
+    // first two tabs: qseqid and saccver end within the first 64 bytes of the row
+    uint64_t th = bits64_at(tabw32, s);
+    if (th == 0) return false;
+    const int p1 = blu_ctz64(th);
+    th &= th - 1;
+    if (th == 0) return false;
+    const int p2 = blu_ctz64(th);
+    const int a = s + p2 + 1;  // first byte of staxid
+    const int m = e - a;       // bytes of the numeric tail
+    if (p1 < 1 || p2 - p1 < 2 || m < 21 || m > 64) return false;
+    const uint64_t mm = m == 64 ? ~0ull : ((1ull << m) - 1ull);
+    const uint64_t tt = bits64_at(tabw32, a) & mm;
+    const uint64_t dt = bits64_at(digw32, a) & mm;
+    if (blu_popc64(tt) != 10) return false;
+    // no empty field: no two adjacent tabs, no tab at either end of the tail
+    if ((tt & (tt << 1)) | (tt & 1ull) | (tt >> (m - 1))) return false;
+    const int q3 = blu_ctz64(tt);                   // end of staxid
+    const int q4 = blu_ctz64(tt & (tt - 1));        // end of pident
+    const int q12 = 63 - blu_clz64(tt);             // tab in front of bitscore
+    const int q11 = 63 - blu_clz64(tt ^ (1ull << q12));  // tab in front of evalue
+    // integer columns <= 18 digits: staxid directly, length..send (7 fields, 6 tabs) through their total span
+    if (q3 > 18 || q11 - q4 - 1 > 30) return false;
+    const uint64_t o = ~(dt | tt) & mm;  // bytes that are neither digit nor tab
+    const uint64_t below_q4 = (1ull << q4) - 1ull;
+    const uint64_t in_pid = below_q4 & ~((2ull << q3) - 1ull);
+    const uint64_t from_ev = ~((2ull << q11) - 1ull);  // evalue, its tab, bitscore
+    if (o & ~(in_pid | from_ev)) return false;
+    // pident: digits with at most one '.', at least one digit
+    const uint64_t op = o & below_q4;
+    if (op) {
+        if (op & (op - 1)) return false;
+        if (q4 - q3 - 1 < 2 || win[a + blu_ctz64(op)] != '.') return false;
+    }
+    // evalue: one of the common float shapes, else the DFA
+    const int l_ev = q12 - q11 - 1;
+    if (l_ev > 32) return false;
+    {
+        const uint32_t oe = (uint32_t)(o >> (q11 + 1)) & (l_ev == 32 ? 0xFFFFFFFFu : ((1u << l_ev) - 1u));
+        if (oe && !float_shape_ok(win + a + q11 + 1, l_ev, oe) && !check_float(win + a + q11 + 1, l_ev)) return false;
+    }
+    // bit score: digits[.digits], <= 15 digits in total (trunc(value) is then exactly the integer part), <= 9 of them
+    // in front of the point (32-bit arithmetic)
+    const int l_bits = m - q12 - 1;
+    if (l_bits > 16) return false;
+    const uint32_t ob = (uint32_t)(o >> (q12 + 1));
+    int n_int = l_bits;
+    if (ob) {
+        if (ob & (ob - 1)) return false;
+        n_int = blu_ffs32(ob);
+        if (l_bits < 2 || win[a + q12 + 1 + n_int] != '.') return false;
+    } else if (l_bits > 15)
+        return false;
+    if (n_int > 9) return false;
+    const uint8_t* b = win + a + q12 + 1;
+    uint32_t v = 0;
+    for (int i = 0; i < n_int; i++) v = v * 10u + (uint32_t)(b[i] - '0');
+    bits = (int64_t)v;
+    q_len = p1;
+    return true;
+}
+
 // first fields (qseqid) of the rows starting at a and b are equal
 BLU_HD uint32_t load_u32_unaligned(const uint8_t* win, int pos) {
 #if defined(__CUDA_ARCH__)
@@ -585,6 +676,35 @@ BLU_HD bool same_first_field(const uint8_t* win, const uint64_t* tabw, int a, in
     for (; i < la; i++)
         if (win[a + i] != win[b + i]) return false;
     return true;
+}
+
+// Same test for the streaming kernel, which already knows the length `la` of the first field of the row at `a`:
+// the row at `b` must have its first tab at the same distance and the same bytes in front of it.
+BLU_HD bool same_qid_lean(const uint8_t* win, const uint32_t* tabw32, int a, int la, int b) {
+    if (la >= 32 || la < 4) {
+        // rare shapes: the first tab of b by the general search
+        int lb = 0;
+        while (true) {
+            const uint32_t t = bits_at(tabw32, b + lb);
+            if (t) {
+                lb += blu_ffs32(t);
+                break;
+            }
+            lb += 32;
+            if (lb > la) return false;
+        }
+        if (lb != la) return false;
+        for (int i = 0; i < la; i++)
+            if (win[a + i] != win[b + i]) return false;
+        return true;
+    }
+    const uint32_t tb = bits_at(tabw32, b);
+    if ((tb & ((2u << la) - 1u)) != (1u << la)) return false;  // first tab of b exactly at la
+    uint32_t diff = 0;
+    int i = 0;
+    for (; i + 4 <= la; i += 4) diff |= load_u32_unaligned(win, a + i) ^ load_u32_unaligned(win, b + i);
+    if (i < la) diff |= load_u32_unaligned(win, a + la - 4) ^ load_u32_unaligned(win, b + la - 4);  // overlapping last word
+    return diff == 0;
 }
 
 // ---- top-group rows ---------------------------------------------------------------------------------------------

@@ -93,7 +93,8 @@ struct WindowIndex {
 
 struct WinGeom {
     unsigned long long lo;  // absolute offset of win[0]
-    int rb;                 // begin - lo (may be negative)
+    int vb;                 // first valid byte of the window (everything before it is not text / not loaded)
+    int rb;                 // == vb when a row is known to start there (virtual newline in front), else -1
     int re;                 // end - lo   (may exceed the window)
     int loaded;             // bytes staged
     int L;                  // bytes scanned (text end + optional virtual newline)
@@ -128,11 +129,12 @@ __device__ __forceinline__ WinGeom make_geom(unsigned long long lo, int max_byte
     if (hi > up) hi = up;
     g.loaded = hi > lo ? (int)(hi - lo) : 0;
     g.rb = begin >= lo ? (int)((begin - lo) > 0x7fffffffull ? 0x7fffffff : (begin - lo)) : -1;
+    g.vb = g.rb < 0 ? 0 : g.rb;
     long long re = (long long)end - (long long)lo;
     g.re = re > (long long)kWin + 64 ? kWin + 64 : (int)re;
     g.covers_eof = end <= lo + (unsigned long long)g.loaded;
     g.L = g.re < g.loaded ? g.re : g.loaded;
-    g.qlo = g.rb < 0 ? 0 : g.rb;
+    g.qlo = g.vb;
     g.qhi = g.L;
     return g;
 }
@@ -182,7 +184,7 @@ __device__ __forceinline__ void classify_chunk(WindowIndex& W, const WinGeom& g,
                                                uint32_t& end) {
     const int pos0 = c << 4;
     const uint4 v = *reinterpret_cast<const uint4*>(W.win + pos0);
-    const int rb = g.rb < 0 ? 0 : g.rb;
+    const int rb = g.vb;
     const int tend = g.re < g.loaded ? g.re : g.loaded;  // end of the text inside the window
     const uint32_t nx = bytes_eq(v.x, 0x0A0A0A0Au), ny = bytes_eq(v.y, 0x0A0A0A0Au), nz = bytes_eq(v.z, 0x0A0A0A0Au), nw = bytes_eq(v.w, 0x0A0A0A0Au);
     const uint32_t tx = bytes_eq(v.x, 0x09090909u), ty = bytes_eq(v.y, 0x09090909u), tz = bytes_eq(v.z, 0x09090909u), tw = bytes_eq(v.w, 0x09090909u);
@@ -216,11 +218,12 @@ __device__ __forceinline__ void classify_chunk(WindowIndex& W, const WinGeom& g,
 template <int NWARPS>
 __device__ bool scan_rows(WindowIndex& W, const WinGeom& g) {
     const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+    const int cbeg = g.vb >> 4;  // chunks in front of the first valid byte are not scanned
     const int nchunks = (g.L + 15) >> 4;
-    const int cpw = (((nchunks + NWARPS - 1) / NWARPS) + 31) & ~31;  // chunks per warp, whole 32-lane rounds
-    const int c0 = w * cpw;
+    const int cpw = ((((nchunks - cbeg) + NWARPS - 1) / NWARPS) + 31) & ~31;  // chunks per warp, whole 32-lane rounds
+    const int c0 = cbeg + w * cpw;
     const int c1 = c0 + cpw < nchunks ? c0 + cpw : nchunks;
-    const int rb = g.rb < 0 ? 0 : g.rb;
+    const int rb = g.vb;
     // ---- pass 1: classify; every warp compacts the row starts / ends of its chunk range ------------------------------
     // A valid row is >= 26 bytes, so a 16-byte chunk holds at most one row start and one row end; a chunk with more
     // proves a malformed (too short) row and is reported as such.  So a warp's k-th row start can be parked at index
@@ -289,7 +292,7 @@ __device__ bool scan_rows(WindowIndex& W, const WinGeom& g) {
 // Writes the virtual newline that terminates an unterminated last row (final chunk only) and fixes g.L.
 __device__ __forceinline__ void finish_geom(WindowIndex& W, WinGeom& g, bool final_chunk) {
     if (final_chunk && g.covers_eof && g.re > 0 && g.re <= g.loaded) {
-        bool needs = (g.re - 1 >= 0) && W.win[g.re - 1] != '\n' && (g.rb < 0 || g.re - 1 >= g.rb);
+        bool needs = (g.re - 1 >= 0) && W.win[g.re - 1] != '\n' && g.re - 1 >= g.vb;
         if (needs) {
             __syncthreads();
             if (threadIdx.x == 0) W.win[g.re] = '\n';  // win has 128 spare bytes
@@ -300,34 +303,88 @@ __device__ __forceinline__ void finish_geom(WindowIndex& W, WinGeom& g, bool fin
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// tile kernel
+// tile kernel (streaming)
+//
+// The text [begin, end) is cut into gridDim.x contiguous segments; CTA c owns every query run whose first row starts
+// inside segment c.  It walks its segment in windows of kTile bytes, staged into shared memory by TMA bulk copies
+// into two alternating buffers (the copy of window k+1 runs under the row / run phases of window k).  A window
+// starts 16-byte aligned just in front of the last complete row of the previous window (that row is the
+// "look-behind" row: it is only there so that the first new row can be compared with its predecessor), so no row
+// and no query ever has to fit a window: the unfinished query is carried in shared memory (row count, best bit
+// score, its top rows so far) from window to window, and a CTA keeps walking past the end of its segment until the
+// query it has open ends.  Phases of one window (all barriers are CTA-wide):
+//   B  classify   every lane owns 32 bytes: SIMD-in-register byte tests (ASCII fast path) -> newline / tab / digit
+//                 bitmasks (dp4a packing), row-start bits, per-warp row counts
+//   C  index      per-warp compaction of the row starts into row_s[] (two ballots per round), next window's TMA
+//   D  rows       one thread per row: validation + truncated bit score (parse_row_lean, falling back to the full
+//                 grammar), head flag (query id differs from the previous row's)
+//   E  runs       one warp per query run: extent, best bit score, top rows (ballot compaction) -> tile top list
+//   K  reserve    warp 0: merges the carried query, ONE global atomic reserves the records / top-row slots of the
+//                 whole window, prefix sums give every run its place
+//   F  emit       one thread per top row (field split + number parse) and one per finished query (record header)
 // ---------------------------------------------------------------------------------------------------------------
-struct WarpScratch {
-    uint16_t idx[32];
+constexpr int kSWarps = kTileThreads / 32;
+constexpr int kUnits = kTile / 32 + 1;     // 32-byte units of a window (+1: the unit that can hold a virtual final newline)
+constexpr int kSRowCap = kTile / 26 + 8;   // a valid row is >= 26 bytes
+constexpr int kRunBatch = 256;             // runs handled per pass of phases E/K/F
+constexpr int kTopCap = 1024;              // top rows a pass can queue (beyond: block path)
+constexpr int kCarryTop = 32;              // top rows of the open query kept in shared memory (beyond: block path)
+
+static_assert(kSRowCap < 0x8000, "row indices are 15-bit");
+static_assert(kTile % 32 == 0 && kTile + 128 < 65536, "window offsets are 16-bit");
+
+enum : uint8_t { RK_EMIT = 1, RK_DEFER = 2, RK_PSEUDO = 4, RK_OPEN = 8, RK_OVF = 16 };
+
+struct CarryRun {
+    unsigned long long head_abs;  // offset of the open query's first row
+    uint32_t qlen;
+    uint32_t nrows;
+    int32_t mx;     // best truncated bit score so far
+    int32_t g;      // top rows so far (kept in tops[])
+    int32_t open;
+    int32_t deferred;  // the query goes to the block path when it ends (top group too large / bit score beyond int32)
+    TopRowRaw tops[kCarryTop];
 };
 
-struct TileQuery {
-    uint16_t head;    // row index of the query's first row
-    uint16_t n_rows;
-    uint16_t g;       // size of the top bit-score group
-    uint16_t top0;    // first entry in top_row[]
-    int32_t bits;     // truncated top bit score
+struct StreamSmem {
+    alignas(128) uint8_t win[2][kTile + 128];
+    // byte-class bitmasks, bit i of word u = byte 32u+i of the window (read by the row parsers as 32/64-bit words)
+    alignas(8) uint32_t tabm[kUnits + 7];
+    alignas(8) uint32_t digm[kUnits + 7];
+    alignas(8) uint32_t nlm[kUnits + 7];
+    uint32_t stm[kUnits + 7];  // row starts
+    uint16_t row_s[kSRowCap + 2];
+    int32_t bits[kSRowCap];
+    uint8_t flags[kSRowCap];   // bit1: bit score does not fit int32
+    uint32_t headw[kSRowCap / 32 + 2];
+    uint16_t runs[kSRowCap + 1];  // head rows in arrival order (bit 15: continuation of the carried query)
+    // one pass of runs
+    unsigned long long run_abs[kRunBatch];
+    uint32_t run_qlen[kRunBatch];
+    uint32_t run_nrows[kRunBatch];
+    int32_t run_mx[kRunBatch];
+    int32_t run_dst[kRunBatch];   // where this window's top rows of the run go: >= 0 offset inside the run's slots, < 0: carry.tops[-1-dst]
+    uint32_t run_slot[kRunBatch];  // first slot of the run, relative to the pass
+    uint16_t run_rec[kRunBatch];   // record of the run, relative to the pass
+    uint16_t run_h[kRunBatch];
+    uint16_t run_e[kRunBatch];
+    uint16_t run_t0[kRunBatch];
+    uint16_t run_gpart[kRunBatch];  // top rows of the run in this window (0 when they are not needed)
+    uint16_t run_gtot[kRunBatch];
+    uint8_t run_kind[kRunBatch];
+    uint16_t top_row[kTopCap];
+    uint16_t top_run[kTopCap];
+    uint16_t stage[kSWarps][32];
+    CarryRun carry;
+    alignas(8) unsigned long long mbar[2];
+    int warp_cnt[kSWarps];
+    int n_starts, last_nl, bad_byte, has_blank, crowded;
+    int n_runs, next_run, n_top;
+    uint32_t rec_base, slot_base;
+    int pass_ok;
 };
 
-static_assert(kWin + 128 < 65536, "window offsets are 16-bit");
-static_assert(2 * (kChunks + 8) * sizeof(uint16_t) >= kRowCap * sizeof(int32_t), "bit scores alias the start/end masks");
-
-struct TileSmem {
-    WindowIndex W;
-    uint8_t flags[kRowCap];  // bit0: head of a run, bit1: bit score does not fit int32
-    uint16_t runs[kMaxRuns];
-    WarpScratch ws[kWarps];
-    int n_runs;
-    int next_run;    // dynamic distribution of the runs over the warps
-    int first_fwd;   // index of the first row of the look-ahead region (start >= own_hi)
-};
-
-static_assert(sizeof(TileSmem) * kTileCtasPerSm + 1024 * kTileCtasPerSm <= 227 * 1024, "tile CTAs must fit one SM");
+static_assert((sizeof(StreamSmem) + 1024) * kTileCtasPerSm <= 227 * 1024, "tile CTAs must fit one SM");
 
 __device__ __forceinline__ void push_defer(const RunParams& p, unsigned long long off, unsigned check_prev) {
     unsigned i = atomicAdd(&p.ctr->n_defer, 1u);
@@ -337,242 +394,599 @@ __device__ __forceinline__ void push_defer(const RunParams& p, unsigned long lon
         p.ctr->cap_overflow = 1;
 }
 
+__device__ __forceinline__ void stream_issue_load(StreamSmem& S, int buf, const uint8_t* text, unsigned long long lo, int bytes) {
+    fence_proxy_async();
+    mbar_expect_tx(&S.mbar[buf], (uint32_t)bytes);
+    for (int o = 0; o < bytes; o += 16384) {
+        const int n = bytes - o < 16384 ? bytes - o : 16384;
+        tma_bulk_g2s(S.win[buf] + o, text + lo + o, (uint32_t)n, &S.mbar[buf]);
+    }
+}
+
+// dp4a gathers the 0x80 flags of two words into 128 * (8-bit mask)
+__device__ __forceinline__ uint32_t pack8(uint32_t a, uint32_t b) { return __dp4a(a, 0x08040201u, __dp4a(b, 0x80402010u, 0u)); }
+__device__ __forceinline__ uint32_t pack32(const uint32_t (&f)[8]) {
+    const uint32_t b0 = pack8(f[0], f[1]) + (pack8(f[2], f[3]) << 8);  // 128 * 16-bit mask
+    const uint32_t b1 = pack8(f[4], f[5]) + (pack8(f[6], f[7]) << 8);
+    const unsigned long long c = (unsigned long long)b0 + ((unsigned long long)b1 << 16);
+    return (uint32_t)(c >> 7);
+}
+
+// Exact byte-wise classification of one 32-byte unit: text edges (bytes outside [vb, tend) are not text), units with
+// non-ASCII bytes, and the exact '"' / '\r' search behind the cheap "suspicious byte" test.
+__device__ __noinline__ void classify_unit_slow(StreamSmem& S, const uint8_t* w, int pos0, int vb, int tend, uint32_t& nl, uint32_t& tab,
+                                                uint32_t& dig) {
+    nl = tab = dig = 0;
+    int bad = INT_MAX;
+    for (int k = 0; k < 32; k++) {
+        const int pos = pos0 + k;
+        if (pos < vb || pos >= tend) continue;
+        const uint32_t c = w[pos];
+        if (c == '\n') nl |= 1u << k;
+        if (c == '\t') tab |= 1u << k;
+        if (c - '0' <= 9u) dig |= 1u << k;
+        if ((c == '"' || c == '\r') && pos < bad) bad = pos;
+    }
+    if (bad != INT_MAX) atomicMin(&S.bad_byte, bad);
+}
+
+// first head row at index >= from, or -1 (whole warp)
+__device__ __forceinline__ int next_head(const StreamSmem& S, int from, int n_rows, int lane) {
+    const int nwords = (n_rows + 31) >> 5;
+    for (int k0 = from >> 5; k0 < nwords; k0 += 32) {
+        const int k = k0 + lane;
+        uint32_t w = k < nwords ? S.headw[k] : 0u;
+        if (k == (from >> 5)) w &= ~0u << (from & 31);
+        const unsigned bal = __ballot_sync(0xffffffffu, w != 0);
+        if (bal) {
+            const int src = __ffs(bal) - 1;
+            const uint32_t wv = __shfl_sync(0xffffffffu, w, src);
+            return ((k0 + src) << 5) + __ffs(wv) - 1;
+        }
+    }
+    return -1;
+}
+
+// end (position of the newline) of the row that starts at window offset s, through the newline mask
+__device__ __noinline__ int row_end_search(const StreamSmem& S, int s, int limit) {
+    for (int u = s >> 5; (u << 5) <= limit; u++) {
+        uint32_t w = S.nlm[u];
+        if (u == (s >> 5)) w &= ~0u << (s & 31);
+        if (w) return (u << 5) + __ffs(w) - 1;
+    }
+    return limit;
+}
+
 __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(const __grid_constant__ RunParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    TileSmem& S = *reinterpret_cast<TileSmem*>(smem_raw);
-    WindowIndex& W = S.W;
-    int32_t* const row_bits = reinterpret_cast<int32_t*>(W.startm);  // valid between the row scan and the next load
+    StreamSmem& S = *reinterpret_cast<StreamSmem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) mbar_init(&W.mbar, 1);
+    const unsigned FULL = 0xffffffffu;
+    if (p.end <= p.begin) return;
+    // ---- this CTA's segment --------------------------------------------------------------------------------------
+    const unsigned long long total = p.end - p.begin;
+    unsigned long long seg = (total + gridDim.x - 1) / gridDim.x;
+    if (seg < 4ull * kTile) seg = 4ull * kTile;
+    const unsigned long long seg_lo = p.begin + (unsigned long long)blockIdx.x * seg;
+    if (seg_lo >= p.end) return;
+    const unsigned long long seg_hi = (seg_lo + seg < p.end) ? seg_lo + seg : p.end;
+    const unsigned long long b16 = p.begin & ~15ull;
+    const unsigned long long up = (p.end + 15ull) & ~15ull;
+
+    if (tid == 0) {
+        mbar_init(&S.mbar[0], 1);
+        mbar_init(&S.mbar[1], 1);
+        S.carry.open = 0;
+        S.carry.deferred = 0;
+        S.carry.g = 0;
+    }
+    for (int i = tid; i < 7; i += kTileThreads) S.tabm[kUnits + i] = S.digm[kUnits + i] = S.nlm[kUnits + i] = S.stm[kUnits + i] = 0u;
     __syncthreads();
-    uint32_t phase = 0;
+    uint32_t ph0 = 0, ph1 = 0;
 
-    const unsigned long long first_tile = p.begin / kTile;
-    const unsigned long long n_tiles = p.end > p.begin ? (p.end + kTile - 1) / kTile - first_tile : 0;
+    unsigned long long lo = seg_lo > p.begin + kBack ? (seg_lo - kBack) & ~15ull : b16;
+    if (lo < b16) lo = b16;
+    unsigned long long own_from = seg_lo;  // rows that start at or after this offset have not been processed yet
+    int buf = 0;
+    if (tid == 0) {
+        const unsigned long long n = up - lo < (unsigned long long)kTile ? up - lo : (unsigned long long)kTile;
+        stream_issue_load(S, 0, p.text, lo, (int)n);
+    }
 
-    for (unsigned long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const unsigned long long base = (first_tile + t) * (unsigned long long)kTile;
-        unsigned long long lo = base >= (unsigned long long)kBack ? base - kBack : 0;
-        const unsigned long long b16 = p.begin & ~15ull;
-        if (lo < b16) lo = b16;
-        const int max_bytes = (int)(base + kTile + kFwd - lo);
-        WinGeom g = make_geom(lo, max_bytes, p.begin, p.end);
-        if (g.loaded <= 0) continue;
-        __syncthreads();  // every warp is done with the previous tile (window, row tables, run queue)
+    while (true) {
+        const uint8_t* const win = S.win[buf];
+        const int loaded = (int)(up - lo < (unsigned long long)kTile ? up - lo : (unsigned long long)kTile);
+        const int tend = (int)(p.end - lo < (unsigned long long)loaded ? p.end - lo : (unsigned long long)loaded);
+        const bool covers_eof = p.end <= lo + (unsigned long long)loaded;
+        const bool has_begin = lo <= p.begin;            // the window contains the first byte of the text
+        const int vb = has_begin ? (int)(p.begin - lo) : 0;
         if (tid == 0) {
-            // published to the other threads by the mbarrier arrive (release) / wait (acquire) of the load below
-            W.bad_byte = INT_MAX;
+            S.last_nl = -1;
+            S.bad_byte = INT_MAX;
+            S.has_blank = 0;
+            S.crowded = 0;
             S.n_runs = 0;
-            S.next_run = 0;
-            S.first_fwd = 0x7fffffff;
+            S.n_top = 0;
         }
-        const unsigned long long own_lo = base, own_hi = base + kTile;
-        // every text byte lies in exactly one tile's [own_lo, own_hi): that tile reports a '"' / '\r' in it
-        g.qlo = own_lo > lo ? (int)(own_lo - lo) : 0;
-        if (g.rb > g.qlo) g.qlo = g.rb;
-        g.qhi = (int)(own_hi - lo) < g.L ? (int)(own_hi - lo) : g.L;
-        load_window(W, p.text, lo, g.loaded, phase, true);
-        if (tid == 32 && t + gridDim.x < n_tiles) {
-            // next tile of this CTA: start moving its owned bytes from HBM to L2 while this one is processed
-            const unsigned long long nb = (first_tile + t + gridDim.x) * (unsigned long long)kTile;
-            const unsigned long long up = (p.end + 15ull) & ~15ull;
-            if (nb < up) {
-                const unsigned long long n = up - nb < (unsigned long long)(kTile + kFwd) ? up - nb : (unsigned long long)(kTile + kFwd);
+        if (tid == 32) {
+            // the window after the next one: start moving it from HBM to L2
+            const unsigned long long nb = lo + 2ull * kTile - 512ull;
+            if (nb < up && (nb < seg_hi + kTile)) {
+                const unsigned long long n = up - nb < (unsigned long long)kTile ? up - nb : (unsigned long long)kTile;
                 tma_prefetch_l2(p.text + nb, (uint32_t)n);
             }
         }
-        finish_geom(W, g, p.final_chunk != 0);
-        if (!scan_rows<kWarps>(W, g)) {
-            if (tid == 0) report(p.ctr, DE_BAD_FIELD_COUNT, lo);
-            continue;
-        }
-        const int n_starts = W.n_starts, n_ends = W.n_ends;
-        const int eskip = (n_ends > 0 && (n_starts == 0 || W.row_e[0] < W.row_s[0])) ? 1 : 0;
-        const int ncomplete = n_starts < n_ends - eskip ? n_starts : n_ends - eskip;
-        const bool has_partial = n_starts > ncomplete;
-        const uint64_t* tabw = reinterpret_cast<const uint64_t*>(W.tabm);
-        const uint64_t* digw = reinterpret_cast<const uint64_t*>(W.digm);
-        if (W.bad_byte != INT_MAX && tid == 0) report(p.ctr, DE_QUOTE_OR_CR, lo + (unsigned)W.bad_byte);
-
-        const uint32_t* tabw32 = reinterpret_cast<const uint32_t*>(W.tabm);
-        const uint32_t* digw32 = reinterpret_cast<const uint32_t*>(W.digm);
-        // ---- phase P: one thread per row of the tile -----------------------------------------------------------------
-        //   head flag (first field differs from the previous row's), run list, validation + truncated bit score.
-        //   Rows before own_lo belong to runs of the previous tile; rows of the look-ahead region only get their head
-        //   flag here and are parsed lazily by the warp that owns their run (phase D).
-        int r_lo, r_hi;  // rows [r_lo, r_hi) start inside [own_lo, own_hi)
+        // wait for this window's bytes
         {
-            const int k_lo = own_lo > lo ? (int)(own_lo - lo) : 0, k_hi = (int)(own_hi - lo);
-            int a = 0, b = ncomplete;
-            while (a < b) {
-                const int m = (a + b) >> 1;
-                if ((int)W.row_s[m] < k_lo) a = m + 1; else b = m;
+            uint32_t& ph = buf ? ph1 : ph0;
+            while (!mbar_try_wait(&S.mbar[buf], ph)) {
             }
-            r_lo = a;
-            b = ncomplete;
+            ph ^= 1;
+        }
+        __syncthreads();  // (also publishes the resets above)
+        // an unterminated last row of the input is closed by a virtual newline at `tend`
+        const bool virt_nl = p.final_chunk && covers_eof && tend > vb && win[tend - 1] != '\n';
+        const int scan_len = tend + (virt_nl ? 1 : 0);
+        const int n_units = (scan_len + 31) >> 5;
+
+        // ---- phase B: classify -----------------------------------------------------------------------------------
+        const int upw = (((n_units + kSWarps - 1) / kSWarps) + 31) & ~31;  // units per warp, whole rounds
+        const int u0 = warp * upw;
+        const int u1 = u0 + upw < n_units ? u0 + upw : n_units;
+        {
+            int cnt = 0, my_last = -1;
+            uint32_t carry_in = 0;
+            if (u0 < u1 && u0 > 0 && (u0 << 5) - 1 >= vb) carry_in = win[(u0 << 5) - 1] == '\n';
+            for (int base = u0; base < u1; base += 32) {
+                const int u = base + lane;
+                const int pos0 = u << 5;
+                uint32_t nl = 0, tab = 0, dig = 0;
+                const bool live = u < u1;
+                const bool edge = (has_begin && pos0 <= vb) || pos0 + 32 > tend;  // first / last bytes of the text
+                if (live) {
+                    const uint4 v0 = *reinterpret_cast<const uint4*>(win + pos0);
+                    const uint4 v1 = *reinterpret_cast<const uint4*>(win + pos0 + 16);
+                    const uint32_t x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                    const uint32_t hi = (x[0] | x[1] | x[2] | x[3] | x[4] | x[5] | x[6] | x[7]) & 0x80808080u;
+                    if (__builtin_expect(edge || hi != 0, 0)) {
+                        classify_unit_slow(S, win, pos0, vb, tend, nl, tab, dig);
+                        if (virt_nl && tend >= pos0 && tend < pos0 + 32) nl |= 1u << (tend - pos0);
+                    } else {
+                        // ASCII bytes: per-byte sums stay below 0x100, so plain 32-bit adds classify four bytes at once
+                        uint32_t fn[8], ft[8], fd[8], sus = 0;
+#pragma unroll
+                        for (int k = 0; k < 8; k++) {
+                            const uint32_t tu = (x[k] ^ 0x09090909u) + 0x7F7F7F7Fu;  // bit 7 clear <=> tab
+                            const uint32_t nu = (x[k] ^ 0x0A0A0A0Au) + 0x7F7F7F7Fu;  // bit 7 clear <=> newline
+                            const uint32_t ge30 = x[k] + 0x50505050u, ge3a = x[k] + 0x46464646u, ge23 = x[k] + 0x5D5D5D5Du;
+                            ft[k] = ~tu & 0x80808080u;
+                            fn[k] = ~nu & 0x80808080u;
+                            fd[k] = ge30 & ~ge3a & 0x80808080u;
+                            sus |= ~ge23 & tu & nu;  // below '#' and neither tab nor newline: look closer
+                        }
+                        nl = pack32(fn);
+                        tab = pack32(ft);
+                        dig = pack32(fd);
+                        if (__builtin_expect((sus & 0x80808080u) != 0, 0)) {
+                            uint32_t a, b, c;
+                            classify_unit_slow(S, win, pos0, vb, tend, a, b, c);  // exact '"' / '\r' search
+                        }
+                    }
+                }
+                // row starts: a non-newline byte behind a newline (or behind the virtual newline in front of the text)
+                const uint32_t upv = __shfl_up_sync(FULL, nl, 1);
+                uint32_t carry = lane == 0 ? carry_in : (upv >> 31);
+                carry_in = __shfl_sync(FULL, nl, 31) >> 31;
+                uint32_t prev = (nl << 1) | carry;
+                uint32_t st;
+                if (__builtin_expect(edge, 0)) {
+                    const uint32_t valid_lo = pos0 >= vb ? ~0u : (vb - pos0 >= 32 ? 0u : ~0u << (vb - pos0));
+                    const uint32_t valid_hi = pos0 + 32 <= tend ? ~0u : (tend <= pos0 ? 0u : ~0u >> (32 - (tend - pos0)));
+                    if (pos0 <= vb) prev &= valid_lo;  // the byte in front of vb is not text
+                    if (has_begin && vb >= pos0 && vb < pos0 + 32) prev |= 1u << (vb - pos0);
+                    st = prev & ~nl & valid_lo & valid_hi;
+                } else
+                    st = prev & ~nl;
+                if (live) {
+                    S.tabm[u] = tab;
+                    S.digm[u] = dig;
+                    S.nlm[u] = nl;
+                    S.stm[u] = st;
+                    cnt += __popc(st);
+                    if (nl & prev) S.has_blank = 1;
+                    if (((st & 0xFFFFu) & ((st & 0xFFFFu) - 1u)) | ((st >> 16) & ((st >> 16) - 1u))) S.crowded = 1;
+                    if (nl) my_last = pos0 + 31 - __clz(nl);
+                }
+            }
+            cnt = __reduce_add_sync(FULL, cnt);
+            my_last = __reduce_max_sync(FULL, my_last);
+            if (lane == 0) {
+                S.warp_cnt[warp] = cnt;
+                if (my_last >= 0) atomicMax(&S.last_nl, my_last);
+            }
+        }
+        if (tid < 4) S.tabm[n_units + tid] = S.digm[n_units + tid] = S.nlm[n_units + tid] = S.stm[n_units + tid] = 0u;
+        __syncthreads();
+        // ---- phase C: row index ----------------------------------------------------------------------------------
+        int so = 0, n_starts = 0;
+#pragma unroll
+        for (int i = 0; i < kSWarps; i++) {
+            const int v = S.warp_cnt[i];
+            if (i < warp) so += v;
+            n_starts += v;
+        }
+        if (S.crowded || n_starts > kSRowCap) {
+            // a row shorter than 16 bytes / more rows than 26-byte rows fit: malformed input
+            if (tid == 0) report(p.ctr, DE_BAD_FIELD_COUNT, lo);
+            return;  // (no copy in flight: the next window has not been requested yet)
+        }
+        {
+            const uint32_t lt = (1u << lane) - 1u;
+            for (int base = u0; base < u1; base += 32) {
+                const int u = base + lane;
+                const uint32_t st = u < u1 ? S.stm[u] : 0u;
+                const uint32_t sl = st & 0xFFFFu, sh = st >> 16;
+                const unsigned bl = __ballot_sync(FULL, sl != 0), bh = __ballot_sync(FULL, sh != 0);
+                int idx = so + __popc(bl & lt) + __popc(bh & lt);
+                if (sl) S.row_s[idx++] = (uint16_t)((u << 5) + __ffs(sl) - 1);
+                if (sh) S.row_s[idx] = (uint16_t)((u << 5) + 16 + __ffs(sh) - 1);
+                so += __popc(bl) + __popc(bh);
+            }
+        }
+        __syncthreads();
+        const int last_nl = S.last_nl;
+        const int n_complete = (n_starts > 0 && (int)S.row_s[n_starts - 1] > last_nl) ? n_starts - 1 : n_starts;
+        if (tid == 0 && n_complete == n_starts) S.row_s[n_starts] = (uint16_t)(last_nl + 1);  // sentinel: end of the last row
+        if (S.bad_byte != INT_MAX && tid == 0) report(p.ctr, DE_QUOTE_OR_CR, lo + (unsigned)S.bad_byte);
+        // first row this CTA has not seen yet / first row beyond the segment
+        int r0, r_hi;
+        {
+            int a = 0, b = n_complete;
             while (a < b) {
                 const int m = (a + b) >> 1;
-                if ((int)W.row_s[m] < k_hi) a = m + 1; else b = m;
+                if (lo + S.row_s[m] < own_from) a = m + 1; else b = m;
+            }
+            r0 = a;
+            b = n_complete;
+            while (a < b) {
+                const int m = (a + b) >> 1;
+                if (lo + S.row_s[m] < seg_hi) a = m + 1; else b = m;
             }
             r_hi = a;
         }
-        if (tid == 0) S.first_fwd = r_hi < ncomplete ? r_hi : 0x7fffffff;
-        for (int r = tid; r < r_lo; r += kTileThreads) S.flags[r] = 0;
-        for (int r = r_lo + tid; r < ncomplete; r += kTileThreads) {
-            const int s = W.row_s[r];
-            const int e = W.row_e[r + eskip];
-            const unsigned long long abs = lo + s;
-            bool head;
-            if (r == 0)
-                head = g.rb >= 0 && s == g.rb;  // first row of the text (else: predecessor not in the window)
-            else
-                head = !same_first_field(W.win, tabw, W.row_s[r - 1], W.row_e[r - 1 + eskip], s, e);
-            uint8_t fl = head ? 1 : 0;
-            if (r < r_hi) {
-                if (head) {
-                    int i = atomicAdd(&S.n_runs, 1);
-                    S.runs[i] = (uint16_t)r;
-                } else if (r == 0) {
-                    push_defer(p, abs, 1);  // predecessor not in the window: the block path decides whether it is a head
-                }
-                int64_t bits;
-                int ql;
-                if (!parse_row_fast(W.win, tabw32, digw32, s, e, bits, ql)) {
-                    LightRow lr = parse_row_masked(W.win, tabw, digw, s, e);
-                    if (lr.err) report(p.ctr, lr.err, abs);
-                    bits = lr.bits;
-                }
-                const int32_t b32 = (int32_t)bits;
-                if ((int64_t)b32 != bits) fl |= 2;
-                row_bits[r] = b32;
-            }
-            S.flags[r] = fl;
+        const bool progress = n_complete > r0;
+        // next window: starts just in front of the last complete row (the look-behind row of the next window)
+        unsigned long long next_lo = lo;
+        if (progress) {
+            const unsigned long long la = lo + S.row_s[n_complete - 1];
+            next_lo = la > p.begin ? (la - 1) & ~15ull : b16;
+            if (next_lo < b16) next_lo = b16;
         }
-        if (tid == 0 && has_partial) {
-            const unsigned long long abs = lo + W.row_s[ncomplete];
-            if (abs >= own_lo && abs < own_hi) push_defer(p, abs, 1);  // unterminated row: the block path sorts it out
+        const bool may_continue = progress && !covers_eof && next_lo > lo;
+        if (tid == 0 && may_continue) {
+            const unsigned long long n = up - next_lo < (unsigned long long)kTile ? up - next_lo : (unsigned long long)kTile;
+            stream_issue_load(S, buf ^ 1, p.text, next_lo, (int)n);
+        }
+        const bool blank = S.has_blank != 0;
+        const uint64_t* tabw = reinterpret_cast<const uint64_t*>(S.tabm);
+        const uint64_t* digw = reinterpret_cast<const uint64_t*>(S.digm);
+        if (tid == 0 && S.carry.open) {
+            S.runs[0] = (uint16_t)(0x8000 | r0);  // the carried query continues (or ends) at row r0
+            S.n_runs = 1;
         }
         __syncthreads();
-        // ---- phase D: one warp per run: extent, top bit-score group, top rows + record header to HBM ------------------
+        // ---- phase D: one thread per row ---------------------------------------------------------------------------
+        for (int rb = 0; rb < n_complete; rb += kTileThreads) {
+            const int r = rb + tid;
+            const bool active = r >= r0 && r < n_complete;
+            bool head = false;
+            if (active) {
+                const int s = S.row_s[r];
+                const int e = blank ? row_end_search(S, s, last_nl) : (int)S.row_s[r + 1] - 1;
+                int64_t bits;
+                int ql;
+                if (!parse_row_lean(win, S.tabm, S.digm, s, e, bits, ql)) {
+                    const LightRow lr = parse_row_masked(win, tabw, digw, s, e);
+                    if (lr.err) report(p.ctr, lr.err, lo + s);
+                    bits = lr.bits;
+                    ql = lr.q_len;
+                }
+                if (r == 0) {
+                    head = has_begin;  // first row of the text; else: predecessor not in the window
+                    if (!head) push_defer(p, lo + s, 1);  // the block path decides whether it starts a query
+                } else
+                    head = !same_qid_lean(win, S.tabm, s, ql, S.row_s[r - 1]);
+                const int32_t b32 = (int32_t)bits;
+                S.flags[r] = ((int64_t)b32 != bits) ? 2 : 0;
+                S.bits[r] = b32;
+                if (head && r < r_hi) {
+                    const int i = atomicAdd(&S.n_runs, 1);
+                    S.runs[i] = (uint16_t)r;
+                }
+            }
+            const unsigned hb = __ballot_sync(FULL, head);
+            if (lane == 0 && (r & ~31) < n_complete) S.headw[r >> 5] = hb;
+        }
+        __syncthreads();
+        // ---- phases E / K / F, kRunBatch runs at a time -------------------------------------------------------------
         const int n_runs = S.n_runs;
-        WarpScratch& ws = S.ws[warp];
-        while (true) {
-            int ri = 0;
-            if (lane == 0) ri = atomicAdd(&S.next_run, 1);
-            ri = __shfl_sync(0xffffffffu, ri, 0);
-            if (ri >= n_runs) break;
-            const int h = S.runs[ri];
-            // end of the run = next head among the complete rows
-            int e = -1;
-            for (int b = h + 1; b < ncomplete; b += 32) {
-                int r = b + lane;
-                bool hd = r < ncomplete && (S.flags[r] & 1);
-                unsigned bal = __ballot_sync(0xffffffffu, hd);
-                if (bal) {
-                    e = b + __ffs(bal) - 1;
-                    break;
-                }
+        const bool closes = covers_eof && p.final_chunk;  // the end of this window ends the open query
+        for (int b0 = 0; b0 < n_runs; b0 += kRunBatch) {
+            const int nb = n_runs - b0 < kRunBatch ? n_runs - b0 : kRunBatch;
+            if (tid == 0) {
+                S.next_run = 0;
+                S.n_top = 0;
             }
-            const unsigned long long h_abs = lo + W.row_s[h];
-            if (e < 0) {
-                if (p.final_chunk && g.covers_eof && !has_partial)
-                    e = ncomplete;
-                else {
-                    if (lane == 0) push_defer(p, h_abs, 0);
-                    continue;
+            __syncthreads();
+            // ---- phase E: one warp per run ---------------------------------------------------------------------------
+            while (true) {
+                int j = 0;
+                if (lane == 0) j = atomicAdd(&S.next_run, 1);
+                j = __shfl_sync(FULL, j, 0);
+                if (j >= nb) break;
+                const int entry = S.runs[b0 + j];
+                const bool pseudo = (entry & 0x8000) != 0;
+                const int h = entry & 0x7FFF;
+                int e = next_head(S, pseudo ? h : h + 1, n_complete, lane);
+                const bool open = e < 0;
+                if (open) e = n_complete;
+                int mx = INT32_MIN;
+                bool ovf = false;
+                for (int r = h + lane; r < e; r += 32) {
+                    const int b = S.bits[r];
+                    mx = b > mx ? b : mx;
+                    ovf |= (S.flags[r] & 2) != 0;
                 }
-            }
-            // rows of this run that lie in the look-ahead region have not been parsed yet
-            {
-                int f0 = S.first_fwd > h ? S.first_fwd : h;
-                if (f0 > e) f0 = e;  // (first_fwd is INT_MAX when the window has no look-ahead rows)
-                for (int r = f0 + lane; r < e; r += 32) {
-                    const int s = W.row_s[r];
-                    const int re = W.row_e[r + eskip];
-                    int64_t bits;
-                    int ql;
-                    if (!parse_row_fast(W.win, tabw32, digw32, s, re, bits, ql)) {
-                        LightRow lr = parse_row_masked(W.win, tabw, digw, s, re);
-                        if (lr.err) report(p.ctr, lr.err, lo + s);
-                        bits = lr.bits;
+                mx = __reduce_max_sync(FULL, mx);
+                ovf = __any_sync(FULL, ovf);
+                int g = 0;
+                for (int b = h; b < e; b += 32) {
+                    const int r = b + lane;
+                    const bool top = r < e && S.bits[r] == mx;
+                    const unsigned bal = __ballot_sync(FULL, top);
+                    const int pos = g + __popc(bal & ((1u << lane) - 1u));
+                    if (top && pos < 32) S.stage[warp][pos] = (uint16_t)r;
+                    g += __popc(bal);
+                }
+                __syncwarp();
+                int t0 = 0;
+                if (g > 32 || ovf)
+                    ovf = true;
+                else if (g > 0) {
+                    if (lane == 0) t0 = atomicAdd(&S.n_top, g);
+                    t0 = __shfl_sync(FULL, t0, 0);
+                    if (t0 + g > kTopCap)
+                        ovf = true;  // the pass's top list is full: block path
+                    else if (lane < g) {
+                        S.top_row[t0 + lane] = S.stage[warp][lane];
+                        S.top_run[t0 + lane] = (uint16_t)j;
                     }
-                    const int32_t b32 = (int32_t)bits;
-                    if ((int64_t)b32 != bits) S.flags[r] |= 2;
-                    row_bits[r] = b32;
+                }
+                if (lane == 0) {
+                    S.run_h[j] = (uint16_t)h;
+                    S.run_e[j] = (uint16_t)e;
+                    S.run_mx[j] = mx;
+                    S.run_t0[j] = (uint16_t)t0;
+                    S.run_gpart[j] = (uint16_t)(ovf ? 0 : g);
+                    S.run_kind[j] = (pseudo ? RK_PSEUDO : 0) | (open ? RK_OPEN : 0) | (ovf ? RK_OVF : 0);
+                    if (!pseudo) {
+                        const int s = S.row_s[h];
+                        const int re = blank ? row_end_search(S, s, last_nl) : (int)S.row_s[h + 1] - 1;
+                        S.run_abs[j] = lo + s;
+                        S.run_qlen[j] = (uint32_t)(next_tab(tabw, s, re) - s);
+                    }
                 }
                 __syncwarp();
             }
-            // max bit score of the run
-            int mx = INT32_MIN;
-            bool ovf = false;
-            for (int r = h + lane; r < e; r += 32) {
-                int b = row_bits[r];
-                mx = b > mx ? b : mx;
-                ovf |= (S.flags[r] & 2) != 0;
-            }
+            __syncthreads();
+            // ---- phase K: warp 0 decides what happens to every run of the pass and reserves the output -----------------
+            if (warp == 0) {
+                // runs that touch the carry (at most two per window): the continuation of the carried query (always entry 0
+                // of the first pass) and the query that is still open at the end of the window
+                int j_open = -1;
+                for (int base = 0; base < nb; base += 32) {
+                    const int j = base + lane;
+                    const uint8_t kind = j < nb ? S.run_kind[j] : (uint8_t)0;
+                    const unsigned bal = __ballot_sync(FULL, (kind & RK_OPEN) && !(kind & RK_PSEUDO));
+                    if (bal) j_open = base + __ffs(bal) - 1;
+                }
+                if (lane == 0) {
+                    for (int pass = 0; pass < 2; pass++) {
+                        {
+                            const int j = pass == 0 ? 0 : j_open;
+                            if (j < 0) continue;
+                            uint8_t kind = S.run_kind[j];
+                            const bool pseudo = (kind & RK_PSEUDO) != 0, open = (kind & RK_OPEN) != 0;
+                            if (pass == 0 ? !pseudo : (pseudo || !open)) continue;
+                            const int rows_t = (int)S.run_e[j] - (int)S.run_h[j];
+                            CarryRun& C = S.carry;
+                            if (pseudo) {
+                                int g_eff = 0, dst = 0;
+                                if (kind & RK_OVF) C.deferred = 1;
+                                if (rows_t > 0 && !C.deferred) {
+                                    const int mxt = S.run_mx[j];
+                                    if (mxt > C.mx) {
+                                        C.mx = mxt;
+                                        C.g = 0;
+                                        g_eff = S.run_gpart[j];
+                                    } else if (mxt == C.mx)
+                                        g_eff = S.run_gpart[j];
+                                    if (C.g + g_eff > kCarryTop) {
+                                        C.deferred = 1;
+                                        g_eff = 0;
+                                    }
+                                }
+                                if (C.deferred) g_eff = 0;
+                                const bool ends = !open || closes;
+                                kind &= ~(RK_EMIT | RK_DEFER);
+                                if (ends) {
+                                    kind &= ~RK_OPEN;
+                                    kind |= C.deferred ? RK_DEFER : RK_EMIT;
+                                    S.run_abs[j] = C.head_abs;
+                                    S.run_qlen[j] = C.qlen;
+                                    S.run_nrows[j] = C.nrows + (uint32_t)rows_t;
+                                    S.run_mx[j] = C.mx;
+                                    S.run_gtot[j] = (uint16_t)(C.g + g_eff);
+                                    dst = C.g;
+                                    C.open = 0;
+                                } else if (covers_eof) {
+                                    // the input continues in the next chunk: the whole query is carried over by the host
+                                    atomicMin(&p.ctr->tail_start, C.head_abs);
+                                    kind &= ~RK_OPEN;
+                                    g_eff = 0;
+                                    C.open = 0;
+                                } else {
+                                    C.nrows += (uint32_t)rows_t;
+                                    dst = -1 - C.g;
+                                    C.g += g_eff;
+                                }
+                                S.run_gpart[j] = (uint16_t)g_eff;
+                                S.run_dst[j] = dst;
+                            } else {
+                                // a query that starts in this window and does not end in it
+                                if (closes) {
+                                    kind &= ~RK_OPEN;  // ... except at the end of the input: an ordinary finished query
+                                } else if (covers_eof) {
+                                    atomicMin(&p.ctr->tail_start, S.run_abs[j]);
+                                    S.run_gpart[j] = 0;
+                                } else {
+                                    C.open = 1;
+                                    C.deferred = (kind & RK_OVF) ? 1 : 0;
+                                    C.head_abs = S.run_abs[j];
+                                    C.qlen = S.run_qlen[j];
+                                    C.nrows = (uint32_t)rows_t;
+                                    C.mx = S.run_mx[j];
+                                    C.g = C.deferred ? 0 : (int)S.run_gpart[j];
+                                    S.run_dst[j] = -1;
+                                }
+                            }
+                            S.run_kind[j] = kind;
+                        }
+                    }
+                }
+                __syncwarp();
+                // ordinary runs + totals: packed (records << 16 | slots) prefix sums over the pass
+                uint32_t tot = 0;
+                for (int base = 0; base < nb; base += 32) {
+                    const int j = base + lane;
+                    uint32_t need = 0;
+                    if (j < nb) {
+                        uint8_t kind = S.run_kind[j];
+                        if (!(kind & (RK_PSEUDO | RK_OPEN))) {
+                            // finished inside this window
+                            kind |= (kind & RK_OVF) ? RK_DEFER : RK_EMIT;
+                            S.run_nrows[j] = (uint32_t)((int)S.run_e[j] - (int)S.run_h[j]);
+                            S.run_gtot[j] = S.run_gpart[j];
+                            S.run_dst[j] = 0;
+                            S.run_kind[j] = kind;
+                        }
+                        if (kind & RK_EMIT) need = (1u << 16) | (uint32_t)S.run_gtot[j];
+                        if (kind & RK_DEFER) push_defer(p, S.run_abs[j], 0);
+                    }
+                    uint32_t inc = need;
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                int o = __shfl_xor_sync(0xffffffffu, mx, d);
-                mx = o > mx ? o : mx;
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const uint32_t t = __shfl_up_sync(FULL, inc, d);
+                        if (lane >= d) inc += t;
+                    }
+                    if (j < nb) {
+                        const uint32_t ex = tot + inc - need;
+                        S.run_rec[j] = (uint16_t)(ex >> 16);
+                        S.run_slot[j] = ex & 0xFFFFu;
+                    }
+                    tot += __shfl_sync(FULL, inc, 31);
+                }
+                const uint32_t n_rec = tot >> 16, n_slot = tot & 0xFFFFu;
+                unsigned long long rs = 0;
+                if (lane == 0 && n_rec) rs = atomicAdd(&p.ctr->rec_slots, ((unsigned long long)n_rec << 32) | (unsigned long long)n_slot);
+                rs = __shfl_sync(FULL, rs, 0);
+                const uint32_t rec_base = (uint32_t)(rs >> 32), slot_base = (uint32_t)rs;
+                const bool ok = (unsigned long long)rec_base + n_rec <= p.rec_cap && (unsigned long long)slot_base + n_slot <= p.slot_cap;
+                if (lane == 0) {
+                    S.rec_base = rec_base;
+                    S.slot_base = slot_base;
+                    S.pass_ok = ok ? 1 : 0;
+                    if (!ok) p.ctr->cap_overflow = 1;
+                }
+                // a carried query that ends here: its earlier top rows go in front of this window's
+                if (b0 == 0 && ok && (S.run_kind[0] & RK_PSEUDO) && (S.run_kind[0] & RK_EMIT)) {
+                    const int n_old = S.run_dst[0];
+                    if (lane < n_old) p.toprows[slot_base + S.run_slot[0] + lane] = S.carry.tops[lane];
+                }
             }
-            ovf = __any_sync(0xffffffffu, ovf);
-            // rows of the top group, in file order
-            int gcount = 0;
-            for (int b = h; b < e; b += 32) {
-                int r = b + lane;
-                bool top = r < e && row_bits[r] == mx;
-                unsigned bal = __ballot_sync(0xffffffffu, top);
-                int pos = gcount + __popc(bal & ((1u << lane) - 1u));
-                if (top && pos < 32) ws.idx[pos] = (uint16_t)r;
-                gcount += __popc(bal);
+            __syncthreads();
+            // ---- phase F: top rows (one thread each) and record headers (one thread per finished query) --------------
+            const int n_top = S.n_top < kTopCap ? S.n_top : kTopCap;
+            const bool ok = S.pass_ok != 0;
+            for (int t = tid; t < n_top; t += kTileThreads) {
+                const int j = S.top_run[t];
+                const int k = t - (int)S.run_t0[j];
+                const uint8_t kind = S.run_kind[j];
+                if (k >= (int)S.run_gpart[j] || !(kind & (RK_EMIT | RK_OPEN))) continue;
+                const int r = S.top_row[t];
+                const int s = S.row_s[r];
+                const int e = blank ? row_end_search(S, s, last_nl) : (int)S.row_s[r + 1] - 1;
+                TopRowRaw tr;
+                const uint32_t err = split_top_row(win, tabw, s, e, lo, tr);
+                if (err) {
+                    report(p.ctr, err, lo + s);
+                    continue;
+                }
+                const int dst = S.run_dst[j];
+                if (kind & RK_EMIT) {
+                    if (ok) p.toprows[S.slot_base + S.run_slot[j] + (uint32_t)(dst + k)] = tr;
+                } else
+                    S.carry.tops[-1 - dst + k] = tr;
             }
-            __syncwarp();
-            if (ovf || gcount > 32) {
-                if (lane == 0) push_defer(p, h_abs, 0);
-                continue;
-            }
-            // reserve one record + gcount top-row slots with a single packed atomic; its latency is covered by the field
-            // split / number parse of the top rows (lanes = top rows), which does not need the result
-            unsigned long long rs = 0;
-            if (lane == 0) rs = atomicAdd(&p.ctr->rec_slots, (1ull << 32) | (unsigned long long)gcount);
-            TopRowRaw tr;
-            uint32_t err = 0;
-            if (lane < gcount) {
-                const int r = ws.idx[lane];
-                const int s = W.row_s[r];
-                err = split_top_row(W.win, tabw, s, W.row_e[r + eskip], lo, tr);
-                if (err) report(p.ctr, err, lo + s);
-            }
-            const int qlen = next_tab(tabw, W.row_s[h], W.row_e[h + eskip]) - (int)W.row_s[h];
-            rs = __shfl_sync(0xffffffffu, rs, 0);
-            const unsigned rec_i = (unsigned)(rs >> 32), slot = (unsigned)rs;
-            if (rec_i >= p.rec_cap || slot + (unsigned)gcount > p.slot_cap) {
-                if (lane == 0) p.ctr->cap_overflow = 1;
-                continue;
-            }
-            if (lane < gcount && !err) p.toprows[slot + lane] = tr;
-            if (lane == 0) {
+            for (int j = tid; j < nb; j += kTileThreads) {
+                if (!(S.run_kind[j] & RK_EMIT) || !ok) continue;
                 blu_record rec;
-                rec.query_off = h_abs;
-                rec.query_len = (uint32_t)qlen;
-                rec.n_rows = (uint32_t)(e - h);
+                rec.query_off = S.run_abs[j];
+                rec.query_len = S.run_qlen[j];
+                rec.n_rows = S.run_nrows[j];
                 rec.keep_mask = 0;
                 rec.perc_identity = 0.0;
-                rec.bit_score = (int64_t)mx;
+                rec.bit_score = (int64_t)S.run_mx[j];
                 rec.ref_lineage = 0;
-                rec.slot_base = slot;
+                rec.slot_base = S.slot_base + S.run_slot[j];
                 rec.n_beans = 0;
-                rec.n_accessions = (uint32_t)gcount;  // size of the top group until the consensus kernel overwrites it
-                rec.status = 2;                       // waiting for the consensus kernel
+                rec.n_accessions = (uint32_t)S.run_gtot[j];  // size of the top group until the consensus kernel overwrites it
+                rec.status = 2;                              // waiting for the consensus kernel
                 rec.single_match = 0;
                 rec.mutated = 0;
                 rec.reached_pos = 0;
                 rec.allowed_pos = -1;
                 rec.bean_level = 0;
                 rec.pad[0] = rec.pad[1] = 0;
-                p.records[rec_i] = rec;
+                p.records[S.rec_base + S.run_rec[j]] = rec;
             }
+            __syncthreads();
         }
+        // ---- where next? -----------------------------------------------------------------------------------------------
+        // The CTA is done when the window reached the end of the text, when a query that belongs to the next segment
+        // started in it, or when nothing is open and the segment is exhausted.
+        bool done = covers_eof;
+        if (!done && r_hi < n_complete) done = next_head(S, r_hi, n_complete, lane) >= 0;
+        const bool open_now = S.carry.open != 0;
+        if (!done && !open_now && lo + (unsigned long long)(last_nl + 1) >= seg_hi) done = true;
+        if (!done && !may_continue) {
+            // no complete new row in a whole window: a row longer than this kernel stages
+            if (tid == 0) report(p.ctr, DE_CARRY_TOO_BIG, own_from);
+            done = true;
+        }
+        if (done) {
+            if (may_continue) {
+                // a copy into the other buffer is in flight: it must land before the CTA exits
+                uint32_t& ph = (buf ^ 1) ? ph1 : ph0;
+                while (!mbar_try_wait(&S.mbar[buf ^ 1], ph)) {
+                }
+            }
+            return;
+        }
+        own_from = lo + (unsigned long long)(last_nl + 1);
+        lo = next_lo;
+        buf ^= 1;
+        __syncthreads();  // everyone has read the carry / window state of this step
     }
 }
 
@@ -1254,7 +1668,7 @@ __global__ void __launch_bounds__(256) dup_kernel(const DupParams p) {
 // launchers
 // ---------------------------------------------------------------------------------------------------------------
 cudaError_t kernels_set_attributes() {
-    cudaError_t e = cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem));
+    cudaError_t e = cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamSmem));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(longrun_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LongSmem));
 }
@@ -1262,11 +1676,11 @@ cudaError_t kernels_set_attributes() {
 int tile_kernel_grid(int device) {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    return kTileCtasPerSm * sms;  // resident CTAs per SM (~70 KB of shared memory each)
+    return kTileCtasPerSm * sms;  // one streaming CTA per resident slot
 }
 
 cudaError_t launch_tile_kernel(const RunParams& p, int grid, cudaStream_t s) {
-    tile_kernel<<<grid, kTileThreads, sizeof(TileSmem), s>>>(p);
+    tile_kernel<<<grid, kTileThreads, sizeof(StreamSmem), s>>>(p);
     return cudaGetLastError();
 }
 

@@ -70,25 +70,22 @@ struct DupParams {
     Counters* ctr;
 };
 
-// Tile geometry of the fused kernel
+// Geometry of the streaming tile kernel: every CTA walks one contiguous segment of the text in
+// kTile-byte steps (double-buffered TMA), carrying the unfinished query from one step to the next.
 #ifndef BLU_TILE_BYTES
-#define BLU_TILE_BYTES 49152
-#endif
-#ifndef BLU_FWD_BYTES
-#define BLU_FWD_BYTES 10240
+#define BLU_TILE_BYTES 32768
 #endif
 #ifndef BLU_TILE_CTAS
 #define BLU_TILE_CTAS 2
 #endif
 #ifndef BLU_TILE_THREADS
-#define BLU_TILE_THREADS 384
+#define BLU_TILE_THREADS 512
 #endif
-constexpr int kTile = BLU_TILE_BYTES;   // bytes owned by one tile
-constexpr int kBack = 1024;             // look-behind so the tile's first row can be compared with its predecessor
-constexpr int kFwd = BLU_FWD_BYTES;     // look-ahead so a query that starts in the tile can finish in the window
-constexpr int kWin = kBack + kTile + kFwd;
+constexpr int kTile = BLU_TILE_BYTES;   // bytes staged per step
+constexpr int kBack = 1024;             // look-behind of a segment's first window (predecessor of its first row)
 constexpr int kTileThreads = BLU_TILE_THREADS;
 constexpr int kTileCtasPerSm = BLU_TILE_CTAS;
+constexpr int kWin = 60416;             // window of the block path (long-run kernel)
 
 int tile_kernel_grid(int device);
 cudaError_t launch_tile_kernel(const RunParams& p, int grid, cudaStream_t s);

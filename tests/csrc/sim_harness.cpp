@@ -55,7 +55,7 @@ extern "C" int blu_sim_run(const int64_t* taxids, const uint64_t* off, const cha
             int qlen;
         };
         std::vector<R> rows;
-        long n_fast = 0;
+        long n_fast = 0, n_lean = 0;
         // byte-class bitmasks exactly as the row scan of the kernels publishes them (bit i = byte i)
         std::vector<uint64_t> tabw(nbytes / 64 + 3, 0), digw(nbytes / 64 + 3, 0);
         for (uint64_t i = 0; i < nbytes; i++) {
@@ -85,6 +85,19 @@ extern "C" int blu_sim_run(const int64_t* taxids, const uint64_t* off, const cha
                         }
                     }
                 }
+                {
+                    // same contract for the streaming kernel's lean parser
+                    int64_t fb = 0;
+                    int fq = 0;
+                    if (parse_row_lean(tx, reinterpret_cast<const uint32_t*>(tabw.data()), reinterpret_cast<const uint32_t*>(digw.data()), (int)p, (int)e,
+                                       fb, fq)) {
+                        n_lean++;
+                        if (lr.err || fb != lr.bits || fq != lr.q_len) {
+                            snprintf(err, errlen, "lean row parser disagrees with the full parser at byte %llu", (unsigned long long)p);
+                            return BLU_ERR_INTERNAL;
+                        }
+                    }
+                }
                 LightRow l2 = light_parse_row(tx + p, (int)(e - p));  // byte-wise variant must agree
                 if ((lr.err != 0) != (l2.err != 0) || (!lr.err && (lr.bits != l2.bits || lr.q_len != l2.q_len))) {
                     snprintf(err, errlen, "masked and byte-wise row parsers disagree at byte %llu", (unsigned long long)p);
@@ -99,7 +112,7 @@ extern "C" int blu_sim_run(const int64_t* taxids, const uint64_t* off, const cha
             p = e + 1;
         }
         if (rows.empty()) throw DataErr("no rows");
-        if (getenv("BLU_SIM_VERBOSE")) fprintf(stderr, "sim: %zu rows, %ld through the fast row parser\n", rows.size(), n_fast);
+        if (getenv("BLU_SIM_VERBOSE")) fprintf(stderr, "sim: %zu rows, %ld through the fast row parser, %ld through the lean one\n", rows.size(), n_fast, n_lean);
         std::vector<blu_record> recs;
         std::vector<blu_bean> beans;
         std::vector<blu_acc> accs;
@@ -108,9 +121,17 @@ extern "C" int blu_sim_run(const int64_t* taxids, const uint64_t* off, const cha
         std::vector<uint16_t> scratch;
         for (size_t h = 0; h < rows.size();) {
             size_t e = h + 1;
-            while (e < rows.size() && same_first_field(tx, tabw.data(), (int)rows[e - 1].s, (int)rows[e - 1].s + rows[e - 1].len, (int)rows[e].s,
-                                                       (int)rows[e].s + rows[e].len))
+            while (e < rows.size()) {
+                const bool same = same_first_field(tx, tabw.data(), (int)rows[e - 1].s, (int)rows[e - 1].s + rows[e - 1].len, (int)rows[e].s,
+                                                   (int)rows[e].s + rows[e].len);
+                // the streaming kernel's variant (knows the id length of the current row) must agree
+                if (same_qid_lean(tx, reinterpret_cast<const uint32_t*>(tabw.data()), (int)rows[e].s, rows[e].qlen, (int)rows[e - 1].s) != same) {
+                    snprintf(err, errlen, "lean query-id compare disagrees at byte %llu", (unsigned long long)rows[e].s);
+                    return BLU_ERR_INTERNAL;
+                }
+                if (!same) break;
                 e++;
+            }
             if (!seen.insert(std::string((const char*)tx + rows[h].s, rows[h].qlen)).second) {
                 snprintf(err, errlen, "non-contiguous query");
                 return BLU_ERR_UNSUPPORTED;
