@@ -590,64 +590,113 @@ BLU_HD uint64_t bits64_at(const uint32_t* w, int pos) {
     return (uint64_t)blu_funnel_r(a, b, sh) | ((uint64_t)blu_funnel_r(b, c, sh) << 32);
 }
 
+// n ASCII digits (0 <= n <= 8) starting at win[pos] -> value, without a per-digit loop: the eight bytes are shifted so
+// that the number is right-aligned in a 64-bit little-endian word (leading bytes zero), then each half is folded with
+// two multiply-adds (digit pairs, then pairs of pairs).  The caller has validated that the bytes are digits.
+BLU_HD uint32_t swar4(uint32_t x) {  // bytes d0 d1 d2 d3 (d0 = lowest byte, most significant digit) -> d0 d1 d2 d3 as a number
+    x &= 0x0F0F0F0Fu;
+    x = x * 10u + (x >> 8);
+    x &= 0x00FF00FFu;
+    return (x & 0xFFFFu) * 100u + (x >> 16);
+}
+BLU_HD uint32_t load_u32_unaligned(const uint8_t* win, int pos);
+BLU_HD uint32_t swar_digits(const uint8_t* win, int pos, int n) {
+    if (n <= 0) return 0u;
+    const uint64_t v = (((uint64_t)load_u32_unaligned(win, pos + 4) << 32) | (uint64_t)load_u32_unaligned(win, pos)) << (8 * (8 - n));
+    return swar4((uint32_t)v) * 10000u + swar4((uint32_t)(v >> 32));
+}
+
+// positions of the first two tabs of the row at s (qseqid / saccver ends), relative to s; both must lie in the first 64 bytes
+BLU_HD bool first_two_tabs(const uint32_t* tabw32, int s, int& p1, int& p2) {
+    const int wi = s >> 5;
+    const uint32_t sh = (uint32_t)s & 31u;
+    const uint32_t w0 = tabw32[wi], w1 = tabw32[wi + 1];
+    const uint32_t t0 = blu_funnel_r(w0, w1, sh);
+    const uint32_t t0b = t0 & (t0 - 1u);
+    if (t0b) {  // the common case: both inside the first 32 bytes
+        p1 = blu_ffs32(t0);
+        p2 = blu_ffs32(t0b);
+        return true;
+    }
+    const uint32_t t1 = blu_funnel_r(w1, tabw32[wi + 2], sh);
+    if (t0) {
+        if (!t1) return false;
+        p1 = blu_ffs32(t0);
+        p2 = 32 + blu_ffs32(t1);
+        return true;
+    }
+    const uint32_t t1b = t1 & (t1 - 1u);
+    if (!t1b) return false;
+    p1 = 32 + blu_ffs32(t1);
+    p2 = 32 + blu_ffs32(t1b);
+    return true;
+}
+
 BLU_HD bool parse_row_lean(const uint8_t* win, const uint32_t* tabw32, const uint32_t* digw32, int s, int e, int64_t& bits, int& q_len) {
-    // first two tabs: qseqid and saccver end within the first 64 bytes of the row
-    uint64_t th = bits64_at(tabw32, s);
-    if (th == 0) return false;
-    const int p1 = blu_ctz64(th);
-    th &= th - 1;
-    if (th == 0) return false;
-    const int p2 = blu_ctz64(th);
+    int p1, p2;
+    if (e < 32 || !first_two_tabs(tabw32, s, p1, p2)) return false;
     const int a = s + p2 + 1;  // first byte of staxid
     const int m = e - a;       // bytes of the numeric tail
     if (p1 < 1 || p2 - p1 < 2 || m < 21 || m > 64) return false;
-    const uint64_t mm = m == 64 ? ~0ull : ((1ull << m) - 1ull);
-    const uint64_t tt = bits64_at(tabw32, a) & mm;
-    const uint64_t dt = bits64_at(digw32, a) & mm;
-    if (blu_popc64(tt) != 10) return false;
+    // the tail through two head-aligned words (bytes a.., a+32..) and one end-aligned word (bytes e-32..e-1)
+    const int ai = a >> 5;
+    const uint32_t ash = (uint32_t)a & 31u;
+    const uint32_t x0 = tabw32[ai], x1 = tabw32[ai + 1], x2 = tabw32[ai + 2];
+    const uint32_t y0 = digw32[ai], y1 = digw32[ai + 1], y2 = digw32[ai + 2];
+    const uint32_t m0 = m >= 32 ? 0xFFFFFFFFu : ((1u << m) - 1u);
+    const uint32_t m1 = m >= 64 ? 0xFFFFFFFFu : (m > 32 ? ((1u << (m - 32)) - 1u) : 0u);
+    const uint32_t ta0 = blu_funnel_r(x0, x1, ash) & m0, ta1 = blu_funnel_r(x1, x2, ash) & m1;
+    const uint32_t oa0 = ~(blu_funnel_r(y0, y1, ash) | ta0) & m0, oa1 = ~(blu_funnel_r(y1, y2, ash) | ta1) & m1;  // neither digit nor tab
+    if (blu_popc32(ta0) + blu_popc32(ta1) != 10) return false;
     // no empty field: no two adjacent tabs, no tab at either end of the tail
-    if ((tt & (tt << 1)) | (tt & 1ull) | (tt >> (m - 1))) return false;
-    const int q3 = blu_ctz64(tt);                   // end of staxid
-    const int q4 = blu_ctz64(tt & (tt - 1));        // end of pident
-    const int q12 = 63 - blu_clz64(tt);             // tab in front of bitscore
-    const int q11 = 63 - blu_clz64(tt ^ (1ull << q12));  // tab in front of evalue
+    const uint32_t last = m > 32 ? (ta1 >> (m - 33)) : (ta0 >> (m - 1));
+    if ((ta0 & (ta0 << 1)) | (ta1 & ((ta1 << 1) | (ta0 >> 31))) | (ta0 & 1u) | (last & 1u)) return false;
+    // staxid / pident end inside the first 32 bytes of the tail
+    const uint32_t ta0b = ta0 & (ta0 - 1u);
+    if (!ta0b) return false;
+    const int q3 = blu_ffs32(ta0), q4 = blu_ffs32(ta0b);
+    // evalue / bitscore start inside the last 32 bytes of the row
+    const int eb = e - 32;
+    const uint32_t me = m >= 32 ? 0xFFFFFFFFu : (0xFFFFFFFFu << (32 - m));  // bytes of the end-aligned word that belong to the tail
+    const uint32_t te = bits_at(tabw32, eb) & me;
+    const uint32_t oe_all = ~(bits_at(digw32, eb) | te) & me;
+    if (!te) return false;
+    const int q12e = 31 - blu_clz32(te);
+    const uint32_t te2 = te ^ (1u << q12e);
+    if (!te2) return false;
+    const int q11e = 31 - blu_clz32(te2);
+    const int q11 = m - 32 + q11e;  // tab in front of evalue, tail coordinates
     // integer columns <= 18 digits: staxid directly, length..send (7 fields, 6 tabs) through their total span
     if (q3 > 18 || q11 - q4 - 1 > 30) return false;
-    const uint64_t o = ~(dt | tt) & mm;  // bytes that are neither digit nor tab
-    const uint64_t below_q4 = (1ull << q4) - 1ull;
-    const uint64_t in_pid = below_q4 & ~((2ull << q3) - 1ull);
-    const uint64_t from_ev = ~((2ull << q11) - 1ull);  // evalue, its tab, bitscore
-    if (o & ~(in_pid | from_ev)) return false;
+    // non-digit bytes may only sit in pident and in evalue / bitscore: compare the counts
+    const uint32_t op = oa0 & ((1u << q4) - 1u) & ~((2u << q3) - 1u);
+    const uint32_t otail = oe_all & ~((2u << q11e) - 1u);
+    if (blu_popc32(oa0) + blu_popc32(oa1) != blu_popc32(op) + blu_popc32(otail)) return false;
     // pident: digits with at most one '.', at least one digit
-    const uint64_t op = o & below_q4;
     if (op) {
-        if (op & (op - 1)) return false;
-        if (q4 - q3 - 1 < 2 || win[a + blu_ctz64(op)] != '.') return false;
+        if (op & (op - 1u)) return false;
+        if (q4 - q3 - 1 < 2 || win[a + blu_ffs32(op)] != '.') return false;
     }
     // evalue: one of the common float shapes, else the DFA
-    const int l_ev = q12 - q11 - 1;
-    if (l_ev > 32) return false;
+    const int l_ev = q12e - q11e - 1;
     {
-        const uint32_t oe = (uint32_t)(o >> (q11 + 1)) & (l_ev == 32 ? 0xFFFFFFFFu : ((1u << l_ev) - 1u));
-        if (oe && !float_shape_ok(win + a + q11 + 1, l_ev, oe) && !check_float(win + a + q11 + 1, l_ev)) return false;
+        const uint32_t oe = (oe_all >> (q11e + 1)) & ((1u << l_ev) - 1u);
+        if (oe && !float_shape_ok(win + eb + q11e + 1, l_ev, oe) && !check_float(win + eb + q11e + 1, l_ev)) return false;
     }
-    // bit score: digits[.digits], <= 15 digits in total (trunc(value) is then exactly the integer part), <= 9 of them
-    // in front of the point (32-bit arithmetic)
-    const int l_bits = m - q12 - 1;
+    // bit score: digits[.digits], <= 15 digits in total (trunc(value) is then exactly the integer part), <= 8 of them
+    // in front of the point
+    const int l_bits = 31 - q12e;
     if (l_bits > 16) return false;
-    const uint32_t ob = (uint32_t)(o >> (q12 + 1));
+    const uint32_t ob = q12e < 31 ? (oe_all >> (q12e + 1)) : 0u;
     int n_int = l_bits;
     if (ob) {
-        if (ob & (ob - 1)) return false;
+        if (ob & (ob - 1u)) return false;
         n_int = blu_ffs32(ob);
-        if (l_bits < 2 || win[a + q12 + 1 + n_int] != '.') return false;
+        if (l_bits < 2 || win[eb + q12e + 1 + n_int] != '.') return false;
     } else if (l_bits > 15)
         return false;
-    if (n_int > 9) return false;
-    const uint8_t* b = win + a + q12 + 1;
-    uint32_t v = 0;
-    for (int i = 0; i < n_int; i++) v = v * 10u + (uint32_t)(b[i] - '0');
-    bits = (int64_t)v;
+    if (n_int > 8) return false;
+    bits = (int64_t)swar_digits(win, eb + q12e + 1, n_int);
     q_len = p1;
     return true;
 }
@@ -807,6 +856,48 @@ BLU_HD uint32_t split_top_row(const uint8_t* win, const uint64_t* tabw, int s, i
     }
     if (!parse_u32_short(win + t3 + 1, t4 - t3 - 1, out.alnlen) && !parse_i64(win + t3 + 1, t4 - t3 - 1, out.alnlen)) return DE_BAD_NUMBER;
     return DE_NONE;
+}
+
+// The streaming kernel's top-row splitter: same result as split_top_row() for the common shapes -- saccver within the
+// first 64 bytes, staxid / length of at most 8 digits, pident `ddd[.ddd]` with at most 9 digits -- computed from two
+// mask words and SWAR digit folds (no per-byte loops, short dependency chain); anything else goes through
+// split_top_row().
+BLU_HD uint32_t split_top_row_lean(const uint8_t* win, const uint32_t* tabw32, const uint32_t* digw32, int s, int e, uint64_t lo, TopRowRaw& out) {
+    int p1, p2;
+    if (first_two_tabs(tabw32, s, p1, p2)) {
+        const int a = s + p2 + 1;
+        const uint32_t ta = bits_at(tabw32, a), da = bits_at(digw32, a);
+        const uint32_t tb = ta & (ta - 1u), tc = tb & (tb - 1u);
+        if (tc) {
+            const int q3 = blu_ffs32(ta), q4 = blu_ffs32(tb), q5 = blu_ffs32(tc);
+            const int lp = q4 - q3 - 1, ll = q5 - q4 - 1;
+            const uint32_t nd = ~da;
+            const uint32_t o_tax = nd & ((1u << q3) - 1u);
+            const uint32_t o_pid = (nd >> (q3 + 1)) & ((1u << lp) - 1u);
+            const uint32_t o_len = (nd >> (q4 + 1)) & ((1u << ll) - 1u);
+            int ni = lp, nf = 0;
+            bool ok = a + q5 < e && p1 >= 1 && p2 - p1 >= 2 && q3 >= 1 && q3 <= 8 && ll >= 1 && ll <= 8 && lp >= 1 && (o_tax | o_len) == 0u;
+            if (o_pid) {
+                ni = blu_ffs32(o_pid);
+                nf = lp - ni - 1;
+                ok = ok && !(o_pid & (o_pid - 1u)) && win[a + q3 + 1 + ni] == '.';
+            }
+            ok = ok && ni <= 8 && nf <= 8 && ni + nf >= 1 && ni + nf <= 9;
+            if (ok) {
+                out.acc_off = lo + (uint64_t)(s + p1 + 1);
+                out.acc_len = (uint32_t)(p2 - p1 - 1);
+                out.pad = 0;
+                out.taxid = (int64_t)swar_digits(win, a, q3);
+                out.alnlen = (int64_t)swar_digits(win, a + q4 + 1, ll);
+                uint32_t p10 = 1u;
+                for (int i = 0; i < nf; i++) p10 *= 10u;
+                const uint32_t mant = swar_digits(win, a + q3 + 1, ni) * p10 + swar_digits(win, a + q3 + 2 + ni, nf);
+                out.pident = nf > 0 ? (double)mant / kPow10[nf] : (double)mant;
+                return DE_NONE;
+            }
+        }
+    }
+    return split_top_row(win, reinterpret_cast<const uint64_t*>(tabw32), s, e, lo, out);
 }
 
 // the join: taxid -> lineage (mod.rs:72-76); a miss / unparsable lineage in a top group is what makes the reference panic

@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 
 #include <climits>
+#include <cstdio>
 
 #include "blu_kernels.h"
 
@@ -312,38 +313,55 @@ __device__ __forceinline__ void finish_geom(WindowIndex& W, WinGeom& g, bool fin
 // "look-behind" row: it is only there so that the first new row can be compared with its predecessor), so no row
 // and no query ever has to fit a window: the unfinished query is carried in shared memory (row count, best bit
 // score, its top rows so far) from window to window, and a CTA keeps walking past the end of its segment until the
-// query it has open ends.  Phases of one window (all barriers are CTA-wide):
+// query it has open ends.  Phases of one window (separated by CTA-wide barriers):
 //   B  classify   every lane owns 32 bytes: SIMD-in-register byte tests (ASCII fast path) -> newline / tab / digit
-//                 bitmasks (dp4a packing), row-start bits, per-warp row counts
-//   C  index      per-warp compaction of the row starts into row_s[] (two ballots per round), next window's TMA
-//   D  rows       one thread per row: validation + truncated bit score (parse_row_lean, falling back to the full
-//                 grammar), head flag (query id differs from the previous row's)
-//   E  runs       one warp per query run: extent, best bit score, top rows (ballot compaction) -> tile top list
-//   K  reserve    warp 0: merges the carried query, ONE global atomic reserves the records / top-row slots of the
-//                 whole window, prefix sums give every run its place
-//   F  emit       one thread per top row (field split + number parse) and one per finished query (record header)
+//                 bitmasks (dp4a packing); row starts compacted per warp with two ballots per round
+//   D  rows       warp w takes the rows that start in warp w's share of the window, one thread per row: validation +
+//                 truncated bit score (parse_row_lean, falling back to the full grammar), head flag (query id differs
+//                 from the previous row's), global row table
+//   E  runs       one warp per query run (dynamic queue): extent, best bit score, top rows (ballot compaction);
+//                 the warp decides the run's fate (finished / still open / block path), merges it with the carried
+//                 query, and takes its place in the window's output with one shared-memory atomic
+//   F  emit       ONE global atomic reserves the records / top-row slots of the whole window while the top rows are
+//                 split and parsed (one thread each); then top rows and record headers (one thread per finished
+//                 query) go to HBM
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kSWarps = kTileThreads / 32;
-constexpr int kUnits = kTile / 32 + 1;     // 32-byte units of a window (+1: the unit that can hold a virtual final newline)
-constexpr int kSRowCap = kTile / 26 + 8;   // a valid row is >= 26 bytes
-constexpr int kRunBatch = 256;             // runs handled per pass of phases E/K/F
-constexpr int kTopCap = 1024;              // top rows a pass can queue (beyond: block path)
-constexpr int kCarryTop = 32;              // top rows of the open query kept in shared memory (beyond: block path)
+constexpr int kUnits = kTile / 32 + 1;       // 32-byte units of a window (+1: the unit that can hold a virtual final newline)
+constexpr int kUnitsPerWarp = ((kUnits + kSWarps - 1) / kSWarps + 31) & ~31;  // whole 32-lane rounds
+constexpr int kSegCap = kUnitsPerWarp * 2;   // row starts one warp can find (<= 1 per 16 bytes, else malformed)
+constexpr int kSRowCap = kTile / 26 + 8;     // a valid row is >= 26 bytes
+constexpr int kRunBatch = 128;                // runs handled per pass of phases E/F
+constexpr int kTopCap = 512;                  // top rows a pass can queue (beyond: block path)
+constexpr int kRecFlush = 128;                // buffered record headers that trigger a flush (one global atomic)
+constexpr int kRecBuf = kRecFlush + kRunBatch;  // capacity of the record buffer
+constexpr uint32_t kSlotSlab = 1024;          // top-row slots a CTA reserves at a time (one global atomic)
+constexpr int kCarryTop = 32;                 // top rows of the open query kept in shared memory (beyond: block path)
 
 static_assert(kSRowCap < 0x8000, "row indices are 15-bit");
 static_assert(kTile % 32 == 0 && kTile + 128 < 65536, "window offsets are 16-bit");
+static_assert(kSWarps <= 32, "per-warp tables are read by one warp");
 
-enum : uint8_t { RK_EMIT = 1, RK_DEFER = 2, RK_PSEUDO = 4, RK_OPEN = 8, RK_OVF = 16 };
+enum : uint8_t { RK_EMIT = 1, RK_DEFER = 2, RK_PSEUDO = 4, RK_OPEN = 8, RK_NEWCARRY = 16 };
 
 struct CarryRun {
     unsigned long long head_abs;  // offset of the open query's first row
     uint32_t qlen;
     uint32_t nrows;
-    int32_t mx;     // best truncated bit score so far
-    int32_t g;      // top rows so far (kept in tops[])
+    int32_t mx;        // best truncated bit score so far
+    int32_t g;         // top rows so far (kept in tops[])
     int32_t open;
     int32_t deferred;  // the query goes to the block path when it ends (top group too large / bit score beyond int32)
     TopRowRaw tops[kCarryTop];
+};
+
+struct StagedRec {
+    unsigned long long abs;
+    uint32_t qlen, nrows;
+    int32_t mx;
+    uint32_t slot;  // first top-row slot (phase E: relative to the pass; phase F adds the pass's base)
+    uint32_t gtot;
+    uint32_t pad;
 };
 
 struct StreamSmem {
@@ -352,36 +370,33 @@ struct StreamSmem {
     alignas(8) uint32_t tabm[kUnits + 7];
     alignas(8) uint32_t digm[kUnits + 7];
     alignas(8) uint32_t nlm[kUnits + 7];
-    uint32_t stm[kUnits + 7];  // row starts
-    uint16_t row_s[kSRowCap + 2];
+    uint16_t seg[kSWarps][kSegCap];  // row starts found by warp w, in order
+    uint16_t row_s[kSRowCap + 2];    // all row starts of the window (written by phase D)
     int32_t bits[kSRowCap];
-    uint8_t flags[kSRowCap];   // bit1: bit score does not fit int32
-    uint32_t headw[kSRowCap / 32 + 2];
-    uint16_t runs[kSRowCap + 1];  // head rows in arrival order (bit 15: continuation of the carried query)
+    uint8_t flags[kSRowCap];         // bit1: bit score does not fit int32
+    uint32_t headw[(kSRowCap + kTileThreads) / 32 + 2];  // head flags, one bit per row (the row loop writes whole rounds)
+    uint16_t runs[kSRowCap + 1];     // head rows in arrival order (bit 15: continuation of the carried query)
     // one pass of runs
-    unsigned long long run_abs[kRunBatch];
-    uint32_t run_qlen[kRunBatch];
-    uint32_t run_nrows[kRunBatch];
-    int32_t run_mx[kRunBatch];
-    int32_t run_dst[kRunBatch];   // where this window's top rows of the run go: >= 0 offset inside the run's slots, < 0: carry.tops[-1-dst]
-    uint32_t run_slot[kRunBatch];  // first slot of the run, relative to the pass
-    uint16_t run_rec[kRunBatch];   // record of the run, relative to the pass
-    uint16_t run_h[kRunBatch];
-    uint16_t run_e[kRunBatch];
+    int32_t run_dst[kRunBatch];    // where this window's top rows of the run go: >= 0 offset inside the run's slots, < 0: carry tops[-1-dst]
+    uint16_t run_slot[kRunBatch];  // first slot of the run, relative to the pass
     uint16_t run_t0[kRunBatch];
     uint16_t run_gpart[kRunBatch];  // top rows of the run in this window (0 when they are not needed)
-    uint16_t run_gtot[kRunBatch];
     uint8_t run_kind[kRunBatch];
+    StagedRec rec_buf[kRecBuf];  // record headers of finished queries, waiting for the next flush
     uint16_t top_row[kTopCap];
     uint16_t top_run[kTopCap];
     uint16_t stage[kSWarps][32];
-    CarryRun carry;
+    CarryRun carry[2];
     alignas(8) unsigned long long mbar[2];
-    int warp_cnt[kSWarps];
-    int n_starts, last_nl, bad_byte, has_blank, crowded;
-    int n_runs, next_run, n_top;
-    uint32_t rec_base, slot_base;
-    int pass_ok;
+    int warp_cnt[32], warp_first[32], warp_last[32];
+    int bad_byte, has_blank, crowded;
+    int n_runs, next_run, n_top, n_skip, term, new_open;
+    uint32_t pass_need;  // records << 16 | slots of the pass
+    uint32_t rec_base;
+    uint32_t slot_cur, slot_end;  // the CTA's current slab of top-row slots: [slot_cur, slot_end) is free
+    int rec_cnt;                  // record headers in rec_buf
+    int out_ok;                   // 0: an output capacity was exceeded (the host grows the arrays and reruns)
+    int old_tops;  // top rows of the carried query that ends in this pass (they precede the window's own)
 };
 
 static_assert((sizeof(StreamSmem) + 1024) * kTileCtasPerSm <= 227 * 1024, "tile CTAs must fit one SM");
@@ -408,8 +423,7 @@ __device__ __forceinline__ uint32_t pack8(uint32_t a, uint32_t b) { return __dp4
 __device__ __forceinline__ uint32_t pack32(const uint32_t (&f)[8]) {
     const uint32_t b0 = pack8(f[0], f[1]) + (pack8(f[2], f[3]) << 8);  // 128 * 16-bit mask
     const uint32_t b1 = pack8(f[4], f[5]) + (pack8(f[6], f[7]) << 8);
-    const unsigned long long c = (unsigned long long)b0 + ((unsigned long long)b1 << 16);
-    return (uint32_t)(c >> 7);
+    return __funnelshift_r(b0 + (b1 << 16), b1 >> 16, 7);
 }
 
 // Exact byte-wise classification of one 32-byte unit: text edges (bytes outside [vb, tend) are not text), units with
@@ -457,9 +471,155 @@ __device__ __noinline__ int row_end_search(const StreamSmem& S, int s, int limit
     return limit;
 }
 
+// Phase B for one warp's share [u0, u1) of the window.  kInterior: every unit is whole text (no edge of the input in
+// the window), so the per-unit edge tests are compiled out.
+template <bool kInterior>
+__device__ __forceinline__ void classify_share(StreamSmem& S, const uint8_t* win, int u0, int u1, int vb, int tend, bool has_begin, bool virt_nl,
+                                               int warp, int lane) {
+    const unsigned FULL = 0xffffffffu;
+    const uint32_t lt = (1u << lane) - 1u;
+    int cnt = 0;
+    uint32_t crowd = 0, blank = 0;
+    uint32_t carry_in = 0;
+    if (u0 < u1 && u0 > 0 && (u0 << 5) - 1 >= vb) carry_in = win[(u0 << 5) - 1] == '\n';
+    uint16_t* const seg = S.seg[warp];
+    for (int base = u0; base < u1; base += 32) {
+        const int u = base + lane;
+        const int pos0 = u << 5;
+        uint32_t nl = 0, tab = 0, dig = 0;
+        const bool live = kInterior || u < u1;
+        const bool edge = !kInterior && ((has_begin && pos0 <= vb) || pos0 + 32 > tend);  // first / last bytes of the text
+        if (live) {
+            const uint4 v0 = *reinterpret_cast<const uint4*>(win + pos0);
+            const uint4 v1 = *reinterpret_cast<const uint4*>(win + pos0 + 16);
+            const uint32_t x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            const uint32_t hi = (x[0] | x[1] | x[2] | x[3] | x[4] | x[5] | x[6] | x[7]) & 0x80808080u;
+            if (__builtin_expect(edge || hi != 0, 0)) {
+                classify_unit_slow(S, win, pos0, vb, tend, nl, tab, dig);
+                if (virt_nl && tend >= pos0 && tend < pos0 + 32) nl |= 1u << (tend - pos0);
+            } else {
+                // ASCII bytes: per-byte sums stay below 0x100, so plain 32-bit adds classify four bytes at once
+                uint32_t fn[8], ft[8], fd[8], sus = 0;
+#pragma unroll
+                for (int k = 0; k < 8; k++) {
+                    const uint32_t tu = (x[k] ^ 0x09090909u) + 0x7F7F7F7Fu;  // bit 7 clear <=> tab
+                    const uint32_t nu = (x[k] ^ 0x0A0A0A0Au) + 0x7F7F7F7Fu;  // bit 7 clear <=> newline
+                    const uint32_t ge30 = x[k] + 0x50505050u, ge3a = x[k] + 0x46464646u, ge23 = x[k] + 0x5D5D5D5Du;
+                    ft[k] = ~tu & 0x80808080u;
+                    fn[k] = ~nu & 0x80808080u;
+                    fd[k] = ge30 & ~ge3a & 0x80808080u;
+                    sus |= ~ge23 & tu & nu;  // below '#' and neither tab nor newline: look closer
+                }
+                nl = pack32(fn);
+                tab = pack32(ft);
+                dig = pack32(fd);
+                if (__builtin_expect((sus & 0x80808080u) != 0, 0)) {
+                    uint32_t a, b, c;
+                    classify_unit_slow(S, win, pos0, vb, tend, a, b, c);  // exact '"' / '\r' search
+                }
+            }
+            S.tabm[u] = tab;
+            S.digm[u] = dig;
+            S.nlm[u] = nl;
+        }
+        // row starts: a non-newline byte behind a newline (or behind the virtual newline in front of the text)
+        const uint32_t upv = __shfl_up_sync(FULL, nl, 1);
+        const uint32_t carry = lane == 0 ? carry_in : (upv >> 31);
+        carry_in = __shfl_sync(FULL, nl, 31) >> 31;
+        uint32_t prev = (nl << 1) | carry;
+        uint32_t st;
+        if (__builtin_expect(edge, 0)) {
+            const uint32_t valid_lo = pos0 >= vb ? ~0u : (vb - pos0 >= 32 ? 0u : ~0u << (vb - pos0));
+            const uint32_t valid_hi = pos0 + 32 <= tend ? ~0u : (tend <= pos0 ? 0u : ~0u >> (32 - (tend - pos0)));
+            if (pos0 <= vb) prev &= valid_lo;  // the byte in front of vb is not text
+            if (has_begin && vb >= pos0 && vb < pos0 + 32) prev |= 1u << (vb - pos0);
+            st = prev & ~nl & valid_lo & valid_hi;
+        } else
+            st = prev & ~nl;
+        blank |= nl & prev;
+        // a valid row is >= 26 bytes: at most one start per 16 bytes, compacted with one ballot per half
+        const uint32_t sl = st & 0xFFFFu, sh = st >> 16;
+        crowd |= (sl & (sl - 1u)) | (sh & (sh - 1u));
+        const unsigned bl = __ballot_sync(FULL, sl != 0), bh = __ballot_sync(FULL, sh != 0);
+        int idx = cnt + __popc(bl & lt) + __popc(bh & lt);
+        if (sl) seg[idx++] = (uint16_t)(pos0 + __ffs(sl) - 1);
+        if (sh) seg[idx] = (uint16_t)(pos0 + 16 + __ffs(sh) - 1);
+        cnt += __popc(bl) + __popc(bh);
+    }
+    if (__any_sync(FULL, blank != 0) && lane == 0) S.has_blank = 1;
+    if (__any_sync(FULL, crowd != 0) && lane == 0) S.crowded = 1;
+    __syncwarp();
+    if (lane == 0) {
+        S.warp_cnt[warp] = cnt;
+        S.warp_first[warp] = cnt ? (int)seg[0] : -1;
+        S.warp_last[warp] = cnt ? (int)seg[cnt - 1] : -1;
+    }
+}
+
+// Flushes the buffered record headers: ONE global atomic reserves their (dense) place in the record array, then every
+// thread writes headers.  All threads of the CTA call; two barriers.
+__device__ __forceinline__ void flush_records(const RunParams& p, StreamSmem& S, int tid) {
+    const int n = S.rec_cnt;
+    if (n == 0) return;
+    if (tid == 0) {
+        const unsigned long long rs = atomicAdd(&p.ctr->rec_slots, (unsigned long long)n << 32);
+        const uint32_t rec_base = (uint32_t)(rs >> 32);
+        S.rec_base = rec_base;
+        if ((unsigned long long)rec_base + (unsigned long long)n > p.rec_cap) {
+            S.out_ok = 0;
+            p.ctr->cap_overflow = 1;
+        }
+    }
+    __syncthreads();
+    if (S.out_ok) {
+        const uint32_t rec_base = S.rec_base;
+        for (int i = tid; i < n; i += kTileThreads) {
+            const StagedRec sr = S.rec_buf[i];
+            blu_record rec;
+            rec.query_off = sr.abs;
+            rec.query_len = sr.qlen;
+            rec.n_rows = sr.nrows;
+            rec.keep_mask = 0;
+            rec.perc_identity = 0.0;
+            rec.bit_score = (int64_t)sr.mx;
+            rec.ref_lineage = 0;
+            rec.slot_base = sr.slot;
+            rec.n_beans = 0;
+            rec.n_accessions = sr.gtot;  // size of the top group until the consensus kernel overwrites it
+            rec.status = 2;              // waiting for the consensus kernel
+            rec.single_match = 0;
+            rec.mutated = 0;
+            rec.reached_pos = 0;
+            rec.allowed_pos = -1;
+            rec.bean_level = 0;
+            rec.pad[0] = rec.pad[1] = 0;
+            p.records[rec_base + i] = rec;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) S.rec_cnt = 0;
+}
+
+#ifdef BLU_PHASE_CLOCKS
+#define PCLK(i)                                  \
+    {                                            \
+        long long _t;                            \
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(_t)::"memory"); \
+        pc[i] += _t - pt;                        \
+        pt = _t;                                 \
+    }
+#else
+#define PCLK(i)
+#endif
+
 __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(const __grid_constant__ RunParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     StreamSmem& S = *reinterpret_cast<StreamSmem*>(smem_raw);
+#ifdef BLU_PHASE_CLOCKS
+    long long pc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long pt = clock64();
+    int n_win = 0;
+#endif
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned FULL = 0xffffffffu;
     if (p.end <= p.begin) return;
@@ -476,13 +636,20 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
     if (tid == 0) {
         mbar_init(&S.mbar[0], 1);
         mbar_init(&S.mbar[1], 1);
-        S.carry.open = 0;
-        S.carry.deferred = 0;
-        S.carry.g = 0;
+        S.carry[0].open = S.carry[1].open = 0;
+        S.bad_byte = INT_MAX;
+        S.has_blank = S.crowded = 0;
+        S.n_runs = S.next_run = S.n_top = S.n_skip = S.term = S.new_open = 0;
+        S.pass_need = 0;
+        S.old_tops = 0;
+        S.slot_cur = S.slot_end = 0;
+        S.rec_cnt = 0;
+        S.out_ok = 1;
     }
-    for (int i = tid; i < 7; i += kTileThreads) S.tabm[kUnits + i] = S.digm[kUnits + i] = S.nlm[kUnits + i] = S.stm[kUnits + i] = 0u;
+    for (int i = tid; i < 7; i += kTileThreads) S.tabm[kUnits + i] = S.digm[kUnits + i] = S.nlm[kUnits + i] = 0u;
     __syncthreads();
     uint32_t ph0 = 0, ph1 = 0;
+    int cur = 0;  // which carry buffer holds the open query
 
     unsigned long long lo = seg_lo > p.begin + kBack ? (seg_lo - kBack) & ~15ull : b16;
     if (lo < b16) lo = b16;
@@ -498,16 +665,8 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
         const int loaded = (int)(up - lo < (unsigned long long)kTile ? up - lo : (unsigned long long)kTile);
         const int tend = (int)(p.end - lo < (unsigned long long)loaded ? p.end - lo : (unsigned long long)loaded);
         const bool covers_eof = p.end <= lo + (unsigned long long)loaded;
-        const bool has_begin = lo <= p.begin;            // the window contains the first byte of the text
+        const bool has_begin = lo <= p.begin;  // the window contains the first byte of the text
         const int vb = has_begin ? (int)(p.begin - lo) : 0;
-        if (tid == 0) {
-            S.last_nl = -1;
-            S.bad_byte = INT_MAX;
-            S.has_blank = 0;
-            S.crowded = 0;
-            S.n_runs = 0;
-            S.n_top = 0;
-        }
         if (tid == 32) {
             // the window after the next one: start moving it from HBM to L2
             const unsigned long long nb = lo + 2ull * kTile - 512ull;
@@ -523,142 +682,85 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
             }
             ph ^= 1;
         }
-        __syncthreads();  // (also publishes the resets above)
+        PCLK(0)
         // an unterminated last row of the input is closed by a virtual newline at `tend`
         const bool virt_nl = p.final_chunk && covers_eof && tend > vb && win[tend - 1] != '\n';
         const int scan_len = tend + (virt_nl ? 1 : 0);
         const int n_units = (scan_len + 31) >> 5;
 
-        // ---- phase B: classify -----------------------------------------------------------------------------------
-        const int upw = (((n_units + kSWarps - 1) / kSWarps) + 31) & ~31;  // units per warp, whole rounds
-        const int u0 = warp * upw;
-        const int u1 = u0 + upw < n_units ? u0 + upw : n_units;
+        // ---- phase B: classify + per-warp row starts ----------------------------------------------------------------
         {
-            int cnt = 0, my_last = -1;
-            uint32_t carry_in = 0;
-            if (u0 < u1 && u0 > 0 && (u0 << 5) - 1 >= vb) carry_in = win[(u0 << 5) - 1] == '\n';
-            for (int base = u0; base < u1; base += 32) {
-                const int u = base + lane;
-                const int pos0 = u << 5;
-                uint32_t nl = 0, tab = 0, dig = 0;
-                const bool live = u < u1;
-                const bool edge = (has_begin && pos0 <= vb) || pos0 + 32 > tend;  // first / last bytes of the text
-                if (live) {
-                    const uint4 v0 = *reinterpret_cast<const uint4*>(win + pos0);
-                    const uint4 v1 = *reinterpret_cast<const uint4*>(win + pos0 + 16);
-                    const uint32_t x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-                    const uint32_t hi = (x[0] | x[1] | x[2] | x[3] | x[4] | x[5] | x[6] | x[7]) & 0x80808080u;
-                    if (__builtin_expect(edge || hi != 0, 0)) {
-                        classify_unit_slow(S, win, pos0, vb, tend, nl, tab, dig);
-                        if (virt_nl && tend >= pos0 && tend < pos0 + 32) nl |= 1u << (tend - pos0);
-                    } else {
-                        // ASCII bytes: per-byte sums stay below 0x100, so plain 32-bit adds classify four bytes at once
-                        uint32_t fn[8], ft[8], fd[8], sus = 0;
-#pragma unroll
-                        for (int k = 0; k < 8; k++) {
-                            const uint32_t tu = (x[k] ^ 0x09090909u) + 0x7F7F7F7Fu;  // bit 7 clear <=> tab
-                            const uint32_t nu = (x[k] ^ 0x0A0A0A0Au) + 0x7F7F7F7Fu;  // bit 7 clear <=> newline
-                            const uint32_t ge30 = x[k] + 0x50505050u, ge3a = x[k] + 0x46464646u, ge23 = x[k] + 0x5D5D5D5Du;
-                            ft[k] = ~tu & 0x80808080u;
-                            fn[k] = ~nu & 0x80808080u;
-                            fd[k] = ge30 & ~ge3a & 0x80808080u;
-                            sus |= ~ge23 & tu & nu;  // below '#' and neither tab nor newline: look closer
-                        }
-                        nl = pack32(fn);
-                        tab = pack32(ft);
-                        dig = pack32(fd);
-                        if (__builtin_expect((sus & 0x80808080u) != 0, 0)) {
-                            uint32_t a, b, c;
-                            classify_unit_slow(S, win, pos0, vb, tend, a, b, c);  // exact '"' / '\r' search
-                        }
-                    }
-                }
-                // row starts: a non-newline byte behind a newline (or behind the virtual newline in front of the text)
-                const uint32_t upv = __shfl_up_sync(FULL, nl, 1);
-                uint32_t carry = lane == 0 ? carry_in : (upv >> 31);
-                carry_in = __shfl_sync(FULL, nl, 31) >> 31;
-                uint32_t prev = (nl << 1) | carry;
-                uint32_t st;
-                if (__builtin_expect(edge, 0)) {
-                    const uint32_t valid_lo = pos0 >= vb ? ~0u : (vb - pos0 >= 32 ? 0u : ~0u << (vb - pos0));
-                    const uint32_t valid_hi = pos0 + 32 <= tend ? ~0u : (tend <= pos0 ? 0u : ~0u >> (32 - (tend - pos0)));
-                    if (pos0 <= vb) prev &= valid_lo;  // the byte in front of vb is not text
-                    if (has_begin && vb >= pos0 && vb < pos0 + 32) prev |= 1u << (vb - pos0);
-                    st = prev & ~nl & valid_lo & valid_hi;
-                } else
-                    st = prev & ~nl;
-                if (live) {
-                    S.tabm[u] = tab;
-                    S.digm[u] = dig;
-                    S.nlm[u] = nl;
-                    S.stm[u] = st;
-                    cnt += __popc(st);
-                    if (nl & prev) S.has_blank = 1;
-                    if (((st & 0xFFFFu) & ((st & 0xFFFFu) - 1u)) | ((st >> 16) & ((st >> 16) - 1u))) S.crowded = 1;
-                    if (nl) my_last = pos0 + 31 - __clz(nl);
-                }
-            }
-            cnt = __reduce_add_sync(FULL, cnt);
-            my_last = __reduce_max_sync(FULL, my_last);
-            if (lane == 0) {
-                S.warp_cnt[warp] = cnt;
-                if (my_last >= 0) atomicMax(&S.last_nl, my_last);
-            }
+            const int u0 = warp * kUnitsPerWarp;
+            const int u1 = u0 + kUnitsPerWarp < n_units ? u0 + kUnitsPerWarp : n_units;
+            if (!has_begin && tend == kTile && !virt_nl && kUnitsPerWarp * kSWarps == kTile / 32)
+                classify_share<true>(S, win, u0, u0 + kUnitsPerWarp, 0, tend, false, false, warp, lane);
+            else
+                classify_share<false>(S, win, u0, u1, vb, tend, has_begin, virt_nl, warp, lane);
         }
-        if (tid < 4) S.tabm[n_units + tid] = S.digm[n_units + tid] = S.nlm[n_units + tid] = S.stm[n_units + tid] = 0u;
+        PCLK(1)
+        if (tid < 4) S.tabm[n_units + tid] = S.digm[n_units + tid] = S.nlm[n_units + tid] = 0u;
         __syncthreads();
-        // ---- phase C: row index ----------------------------------------------------------------------------------
-        int so = 0, n_starts = 0;
+        PCLK(2)
+        // ---- row geometry of the window (every warp derives it from the per-warp tables) -----------------------------
+        // lane i < kSWarps holds the tables of warp i: row count, inclusive prefix, first start of the next non-empty
+        // share, last start of the previous one
+        int c_i, inc_i, nfirst_i, plast_i, n_starts, last_start;
+        {
+            c_i = lane < kSWarps ? S.warp_cnt[lane] : 0;
+            inc_i = c_i;
 #pragma unroll
-        for (int i = 0; i < kSWarps; i++) {
-            const int v = S.warp_cnt[i];
-            if (i < warp) so += v;
-            n_starts += v;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int t = __shfl_up_sync(FULL, inc_i, d);
+                if (lane >= d) inc_i += t;
+            }
+            n_starts = __shfl_sync(FULL, inc_i, 31);
+            const unsigned ne = __ballot_sync(FULL, c_i > 0);
+            const unsigned below = ne & ((1u << lane) - 1u), above = lane >= 31 ? 0u : (ne & (~0u << (lane + 1)));
+            const int wl = lane < kSWarps ? S.warp_last[lane] : -1, wf = lane < kSWarps ? S.warp_first[lane] : -1;
+            plast_i = __shfl_sync(FULL, wl, below ? 31 - __clz(below) : 0);
+            if (!below) plast_i = -1;
+            nfirst_i = __shfl_sync(FULL, wf, above ? __ffs(above) - 1 : 0);
+            if (!above) nfirst_i = -1;
+            last_start = __shfl_sync(FULL, wl, ne ? 31 - __clz(ne) : 0);
+            if (!ne) last_start = -1;
         }
-        if (S.crowded || n_starts > kSRowCap) {
+        int last_nl = -1;  // last newline of the window
+        for (int ub = n_units - 1; ub >= 0 && last_nl < 0; ub -= 32) {
+            const int u = ub - lane;
+            const uint32_t w = u >= 0 ? S.nlm[u] : 0u;
+            const unsigned bal = __ballot_sync(FULL, w != 0);
+            if (bal) {
+                const int src = __ffs(bal) - 1;
+                const uint32_t wv = __shfl_sync(FULL, w, src);
+                last_nl = ((ub - src) << 5) + 31 - __clz(wv);
+            }
+        }
+        const bool crowded = S.crowded != 0 || n_starts > kSRowCap;
+        const bool blank = S.has_blank != 0;
+        const int bad_byte = S.bad_byte;
+        const int n_complete = (n_starts > 0 && last_start > last_nl) ? n_starts - 1 : n_starts;
+        if (crowded) {
             // a row shorter than 16 bytes / more rows than 26-byte rows fit: malformed input
             if (tid == 0) report(p.ctr, DE_BAD_FIELD_COUNT, lo);
-            return;  // (no copy in flight: the next window has not been requested yet)
+            break;  // (no copy in flight: the next window has not been requested yet)
         }
-        {
-            const uint32_t lt = (1u << lane) - 1u;
-            for (int base = u0; base < u1; base += 32) {
-                const int u = base + lane;
-                const uint32_t st = u < u1 ? S.stm[u] : 0u;
-                const uint32_t sl = st & 0xFFFFu, sh = st >> 16;
-                const unsigned bl = __ballot_sync(FULL, sl != 0), bh = __ballot_sync(FULL, sh != 0);
-                int idx = so + __popc(bl & lt) + __popc(bh & lt);
-                if (sl) S.row_s[idx++] = (uint16_t)((u << 5) + __ffs(sl) - 1);
-                if (sh) S.row_s[idx] = (uint16_t)((u << 5) + 16 + __ffs(sh) - 1);
-                so += __popc(bl) + __popc(bh);
-            }
-        }
-        __syncthreads();
-        const int last_nl = S.last_nl;
-        const int n_complete = (n_starts > 0 && (int)S.row_s[n_starts - 1] > last_nl) ? n_starts - 1 : n_starts;
-        if (tid == 0 && n_complete == n_starts) S.row_s[n_starts] = (uint16_t)(last_nl + 1);  // sentinel: end of the last row
-        if (S.bad_byte != INT_MAX && tid == 0) report(p.ctr, DE_QUOTE_OR_CR, lo + (unsigned)S.bad_byte);
-        // first row this CTA has not seen yet / first row beyond the segment
-        int r0, r_hi;
-        {
-            int a = 0, b = n_complete;
-            while (a < b) {
-                const int m = (a + b) >> 1;
-                if (lo + S.row_s[m] < own_from) a = m + 1; else b = m;
-            }
-            r0 = a;
-            b = n_complete;
-            while (a < b) {
-                const int m = (a + b) >> 1;
-                if (lo + S.row_s[m] < seg_hi) a = m + 1; else b = m;
-            }
-            r_hi = a;
-        }
-        const bool progress = n_complete > r0;
+        if (bad_byte != INT_MAX && tid == 0) report(p.ctr, DE_QUOTE_OR_CR, lo + (unsigned)bad_byte);
         // next window: starts just in front of the last complete row (the look-behind row of the next window)
+        int lc = last_start;
+        if (n_complete != n_starts) {
+            // the last start is an unterminated row; the last complete row is the start before it
+            const unsigned ne = __ballot_sync(FULL, c_i > 0);
+            const int wlast = 31 - __clz(ne);  // (ne != 0: n_starts > 0)
+            const int cl = __shfl_sync(FULL, c_i, wlast);
+            const unsigned rest = ne & ~(1u << wlast);
+            const int w2 = rest ? 31 - __clz(rest) : 0;
+            const int c2 = __shfl_sync(FULL, c_i, w2);
+            lc = cl >= 2 ? (int)S.seg[wlast][cl - 2] : (rest ? (int)S.seg[w2][c2 - 1] : -1);
+        }
+        const bool progress = lc >= 0 && lo + (unsigned long long)lc >= own_from;  // a complete row this CTA had not seen yet
         unsigned long long next_lo = lo;
         if (progress) {
-            const unsigned long long la = lo + S.row_s[n_complete - 1];
+            const unsigned long long la = lo + (unsigned long long)lc;
             next_lo = la > p.begin ? (la - 1) & ~15ull : b16;
             if (next_lo < b16) next_lo = b16;
         }
@@ -667,57 +769,82 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
             const unsigned long long n = up - next_lo < (unsigned long long)kTile ? up - next_lo : (unsigned long long)kTile;
             stream_issue_load(S, buf ^ 1, p.text, next_lo, (int)n);
         }
-        const bool blank = S.has_blank != 0;
         const uint64_t* tabw = reinterpret_cast<const uint64_t*>(S.tabm);
         const uint64_t* digw = reinterpret_cast<const uint64_t*>(S.digm);
-        if (tid == 0 && S.carry.open) {
-            S.runs[0] = (uint16_t)(0x8000 | r0);  // the carried query continues (or ends) at row r0
-            S.n_runs = 1;
-        }
-        __syncthreads();
-        // ---- phase D: one thread per row ---------------------------------------------------------------------------
-        for (int rb = 0; rb < n_complete; rb += kTileThreads) {
+        PCLK(3)
+        // ---- phase D: one thread per row -------------------------------------------------------------------------------
+        for (int rb = 0; rb < n_starts; rb += kTileThreads) {
             const int r = rb + tid;
-            const bool active = r >= r0 && r < n_complete;
-            bool head = false;
-            if (active) {
-                const int s = S.row_s[r];
-                const int e = blank ? row_end_search(S, s, last_nl) : (int)S.row_s[r + 1] - 1;
-                int64_t bits;
-                int ql;
-                if (!parse_row_lean(win, S.tabm, S.digm, s, e, bits, ql)) {
-                    const LightRow lr = parse_row_masked(win, tabw, digw, s, e);
-                    if (lr.err) report(p.ctr, lr.err, lo + s);
-                    bits = lr.bits;
-                    ql = lr.q_len;
-                }
-                if (r == 0) {
-                    head = has_begin;  // first row of the text; else: predecessor not in the window
-                    if (!head) push_defer(p, lo + s, 1);  // the block path decides whether it starts a query
-                } else
-                    head = !same_qid_lean(win, S.tabm, s, ql, S.row_s[r - 1]);
-                const int32_t b32 = (int32_t)bits;
-                S.flags[r] = ((int64_t)b32 != bits) ? 2 : 0;
-                S.bits[r] = b32;
-                if (head && r < r_hi) {
-                    const int i = atomicAdd(&S.n_runs, 1);
-                    S.runs[i] = (uint16_t)r;
+            const bool live = r < n_starts;
+            const int rr = live ? r : n_starts - 1;
+            // which warp's share found row rr: number of shares that end at or before it
+            int w = 0;
+#pragma unroll
+            for (int step = 16; step; step >>= 1) {
+                const int cand = w + step;
+                const int v = __shfl_sync(FULL, inc_i, (cand - 1) & 31);
+                if (cand <= kSWarps && v <= rr) w = cand;
+            }
+            const int cw = __shfl_sync(FULL, c_i, w);
+            const int k = rr - (__shfl_sync(FULL, inc_i, w) - cw);
+            const int nf = __shfl_sync(FULL, nfirst_i, w), pl = __shfl_sync(FULL, plast_i, w);
+            bool head = false, skip = false;
+            if (live) {
+                const uint16_t* const seg_w = S.seg[w];
+                const int s = seg_w[k];
+                S.row_s[r] = (uint16_t)s;
+                const unsigned long long abs = lo + (unsigned long long)s;
+                if (abs < own_from)
+                    skip = true;  // look-behind rows: seen by the previous window / owned by the previous segment
+                else if (r < n_complete) {
+                    const int nxt = k + 1 < cw ? (int)seg_w[k + 1] : (nf >= 0 ? nf : last_nl + 1);
+                    const int e = blank ? row_end_search(S, s, last_nl) : nxt - 1;
+                    int64_t bits;
+                    int ql;
+                    if (!parse_row_lean(win, S.tabm, S.digm, s, e, bits, ql)) {
+                        const LightRow lr = parse_row_masked(win, tabw, digw, s, e);
+                        if (lr.err) report(p.ctr, lr.err, abs);
+                        bits = lr.bits;
+                        ql = lr.q_len;
+                    }
+                    const int prv = k > 0 ? (int)seg_w[k - 1] : pl;
+                    if (prv < 0) {
+                        head = has_begin;  // first row of the text; else: predecessor not in the window
+                        if (!head) push_defer(p, abs, 1);  // the block path decides whether it starts a query
+                    } else
+                        head = !same_qid_lean(win, S.tabm, s, ql, prv);
+                    const int32_t b32 = (int32_t)bits;
+                    S.flags[r] = ((int64_t)b32 != bits) ? 2 : 0;
+                    S.bits[r] = b32;
+                    if (head) {
+                        if (abs < seg_hi) {
+                            const int i = atomicAdd(&S.n_runs, 1);
+                            S.runs[i] = (uint16_t)r;
+                        } else
+                            S.term = 1;  // a query of the next segment starts here: this CTA ends with this window
+                    }
                 }
             }
             const unsigned hb = __ballot_sync(FULL, head);
-            if (lane == 0 && (r & ~31) < n_complete) S.headw[r >> 5] = hb;
+            if (lane == 0) S.headw[r >> 5] = hb;
+            const unsigned sb = __ballot_sync(FULL, skip);
+            if (sb && lane == 0) atomicAdd(&S.n_skip, __popc(sb));
+        }
+        PCLK(4)
+        if (tid == 0) {
+            if (n_complete == n_starts) S.row_s[n_starts] = (uint16_t)(last_nl + 1);  // sentinel: end of the last row
         }
         __syncthreads();
-        // ---- phases E / K / F, kRunBatch runs at a time -------------------------------------------------------------
+        PCLK(5)
+        // ---- phases E / F, kRunBatch runs at a time -------------------------------------------------------------------
         const int n_runs = S.n_runs;
+        const int r0 = S.n_skip;  // first row of this window the CTA had not seen
+        const bool term = S.term != 0;
         const bool closes = covers_eof && p.final_chunk;  // the end of this window ends the open query
+        bool new_open = false;                            // a query that starts in this window stays open
         for (int b0 = 0; b0 < n_runs; b0 += kRunBatch) {
             const int nb = n_runs - b0 < kRunBatch ? n_runs - b0 : kRunBatch;
-            if (tid == 0) {
-                S.next_run = 0;
-                S.n_top = 0;
-            }
-            __syncthreads();
+            PCLK(6)
             // ---- phase E: one warp per run ---------------------------------------------------------------------------
             while (true) {
                 int j = 0;
@@ -726,10 +853,11 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
                 if (j >= nb) break;
                 const int entry = S.runs[b0 + j];
                 const bool pseudo = (entry & 0x8000) != 0;
-                const int h = entry & 0x7FFF;
+                const int h = pseudo ? r0 : (entry & 0x7FFF);
                 int e = next_head(S, pseudo ? h : h + 1, n_complete, lane);
                 const bool open = e < 0;
                 if (open) e = n_complete;
+                if (e < h) e = h;
                 int mx = INT32_MIN;
                 bool ovf = false;
                 for (int r = h + lane; r < e; r += 32) {
@@ -763,161 +891,115 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
                     }
                 }
                 if (lane == 0) {
-                    S.run_h[j] = (uint16_t)h;
-                    S.run_e[j] = (uint16_t)e;
-                    S.run_mx[j] = mx;
-                    S.run_t0[j] = (uint16_t)t0;
-                    S.run_gpart[j] = (uint16_t)(ovf ? 0 : g);
-                    S.run_kind[j] = (pseudo ? RK_PSEUDO : 0) | (open ? RK_OPEN : 0) | (ovf ? RK_OVF : 0);
-                    if (!pseudo) {
+                    // what happens to the run
+                    const int rows_t = e - h;
+                    int g_part = ovf ? 0 : g, g_tot = 0, dst = 0;
+                    uint8_t kind = pseudo ? RK_PSEUDO : 0;
+                    unsigned long long abs;
+                    uint32_t qlen, nrows;
+                    if (pseudo) {
+                        CarryRun& C = S.carry[cur];
+                        if (ovf) C.deferred = 1;
+                        if (rows_t > 0 && !C.deferred) {
+                            if (mx > C.mx) {
+                                C.mx = mx;
+                                C.g = 0;
+                            } else if (mx < C.mx)
+                                g_part = 0;
+                            if (C.g + g_part > kCarryTop) C.deferred = 1;
+                        }
+                        if (C.deferred || rows_t == 0) g_part = 0;
+                        abs = C.head_abs, qlen = C.qlen, nrows = C.nrows + (uint32_t)rows_t;
+                        mx = C.mx;
+                        if (!open || closes) {
+                            kind |= C.deferred ? RK_DEFER : RK_EMIT;
+                            g_tot = C.g + g_part;
+                            dst = C.g;
+                            if (!C.deferred) S.old_tops = C.g;
+                            C.open = 0;
+                        } else if (covers_eof) {
+                            // the input continues in the next chunk: the whole query is carried over by the host
+                            atomicMin(&p.ctr->tail_start, C.head_abs);
+                            g_part = 0;
+                            C.open = 0;
+                        } else {
+                            kind |= RK_OPEN;
+                            C.nrows = nrows;
+                            dst = -1 - C.g;
+                            C.g += g_part;
+                        }
+                    } else {
                         const int s = S.row_s[h];
                         const int re = blank ? row_end_search(S, s, last_nl) : (int)S.row_s[h + 1] - 1;
-                        S.run_abs[j] = lo + s;
-                        S.run_qlen[j] = (uint32_t)(next_tab(tabw, s, re) - s);
+                        abs = lo + (unsigned long long)s;
+                        qlen = (uint32_t)(next_tab(tabw, s, re) - s);
+                        nrows = (uint32_t)rows_t;
+                        if (!open || closes) {
+                            kind |= ovf ? RK_DEFER : RK_EMIT;
+                            g_tot = g_part;
+                        } else if (covers_eof) {
+                            atomicMin(&p.ctr->tail_start, abs);
+                            g_part = 0;
+                        } else {
+                            // a query that starts in this window and does not end in it: it becomes the carried query
+                            CarryRun& C = S.carry[cur ^ 1];
+                            kind |= RK_OPEN | RK_NEWCARRY;
+                            C.open = 1;
+                            C.deferred = ovf ? 1 : 0;
+                            C.head_abs = abs;
+                            C.qlen = qlen;
+                            C.nrows = nrows;
+                            C.mx = mx;
+                            C.g = g_part;
+                            dst = -1;
+                            S.new_open = 1;
+                        }
                     }
+                    if (kind & RK_EMIT) {
+                        // the run's place in the output of the pass (records << 16 | slots)
+                        const uint32_t o = atomicAdd(&S.pass_need, (1u << 16) | (uint32_t)g_tot);
+                        StagedRec sr;
+                        sr.abs = abs, sr.qlen = qlen, sr.nrows = nrows, sr.mx = mx, sr.gtot = (uint32_t)g_tot, sr.slot = o & 0xFFFFu, sr.pad = 0;
+                        S.rec_buf[S.rec_cnt + (int)(o >> 16)] = sr;
+                        S.run_slot[j] = (uint16_t)(o & 0xFFFFu);
+                    }
+                    if (kind & RK_DEFER) push_defer(p, abs, 0);
+                    S.run_t0[j] = (uint16_t)t0;
+                    S.run_gpart[j] = (uint16_t)g_part;
+                    S.run_dst[j] = dst;
+                    S.run_kind[j] = kind;
                 }
                 __syncwarp();
             }
+            PCLK(7)
             __syncthreads();
-            // ---- phase K: warp 0 decides what happens to every run of the pass and reserves the output -----------------
-            if (warp == 0) {
-                // runs that touch the carry (at most two per window): the continuation of the carried query (always entry 0
-                // of the first pass) and the query that is still open at the end of the window
-                int j_open = -1;
-                for (int base = 0; base < nb; base += 32) {
-                    const int j = base + lane;
-                    const uint8_t kind = j < nb ? S.run_kind[j] : (uint8_t)0;
-                    const unsigned bal = __ballot_sync(FULL, (kind & RK_OPEN) && !(kind & RK_PSEUDO));
-                    if (bal) j_open = base + __ffs(bal) - 1;
-                }
-                if (lane == 0) {
-                    for (int pass = 0; pass < 2; pass++) {
-                        {
-                            const int j = pass == 0 ? 0 : j_open;
-                            if (j < 0) continue;
-                            uint8_t kind = S.run_kind[j];
-                            const bool pseudo = (kind & RK_PSEUDO) != 0, open = (kind & RK_OPEN) != 0;
-                            if (pass == 0 ? !pseudo : (pseudo || !open)) continue;
-                            const int rows_t = (int)S.run_e[j] - (int)S.run_h[j];
-                            CarryRun& C = S.carry;
-                            if (pseudo) {
-                                int g_eff = 0, dst = 0;
-                                if (kind & RK_OVF) C.deferred = 1;
-                                if (rows_t > 0 && !C.deferred) {
-                                    const int mxt = S.run_mx[j];
-                                    if (mxt > C.mx) {
-                                        C.mx = mxt;
-                                        C.g = 0;
-                                        g_eff = S.run_gpart[j];
-                                    } else if (mxt == C.mx)
-                                        g_eff = S.run_gpart[j];
-                                    if (C.g + g_eff > kCarryTop) {
-                                        C.deferred = 1;
-                                        g_eff = 0;
-                                    }
-                                }
-                                if (C.deferred) g_eff = 0;
-                                const bool ends = !open || closes;
-                                kind &= ~(RK_EMIT | RK_DEFER);
-                                if (ends) {
-                                    kind &= ~RK_OPEN;
-                                    kind |= C.deferred ? RK_DEFER : RK_EMIT;
-                                    S.run_abs[j] = C.head_abs;
-                                    S.run_qlen[j] = C.qlen;
-                                    S.run_nrows[j] = C.nrows + (uint32_t)rows_t;
-                                    S.run_mx[j] = C.mx;
-                                    S.run_gtot[j] = (uint16_t)(C.g + g_eff);
-                                    dst = C.g;
-                                    C.open = 0;
-                                } else if (covers_eof) {
-                                    // the input continues in the next chunk: the whole query is carried over by the host
-                                    atomicMin(&p.ctr->tail_start, C.head_abs);
-                                    kind &= ~RK_OPEN;
-                                    g_eff = 0;
-                                    C.open = 0;
-                                } else {
-                                    C.nrows += (uint32_t)rows_t;
-                                    dst = -1 - C.g;
-                                    C.g += g_eff;
-                                }
-                                S.run_gpart[j] = (uint16_t)g_eff;
-                                S.run_dst[j] = dst;
-                            } else {
-                                // a query that starts in this window and does not end in it
-                                if (closes) {
-                                    kind &= ~RK_OPEN;  // ... except at the end of the input: an ordinary finished query
-                                } else if (covers_eof) {
-                                    atomicMin(&p.ctr->tail_start, S.run_abs[j]);
-                                    S.run_gpart[j] = 0;
-                                } else {
-                                    C.open = 1;
-                                    C.deferred = (kind & RK_OVF) ? 1 : 0;
-                                    C.head_abs = S.run_abs[j];
-                                    C.qlen = S.run_qlen[j];
-                                    C.nrows = (uint32_t)rows_t;
-                                    C.mx = S.run_mx[j];
-                                    C.g = C.deferred ? 0 : (int)S.run_gpart[j];
-                                    S.run_dst[j] = -1;
-                                }
-                            }
-                            S.run_kind[j] = kind;
-                        }
-                    }
-                }
-                __syncwarp();
-                // ordinary runs + totals: packed (records << 16 | slots) prefix sums over the pass
-                uint32_t tot = 0;
-                for (int base = 0; base < nb; base += 32) {
-                    const int j = base + lane;
-                    uint32_t need = 0;
-                    if (j < nb) {
-                        uint8_t kind = S.run_kind[j];
-                        if (!(kind & (RK_PSEUDO | RK_OPEN))) {
-                            // finished inside this window
-                            kind |= (kind & RK_OVF) ? RK_DEFER : RK_EMIT;
-                            S.run_nrows[j] = (uint32_t)((int)S.run_e[j] - (int)S.run_h[j]);
-                            S.run_gtot[j] = S.run_gpart[j];
-                            S.run_dst[j] = 0;
-                            S.run_kind[j] = kind;
-                        }
-                        if (kind & RK_EMIT) need = (1u << 16) | (uint32_t)S.run_gtot[j];
-                        if (kind & RK_DEFER) push_defer(p, S.run_abs[j], 0);
-                    }
-                    uint32_t inc = need;
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const uint32_t t = __shfl_up_sync(FULL, inc, d);
-                        if (lane >= d) inc += t;
-                    }
-                    if (j < nb) {
-                        const uint32_t ex = tot + inc - need;
-                        S.run_rec[j] = (uint16_t)(ex >> 16);
-                        S.run_slot[j] = ex & 0xFFFFu;
-                    }
-                    tot += __shfl_sync(FULL, inc, 31);
-                }
-                const uint32_t n_rec = tot >> 16, n_slot = tot & 0xFFFFu;
-                unsigned long long rs = 0;
-                if (lane == 0 && n_rec) rs = atomicAdd(&p.ctr->rec_slots, ((unsigned long long)n_rec << 32) | (unsigned long long)n_slot);
-                rs = __shfl_sync(FULL, rs, 0);
-                const uint32_t rec_base = (uint32_t)(rs >> 32), slot_base = (uint32_t)rs;
-                const bool ok = (unsigned long long)rec_base + n_rec <= p.rec_cap && (unsigned long long)slot_base + n_slot <= p.slot_cap;
-                if (lane == 0) {
-                    S.rec_base = rec_base;
-                    S.slot_base = slot_base;
-                    S.pass_ok = ok ? 1 : 0;
-                    if (!ok) p.ctr->cap_overflow = 1;
-                }
-                // a carried query that ends here: its earlier top rows go in front of this window's
-                if (b0 == 0 && ok && (S.run_kind[0] & RK_PSEUDO) && (S.run_kind[0] & RK_EMIT)) {
-                    const int n_old = S.run_dst[0];
-                    if (lane < n_old) p.toprows[slot_base + S.run_slot[0] + lane] = S.carry.tops[lane];
-                }
-            }
-            __syncthreads();
-            // ---- phase F: top rows (one thread each) and record headers (one thread per finished query) --------------
+            PCLK(8)
+            // ---- phase F: top rows (one thread each: field split + number parse) go straight to their slots ---------------
+            const uint32_t need = S.pass_need;
+            const int n_rec = (int)(need >> 16);
+            const uint32_t n_slot = need & 0xFFFFu;
+            if (S.new_open) new_open = true;
             const int n_top = S.n_top < kTopCap ? S.n_top : kTopCap;
-            const bool ok = S.pass_ok != 0;
+            const int n_old = S.old_tops;
+            const int rec_cnt = S.rec_cnt;
+            // slots come from the CTA's slab; a new slab costs one global atomic (every few dozen windows)
+            uint32_t slot_base = S.slot_cur;
+            if (n_slot > S.slot_end - slot_base) {
+                __syncthreads();  // everyone has read the old slab
+                if (tid == 0) {
+                    const uint32_t slab = n_slot > kSlotSlab ? n_slot : kSlotSlab;
+                    const unsigned long long rs = atomicAdd(&p.ctr->rec_slots, (unsigned long long)slab);
+                    S.slot_cur = (uint32_t)rs;
+                    S.slot_end = (uint32_t)rs + slab;
+                    if ((rs & 0xFFFFFFFFull) + (unsigned long long)slab > (unsigned long long)p.slot_cap) {
+                        S.out_ok = 0;
+                        p.ctr->cap_overflow = 1;
+                    }
+                }
+                __syncthreads();
+                slot_base = S.slot_cur;
+            }
+            const bool ok = S.out_ok != 0;
             for (int t = tid; t < n_top; t += kTileThreads) {
                 const int j = S.top_run[t];
                 const int k = t - (int)S.run_t0[j];
@@ -927,47 +1009,44 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
                 const int s = S.row_s[r];
                 const int e = blank ? row_end_search(S, s, last_nl) : (int)S.row_s[r + 1] - 1;
                 TopRowRaw tr;
-                const uint32_t err = split_top_row(win, tabw, s, e, lo, tr);
+                const uint32_t err = split_top_row_lean(win, S.tabm, S.digm, s, e, lo, tr);
                 if (err) {
                     report(p.ctr, err, lo + s);
                     continue;
                 }
                 const int dst = S.run_dst[j];
                 if (kind & RK_EMIT) {
-                    if (ok) p.toprows[S.slot_base + S.run_slot[j] + (uint32_t)(dst + k)] = tr;
+                    if (ok) p.toprows[slot_base + S.run_slot[j] + (uint32_t)(dst + k)] = tr;
                 } else
-                    S.carry.tops[-1 - dst + k] = tr;
+                    S.carry[(kind & RK_NEWCARRY) ? (cur ^ 1) : cur].tops[-1 - dst + k] = tr;
             }
-            for (int j = tid; j < nb; j += kTileThreads) {
-                if (!(S.run_kind[j] & RK_EMIT) || !ok) continue;
-                blu_record rec;
-                rec.query_off = S.run_abs[j];
-                rec.query_len = S.run_qlen[j];
-                rec.n_rows = S.run_nrows[j];
-                rec.keep_mask = 0;
-                rec.perc_identity = 0.0;
-                rec.bit_score = (int64_t)S.run_mx[j];
-                rec.ref_lineage = 0;
-                rec.slot_base = S.slot_base + S.run_slot[j];
-                rec.n_beans = 0;
-                rec.n_accessions = (uint32_t)S.run_gtot[j];  // size of the top group until the consensus kernel overwrites it
-                rec.status = 2;                              // waiting for the consensus kernel
-                rec.single_match = 0;
-                rec.mutated = 0;
-                rec.reached_pos = 0;
-                rec.allowed_pos = -1;
-                rec.bean_level = 0;
-                rec.pad[0] = rec.pad[1] = 0;
-                p.records[S.rec_base + S.run_rec[j]] = rec;
-            }
+            // a carried query that ends here: its earlier top rows go in front of this window's
+            if (b0 == 0 && ok && tid < n_old) p.toprows[slot_base + S.run_slot[0] + tid] = S.carry[cur].tops[tid];
+            // the pass's record headers now know where their slots are
+            for (int i = tid; i < n_rec; i += kTileThreads) S.rec_buf[rec_cnt + i].slot += slot_base;
+            PCLK(9)
             __syncthreads();
+            PCLK(10)
+            if (tid == 0) {
+                S.next_run = 0;
+                S.n_top = 0;
+                S.pass_need = 0;
+                S.old_tops = 0;
+                S.slot_cur = slot_base + n_slot;
+                S.rec_cnt = rec_cnt + n_rec;
+            }
+            if (rec_cnt + n_rec >= kRecFlush) {
+                __syncthreads();
+                flush_records(p, S, tid);
+            } else if (b0 + kRunBatch < n_runs)
+                __syncthreads();
         }
         // ---- where next? -----------------------------------------------------------------------------------------------
         // The CTA is done when the window reached the end of the text, when a query that belongs to the next segment
         // started in it, or when nothing is open and the segment is exhausted.
-        bool done = covers_eof;
-        if (!done && r_hi < n_complete) done = next_head(S, r_hi, n_complete, lane) >= 0;
-        const bool open_now = S.carry.open != 0;
+        if (new_open) cur ^= 1;
+        const bool open_now = S.carry[cur].open != 0;
+        bool done = covers_eof || term;
         if (!done && !open_now && lo + (unsigned long long)(last_nl + 1) >= seg_hi) done = true;
         if (!done && !may_continue) {
             // no complete new row in a whole window: a row longer than this kernel stages
@@ -981,13 +1060,35 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
                 while (!mbar_try_wait(&S.mbar[buf ^ 1], ph)) {
                 }
             }
-            return;
+            break;
         }
+#ifdef BLU_PHASE_CLOCKS
+        n_win++;
+#endif
         own_from = lo + (unsigned long long)(last_nl + 1);
         lo = next_lo;
         buf ^= 1;
-        __syncthreads();  // everyone has read the carry / window state of this step
+        if (n_runs == 0) __syncthreads();  // (else: the barrier that ends the last pass) everyone has read the window's state
+        // reset the per-window state (published by the barrier behind phase B of the next window)
+        if (tid == 0) {
+            S.bad_byte = INT_MAX;
+            S.has_blank = 0;
+            S.n_skip = 0;
+            S.term = 0;
+            S.new_open = 0;
+            S.n_runs = open_now ? 1 : 0;
+            S.runs[0] = 0x8000;  // the carried query continues (or ends) at the first new row
+        }
     }
+#ifdef BLU_PHASE_CLOCKS
+    if ((blockIdx.x == 7 || blockIdx.x == 200) && (lane == 0) && (warp == 0 || warp == 1 || warp == kSWarps - 1))
+        printf("cta %d warp %d windows %d | tma %lld B %lld bar1 %lld geom %lld D %lld bar2 %lld flush %lld E %lld bar3 %lld F %lld bar4 %lld\n", blockIdx.x, warp, n_win, pc[0] / (n_win + 1),
+               pc[1] / (n_win + 1), pc[2] / (n_win + 1), pc[3] / (n_win + 1), pc[4] / (n_win + 1), pc[5] / (n_win + 1), pc[6] / (n_win + 1), pc[7] / (n_win + 1), pc[8] / (n_win + 1),
+               pc[9] / (n_win + 1), pc[10] / (n_win + 1));
+#endif
+    // ---- the record headers still in the buffer -------------------------------------------------------------------------
+    __syncthreads();
+    flush_records(p, S, tid);
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -1,4 +1,5 @@
-"""Instruction / stall-sample breakdown of an ncu source dump by function (line ranges found in the sources)."""
+"""Instruction / stall-sample breakdown of an ncu source dump by kernel phase / helper function (line ranges located
+by text markers in the sources)."""
 import csv, sys
 src = sys.argv[1]
 def num(x):
@@ -17,8 +18,10 @@ def line_of(pat, f):
         if pat in l: return i
     return None
 K='blu_kernels.cu'; C='blu_core.cuh'
-marks={K:[('load_window','void load_window'),('make_geom','WinGeom make_geom'),('byte tests/pack','uint32_t bytes_eq'),('classify_chunk','void classify_chunk'),('scan_rows','bool scan_rows'),('finish_geom','void finish_geom'),('tile prologue',') tile_kernel('),('phase P','---- phase P'),('phase D','---- phase D'),('longrun','struct LongSmem')],
-       C:[('probe','uint32_t probe_taxid'),('parse_i64','bool parse_i64'),('parse_f64','uint32_t parse_f64'),('num_class/dfa','int num_class'),('light_parse_row','LightRow light_parse_row'),('ctz/next_tab/all_digits','int blu_ctz64'),('parse_row_masked','LightRow parse_row_masked'),('fast helpers','uint32_t blu_funnel_r'),('float_shape_ok','bool float_shape_ok'),('parse_row_fast','bool parse_row_fast'),('same_first_field','bool same_first_field'),('TopRow/heavy','struct TopRow'),('split_top_row','uint32_t split_top_row'),('join/heavy_masked','uint32_t join_top_row'),('consensus','struct QueryOut')]}
+marks={K:[('ptx wrappers','uint32_t smem_u32'),('longrun window code','struct WindowIndex'),('stream helpers','struct CarryRun'),('pack32','uint32_t pack8'),('classify_unit_slow','void classify_unit_slow'),('next_head','int next_head'),
+          ('row_end_search','int row_end_search'),('tile prologue',') tile_kernel('),('window setup','while (true) {\n'),('phase B classify','---- phase B'),('phase C index','---- phase C'),('phase D rows','---- phase D'),
+          ('phase E runs','---- phase E:'),('phase K reserve','---- phase K'),('phase F emit','---- phase F'),('where next','---- where next'),('longrun','// long-run kernel')],
+       C:[('probe','uint32_t probe_taxid'),('parse_i64','bool parse_i64'),('parse_f64','uint32_t parse_f64'),('num_class/dfa/check_float','int num_class'),('light_parse_row','LightRow light_parse_row'),('ctz/next_tab/all_digits','int blu_ctz64'),('parse_row_masked','LightRow parse_row_masked'),('bit helpers','uint32_t blu_funnel_r'),('float_shape_ok','bool float_shape_ok'),('parse_row_fast','bool parse_row_fast'),('lean helpers','int blu_popc64'),('parse_row_lean','bool parse_row_lean'),('load_u32_unaligned','uint32_t load_u32_unaligned'),('same_first_field','bool same_first_field'),('same_qid_lean','bool same_qid_lean'),('TopRow/heavy','struct TopRow'),('parse shorts','bool parse_u32_short'),('split_top_row','uint32_t split_top_row'),('join/heavy_masked','uint32_t join_top_row'),('consensus','struct QueryOut')]}
 ti=sum(v[0] for v in agg.values()) or 1; ts=sum(v[1] for v in agg.values()) or 1
 print('total warp-inst',ti,'samples',ts)
 for f,ms in marks.items():
