@@ -859,7 +859,7 @@ BLU_HD uint32_t split_top_row(const uint8_t* win, const uint64_t* tabw, int s, i
 }
 
 // The streaming kernel's top-row splitter: same result as split_top_row() for the common shapes -- saccver within the
-// first 64 bytes, staxid / length of at most 8 digits, pident `ddd[.ddd]` with at most 9 digits -- computed from two
+// first 64 bytes, staxid of at most 16 and length of at most 8 digits, pident `ddd[.ddd]` with at most 9 digits -- computed from two
 // mask words and SWAR digit folds (no per-byte loops, short dependency chain); anything else goes through
 // split_top_row().
 BLU_HD uint32_t split_top_row_lean(const uint8_t* win, const uint32_t* tabw32, const uint32_t* digw32, int s, int e, uint64_t lo, TopRowRaw& out) {
@@ -876,7 +876,7 @@ BLU_HD uint32_t split_top_row_lean(const uint8_t* win, const uint32_t* tabw32, c
             const uint32_t o_pid = (nd >> (q3 + 1)) & ((1u << lp) - 1u);
             const uint32_t o_len = (nd >> (q4 + 1)) & ((1u << ll) - 1u);
             int ni = lp, nf = 0;
-            bool ok = a + q5 < e && p1 >= 1 && p2 - p1 >= 2 && q3 >= 1 && q3 <= 8 && ll >= 1 && ll <= 8 && lp >= 1 && (o_tax | o_len) == 0u;
+            bool ok = a + q5 < e && p1 >= 1 && p2 - p1 >= 2 && q3 >= 1 && q3 <= 16 && ll >= 1 && ll <= 8 && lp >= 1 && (o_tax | o_len) == 0u;
             if (o_pid) {
                 ni = blu_ffs32(o_pid);
                 nf = lp - ni - 1;
@@ -887,7 +887,9 @@ BLU_HD uint32_t split_top_row_lean(const uint8_t* win, const uint32_t* tabw32, c
                 out.acc_off = lo + (uint64_t)(s + p1 + 1);
                 out.acc_len = (uint32_t)(p2 - p1 - 1);
                 out.pad = 0;
-                out.taxid = (int64_t)swar_digits(win, a, q3);
+                // staxid: up to 16 digits as (leading digits) * 10^8 + (last eight)
+                out.taxid = q3 <= 8 ? (int64_t)swar_digits(win, a, q3)
+                                    : (int64_t)((uint64_t)swar_digits(win, a, q3 - 8) * 100000000ull + (uint64_t)swar_digits(win, a + q3 - 8, 8));
                 out.alnlen = (int64_t)swar_digits(win, a + q4 + 1, ll);
                 uint32_t p10 = 1u;
                 for (int i = 0; i < nf; i++) p10 *= 10u;

@@ -328,8 +328,9 @@ __device__ __forceinline__ void finish_geom(WindowIndex& W, WinGeom& g, bool fin
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kSWarps = kTileThreads / 32;
 constexpr int kUnits = kTile / 32 + 1;       // 32-byte units of a window (+1: the unit that can hold a virtual final newline)
-constexpr int kUnitsPerWarp = ((kUnits + kSWarps - 1) / kSWarps + 31) & ~31;  // whole 32-lane rounds
-constexpr int kSegCap = kUnitsPerWarp * 2;   // row starts one warp can find (<= 1 per 16 bytes, else malformed)
+constexpr int kUnitsPerWarp = ((kTile / 32 + kSWarps - 1) / kSWarps + 31) & ~31;  // whole 32-lane rounds (the extra unit of a
+                                                                                   // virtual final newline goes to the last warp)
+constexpr int kSegCap = kUnitsPerWarp * 2 + 2;   // row starts one warp can find (<= 1 per 16 bytes, else malformed)
 constexpr int kSRowCap = kTile / 26 + 8;     // a valid row is >= 26 bytes
 constexpr int kRunBatch = 128;                // runs handled per pass of phases E/F
 constexpr int kTopCap = 512;                  // top rows a pass can queue (beyond: block path)
@@ -341,6 +342,7 @@ constexpr int kCarryTop = 32;                 // top rows of the open query kept
 static_assert(kSRowCap < 0x8000, "row indices are 15-bit");
 static_assert(kTile % 32 == 0 && kTile + 128 < 65536, "window offsets are 16-bit");
 static_assert(kSWarps <= 32, "per-warp tables are read by one warp");
+static_assert(kUnitsPerWarp * kSWarps >= kTile / 32, "the warps' shares cover the window");
 
 enum : uint8_t { RK_EMIT = 1, RK_DEFER = 2, RK_PSEUDO = 4, RK_OPEN = 8, RK_NEWCARRY = 16 };
 
@@ -604,6 +606,7 @@ __device__ __forceinline__ void flush_records(const RunParams& p, StreamSmem& S,
 #define PCLK(i)                                  \
     {                                            \
         long long _t;                            \
+        (void)*(volatile int*)&S.n_runs; /* a shared-memory access: the warp really is past the barrier */ \
         asm volatile("mov.u64 %0, %%clock64;" : "=l"(_t)::"memory"); \
         pc[i] += _t - pt;                        \
         pt = _t;                                 \
@@ -691,7 +694,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
         // ---- phase B: classify + per-warp row starts ----------------------------------------------------------------
         {
             const int u0 = warp * kUnitsPerWarp;
-            const int u1 = u0 + kUnitsPerWarp < n_units ? u0 + kUnitsPerWarp : n_units;
+            const int u1 = (warp == kSWarps - 1 || u0 + kUnitsPerWarp > n_units) ? n_units : u0 + kUnitsPerWarp;
             if (!has_begin && tend == kTile && !virt_nl && kUnitsPerWarp * kSWarps == kTile / 32)
                 classify_share<true>(S, win, u0, u0 + kUnitsPerWarp, 0, tend, false, false, warp, lane);
             else
@@ -1081,7 +1084,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
         }
     }
 #ifdef BLU_PHASE_CLOCKS
-    if ((blockIdx.x == 7 || blockIdx.x == 200) && (lane == 0) && (warp == 0 || warp == 1 || warp == kSWarps - 1))
+    if ((blockIdx.x == 7 || blockIdx.x == 200) && (lane == 0))
         printf("cta %d warp %d windows %d | tma %lld B %lld bar1 %lld geom %lld D %lld bar2 %lld flush %lld E %lld bar3 %lld F %lld bar4 %lld\n", blockIdx.x, warp, n_win, pc[0] / (n_win + 1),
                pc[1] / (n_win + 1), pc[2] / (n_win + 1), pc[3] / (n_win + 1), pc[4] / (n_win + 1), pc[5] / (n_win + 1), pc[6] / (n_win + 1), pc[7] / (n_win + 1), pc[8] / (n_win + 1),
                pc[9] / (n_win + 1), pc[10] / (n_win + 1));
