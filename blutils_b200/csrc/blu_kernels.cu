@@ -332,11 +332,10 @@ constexpr int kUnitsPerWarp = ((kTile / 32 + kSWarps - 1) / kSWarps + 31) & ~31;
                                                                                    // virtual final newline goes to the last warp)
 constexpr int kSegCap = kUnitsPerWarp * 2 + 2;   // row starts one warp can find (<= 1 per 16 bytes, else malformed)
 constexpr int kSRowCap = kTile / 26 + 8;     // a valid row is >= 26 bytes
-constexpr int kRunBatch = 128;                // runs handled per pass of phases E/F
-constexpr int kTopCap = 512;                  // top rows a pass can queue (beyond: block path)
 constexpr int kRecFlush = 128;                // buffered record headers that trigger a flush (one global atomic)
-constexpr int kRecBuf = kRecFlush + kRunBatch;  // capacity of the record buffer
+constexpr int kRecBuf = 256;                  // capacity of the record buffer (beyond: the run reserves its record itself)
 constexpr uint32_t kSlotSlab = 1024;          // top-row slots a CTA reserves at a time (one global atomic)
+constexpr uint32_t kSlotLow = 128;            // a new slab is fetched at the end of a window that leaves fewer free slots
 constexpr int kCarryTop = 32;                 // top rows of the open query kept in shared memory (beyond: block path)
 
 static_assert(kSRowCap < 0x8000, "row indices are 15-bit");
@@ -344,7 +343,7 @@ static_assert(kTile % 32 == 0 && kTile + 128 < 65536, "window offsets are 16-bit
 static_assert(kSWarps <= 32, "per-warp tables are read by one warp");
 static_assert(kUnitsPerWarp * kSWarps >= kTile / 32, "the warps' shares cover the window");
 
-enum : uint8_t { RK_EMIT = 1, RK_DEFER = 2, RK_PSEUDO = 4, RK_OPEN = 8, RK_NEWCARRY = 16 };
+enum : uint32_t { RK_EMIT = 1, RK_DEFER = 2, RK_PSEUDO = 4, RK_OPEN = 8, RK_NEWCARRY = 16 };
 
 struct CarryRun {
     unsigned long long head_abs;  // offset of the open query's first row
@@ -361,7 +360,7 @@ struct StagedRec {
     unsigned long long abs;
     uint32_t qlen, nrows;
     int32_t mx;
-    uint32_t slot;  // first top-row slot (phase E: relative to the pass; phase F adds the pass's base)
+    uint32_t slot;  // first top-row slot
     uint32_t gtot;
     uint32_t pad;
 };
@@ -378,27 +377,17 @@ struct StreamSmem {
     uint8_t flags[kSRowCap];         // bit1: bit score does not fit int32
     uint32_t headw[(kSRowCap + kTileThreads) / 32 + 2];  // head flags, one bit per row (the row loop writes whole rounds)
     uint16_t runs[kSRowCap + 1];     // head rows in arrival order (bit 15: continuation of the carried query)
-    // one pass of runs
-    int32_t run_dst[kRunBatch];    // where this window's top rows of the run go: >= 0 offset inside the run's slots, < 0: carry tops[-1-dst]
-    uint16_t run_slot[kRunBatch];  // first slot of the run, relative to the pass
-    uint16_t run_t0[kRunBatch];
-    uint16_t run_gpart[kRunBatch];  // top rows of the run in this window (0 when they are not needed)
-    uint8_t run_kind[kRunBatch];
     StagedRec rec_buf[kRecBuf];  // record headers of finished queries, waiting for the next flush
-    uint16_t top_row[kTopCap];
-    uint16_t top_run[kTopCap];
     uint16_t stage[kSWarps][32];
     CarryRun carry[2];
     alignas(8) unsigned long long mbar[2];
     int warp_cnt[32], warp_first[32], warp_last[32];
     int bad_byte, has_blank, crowded;
-    int n_runs, next_run, n_top, n_skip, term, new_open;
-    uint32_t pass_need;  // records << 16 | slots of the pass
+    int n_runs, next_run, n_skip, term, new_open;
     uint32_t rec_base;
     uint32_t slot_cur, slot_end;  // the CTA's current slab of top-row slots: [slot_cur, slot_end) is free
     int rec_cnt;                  // record headers in rec_buf
     int out_ok;                   // 0: an output capacity was exceeded (the host grows the arrays and reruns)
-    int old_tops;  // top rows of the carried query that ends in this pass (they precede the window's own)
 };
 
 static_assert((sizeof(StreamSmem) + 1024) * kTileCtasPerSm <= 227 * 1024, "tile CTAs must fit one SM");
@@ -558,10 +547,32 @@ __device__ __forceinline__ void classify_share(StreamSmem& S, const uint8_t* win
     }
 }
 
+__device__ __forceinline__ void write_record(blu_record* dst, const StagedRec& sr) {
+    blu_record rec;
+    rec.query_off = sr.abs;
+    rec.query_len = sr.qlen;
+    rec.n_rows = sr.nrows;
+    rec.keep_mask = 0;
+    rec.perc_identity = 0.0;
+    rec.bit_score = (int64_t)sr.mx;
+    rec.ref_lineage = 0;
+    rec.slot_base = sr.slot;
+    rec.n_beans = 0;
+    rec.n_accessions = sr.gtot;  // size of the top group until the consensus kernel overwrites it
+    rec.status = 2;              // waiting for the consensus kernel
+    rec.single_match = 0;
+    rec.mutated = 0;
+    rec.reached_pos = 0;
+    rec.allowed_pos = -1;
+    rec.bean_level = 0;
+    rec.pad[0] = rec.pad[1] = 0;
+    *dst = rec;
+}
+
 // Flushes the buffered record headers: ONE global atomic reserves their (dense) place in the record array, then every
 // thread writes headers.  All threads of the CTA call; two barriers.
 __device__ __forceinline__ void flush_records(const RunParams& p, StreamSmem& S, int tid) {
-    const int n = S.rec_cnt;
+    const int n = S.rec_cnt < kRecBuf ? S.rec_cnt : kRecBuf;
     if (n == 0) return;
     if (tid == 0) {
         const unsigned long long rs = atomicAdd(&p.ctr->rec_slots, (unsigned long long)n << 32);
@@ -575,28 +586,7 @@ __device__ __forceinline__ void flush_records(const RunParams& p, StreamSmem& S,
     __syncthreads();
     if (S.out_ok) {
         const uint32_t rec_base = S.rec_base;
-        for (int i = tid; i < n; i += kTileThreads) {
-            const StagedRec sr = S.rec_buf[i];
-            blu_record rec;
-            rec.query_off = sr.abs;
-            rec.query_len = sr.qlen;
-            rec.n_rows = sr.nrows;
-            rec.keep_mask = 0;
-            rec.perc_identity = 0.0;
-            rec.bit_score = (int64_t)sr.mx;
-            rec.ref_lineage = 0;
-            rec.slot_base = sr.slot;
-            rec.n_beans = 0;
-            rec.n_accessions = sr.gtot;  // size of the top group until the consensus kernel overwrites it
-            rec.status = 2;              // waiting for the consensus kernel
-            rec.single_match = 0;
-            rec.mutated = 0;
-            rec.reached_pos = 0;
-            rec.allowed_pos = -1;
-            rec.bean_level = 0;
-            rec.pad[0] = rec.pad[1] = 0;
-            p.records[rec_base + i] = rec;
-        }
+        for (int i = tid; i < n; i += kTileThreads) write_record(p.records + rec_base + i, S.rec_buf[i]);
     }
     __syncthreads();
     if (tid == 0) S.rec_cnt = 0;
@@ -642,17 +632,25 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
         S.carry[0].open = S.carry[1].open = 0;
         S.bad_byte = INT_MAX;
         S.has_blank = S.crowded = 0;
-        S.n_runs = S.next_run = S.n_top = S.n_skip = S.term = S.new_open = 0;
-        S.pass_need = 0;
-        S.old_tops = 0;
-        S.slot_cur = S.slot_end = 0;
+        S.n_runs = S.next_run = S.n_skip = S.term = S.new_open = 0;
+        {
+            // the CTA's first slab of top-row slots
+            const unsigned long long rs = atomicAdd(&p.ctr->rec_slots, (unsigned long long)kSlotSlab);
+            S.slot_cur = (uint32_t)rs;
+            S.slot_end = (uint32_t)rs + kSlotSlab;
+        }
         S.rec_cnt = 0;
         S.out_ok = 1;
+        if ((unsigned long long)S.slot_end > (unsigned long long)p.slot_cap) {
+            S.out_ok = 0;
+            p.ctr->cap_overflow = 1;
+        }
     }
     for (int i = tid; i < 7; i += kTileThreads) S.tabm[kUnits + i] = S.digm[kUnits + i] = S.nlm[kUnits + i] = 0u;
     __syncthreads();
     uint32_t ph0 = 0, ph1 = 0;
     int cur = 0;  // which carry buffer holds the open query
+    int win_idx = 1;  // number of the window (epoch of S.new_open)
 
     unsigned long long lo = seg_lo > p.begin + kBack ? (seg_lo - kBack) & ~15ull : b16;
     if (lo < b16) lo = b16;
@@ -839,211 +837,191 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
         }
         __syncthreads();
         PCLK(5)
-        // ---- phases E / F, kRunBatch runs at a time -------------------------------------------------------------------
+        // ---- phase R: one warp per query run (dynamic queue) -----------------------------------------------------------
+        //   extent, best bit score, top rows (ballot compaction); the warp decides the run's fate (finished / still open /
+        //   block path), merges it with the carried query, reserves its output and splits + parses its own top rows
         const int n_runs = S.n_runs;
         const int r0 = S.n_skip;  // first row of this window the CTA had not seen
         const bool term = S.term != 0;
         const bool closes = covers_eof && p.final_chunk;  // the end of this window ends the open query
-        bool new_open = false;                            // a query that starts in this window stays open
-        for (int b0 = 0; b0 < n_runs; b0 += kRunBatch) {
-            const int nb = n_runs - b0 < kRunBatch ? n_runs - b0 : kRunBatch;
-            PCLK(6)
-            // ---- phase E: one warp per run ---------------------------------------------------------------------------
-            while (true) {
-                int j = 0;
-                if (lane == 0) j = atomicAdd(&S.next_run, 1);
-                j = __shfl_sync(FULL, j, 0);
-                if (j >= nb) break;
-                const int entry = S.runs[b0 + j];
-                const bool pseudo = (entry & 0x8000) != 0;
-                const int h = pseudo ? r0 : (entry & 0x7FFF);
-                int e = next_head(S, pseudo ? h : h + 1, n_complete, lane);
-                const bool open = e < 0;
-                if (open) e = n_complete;
-                if (e < h) e = h;
-                int mx = INT32_MIN;
-                bool ovf = false;
-                for (int r = h + lane; r < e; r += 32) {
-                    const int b = S.bits[r];
-                    mx = b > mx ? b : mx;
-                    ovf |= (S.flags[r] & 2) != 0;
-                }
-                mx = __reduce_max_sync(FULL, mx);
-                ovf = __any_sync(FULL, ovf);
-                int g = 0;
-                for (int b = h; b < e; b += 32) {
-                    const int r = b + lane;
-                    const bool top = r < e && S.bits[r] == mx;
-                    const unsigned bal = __ballot_sync(FULL, top);
-                    const int pos = g + __popc(bal & ((1u << lane) - 1u));
-                    if (top && pos < 32) S.stage[warp][pos] = (uint16_t)r;
-                    g += __popc(bal);
-                }
-                __syncwarp();
-                int t0 = 0;
-                if (g > 32 || ovf)
-                    ovf = true;
-                else if (g > 0) {
-                    if (lane == 0) t0 = atomicAdd(&S.n_top, g);
-                    t0 = __shfl_sync(FULL, t0, 0);
-                    if (t0 + g > kTopCap)
-                        ovf = true;  // the pass's top list is full: block path
-                    else if (lane < g) {
-                        S.top_row[t0 + lane] = S.stage[warp][lane];
-                        S.top_run[t0 + lane] = (uint16_t)j;
-                    }
-                }
-                if (lane == 0) {
-                    // what happens to the run
-                    const int rows_t = e - h;
-                    int g_part = ovf ? 0 : g, g_tot = 0, dst = 0;
-                    uint8_t kind = pseudo ? RK_PSEUDO : 0;
-                    unsigned long long abs;
-                    uint32_t qlen, nrows;
-                    if (pseudo) {
-                        CarryRun& C = S.carry[cur];
-                        if (ovf) C.deferred = 1;
-                        if (rows_t > 0 && !C.deferred) {
-                            if (mx > C.mx) {
-                                C.mx = mx;
-                                C.g = 0;
-                            } else if (mx < C.mx)
-                                g_part = 0;
-                            if (C.g + g_part > kCarryTop) C.deferred = 1;
-                        }
-                        if (C.deferred || rows_t == 0) g_part = 0;
-                        abs = C.head_abs, qlen = C.qlen, nrows = C.nrows + (uint32_t)rows_t;
-                        mx = C.mx;
-                        if (!open || closes) {
-                            kind |= C.deferred ? RK_DEFER : RK_EMIT;
-                            g_tot = C.g + g_part;
-                            dst = C.g;
-                            if (!C.deferred) S.old_tops = C.g;
-                            C.open = 0;
-                        } else if (covers_eof) {
-                            // the input continues in the next chunk: the whole query is carried over by the host
-                            atomicMin(&p.ctr->tail_start, C.head_abs);
-                            g_part = 0;
-                            C.open = 0;
-                        } else {
-                            kind |= RK_OPEN;
-                            C.nrows = nrows;
-                            dst = -1 - C.g;
-                            C.g += g_part;
-                        }
-                    } else {
-                        const int s = S.row_s[h];
-                        const int re = blank ? row_end_search(S, s, last_nl) : (int)S.row_s[h + 1] - 1;
-                        abs = lo + (unsigned long long)s;
-                        qlen = (uint32_t)(next_tab(tabw, s, re) - s);
-                        nrows = (uint32_t)rows_t;
-                        if (!open || closes) {
-                            kind |= ovf ? RK_DEFER : RK_EMIT;
-                            g_tot = g_part;
-                        } else if (covers_eof) {
-                            atomicMin(&p.ctr->tail_start, abs);
-                            g_part = 0;
-                        } else {
-                            // a query that starts in this window and does not end in it: it becomes the carried query
-                            CarryRun& C = S.carry[cur ^ 1];
-                            kind |= RK_OPEN | RK_NEWCARRY;
-                            C.open = 1;
-                            C.deferred = ovf ? 1 : 0;
-                            C.head_abs = abs;
-                            C.qlen = qlen;
-                            C.nrows = nrows;
+        PCLK(6)
+        while (true) {
+            int j = 0;
+            if (lane == 0) j = atomicAdd(&S.next_run, 1);
+            j = __shfl_sync(FULL, j, 0);
+            if (j >= n_runs) break;
+            const int entry = S.runs[j];
+            const bool pseudo = (entry & 0x8000) != 0;
+            const int h = pseudo ? r0 : (entry & 0x7FFF);
+            int e = next_head(S, pseudo ? h : h + 1, n_complete, lane);
+            const bool open = e < 0;
+            if (open) e = n_complete;
+            if (e < h) e = h;
+            int mx = INT32_MIN;
+            bool ovf = false;
+            for (int r = h + lane; r < e; r += 32) {
+                const int b = S.bits[r];
+                mx = b > mx ? b : mx;
+                ovf |= (S.flags[r] & 2) != 0;
+            }
+            mx = __reduce_max_sync(FULL, mx);
+            ovf = __any_sync(FULL, ovf);
+            int g = 0;
+            for (int b = h; b < e; b += 32) {
+                const int r = b + lane;
+                const bool top = r < e && S.bits[r] == mx;
+                const unsigned bal = __ballot_sync(FULL, top);
+                const int pos = g + __popc(bal & ((1u << lane) - 1u));
+                if (top && pos < 32) S.stage[warp][pos] = (uint16_t)r;
+                g += __popc(bal);
+            }
+            if (g > 32) ovf = true;
+            // ---- lane 0: what happens to the run ------------------------------------------------------------------------
+            uint32_t kind = 0, slot = 0;
+            int g_part = 0, dst = 0, n_old = 0;
+            if (lane == 0) {
+                const int rows_t = e - h;
+                g_part = ovf ? 0 : g;
+                int g_tot = 0;
+                kind = pseudo ? RK_PSEUDO : 0;
+                unsigned long long abs;
+                uint32_t qlen, nrows;
+                if (pseudo) {
+                    CarryRun& C = S.carry[cur];
+                    if (ovf) C.deferred = 1;
+                    if (rows_t > 0 && !C.deferred) {
+                        if (mx > C.mx) {
                             C.mx = mx;
-                            C.g = g_part;
-                            dst = -1;
-                            S.new_open = 1;
+                            C.g = 0;
+                        } else if (mx < C.mx)
+                            g_part = 0;
+                        if (C.g + g_part > kCarryTop) C.deferred = 1;
+                    }
+                    if (C.deferred || rows_t == 0) g_part = 0;
+                    abs = C.head_abs, qlen = C.qlen, nrows = C.nrows + (uint32_t)rows_t;
+                    mx = C.mx;
+                    if (!open || closes) {
+                        kind |= C.deferred ? RK_DEFER : RK_EMIT;
+                        g_tot = C.g + g_part;
+                        dst = C.g;
+                        n_old = C.deferred ? 0 : C.g;
+                        C.open = 0;
+                    } else if (covers_eof) {
+                        // the input continues in the next chunk: the whole query is carried over by the host
+                        atomicMin(&p.ctr->tail_start, C.head_abs);
+                        g_part = 0;
+                        C.open = 0;
+                    } else {
+                        kind |= RK_OPEN;
+                        C.nrows = nrows;
+                        dst = -1 - C.g;
+                        C.g += g_part;
+                    }
+                } else {
+                    const int s = S.row_s[h];
+                    int p1 = 0, p2 = 0;
+                    if (first_two_tabs(S.tabm, s, p1, p2))
+                        qlen = (uint32_t)p1;
+                    else {
+                        const int re = blank ? row_end_search(S, s, last_nl) : (int)S.row_s[h + 1] - 1;
+                        qlen = (uint32_t)(next_tab(tabw, s, re) - s);
+                    }
+                    abs = lo + (unsigned long long)s;
+                    nrows = (uint32_t)rows_t;
+                    if (!open || closes) {
+                        kind |= ovf ? RK_DEFER : RK_EMIT;
+                        g_tot = g_part;
+                    } else if (covers_eof) {
+                        atomicMin(&p.ctr->tail_start, abs);
+                        g_part = 0;
+                    } else {
+                        // a query that starts in this window and does not end in it: it becomes the carried query
+                        CarryRun& C = S.carry[cur ^ 1];
+                        kind |= RK_OPEN | RK_NEWCARRY;
+                        C.open = 1;
+                        C.deferred = ovf ? 1 : 0;
+                        C.head_abs = abs;
+                        C.qlen = qlen;
+                        C.nrows = nrows;
+                        C.mx = mx;
+                        C.g = g_part;
+                        dst = -1;
+                        S.new_open = win_idx;
+                    }
+                }
+                if (kind & RK_EMIT) {
+                    // top-row slots from the CTA's slab (or, when it is exhausted, straight from the global counter)
+                    if (g_tot > 0) {
+                        slot = atomicAdd(&S.slot_cur, (uint32_t)g_tot);
+                        if (slot + (uint32_t)g_tot > S.slot_end || slot + (uint32_t)g_tot < slot) {
+                            const unsigned long long rs = atomicAdd(&p.ctr->rec_slots, (unsigned long long)g_tot);
+                            slot = (uint32_t)rs;
+                            if ((rs & 0xFFFFFFFFull) + (unsigned long long)g_tot > (unsigned long long)p.slot_cap) {
+                                S.out_ok = 0;
+                                p.ctr->cap_overflow = 1;
+                            }
                         }
                     }
-                    if (kind & RK_EMIT) {
-                        // the run's place in the output of the pass (records << 16 | slots)
-                        const uint32_t o = atomicAdd(&S.pass_need, (1u << 16) | (uint32_t)g_tot);
-                        StagedRec sr;
-                        sr.abs = abs, sr.qlen = qlen, sr.nrows = nrows, sr.mx = mx, sr.gtot = (uint32_t)g_tot, sr.slot = o & 0xFFFFu, sr.pad = 0;
-                        S.rec_buf[S.rec_cnt + (int)(o >> 16)] = sr;
-                        S.run_slot[j] = (uint16_t)(o & 0xFFFFu);
-                    }
-                    if (kind & RK_DEFER) push_defer(p, abs, 0);
-                    S.run_t0[j] = (uint16_t)t0;
-                    S.run_gpart[j] = (uint16_t)g_part;
-                    S.run_dst[j] = dst;
-                    S.run_kind[j] = kind;
-                }
-                __syncwarp();
-            }
-            PCLK(7)
-            __syncthreads();
-            PCLK(8)
-            // ---- phase F: top rows (one thread each: field split + number parse) go straight to their slots ---------------
-            const uint32_t need = S.pass_need;
-            const int n_rec = (int)(need >> 16);
-            const uint32_t n_slot = need & 0xFFFFu;
-            if (S.new_open) new_open = true;
-            const int n_top = S.n_top < kTopCap ? S.n_top : kTopCap;
-            const int n_old = S.old_tops;
-            const int rec_cnt = S.rec_cnt;
-            // slots come from the CTA's slab; a new slab costs one global atomic (every few dozen windows)
-            uint32_t slot_base = S.slot_cur;
-            if (n_slot > S.slot_end - slot_base) {
-                __syncthreads();  // everyone has read the old slab
-                if (tid == 0) {
-                    const uint32_t slab = n_slot > kSlotSlab ? n_slot : kSlotSlab;
-                    const unsigned long long rs = atomicAdd(&p.ctr->rec_slots, (unsigned long long)slab);
-                    S.slot_cur = (uint32_t)rs;
-                    S.slot_end = (uint32_t)rs + slab;
-                    if ((rs & 0xFFFFFFFFull) + (unsigned long long)slab > (unsigned long long)p.slot_cap) {
-                        S.out_ok = 0;
-                        p.ctr->cap_overflow = 1;
+                    StagedRec sr;
+                    sr.abs = abs, sr.qlen = qlen, sr.nrows = nrows, sr.mx = mx, sr.gtot = (uint32_t)g_tot, sr.slot = slot, sr.pad = 0;
+                    const int ri = atomicAdd(&S.rec_cnt, 1);
+                    if (ri < kRecBuf)
+                        S.rec_buf[ri] = sr;
+                    else {
+                        // record buffer full (a window of very short queries): this record is reserved on its own
+                        const unsigned long long rs = atomicAdd(&p.ctr->rec_slots, 1ull << 32);
+                        if ((rs >> 32) < (unsigned long long)p.rec_cap)
+                            write_record(p.records + (rs >> 32), sr);
+                        else
+                            p.ctr->cap_overflow = 1;
                     }
                 }
-                __syncthreads();
-                slot_base = S.slot_cur;
+                if (kind & RK_DEFER) push_defer(p, abs, 0);
             }
+            kind = __shfl_sync(FULL, kind, 0);
+            slot = __shfl_sync(FULL, slot, 0);
+            g_part = __shfl_sync(FULL, g_part, 0);
+            dst = __shfl_sync(FULL, dst, 0);
+            n_old = __shfl_sync(FULL, n_old, 0);
             const bool ok = S.out_ok != 0;
-            for (int t = tid; t < n_top; t += kTileThreads) {
-                const int j = S.top_run[t];
-                const int k = t - (int)S.run_t0[j];
-                const uint8_t kind = S.run_kind[j];
-                if (k >= (int)S.run_gpart[j] || !(kind & (RK_EMIT | RK_OPEN))) continue;
-                const int r = S.top_row[t];
+            // ---- the run's top rows of this window: field split + number parse, one lane each ----------------------------------
+            if (lane < g_part && (kind & (RK_EMIT | RK_OPEN))) {
+                const int r = S.stage[warp][lane];
                 const int s = S.row_s[r];
-                const int e = blank ? row_end_search(S, s, last_nl) : (int)S.row_s[r + 1] - 1;
+                const int re = blank ? row_end_search(S, s, last_nl) : (int)S.row_s[r + 1] - 1;
                 TopRowRaw tr;
-                const uint32_t err = split_top_row_lean(win, S.tabm, S.digm, s, e, lo, tr);
-                if (err) {
+                const uint32_t err = split_top_row_lean(win, S.tabm, S.digm, s, re, lo, tr);
+                if (err)
                     report(p.ctr, err, lo + s);
-                    continue;
-                }
-                const int dst = S.run_dst[j];
-                if (kind & RK_EMIT) {
-                    if (ok) p.toprows[slot_base + S.run_slot[j] + (uint32_t)(dst + k)] = tr;
+                else if (kind & RK_EMIT) {
+                    if (ok) p.toprows[slot + (uint32_t)(dst + lane)] = tr;
                 } else
-                    S.carry[(kind & RK_NEWCARRY) ? (cur ^ 1) : cur].tops[-1 - dst + k] = tr;
+                    S.carry[(kind & RK_NEWCARRY) ? (cur ^ 1) : cur].tops[-1 - dst + lane] = tr;
             }
             // a carried query that ends here: its earlier top rows go in front of this window's
-            if (b0 == 0 && ok && tid < n_old) p.toprows[slot_base + S.run_slot[0] + tid] = S.carry[cur].tops[tid];
-            // the pass's record headers now know where their slots are
-            for (int i = tid; i < n_rec; i += kTileThreads) S.rec_buf[rec_cnt + i].slot += slot_base;
-            PCLK(9)
-            __syncthreads();
-            PCLK(10)
-            if (tid == 0) {
-                S.next_run = 0;
-                S.n_top = 0;
-                S.pass_need = 0;
-                S.old_tops = 0;
-                S.slot_cur = slot_base + n_slot;
-                S.rec_cnt = rec_cnt + n_rec;
-            }
-            if (rec_cnt + n_rec >= kRecFlush) {
-                __syncthreads();
-                flush_records(p, S, tid);
-            } else if (b0 + kRunBatch < n_runs)
-                __syncthreads();
+            if (lane < n_old && ok) p.toprows[slot + lane] = S.carry[cur].tops[lane];
+            __syncwarp();
         }
+        PCLK(7)
+        __syncthreads();
+        PCLK(8)
+        const bool new_open = S.new_open == win_idx;  // (an epoch, not a flag: nothing to reset)
+        const bool need_flush = S.rec_cnt >= kRecFlush;
+        if (tid == 0) {
+            S.next_run = 0;
+            // a new slab of slots when this one runs low (one global atomic every few dozen windows)
+            if (S.slot_end - S.slot_cur < kSlotLow || S.slot_cur > S.slot_end) {
+                const unsigned long long rs = atomicAdd(&p.ctr->rec_slots, (unsigned long long)kSlotSlab);
+                S.slot_cur = (uint32_t)rs;
+                S.slot_end = (uint32_t)rs + kSlotSlab;
+                if ((rs & 0xFFFFFFFFull) + (unsigned long long)kSlotSlab > (unsigned long long)p.slot_cap) {
+                    S.out_ok = 0;
+                    p.ctr->cap_overflow = 1;
+                }
+            }
+        }
+        if (need_flush) flush_records(p, S, tid);
+        PCLK(9)
         // ---- where next? -----------------------------------------------------------------------------------------------
         // The CTA is done when the window reached the end of the text, when a query that belongs to the next segment
         // started in it, or when nothing is open and the segment is exhausted.
@@ -1071,14 +1049,13 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
         own_from = lo + (unsigned long long)(last_nl + 1);
         lo = next_lo;
         buf ^= 1;
-        if (n_runs == 0) __syncthreads();  // (else: the barrier that ends the last pass) everyone has read the window's state
+        win_idx++;
         // reset the per-window state (published by the barrier behind phase B of the next window)
         if (tid == 0) {
             S.bad_byte = INT_MAX;
             S.has_blank = 0;
             S.n_skip = 0;
             S.term = 0;
-            S.new_open = 0;
             S.n_runs = open_now ? 1 : 0;
             S.runs[0] = 0x8000;  // the carried query continues (or ends) at the first new row
         }
