@@ -365,6 +365,18 @@ struct StagedRec {
     uint32_t pad;
 };
 
+struct WinDesc {  // what a window covers; written one window ahead, together with the request for its bytes
+    unsigned long long lo;  // text offset of win[0] (16-byte aligned)
+    int loaded, tend, vb;   // bytes staged; end / begin of the text inside the window
+    int flags;              // 1: the window reaches the end of the text, 2: it contains the first byte of the text
+};
+
+struct WinGeo {  // row geometry of a window; written by the last warp that leaves phase B
+    unsigned long long next_lo;
+    int n_starts, n_complete, last_nl, may_continue, crowded;
+    int inc[32], nfirst[32], plast[32];  // per warp share: rows up to and including it; first row start behind / last before it
+};
+
 struct StreamSmem {
     alignas(128) uint8_t win[2][kTile + 128];
     // byte-class bitmasks, bit i of word u = byte 32u+i of the window (read by the row parsers as 32/64-bit words)
@@ -382,6 +394,9 @@ struct StreamSmem {
     CarryRun carry[2];
     alignas(8) unsigned long long mbar[2];
     int warp_cnt[32], warp_first[32], warp_last[32];
+    WinDesc wd[2];
+    WinGeo geo;
+    int b_done;  // warps that have finished phase B of the current window
     int bad_byte, has_blank, crowded;
     int n_runs, next_run, n_skip, term, new_open;
     uint32_t rec_base;
@@ -592,6 +607,20 @@ __device__ __forceinline__ void flush_records(const RunParams& p, StreamSmem& S,
     if (tid == 0) S.rec_cnt = 0;
 }
 
+// One thread: describes the window that starts at `lo` in S.wd[buf] and asks the TMA unit for its bytes.
+__device__ __forceinline__ void describe_and_load(StreamSmem& S, int buf, const RunParams& p, unsigned long long lo, unsigned long long up) {
+    const int loaded = (int)(up - lo < (unsigned long long)kTile ? up - lo : (unsigned long long)kTile);
+    WinDesc d;
+    d.lo = lo;
+    d.loaded = loaded;
+    d.tend = (int)(p.end - lo < (unsigned long long)loaded ? p.end - lo : (unsigned long long)loaded);
+    const bool has_begin = lo <= p.begin;
+    d.vb = has_begin ? (int)(p.begin - lo) : 0;
+    d.flags = (p.end <= lo + (unsigned long long)loaded ? 1 : 0) | (has_begin ? 2 : 0);
+    S.wd[buf] = d;
+    stream_issue_load(S, buf, p.text, lo, loaded);
+}
+
 #ifdef BLU_PHASE_CLOCKS
 #define PCLK(i)                                  \
     {                                            \
@@ -633,6 +662,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
         S.bad_byte = INT_MAX;
         S.has_blank = S.crowded = 0;
         S.n_runs = S.next_run = S.n_skip = S.term = S.new_open = 0;
+        S.b_done = 0;
         {
             // the CTA's first slab of top-row slots
             const unsigned long long rs = atomicAdd(&p.ctr->rec_slots, (unsigned long long)kSlotSlab);
@@ -651,23 +681,20 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
     uint32_t ph0 = 0, ph1 = 0;
     int cur = 0;  // which carry buffer holds the open query
     int win_idx = 1;  // number of the window (epoch of S.new_open)
-
-    unsigned long long lo = seg_lo > p.begin + kBack ? (seg_lo - kBack) & ~15ull : b16;
-    if (lo < b16) lo = b16;
     unsigned long long own_from = seg_lo;  // rows that start at or after this offset have not been processed yet
     int buf = 0;
     if (tid == 0) {
-        const unsigned long long n = up - lo < (unsigned long long)kTile ? up - lo : (unsigned long long)kTile;
-        stream_issue_load(S, 0, p.text, lo, (int)n);
+        unsigned long long lo0 = seg_lo > p.begin + kBack ? (seg_lo - kBack) & ~15ull : b16;
+        if (lo0 < b16) lo0 = b16;
+        describe_and_load(S, 0, p, lo0, up);
     }
+    __syncthreads();
 
     while (true) {
         const uint8_t* const win = S.win[buf];
-        const int loaded = (int)(up - lo < (unsigned long long)kTile ? up - lo : (unsigned long long)kTile);
-        const int tend = (int)(p.end - lo < (unsigned long long)loaded ? p.end - lo : (unsigned long long)loaded);
-        const bool covers_eof = p.end <= lo + (unsigned long long)loaded;
-        const bool has_begin = lo <= p.begin;  // the window contains the first byte of the text
-        const int vb = has_begin ? (int)(p.begin - lo) : 0;
+        const unsigned long long lo = S.wd[buf].lo;
+        const int tend = S.wd[buf].tend, vb = S.wd[buf].vb;
+        const bool covers_eof = (S.wd[buf].flags & 1) != 0, has_begin = (S.wd[buf].flags & 2) != 0;
         if (tid == 32) {
             // the window after the next one: start moving it from HBM to L2
             const unsigned long long nb = lo + 2ull * kTile - 512ull;
@@ -699,77 +726,100 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
                 classify_share<false>(S, win, u0, u1, vb, tend, has_begin, virt_nl, warp, lane);
         }
         PCLK(1)
-        if (tid < 4) S.tabm[n_units + tid] = S.digm[n_units + tid] = S.nlm[n_units + tid] = 0u;
+        // ---- row geometry of the window: computed ONCE, by the last warp that leaves phase B ------------------------------
+        {
+            int ticket = 0;
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                ticket = atomicAdd(&S.b_done, 1);
+            }
+            ticket = __shfl_sync(FULL, ticket, 0);
+            if (ticket == kSWarps - 1) {
+                __threadfence_block();
+                // lane i < kSWarps holds the tables of warp i's share
+                const int c_i = lane < kSWarps ? S.warp_cnt[lane] : 0;
+                int inc_i = c_i;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const int t = __shfl_up_sync(FULL, inc_i, d);
+                    if (lane >= d) inc_i += t;
+                }
+                const int n_starts = __shfl_sync(FULL, inc_i, 31);
+                const unsigned ne = __ballot_sync(FULL, c_i > 0);
+                const unsigned below = ne & ((1u << lane) - 1u), above = lane >= 31 ? 0u : (ne & (~0u << (lane + 1)));
+                const int wl = lane < kSWarps ? S.warp_last[lane] : -1, wf = lane < kSWarps ? S.warp_first[lane] : -1;
+                int plast_i = __shfl_sync(FULL, wl, below ? 31 - __clz(below) : 0);
+                if (!below) plast_i = -1;
+                int nfirst_i = __shfl_sync(FULL, wf, above ? __ffs(above) - 1 : 0);
+                if (!above) nfirst_i = -1;
+                int last_start = __shfl_sync(FULL, wl, ne ? 31 - __clz(ne) : 0);
+                if (!ne) last_start = -1;
+                int last_nl = -1;  // last newline of the window
+                for (int ub = n_units - 1; ub >= 0 && last_nl < 0; ub -= 32) {
+                    const int u = ub - lane;
+                    const uint32_t w = u >= 0 ? S.nlm[u] : 0u;
+                    const unsigned bal = __ballot_sync(FULL, w != 0);
+                    if (bal) {
+                        const int src = __ffs(bal) - 1;
+                        const uint32_t wv = __shfl_sync(FULL, w, src);
+                        last_nl = ((ub - src) << 5) + 31 - __clz(wv);
+                    }
+                }
+                const int n_complete = (n_starts > 0 && last_start > last_nl) ? n_starts - 1 : n_starts;
+                // the last complete row: the look-behind row of the next window
+                int lc = last_start;
+                if (n_complete != n_starts) {
+                    const int wlast = 31 - __clz(ne);  // (ne != 0: n_starts > 0)
+                    const int cl = __shfl_sync(FULL, c_i, wlast);
+                    const unsigned rest = ne & ~(1u << wlast);
+                    const int w2 = rest ? 31 - __clz(rest) : 0;
+                    const int c2 = __shfl_sync(FULL, c_i, w2);
+                    lc = cl >= 2 ? (int)S.seg[wlast][cl - 2] : (rest ? (int)S.seg[w2][c2 - 1] : -1);
+                }
+                const bool crowded = S.crowded != 0 || n_starts > kSRowCap;
+                const bool progress = lc >= 0 && lo + (unsigned long long)lc >= own_from;  // a complete row this CTA had not seen yet
+                unsigned long long next_lo = lo;
+                if (progress) {
+                    const unsigned long long la = lo + (unsigned long long)lc;
+                    next_lo = la > p.begin ? (la - 1) & ~15ull : b16;
+                    if (next_lo < b16) next_lo = b16;
+                }
+                const bool may_continue = progress && !covers_eof && next_lo > lo && !crowded;
+                if (lane < kSWarps) {
+                    S.geo.inc[lane] = inc_i;
+                    S.geo.nfirst[lane] = nfirst_i;
+                    S.geo.plast[lane] = plast_i;
+                }
+                if (lane < 4) S.tabm[n_units + lane] = S.digm[n_units + lane] = S.nlm[n_units + lane] = 0u;
+                if (lane == 0) {
+                    S.geo.next_lo = next_lo;
+                    S.geo.n_starts = n_starts;
+                    S.geo.n_complete = n_complete;
+                    S.geo.last_nl = last_nl;
+                    S.geo.may_continue = may_continue ? 1 : 0;
+                    S.geo.crowded = crowded ? 1 : 0;
+                    S.b_done = 0;
+                    if (n_complete == n_starts && n_starts <= kSRowCap) S.row_s[n_starts] = (uint16_t)(last_nl + 1);  // sentinel: end of the last row
+                    // the next window: starts just in front of the last complete row; its bytes are requested now
+                    if (may_continue) describe_and_load(S, buf ^ 1, p, next_lo, up);
+                }
+            }
+        }
         __syncthreads();
         PCLK(2)
-        // ---- row geometry of the window (every warp derives it from the per-warp tables) -----------------------------
-        // lane i < kSWarps holds the tables of warp i: row count, inclusive prefix, first start of the next non-empty
-        // share, last start of the previous one
-        int c_i, inc_i, nfirst_i, plast_i, n_starts, last_start;
-        {
-            c_i = lane < kSWarps ? S.warp_cnt[lane] : 0;
-            inc_i = c_i;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int t = __shfl_up_sync(FULL, inc_i, d);
-                if (lane >= d) inc_i += t;
-            }
-            n_starts = __shfl_sync(FULL, inc_i, 31);
-            const unsigned ne = __ballot_sync(FULL, c_i > 0);
-            const unsigned below = ne & ((1u << lane) - 1u), above = lane >= 31 ? 0u : (ne & (~0u << (lane + 1)));
-            const int wl = lane < kSWarps ? S.warp_last[lane] : -1, wf = lane < kSWarps ? S.warp_first[lane] : -1;
-            plast_i = __shfl_sync(FULL, wl, below ? 31 - __clz(below) : 0);
-            if (!below) plast_i = -1;
-            nfirst_i = __shfl_sync(FULL, wf, above ? __ffs(above) - 1 : 0);
-            if (!above) nfirst_i = -1;
-            last_start = __shfl_sync(FULL, wl, ne ? 31 - __clz(ne) : 0);
-            if (!ne) last_start = -1;
-        }
-        int last_nl = -1;  // last newline of the window
-        for (int ub = n_units - 1; ub >= 0 && last_nl < 0; ub -= 32) {
-            const int u = ub - lane;
-            const uint32_t w = u >= 0 ? S.nlm[u] : 0u;
-            const unsigned bal = __ballot_sync(FULL, w != 0);
-            if (bal) {
-                const int src = __ffs(bal) - 1;
-                const uint32_t wv = __shfl_sync(FULL, w, src);
-                last_nl = ((ub - src) << 5) + 31 - __clz(wv);
-            }
-        }
-        const bool crowded = S.crowded != 0 || n_starts > kSRowCap;
+        const int n_starts = S.geo.n_starts, n_complete = S.geo.n_complete, last_nl = S.geo.last_nl;
+        const bool may_continue = S.geo.may_continue != 0;
         const bool blank = S.has_blank != 0;
-        const int bad_byte = S.bad_byte;
-        const int n_complete = (n_starts > 0 && last_start > last_nl) ? n_starts - 1 : n_starts;
-        if (crowded) {
+        if (S.geo.crowded) {
             // a row shorter than 16 bytes / more rows than 26-byte rows fit: malformed input
             if (tid == 0) report(p.ctr, DE_BAD_FIELD_COUNT, lo);
-            break;  // (no copy in flight: the next window has not been requested yet)
+            break;  // (no copy in flight: the next window has not been requested)
         }
-        if (bad_byte != INT_MAX && tid == 0) report(p.ctr, DE_QUOTE_OR_CR, lo + (unsigned)bad_byte);
-        // next window: starts just in front of the last complete row (the look-behind row of the next window)
-        int lc = last_start;
-        if (n_complete != n_starts) {
-            // the last start is an unterminated row; the last complete row is the start before it
-            const unsigned ne = __ballot_sync(FULL, c_i > 0);
-            const int wlast = 31 - __clz(ne);  // (ne != 0: n_starts > 0)
-            const int cl = __shfl_sync(FULL, c_i, wlast);
-            const unsigned rest = ne & ~(1u << wlast);
-            const int w2 = rest ? 31 - __clz(rest) : 0;
-            const int c2 = __shfl_sync(FULL, c_i, w2);
-            lc = cl >= 2 ? (int)S.seg[wlast][cl - 2] : (rest ? (int)S.seg[w2][c2 - 1] : -1);
-        }
-        const bool progress = lc >= 0 && lo + (unsigned long long)lc >= own_from;  // a complete row this CTA had not seen yet
-        unsigned long long next_lo = lo;
-        if (progress) {
-            const unsigned long long la = lo + (unsigned long long)lc;
-            next_lo = la > p.begin ? (la - 1) & ~15ull : b16;
-            if (next_lo < b16) next_lo = b16;
-        }
-        const bool may_continue = progress && !covers_eof && next_lo > lo;
-        if (tid == 0 && may_continue) {
-            const unsigned long long n = up - next_lo < (unsigned long long)kTile ? up - next_lo : (unsigned long long)kTile;
-            stream_issue_load(S, buf ^ 1, p.text, next_lo, (int)n);
-        }
+        if (tid == 0 && S.bad_byte != INT_MAX) report(p.ctr, DE_QUOTE_OR_CR, lo + (unsigned)S.bad_byte);
+        const int c_i = lane < kSWarps ? S.warp_cnt[lane] : 0;
+        const int inc_i = lane < kSWarps ? S.geo.inc[lane] : n_starts;
+        const int nfirst_i = S.geo.nfirst[lane & (kSWarps - 1)], plast_i = S.geo.plast[lane & (kSWarps - 1)];
         const uint64_t* tabw = reinterpret_cast<const uint64_t*>(S.tabm);
         const uint64_t* digw = reinterpret_cast<const uint64_t*>(S.digm);
         PCLK(3)
@@ -832,9 +882,6 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
             if (sb && lane == 0) atomicAdd(&S.n_skip, __popc(sb));
         }
         PCLK(4)
-        if (tid == 0) {
-            if (n_complete == n_starts) S.row_s[n_starts] = (uint16_t)(last_nl + 1);  // sentinel: end of the last row
-        }
         __syncthreads();
         PCLK(5)
         // ---- phase R: one warp per query run (dynamic queue) -----------------------------------------------------------
@@ -1047,7 +1094,6 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
         n_win++;
 #endif
         own_from = lo + (unsigned long long)(last_nl + 1);
-        lo = next_lo;
         buf ^= 1;
         win_idx++;
         // reset the per-window state (published by the barrier behind phase B of the next window)
