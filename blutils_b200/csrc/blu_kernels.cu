@@ -433,10 +433,10 @@ __device__ __forceinline__ uint32_t pack32(const uint32_t (&f)[8]) {
 }
 
 // Exact byte-wise classification of one 32-byte unit: text edges (bytes outside [vb, tend) are not text), units with
-// non-ASCII bytes, and the exact '"' / '\r' search behind the cheap "suspicious byte" test.
-__device__ __noinline__ void classify_unit_slow(StreamSmem& S, const uint8_t* w, int pos0, int vb, int tend, uint32_t& nl, uint32_t& tab,
-                                                uint32_t& dig) {
-    nl = tab = dig = 0;
+// non-ASCII bytes, and the exact '"' / '\r' search behind the cheap "suspicious byte" test.  Publishes the unit's tab /
+// digit / newline masks when `publish` is set and returns the newline mask.
+__device__ __noinline__ uint32_t classify_unit_slow(StreamSmem& S, const uint8_t* w, int pos0, int vb, int tend, int virt_nl_at, bool publish) {
+    uint32_t nl = 0, tab = 0, dig = 0;
     int bad = INT_MAX;
     for (int k = 0; k < 32; k++) {
         const int pos = pos0 + k;
@@ -448,6 +448,14 @@ __device__ __noinline__ void classify_unit_slow(StreamSmem& S, const uint8_t* w,
         if ((c == '"' || c == '\r') && pos < bad) bad = pos;
     }
     if (bad != INT_MAX) atomicMin(&S.bad_byte, bad);
+    if (virt_nl_at >= pos0 && virt_nl_at < pos0 + 32) nl |= 1u << (virt_nl_at - pos0);
+    if (publish) {
+        const int u = pos0 >> 5;
+        S.tabm[u] = tab;
+        S.digm[u] = dig;
+        S.nlm[u] = nl;
+    }
+    return nl;
 }
 
 // first head row at index >= from, or -1 (whole warp)
@@ -492,7 +500,7 @@ __device__ __forceinline__ void classify_share(StreamSmem& S, const uint8_t* win
     for (int base = u0; base < u1; base += 32) {
         const int u = base + lane;
         const int pos0 = u << 5;
-        uint32_t nl = 0, tab = 0, dig = 0;
+        uint32_t nl = 0;
         const bool live = kInterior || u < u1;
         const bool edge = !kInterior && ((has_begin && pos0 <= vb) || pos0 + 32 > tend);  // first / last bytes of the text
         if (live) {
@@ -501,15 +509,17 @@ __device__ __forceinline__ void classify_share(StreamSmem& S, const uint8_t* win
             const uint32_t x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
             const uint32_t hi = (x[0] | x[1] | x[2] | x[3] | x[4] | x[5] | x[6] | x[7]) & 0x80808080u;
             if (__builtin_expect(edge || hi != 0, 0)) {
-                classify_unit_slow(S, win, pos0, vb, tend, nl, tab, dig);
-                if (virt_nl && tend >= pos0 && tend < pos0 + 32) nl |= 1u << (tend - pos0);
+                nl = classify_unit_slow(S, win, pos0, vb, tend, virt_nl ? tend : -1, true);
             } else {
                 // ASCII bytes: per-byte sums stay below 0x100, so plain 32-bit adds classify four bytes at once
                 uint32_t fn[8], ft[8], fd[8], sus = 0;
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    const uint32_t tu = (x[k] ^ 0x09090909u) + 0x7F7F7F7Fu;  // bit 7 clear <=> tab
-                    const uint32_t nu = (x[k] ^ 0x0A0A0A0Au) + 0x7F7F7F7Fu;  // bit 7 clear <=> newline
+                    uint32_t tu = (x[k] ^ 0x09090909u) + 0x7F7F7F7Fu;  // bit 7 clear <=> tab
+                    uint32_t nu = (x[k] ^ 0x0A0A0A0Au) + 0x7F7F7F7Fu;  // bit 7 clear <=> newline
+                    // (opaque to the optimiser: it would otherwise re-derive ~tu / ~nu with a second add per word)
+                    asm("" : "+r"(tu));
+                    asm("" : "+r"(nu));
                     const uint32_t ge30 = x[k] + 0x50505050u, ge3a = x[k] + 0x46464646u, ge23 = x[k] + 0x5D5D5D5Du;
                     ft[k] = ~tu & 0x80808080u;
                     fn[k] = ~nu & 0x80808080u;
@@ -517,16 +527,11 @@ __device__ __forceinline__ void classify_share(StreamSmem& S, const uint8_t* win
                     sus |= ~ge23 & tu & nu;  // below '#' and neither tab nor newline: look closer
                 }
                 nl = pack32(fn);
-                tab = pack32(ft);
-                dig = pack32(fd);
-                if (__builtin_expect((sus & 0x80808080u) != 0, 0)) {
-                    uint32_t a, b, c;
-                    classify_unit_slow(S, win, pos0, vb, tend, a, b, c);  // exact '"' / '\r' search
-                }
+                S.tabm[u] = pack32(ft);
+                S.digm[u] = pack32(fd);
+                S.nlm[u] = nl;
+                if (__builtin_expect((sus & 0x80808080u) != 0, 0)) classify_unit_slow(S, win, pos0, vb, tend, -1, false);  // exact '"' / '\r' search
             }
-            S.tabm[u] = tab;
-            S.digm[u] = dig;
-            S.nlm[u] = nl;
         }
         // row starts: a non-newline byte behind a newline (or behind the virtual newline in front of the text)
         const uint32_t upv = __shfl_up_sync(FULL, nl, 1);
