@@ -731,7 +731,9 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
                 classify_share<false>(S, win, u0, u1, vb, tend, has_begin, virt_nl, warp, lane);
         }
         PCLK(1)
-        // ---- row geometry of the window: computed ONCE, by the last warp that leaves phase B ------------------------------
+        // ---- row tables of the window: the prefix over the warps' shares is computed ONCE, by the last warp that leaves
+        //      phase B; everything else (last newline, next window) is worked out behind the barrier by the last warp of the
+        //      CTA, which normally has no rows in phase D, while the others already parse rows
         {
             int ticket = 0;
             __syncwarp();
@@ -758,39 +760,6 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
                 if (!below) plast_i = -1;
                 int nfirst_i = __shfl_sync(FULL, wf, above ? __ffs(above) - 1 : 0);
                 if (!above) nfirst_i = -1;
-                int last_start = __shfl_sync(FULL, wl, ne ? 31 - __clz(ne) : 0);
-                if (!ne) last_start = -1;
-                int last_nl = -1;  // last newline of the window
-                for (int ub = n_units - 1; ub >= 0 && last_nl < 0; ub -= 32) {
-                    const int u = ub - lane;
-                    const uint32_t w = u >= 0 ? S.nlm[u] : 0u;
-                    const unsigned bal = __ballot_sync(FULL, w != 0);
-                    if (bal) {
-                        const int src = __ffs(bal) - 1;
-                        const uint32_t wv = __shfl_sync(FULL, w, src);
-                        last_nl = ((ub - src) << 5) + 31 - __clz(wv);
-                    }
-                }
-                const int n_complete = (n_starts > 0 && last_start > last_nl) ? n_starts - 1 : n_starts;
-                // the last complete row: the look-behind row of the next window
-                int lc = last_start;
-                if (n_complete != n_starts) {
-                    const int wlast = 31 - __clz(ne);  // (ne != 0: n_starts > 0)
-                    const int cl = __shfl_sync(FULL, c_i, wlast);
-                    const unsigned rest = ne & ~(1u << wlast);
-                    const int w2 = rest ? 31 - __clz(rest) : 0;
-                    const int c2 = __shfl_sync(FULL, c_i, w2);
-                    lc = cl >= 2 ? (int)S.seg[wlast][cl - 2] : (rest ? (int)S.seg[w2][c2 - 1] : -1);
-                }
-                const bool crowded = S.crowded != 0 || n_starts > kSRowCap;
-                const bool progress = lc >= 0 && lo + (unsigned long long)lc >= own_from;  // a complete row this CTA had not seen yet
-                unsigned long long next_lo = lo;
-                if (progress) {
-                    const unsigned long long la = lo + (unsigned long long)lc;
-                    next_lo = la > p.begin ? (la - 1) & ~15ull : b16;
-                    if (next_lo < b16) next_lo = b16;
-                }
-                const bool may_continue = progress && !covers_eof && next_lo > lo && !crowded;
                 if (lane < kSWarps) {
                     S.geo.inc[lane] = inc_i;
                     S.geo.nfirst[lane] = nfirst_i;
@@ -798,23 +767,15 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
                 }
                 if (lane < 4) S.tabm[n_units + lane] = S.digm[n_units + lane] = S.nlm[n_units + lane] = 0u;
                 if (lane == 0) {
-                    S.geo.next_lo = next_lo;
                     S.geo.n_starts = n_starts;
-                    S.geo.n_complete = n_complete;
-                    S.geo.last_nl = last_nl;
-                    S.geo.may_continue = may_continue ? 1 : 0;
-                    S.geo.crowded = crowded ? 1 : 0;
+                    S.geo.crowded = (S.crowded != 0 || n_starts > kSRowCap) ? 1 : 0;
                     S.b_done = 0;
-                    if (n_complete == n_starts && n_starts <= kSRowCap) S.row_s[n_starts] = (uint16_t)(last_nl + 1);  // sentinel: end of the last row
-                    // the next window: starts just in front of the last complete row; its bytes are requested now
-                    if (may_continue) describe_and_load(S, buf ^ 1, p, next_lo, up);
                 }
             }
         }
         __syncthreads();
         PCLK(2)
-        const int n_starts = S.geo.n_starts, n_complete = S.geo.n_complete, last_nl = S.geo.last_nl;
-        const bool may_continue = S.geo.may_continue != 0;
+        const int n_starts = S.geo.n_starts;
         const bool blank = S.has_blank != 0;
         if (S.geo.crowded) {
             // a row shorter than 16 bytes / more rows than 26-byte rows fit: malformed input
@@ -824,7 +785,50 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
         if (tid == 0 && S.bad_byte != INT_MAX) report(p.ctr, DE_QUOTE_OR_CR, lo + (unsigned)S.bad_byte);
         const int c_i = lane < kSWarps ? S.warp_cnt[lane] : 0;
         const int inc_i = lane < kSWarps ? S.geo.inc[lane] : n_starts;
-        const int nfirst_i = S.geo.nfirst[lane & (kSWarps - 1)], plast_i = S.geo.plast[lane & (kSWarps - 1)];
+        const int nfirst_i = lane < kSWarps ? S.geo.nfirst[lane] : -1, plast_i = lane < kSWarps ? S.geo.plast[lane] : -1;
+        if (warp == kSWarps - 1) {
+            // ---- last newline, last complete row, the next window (its bytes are requested now) ---------------------------
+            const unsigned ne = __ballot_sync(FULL, c_i > 0);
+            int last_start = __shfl_sync(FULL, lane < kSWarps ? S.warp_last[lane] : -1, ne ? 31 - __clz(ne) : 0);
+            if (!ne) last_start = -1;
+            int last_nl = -1;
+            for (int ub = n_units - 1; ub >= 0 && last_nl < 0; ub -= 32) {
+                const int u = ub - lane;
+                const uint32_t w = u >= 0 ? S.nlm[u] : 0u;
+                const unsigned bal = __ballot_sync(FULL, w != 0);
+                if (bal) {
+                    const int src = __ffs(bal) - 1;
+                    const uint32_t wv = __shfl_sync(FULL, w, src);
+                    last_nl = ((ub - src) << 5) + 31 - __clz(wv);
+                }
+            }
+            const int n_complete = (n_starts > 0 && last_start > last_nl) ? n_starts - 1 : n_starts;
+            // the last complete row: the look-behind row of the next window
+            int lc = last_start;
+            if (n_complete != n_starts) {
+                const int wlast = 31 - __clz(ne);  // (ne != 0: n_starts > 0)
+                const int cl = __shfl_sync(FULL, c_i, wlast);
+                const unsigned rest = ne & ~(1u << wlast);
+                const int w2 = rest ? 31 - __clz(rest) : 0;
+                const int c2 = __shfl_sync(FULL, c_i, w2);
+                lc = cl >= 2 ? (int)S.seg[wlast][cl - 2] : (rest ? (int)S.seg[w2][c2 - 1] : -1);
+            }
+            if (lane == 0) {
+                const bool progress = lc >= 0 && lo + (unsigned long long)lc >= own_from;  // a complete row this CTA had not seen yet
+                unsigned long long next_lo = lo;
+                if (progress) {
+                    const unsigned long long la = lo + (unsigned long long)lc;
+                    next_lo = la > p.begin ? (la - 1) & ~15ull : b16;
+                    if (next_lo < b16) next_lo = b16;
+                }
+                const bool may_continue = progress && !covers_eof && next_lo > lo;
+                S.geo.n_complete = n_complete;
+                S.geo.last_nl = last_nl;
+                S.geo.may_continue = may_continue ? 1 : 0;
+                if (n_complete == n_starts) S.row_s[n_starts] = (uint16_t)(last_nl + 1);  // sentinel: end of the last row
+                if (may_continue) describe_and_load(S, buf ^ 1, p, next_lo, up);
+            }
+        }
         const uint64_t* tabw = reinterpret_cast<const uint64_t*>(S.tabm);
         const uint64_t* digw = reinterpret_cast<const uint64_t*>(S.digm);
         PCLK(3)
@@ -852,9 +856,12 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
                 const unsigned long long abs = lo + (unsigned long long)s;
                 if (abs < own_from)
                     skip = true;  // look-behind rows: seen by the previous window / owned by the previous segment
-                else if (r < n_complete) {
-                    const int nxt = k + 1 < cw ? (int)seg_w[k + 1] : (nf >= 0 ? nf : last_nl + 1);
-                    const int e = blank ? row_end_search(S, s, last_nl) : nxt - 1;
+                else {
+                    // the row's newline: in front of the next row start; the window's last start (and any row of a window
+                    // with blank lines) looks it up in the newline mask -- none: an unterminated row, left to the next window
+                    const int nxt = k + 1 < cw ? (int)seg_w[k + 1] : nf;
+                    const int e = (nxt < 0 || blank) ? row_end_search(S, s, scan_len) : nxt - 1;
+                    if (e >= scan_len) goto row_done;
                     int64_t bits;
                     int ql;
                     if (!parse_row_lean(win, S.tabm, S.digm, s, e, bits, ql)) {
@@ -881,6 +888,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
                     }
                 }
             }
+        row_done:
             const unsigned hb = __ballot_sync(FULL, head);
             if (lane == 0) S.headw[r >> 5] = hb;
             const unsigned sb = __ballot_sync(FULL, skip);
@@ -892,6 +900,8 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
         // ---- phase R: one warp per query run (dynamic queue) -----------------------------------------------------------
         //   extent, best bit score, top rows (ballot compaction); the warp decides the run's fate (finished / still open /
         //   block path), merges it with the carried query, reserves its output and splits + parses its own top rows
+        const int n_complete = S.geo.n_complete, last_nl = S.geo.last_nl;
+        const bool may_continue = S.geo.may_continue != 0;
         const int n_runs = S.n_runs;
         const int r0 = S.n_skip;  // first row of this window the CTA had not seen
         const bool term = S.term != 0;
