@@ -12,6 +12,7 @@
 //   rank selection / filtering ...... build_blast_consensus_identity.rs:9-105, linnaean_ranks.rs:174-212
 //   bean folding .................... consensus_result.rs:65-88
 #pragma once
+#include <string.h>
 #include <stdint.h>
 
 #include "../../include/blu_consensus.h"
@@ -793,13 +794,26 @@ BLU_HD uint32_t heavy_parse_row(const uint8_t* p, int len, uint64_t row_abs_off,
 // A top-group row as the tile kernel emits it: numbers parsed, lineage not joined yet (the consensus kernel probes
 // the taxid table, where full occupancy hides the lookup latency).
 struct TopRowRaw {
-    double pident;
+    double pident;     // (or, when dec_frac != 0, its decimal form: see toprow_pident)
     int64_t alnlen;
     uint64_t acc_off;  // absolute offset of saccver in the text buffer
     int64_t taxid;
     uint32_t acc_len;
-    uint32_t pad;
+    uint32_t dec_frac;  // 0: `pident` is the value; 0x80000000 | nf: the 8 bytes of `pident` hold the decimal mantissa m
+                        // (low word) of a `ddd.fff` literal with nf fraction digits, value = m / 10^nf -- the tile kernel
+                        // leaves that one IEEE division to the consensus kernel
 };
+
+// value of a raw top row's pident: the exact Clinger path (mantissa < 2^53, one correctly rounded division), the same
+// arithmetic parse_f64_short() performs
+BLU_HD double toprow_pident(const TopRowRaw& raw) {
+    if (!(raw.dec_frac & 0x80000000u)) return raw.pident;
+    uint64_t bits;
+    memcpy(&bits, &raw.pident, 8);
+    const uint32_t m = (uint32_t)bits;
+    const int nf = (int)(raw.dec_frac & 0xFFu);
+    return nf > 0 ? (double)m / kPow10[nf] : (double)m;
+}
 
 // digits-only unsigned integer of at most 9 digits (the common staxid / length): 32-bit arithmetic
 BLU_HD bool parse_u32_short(const uint8_t* p, int len, int64_t& v) {
@@ -848,7 +862,7 @@ BLU_HD uint32_t split_top_row(const uint8_t* win, const uint64_t* tabw, int s, i
     const int alen = t1 - t0 - 1;
     if (alen > 65535) return DE_NUM_UNSUPPORTED;
     out.acc_len = (uint32_t)alen;
-    out.pad = 0;
+    out.dec_frac = 0;
     if (!parse_u32_short(win + t1 + 1, t2 - t1 - 1, out.taxid) && !parse_i64(win + t1 + 1, t2 - t1 - 1, out.taxid)) return DE_BAD_NUMBER;
     if (!parse_f64_short(win + t2 + 1, t3 - t2 - 1, out.pident)) {
         uint32_t er = parse_f64(win + t2 + 1, t3 - t2 - 1, out.pident);
@@ -886,7 +900,6 @@ BLU_HD uint32_t split_top_row_lean(const uint8_t* win, const uint32_t* tabw32, c
             if (ok) {
                 out.acc_off = lo + (uint64_t)(s + p1 + 1);
                 out.acc_len = (uint32_t)(p2 - p1 - 1);
-                out.pad = 0;
                 // staxid: up to 16 digits as (leading digits) * 10^8 + (last eight)
                 out.taxid = q3 <= 8 ? (int64_t)swar_digits(win, a, q3)
                                     : (int64_t)((uint64_t)swar_digits(win, a, q3 - 8) * 100000000ull + (uint64_t)swar_digits(win, a + q3 - 8, 8));
@@ -894,7 +907,11 @@ BLU_HD uint32_t split_top_row_lean(const uint8_t* win, const uint32_t* tabw32, c
                 uint32_t p10 = 1u;
                 for (int i = 0; i < nf; i++) p10 *= 10u;
                 const uint32_t mant = swar_digits(win, a + q3 + 1, ni) * p10 + swar_digits(win, a + q3 + 2 + ni, nf);
-                out.pident = nf > 0 ? (double)mant / kPow10[nf] : (double)mant;
+                {
+                    const uint64_t dec = (uint64_t)mant;  // decimal form: the division is left to toprow_pident()
+                    memcpy(&out.pident, &dec, 8);
+                    out.dec_frac = 0x80000000u | (uint32_t)nf;
+                }
                 return DE_NONE;
             }
         }
@@ -904,7 +921,7 @@ BLU_HD uint32_t split_top_row_lean(const uint8_t* win, const uint32_t* tabw32, c
 
 // the join: taxid -> lineage (mod.rs:72-76); a miss / unparsable lineage in a top group is what makes the reference panic
 BLU_HD uint32_t join_top_row(const TopRowRaw& raw, const LinTables& T, TopRow& out) {
-    out.pident = raw.pident;
+    out.pident = toprow_pident(raw);
     out.alnlen = raw.alnlen;
     out.acc_off = raw.acc_off;
     out.acc_len = (uint16_t)raw.acc_len;

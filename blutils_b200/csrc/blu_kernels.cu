@@ -388,7 +388,7 @@ struct StreamSmem {
     int32_t bits[kSRowCap];
     uint8_t flags[kSRowCap];         // bit1: bit score does not fit int32
     uint32_t headw[(kSRowCap + kTileThreads) / 32 + 2];  // head flags, one bit per row (the row loop writes whole rounds)
-    uint16_t runs[kSRowCap + 1];     // head rows in arrival order (bit 15: continuation of the carried query)
+    uint32_t runs[kSRowCap + 1];     // head rows in arrival order: row | id length << 16 (bit 15: continuation of the carried query)
     StagedRec rec_buf[kRecBuf];  // record headers of finished queries, waiting for the next flush
     uint16_t stage[kSWarps][32];
     CarryRun carry[2];
@@ -635,8 +635,16 @@ __device__ __forceinline__ void describe_and_load(StreamSmem& S, int buf, const 
         pc[i] += _t - pt;                        \
         pt = _t;                                 \
     }
+#define RCLK(i)                                  \
+    {                                            \
+        long long _t;                            \
+        asm volatile("mov.u64 %0, %%clock64;" : "=l"(_t)::"memory"); \
+        rc[i] += _t - rt;                        \
+        rt = _t;                                 \
+    }
 #else
 #define PCLK(i)
+#define RCLK(i)
 #endif
 
 __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(const __grid_constant__ RunParams p) {
@@ -646,6 +654,8 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
     long long pc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long pt = clock64();
     int n_win = 0;
+    long long rc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long rt = 0;
 #endif
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned FULL = 0xffffffffu;
@@ -882,7 +892,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
                     if (head) {
                         if (abs < seg_hi) {
                             const int i = atomicAdd(&S.n_runs, 1);
-                            S.runs[i] = (uint16_t)r;
+                            S.runs[i] = (uint32_t)r | ((uint32_t)(ql > 0xFFFF ? 0xFFFF : ql) << 16);
                         } else
                             S.term = 1;  // a query of the next segment starts here: this CTA ends with this window
                     }
@@ -907,37 +917,64 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
         const bool term = S.term != 0;
         const bool closes = covers_eof && p.final_chunk;  // the end of this window ends the open query
         PCLK(6)
-        while (true) {
-            int j = 0;
-            if (lane == 0) j = atomicAdd(&S.next_run, 1);
-            j = __shfl_sync(FULL, j, 0);
-            if (j >= n_runs) break;
-            const int entry = S.runs[j];
-            const bool pseudo = (entry & 0x8000) != 0;
-            const int h = pseudo ? r0 : (entry & 0x7FFF);
+#ifdef BLU_PHASE_CLOCKS
+        rt = clock64();
+#endif
+        for (int j = warp; j < n_runs; j += kSWarps) {
+            RCLK(0)
+            const uint32_t entry = S.runs[j];
+            const bool pseudo = (entry & 0x8000u) != 0;
+            const int h = pseudo ? r0 : (int)(entry & 0x7FFFu);
             int e = next_head(S, pseudo ? h : h + 1, n_complete, lane);
             const bool open = e < 0;
             if (open) e = n_complete;
             if (e < h) e = h;
+            RCLK(1)
             int mx = INT32_MIN;
             bool ovf = false;
-            for (int r = h + lane; r < e; r += 32) {
-                const int b = S.bits[r];
-                mx = b > mx ? b : mx;
-                ovf |= (S.flags[r] & 2) != 0;
-            }
-            mx = __reduce_max_sync(FULL, mx);
-            ovf = __any_sync(FULL, ovf);
             int g = 0;
-            for (int b = h; b < e; b += 32) {
-                const int r = b + lane;
-                const bool top = r < e && S.bits[r] == mx;
-                const unsigned bal = __ballot_sync(FULL, top);
-                const int pos = g + __popc(bal & ((1u << lane) - 1u));
-                if (top && pos < 32) S.stage[warp][pos] = (uint16_t)r;
-                g += __popc(bal);
+            if (e - h <= 64) {
+                // the usual case: the run's bit scores in two registers per lane, one pass over shared memory
+                const int ra = h + lane, rb2 = ra + 32;
+                int ba = INT32_MIN, bb = INT32_MIN;
+                if (ra < e) {
+                    ba = S.bits[ra];
+                    ovf = (S.flags[ra] & 2) != 0;
+                }
+                if (rb2 < e) {
+                    bb = S.bits[rb2];
+                    ovf |= (S.flags[rb2] & 2) != 0;
+                }
+                mx = __reduce_max_sync(FULL, ba > bb ? ba : bb);
+                ovf = __any_sync(FULL, ovf);
+                const bool ta = ra < e && ba == mx, tb = rb2 < e && bb == mx;
+                const unsigned bala = __ballot_sync(FULL, ta), balb = __ballot_sync(FULL, tb);
+                const unsigned lt = (1u << lane) - 1u;
+                const int na = __popc(bala);
+                const int pa = __popc(bala & lt), pb = na + __popc(balb & lt);
+                if (ta && pa < 32) S.stage[warp][pa] = (uint16_t)ra;
+                if (tb && pb < 32) S.stage[warp][pb] = (uint16_t)rb2;
+                g = na + __popc(balb);
+            } else {
+                for (int r = h + lane; r < e; r += 32) {
+                    const int b = S.bits[r];
+                    mx = b > mx ? b : mx;
+                    ovf |= (S.flags[r] & 2) != 0;
+                }
+                mx = __reduce_max_sync(FULL, mx);
+                ovf = __any_sync(FULL, ovf);
+                for (int b = h; b < e; b += 32) {
+                    const int r = b + lane;
+                    const bool top = r < e && S.bits[r] == mx;
+                    const unsigned bal = __ballot_sync(FULL, top);
+                    const int pos = g + __popc(bal & ((1u << lane) - 1u));
+                    if (top && pos < 32) S.stage[warp][pos] = (uint16_t)r;
+                    g += __popc(bal);
+                }
             }
+            __syncwarp();
             if (g > 32) ovf = true;
+            RCLK(2)
             // ---- lane 0: what happens to the run ------------------------------------------------------------------------
             uint32_t kind = 0, slot = 0;
             int g_part = 0, dst = 0, n_old = 0;
@@ -981,10 +1018,8 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
                     }
                 } else {
                     const int s = S.row_s[h];
-                    int p1 = 0, p2 = 0;
-                    if (first_two_tabs(S.tabm, s, p1, p2))
-                        qlen = (uint32_t)p1;
-                    else {
+                    qlen = entry >> 16;
+                    if (qlen == 0xFFFFu) {
                         const int re = blank ? row_end_search(S, s, last_nl) : (int)S.row_s[h + 1] - 1;
                         qlen = (uint32_t)(next_tab(tabw, s, re) - s);
                     }
@@ -1040,6 +1075,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
                 }
                 if (kind & RK_DEFER) push_defer(p, abs, 0);
             }
+            RCLK(3)
             kind = __shfl_sync(FULL, kind, 0);
             slot = __shfl_sync(FULL, slot, 0);
             g_part = __shfl_sync(FULL, g_part, 0);
@@ -1060,9 +1096,11 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
                 } else
                     S.carry[(kind & RK_NEWCARRY) ? (cur ^ 1) : cur].tops[-1 - dst + lane] = tr;
             }
+            RCLK(4)
             // a carried query that ends here: its earlier top rows go in front of this window's
             if (lane < n_old && ok) p.toprows[slot + lane] = S.carry[cur].tops[lane];
             __syncwarp();
+            RCLK(5)
         }
         PCLK(7)
         __syncthreads();
@@ -1070,7 +1108,6 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
         const bool new_open = S.new_open == win_idx;  // (an epoch, not a flag: nothing to reset)
         const bool need_flush = S.rec_cnt >= kRecFlush;
         if (tid == 0) {
-            S.next_run = 0;
             // a new slab of slots when this one runs low (one global atomic every few dozen windows)
             if (S.slot_end - S.slot_cur < kSlotLow || S.slot_cur > S.slot_end) {
                 const unsigned long long rs = atomicAdd(&p.ctr->rec_slots, (unsigned long long)kSlotSlab);
@@ -1126,6 +1163,9 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
         printf("cta %d warp %d windows %d | tma %lld B %lld bar1 %lld geom %lld D %lld bar2 %lld flush %lld E %lld bar3 %lld F %lld bar4 %lld\n", blockIdx.x, warp, n_win, pc[0] / (n_win + 1),
                pc[1] / (n_win + 1), pc[2] / (n_win + 1), pc[3] / (n_win + 1), pc[4] / (n_win + 1), pc[5] / (n_win + 1), pc[6] / (n_win + 1), pc[7] / (n_win + 1), pc[8] / (n_win + 1),
                pc[9] / (n_win + 1), pc[10] / (n_win + 1));
+    if ((blockIdx.x == 7) && (lane == 0))
+        printf("rcl %d warp %d windows %d | queue %lld head %lld stats %lld decide %lld parse %lld old %lld\n", blockIdx.x, warp, n_win, rc[0] / (n_win + 1), rc[1] / (n_win + 1),
+               rc[2] / (n_win + 1), rc[3] / (n_win + 1), rc[4] / (n_win + 1), rc[5] / (n_win + 1));
 #endif
     // ---- the record headers still in the buffer -------------------------------------------------------------------------
     __syncthreads();

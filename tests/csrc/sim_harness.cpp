@@ -151,7 +151,7 @@ extern "C" int blu_sim_run(const int64_t* taxids, const uint64_t* off, const cha
                         uint32_t erl = split_top_row_lean(tx, reinterpret_cast<const uint32_t*>(tabw.data()), reinterpret_cast<const uint32_t*>(digw.data()),
                                                           (int)rows[r].s, (int)rows[r].s + rows[r].len, 0, raw2);
                         if (erl != er || (!er && (raw2.acc_off != raw.acc_off || raw2.acc_len != raw.acc_len || raw2.taxid != raw.taxid ||
-                                                  raw2.alnlen != raw.alnlen || memcmp(&raw2.pident, &raw.pident, 8) != 0))) {
+                                                  raw2.alnlen != raw.alnlen || toprow_pident(raw2) != toprow_pident(raw)))) {
                             snprintf(err, errlen, "lean top-row splitter disagrees at byte %llu", (unsigned long long)rows[r].s);
                             return BLU_ERR_INTERNAL;
                         }
