@@ -634,72 +634,87 @@ BLU_HD bool first_two_tabs(const uint32_t* tabw32, int s, int& p1, int& p2) {
 }
 
 BLU_HD bool parse_row_lean(const uint8_t* win, const uint32_t* tabw32, const uint32_t* digw32, int s, int e, int64_t& bits, int& q_len) {
+    // Written without early exits: every check only clears `ok`, all indices are clamped so that every load stays inside
+    // the window whatever the row looks like.  The independent parts (first two tabs, head-aligned tail words,
+    // end-aligned word, the '.' bytes, the digit fold) can then overlap instead of waiting for one another's branches.
+    bool ok = e >= 32;
+    // ---- first two tabs (qseqid / saccver end inside the first 64 bytes) ---------------------------------------------
     int p1, p2;
-    if (e < 32 || !first_two_tabs(tabw32, s, p1, p2)) return false;
+    {
+        const int wi = s >> 5;
+        const uint32_t sh = (uint32_t)s & 31u;
+        const uint32_t w0 = tabw32[wi], w1 = tabw32[wi + 1], w2 = tabw32[wi + 2];
+        const uint32_t t0 = blu_funnel_r(w0, w1, sh), t1 = blu_funnel_r(w1, w2, sh);
+        const uint32_t t0b = t0 & (t0 - 1u), t1b = t1 & (t1 - 1u);
+        // first tab: in t0, else in t1; second: the next one after it
+        const uint32_t f1 = t0 ? t0 : t1;
+        const uint32_t f2 = t0 ? (t0b ? t0b : t1) : t1b;
+        ok = ok && f1 != 0u && f2 != 0u;
+        p1 = (t0 ? 0 : 32) + blu_ffs32(f1 | 0x80000000u);
+        p2 = ((t0 && t0b) ? 0 : 32) + blu_ffs32(f2 | 0x80000000u);
+    }
     const int a = s + p2 + 1;  // first byte of staxid
     const int m = e - a;       // bytes of the numeric tail
-    if (p1 < 1 || p2 - p1 < 2 || m < 21 || m > 64) return false;
-    // the tail through two head-aligned words (bytes a.., a+32..) and one end-aligned word (bytes e-32..e-1)
+    ok = ok && p1 >= 1 && p2 - p1 >= 2 && m >= 21 && m <= 64;
+    const int mc = m < 21 ? 21 : (m > 64 ? 64 : m);
+    // ---- the tail through two head-aligned words (bytes a.., a+32..) and one end-aligned word (bytes e-32..e-1) ------
     const int ai = a >> 5;
     const uint32_t ash = (uint32_t)a & 31u;
     const uint32_t x0 = tabw32[ai], x1 = tabw32[ai + 1], x2 = tabw32[ai + 2];
     const uint32_t y0 = digw32[ai], y1 = digw32[ai + 1], y2 = digw32[ai + 2];
-    const uint32_t m0 = m >= 32 ? 0xFFFFFFFFu : ((1u << m) - 1u);
-    const uint32_t m1 = m >= 64 ? 0xFFFFFFFFu : (m > 32 ? ((1u << (m - 32)) - 1u) : 0u);
+    const int eb = e >= 32 ? e - 32 : 0;
+    const uint32_t te_raw = bits_at(tabw32, eb), de_raw = bits_at(digw32, eb);
+    const uint32_t m0 = mc >= 32 ? 0xFFFFFFFFu : ((1u << mc) - 1u);
+    const uint32_t m1 = mc >= 64 ? 0xFFFFFFFFu : (mc > 32 ? ((1u << (mc - 32)) - 1u) : 0u);
     const uint32_t ta0 = blu_funnel_r(x0, x1, ash) & m0, ta1 = blu_funnel_r(x1, x2, ash) & m1;
     const uint32_t oa0 = ~(blu_funnel_r(y0, y1, ash) | ta0) & m0, oa1 = ~(blu_funnel_r(y1, y2, ash) | ta1) & m1;  // neither digit nor tab
-    if (blu_popc32(ta0) + blu_popc32(ta1) != 10) return false;
+    ok = ok && blu_popc32(ta0) + blu_popc32(ta1) == 10;
     // no empty field: no two adjacent tabs, no tab at either end of the tail
-    const uint32_t last = m > 32 ? (ta1 >> (m - 33)) : (ta0 >> (m - 1));
-    if ((ta0 & (ta0 << 1)) | (ta1 & ((ta1 << 1) | (ta0 >> 31))) | (ta0 & 1u) | (last & 1u)) return false;
+    const uint32_t last = mc > 32 ? (ta1 >> (mc - 33)) : (ta0 >> (mc - 1));
+    ok = ok && (((ta0 & (ta0 << 1)) | (ta1 & ((ta1 << 1) | (ta0 >> 31))) | (ta0 & 1u) | (last & 1u)) == 0u);
     // staxid / pident end inside the first 32 bytes of the tail
     const uint32_t ta0b = ta0 & (ta0 - 1u);
-    if (!ta0b) return false;
-    const int q3 = blu_ffs32(ta0), q4 = blu_ffs32(ta0b);
+    ok = ok && ta0b != 0u;
+    const int q3 = blu_ffs32(ta0 | 0x80000000u), q4 = blu_ffs32(ta0b | 0x80000000u);
     // evalue / bitscore start inside the last 32 bytes of the row
-    const int eb = e - 32;
-    const uint32_t me = m >= 32 ? 0xFFFFFFFFu : (0xFFFFFFFFu << (32 - m));  // bytes of the end-aligned word that belong to the tail
-    const uint32_t te = bits_at(tabw32, eb) & me;
-    const uint32_t oe_all = ~(bits_at(digw32, eb) | te) & me;
-    if (!te) return false;
-    const int q12e = 31 - blu_clz32(te);
-    const uint32_t te2 = te ^ (1u << q12e);
-    if (!te2) return false;
-    const int q11e = 31 - blu_clz32(te2);
-    const int q11 = m - 32 + q11e;  // tab in front of evalue, tail coordinates
+    const uint32_t me = mc >= 32 ? 0xFFFFFFFFu : (0xFFFFFFFFu << (32 - mc));  // bytes of the end-aligned word that belong to the tail
+    const uint32_t te = te_raw & me;
+    const uint32_t oe_all = ~(de_raw | te) & me;
+    const int q12e = 31 - blu_clz32(te | 1u);
+    const uint32_t te2 = te & ~(1u << q12e);
+    ok = ok && te != 0u && te2 != 0u && q12e < 31;
+    const int q11e = 31 - blu_clz32(te2 | 1u);
+    const int q11 = mc - 32 + q11e;  // tab in front of evalue, tail coordinates
     // integer columns <= 18 digits: staxid directly, length..send (7 fields, 6 tabs) through their total span
-    if (q3 > 18 || q11 - q4 - 1 > 30) return false;
+    ok = ok && q3 <= 18 && q11 - q4 - 1 <= 30;
     // non-digit bytes may only sit in pident and in evalue / bitscore: compare the counts
-    const uint32_t op = oa0 & ((1u << q4) - 1u) & ~((2u << q3) - 1u);
-    const uint32_t otail = oe_all & ~((2u << q11e) - 1u);
-    if (blu_popc32(oa0) + blu_popc32(oa1) != blu_popc32(op) + blu_popc32(otail)) return false;
+    const uint32_t op = oa0 & ((1u << (q4 & 31)) - 1u) & ~((2u << (q3 & 31)) - 1u);
+    const uint32_t otail = oe_all & ~((2u << (q11e & 31)) - 1u);
+    ok = ok && blu_popc32(oa0) + blu_popc32(oa1) == blu_popc32(op) + blu_popc32(otail);
     // pident: digits with at most one '.', at least one digit
-    if (op) {
-        if (op & (op - 1u)) return false;
-        if (q4 - q3 - 1 < 2 || win[a + blu_ffs32(op)] != '.') return false;
-    }
-    // evalue: one of the common float shapes, else the DFA
-    const int l_ev = q12e - q11e - 1;
     {
-        const uint32_t oe = (oe_all >> (q11e + 1)) & ((1u << l_ev) - 1u);
-        if (oe && !float_shape_ok(win + eb + q11e + 1, l_ev, oe) && !check_float(win + eb + q11e + 1, l_ev)) return false;
+        const uint8_t c = win[a + blu_ffs32(op | 0x80000000u)];
+        ok = ok && (op == 0u || ((op & (op - 1u)) == 0u && q4 - q3 - 1 >= 2 && c == '.'));
     }
     // bit score: digits[.digits], <= 15 digits in total (trunc(value) is then exactly the integer part), <= 8 of them
     // in front of the point
     const int l_bits = 31 - q12e;
-    if (l_bits > 16) return false;
-    const uint32_t ob = q12e < 31 ? (oe_all >> (q12e + 1)) : 0u;
-    int n_int = l_bits;
-    if (ob) {
-        if (ob & (ob - 1u)) return false;
-        n_int = blu_ffs32(ob);
-        if (l_bits < 2 || win[eb + q12e + 1 + n_int] != '.') return false;
-    } else if (l_bits > 15)
-        return false;
-    if (n_int > 8) return false;
-    bits = (int64_t)swar_digits(win, eb + q12e + 1, n_int);
+    const uint32_t ob = q12e < 31 ? (oe_all >> ((q12e + 1) & 31)) : 0u;
+    const int n_int = ob ? blu_ffs32(ob) : l_bits;
+    {
+        const uint8_t c = win[eb + q12e + 1 + (n_int & 31)];
+        ok = ok && (ob ? ((ob & (ob - 1u)) == 0u && l_bits >= 2 && l_bits <= 16 && c == '.') : l_bits <= 15) && n_int <= 8;
+    }
+    const uint32_t v = swar_digits(win, eb + q12e + 1, n_int > 8 ? 8 : n_int);
+    // evalue: one of the common float shapes, else the DFA
+    const int l_ev = q12e - q11e - 1;
+    if (ok) {
+        const uint32_t oe = (oe_all >> (q11e + 1)) & ((1u << l_ev) - 1u);
+        if (oe && !float_shape_ok(win + eb + q11e + 1, l_ev, oe) && !check_float(win + eb + q11e + 1, l_ev)) ok = false;
+    }
+    bits = (int64_t)v;
     q_len = p1;
-    return true;
+    return ok;
 }
 
 // first fields (qseqid) of the rows starting at a and b are equal
