@@ -335,7 +335,7 @@ constexpr int kSRowCap = kTile / 26 + 8;     // a valid row is >= 26 bytes
 constexpr int kRecFlush = 128;                // buffered record headers that trigger a flush (one global atomic)
 constexpr int kRecBuf = 256;                  // capacity of the record buffer (beyond: the run reserves its record itself)
 constexpr uint32_t kSlotSlab = 1024;          // top-row slots a CTA reserves at a time (one global atomic)
-constexpr uint32_t kSlotLow = 128;            // a new slab is fetched at the end of a window that leaves fewer free slots
+constexpr uint32_t kSlotLow = 64;             // a new slab is fetched at the end of a window that leaves fewer free slots
 constexpr int kCarryTop = 32;                 // top rows of the open query kept in shared memory (beyond: block path)
 
 static_assert(kSRowCap < 0x8000, "row indices are 15-bit");
@@ -402,6 +402,7 @@ struct StreamSmem {
     uint32_t rec_base;
     uint32_t slot_cur, slot_end;  // the CTA's current slab of top-row slots: [slot_cur, slot_end) is free
     int rec_cnt;                  // record headers in rec_buf
+    uint32_t slots_taken;         // slots this CTA has reserved in slabs so far (sizes the next slab)
     int out_ok;                   // 0: an output capacity was exceeded (the host grows the arrays and reruns)
 };
 
@@ -679,10 +680,13 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
         S.n_runs = S.next_run = S.n_skip = S.term = S.new_open = 0;
         S.b_done = 0;
         {
-            // the CTA's first slab of top-row slots
-            const unsigned long long rs = atomicAdd(&p.ctr->rec_slots, (unsigned long long)kSlotSlab);
+            // the CTA's first slab of top-row slots (about 40 per window of the segment, at most kSlotSlab)
+            const unsigned long long est = ((seg_hi - seg_lo) / (unsigned long long)kTile + 1ull) * 40ull + (unsigned long long)kSlotLow;
+            const uint32_t slab = est < (unsigned long long)kSlotSlab ? (uint32_t)est : kSlotSlab;
+            const unsigned long long rs = atomicAdd(&p.ctr->rec_slots, (unsigned long long)slab);
             S.slot_cur = (uint32_t)rs;
-            S.slot_end = (uint32_t)rs + kSlotSlab;
+            S.slot_end = (uint32_t)rs + slab;
+            S.slots_taken = slab;
         }
         S.rec_cnt = 0;
         S.out_ok = 1;
@@ -1110,10 +1114,16 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
         if (tid == 0) {
             // a new slab of slots when this one runs low (one global atomic every few dozen windows)
             if (S.slot_end - S.slot_cur < kSlotLow || S.slot_cur > S.slot_end) {
-                const unsigned long long rs = atomicAdd(&p.ctr->rec_slots, (unsigned long long)kSlotSlab);
+                // sized by what the rest of the segment is likely to need (slots used per window so far x windows left), so that
+                // the unused tail of a CTA's last slab -- a hole in slot space that is downloaded with the results -- stays small
+                const unsigned long long left = seg_hi > lo ? (seg_hi - lo) / (unsigned long long)kTile + 1ull : 1ull;
+                const unsigned long long est = (unsigned long long)(S.slots_taken / (uint32_t)win_idx + 8u) * left + (unsigned long long)kSlotLow;
+                const uint32_t slab = est < (unsigned long long)kSlotSlab ? (uint32_t)est : kSlotSlab;
+                S.slots_taken += slab;
+                const unsigned long long rs = atomicAdd(&p.ctr->rec_slots, (unsigned long long)slab);
                 S.slot_cur = (uint32_t)rs;
-                S.slot_end = (uint32_t)rs + kSlotSlab;
-                if ((rs & 0xFFFFFFFFull) + (unsigned long long)kSlotSlab > (unsigned long long)p.slot_cap) {
+                S.slot_end = (uint32_t)rs + slab;
+                if ((rs & 0xFFFFFFFFull) + (unsigned long long)slab > (unsigned long long)p.slot_cap) {
                     S.out_ok = 0;
                     p.ctr->cap_overflow = 1;
                 }
