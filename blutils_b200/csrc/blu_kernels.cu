@@ -1,13 +1,14 @@
 // blu_kernels.cu -- hand-written sm_100a kernels of the consensus-identity path.
 //
-//   tile_kernel    : the dominant, HBM-bound kernel.  One CTA stages a ~61 KB window of outfmt-6 text into shared
-//                    memory with TMA bulk copies (cp.async.bulk + mbarrier), builds the row index with 16-byte
-//                    SIMD-in-register newline masks + warp prefix sums, validates/parses every row, finds query
-//                    runs and their top bit-score group, joins the top rows with the lineage tables (taxid hash
-//                    probe in HBM/L2) and emits one consensus record per query.  Text is read from HBM once;
-//                    nothing per-row is ever written back to HBM.
-//   longrun_kernel : block-per-query path for queries that do not fit a tile window (long-tail / straddlers),
-//                    whose top group exceeds one warp, or that touch the end of a streamed chunk.
+//   tile_kernel    : the dominant kernel (streaming).  Every CTA walks one contiguous segment of the outfmt-6 text in
+//                    32 KB windows staged by TMA bulk copies (cp.async.bulk + mbarrier, double-buffered), classifies
+//                    the bytes with SIMD-in-register tests (newline / tab / digit bitmasks, dp4a packing), indexes
+//                    the rows, validates / parses every row, finds query runs and their top bit-score group --
+//                    carrying the unfinished query from window to window -- and emits one record header plus the
+//                    parsed top rows per query.  Text is read from HBM once; nothing per-row is written back.
+//   consensus_kernel: one warp per query: taxid join, multi-taxa consensus, cutoffs (reads the tile kernel's output).
+//   longrun_kernel : block-per-query path for the few queries the tile kernel hands over (top group of more than 32
+//                    rows, bit score beyond int32, first row without a predecessor in its window).
 //   gather_kernel  : copies query ids and accessions of finished queries into the result's string pool.
 //   dup_kernel     : detects a query id that occurs in two separate runs (non-contiguous input).
 //
@@ -23,11 +24,7 @@ namespace blu {
 
 namespace {
 
-constexpr int kWarps = kTileThreads / 32;
 constexpr int kRowCap = kWin / 26 + 16;   // a valid row is >= 26 bytes (13 one-byte fields, 12 tabs, '\n')
-constexpr int kMaxRuns = kRowCap;           // owned heads <= rows in the window
-constexpr int kTopList = 768;             // top rows a tile can queue (beyond: block path)
-constexpr int kTileQ = 384;               // queries a tile can queue (beyond: block path)
 constexpr int kLongTopCap = 1024;         // largest top bit-score group the block path sorts
 constexpr int kLongThreads = 512;
 constexpr int kLongWarps = kLongThreads / 32;
