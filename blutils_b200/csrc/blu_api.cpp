@@ -292,6 +292,14 @@ void check_device_error(blu_ctx*, const Counters& h, uint64_t stream_base) {
     throw DataErr(m);
 }
 
+// BLU_SYNC_DEBUG=1: synchronise behind every kernel so that a device fault is attributed to the kernel that caused it
+inline void dbg_sync(cudaStream_t s, const char* what) {
+    static const bool on = getenv("BLU_SYNC_DEBUG") != nullptr;
+    if (!on) return;
+    cudaError_t e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
 // Runs the kernels on one resident chunk.  rec_begin = number of records before this chunk.
 void launch_chunk(blu_ctx* c, const uint8_t* dtext, uint64_t begin, uint64_t end, bool final_chunk, const Caps& k, cudaStream_t s,
                   uint32_t rec_begin_hint, bool time_it) {
@@ -314,8 +322,10 @@ void launch_chunk(blu_ctx* c, const uint8_t* dtext, uint64_t begin, uint64_t end
     (void)rec_begin_hint;
     if (time_it) CK(cudaEventRecord(c->ev[0], s));
     CK(launch_tile_kernel(p, tile_kernel_grid(c->device), s));
+    dbg_sync(s, "tile_kernel");
     if (time_it) CK(cudaEventRecord(c->ev[1], s));
     CK(launch_longrun_kernel(p, c->sms, s));
+    dbg_sync(s, "longrun_kernel");
     if (time_it) CK(cudaEventRecord(c->ev[2], s));
     c->tm.n_kernel_launches += 2;
 }
@@ -404,7 +414,7 @@ float ev_ms(cudaEvent_t a, cudaEvent_t b) {
 }
 
 // Post-pass on all records of the run: string gather for [rec_begin, rec_end) + (at the end) duplicate check.
-void launch_gather(blu_ctx* c, const uint8_t* dtext, uint32_t rec_begin, uint32_t rec_end, const Caps& k, cudaStream_t s) {
+void launch_gather(blu_ctx* c, const uint8_t* dtext, uint64_t text_end, uint32_t rec_begin, uint32_t rec_end, const Caps& k, cudaStream_t s) {
     {
         // warp-per-query consensus over the top-row table the tile kernel produced for these records
         ConsParams q{};
@@ -415,10 +425,12 @@ void launch_gather(blu_ctx* c, const uint8_t* dtext, uint32_t rec_begin, uint32_
         q.beans = c->d_beans.p;
         q.accs = c->d_accs.p;
         q.text = dtext;
+        q.text_end = text_end;
         q.T = c->dT;
         q.strategy = c->opts.strategy;
         q.ctr = c->d_ctr;
         CK(launch_consensus_kernel(q, s));
+        dbg_sync(s, "consensus_kernel");
         if (rec_end > rec_begin) c->tm.n_kernel_launches += 1;
     }
     GatherParams g{};
@@ -431,6 +443,7 @@ void launch_gather(blu_ctx* c, const uint8_t* dtext, uint32_t rec_begin, uint32_
     g.pool_cap = k.pool;
     g.ctr = c->d_ctr;
     CK(launch_gather_kernel(g, s));
+    dbg_sync(s, "gather_kernel");
     if (rec_end > rec_begin) c->tm.n_kernel_launches += 1;
 }
 
@@ -444,10 +457,12 @@ void launch_dup(blu_ctx* c, uint32_t n_rec, cudaStream_t s) {
     d.records = c->d_rec.p;
     d.n_rec = n_rec;
     d.pool = c->d_pool.p;
+    d.pool_cap = c->d_pool.cap;
     d.table = c->d_dup.p;
     d.mask = (uint32_t)(cap - 1);
     d.ctr = c->d_ctr;
     CK(launch_dup_kernel(d, s));
+    dbg_sync(s, "dup_kernel");
     c->tm.n_kernel_launches += 1;
 }
 
@@ -559,7 +574,7 @@ void run_device(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStream_t s, bl
             }
             check_device_error(c, h, 0);
             CK(cudaEventRecord(c->ev[3], s));
-            launch_gather(c, dtext, rec_done, (uint32_t)n_rec_of(h), k, s);
+            launch_gather(c, dtext, end, rec_done, (uint32_t)n_rec_of(h), k, s);
             if (final_range) launch_dup(c, (uint32_t)n_rec_of(h), s);
             CK(cudaEventRecord(c->ev[4], s));
             rec_done = (uint32_t)n_rec_of(h);
@@ -669,7 +684,7 @@ void run_host(blu_ctx* c, const char* text, uint64_t n, blu_result* r) {
             }
             check_device_error(c, h, off - text_off);  // err_off is in buffer coordinates
             CK(cudaEventRecord(c->ev[3], s));
-            launch_gather(c, buf, rec_done, n_rec_of(h), k, s);
+            launch_gather(c, buf, end, rec_done, n_rec_of(h), k, s);
             CK(cudaEventRecord(c->ev[4], s));
             rec_done = n_rec_of(h);
             if (!final_chunk) {

@@ -607,33 +607,9 @@ BLU_HD uint32_t swar_digits(const uint8_t* win, int pos, int n) {
     return swar4((uint32_t)v) * 10000u + swar4((uint32_t)(v >> 32));
 }
 
-// positions of the first two tabs of the row at s (qseqid / saccver ends), relative to s; both must lie in the first 64 bytes
-BLU_HD bool first_two_tabs(const uint32_t* tabw32, int s, int& p1, int& p2) {
-    const int wi = s >> 5;
-    const uint32_t sh = (uint32_t)s & 31u;
-    const uint32_t w0 = tabw32[wi], w1 = tabw32[wi + 1];
-    const uint32_t t0 = blu_funnel_r(w0, w1, sh);
-    const uint32_t t0b = t0 & (t0 - 1u);
-    if (t0b) {  // the common case: both inside the first 32 bytes
-        p1 = blu_ffs32(t0);
-        p2 = blu_ffs32(t0b);
-        return true;
-    }
-    const uint32_t t1 = blu_funnel_r(w1, tabw32[wi + 2], sh);
-    if (t0) {
-        if (!t1) return false;
-        p1 = blu_ffs32(t0);
-        p2 = 32 + blu_ffs32(t1);
-        return true;
-    }
-    const uint32_t t1b = t1 & (t1 - 1u);
-    if (!t1b) return false;
-    p1 = 32 + blu_ffs32(t1);
-    p2 = 32 + blu_ffs32(t1b);
-    return true;
-}
+constexpr uint32_t kRowInfoValid = 0x80000000u;
 
-BLU_HD bool parse_row_lean(const uint8_t* win, const uint32_t* tabw32, const uint32_t* digw32, int s, int e, int64_t& bits, int& q_len) {
+BLU_HD bool parse_row_lean(const uint8_t* win, const uint32_t* tabw32, const uint32_t* digw32, int s, int e, int64_t& bits, int& q_len, uint32_t& info) {
     // Written without early exits: every check only clears `ok`, all indices are clamped so that every load stays inside
     // the window whatever the row looks like.  The independent parts (first two tabs, head-aligned tail words,
     // end-aligned word, the '.' bytes, the digit fold) can then overlap instead of waiting for one another's branches.
@@ -714,6 +690,13 @@ BLU_HD bool parse_row_lean(const uint8_t* win, const uint32_t* tabw32, const uin
     }
     bits = (int64_t)v;
     q_len = p1;
+    // where fields 1..4 sit (for the consensus kernel, should this be a top row): ends of qseqid / saccver relative to the
+    // row, ends of staxid / pident / length relative to the byte behind saccver's tab
+    {
+        const uint32_t ta0c = ta0b & (ta0b - 1u);
+        const int q5 = ta0c ? blu_ffs32(ta0c) : 32 + blu_ffs32(ta1 | 0x80000000u);
+        info = (ok && q5 < 64) ? (kRowInfoValid | (uint32_t)p1 | ((uint32_t)p2 << 6) | ((uint32_t)q3 << 12) | ((uint32_t)q4 << 17) | ((uint32_t)q5 << 22)) : 0u;
+    }
     return ok;
 }
 
@@ -814,10 +797,13 @@ struct TopRowRaw {
     uint64_t acc_off;  // absolute offset of saccver in the text buffer
     int64_t taxid;
     uint32_t acc_len;
-    uint32_t dec_frac;  // 0: `pident` is the value; 0x80000000 | nf: the 8 bytes of `pident` hold the decimal mantissa m
+    uint32_t dec_frac;  // 0: `pident` is the value; kTopRowUnparsed: nothing is parsed, acc_off / acc_len are the ROW's offset and
+                        // length (the consensus kernel runs heavy_parse_row on it); 0x80000000 | nf: the 8 bytes of `pident` hold the decimal mantissa m
                         // (low word) of a `ddd.fff` literal with nf fraction digits, value = m / 10^nf -- the tile kernel
                         // leaves that one IEEE division to the consensus kernel
 };
+
+constexpr uint32_t kTopRowUnparsed = 0x40000000u;
 
 // value of a raw top row's pident: the exact Clinger path (mantissa < 2^53, one correctly rounded division), the same
 // arithmetic parse_f64_short() performs
@@ -887,51 +873,38 @@ BLU_HD uint32_t split_top_row(const uint8_t* win, const uint64_t* tabw, int s, i
     return DE_NONE;
 }
 
-// The streaming kernel's top-row splitter: same result as split_top_row() for the common shapes -- saccver within the
-// first 64 bytes, staxid of at most 16 and length of at most 8 digits, pident `ddd[.ddd]` with at most 9 digits -- computed from two
-// mask words and SWAR digit folds (no per-byte loops, short dependency chain); anything else goes through
-// split_top_row().
-BLU_HD uint32_t split_top_row_lean(const uint8_t* win, const uint32_t* tabw32, const uint32_t* digw32, int s, int e, uint64_t lo, TopRowRaw& out) {
-    int p1, p2;
-    if (first_two_tabs(tabw32, s, p1, p2)) {
-        const int a = s + p2 + 1;
-        const uint32_t ta = bits_at(tabw32, a), da = bits_at(digw32, a);
-        const uint32_t tb = ta & (ta - 1u), tc = tb & (tb - 1u);
-        if (tc) {
-            const int q3 = blu_ffs32(ta), q4 = blu_ffs32(tb), q5 = blu_ffs32(tc);
-            const int lp = q4 - q3 - 1, ll = q5 - q4 - 1;
-            const uint32_t nd = ~da;
-            const uint32_t o_tax = nd & ((1u << q3) - 1u);
-            const uint32_t o_pid = (nd >> (q3 + 1)) & ((1u << lp) - 1u);
-            const uint32_t o_len = (nd >> (q4 + 1)) & ((1u << ll) - 1u);
-            int ni = lp, nf = 0;
-            bool ok = a + q5 < e && p1 >= 1 && p2 - p1 >= 2 && q3 >= 1 && q3 <= 16 && ll >= 1 && ll <= 8 && lp >= 1 && (o_tax | o_len) == 0u;
-            if (o_pid) {
-                ni = blu_ffs32(o_pid);
-                nf = lp - ni - 1;
-                ok = ok && !(o_pid & (o_pid - 1u)) && win[a + q3 + 1 + ni] == '.';
-            }
-            ok = ok && ni <= 8 && nf <= 8 && ni + nf >= 1 && ni + nf <= 9;
-            if (ok) {
-                out.acc_off = lo + (uint64_t)(s + p1 + 1);
-                out.acc_len = (uint32_t)(p2 - p1 - 1);
-                // staxid: up to 16 digits as (leading digits) * 10^8 + (last eight)
-                out.taxid = q3 <= 8 ? (int64_t)swar_digits(win, a, q3)
-                                    : (int64_t)((uint64_t)swar_digits(win, a, q3 - 8) * 100000000ull + (uint64_t)swar_digits(win, a + q3 - 8, 8));
-                out.alnlen = (int64_t)swar_digits(win, a + q4 + 1, ll);
-                uint32_t p10 = 1u;
-                for (int i = 0; i < nf; i++) p10 *= 10u;
-                const uint32_t mant = swar_digits(win, a + q3 + 1, ni) * p10 + swar_digits(win, a + q3 + 2 + ni, nf);
-                {
-                    const uint64_t dec = (uint64_t)mant;  // decimal form: the division is left to toprow_pident()
-                    memcpy(&out.pident, &dec, 8);
-                    out.dec_frac = 0x80000000u | (uint32_t)nf;
-                }
-                return DE_NONE;
-            }
-        }
+// Fields 1..4 of a validated row whose tab positions are known (packed by parse_row_lean) -- the tile kernel's top-row
+// splitter: no tab search, SWAR digit folds for staxid (<= 16 digits), length (<= 8) and pident's decimal mantissa
+// (`ddd[.ddd]`, <= 9 digits; the division is left to toprow_pident() in the consensus kernel).  Returns false for any
+// other shape (the caller then emits the row unparsed).  Same values as split_top_row() (checked row by row in
+// tests/csrc/sim_harness.cpp).
+BLU_HD bool top_row_from_info(const uint8_t* win, const uint32_t* digw32, int s, uint32_t info, uint64_t lo, TopRowRaw& out) {
+    const int p1 = (int)(info & 63u), p2 = (int)((info >> 6) & 63u), q3 = (int)((info >> 12) & 31u), q4 = (int)((info >> 17) & 31u),
+              q5 = (int)((info >> 22) & 63u);
+    const int a = s + p2 + 1;
+    const int lp = q4 - q3 - 1, ll = q5 - q4 - 1;
+    const uint32_t nd = ~bits_at(digw32, a);
+    const uint32_t o_pid = (nd >> (q3 + 1)) & ((1u << lp) - 1u);  // (staxid and length are digits only: parse_row_lean checked)
+    int ni = lp, nf = 0;
+    bool ok = (info & kRowInfoValid) != 0u && q3 <= 16 && q5 < 32 && ll <= 8;
+    if (o_pid) {
+        ni = blu_ffs32(o_pid);
+        nf = lp - ni - 1;
+        ok = ok && !(o_pid & (o_pid - 1u));  // (the one non-digit byte is a '.': parse_row_lean checked)
     }
-    return split_top_row(win, reinterpret_cast<const uint64_t*>(tabw32), s, e, lo, out);
+    ok = ok && ni <= 8 && nf <= 8 && ni + nf >= 1 && ni + nf <= 9;
+    if (!ok) return false;
+    out.acc_off = lo + (uint64_t)(s + p1 + 1);
+    out.acc_len = (uint32_t)(p2 - p1 - 1);
+    out.taxid = q3 <= 8 ? (int64_t)swar_digits(win, a, q3)
+                        : (int64_t)((uint64_t)swar_digits(win, a, q3 - 8) * 100000000ull + (uint64_t)swar_digits(win, a + q3 - 8, 8));
+    out.alnlen = (int64_t)swar_digits(win, a + q4 + 1, ll);
+    uint32_t p10 = 1u;
+    for (int i = 0; i < nf; i++) p10 *= 10u;
+    const uint64_t dec = (uint64_t)(swar_digits(win, a + q3 + 1, ni) * p10 + swar_digits(win, a + q3 + 2 + ni, nf));
+    memcpy(&out.pident, &dec, 8);
+    out.dec_frac = 0x80000000u | (uint32_t)nf;
+    return true;
 }
 
 // the join: taxid -> lineage (mod.rs:72-76); a miss / unparsable lineage in a top group is what makes the reference panic

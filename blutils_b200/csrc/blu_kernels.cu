@@ -350,7 +350,7 @@ struct CarryRun {
     int32_t g;         // top rows so far (kept in tops[])
     int32_t open;
     int32_t deferred;  // the query goes to the block path when it ends (top group too large / bit score beyond int32)
-    TopRowRaw tops[kCarryTop];
+    TopRowRaw tops[kCarryTop];  // its top rows so far
 };
 
 struct StagedRec {
@@ -384,6 +384,7 @@ struct StreamSmem {
     uint16_t row_s[kSRowCap + 2];    // all row starts of the window (written by phase D)
     int32_t bits[kSRowCap];
     uint8_t flags[kSRowCap];         // bit1: bit score does not fit int32
+    uint32_t rowinfo[kSRowCap];      // packed tab positions of the row (parse_row_lean), 0: unknown
     uint32_t headw[(kSRowCap + kTileThreads) / 32 + 2];  // head flags, one bit per row (the row loop writes whole rounds)
     uint32_t runs[kSRowCap + 1];     // head rows in arrival order: row | id length << 16 (bit 15: continuation of the carried query)
     StagedRec rec_buf[kRecBuf];  // record headers of finished queries, waiting for the next flush
@@ -875,12 +876,15 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
                     if (e >= scan_len) goto row_done;
                     int64_t bits;
                     int ql;
-                    if (!parse_row_lean(win, S.tabm, S.digm, s, e, bits, ql)) {
+                    uint32_t info;
+                    if (!parse_row_lean(win, S.tabm, S.digm, s, e, bits, ql, info)) {
                         const LightRow lr = parse_row_masked(win, tabw, digw, s, e);
                         if (lr.err) report(p.ctr, lr.err, abs);
                         bits = lr.bits;
                         ql = lr.q_len;
+                        info = 0;
                     }
+                    S.rowinfo[r] = info;
                     const int prv = k > 0 ? (int)seg_w[k - 1] : pl;
                     if (prv < 0) {
                         head = has_begin;  // first row of the text; else: predecessor not in the window
@@ -1088,14 +1092,20 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
                 const int r = S.stage[warp][lane];
                 const int s = S.row_s[r];
                 const int re = blank ? row_end_search(S, s, last_nl) : (int)S.row_s[r + 1] - 1;
-                TopRowRaw tr;
-                const uint32_t err = split_top_row_lean(win, S.tabm, S.digm, s, re, lo, tr);
-                if (err)
-                    report(p.ctr, err, lo + s);
-                else if (kind & RK_EMIT) {
-                    if (ok) p.toprows[slot + (uint32_t)(dst + lane)] = tr;
+                // a top row leaves the tile kernel as a reference into the text: the consensus kernel splits and parses it
+                // fields 1..4 through the tab positions the row phase found: digit folds only, no second tab search; a row of any
+                // other shape leaves unparsed (offset + length) and is split by the consensus kernel's full parser
+                TopRowRaw ref;
+                if (!top_row_from_info(win, S.digm, s, S.rowinfo[r], lo, ref)) {
+                    ref.acc_off = lo + (unsigned long long)s;
+                    ref.acc_len = (uint32_t)(re - s);
+                    ref.taxid = 0, ref.alnlen = 0, ref.pident = 0.0;
+                    ref.dec_frac = kTopRowUnparsed;
+                }
+                if (kind & RK_EMIT) {
+                    if (ok) p.toprows[slot + (uint32_t)(dst + lane)] = ref;
                 } else
-                    S.carry[(kind & RK_NEWCARRY) ? (cur ^ 1) : cur].tops[-1 - dst + lane] = tr;
+                    S.carry[(kind & RK_NEWCARRY) ? (cur ^ 1) : cur].tops[-1 - dst + lane] = ref;
             }
             RCLK(4)
             // a carried query that ends here: its earlier top rows go in front of this window's
@@ -1563,16 +1573,24 @@ __global__ void __launch_bounds__(256) consensus_kernel(const ConsParams p) {
     uint32_t pos0 = 0;
     uint32_t jerr = 0;
     if (on) {
-        // the join (left_join on subject_taxid == taxid, mod.rs:72-76): probe the taxid table
+        // the row as the tile kernel left it -- a reference into the text: fields 1..4 are split and parsed here (the row was
+        // validated by the tile kernel), then the join (left_join on subject_taxid == taxid, mod.rs:72-76) probes the taxid table
         const TopRowRaw raw = p.toprows[slot + lane];
-        jerr = join_top_row(raw, T, r);
+        unsigned long long off = raw.acc_off;
+        if (raw.dec_frac == kTopRowUnparsed) {
+            // a row of unusual shape: split and parsed here by the full parser (acc_off / acc_len are the row's)
+            jerr = off + (unsigned long long)raw.acc_len <= p.text_end ? heavy_parse_row(p.text + off, (int)raw.acc_len, off, T, r) : (uint32_t)DE_INTERNAL;
+        } else
+            jerr = join_top_row(raw, T, r);
         if (jerr)
-            report(p.ctr, jerr, raw.acc_off);
+            report(p.ctr, jerr, off);
         else
             pos0 = T.lin_off[r.lin];
     }
     if (__any_sync(FULL, jerr != 0)) {
-        if (lane == 0) rec->status = 0;
+        // (the run is over: the host reports the error; the record is emptied so that the gather / duplicate kernels that
+        // are already queued behind this one do not follow accession slots that were never filled)
+        if (lane == 0) rec->status = 0, rec->n_accessions = 0;
         return;
     }
     if (g == 1) {
@@ -1831,6 +1849,9 @@ __global__ void __launch_bounds__(256) dup_kernel(const DupParams p) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= p.n_rec) return;
     const blu_record& r = p.records[i];
+    // (this kernel is queued behind the gather pass before the host has looked at its overflow flag: when the string pool
+    // was too small the ids were not moved and query_off still is a text offset)
+    if (r.query_off + (unsigned long long)r.query_len > p.pool_cap) return;
     unsigned long long h = 0xcbf29ce484222325ull;
     const uint8_t* q = p.pool + r.query_off;
     for (unsigned k = 0; k < r.query_len; k++) {

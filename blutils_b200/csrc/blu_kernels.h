@@ -32,7 +32,8 @@ struct RunParams {
     uint32_t rec_cap;
     blu_bean* beans;
     blu_acc* accs;
-    TopRowRaw* toprows;    // top bit-score rows of every query (numbers parsed, lineage not joined yet), slot-indexed
+    TopRowRaw* toprows;    // top bit-score rows of every query (fields 1..4 folded to integers, or unparsed references;
+                           // lineage not joined yet), slot-indexed
     uint32_t slot_cap;
     uint64_t* defer;       // (offset << 1) | check_prev
     uint32_t defer_cap;
@@ -43,6 +44,7 @@ struct ConsParams {
     blu_record* records;
     uint32_t rec_begin, rec_end;
     const TopRowRaw* toprows;
+    uint64_t text_end;     // valid text is [0, text_end) of `text` (references beyond it are an internal error)
     blu_bean* beans;
     blu_acc* accs;
     const uint8_t* text;
@@ -65,6 +67,7 @@ struct DupParams {
     const blu_record* records;
     uint32_t n_rec;
     const uint8_t* pool;
+    uint64_t pool_cap;          // bytes of `pool` (ids outside it: the gather pass overflowed, the host reruns with a larger pool)
     unsigned long long* table;  // open addressing, 0 = empty
     uint32_t mask;
     Counters* ctr;

@@ -55,7 +55,7 @@ extern "C" int blu_sim_run(const int64_t* taxids, const uint64_t* off, const cha
             int qlen;
         };
         std::vector<R> rows;
-        long n_fast = 0, n_lean = 0;
+        long n_fast = 0, n_lean = 0, n_info = 0;
         // byte-class bitmasks exactly as the row scan of the kernels publishes them (bit i = byte i)
         std::vector<uint64_t> tabw(nbytes / 64 + 3, 0), digw(nbytes / 64 + 3, 0);
         for (uint64_t i = 0; i < nbytes; i++) {
@@ -89,12 +89,26 @@ extern "C" int blu_sim_run(const int64_t* taxids, const uint64_t* off, const cha
                     // same contract for the streaming kernel's lean parser
                     int64_t fb = 0;
                     int fq = 0;
+                    uint32_t info = 0;
                     if (parse_row_lean(tx, reinterpret_cast<const uint32_t*>(tabw.data()), reinterpret_cast<const uint32_t*>(digw.data()), (int)p, (int)e,
-                                       fb, fq)) {
+                                       fb, fq, info)) {
                         n_lean++;
                         if (lr.err || fb != lr.bits || fq != lr.q_len) {
                             snprintf(err, errlen, "lean row parser disagrees with the full parser at byte %llu", (unsigned long long)p);
                             return BLU_ERR_INTERNAL;
+                        }
+                        {
+                            // the tab positions it hands over must split the row like the full splitter does
+                            TopRowRaw ra, rb;
+                            if (top_row_from_info(tx, reinterpret_cast<const uint32_t*>(digw.data()), (int)p, info, 0, ra)) {
+                                n_info++;
+                                const uint32_t eb = split_top_row(tx, tabw.data(), (int)p, (int)e, 0, rb);
+                                if (eb || ra.acc_off != rb.acc_off || ra.acc_len != rb.acc_len || ra.taxid != rb.taxid || ra.alnlen != rb.alnlen ||
+                                    toprow_pident(ra) != toprow_pident(rb)) {
+                                    snprintf(err, errlen, "row info of the lean parser splits the row differently at byte %llu", (unsigned long long)p);
+                                    return BLU_ERR_INTERNAL;
+                                }
+                            }
                         }
                     }
                 }
@@ -112,7 +126,7 @@ extern "C" int blu_sim_run(const int64_t* taxids, const uint64_t* off, const cha
             p = e + 1;
         }
         if (rows.empty()) throw DataErr("no rows");
-        if (getenv("BLU_SIM_VERBOSE")) fprintf(stderr, "sim: %zu rows, %ld through the fast row parser, %ld through the lean one\n", rows.size(), n_fast, n_lean);
+        if (getenv("BLU_SIM_VERBOSE")) fprintf(stderr, "sim: %zu rows, %ld through the fast row parser, %ld through the lean one, %ld with usable tab positions\n", rows.size(), n_fast, n_lean, n_info);
         std::vector<blu_record> recs;
         std::vector<blu_bean> beans;
         std::vector<blu_acc> accs;
@@ -145,17 +159,6 @@ extern "C" int blu_sim_run(const int64_t* taxids, const uint64_t* off, const cha
                     // the kernels' path: field split + number parse (tile kernel), then the taxid join (consensus kernel)
                     TopRowRaw raw;
                     uint32_t er = split_top_row(tx, tabw.data(), (int)rows[r].s, (int)rows[r].s + rows[r].len, 0, raw);
-                    {
-                        // the streaming kernel's lean splitter must give the same raw row (or the same error)
-                        TopRowRaw raw2;
-                        uint32_t erl = split_top_row_lean(tx, reinterpret_cast<const uint32_t*>(tabw.data()), reinterpret_cast<const uint32_t*>(digw.data()),
-                                                          (int)rows[r].s, (int)rows[r].s + rows[r].len, 0, raw2);
-                        if (erl != er || (!er && (raw2.acc_off != raw.acc_off || raw2.acc_len != raw.acc_len || raw2.taxid != raw.taxid ||
-                                                  raw2.alnlen != raw.alnlen || toprow_pident(raw2) != toprow_pident(raw)))) {
-                            snprintf(err, errlen, "lean top-row splitter disagrees at byte %llu", (unsigned long long)rows[r].s);
-                            return BLU_ERR_INTERNAL;
-                        }
-                    }
                     if (!er) er = join_top_row(raw, L, t);
                     {
                         TopRow t2;
