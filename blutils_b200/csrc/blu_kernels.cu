@@ -1637,12 +1637,18 @@ __global__ void __launch_bounds__(256) consensus_kernel(const ConsParams p) {
     // ---- first 16 accession bytes as big-endian keys ---------------------------------------------------------------
     unsigned long long k0 = 0, k1 = 0;
     if (on) {
-        const uint8_t* a = p.text + r.acc_off;
+        // five aligned words cover the 16 bytes at any alignment (the row goes on for >= 20 bytes behind saccver, so the
+        // reads stay inside the text); realigned by funnel shifts, byte-swapped to big-endian, bytes beyond the accession zeroed
         const unsigned n = r.acc_len;
-#pragma unroll
-        for (unsigned b = 0; b < 8; b++) k0 = (k0 << 8) | (b < n ? a[b] : 0u);
-#pragma unroll
-        for (unsigned b = 8; b < 16; b++) k1 = (k1 << 8) | (b < n ? a[b] : 0u);
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(p.text + (r.acc_off & ~3ull));
+        const uint32_t sh8 = (uint32_t)(r.acc_off & 3ull) * 8u;
+        const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], w3 = wp[3], w4 = wp[4];
+        const uint32_t q0 = __byte_perm(__funnelshift_r(w0, w1, sh8), 0u, 0x0123), q1 = __byte_perm(__funnelshift_r(w1, w2, sh8), 0u, 0x0123),
+                       q2 = __byte_perm(__funnelshift_r(w2, w3, sh8), 0u, 0x0123), q3 = __byte_perm(__funnelshift_r(w3, w4, sh8), 0u, 0x0123);
+        k0 = ((unsigned long long)q0 << 32) | (unsigned long long)q1;
+        k1 = ((unsigned long long)q2 << 32) | (unsigned long long)q3;
+        if (n < 16) k1 = n > 8 ? (k1 & (~0ull << (8u * (16u - n)))) : 0ull;
+        if (n < 8) k0 = n > 0 ? (k0 & (~0ull << (8u * (8u - n)))) : 0ull;
     }
     // ---- S = stable sort by (lineage length, pident, align length, accession)   fmtc.rs:39-54 ----------------------
     int rank = 0;
