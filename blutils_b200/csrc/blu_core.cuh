@@ -692,10 +692,15 @@ BLU_HD bool parse_row_lean(const uint8_t* win, const uint32_t* tabw32, const uin
     q_len = p1;
     // where fields 1..4 sit (for the consensus kernel, should this be a top row): ends of qseqid / saccver relative to the
     // row, ends of staxid / pident / length relative to the byte behind saccver's tab
+    // layout: p1:6 | p2:6 | q3:5 | q4:5 | width of `length`:4 | digits in front of pident's '.' (31: no '.'):5 | valid:1
     {
         const uint32_t ta0c = ta0b & (ta0b - 1u);
         const int q5 = ta0c ? blu_ffs32(ta0c) : 32 + blu_ffs32(ta1 | 0x80000000u);
-        info = (ok && q5 < 64) ? (kRowInfoValid | (uint32_t)p1 | ((uint32_t)p2 << 6) | ((uint32_t)q3 << 12) | ((uint32_t)q4 << 17) | ((uint32_t)q5 << 22)) : 0u;
+        const int ll = q5 - q4 - 1;
+        const int dot = op ? blu_ffs32(op) - (q3 + 1) : 31;
+        info = (ok && ll >= 1 && ll <= 15 && dot >= 0 && dot <= 31)
+                   ? (kRowInfoValid | (uint32_t)p1 | ((uint32_t)p2 << 6) | ((uint32_t)q3 << 12) | ((uint32_t)q4 << 17) | ((uint32_t)ll << 22) | ((uint32_t)dot << 26))
+                   : 0u;
     }
     return ok;
 }
@@ -873,27 +878,20 @@ BLU_HD uint32_t split_top_row(const uint8_t* win, const uint64_t* tabw, int s, i
     return DE_NONE;
 }
 
-// Fields 1..4 of a validated row whose tab positions are known (packed by parse_row_lean) -- the tile kernel's top-row
-// splitter: no tab search, SWAR digit folds for staxid (<= 16 digits), length (<= 8) and pident's decimal mantissa
+// Fields 1..4 of a validated row whose field positions are known (packed by parse_row_lean) -- the tile kernel's top-row
+// splitter: no tab search, no mask access, SWAR digit folds for staxid (<= 16 digits), length (<= 8) and pident's decimal mantissa
 // (`ddd[.ddd]`, <= 9 digits; the division is left to toprow_pident() in the consensus kernel).  Returns false for any
 // other shape (the caller then emits the row unparsed).  Same values as split_top_row() (checked row by row in
 // tests/csrc/sim_harness.cpp).
-BLU_HD bool top_row_from_info(const uint8_t* win, const uint32_t* digw32, int s, uint32_t info, uint64_t lo, TopRowRaw& out) {
+BLU_HD bool top_row_from_info(const uint8_t* win, int s, uint32_t info, uint64_t lo, TopRowRaw& out) {
     const int p1 = (int)(info & 63u), p2 = (int)((info >> 6) & 63u), q3 = (int)((info >> 12) & 31u), q4 = (int)((info >> 17) & 31u),
-              q5 = (int)((info >> 22) & 63u);
+              ll = (int)((info >> 22) & 15u), dot = (int)((info >> 26) & 31u);
     const int a = s + p2 + 1;
-    const int lp = q4 - q3 - 1, ll = q5 - q4 - 1;
-    const uint32_t nd = ~bits_at(digw32, a);
-    const uint32_t o_pid = (nd >> (q3 + 1)) & ((1u << lp) - 1u);  // (staxid and length are digits only: parse_row_lean checked)
-    int ni = lp, nf = 0;
-    bool ok = (info & kRowInfoValid) != 0u && q3 <= 16 && q5 < 32 && ll <= 8;
-    if (o_pid) {
-        ni = blu_ffs32(o_pid);
-        nf = lp - ni - 1;
-        ok = ok && !(o_pid & (o_pid - 1u));  // (the one non-digit byte is a '.': parse_row_lean checked)
-    }
-    ok = ok && ni <= 8 && nf <= 8 && ni + nf >= 1 && ni + nf <= 9;
-    if (!ok) return false;
+    const int lp = q4 - q3 - 1;
+    // pident: `dot` digits, then (unless dot == 31: digits only) a '.', then the rest -- parse_row_lean checked the shape
+    const int ni = dot == 31 ? lp : dot;
+    const int nf = dot == 31 ? 0 : lp - dot - 1;
+    if (!(info & kRowInfoValid) || q3 > 16 || ll > 8 || ni > 8 || nf > 8 || ni + nf < 1 || ni + nf > 9) return false;
     out.acc_off = lo + (uint64_t)(s + p1 + 1);
     out.acc_len = (uint32_t)(p2 - p1 - 1);
     out.taxid = q3 <= 8 ? (int64_t)swar_digits(win, a, q3)

@@ -325,9 +325,9 @@ __device__ __forceinline__ void finish_geom(WindowIndex& W, WinGeom& g, bool fin
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kSWarps = kTileThreads / 32;
 constexpr int kUnits = kTile / 32 + 1;       // 32-byte units of a window (+1: the unit that can hold a virtual final newline)
-constexpr int kUnitsPerWarp = ((kTile / 32 + kSWarps - 1) / kSWarps + 31) & ~31;  // whole 32-lane rounds (the extra unit of a
-                                                                                   // virtual final newline goes to the last warp)
-constexpr int kSegCap = kUnitsPerWarp * 2 + 2;   // row starts one warp can find (<= 1 per 16 bytes, else malformed)
+constexpr int kRounds = kTile / 1024;        // phase B works in rounds of 32 units = 1 KB (the extra unit of a virtual final
+                                             // newline goes to the last round)
+constexpr int kSegCap = 32 * 2 + 4;           // row starts one round can find (<= 1 per 16 bytes, else malformed)
 constexpr int kSRowCap = kTile / 26 + 8;     // a valid row is >= 26 bytes
 constexpr int kRecFlush = 128;                // buffered record headers that trigger a flush (one global atomic)
 constexpr int kRecBuf = 256;                  // capacity of the record buffer (beyond: the run reserves its record itself)
@@ -337,8 +337,7 @@ constexpr int kCarryTop = 32;                 // top rows of the open query kept
 
 static_assert(kSRowCap < 0x8000, "row indices are 15-bit");
 static_assert(kTile % 32 == 0 && kTile + 128 < 65536, "window offsets are 16-bit");
-static_assert(kSWarps <= 32, "per-warp tables are read by one warp");
-static_assert(kUnitsPerWarp * kSWarps >= kTile / 32, "the warps' shares cover the window");
+static_assert(kTile % 1024 == 0 && kRounds <= 32, "per-round tables are read by one warp");
 
 enum : uint32_t { RK_EMIT = 1, RK_DEFER = 2, RK_PSEUDO = 4, RK_OPEN = 8, RK_NEWCARRY = 16 };
 
@@ -380,7 +379,7 @@ struct StreamSmem {
     alignas(8) uint32_t tabm[kUnits + 7];
     alignas(8) uint32_t digm[kUnits + 7];
     alignas(8) uint32_t nlm[kUnits + 7];
-    uint16_t seg[kSWarps][kSegCap];  // row starts found by warp w, in order
+    uint16_t seg[kRounds][kSegCap];  // row starts found in round i, in order
     uint16_t row_s[kSRowCap + 2];    // all row starts of the window (written by phase D)
     int32_t bits[kSRowCap];
     uint8_t flags[kSRowCap];         // bit1: bit score does not fit int32
@@ -391,7 +390,7 @@ struct StreamSmem {
     uint16_t stage[kSWarps][32];
     CarryRun carry[2];
     alignas(8) unsigned long long mbar[2];
-    int warp_cnt[32], warp_first[32], warp_last[32];
+    int warp_cnt[32], warp_first[32], warp_last[32];  // per round of phase B: row starts, the first and the last one
     WinDesc wd[2];
     WinGeo geo;
     int b_done;  // warps that have finished phase B of the current window
@@ -484,18 +483,18 @@ __device__ __noinline__ int row_end_search(const StreamSmem& S, int s, int limit
     return limit;
 }
 
-// Phase B for one warp's share [u0, u1) of the window.  kInterior: every unit is whole text (no edge of the input in
-// the window), so the per-unit edge tests are compiled out.
+// Phase B for one round: units [u0, u1) of the window (32 of them; the last round may have one more).  kInterior: every
+// unit is whole text (no edge of the input in the window), so the per-unit edge tests are compiled out.
 template <bool kInterior>
-__device__ __forceinline__ void classify_share(StreamSmem& S, const uint8_t* win, int u0, int u1, int vb, int tend, bool has_begin, bool virt_nl,
-                                               int warp, int lane) {
+__device__ __forceinline__ void classify_round(StreamSmem& S, const uint8_t* win, int round, int u0, int u1, int vb, int tend, bool has_begin,
+                                               bool virt_nl, int lane) {
     const unsigned FULL = 0xffffffffu;
     const uint32_t lt = (1u << lane) - 1u;
     int cnt = 0;
     uint32_t crowd = 0, blank = 0;
     uint32_t carry_in = 0;
     if (u0 < u1 && u0 > 0 && (u0 << 5) - 1 >= vb) carry_in = win[(u0 << 5) - 1] == '\n';
-    uint16_t* const seg = S.seg[warp];
+    uint16_t* const seg = S.seg[round];
     for (int base = u0; base < u1; base += 32) {
         const int u = base + lane;
         const int pos0 = u << 5;
@@ -560,9 +559,9 @@ __device__ __forceinline__ void classify_share(StreamSmem& S, const uint8_t* win
     if (__any_sync(FULL, crowd != 0) && lane == 0) S.crowded = 1;
     __syncwarp();
     if (lane == 0) {
-        S.warp_cnt[warp] = cnt;
-        S.warp_first[warp] = cnt ? (int)seg[0] : -1;
-        S.warp_last[warp] = cnt ? (int)seg[cnt - 1] : -1;
+        S.warp_cnt[round] = cnt;
+        S.warp_first[round] = cnt ? (int)seg[0] : -1;
+        S.warp_last[round] = cnt ? (int)seg[cnt - 1] : -1;
     }
 }
 
@@ -735,12 +734,16 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
 
         // ---- phase B: classify + per-warp row starts ----------------------------------------------------------------
         {
-            const int u0 = warp * kUnitsPerWarp;
-            const int u1 = (warp == kSWarps - 1 || u0 + kUnitsPerWarp > n_units) ? n_units : u0 + kUnitsPerWarp;
-            if (!has_begin && tend == kTile && !virt_nl && kUnitsPerWarp * kSWarps == kTile / 32)
-                classify_share<true>(S, win, u0, u0 + kUnitsPerWarp, 0, tend, false, false, warp, lane);
-            else
-                classify_share<false>(S, win, u0, u1, vb, tend, has_begin, virt_nl, warp, lane);
+            const bool interior = !has_begin && tend == kTile && !virt_nl;
+            for (int rd = warp; rd < kRounds; rd += kSWarps) {
+                const int u0 = rd << 5;
+                if (interior)
+                    classify_round<true>(S, win, rd, u0, u0 + 32, 0, tend, false, false, lane);
+                else {
+                    const int u1 = (rd == kRounds - 1 || u0 + 32 > n_units) ? n_units : u0 + 32;
+                    classify_round<false>(S, win, rd, u0, u1 > u0 ? u1 : u0, vb, tend, has_begin, virt_nl, lane);
+                }
+            }
         }
         PCLK(1)
         // ---- row tables of the window: the prefix over the warps' shares is computed ONCE, by the last warp that leaves
@@ -756,8 +759,8 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
             ticket = __shfl_sync(FULL, ticket, 0);
             if (ticket == kSWarps - 1) {
                 __threadfence_block();
-                // lane i < kSWarps holds the tables of warp i's share
-                const int c_i = lane < kSWarps ? S.warp_cnt[lane] : 0;
+                // lane i < kRounds holds the tables of round i
+                const int c_i = lane < kRounds ? S.warp_cnt[lane] : 0;
                 int inc_i = c_i;
 #pragma unroll
                 for (int d = 1; d < 32; d <<= 1) {
@@ -767,12 +770,12 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
                 const int n_starts = __shfl_sync(FULL, inc_i, 31);
                 const unsigned ne = __ballot_sync(FULL, c_i > 0);
                 const unsigned below = ne & ((1u << lane) - 1u), above = lane >= 31 ? 0u : (ne & (~0u << (lane + 1)));
-                const int wl = lane < kSWarps ? S.warp_last[lane] : -1, wf = lane < kSWarps ? S.warp_first[lane] : -1;
+                const int wl = lane < kRounds ? S.warp_last[lane] : -1, wf = lane < kRounds ? S.warp_first[lane] : -1;
                 int plast_i = __shfl_sync(FULL, wl, below ? 31 - __clz(below) : 0);
                 if (!below) plast_i = -1;
                 int nfirst_i = __shfl_sync(FULL, wf, above ? __ffs(above) - 1 : 0);
                 if (!above) nfirst_i = -1;
-                if (lane < kSWarps) {
+                if (lane < kRounds) {
                     S.geo.inc[lane] = inc_i;
                     S.geo.nfirst[lane] = nfirst_i;
                     S.geo.plast[lane] = plast_i;
@@ -795,13 +798,13 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
             break;  // (no copy in flight: the next window has not been requested)
         }
         if (tid == 0 && S.bad_byte != INT_MAX) report(p.ctr, DE_QUOTE_OR_CR, lo + (unsigned)S.bad_byte);
-        const int c_i = lane < kSWarps ? S.warp_cnt[lane] : 0;
-        const int inc_i = lane < kSWarps ? S.geo.inc[lane] : n_starts;
-        const int nfirst_i = lane < kSWarps ? S.geo.nfirst[lane] : -1, plast_i = lane < kSWarps ? S.geo.plast[lane] : -1;
+        const int c_i = lane < kRounds ? S.warp_cnt[lane] : 0;
+        const int inc_i = lane < kRounds ? S.geo.inc[lane] : n_starts;
+        const int nfirst_i = lane < kRounds ? S.geo.nfirst[lane] : -1, plast_i = lane < kRounds ? S.geo.plast[lane] : -1;
         if (warp == kSWarps - 1) {
             // ---- last newline, last complete row, the next window (its bytes are requested now) ---------------------------
             const unsigned ne = __ballot_sync(FULL, c_i > 0);
-            int last_start = __shfl_sync(FULL, lane < kSWarps ? S.warp_last[lane] : -1, ne ? 31 - __clz(ne) : 0);
+            int last_start = __shfl_sync(FULL, lane < kRounds ? S.warp_last[lane] : -1, ne ? 31 - __clz(ne) : 0);
             if (!ne) last_start = -1;
             int last_nl = -1;
             for (int ub = n_units - 1; ub >= 0 && last_nl < 0; ub -= 32) {
@@ -855,7 +858,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
             for (int step = 16; step; step >>= 1) {
                 const int cand = w + step;
                 const int v = __shfl_sync(FULL, inc_i, (cand - 1) & 31);
-                if (cand <= kSWarps && v <= rr) w = cand;
+                if (cand <= kRounds && v <= rr) w = cand;
             }
             const int cw = __shfl_sync(FULL, c_i, w);
             const int k = rr - (__shfl_sync(FULL, inc_i, w) - cw);
@@ -1096,7 +1099,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
                 // fields 1..4 through the tab positions the row phase found: digit folds only, no second tab search; a row of any
                 // other shape leaves unparsed (offset + length) and is split by the consensus kernel's full parser
                 TopRowRaw ref;
-                if (!top_row_from_info(win, S.digm, s, S.rowinfo[r], lo, ref)) {
+                if (!top_row_from_info(win, s, S.rowinfo[r], lo, ref)) {
                     ref.acc_off = lo + (unsigned long long)s;
                     ref.acc_len = (uint32_t)(re - s);
                     ref.taxid = 0, ref.alnlen = 0, ref.pident = 0.0;

@@ -100,7 +100,7 @@ extern "C" int blu_sim_run(const int64_t* taxids, const uint64_t* off, const cha
                         {
                             // the tab positions it hands over must split the row like the full splitter does
                             TopRowRaw ra, rb;
-                            if (top_row_from_info(tx, reinterpret_cast<const uint32_t*>(digw.data()), (int)p, info, 0, ra)) {
+                            if (top_row_from_info(tx, (int)p, info, 0, ra)) {
                                 n_info++;
                                 const uint32_t eb = split_top_row(tx, tabw.data(), (int)p, (int)e, 0, rb);
                                 if (eb || ra.acc_off != rb.acc_off || ra.acc_len != rb.acc_len || ra.taxid != rb.taxid || ra.alnlen != rb.alnlen ||
