@@ -864,11 +864,15 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
             const int k = rr - (__shfl_sync(FULL, inc_i, w) - cw);
             const int nf = __shfl_sync(FULL, nfirst_i, w), pl = __shfl_sync(FULL, plast_i, w);
             bool head = false, skip = false;
+            // part 1: validate + parse the row (the lanes of a warp part ways here: evalue shapes, the rare full-grammar path)
+            bool parsed = false;
+            int s = 0, ql = 0, prv = -1;
+            unsigned long long abs = 0;
             if (live) {
                 const uint16_t* const seg_w = S.seg[w];
-                const int s = seg_w[k];
+                s = seg_w[k];
                 S.row_s[r] = (uint16_t)s;
-                const unsigned long long abs = lo + (unsigned long long)s;
+                abs = lo + (unsigned long long)s;
                 if (abs < own_from)
                     skip = true;  // look-behind rows: seen by the previous window / owned by the previous segment
                 else {
@@ -876,37 +880,42 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
                     // with blank lines) looks it up in the newline mask -- none: an unterminated row, left to the next window
                     const int nxt = k + 1 < cw ? (int)seg_w[k + 1] : nf;
                     const int e = (nxt < 0 || blank) ? row_end_search(S, s, scan_len) : nxt - 1;
-                    if (e >= scan_len) goto row_done;
-                    int64_t bits;
-                    int ql;
-                    uint32_t info;
-                    if (!parse_row_lean(win, S.tabm, S.digm, s, e, bits, ql, info)) {
-                        const LightRow lr = parse_row_masked(win, tabw, digw, s, e);
-                        if (lr.err) report(p.ctr, lr.err, abs);
-                        bits = lr.bits;
-                        ql = lr.q_len;
-                        info = 0;
-                    }
-                    S.rowinfo[r] = info;
-                    const int prv = k > 0 ? (int)seg_w[k - 1] : pl;
-                    if (prv < 0) {
-                        head = has_begin;  // first row of the text; else: predecessor not in the window
-                        if (!head) push_defer(p, abs, 1);  // the block path decides whether it starts a query
-                    } else
-                        head = !same_qid_lean(win, S.tabm, s, ql, prv);
-                    const int32_t b32 = (int32_t)bits;
-                    S.flags[r] = ((int64_t)b32 != bits) ? 2 : 0;
-                    S.bits[r] = b32;
-                    if (head) {
-                        if (abs < seg_hi) {
-                            const int i = atomicAdd(&S.n_runs, 1);
-                            S.runs[i] = (uint32_t)r | ((uint32_t)(ql > 0xFFFF ? 0xFFFF : ql) << 16);
-                        } else
-                            S.term = 1;  // a query of the next segment starts here: this CTA ends with this window
+                    if (e < scan_len) {
+                        int64_t bits;
+                        uint32_t info;
+                        if (!parse_row_lean(win, S.tabm, S.digm, s, e, bits, ql, info)) {
+                            const LightRow lr = parse_row_masked(win, tabw, digw, s, e);
+                            if (lr.err) report(p.ctr, lr.err, abs);
+                            bits = lr.bits;
+                            ql = lr.q_len;
+                            info = 0;
+                        }
+                        S.rowinfo[r] = info;
+                        const int32_t b32 = (int32_t)bits;
+                        S.flags[r] = ((int64_t)b32 != bits) ? 2 : 0;
+                        S.bits[r] = b32;
+                        prv = k > 0 ? (int)seg_w[k - 1] : pl;
+                        parsed = true;
                     }
                 }
             }
-        row_done:
+            // part 2, with the warp back together (without this the two halves of a warp that took different branches above run
+            // the compare one after the other): head flag = the query id differs from the previous row's
+            __syncwarp();
+            if (parsed) {
+                if (prv < 0) {
+                    head = has_begin;  // first row of the text; else: predecessor not in the window
+                    if (!head) push_defer(p, abs, 1);  // the block path decides whether it starts a query
+                } else
+                    head = !same_qid_lean(win, S.tabm, s, ql, prv);
+                if (head) {
+                    if (abs < seg_hi) {
+                        const int i = atomicAdd(&S.n_runs, 1);
+                        S.runs[i] = (uint32_t)r | ((uint32_t)(ql > 0xFFFF ? 0xFFFF : ql) << 16);
+                    } else
+                        S.term = 1;  // a query of the next segment starts here: this CTA ends with this window
+                }
+            }
             const unsigned hb = __ballot_sync(FULL, head);
             if (lane == 0) S.headw[r >> 5] = hb;
             const unsigned sb = __ballot_sync(FULL, skip);
