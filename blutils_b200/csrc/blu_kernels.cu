@@ -1919,8 +1919,9 @@ cudaError_t launch_longrun_kernel(const RunParams& p, int grid, cudaStream_t s) 
 
 cudaError_t launch_consensus_kernel(const ConsParams& p, cudaStream_t s) {
     if (p.rec_end <= p.rec_begin) return cudaSuccess;
-    const unsigned n = p.rec_end - p.rec_begin;  // one warp per record, 8 per CTA
-    consensus_kernel<<<(n + 7) / 8, 256, 0, s>>>(p);
+    const unsigned n = p.rec_end - p.rec_begin;  // one warp per record; two per CTA: the warps of a CTA finish at very different
+                                                 // times (top groups of 1..32 rows), and a slot is only refilled when its whole CTA is gone
+    consensus_kernel<<<(n + 1) / 2, 64, 0, s>>>(p);
     return cudaGetLastError();
 }
 
