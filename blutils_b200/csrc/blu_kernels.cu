@@ -310,18 +310,20 @@ __device__ __forceinline__ void finish_geom(WindowIndex& W, WinGeom& g, bool fin
 // "look-behind" row: it is only there so that the first new row can be compared with its predecessor), so no row
 // and no query ever has to fit a window: the unfinished query is carried in shared memory (row count, best bit
 // score, its top rows so far) from window to window, and a CTA keeps walking past the end of its segment until the
-// query it has open ends.  Phases of one window (separated by CTA-wide barriers):
+// query it has open ends.  Phases of one window (three CTA-wide barriers):
 //   B  classify   every lane owns 32 bytes: SIMD-in-register byte tests (ASCII fast path) -> newline / tab / digit
-//                 bitmasks (dp4a packing); row starts compacted per warp with two ballots per round
-//   D  rows       warp w takes the rows that start in warp w's share of the window, one thread per row: validation +
-//                 truncated bit score (parse_row_lean, falling back to the full grammar), head flag (query id differs
-//                 from the previous row's), global row table
-//   E  runs       one warp per query run (dynamic queue): extent, best bit score, top rows (ballot compaction);
+//                 bitmasks (dp4a packing); row starts compacted per 1 KB round with two ballots; the last warp out
+//                 computes the prefix over the rounds' row counts
+//   D  rows       one thread per row (global row index -> round by a shuffle search): validation + truncated bit score
+//                 (parse_row_lean, falling back to the full grammar), packed field positions, head flag (query id
+//                 differs from the previous row's); meanwhile the last warp of the CTA finds the last newline and
+//                 requests the next window's bytes
+//   E  runs       one warp per query run (static assignment): extent, best bit score, top rows (ballot compaction);
 //                 the warp decides the run's fate (finished / still open / block path), merges it with the carried
-//                 query, and takes its place in the window's output with one shared-memory atomic
-//   F  emit       ONE global atomic reserves the records / top-row slots of the whole window while the top rows are
-//                 split and parsed (one thread each); then top rows and record headers (one thread per finished
-//                 query) go to HBM
+//                 query, takes top-row slots from the CTA's slab and a place in the record buffer (shared-memory
+//                 atomics), folds its top rows' digits (top_row_from_info) and writes them to HBM / the carry
+//      then       thread 0: a new slot slab when the current one runs low, record flush (one global atomic per >= 128
+//                 headers), where the CTA goes next
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kSWarps = kTileThreads / 32;
 constexpr int kUnits = kTile / 32 + 1;       // 32-byte units of a window (+1: the unit that can hold a virtual final newline)
@@ -732,7 +734,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
         const int scan_len = tend + (virt_nl ? 1 : 0);
         const int n_units = (scan_len + 31) >> 5;
 
-        // ---- phase B: classify + per-warp row starts ----------------------------------------------------------------
+        // ---- phase B: classify + row starts, 1 KB rounds ------------------------------------------------------------------
         {
             const bool interior = !has_begin && tend == kTile && !virt_nl;
             for (int rd = warp; rd < kRounds; rd += kSWarps) {
@@ -746,7 +748,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
             }
         }
         PCLK(1)
-        // ---- row tables of the window: the prefix over the warps' shares is computed ONCE, by the last warp that leaves
+        // ---- row tables of the window: the prefix over the rounds is computed ONCE, by the last warp that leaves
         //      phase B; everything else (last newline, next window) is worked out behind the barrier by the last warp of the
         //      CTA, which normally has no rows in phase D, while the others already parse rows
         {
@@ -852,7 +854,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
             const int r = rb + tid;
             const bool live = r < n_starts;
             const int rr = live ? r : n_starts - 1;
-            // which warp's share found row rr: number of shares that end at or before it
+            // which round found row rr: number of rounds that end at or before it
             int w = 0;
 #pragma unroll
             for (int step = 16; step; step >>= 1) {
@@ -924,7 +926,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
         PCLK(4)
         __syncthreads();
         PCLK(5)
-        // ---- phase R: one warp per query run (dynamic queue) -----------------------------------------------------------
+        // ---- phase E: one warp per query run (static assignment) -----------------------------------------------------------
         //   extent, best bit score, top rows (ballot compaction); the warp decides the run's fate (finished / still open /
         //   block path), merges it with the carried query, reserves its output and splits + parses its own top rows
         const int n_complete = S.geo.n_complete, last_nl = S.geo.last_nl;

@@ -20,7 +20,7 @@ def line_of(pat, f):
 K='blu_kernels.cu'; C='blu_core.cuh'
 marks={K:[('ptx wrappers','uint32_t smem_u32'),('longrun window code','struct WindowIndex'),('stream helpers','struct CarryRun'),('pack32','uint32_t pack8'),('classify_unit_slow','void classify_unit_slow'),('next_head','int next_head'),
           ('row_end_search','int row_end_search'),('phase B classify','void classify_round('),('write_record/flush','void write_record('),('tile prologue',') tile_kernel('),('window setup','    while (true) {\n        const uint8_t* const win'),('phase B call','---- phase B'),('geometry','---- row geometry'),('phase D rows','---- phase D'),
-          ('phase R runs','---- phase R'),('phase R decide (lane 0)','---- lane 0: what happens'),('phase R top rows','---- the run\'s top rows'),('where next','---- where next'),('longrun','// long-run kernel')],
+          ('phase E runs','---- phase E: one warp per query run'),('phase E decide (lane 0)','---- lane 0: what happens'),('phase E top rows','---- the run\'s top rows'),('where next','---- where next'),('longrun','// long-run kernel')],
        C:[('probe','uint32_t probe_taxid'),('parse_i64','bool parse_i64'),('parse_f64','uint32_t parse_f64'),('num_class/dfa/check_float','int num_class'),('light_parse_row','LightRow light_parse_row'),('ctz/next_tab/all_digits','int blu_ctz64'),('parse_row_masked','LightRow parse_row_masked'),('bit helpers','uint32_t blu_funnel_r'),('float_shape_ok','bool float_shape_ok'),('parse_row_fast','bool parse_row_fast'),('lean helpers','int blu_popc64'),('swar digits','uint32_t swar4('),('parse_row_lean','bool parse_row_lean'),('load_u32_unaligned','uint32_t load_u32_unaligned(const uint8_t* win, int pos) {'),('same_first_field','bool same_first_field'),('same_qid_lean','bool same_qid_lean'),('TopRow/heavy','struct TopRow'),('parse shorts','bool parse_u32_short'),('split_top_row','uint32_t split_top_row('),('top_row_from_info','bool top_row_from_info('),('join/heavy_masked','uint32_t join_top_row'),('consensus','struct QueryOut')]}
 ti=sum(v[0] for v in agg.values()) or 1; ts=sum(v[1] for v in agg.values()) or 1
 print('total warp-inst',ti,'samples',ts)
