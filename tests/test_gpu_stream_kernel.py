@@ -138,3 +138,19 @@ def test_large_table_is_deterministic():
         assert len(out) == 52000 and out.checksum() == want
         out.close()
     eng.close()
+
+
+def test_query_spanning_many_segments():
+    """One query of 150 k rows (~10 MB: dozens of 128 KB+ segments lie entirely inside it) between ordinary queries: the CTA
+    that owns its first row walks through all of them, the CTAs of the segments in between find no query of their own."""
+    rows = []
+    for q in range(40):
+        for h in range(30):
+            rows.append(_row(f"small_a{q:03d}", f"NR_{h:06d}.1", IDS[h % 3], "97.500", 300, "400" if h < 2 else str(100 + h)))
+    for h in range(150_000):
+        bits = "999" if h in (7, 70_000, 149_999) else str(100 + h % 800)
+        rows.append(_row("the_big_one", f"NR_{h % 5000:06d}.1", IDS[h % 4], f"9{h % 10}.{h % 1000:03d}", 250 + h % 100, bits))
+    for q in range(40):
+        for h in range(30):
+            rows.append(_row(f"small_b{q:03d}", f"NR_{h:06d}.1", IDS[(h + 1) % 3], "96.250", 300, "380" if h < 3 else str(90 + h)))
+    _check("".join(rows), strategies=("relaxed",), chunks=(0, 4 << 20))
