@@ -254,8 +254,18 @@ class ConsensusEngine:
         if rc != 0:
             _raise(rc, (_ffi.lib().blu_last_error(self._h) or b"").decode())
 
-    def load_taxonomy(self, taxonomies_file: str) -> None:
-        self._check(_ffi.lib().blu_taxonomy_load_json(self._h, os.fspath(taxonomies_file).encode()))
+    def load_taxonomy(self, taxonomies_file: str, cache: Union[None, bool, str] = None) -> Optional[int]:
+        """get_taxonomies_dataframe (mod.rs:246-327).  `cache`: None/False = parse the JSON (what the reference does on every
+        run); True = side-car cache `<taxonomies_file>.blucache`; a path = that cache file.  With a cache the return
+        value is 1 (loaded from the cache), 0 (built, cache written) or -1 (built, cache not writable)."""
+        path = os.fspath(taxonomies_file).encode()
+        if not cache:
+            self._check(_ffi.lib().blu_taxonomy_load_json(self._h, path))
+            return None
+        state = C.c_int(0)
+        cpath = None if cache is True else os.fspath(cache).encode()
+        self._check(_ffi.lib().blu_taxonomy_load_json_cached(self._h, path, cpath, C.byref(state)))
+        return state.value
 
     def load_taxonomy_arrays(self, taxids, lineages: Sequence[Union[str, bytes]]) -> None:
         import numpy as np

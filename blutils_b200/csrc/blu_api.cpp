@@ -864,6 +864,35 @@ int blu_taxonomy_load_json(blu_ctx* c, const char* path) {
     return blu_taxonomy_load_arrays(c, ids.data(), off.data(), blob.data(), ids.size());
 }
 
+int blu_taxonomy_load_json_cached(blu_ctx* c, const char* path, const char* cache_path, int* cache_state) {
+    if (!c || !path) return fail(c, BLU_ERR_ARG, "null argument");
+    if (cache_state) *cache_state = 0;
+    const std::string cpath = cache_path ? std::string(cache_path) : std::string(path) + ".blucache";
+    return guarded(c, [&] {
+        CK(cudaSetDevice(c->device));
+        const TaxCacheKey key = make_cache_key(path, c->opts.use_taxid != 0, c->cut);  // IoErr if the JSON is unreadable
+        auto T = std::make_shared<HostTaxonomy>();
+        int state = 1;
+        if (!load_taxonomy_cache(cpath.c_str(), key, *T)) {
+            std::vector<int64_t> ids;
+            std::vector<uint64_t> off;
+            std::string blob;
+            read_taxonomy_json(path, c->opts.use_taxid != 0, ids, off, blob);
+            static const uint64_t zero = 0;
+            build_taxonomy(ids.data(), ids.empty() ? &zero : off.data(), blob.data(), ids.size(), c->cut, *T);
+            state = 0;
+            try {
+                save_taxonomy_cache(cpath.c_str(), key, *T);
+            } catch (const IoErr&) {
+                state = -1;
+            }
+        }
+        c->tax = T;
+        upload_taxonomy(c);
+        if (cache_state) *cache_state = state;
+    });
+}
+
 int blu_consensus_run_device(blu_ctx* c, const void* dtext, uint64_t n, void* stream, blu_result** out) {
     if (!c || !out || (!dtext && n)) return fail(c, BLU_ERR_ARG, "null argument");
     *out = nullptr;

@@ -135,7 +135,13 @@ int main(int argc, char** argv) {
         die("Custom taxon values are required when the custom taxon option is selected.");
     blu_ctx* ctx = nullptr;
     if (blu_ctx_create(&o, &ctx) != BLU_OK) die(blu_last_error(nullptr));
-    if (blu_taxonomy_load_json(ctx, tax_file.c_str()) != BLU_OK) die(blu_last_error(ctx));
+    // BLU_TAX_CACHE=1: binary side-car cache next to the taxonomy file; BLU_TAX_CACHE=<path>: that file.  An
+    // environment variable, not a flag: the argument list stays the reference's (commands.rs:105-143).
+    const char* tc = getenv("BLU_TAX_CACHE");
+    if (tc && *tc && strcmp(tc, "0") != 0) {
+        if (blu_taxonomy_load_json_cached(ctx, tax_file.c_str(), strcmp(tc, "1") == 0 ? nullptr : tc, nullptr) != BLU_OK) die(blu_last_error(ctx));
+    } else if (blu_taxonomy_load_json(ctx, tax_file.c_str()) != BLU_OK)
+        die(blu_last_error(ctx));
     blu_result* res = nullptr;
     if (blu_consensus_run_file(ctx, blast_out.c_str(), &res) != BLU_OK) die(std::string("Unexpected error on parse blast results: ") + blu_last_error(ctx));
     if (blu_result_write(res, have_out ? out_file.c_str() : nullptr, format, nullptr) != BLU_OK) die("Error on persist output results");

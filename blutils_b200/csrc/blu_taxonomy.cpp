@@ -9,6 +9,9 @@
 #include <map>
 #include <numeric>
 
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include "blu_json.h"
 
 namespace blu {
@@ -159,21 +162,140 @@ size_t HostTaxonomy::device_bytes() const {
 }
 
 namespace {
-struct SvHash {
-    size_t operator()(std::string_view s) const { return std::hash<std::string_view>()(s); }
+
+// string -> dense id in first-appearance order.  Open addressing over one byte arena: no allocation per key and one
+// probable cache miss per lookup (the std::unordered_map<std::string, ..> this replaces spent 15 s on 2 M lineages).
+class StrInterner {
+    std::vector<uint64_t> slots_;  // (hash & ~0xFFFFFFFF) | (id + 1); 0 = empty
+    std::vector<uint64_t> off_;    // key id -> arena offset (n + 1 entries)
+    std::string arena_;
+    uint64_t mask_;
+
+    static uint64_t hash(std::string_view s) {
+        uint64_t h = 0x9E3779B97F4A7C15ull ^ (uint64_t)s.size();
+        const char* p = s.data();
+        size_t n = s.size();
+        for (; n >= 8; p += 8, n -= 8) {
+            uint64_t w;
+            memcpy(&w, p, 8);
+            h = mix64(h ^ w);
+        }
+        if (n) {
+            uint64_t w = 0;
+            memcpy(&w, p, n);
+            h = mix64(h ^ w ^ 0xA5A5A5A5A5A5A5A5ull);
+        }
+        return mix64(h);
+    }
+    void grow() {
+        std::vector<uint64_t> old;
+        old.swap(slots_);
+        slots_.assign(old.size() * 2, 0);
+        mask_ = slots_.size() - 1;
+        for (uint64_t e : old)
+            if (e) {
+                uint64_t i = (e >> 32) & mask_;
+                while (slots_[i]) i = (i + 1) & mask_;
+                slots_[i] = e;
+            }
+    }
+
+   public:
+    explicit StrInterner(size_t expect = 64) {
+        size_t cap = 64;
+        while (cap < 2 * expect) cap <<= 1;
+        slots_.assign(cap, 0);
+        mask_ = cap - 1;
+        off_.push_back(0);
+    }
+    size_t size() const { return off_.size() - 1; }
+    std::string_view at(uint32_t id) const { return std::string_view(arena_.data() + off_[id], off_[id + 1] - off_[id]); }
+    // id of `s`; *fresh = true when this call added it
+    uint32_t intern(std::string_view s, bool* fresh = nullptr) {
+        const uint64_t h = hash(s), tag = h & ~0xFFFFFFFFull;
+        uint64_t i = (h >> 32) & mask_;
+        for (uint64_t e; (e = slots_[i]) != 0; i = (i + 1) & mask_)
+            if ((e & ~0xFFFFFFFFull) == tag) {
+                const uint32_t id = (uint32_t)e - 1;
+                if (at(id) == s) {
+                    if (fresh) *fresh = false;
+                    return id;
+                }
+            }
+        const uint32_t id = (uint32_t)size();
+        if (id >= 0xFFFFFFF0u) throw std::invalid_argument("more than 2^32 distinct strings in the taxonomy");
+        arena_.append(s.data(), s.size());
+        off_.push_back(arena_.size());
+        slots_[i] = tag | (uint64_t)(id + 1);
+        if (fresh) *fresh = true;
+        if (2 * (size_t)(id + 1) > slots_.size()) grow();
+        return id;
+    }
 };
+
+// (rank id, identifier id) -> dense pair id, same scheme for 64-bit keys
+class PairInterner {
+    std::vector<uint64_t> keys_;  // key + 1 (0 = empty)
+    std::vector<uint32_t> vals_;
+    uint64_t mask_;
+    uint32_t n_ = 0;
+
+    void grow() {
+        std::vector<uint64_t> ok;
+        std::vector<uint32_t> ov;
+        ok.swap(keys_);
+        ov.swap(vals_);
+        keys_.assign(ok.size() * 2, 0);
+        vals_.assign(ok.size() * 2, 0);
+        mask_ = keys_.size() - 1;
+        for (size_t j = 0; j < ok.size(); j++)
+            if (ok[j]) {
+                uint64_t i = mix64(ok[j]) & mask_;
+                while (keys_[i]) i = (i + 1) & mask_;
+                keys_[i] = ok[j];
+                vals_[i] = ov[j];
+            }
+    }
+
+   public:
+    explicit PairInterner(size_t expect = 64) {
+        size_t cap = 64;
+        while (cap < 2 * expect) cap <<= 1;
+        keys_.assign(cap, 0);
+        vals_.assign(cap, 0);
+        mask_ = cap - 1;
+    }
+    uint32_t intern(uint64_t key, bool* fresh) {
+        const uint64_t k1 = key + 1;
+        uint64_t i = mix64(k1) & mask_;
+        for (; keys_[i]; i = (i + 1) & mask_)
+            if (keys_[i] == k1) {
+                *fresh = false;
+                return vals_[i];
+            }
+        keys_[i] = k1;
+        vals_[i] = n_;
+        *fresh = true;
+        const uint32_t id = n_++;
+        if (2 * (size_t)n_ > keys_.size()) grow();
+        return id;
+    }
+};
+
 }  // namespace
 
 void build_taxonomy(const int64_t* taxids, const uint64_t* off, const char* blob, uint64_t n, const Cutoffs& cutoffs, HostTaxonomy& T) {
     T = HostTaxonomy();
     const auto bb = make_backbone(cutoffs);
-    std::unordered_map<std::string, uint32_t> rank_raw;    // raw rank text -> rank id
+    StrInterner rank_raw;                                  // raw rank text -> raw id
+    std::vector<int64_t> raw_rid;                          // raw id -> rank id, -1 = rank_from_str rejects it
     std::unordered_map<std::string, uint32_t> rank_canon;  // (def|slug) -> rank id
-    std::unordered_map<std::string, uint32_t> ident_id;
-    std::unordered_map<uint64_t, uint32_t> pair_id;  // (rank, ident) -> pair
+    StrInterner ident_id(n);
+    PairInterner pair_id(n);  // (rank, ident) -> pair
     std::vector<std::pair<uint32_t, uint32_t>> pairs;
     std::vector<uint32_t> pos_pair;
     std::unordered_map<std::string, std::vector<double>> interp_memo;
+    std::string memo_key;
 
     T.taxids.assign(taxids, taxids + n);
     T.lin_off.reserve(n + 1);
@@ -181,6 +303,9 @@ void build_taxonomy(const int64_t* taxids, const uint64_t* off, const char* blob
     T.lin_ok.resize(n);
     std::vector<uint32_t> tmp_rank, tmp_ident;
     std::vector<const RankInfo*> rk;
+    std::string_view memo_raw[65];  // views into `blob`
+    uint32_t memo_raw_id[65];
+    std::fill(memo_raw_id, memo_raw_id + 65, 0xFFFFFFFFu);  // = not set (an empty view would equal an empty rank name)
     for (uint64_t i = 0; i < n; i++) {
         std::string_view s(blob + off[i], off[i + 1] - off[i]);
         tmp_rank.clear();
@@ -196,41 +321,41 @@ void build_taxonomy(const int64_t* taxids, const uint64_t* off, const char* blob
                 ok = false;
                 break;
             }
-            std::string rraw(part.substr(0, k));
-            std::string ident(part.substr(k + 2));
-            uint32_t rid;
-            auto it = rank_raw.find(rraw);
-            if (it != rank_raw.end())
-                rid = it->second;
+            const std::string_view rraw = part.substr(0, k), ident = part.substr(k + 2);
+            bool fresh = false;
+            // neighbouring lineages mostly carry the same rank name at the same depth: one compare instead of a lookup
+            const size_t depth = std::min<size_t>(tmp_rank.size(), 64);
+            uint32_t raw;
+            if (memo_raw_id[depth] != 0xFFFFFFFFu && memo_raw[depth] == rraw)
+                raw = memo_raw_id[depth];
             else {
-                RankInfo ri;
+                raw = rank_raw.intern(rraw, &fresh);
+                memo_raw[depth] = rraw, memo_raw_id[depth] = raw;
+            }
+            if (fresh) {
+                int64_t rid = -1;  // the reference would panic while parsing this lineage; only fatal if a top row uses it
                 try {
-                    ri = rank_from_str(rraw);
+                    RankInfo ri = rank_from_str(rraw);
+                    std::string canon = ri.def >= 0 ? std::string("D") + std::to_string(ri.def) : "O" + ri.slug;
+                    auto ic = rank_canon.find(canon);
+                    if (ic != rank_canon.end())
+                        rid = ic->second;
+                    else {
+                        rid = (int64_t)T.ranks.size();
+                        T.ranks.push_back(ri);
+                        rank_canon.emplace(canon, (uint32_t)rid);
+                    }
                 } catch (const DataErr&) {
-                    ok = false;  // the reference would panic while parsing this lineage; only fatal if a top row uses it
-                    break;
                 }
-                std::string canon = ri.def >= 0 ? std::string("D") + std::to_string(ri.def) : "O" + ri.slug;
-                auto ic = rank_canon.find(canon);
-                if (ic != rank_canon.end())
-                    rid = ic->second;
-                else {
-                    rid = (uint32_t)T.ranks.size();
-                    T.ranks.push_back(ri);
-                    rank_canon.emplace(canon, rid);
-                }
-                rank_raw.emplace(rraw, rid);
+                raw_rid.push_back(rid);
             }
-            uint32_t iid;
-            auto ii = ident_id.find(ident);
-            if (ii != ident_id.end())
-                iid = ii->second;
-            else {
-                iid = (uint32_t)T.idents.size();
-                T.idents.push_back(ident);
-                ident_id.emplace(std::move(ident), iid);
+            if (raw_rid[raw] < 0) {
+                ok = false;
+                break;
             }
-            tmp_rank.push_back(rid);
+            const uint32_t iid = ident_id.intern(ident, &fresh);
+            if (fresh) T.idents.emplace_back(ident);
+            tmp_rank.push_back((uint32_t)raw_rid[raw]);
             tmp_ident.push_back(iid);
             if (semi == std::string_view::npos) break;
             pos = semi + 1;
@@ -242,38 +367,34 @@ void build_taxonomy(const int64_t* taxids, const uint64_t* off, const char* blob
             for (size_t j = 0; j < tmp_rank.size(); j++) {
                 T.pos_rank.push_back(tmp_rank[j]);
                 T.pos_ident.push_back(tmp_ident[j]);
-                uint64_t pk = ((uint64_t)tmp_rank[j] << 32) | tmp_ident[j];
-                auto ip = pair_id.find(pk);
-                uint32_t pid;
-                if (ip != pair_id.end())
-                    pid = ip->second;
-                else {
-                    pid = (uint32_t)pairs.size();
-                    pairs.push_back({tmp_rank[j], tmp_ident[j]});
-                    pair_id.emplace(pk, pid);
-                }
+                bool fresh;
+                const uint32_t pid = pair_id.intern(((uint64_t)tmp_rank[j] << 32) | tmp_ident[j], &fresh);
+                if (fresh) pairs.push_back({tmp_rank[j], tmp_ident[j]});
                 pos_pair.push_back(pid);
             }
             // cutoffs: a pure function of the rank vector -> memoised
-            std::string key((const char*)tmp_rank.data(), tmp_rank.size() * 4);
-            auto im = interp_memo.find(key);
+            memo_key.assign((const char*)tmp_rank.data(), tmp_rank.size() * 4);
+            auto im = interp_memo.find(memo_key);
             if (im == interp_memo.end()) {
                 rk.clear();
                 for (uint32_t r : tmp_rank) rk.push_back(&T.ranks[r]);
-                im = interp_memo.emplace(key, interpolate_cutoffs(rk, bb)).first;
+                im = interp_memo.emplace(memo_key, interpolate_cutoffs(rk, bb)).first;
             }
             T.cut.insert(T.cut.end(), im->second.begin(), im->second.end());
         }
         T.lin_off.push_back((uint32_t)T.pos_rank.size());
     }
     // string dictionaries over the distinct (rank, identifier) pairs
-    std::unordered_map<std::string, uint32_t> lvl_dict, bean_dict;
+    StrInterner lvl_dict(pairs.size()), bean_dict(pairs.size());
     std::vector<uint32_t> pair_lvl(pairs.size()), pair_bean(pairs.size());
+    std::string tmp;
     for (size_t p = 0; p < pairs.size(); p++) {
         const std::string& d = T.ranks[pairs[p].first].display;
         const std::string& id = T.idents[pairs[p].second];
-        pair_lvl[p] = lvl_dict.emplace(d + id, (uint32_t)lvl_dict.size()).first->second;            // fmtc.rs:153-157
-        pair_bean[p] = bean_dict.emplace(d + "__" + id, (uint32_t)bean_dict.size()).first->second;  // consensus_result.rs:70-73
+        tmp.assign(d).append(id);
+        pair_lvl[p] = lvl_dict.intern(tmp);  // fmtc.rs:153-157
+        tmp.assign(d).append("__").append(id);
+        pair_bean[p] = bean_dict.intern(tmp);  // consensus_result.rs:70-73
     }
     // identifier order (String cmp = bytewise) for the bean sort (bbci.rs:50-60)
     std::vector<uint32_t> iord(T.idents.size());
@@ -573,6 +694,254 @@ void read_custom_cutoffs(const char* path, Cutoffs& out) {
     if (v[7] == BLU_CUTOFF_ABSENT) throw DataErr("Could not parse custom taxon file: missing field `species`");
     out.has_custom = true;
     for (int i = 0; i < 8; i++) out.custom[i] = v[i];
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------
+// Side-car cache.  Layout (native little-endian): CacheHeader, then the sections in the order of write_all() below,
+// each vector as u64 count + raw elements; strings as u32 length + bytes.  `payload_hash` covers everything behind
+// the header, `file_size` the whole file, so a cut-off or bit-flipped cache is rejected.
+namespace {
+
+constexpr uint64_t kCacheMagic = 0x3143584154554C42ull;  // "BLUTAXC1"
+constexpr uint32_t kCacheVersion = 1;
+
+struct CacheHeader {
+    uint64_t magic;
+    uint32_t version, header_bytes;
+    TaxCacheKey key;
+    uint64_t file_size, payload_hash;
+};
+
+// four independent multiply-xorshift lanes over 32-byte blocks (~ memory speed), folded at the end
+struct StreamHash {
+    uint64_t h[4] = {0x243F6A8885A308D3ull, 0x13198A2E03707344ull, 0xA4093822299F31D0ull, 0x082EFA98EC4E6C89ull};
+    uint64_t total = 0;
+    unsigned char tail[32];
+    size_t n_tail = 0;
+
+    static uint64_t step(uint64_t h, uint64_t w) {
+        h = (h ^ w) * 0x9E3779B97F4A7C15ull;
+        return h ^ (h >> 29);
+    }
+    void block(const unsigned char* p) {
+        uint64_t w[4];
+        memcpy(w, p, 32);
+        for (int i = 0; i < 4; i++) h[i] = step(h[i], w[i]);
+    }
+    void update(const void* data, size_t n) {
+        const unsigned char* p = (const unsigned char*)data;
+        total += n;
+        if (n_tail) {
+            size_t take = std::min(n, 32 - n_tail);
+            memcpy(tail + n_tail, p, take);
+            n_tail += take, p += take, n -= take;
+            if (n_tail < 32) return;
+            block(tail);
+            n_tail = 0;
+        }
+        for (; n >= 32; p += 32, n -= 32) block(p);
+        if (n) memcpy(tail, p, n), n_tail = n;
+    }
+    uint64_t finish() {
+        if (n_tail) {
+            memset(tail + n_tail, 0, 32 - n_tail);
+            block(tail);
+        }
+        uint64_t x = total;
+        for (int i = 0; i < 4; i++) x = mix64(x ^ h[i]);
+        return x;
+    }
+};
+
+struct FileCloser {
+    FILE* f;
+    ~FileCloser() {
+        if (f) fclose(f);
+    }
+};
+
+struct CacheWriter {
+    FILE* f;
+    StreamHash hash;
+    void raw(const void* p, size_t n) {
+        if (n && fwrite(p, 1, n, f) != n) throw IoErr("could not write the taxonomy cache (disk full?)");
+        hash.update(p, n);
+    }
+    template <class T>
+    void vec(const std::vector<T>& v) {
+        const uint64_t n = v.size();
+        raw(&n, 8);
+        raw(v.data(), n * sizeof(T));
+    }
+    void str(const std::string& s) {
+        const uint32_t n = (uint32_t)s.size();
+        raw(&n, 4);
+        raw(s.data(), n);
+    }
+};
+
+// reads straight from the file into the destination vectors, hashing as it goes; `left` = payload bytes not yet read
+struct CacheReader {
+    FILE* f;
+    uint64_t left;
+    StreamHash hash;
+    void raw(void* dst, size_t n) {
+        if (left < n || (n && fread(dst, 1, n, f) != n)) throw IoErr("taxonomy cache is truncated");
+        left -= n;
+        hash.update(dst, n);
+    }
+    template <class T>
+    void vec(std::vector<T>& v) {
+        uint64_t n;
+        raw(&n, 8);
+        if (n > left / sizeof(T)) throw IoErr("taxonomy cache is truncated");
+        v.resize(n);
+        raw(v.data(), n * sizeof(T));
+    }
+    void str(std::string& s) {
+        uint32_t n;
+        raw(&n, 4);
+        if (n > left) throw IoErr("taxonomy cache is truncated");
+        s.resize(n);
+        raw(s.data(), n);
+    }
+};
+
+bool same_key(const TaxCacheKey& a, const TaxCacheKey& b) {
+    if (a.json_size != b.json_size || a.json_hash != b.json_hash || a.use_taxid != b.use_taxid || a.taxon != b.taxon || a.has_custom != b.has_custom)
+        return false;
+    if (a.has_custom)
+        for (int i = 0; i < 8; i++)
+            if (a.custom[i] != b.custom[i]) return false;
+    return true;
+}
+
+}  // namespace
+
+uint64_t hash_file(const char* path, uint64_t* size) {
+    FileCloser fc{fopen(path, "rb")};
+    if (!fc.f) throw IoErr(std::string("Taxonomies file not found: ") + path);
+    std::vector<char> buf(4 << 20);
+    StreamHash h;
+    for (;;) {
+        size_t n = fread(buf.data(), 1, buf.size(), fc.f);
+        h.update(buf.data(), n);
+        if (n < buf.size()) {
+            if (ferror(fc.f)) throw IoErr("Unexpected error on read `Taxonomies` file");
+            break;
+        }
+    }
+    if (size) *size = h.total;
+    return h.finish();
+}
+
+TaxCacheKey make_cache_key(const char* json_path, bool use_taxid, const Cutoffs& cut) {
+    TaxCacheKey k;
+    k.json_hash = hash_file(json_path, &k.json_size);
+    k.use_taxid = use_taxid ? 1 : 0;
+    k.taxon = cut.taxon;
+    k.has_custom = cut.has_custom ? 1 : 0;
+    for (int i = 0; i < 8; i++) k.custom[i] = cut.has_custom ? cut.custom[i] : 0;
+    return k;
+}
+
+void save_taxonomy_cache(const char* cache_path, const TaxCacheKey& key, const HostTaxonomy& T) {
+    const std::string tmp = std::string(cache_path) + ".tmp." + std::to_string((long long)getpid());
+    CacheHeader hd{};
+    hd.magic = kCacheMagic;
+    hd.version = kCacheVersion;
+    hd.header_bytes = sizeof(CacheHeader);
+    hd.key = key;
+    try {
+        FileCloser fc{fopen(tmp.c_str(), "wb")};
+        if (!fc.f) throw IoErr("could not create the taxonomy cache " + tmp);
+        if (fwrite(&hd, 1, sizeof hd, fc.f) != sizeof hd) throw IoErr("could not write the taxonomy cache");
+        CacheWriter w{fc.f, StreamHash{}};
+        const uint64_t n_ranks = T.ranks.size();
+        w.raw(&n_ranks, 8);
+        for (const RankInfo& r : T.ranks) {
+            const int32_t def = r.def;
+            w.raw(&def, 4);
+            w.str(r.slug);
+            w.str(r.display);
+            w.str(r.full);
+        }
+        // identifiers: lengths, then one blob
+        std::vector<uint32_t> len(T.idents.size());
+        std::vector<char> blob;
+        size_t total = 0;
+        for (size_t i = 0; i < T.idents.size(); i++) total += T.idents[i].size(), len[i] = (uint32_t)T.idents[i].size();
+        blob.reserve(total);
+        for (const std::string& s : T.idents) blob.insert(blob.end(), s.begin(), s.end());
+        w.vec(len);
+        w.vec(blob);
+        w.vec(T.taxids), w.vec(T.lin_off), w.vec(T.lin_ok);
+        w.vec(T.pos_rank), w.vec(T.pos_ident), w.vec(T.lvl_key), w.vec(T.bean_key), w.vec(T.ident_rank);
+        w.vec(T.cut), w.vec(T.rank_cls), w.vec(T.allowed_cls), w.vec(T.slots);
+        w.raw(&T.hash_mask, 4);
+        hd.file_size = sizeof hd + w.hash.total;
+        hd.payload_hash = w.hash.finish();
+        if (fseek(fc.f, 0, SEEK_SET) != 0 || fwrite(&hd, 1, sizeof hd, fc.f) != sizeof hd || fflush(fc.f) != 0)
+            throw IoErr("could not write the taxonomy cache");
+    } catch (...) {
+        remove(tmp.c_str());
+        throw;
+    }
+    if (rename(tmp.c_str(), cache_path) != 0) {
+        remove(tmp.c_str());
+        throw IoErr(std::string("could not move the taxonomy cache into place: ") + cache_path);
+    }
+}
+
+bool load_taxonomy_cache(const char* cache_path, const TaxCacheKey& key, HostTaxonomy& T) {
+    FileCloser fc{fopen(cache_path, "rb")};
+    if (!fc.f) return false;
+    CacheHeader hd;
+    if (fread(&hd, 1, sizeof hd, fc.f) != sizeof hd) return false;
+    if (hd.magic != kCacheMagic || hd.version != kCacheVersion || hd.header_bytes != sizeof(CacheHeader) || !same_key(hd.key, key)) return false;
+    struct stat st;
+    if (fstat(fileno(fc.f), &st) != 0 || (uint64_t)st.st_size != hd.file_size || hd.file_size < sizeof hd) return false;
+    try {
+        T = HostTaxonomy();
+        CacheReader r{fc.f, hd.file_size - sizeof hd, StreamHash{}};
+        uint64_t n_ranks;
+        r.raw(&n_ranks, 8);
+        if (n_ranks > 65536) throw IoErr("bad rank count");
+        T.ranks.resize(n_ranks);
+        for (RankInfo& ri : T.ranks) {
+            int32_t def;
+            r.raw(&def, 4);
+            ri.def = def;
+            r.str(ri.slug), r.str(ri.display), r.str(ri.full);
+        }
+        std::vector<uint32_t> len;
+        std::vector<char> blob;
+        r.vec(len);
+        r.vec(blob);
+        T.idents.resize(len.size());
+        uint64_t at = 0;
+        for (size_t i = 0; i < len.size(); i++) {
+            if (at + len[i] > blob.size()) throw IoErr("bad identifier table");
+            T.idents[i].assign(blob.data() + at, len[i]);
+            at += len[i];
+        }
+        r.vec(T.taxids), r.vec(T.lin_off), r.vec(T.lin_ok);
+        r.vec(T.pos_rank), r.vec(T.pos_ident), r.vec(T.lvl_key), r.vec(T.bean_key), r.vec(T.ident_rank);
+        r.vec(T.cut), r.vec(T.rank_cls), r.vec(T.allowed_cls), r.vec(T.slots);
+        r.raw(&T.hash_mask, 4);
+        // shape checks: the kernels index these arrays without bounds tests
+        const size_t np = T.pos_rank.size(), nl = T.taxids.size();
+        const bool ok = r.left == 0 && r.hash.finish() == hd.payload_hash && T.lin_off.size() == nl + 1 && T.lin_ok.size() == nl &&
+                        T.lin_off.back() == np && T.pos_ident.size() == np && T.lvl_key.size() == np && T.bean_key.size() == np &&
+                        T.ident_rank.size() == np && T.cut.size() == np && T.rank_cls.size() == np && T.allowed_cls.size() == np &&
+                        T.slots.size() == (size_t)T.hash_mask + 1 && (T.slots.size() & (T.slots.size() - 1)) == 0 && T.slots.size() >= 2 * nl;
+        if (!ok) throw IoErr("taxonomy cache failed its checks");
+        return true;
+    } catch (const std::exception&) {  // IoErr, or bad_alloc / length_error from a damaged count
+        T = HostTaxonomy();
+        return false;
+    }
 }
 
 }  // namespace blu

@@ -80,6 +80,22 @@ void build_taxonomy(const int64_t* taxids, const uint64_t* off, const char* blob
 // textLineage, applies the u64 -> f64 -> i64 key cast.  Throws IoErr (maps to Err(MappedErrors)).
 void read_taxonomy_json(const char* path, bool use_taxid, std::vector<int64_t>& taxids, std::vector<uint64_t>& off, std::string& blob);
 
+// --- binary side-car cache of a built HostTaxonomy -------------------------------------
+// The reference re-parses the taxonomy JSON on every run (mod.rs:254-265).  The cache stores every array that
+// build_taxonomy() produces, keyed by the content hash of the JSON file and by everything else the arrays depend
+// on (use_taxid, cutoff backbone).  A missing, stale, truncated or corrupted cache reads as a miss, never an error.
+struct TaxCacheKey {
+    uint64_t json_size = 0, json_hash = 0;
+    int32_t use_taxid = 0, taxon = 0, has_custom = 0;
+    int32_t custom[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+// 64-bit content hash + size of a file.  Throws IoErr if it cannot be read.
+uint64_t hash_file(const char* path, uint64_t* size);
+TaxCacheKey make_cache_key(const char* json_path, bool use_taxid, const Cutoffs& cut);
+bool load_taxonomy_cache(const char* cache_path, const TaxCacheKey& key, HostTaxonomy& out);
+// Written to `<cache_path>.tmp.<pid>` and renamed into place.  Throws IoErr.
+void save_taxonomy_cache(const char* cache_path, const TaxCacheKey& key, const HostTaxonomy& T);
+
 // CustomTaxon::from_file (taxon.rs:28-65)
 void read_custom_cutoffs(const char* path, Cutoffs& out);
 

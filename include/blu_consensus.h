@@ -124,6 +124,12 @@ int blu_custom_cutoffs_from_file(const char* path, blu_opts* opts, char* err, si
 
 /* ---- taxonomy (get_taxonomies_dataframe, mod.rs:246-327; TaxonomiesMap, taxonomies_map.rs:6-32) ---------- */
 int blu_taxonomy_load_json(blu_ctx* ctx, const char* path);
+/* Same, through a binary side-car cache (the reference re-parses the JSON on every run,
+ * mod.rs:254-265).  The cache holds the encoded lineage tables and is keyed by the content hash of the JSON file,
+ * use_taxid and the cutoff options of `ctx`; a missing, stale or damaged cache is rebuilt from the JSON.
+ * cache_path == NULL means `<path>.blucache`.  *cache_state (may be NULL): 1 = loaded from the cache, 0 = built from
+ * the JSON and cache written, -1 = built from the JSON, cache could not be written (the call still succeeds). */
+int blu_taxonomy_load_json_cached(blu_ctx* ctx, const char* path, const char* cache_path, int* cache_state);
 /* Same, from memory: n lineage strings concatenated in blob, string i = blob[off[i]..off[i+1]). */
 int blu_taxonomy_load_arrays(blu_ctx* ctx, const int64_t* taxids, const uint64_t* off, const char* blob, uint64_t n);
 

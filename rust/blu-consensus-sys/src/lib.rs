@@ -31,6 +31,7 @@ extern "C" {
     pub fn blu_last_error(ctx: *const blu_ctx) -> *const c_char;
     pub fn blu_custom_cutoffs_from_file(path: *const c_char, opts: *mut blu_opts, err: *mut c_char, errlen: size_t) -> c_int;
     pub fn blu_taxonomy_load_json(ctx: *mut blu_ctx, path: *const c_char) -> c_int;
+    pub fn blu_taxonomy_load_json_cached(ctx: *mut blu_ctx, path: *const c_char, cache_path: *const c_char, cache_state: *mut c_int) -> c_int;
     pub fn blu_consensus_run_file(ctx: *mut blu_ctx, blast_out: *const c_char, out: *mut *mut blu_result) -> c_int;
     pub fn blu_consensus_run_host(ctx: *mut blu_ctx, text: *const c_char, n: u64, out: *mut *mut blu_result) -> c_int;
     pub fn blu_result_add_headers(res: *mut blu_result, headers_nl: *const c_char, len: u64) -> c_int;

@@ -294,3 +294,58 @@ extern "C" long long blu_sim_read_taxonomy_json(const char* path, int use_taxid,
         return -1;
     }
 }
+
+// Side-car taxonomy cache of the product (same sequence as blu_taxonomy_load_json_cached, minus the upload):
+// *state = 1 loaded from the cache, 0 built + written, -1 built, not writable.  *checksum covers every field of the
+// resulting HostTaxonomy, so "loaded" and "built" can be compared.
+extern "C" int blu_sim_taxonomy_cached(const char* json_path, const char* cache_path, int use_taxid, int taxon, int has_custom, const int32_t* custom8,
+                                       int* state, uint64_t* checksum, char* err, int errlen) {
+    try {
+        Cutoffs cut;
+        cut.taxon = taxon;
+        cut.has_custom = has_custom != 0;
+        if (has_custom)
+            for (int i = 0; i < 8; i++) cut.custom[i] = custom8[i];
+        const TaxCacheKey key = make_cache_key(json_path, use_taxid != 0, cut);
+        HostTaxonomy T;
+        *state = 1;
+        if (!load_taxonomy_cache(cache_path, key, T)) {
+            std::vector<int64_t> ids;
+            std::vector<uint64_t> off;
+            std::string blob;
+            read_taxonomy_json(json_path, use_taxid != 0, ids, off, blob);
+            static const uint64_t zero = 0;
+            build_taxonomy(ids.data(), ids.empty() ? &zero : off.data(), blob.data(), ids.size(), cut, T);
+            *state = 0;
+            try {
+                save_taxonomy_cache(cache_path, key, T);
+            } catch (const IoErr&) {
+                *state = -1;
+            }
+        }
+        uint64_t h = 1469598103934665603ull;
+        auto mixin = [&](const void* p, size_t n) {
+            const unsigned char* b = (const unsigned char*)p;
+            for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 1099511628211ull;
+            h = (h ^ n) * 1099511628211ull;
+        };
+        auto vec = [&](const auto& v) { mixin(v.data(), v.size() * sizeof(v[0])); };
+        for (const RankInfo& r : T.ranks) {
+            mixin(&r.def, sizeof r.def);
+            mixin(r.slug.data(), r.slug.size()), mixin(r.display.data(), r.display.size()), mixin(r.full.data(), r.full.size());
+        }
+        for (const std::string& s : T.idents) mixin(s.data(), s.size());
+        vec(T.taxids), vec(T.lin_off), vec(T.lin_ok), vec(T.pos_rank), vec(T.pos_ident), vec(T.lvl_key), vec(T.bean_key), vec(T.ident_rank);
+        vec(T.cut), vec(T.rank_cls), vec(T.allowed_cls);
+        for (const HashSlot& s : T.slots) mixin(&s.key, 8), mixin(&s.val, 4), mixin(&s.used, 4);
+        mixin(&T.hash_mask, 4);
+        *checksum = h;
+        return 0;
+    } catch (const IoErr& e) {
+        snprintf(err, errlen, "%s", e.what());
+        return 1;
+    } catch (const std::exception& e) {
+        snprintf(err, errlen, "%s", e.what());
+        return 2;
+    }
+}

@@ -102,3 +102,21 @@ def read_taxonomy_json(path: str, use_taxid: bool = False) -> int:
     if n < 0:
         raise IOError(err.value.decode())
     return n
+
+
+def taxonomy_cached(json_path: str, cache_path: str, use_taxid: bool = False, taxon: str = "bacteria", custom=None):
+    """Product's side-car cache sequence on the host.  Returns (state, checksum of the resulting tables)."""
+    l = lib()
+    l.blu_sim_taxonomy_cached.restype = C.c_int
+    l.blu_sim_taxonomy_cached.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_uint64),
+                                          C.c_char_p, C.c_int]
+    c8 = _c8(custom)
+    state, ck = C.c_int(0), C.c_uint64(0)
+    err = C.create_string_buffer(512)
+    rc = l.blu_sim_taxonomy_cached(json_path.encode(), cache_path.encode(), int(use_taxid), TAXON[taxon], 1 if c8 is not None else 0,
+                                   C.cast(c8, C.c_void_p) if c8 is not None else None, C.byref(state), C.byref(ck), err, 512)
+    if rc == 1:
+        raise IOError(err.value.decode())
+    if rc:
+        raise ValueError(err.value.decode())
+    return state.value, ck.value
