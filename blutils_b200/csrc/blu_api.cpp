@@ -541,8 +541,33 @@ void run_device(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStream_t s, bl
     // Large resident tables are processed in a few query-aligned ranges so that the download of one range's records
     // overlaps the kernels of the next (the unfinished last query of a range simply starts the next range: the
     // buffer is contiguous, nothing is copied).
-    const uint64_t n_ranges = n >= (512ull << 20) ? 4 : (n >= (128ull << 20) ? 2 : 1);
-    const uint64_t range_bytes = ((n + n_ranges - 1) / n_ranges + (uint64_t)kTile - 1) / (uint64_t)kTile * (uint64_t)kTile;
+    // Equal ranges measured best (tools/range_split.py, profiles/README.md): the step is K_1 + ... + K_n + D_n + ~0.1 ms of
+    // host round trips per range; a smaller last range makes an earlier download spill past its kernels instead.
+    // BLU_RANGE_FRACS="0.3,0.3,0.25,0.15" overrides the split (measurement knob).
+    std::vector<double> fracs(n >= (512ull << 20) ? 4 : (n >= (128ull << 20) ? 2 : 1), 1.0);
+    if (const char* ev = getenv("BLU_RANGE_FRACS")) {
+        std::vector<double> f;
+        for (const char* q = ev; *q;) {
+            char* e2 = nullptr;
+            double v = strtod(q, &e2);
+            if (e2 == q || !(v > 0)) break;
+            f.push_back(v);
+            q = *e2 == ',' ? e2 + 1 : e2;
+        }
+        if (!f.empty() && f.size() <= 64) fracs = f;
+    }
+    const uint64_t n_ranges = fracs.size();
+    std::vector<uint64_t> range_end(n_ranges);
+    {
+        double tot = 0, acc = 0;
+        for (double f : fracs) tot += f;
+        for (uint64_t i = 0; i < n_ranges; i++) {
+            acc += fracs[i];
+            const uint64_t e = (uint64_t)((double)n * (acc / tot));
+            range_end[i] = std::min<uint64_t>(n, (e + (uint64_t)kTile - 1) / (uint64_t)kTile * (uint64_t)kTile);
+        }
+        range_end[n_ranges - 1] = n;
+    }
     Downloader dl(c, r);
     for (int attempt = 0; attempt < 6; attempt++) {
         ensure_out(c, k);
@@ -556,7 +581,7 @@ void run_device(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStream_t s, bl
         Counters h{};
         for (uint64_t ri = 0; ri < n_ranges && !retry; ri++) {
             const bool final_range = ri + 1 == n_ranges;
-            const uint64_t end = final_range ? n : std::min<uint64_t>(n, (ri + 1) * range_bytes);
+            const uint64_t end = range_end[ri];
             if (end <= begin && !final_range) continue;
             if (ri) reset_counters_async(c, s, false);
             launch_chunk(c, dtext, begin, end, final_range, k, s, rec_done, true);
