@@ -5,9 +5,15 @@
 // blu_kernels.cu; without a CUDA device every compute entry point fails with BLU_ERR_CUDA.
 #include <cuda_runtime.h>
 
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <cerrno>
 #include <cstdio>
 #include <cstring>
 #include <filesystem>
@@ -471,12 +477,20 @@ void read_counters(blu_ctx* c, cudaStream_t s) {
     CK(cudaStreamSynchronize(s));
 }
 
-bool grow_caps(const Counters& h, Caps& k, uint64_t defer_seen) {
+// `scale` = whole input / part of it the counters cover (>= 1): records, slots and pool bytes are cumulative over the
+// chunks / ranges processed so far, so the new capacity is extrapolated to the whole input -- otherwise a table of tiny
+// rows in many chunks needs one retry per chunk.  `n_bytes` bounds the extrapolation (a row has >= 26 bytes).
+bool grow_caps(const Counters& h, Caps& k, uint64_t defer_seen, double scale, uint64_t n_bytes) {
     bool grew = false;
-    if (n_rec_of(h) > k.rec) k.rec = (size_t)n_rec_of(h) + n_rec_of(h) / 8 + 1024, grew = true;
-    if (n_slots_of(h) > k.slots) k.slots = (size_t)n_slots_of(h) + n_slots_of(h) / 8 + 1024, grew = true;
+    scale = std::max(1.0, scale);
+    auto want = [&](uint64_t seen, uint64_t slack, uint64_t bound) {
+        const double w = (double)seen * scale * 1.125 + (double)slack;
+        return (size_t)std::max<double>((double)seen + (double)slack, std::min<double>(w, (double)bound + (double)slack));
+    };
+    if (n_rec_of(h) > k.rec) k.rec = want(n_rec_of(h), 1024, n_bytes / 26), grew = true;
+    if (n_slots_of(h) > k.slots) k.slots = want(n_slots_of(h), 1024, n_bytes / 26), grew = true;
     if (defer_seen > k.defer) k.defer = (size_t)defer_seen + defer_seen / 8 + 1024, grew = true;
-    if (h.pool_used > k.pool) k.pool = (size_t)h.pool_used + h.pool_used / 8 + 4096, grew = true;
+    if (h.pool_used > k.pool) k.pool = want(h.pool_used, 4096, n_bytes), grew = true;
     if (!grew) {  // overflow flagged but counts look fine (reservation raced past the cap): grow everything
         k.rec *= 2, k.slots *= 2, k.defer *= 2, k.pool *= 2;
     }
@@ -569,7 +583,7 @@ void run_device(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStream_t s, bl
         range_end[n_ranges - 1] = n;
     }
     Downloader dl(c, r);
-    for (int attempt = 0; attempt < 6; attempt++) {
+    for (int attempt = 0; attempt < 8; attempt++) {
         ensure_out(c, k);
         reset_counters_async(c, s, true);
         bool retry = false;
@@ -593,7 +607,7 @@ void run_device(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStream_t s, bl
             defer_total = std::max<uint64_t>(defer_total, h.n_defer);
             c->tm.n_deferred_runs += h.n_defer;
             if (h.cap_overflow || n_rec_of(h) > k.rec || n_slots_of(h) > k.slots || h.n_defer > k.defer) {
-                grow_caps(h, k, h.n_defer);
+                grow_caps(h, k, h.n_defer, (double)n / (double)std::max<uint64_t>(end, 1), n);
                 retry = true;
                 break;
             }
@@ -607,7 +621,7 @@ void run_device(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStream_t s, bl
             h = *c->h_ctr;
             ms_post += ev_ms(c->ev[3], c->ev[4]);
             if (h.cap_overflow || h.pool_used > k.pool) {
-                grow_caps(h, k, defer_total);
+                grow_caps(h, k, defer_total, (double)n / (double)std::max<uint64_t>(end, 1), n);
                 retry = true;
                 break;
             }
@@ -645,12 +659,150 @@ void run_device(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStream_t s, bl
     throw std::runtime_error("output capacity did not converge");
 }
 
+// --- where the streamed path takes the text of chunk `ci` from -------------------------------------------------
+struct ChunkSource {
+    virtual ~ChunkSource() = default;
+    virtual const char* acquire(uint64_t ci) = 0;  // host pointer to chunk ci (may block until it is there)
+    virtual void release(uint64_t) {}              // the host->device copy of chunk ci has completed
+    virtual void restart() {}                      // the run starts over from chunk 0 (no copy is in flight)
+};
+
+struct MemorySource : ChunkSource {
+    const char* text;
+    uint64_t chunk;
+    MemorySource(const char* t, uint64_t ch) : text(t), chunk(ch) {}
+    const char* acquire(uint64_t ci) override { return text + ci * chunk; }
+};
+
+// A file, read by parallel pread()s into a ring of three pinned staging buffers while earlier chunks are copied to
+// the device and processed: the file never has to fit in (pinned) host memory, and reading overlaps everything else.
+class FileSource : public ChunkSource {
+    static constexpr uint64_t kRing = 3;
+    blu_ctx* c_;
+    int fd_;
+    uint64_t n_, chunk_, n_chunks_;
+    int n_readers_;
+    PinnedBuf buf_[kRing];
+    std::mutex mu_;
+    std::condition_variable cv_;
+    uint64_t staged_ = 0;    // chunks [0, staged_) of this epoch are in their buffers
+    uint64_t released_ = 0;  // chunks [0, released_) may be overwritten
+    uint64_t epoch_ = 0;
+    bool stop_ = false;
+    std::string error_;
+    std::thread coordinator_;
+
+    bool read_span(char* dst, uint64_t off, uint64_t len, std::string& err) const {
+        while (len) {
+            ssize_t got = pread(fd_, dst, (size_t)std::min<uint64_t>(len, 1ull << 30), (off_t)off);
+            if (got < 0 && errno == EINTR) continue;
+            if (got <= 0) {
+                err = got == 0 ? "the blast output shrank while it was read" : std::string("read error on the blast output: ") + strerror(errno);
+                return false;
+            }
+            dst += got, off += (uint64_t)got, len -= (uint64_t)got;
+        }
+        return true;
+    }
+    bool read_chunk(uint64_t ci, std::string& err) const {
+        char* dst = (char*)buf_[ci % kRing].p;
+        const uint64_t off = ci * chunk_, len = std::min(chunk_, n_ - off);
+        const uint64_t slice = std::max<uint64_t>(((len + n_readers_ - 1) / n_readers_ + 4095) & ~4095ull, 1ull << 20);
+        std::vector<std::thread> th;
+        std::vector<std::string> errs((size_t)n_readers_);
+        std::atomic<bool> ok{true};
+        int t = 0;
+        for (uint64_t o = slice; o < len; o += slice, t++)
+            th.emplace_back([&, o, t] {
+                if (!read_span(dst + o, off + o, std::min(slice, len - o), errs[(size_t)t])) ok = false;
+            });
+        std::string e0;
+        if (!read_span(dst, off, std::min(slice, len), e0)) ok = false;
+        for (auto& x : th) x.join();
+        if (!ok) {
+            err = e0;
+            for (auto& e : errs)
+                if (err.empty()) err = e;
+        }
+        return ok;
+    }
+    void run() {
+        uint64_t my_epoch = 0, next = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || epoch_ != my_epoch || (next < n_chunks_ && next < released_ + kRing); });
+                if (stop_) return;
+                if (epoch_ != my_epoch) {
+                    my_epoch = epoch_, next = 0;
+                    continue;
+                }
+            }
+            std::string err;
+            const bool ok = read_chunk(next, err);
+            {
+                std::lock_guard<std::mutex> g(mu_);
+                if (epoch_ == my_epoch) {
+                    if (ok)
+                        staged_ = next + 1;
+                    else
+                        error_ = err;
+                }
+            }
+            cv_.notify_all();
+            next = ok ? next + 1 : n_chunks_;  // after an error: idle until restart() or the destructor
+        }
+    }
+
+   public:
+    FileSource(blu_ctx* c, int fd, uint64_t n, uint64_t chunk) : c_(c), fd_(fd), n_(n), chunk_(chunk), n_chunks_((n + chunk - 1) / chunk) {
+        const unsigned hc = std::thread::hardware_concurrency();
+        n_readers_ = (int)std::min<unsigned>(8, std::max<unsigned>(1, hc ? hc : 4));
+        if (const char* ev = getenv("BLU_READ_THREADS")) n_readers_ = std::max(1, std::min(64, atoi(ev)));
+        const uint64_t used = std::min<uint64_t>(kRing, n_chunks_);
+        for (uint64_t i = 0; i < used; i++) buf_[i] = c->acquire(std::min(chunk, n));
+        coordinator_ = std::thread([this] { run(); });
+    }
+    ~FileSource() override {
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        coordinator_.join();
+        for (auto& b : buf_) c_->pool->release(b);
+    }
+    const char* acquire(uint64_t ci) override {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return staged_ > ci || !error_.empty(); });
+        if (staged_ <= ci) throw IoErr(error_);
+        return (const char*)buf_[ci % kRing].p;
+    }
+    void release(uint64_t ci) override {
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            released_ = std::max(released_, ci + 1);
+        }
+        cv_.notify_all();
+    }
+    void restart() override {
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            epoch_++;
+            staged_ = released_ = 0;
+            error_.clear();
+        }
+        cv_.notify_all();
+    }
+};
+
 // --- text on the host: chunked, double-buffered H2D overlapped with the kernels --------------------------------
-void run_host(blu_ctx* c, const char* text, uint64_t n, blu_result* r) {
+inline uint64_t chunk_bytes_of(const blu_ctx* c, uint64_t dflt) { return c->opts.chunk_bytes ? ((c->opts.chunk_bytes + 127) & ~127ull) : dflt; }
+
+void run_host_chunks(blu_ctx* c, ChunkSource& src, uint64_t n, const uint64_t chunk, blu_result* r) {
     require_ready(c);
     if (n == 0) throw DataErr("empty blast output (the reference's CsvReader fails on an empty file)");
     c->tm = blu_timings{};
-    const uint64_t chunk = c->opts.chunk_bytes ? ((c->opts.chunk_bytes + 127) & ~127ull) : (256ull << 20);
     const uint64_t carry = c->carry_bytes;
     const uint64_t n_chunks = (n + chunk - 1) / chunk;
     const bool single = n_chunks == 1;
@@ -662,7 +814,7 @@ void run_host(blu_ctx* c, const char* text, uint64_t n, blu_result* r) {
     cudaStream_t s = c->stream, cs = c->copy_stream;
     Downloader dl(c, r);
     auto t0 = std::chrono::steady_clock::now();
-    for (int attempt = 0; attempt < 6; attempt++) {
+    for (int attempt = 0; attempt < 8; attempt++) {
         ensure_out(c, k);
         reset_counters_async(c, s, true);
         bool retry = false;
@@ -673,7 +825,7 @@ void run_host(blu_ctx* c, const char* text, uint64_t n, blu_result* r) {
         uint64_t launches = 0;
         auto issue_h2d = [&](uint64_t ci) {
             const uint64_t off = ci * chunk, len = std::min(chunk, n - off);
-            CK(cudaMemcpyAsync(c->d_text[ci & 1].p + text_off, text + off, len, cudaMemcpyHostToDevice, cs));
+            CK(cudaMemcpyAsync(c->d_text[ci & 1].p + text_off, src.acquire(ci), len, cudaMemcpyHostToDevice, cs));
             CK(cudaEventRecord(c->ev_h2d[ci & 1], cs));
             c->tm.h2d_bytes += len;
         };
@@ -690,20 +842,21 @@ void run_host(blu_ctx* c, const char* text, uint64_t n, blu_result* r) {
                 CK(cudaMemcpyAsync(buf + text_off - tail_len, prev + prev_end - tail_len, tail_len, cudaMemcpyDeviceToDevice, s));
             }
             CK(cudaEventRecord(c->ev_free[(ci + 1) & 1], s));  // previous buffer no longer read after this point
-            if (!final_chunk) {
-                CK(cudaStreamWaitEvent(cs, c->ev_free[(ci + 1) & 1], 0));
-                issue_h2d(ci + 1);
-            }
             if (ci) reset_counters_async(c, s, false);
             const uint64_t begin = text_off - tail_len, end = text_off + len;
             launch_chunk(c, buf, begin, end, final_chunk, k, s, rec_done, true);
+            if (!final_chunk) {  // behind the launches: a file source may block here until the next chunk has been read
+                CK(cudaStreamWaitEvent(cs, c->ev_free[(ci + 1) & 1], 0));
+                issue_h2d(ci + 1);
+            }
             read_counters(c, s);
+            src.release(ci);  // `s` waited for this chunk's copy, so it has completed
             Counters h = *c->h_ctr;
             ms_tile += ev_ms(c->ev[0], c->ev[1]);
             ms_long += ev_ms(c->ev[1], c->ev[2]);
             defer_total = std::max<uint64_t>(defer_total, h.n_defer);
             if (h.cap_overflow || n_rec_of(h) > k.rec || n_slots_of(h) > k.slots || h.n_defer > k.defer) {
-                grow_caps(h, k, h.n_defer);
+                grow_caps(h, k, h.n_defer, (double)n / (double)(off + len), n);
                 retry = true;
                 break;
             }
@@ -727,7 +880,7 @@ void run_host(blu_ctx* c, const char* text, uint64_t n, blu_result* r) {
             if (!final_chunk) {
                 const Counters hg = *c->h_ctr;
                 if (hg.cap_overflow || hg.pool_used > k.pool) {
-                    grow_caps(hg, k, defer_total);
+                    grow_caps(hg, k, defer_total, (double)n / (double)(off + len), n);
                     retry = true;
                     break;
                 }
@@ -742,6 +895,7 @@ void run_host(blu_ctx* c, const char* text, uint64_t n, blu_result* r) {
             CK(cudaStreamSynchronize(cs));
             CK(cudaStreamSynchronize(s));
             dl.abandon();
+            src.restart();
             c->tm = blu_timings{};
             continue;
         }
@@ -749,8 +903,9 @@ void run_host(blu_ctx* c, const char* text, uint64_t n, blu_result* r) {
         read_counters(c, s);
         Counters h = *c->h_ctr;
         if (h.cap_overflow || h.pool_used > k.pool) {
-            grow_caps(h, k, defer_total);
+            grow_caps(h, k, defer_total, 1.0, n);
             dl.abandon();
+            src.restart();
             c->tm = blu_timings{};
             continue;
         }
@@ -771,6 +926,24 @@ void run_host(blu_ctx* c, const char* text, uint64_t n, blu_result* r) {
         return;
     }
     throw std::runtime_error("output capacity did not converge");
+}
+
+// On any failure nothing may still be reading the caller's text (or a staging buffer) when the call returns.
+void run_host_source(blu_ctx* c, ChunkSource& src, uint64_t n, uint64_t chunk, blu_result* r) {
+    try {
+        run_host_chunks(c, src, n, chunk, r);
+    } catch (...) {
+        cudaStreamSynchronize(c->copy_stream);
+        cudaStreamSynchronize(c->stream);
+        cudaStreamSynchronize(c->d2h_stream);
+        throw;
+    }
+}
+
+void run_host(blu_ctx* c, const char* text, uint64_t n, blu_result* r) {
+    const uint64_t chunk = chunk_bytes_of(c, 256ull << 20);
+    MemorySource src(text, chunk);
+    run_host_source(c, src, n, chunk, r);
 }
 
 }  // namespace
@@ -973,25 +1146,63 @@ int blu_consensus_run_host(blu_ctx* c, const char* text, uint64_t n, blu_result*
     return BLU_OK;
 }
 
+// Streams the file (FileSource); only a non-contiguous table (regrouping needs all rows at once) is read whole.
 int blu_consensus_run_file(blu_ctx* c, const char* path, blu_result** out) {
     if (!c || !path || !out) return fail(c, BLU_ERR_ARG, "null argument");
-    std::ifstream f(path, std::ios::binary);
-    if (!f) return fail(c, BLU_ERR_IO, "Unexpected error occurred on load table.");  // mod.rs:357-364
-    f.seekg(0, std::ios::end);
-    std::streamoff n = f.tellg();
-    f.seekg(0);
-    void* pinned = nullptr;
-    if (n > 0) {
-        cudaSetDevice(c->device);
-        if (cudaHostAlloc(&pinned, (size_t)n, cudaHostAllocDefault) != cudaSuccess) return fail(c, BLU_ERR_CUDA, "cudaHostAlloc failed");
-        if (!f.read((char*)pinned, n)) {
-            cudaFreeHost(pinned);
-            return fail(c, BLU_ERR_IO, "Unexpected error occurred on load table.");
+    *out = nullptr;
+    struct Fd {
+        int fd;
+        ~Fd() {
+            if (fd >= 0) close(fd);
         }
+    } f{open(path, O_RDONLY | O_CLOEXEC)};
+    struct stat st;
+    if (f.fd < 0 || fstat(f.fd, &st) != 0 || !S_ISREG(st.st_mode))
+        return fail(c, BLU_ERR_IO, "Unexpected error occurred on load table.");  // mod.rs:357-364
+    const uint64_t n = (uint64_t)st.st_size;
+    auto r = std::make_unique<blu_result>();
+    r->pinned = c->pool;
+    bool regroup = false;
+    int rc = guarded(c, [&] {
+        CK(cudaSetDevice(c->device));
+        r->tax = c->tax;
+        r->cut = c->cut;
+        require_ready(c);
+        if (n == 0) throw DataErr("empty blast output (the reference's CsvReader fails on an empty file)");
+        try {
+            const uint64_t chunk = chunk_bytes_of(c, 64ull << 20);
+            FileSource src(c, f.fd, n, chunk);
+            run_host_source(c, src, n, chunk, r.get());
+        } catch (const NonContiguous&) {
+            regroup = true;
+        }
+    });
+    if (rc == BLU_OK && regroup) {
+        rc = guarded(c, [&] {
+            std::string all((size_t)n, '\0');
+            for (uint64_t off = 0; off < n;) {
+                ssize_t got = pread(f.fd, all.data() + off, (size_t)std::min<uint64_t>(n - off, 1ull << 30), (off_t)off);
+                if (got < 0 && errno == EINTR) continue;
+                if (got <= 0) throw IoErr("Unexpected error occurred on load table.");
+                off += (uint64_t)got;
+            }
+            std::string re = regroup_by_query(all.data(), n);
+            std::string().swap(all);
+            blu_result_free(r.release());  // whatever the streamed attempt had downloaded
+            r = std::make_unique<blu_result>();
+            r->pinned = c->pool;
+            r->tax = c->tax;
+            r->cut = c->cut;
+            run_host(c, re.data(), re.size(), r.get());
+            c->tm.n_regrouped = 1;
+        });
     }
-    int rc = blu_consensus_run_host(c, (const char*)pinned, (uint64_t)n, out);
-    if (pinned) cudaFreeHost(pinned);
-    return rc;
+    if (rc != BLU_OK) {
+        blu_result_free(r.release());
+        return rc;
+    }
+    *out = r.release();
+    return BLU_OK;
 }
 
 int blu_result_add_headers(blu_result* r, const char* headers_nl, uint64_t len) {

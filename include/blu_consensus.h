@@ -139,7 +139,10 @@ int blu_consensus_run_host(blu_ctx* ctx, const char* text, uint64_t n_bytes, blu
 /* Text already resident in device memory of ctx's device.  `dtext` must be 16-byte aligned and readable up to
  * n_bytes rounded up to 128.  `stream` is a cudaStream_t (NULL = the context's own stream). */
 int blu_consensus_run_device(blu_ctx* ctx, const void* dtext, uint64_t n_bytes, void* stream, blu_result** out);
-/* ParallelBlastOutput.output_file (parallel_blast_output.rs:3-7): reads the file and runs the host path. */
+/* ParallelBlastOutput.output_file (parallel_blast_output.rs:3-7).  The file is streamed: parallel pread()s fill a ring of
+ * three pinned staging buffers (opts.chunk_bytes each, default 64 MiB; BLU_READ_THREADS readers, default 8) while
+ * earlier chunks are copied to the device and processed, so it never has to fit in host memory.  Only a table whose
+ * queries are not contiguous is read whole (regrouping needs every row). */
 int blu_consensus_run_file(blu_ctx* ctx, const char* blast_out_path, blu_result** out);
 /* ParallelBlastOutput.headers: '\n'-separated query ids; ids without hits become NoConsensusFound
  * (mod.rs:84-102).  Call before serialising. */
