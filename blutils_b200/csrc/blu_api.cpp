@@ -472,6 +472,8 @@ void launch_dup(blu_ctx* c, uint32_t n_rec, cudaStream_t s) {
     c->tm.n_kernel_launches += 1;
 }
 
+// Tried and dropped (profiles/README.md): a one-thread kernel writing the counters to mapped host memory with the host
+// spinning on a sequence word, to avoid the copy engine and the stream-synchronise wake-up: no measurable difference.
 void read_counters(blu_ctx* c, cudaStream_t s) {
     CK(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -545,6 +547,50 @@ struct NonContiguous : std::runtime_error {
     using std::runtime_error::runtime_error;
 };
 
+// BLU_TIMELINE=1: device-side event timeline of one resident run (ms from its start), printed to stderr.  A debugging
+// aid for the overlap of result downloads with the next range's kernels; events are only created when it is on.
+struct Timeline {
+    struct Mark {
+        const char* what;
+        int range;
+        cudaEvent_t ev;
+        double host_ms;
+    };
+    bool on = getenv("BLU_TIMELINE") != nullptr;
+    std::vector<Mark> marks;
+    cudaEvent_t t0 = nullptr;
+    std::chrono::steady_clock::time_point h0;
+    void start(cudaStream_t s) {
+        if (!on) return;
+        cudaEventCreate(&t0);
+        cudaEventRecord(t0, s);
+        h0 = std::chrono::steady_clock::now();
+    }
+    void mark(const char* what, int range, cudaStream_t s) {
+        if (!on) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        marks.push_back({what, range, e, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count()});
+    }
+    void host(const char* what, int range) {
+        if (!on) return;
+        marks.push_back({what, range, nullptr, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count()});
+    }
+    void dump() {
+        if (!on) return;
+        cudaDeviceSynchronize();
+        for (auto& m : marks) {
+            float ms = -1;
+            if (m.ev) cudaEventElapsedTime(&ms, t0, m.ev);
+            fprintf(stderr, "[timeline] range %d %-22s device %8.3f ms   host(issue) %8.3f ms\n", m.range, m.what, ms, m.host_ms);
+            if (m.ev) cudaEventDestroy(m.ev);
+        }
+        if (t0) cudaEventDestroy(t0);
+        marks.clear();
+    }
+};
+
 // --- text resident on the device ------------------------------------------------------------------------------
 void run_device(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStream_t s, blu_result* r) {
     require_ready(c);
@@ -593,14 +639,19 @@ void run_device(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStream_t s, bl
         double ms_tile = 0, ms_long = 0, ms_post = 0;
         uint64_t launches = 0;
         Counters h{};
+        Timeline tl;
+        tl.start(s);
         for (uint64_t ri = 0; ri < n_ranges && !retry; ri++) {
             const bool final_range = ri + 1 == n_ranges;
             const uint64_t end = range_end[ri];
             if (end <= begin && !final_range) continue;
             if (ri) reset_counters_async(c, s, false);
+            tl.mark("tile+longrun begin", (int)ri, s);
             launch_chunk(c, dtext, begin, end, final_range, k, s, rec_done, true);
+            tl.mark("tile+longrun end", (int)ri, s);
             launches++;
             read_counters(c, s);
+            tl.host("counters #1 on host", (int)ri);
             h = *c->h_ctr;
             ms_tile += ev_ms(c->ev[0], c->ev[1]);
             ms_long += ev_ms(c->ev[1], c->ev[2]);
@@ -616,8 +667,10 @@ void run_device(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStream_t s, bl
             launch_gather(c, dtext, end, rec_done, (uint32_t)n_rec_of(h), k, s);
             if (final_range) launch_dup(c, (uint32_t)n_rec_of(h), s);
             CK(cudaEventRecord(c->ev[4], s));
+            tl.mark("consensus+gather end", (int)ri, s);
             rec_done = (uint32_t)n_rec_of(h);
             read_counters(c, s);
+            tl.host("counters #2 on host", (int)ri);
             h = *c->h_ctr;
             ms_post += ev_ms(c->ev[3], c->ev[4]);
             if (h.cap_overflow || h.pool_used > k.pool) {
@@ -632,7 +685,9 @@ void run_device(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStream_t s, bl
                     const double f = 1.15 * (double)n / (double)end;
                     dl.reserve((uint64_t)(n_rec_of(h) * f) + 4096, (uint64_t)(n_slots_of(h) * f) + 8192, (uint64_t)(h.pool_used * f) + 65536);
                 }
+                tl.mark("download begin", (int)ri, c->d2h_stream);
                 dl.push(h);  // runs on the download stream under the next range's kernels
+                tl.mark("download end", (int)ri, c->d2h_stream);
                 begin = h.tail_start != ~0ull ? h.tail_start : end;
             }
         }
@@ -653,7 +708,11 @@ void run_device(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStream_t s, bl
         c->tm.text_bytes = n;
         c->tm.taxonomy_bytes = c->tax->device_bytes();
         c->tm.n_tile_launches = launches;
+        tl.mark("last download begin", (int)n_ranges - 1, c->d2h_stream);
         dl.finish(h);
+        tl.mark("last download end", (int)n_ranges - 1, c->d2h_stream);
+        tl.host("run complete", (int)n_ranges - 1);
+        tl.dump();
         return;
     }
     throw std::runtime_error("output capacity did not converge");
