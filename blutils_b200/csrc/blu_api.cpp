@@ -151,7 +151,7 @@ struct blu_ctx {
     DevBuf<uint8_t> d_pool;
     DevBuf<unsigned long long> d_dup;
     Counters* d_ctr = nullptr;
-    Counters* h_ctr = nullptr;  // pinned
+    Counters* h_ctr = nullptr;  // pinned, two entries
     std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
     std::string err;
     blu_timings tm{};
@@ -592,7 +592,7 @@ struct Timeline {
 };
 
 // --- text resident on the device ------------------------------------------------------------------------------
-void run_device(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStream_t s, blu_result* r) {
+void run_device_serial(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStream_t s, blu_result* r) {
     require_ready(c);
     if (n == 0) throw DataErr("empty blast output (the reference's CsvReader fails on an empty file)");
     if (((uintptr_t)dtext & 15) != 0) throw std::invalid_argument("device text must be 16-byte aligned");
@@ -716,6 +716,162 @@ void run_device(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStream_t s, bl
         return;
     }
     throw std::runtime_error("output capacity did not converge");
+}
+
+void run_device_pipelined(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStream_t s, blu_result* r) {
+    require_ready(c);
+    if (n == 0) throw DataErr("empty blast output (the reference's CsvReader fails on an empty file)");
+    if (((uintptr_t)dtext & 15) != 0) throw std::invalid_argument("device text must be 16-byte aligned");
+    c->tm = blu_timings{};
+    Caps k = initial_caps(n);
+    // Large resident tables are processed in a few query-aligned ranges so that the download of one range's records
+    // overlaps the kernels of the next (the unfinished last query of a range simply starts the next range: the
+    // buffer is contiguous, nothing is copied).
+    // Equal ranges measured best (tools/range_split.py, profiles/README.md): the step is K_1 + ... + K_n + D_n + ~0.1 ms of
+    // host round trips per range; a smaller last range makes an earlier download spill past its kernels instead.
+    // BLU_RANGE_FRACS="0.3,0.3,0.25,0.15" overrides the split (measurement knob).
+    std::vector<double> fracs(n >= (512ull << 20) ? 4 : (n >= (128ull << 20) ? 2 : 1), 1.0);
+    if (const char* ev = getenv("BLU_RANGE_FRACS")) {
+        std::vector<double> f;
+        for (const char* q = ev; *q;) {
+            char* e2 = nullptr;
+            double v = strtod(q, &e2);
+            if (e2 == q || !(v > 0)) break;
+            f.push_back(v);
+            q = *e2 == ',' ? e2 + 1 : e2;
+        }
+        if (!f.empty() && f.size() <= 64) fracs = f;
+    }
+    const uint64_t n_ranges = fracs.size();
+    std::vector<uint64_t> range_end(n_ranges);
+    {
+        double tot = 0, acc = 0;
+        for (double f : fracs) tot += f;
+        for (uint64_t i = 0; i < n_ranges; i++) {
+            acc += fracs[i];
+            const uint64_t e = (uint64_t)((double)n * (acc / tot));
+            range_end[i] = std::min<uint64_t>(n, (e + (uint64_t)kTile - 1) / (uint64_t)kTile * (uint64_t)kTile);
+        }
+        range_end[n_ranges - 1] = n;
+    }
+    Downloader dl(c, r);
+    for (int attempt = 0; attempt < 8; attempt++) {
+        ensure_out(c, k);
+        reset_counters_async(c, s, true);
+        bool retry = false;
+        uint32_t rec_done = 0;
+        uint64_t defer_total = 0;
+        double ms_tile = 0, ms_long = 0, ms_post = 0;
+        uint64_t launches = 0;
+        Counters h{}, h2{};
+        Timeline tl;
+        tl.start(s);
+        auto launch_range = [&](uint64_t ri, uint64_t begin) {
+            if (ri) reset_counters_async(c, s, false);
+            tl.mark("tile+longrun begin", (int)ri, s);
+            launch_chunk(c, dtext, begin, range_end[ri], ri + 1 == n_ranges, k, s, rec_done, true);
+            tl.mark("tile+longrun end", (int)ri, s);
+            launches++;
+        };
+        // The kernels of range i+1 are queued BEFORE the host looks at the post-pass of range i: the GPU goes from the
+        // gather of one range straight into the tile kernel of the next, and the download of range i still starts the
+        // moment its post-pass is done (ev[5] + a second pinned copy of the counters, taken between the two).
+        uint64_t ri = 0;
+        launch_range(0, 0);
+        for (;;) {
+            const bool final_range = ri + 1 == n_ranges;
+            const uint64_t end = range_end[ri];
+            read_counters(c, s);
+            tl.host("counters #1 on host", (int)ri);
+            h = c->h_ctr[0];
+            ms_tile += ev_ms(c->ev[0], c->ev[1]);
+            ms_long += ev_ms(c->ev[1], c->ev[2]);
+            defer_total = std::max<uint64_t>(defer_total, h.n_defer);
+            c->tm.n_deferred_runs += h.n_defer;
+            if (h.cap_overflow || n_rec_of(h) > k.rec || n_slots_of(h) > k.slots || h.n_defer > k.defer || h.pool_used > k.pool) {
+                grow_caps(h, k, h.n_defer, (double)n / (double)std::max<uint64_t>(end, 1), n);
+                retry = true;
+                break;
+            }
+            check_device_error(c, h, 0);
+            CK(cudaEventRecord(c->ev[3], s));
+            launch_gather(c, dtext, end, rec_done, (uint32_t)n_rec_of(h), k, s);
+            if (final_range) launch_dup(c, (uint32_t)n_rec_of(h), s);
+            CK(cudaEventRecord(c->ev[4], s));
+            tl.mark("consensus+gather end", (int)ri, s);
+            CK(cudaMemcpyAsync(&c->h_ctr[1], c->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+            CK(cudaEventRecord(c->ev[5], s));
+            rec_done = (uint32_t)n_rec_of(h);
+            uint64_t next = ri;
+            if (!final_range) {
+                const uint64_t begin = h.tail_start != ~0ull ? h.tail_start : end;  // final after tile + long-run
+                next = ri + 1;
+                while (next + 1 < n_ranges && range_end[next] <= begin) next++;  // a query longer than a whole range
+                launch_range(next, begin);
+            }
+            CK(cudaEventSynchronize(c->ev[5]));
+            tl.host("counters #2 on host", (int)ri);
+            h2 = c->h_ctr[1];
+            ms_post += ev_ms(c->ev[3], c->ev[4]);
+            if (h2.cap_overflow || h2.pool_used > k.pool) {
+                grow_caps(h2, k, defer_total, (double)n / (double)std::max<uint64_t>(end, 1), n);
+                retry = true;
+                break;
+            }
+            check_device_error(c, h2, 0);
+            if (final_range) break;
+            if (ri == 0 && end > 0) {
+                // size the pinned result buffers from the density of the first range
+                const double f = 1.15 * (double)n / (double)end;
+                dl.reserve((uint64_t)(n_rec_of(h2) * f) + 4096, (uint64_t)(n_slots_of(h2) * f) + 8192, (uint64_t)(h2.pool_used * f) + 65536);
+            }
+            tl.mark("download begin", (int)ri, c->d2h_stream);
+            dl.push(h2);  // runs on the download stream under the next range's kernels
+            tl.mark("download end", (int)ri, c->d2h_stream);
+            ri = next;
+        }
+        if (retry) {
+            CK(cudaStreamSynchronize(s));  // the next range may already be running
+            dl.abandon();
+            c->tm = blu_timings{};
+            continue;
+        }
+        if (h2.dup_found) {
+            dl.abandon();
+            throw NonContiguous("a query id occurs in two non-adjacent groups of rows");
+        }
+        if (n_rec_of(h2) == 0) throw DataErr("the blast output holds no rows");
+        c->tm.ms_tile_kernel = ms_tile;
+        c->tm.ms_longrun_kernel = ms_long;
+        c->tm.ms_gather_kernel = ms_post;
+        c->tm.ms_total_device = ms_tile + ms_long + ms_post;
+        c->tm.text_bytes = n;
+        c->tm.taxonomy_bytes = c->tax->device_bytes();
+        c->tm.n_tile_launches = launches;
+        tl.mark("last download begin", (int)n_ranges - 1, c->d2h_stream);
+        dl.finish(h2);
+        tl.mark("last download end", (int)n_ranges - 1, c->d2h_stream);
+        tl.host("run complete", (int)n_ranges - 1);
+        tl.dump();
+        return;
+    }
+    throw std::runtime_error("output capacity did not converge");
+}
+
+// BLU_RESIDENT_SERIAL=1 selects the loop with two host round trips per range (A/B measurement).  On any failure nothing
+// may still be reading the caller's device text when the call returns.
+void run_device(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStream_t s, blu_result* r) {
+    static const bool serial = getenv("BLU_RESIDENT_SERIAL") != nullptr;
+    try {
+        if (serial)
+            run_device_serial(c, dtext, n, s, r);
+        else
+            run_device_pipelined(c, dtext, n, s, r);
+    } catch (...) {
+        cudaStreamSynchronize(s);
+        cudaStreamSynchronize(c->d2h_stream);
+        throw;
+    }
 }
 
 // --- where the streamed path takes the text of chunk `ci` from -------------------------------------------------
@@ -1047,7 +1203,7 @@ int blu_ctx_create(const blu_opts* opts, blu_ctx** out) {
         for (auto& e2 : c->ev_h2d) CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
         for (auto& e2 : c->ev_free) CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
         CK(cudaMalloc((void**)&c->d_ctr, sizeof(Counters)));
-        CK(cudaHostAlloc((void**)&c->h_ctr, sizeof(Counters), cudaHostAllocDefault));
+        CK(cudaHostAlloc((void**)&c->h_ctr, 2 * sizeof(Counters), cudaHostAllocDefault));  // [0]: read_counters, [1]: post-pass snapshot
         CK(kernels_set_attributes());
     });
     if (rc != BLU_OK) {
