@@ -44,6 +44,7 @@ SYMBOLS = [
     ("blu_custom_cutoffs_from_file", C.c_int, [C.c_char_p, C.POINTER(blu_opts), C.c_char_p, C.c_size_t]),
     ("blu_taxonomy_load_json", C.c_int, [C.c_void_p, C.c_char_p]),
     ("blu_taxonomy_load_json_cached", C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int)]),
+    ("blu_result_file_to_tabular", C.c_int, [C.c_char_p, C.c_char_p, C.c_int, C.c_char_p, C.c_char_p, C.c_size_t]),
     ("blu_taxonomy_load_arrays", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
     ("blu_consensus_run_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
     ("blu_consensus_run_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_void_p)]),

@@ -354,3 +354,14 @@ def write_blutils_output(results: ConsensusOutput, config=None, blutils_out_file
     if config is not None:
         raise Unsupported("BlastBuilder config echo belongs to run-with-consensus, which is out of scope")
     results.write(blutils_out_file, out_format)
+
+
+def parse_consensus_as_tabular(blutils_result: str = "-", output_file: Optional[str] = None, result_format: OutputFormat = OutputFormat.Json,
+                               run_id: Optional[str] = None) -> None:
+    """parse_consensus_as_tabular/mod.rs:15-19 (`blu blastn build-tabular`): blutils result file (or "-" = stdin) -> TSV.
+    Needs no GPU.  `run_id` replaces the reference's random UUID where the input carries none."""
+    err = C.create_string_buffer(1024)
+    rc = _ffi.lib().blu_result_file_to_tabular(os.fspath(blutils_result).encode(), None if output_file is None else os.fspath(output_file).encode(),
+                                               result_format.value, None if run_id is None else run_id.encode(), err, 1024)
+    if rc != 0:
+        _raise(rc, err.value.decode())

@@ -32,6 +32,7 @@
 #include "blu_decode.h"
 #include "blu_json.h"
 #include "blu_kernels.h"
+#include "blu_tabular.h"
 #include "blu_taxonomy.h"
 
 using namespace blu;
@@ -1488,6 +1489,19 @@ int blu_result_write_tabular(const blu_result* r, const char* path, const char* 
     } catch (const std::exception&) {
         return BLU_ERR_INTERNAL;
     }
+}
+
+int blu_result_file_to_tabular(const char* in_path, const char* out_path, int input_format, const char* run_id, char* err, size_t errlen) {
+    std::string msg;
+    int rc;
+    try {
+        rc = result_file_to_tabular(in_path, out_path, input_format, run_id, msg);
+    } catch (const std::exception& e) {
+        msg = e.what();
+        rc = BLU_ERR_INTERNAL;
+    }
+    if (rc != BLU_OK && err && errlen) snprintf(err, errlen, "%s", msg.c_str());
+    return rc;
 }
 
 void blu_result_free(blu_result* r) {

@@ -1,4 +1,4 @@
-// blu_cli.cpp -- `blu blastn build-consensus` shim over the C ABI.
+// blu_cli.cpp -- `blu blastn build-consensus` and `blu blastn build-tabular` shims over the C ABI.
 // Argument surface = BuildConsensusArguments (reference ports/cli/src/cmds/blast/commands.rs:105-143) plus the
 // global flags of CliLauncher (ports/cli/src/models/cli_launcher.rs:7-22), which this stage accepts and ignores
 // (`--threads` never reaches the consensus stage in the reference either: cmds/blast/mod.rs:104).
@@ -15,7 +15,8 @@ static void usage() {
             "Usage: blu [--log-level L] [--log-file F] [--log-format F] [-t|--threads N] blastn build-consensus <BLAST_OUT>\n"
             "           -t|--tax-file <FILE> --taxon <fungi|bacteria|eukaryotes|custom> --strategy <cautious|relaxed>\n"
             "           [-c|--custom-taxon-cutoff-file <FILE>] [-u|--use-taxid] [--blutils-out-file <FILE>]\n"
-            "           [--out-format <json|jsonl|yaml>] [--device N]\n");
+            "           [--out-format <json|jsonl|yaml>] [--device N]\n"
+            "       blu blastn build-tabular [BLU_RESULT|-] [-o|--output-file <FILE>] [-i|--input-format <json|jsonl>]\n");
 }
 
 [[noreturn]] static void die(const std::string& m) {
@@ -39,8 +40,51 @@ int main(int argc, char** argv) {
             return 2;
         }
     }
+    if (i + 1 < a.size() && a[i] == "blastn" && a[i + 1] == "build-tabular") {
+        // BuildTabularArguments (ports/cli/src/cmds/blast/commands.rs:145-161); no GPU involved
+        std::string in = "-", out, fmt = "json";
+        bool have_out = false, have_in = false;
+        for (i += 2; i < a.size(); i++) {
+            auto value = [&](const char* shortf, const char* longf, std::string& dst) {
+                const std::string eq = std::string(longf) + "=";
+                if (a[i] == shortf || a[i] == longf) {
+                    if (i + 1 >= a.size()) die(std::string("a value is required for '") + longf + "'");
+                    dst = a[++i];
+                    return true;
+                }
+                if (a[i].rfind(eq, 0) == 0) {
+                    dst = a[i].substr(eq.size());
+                    return true;
+                }
+                return false;
+            };
+            if (value("-o", "--output-file", out)) {
+                have_out = true;
+                continue;
+            }
+            if (value("-i", "--input-format", fmt)) continue;
+            if (a[i] != "-" && !a[i].empty() && a[i][0] == '-') {
+                fprintf(stderr, "error: unexpected argument '%s'\n", a[i].c_str());
+                usage();
+                return 2;
+            }
+            if (have_in) {
+                fprintf(stderr, "error: unexpected argument '%s'\n", a[i].c_str());
+                return 2;
+            }
+            in = a[i], have_in = true;
+        }
+        const int format = fmt == "json" ? BLU_FORMAT_JSON : fmt == "jsonl" ? BLU_FORMAT_JSONL : fmt == "yaml" ? BLU_FORMAT_YAML : -1;
+        if (format < 0) {
+            fprintf(stderr, "error: invalid value '%s' for '--input-format <INPUT_FORMAT>' [possible values: json, jsonl, yaml]\n", fmt.c_str());
+            return 2;
+        }
+        char err[1024] = {0};
+        if (blu_result_file_to_tabular(in.c_str(), have_out ? out.c_str() : nullptr, format, nullptr, err, sizeof err) != BLU_OK) die(err);
+        return 0;
+    }
     if (i + 1 >= a.size() || a[i] != "blastn" || a[i + 1] != "build-consensus") {
-        fprintf(stderr, "only `blastn build-consensus` is provided by this build (the consensus-identity hot path)\n");
+        fprintf(stderr, "only `blastn build-consensus` and `blastn build-tabular` are provided by this build (the consensus-identity hot path)\n");
         usage();
         return 2;
     }

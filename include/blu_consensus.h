@@ -168,6 +168,13 @@ int blu_result_write(const blu_result* res, const char* path, int format, const 
  * stdout, else the extension is forced to `.tsv`.  Reproduces the reference byte for byte, including its quirk of
  * not writing line breaks between pieces in file mode. */
 int blu_result_write_tabular(const blu_result* res, const char* path, const char* run_id);
+/* `blu blastn build-tabular` proper (parse_consensus_as_tabular/mod.rs:15-173 + file_or_stdin.rs:96-176): reads a blutils
+ * result file (BLU_FORMAT_JSON or BLU_FORMAT_JSONL; path NULL or "-" = stdin) and writes the same TSV (output_file NULL =
+ * stdout, else extension forced to `.tsv`).  Needs no context and no GPU.  `run_id` is used where neither the result nor
+ * the config carries one (NULL = a fresh UUIDv4, as the reference).  BLU_ERR_IO with the message in `err` mirrors the
+ * reference's Err(MappedErrors); YAML input returns BLU_ERR_UNSUPPORTED. */
+int blu_result_file_to_tabular(const char* blu_result_path, const char* output_file, int input_format, const char* run_id, char* err,
+                               size_t errlen);
 void blu_result_free(blu_result* res);
 void blu_free(void* p);
 

@@ -1,0 +1,155 @@
+"""`blu blastn build-tabular`: blutils result file -> 12-column TSV, through the C ABI
+(`blu_result_file_to_tabular`, no GPU needed) and the CLI shim.  Expected bytes come from the Python oracle's restatement of
+parse_consensus_as_tabular (mod.rs:15-173); the input files are what write_blutils_output produces for the mock 16S run
+(serde_json pretty / compact / JSONL)."""
+import json
+import os
+import subprocess
+
+import pytest
+
+import pyoracle as po
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+DIR = os.path.join(HERE, "golden", "mock16s")
+RUN_ID = "0b0e3c55-7a2f-4a61-9d4e-5f1c2a7b8c9d"
+OTHER_ID = "11111111-2222-4333-8444-555555555555"
+
+
+def _results(use_taxid=False, strategy="relaxed"):
+    text = open(os.path.join(DIR, "blast.out"), "rb").read()
+    headers = open(os.path.join(DIR, "headers.txt")).read().split()
+    tax = po.load_taxonomy(os.path.join(DIR, "mock-16S.blutils.json"), use_taxid)
+    return po.build_consensus_identities(text, tax, "bacteria", strategy, headers=headers)
+
+
+def _doc(results, run_id=RUN_ID, config=None):
+    return {"results": [dict(([("runId", run_id)] if run_id else []) + list(r.items())) for r in results], "config": config}
+
+
+def _tab(in_path, out_path, fmt="json", run_id=None):
+    from blutils_b200 import OutputFormat, parse_consensus_as_tabular
+
+    parse_consensus_as_tabular(in_path, out_path, {"json": OutputFormat.Json, "jsonl": OutputFormat.Jsonl, "yaml": OutputFormat.Yaml}[fmt], run_id)
+
+
+@pytest.mark.parametrize("use_taxid,strategy", [(False, "relaxed"), (True, "cautious")])
+@pytest.mark.parametrize("pretty", [True, False])
+def test_json_to_tsv_file(tmp_path, use_taxid, strategy, pretty):
+    res = _results(use_taxid, strategy)
+    src = tmp_path / "blutils.json"
+    src.write_text(po.to_json_pretty(_doc(res)) if pretty else po.to_json_compact(_doc(res)))
+    _tab(str(src), str(tmp_path / "table.txt"))  # extension forced to .tsv
+    want = po.results_to_tabular(res, RUN_ID, to_stdout=False)
+    assert (tmp_path / "table.tsv").read_text() == want
+    assert any(r["taxon"] is None for r in res) and any(r["taxon"] and r["taxon"]["consensusBeans"] for r in res)
+    # an existing output is replaced, not appended to
+    _tab(str(src), str(tmp_path / "table.tsv"))
+    assert (tmp_path / "table.tsv").read_text() == want
+
+
+def test_run_id_sources(tmp_path):
+    res = _results()
+    # no per-result runId: the config's run id is used ...
+    src = tmp_path / "a.json"
+    src.write_text(po.to_json_compact(_doc(res, run_id=None, config={"runId": OTHER_ID, "isConfig": True, "anything": [1, {"x": None}]})))
+    _tab(str(src), str(tmp_path / "a.tsv"))
+    assert (tmp_path / "a.tsv").read_text() == po.results_to_tabular(res, OTHER_ID, to_stdout=False)
+    # ... without a config the caller's (the reference: a random UUIDv4)
+    src.write_text(po.to_json_compact(_doc(res, run_id=None)))
+    _tab(str(src), str(tmp_path / "b.tsv"), run_id=RUN_ID)
+    assert (tmp_path / "b.tsv").read_text() == po.results_to_tabular(res, RUN_ID, to_stdout=False)
+    _tab(str(src), str(tmp_path / "c.tsv"))
+    import re
+
+    rid = re.search(r"[0-9a-f]{8}-[0-9a-f]{4}-4[0-9a-f]{3}-[89ab][0-9a-f]{3}-[0-9a-f]{12}", (tmp_path / "c.tsv").read_text()).group(0)
+    assert (tmp_path / "c.tsv").read_text() == po.results_to_tabular(res, rid, to_stdout=False)
+    # upper-case / simple-form UUIDs are printed in Uuid's Display form
+    src.write_text(po.to_json_compact(_doc(res, run_id=RUN_ID.upper().replace("-", ""))))
+    _tab(str(src), str(tmp_path / "d.tsv"))
+    assert (tmp_path / "d.tsv").read_text() == po.results_to_tabular(res, RUN_ID, to_stdout=False)
+
+
+def test_jsonl_input(tmp_path):
+    from blutils_b200 import MappedErrors
+
+    res = _results()
+    body = po.results_to_jsonl(res, RUN_ID)
+    src = tmp_path / "r.jsonl"
+    (tmp_path / "r.json").write_text("{}")  # the reference's existence check looks at <name>.json whatever the format
+    # run-with-consensus style: a config line (recognised by `isConfig`), blank lines skipped
+    src.write_text(json.dumps({"runId": OTHER_ID, "isConfig": True}) + "\n\n" + body)
+    _tab(str(src), str(tmp_path / "r.tsv"), "jsonl")
+    assert (tmp_path / "r.tsv").read_text() == po.results_to_tabular(res, RUN_ID, to_stdout=False)
+    # build-consensus writes `null` as the config line: not a QueryWithConsensus -> the reference fails, so does this
+    src.write_text("null\n" + body)
+    with pytest.raises(MappedErrors, match="unable to parse line as JSON"):
+        _tab(str(src), str(tmp_path / "r2.tsv"), "jsonl")
+
+
+def test_errors(tmp_path):
+    from blutils_b200 import MappedErrors, Unsupported
+
+    with pytest.raises(MappedErrors, match="does not exist"):
+        _tab(str(tmp_path / "absent.json"), None)
+    res = _results()
+    only_jsonl = tmp_path / "x.jsonl"
+    only_jsonl.write_text(po.results_to_jsonl(res, RUN_ID))
+    with pytest.raises(MappedErrors, match="does not exist"):  # x.json is what the reference probes
+        _tab(str(only_jsonl), None, "jsonl")
+    bad = tmp_path / "bad.json"
+    for text, what in [("{\"config\": null}", "missing field `results`"), ("{\"results\": [{\"taxon\": null}], \"config\": null}", "missing field `query`"),
+                       ("{\"results\": [{\"query\": \"q\", \"query\": \"q\"}]}", "duplicate field `query`"),
+                       ("{\"results\": [{\"query\": \"q\", \"taxon\": {\"reachedRank\": \"species\"}}]}", "missing field `identifier`"),
+                       ("{\"results\": [{\"query\": \"q\", \"runId\": \"not-a-uuid\"}]}", "invalid UUID"), ("{\"results\": [] } x", "trailing characters"),
+                       ("[]", "unexpected character")]:
+        bad.write_text(text)
+        with pytest.raises(MappedErrors, match=what):
+            _tab(str(bad), str(tmp_path / "o.tsv"))
+    bad.write_text("{\"results\": []}")
+    with pytest.raises(Unsupported):
+        _tab(str(bad), None, "yaml")
+    _tab(str(bad), str(tmp_path / "empty.tsv"))  # config may be missing (Option); no results -> header only
+    assert (tmp_path / "empty.tsv").read_text() == po.results_to_tabular([], RUN_ID, to_stdout=False)
+
+
+def test_extra_fields_floats_and_ranks(tmp_path):
+    """Unknown fields are skipped, Option fields may be absent, f64 fields take integers / exponents, rank strings pass through."""
+    doc = {"results": [{"query": "q1", "extra": {"a": [1, 2]}, "taxon": {
+        "reachedRank": "species-group", "identifier": "x y", "percIdentity": 1e2, "bitScore": 845, "mutated": False, "singleMatch": True,
+        "consensusBeans": [{"rank": "Species", "identifier": "b", "occurrences": 3, "accessions": []},
+                           {"rank": "genus", "identifier": "c", "occurrences": 1, "taxonomy": "d__x;g__c", "accessions": ["A.1", "B.2"]}]}},
+        {"runId": None, "query": "q2", "taxon": {"reachedRank": "genus", "maxAllowedRank": None, "identifier": "g", "percIdentity": 97.125,
+                                                  "bitScore": 0.5, "taxonomy": "d__x;g__g", "mutated": True, "singleMatch": False,
+                                                  "consensusBeans": None}}]}
+    src = tmp_path / "m.json"
+    src.write_text(json.dumps(doc))
+    _tab(str(src), str(tmp_path / "m.tsv"), run_id=RUN_ID)
+    for r in doc["results"]:
+        for b in r["taxon"].get("consensusBeans") or []:
+            b.setdefault("taxonomy", None)
+    want = po.results_to_tabular([{"query": r["query"], "taxon": dict({"taxonomy": None, "consensusBeans": None}, **r["taxon"])} for r in doc["results"]],
+                                 RUN_ID, to_stdout=False)
+    got = (tmp_path / "m.tsv").read_text()
+    assert got == want
+    assert "\t100\t845\t" in got and "\tspecies-group\tx y\t" in got and "\tSpecies\tb\tnull\t845\tnull\t" in got and "\t97.125\t0.5\t" in got
+
+
+def test_cli_stdout_and_stdin(tmp_path):
+    """The CLI shim: result on stdin ("-" is the default), TSV on stdout with one println! per piece."""
+    cli = os.path.join(ROOT, "blutils_b200", "blu")
+    if not os.path.exists(cli):
+        pytest.skip("CLI shim not built")
+    res = _results()
+    text = po.to_json_pretty(_doc(res))
+    p = subprocess.run([cli, "blastn", "build-tabular"], input=text.encode(), stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
+    assert p.returncode == 0, p.stderr
+    assert p.stdout.decode() == po.results_to_tabular(res, RUN_ID, to_stdout=True)
+    src = tmp_path / "in.json"
+    src.write_text(text)
+    p = subprocess.run([cli, "blastn", "build-tabular", str(src), "-o", str(tmp_path / "out.tsv"), "--input-format=json"], stdout=subprocess.PIPE,
+                       stderr=subprocess.PIPE, timeout=60)
+    assert p.returncode == 0 and p.stdout == b"" and (tmp_path / "out.tsv").read_text() == po.results_to_tabular(res, RUN_ID, to_stdout=False)
+    p = subprocess.run([cli, "blastn", "build-tabular", str(tmp_path / "nope.json")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
+    assert p.returncode == 101 and b"does not exist" in p.stderr
