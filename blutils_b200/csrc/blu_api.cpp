@@ -928,10 +928,15 @@ class FileSource : public ChunkSource {
         std::vector<std::string> errs((size_t)n_readers_);
         std::atomic<bool> ok{true};
         int t = 0;
-        for (uint64_t o = slice; o < len; o += slice, t++)
-            th.emplace_back([&, o, t] {
-                if (!read_span(dst + o, off + o, std::min(slice, len - o), errs[(size_t)t])) ok = false;
-            });
+        try {
+            for (uint64_t o = slice; o < len; o += slice, t++)
+                th.emplace_back([&, o, t] {
+                    if (!read_span(dst + o, off + o, std::min(slice, len - o), errs[(size_t)t])) ok = false;
+                });
+        } catch (...) {  // could not start a thread: the ones already running must be joined before unwinding
+            for (auto& x : th) x.join();
+            throw;
+        }
         std::string e0;
         if (!read_span(dst, off, std::min(slice, len), e0)) ok = false;
         for (auto& x : th) x.join();
@@ -955,7 +960,12 @@ class FileSource : public ChunkSource {
                 }
             }
             std::string err;
-            const bool ok = read_chunk(next, err);
+            bool ok = false;
+            try {
+                ok = read_chunk(next, err);
+            } catch (const std::exception& e) {  // e.g. no more threads: reported through acquire(), not std::terminate
+                err = std::string("reading the blast output failed: ") + e.what();
+            }
             {
                 std::lock_guard<std::mutex> g(mu_);
                 if (epoch_ == my_epoch) {
