@@ -153,3 +153,52 @@ def test_cli_stdout_and_stdin(tmp_path):
     assert p.returncode == 0 and p.stdout == b"" and (tmp_path / "out.tsv").read_text() == po.results_to_tabular(res, RUN_ID, to_stdout=False)
     p = subprocess.run([cli, "blastn", "build-tabular", str(tmp_path / "nope.json")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=60)
     assert p.returncode == 101 and b"does not exist" in p.stderr
+
+
+def test_random_documents(tmp_path):
+    """Seeded random result documents (escapes, non-ASCII, surrogate pairs, float shapes, optional fields in any order) written by
+    Python's json module in both ASCII-escaped and raw UTF-8 form: same TSV as the oracle computes from the same objects."""
+    import random
+
+    rng = random.Random(20261018)
+    alphabet = ["a", "Z", "0", " ", "_", "-", ".", ";", "\"", "\\", "/", "\t", "\n", "é", "ß", "漢", "𝔘", " ", "|", "'"]
+
+    def word(lo=1, hi=12):
+        return "".join(rng.choice(alphabet) for _ in range(rng.randint(lo, hi)))
+
+    def number():
+        k = rng.random()
+        if k < 0.3:
+            return float(rng.randint(0, 2000))
+        if k < 0.6:
+            return round(rng.uniform(0, 100), rng.randint(0, 6))
+        if k < 0.8:
+            return rng.uniform(0, 1e-5)
+        return rng.uniform(1e15, 1e22)
+
+    def shuffled(d):
+        items = list(d.items())
+        rng.shuffle(items)
+        return dict(items)
+
+    results = []
+    for i in range(300):
+        if rng.random() < 0.15:
+            results.append({"query": word(), "taxon": None})
+            continue
+        beans = None
+        if rng.random() < 0.7:
+            beans = [{"rank": rng.choice(["species", "genus", "clade", "species-group", word()]), "identifier": word(), "occurrences": rng.randint(1, 500),
+                      "taxonomy": rng.choice([None, "d__x;p__" + word()]), "accessions": [word() for _ in range(rng.randint(0, 4))]}
+                     for _ in range(rng.randint(0, 5))]
+        results.append({"query": word(), "taxon": {
+            "reachedRank": rng.choice(["domain", "family", "strain", word()]), "maxAllowedRank": rng.choice([None, "genus"]), "identifier": word(),
+            "percIdentity": number(), "bitScore": number(), "taxonomy": rng.choice([None, "d__bac;" + word()]), "mutated": rng.random() < 0.5,
+            "singleMatch": rng.random() < 0.5, "consensusBeans": beans}})
+    doc = {"config": None, "results": [shuffled(dict(r, runId=RUN_ID, taxon=shuffled(r["taxon"]) if r["taxon"] else None)) for r in results]}
+    want = po.results_to_tabular(results, RUN_ID, to_stdout=False)
+    for ascii_only in (True, False):
+        src = tmp_path / f"rand{int(ascii_only)}.json"
+        src.write_text(json.dumps(doc, ensure_ascii=ascii_only, indent=rng.choice([None, 1, 4])), encoding="utf-8")
+        _tab(str(src), str(tmp_path / f"rand{int(ascii_only)}.tsv"))
+        assert (tmp_path / f"rand{int(ascii_only)}.tsv").read_text(encoding="utf-8") == want
