@@ -1,9 +1,10 @@
 #!/usr/bin/env python
 """Throughput + parity of the larger BASELINE configs (C3, C4) on one GPU, at a size that fits a short GPU session.
-Not part of pytest / bench.py; results are quoted in DESIGN.md.
+Not collected by pytest and not part of bench.py; it lives under tests/ because it uses the CPU oracle as its checker.
+Results are quoted in DESIGN.md.
 
-  python tools/run_configs.py C3 --queries 2000000      # 100 hits/query, 2 M-taxon lineage map, bacteria cutoffs
-  python tools/run_configs.py C4 --queries 400000       # Zipf(1.1) hits on [1, 5000]
+  python tests/run_configs.py C3 --queries 2000000      # 100 hits/query, 2 M-taxon lineage map, bacteria cutoffs
+  python tests/run_configs.py C4 --queries 400000       # Zipf(1.1) hits on [1, 5000]
 
 Parity at size: (1) the first `--check` queries are re-run alone and compared with the CPU oracle (checksum of the
 canonical JSONL); (2) shard-sum invariance on the full table: the checksums of 8 query-aligned shards add up to the
