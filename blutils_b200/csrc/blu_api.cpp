@@ -986,8 +986,13 @@ class FileSource : public ChunkSource {
         n_readers_ = (int)std::min<unsigned>(8, std::max<unsigned>(1, hc ? hc : 4));
         if (const char* ev = getenv("BLU_READ_THREADS")) n_readers_ = std::max(1, std::min(64, atoi(ev)));
         const uint64_t used = std::min<uint64_t>(kRing, n_chunks_);
-        for (uint64_t i = 0; i < used; i++) buf_[i] = c->acquire(std::min(chunk, n));
-        coordinator_ = std::thread([this] { run(); });
+        try {
+            for (uint64_t i = 0; i < used; i++) buf_[i] = c->acquire(std::min(chunk, n));
+            coordinator_ = std::thread([this] { run(); });
+        } catch (...) {  // a constructor that throws gets no destructor call
+            for (auto& b : buf_) c_->pool->release(b);
+            throw;
+        }
     }
     ~FileSource() override {
         {
