@@ -17,15 +17,22 @@ BLU_CUTOFF_ABSENT = -(2 ** 31)
 
 class blu_opts(C.Structure):
     _fields_ = [("device", C.c_int32), ("taxon", C.c_int32), ("strategy", C.c_int32), ("use_taxid", C.c_int32),
-                ("has_custom", C.c_int32), ("custom", C.c_int32 * 8), ("chunk_bytes", C.c_uint64), ("reserved", C.c_uint64 * 4)]
+                ("has_custom", C.c_int32), ("custom", C.c_int32 * 8), ("chunk_bytes", C.c_uint64), ("flags", C.c_uint64), ("reserved", C.c_uint64 * 3)]
 
 
 class blu_record(C.Structure):
     _fields_ = [("query_off", C.c_uint64), ("query_len", C.c_uint32), ("n_rows", C.c_uint32), ("keep_mask", C.c_uint64),
-                ("perc_identity", C.c_double), ("bit_score", C.c_int64), ("ref_lineage", C.c_uint32), ("slot_base", C.c_uint32),
-                ("n_beans", C.c_uint32), ("n_accessions", C.c_uint32), ("status", C.c_uint8), ("single_match", C.c_uint8),
+                ("perc_identity", C.c_double), ("bit_score", C.c_int64), ("ref_lineage", C.c_uint32), ("bean_base", C.c_uint32),
+                ("n_beans", C.c_uint32), ("acc_base", C.c_uint32), ("status", C.c_uint8), ("single_match", C.c_uint8),
                 ("mutated", C.c_uint8), ("reached_pos", C.c_int8), ("allowed_pos", C.c_int8), ("bean_level", C.c_int8),
                 ("pad", C.c_uint8 * 2)]
+
+
+class blu_bean(C.Structure):
+    _fields_ = [("first_lineage", C.c_uint32), ("occurrences", C.c_uint32), ("acc_begin", C.c_uint32), ("n_acc", C.c_uint32)]
+
+
+BLU_OPT_TEXT_REFS = 1
 
 
 class blu_timings(C.Structure):
@@ -39,6 +46,8 @@ class blu_timings(C.Structure):
 SYMBOLS = [
     ("blu_abi_version", C.c_int, []),
     ("blu_ctx_create", C.c_int, [C.POINTER(blu_opts), C.POINTER(C.c_void_p)]),
+    ("blu_ctx_create_multi", C.c_int, [C.POINTER(blu_opts), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    ("blu_ctx_num_devices", C.c_int, [C.c_void_p]),
     ("blu_ctx_destroy", None, [C.c_void_p]),
     ("blu_last_error", C.c_char_p, [C.c_void_p]),
     ("blu_custom_cutoffs_from_file", C.c_int, [C.c_char_p, C.POINTER(blu_opts), C.c_char_p, C.c_size_t]),
@@ -48,6 +57,11 @@ SYMBOLS = [
     ("blu_taxonomy_load_arrays", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]),
     ("blu_consensus_run_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
     ("blu_consensus_run_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_void_p)]),
+    ("blu_consensus_run_device_resident", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_void_p)]),
+    ("blu_result_device_records", C.c_void_p, [C.c_void_p]),
+    ("blu_result_device_beans", C.c_void_p, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    ("blu_result_device_accessions", C.c_void_p, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    ("blu_result_download", C.c_int, [C.c_void_p]),
     ("blu_consensus_run_file", C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_void_p)]),
     ("blu_result_add_headers", C.c_int, [C.c_void_p, C.c_char_p, C.c_uint64]),
     ("blu_result_num_queries", C.c_uint64, [C.c_void_p]),
@@ -56,6 +70,8 @@ SYMBOLS = [
     ("blu_result_beans", C.c_void_p, [C.c_void_p]),
     ("blu_result_accessions", C.c_void_p, [C.c_void_p]),
     ("blu_result_pool", C.c_void_p, [C.c_void_p, C.POINTER(C.c_uint64)]),
+    ("blu_result_num_beans", C.c_uint64, [C.c_void_p]),
+    ("blu_result_num_accessions", C.c_uint64, [C.c_void_p]),
     ("blu_result_checksum", C.c_uint64, [C.c_void_p]),
     ("blu_result_to_jsonl", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     ("blu_result_write", C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_char_p]),
@@ -64,6 +80,7 @@ SYMBOLS = [
     ("blu_free", None, [C.c_void_p]),
     ("blu_ctx_last_timings", C.c_int, [C.c_void_p, C.POINTER(blu_timings)]),
     ("blu_ctx_measure_h2d", C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_double)]),
+    ("blu_ctx_measure_d2h", C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_double)]),
     ("blu_shard_cuts", C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]),
     ("blu_host_alloc", C.c_void_p, [C.c_uint64]),
     ("blu_host_free", None, [C.c_void_p]),
@@ -83,7 +100,7 @@ def lib():
             fn = getattr(l, name)  # AttributeError if the .so does not export it
             fn.restype = res
             fn.argtypes = args
-        if l.blu_abi_version() != 1:
+        if l.blu_abi_version() != 2:
             raise ImportError("libblu_consensus.so ABI version mismatch")
         _lib = l
     return _lib

@@ -161,6 +161,7 @@ class ConsensusOutput:
     def __init__(self, engine: "ConsensusEngine", handle: int):
         self._engine = engine
         self._h = C.c_void_p(handle)
+        self._keep = None
 
     def __len__(self) -> int:
         return _ffi.lib().blu_result_num_queries(self._h)
@@ -216,10 +217,30 @@ class ConsensusOutput:
         if rc != 0:
             raise MappedErrors("could not write the tabular output")
 
+    def download(self) -> "ConsensusOutput":
+        """Device-resident result (run_device_resident) -> host; afterwards every accessor / writer works."""
+        if _ffi.lib().blu_result_download(self._h) != 0:
+            raise RuntimeError("blu_result_download failed")
+        return self
+
+    def device_arrays(self):
+        """(records_ptr, beans_ptr, n_beans, accessions_ptr, n_accessions) of a device-resident result."""
+        nb, na = C.c_uint64(), C.c_uint64()
+        l = _ffi.lib()
+        return (l.blu_result_device_records(self._h), l.blu_result_device_beans(self._h, C.byref(nb)), nb.value,
+                l.blu_result_device_accessions(self._h, C.byref(na)), na.value)
+
+    def records(self):
+        """The binary records as a ctypes array (host results)."""
+        n = _ffi.lib().blu_result_num_queries(self._h)
+        p = _ffi.lib().blu_result_records(self._h)
+        return C.cast(p, C.POINTER(_ffi.blu_record * n)).contents if p else None
+
     def close(self) -> None:
         if self._h:
             _ffi.lib().blu_result_free(self._h)
             self._h = None
+        self._keep = None
 
     def __del__(self):
         try:
@@ -229,12 +250,16 @@ class ConsensusOutput:
 
 
 class ConsensusEngine:
-    """One blu_ctx: (taxon, strategy, use_taxid, custom cutoffs) + a taxonomy resident on one GPU."""
+    """One blu_ctx: (taxon, strategy, use_taxid, custom cutoffs) + a taxonomy resident on one GPU, or -- with
+    `devices=[...]` -- on several GPUs of one box: the hit table is then sharded by query range over them
+    (blu_ctx_create_multi; no collective) and the shards' results come back as one result."""
 
     def __init__(self, taxon: Taxon, strategy: ConsensusStrategy, use_taxid: Optional[bool] = None,
-                 custom_taxon_values: Optional[CustomTaxon] = None, device: int = 0, chunk_bytes: int = 0):
+                 custom_taxon_values: Optional[CustomTaxon] = None, device: int = 0, chunk_bytes: int = 0,
+                 devices: Optional[Sequence[int]] = None, text_refs: bool = False):
         o = blu_opts()
         o.device = device
+        o.flags = _ffi.BLU_OPT_TEXT_REFS if text_refs else 0
         o.taxon = taxon.value
         o.strategy = strategy.value
         o.use_taxid = 1 if use_taxid else 0
@@ -244,11 +269,17 @@ class ConsensusEngine:
             o.custom[i] = arr[i]
         o.chunk_bytes = chunk_bytes
         h = C.c_void_p()
-        rc = _ffi.lib().blu_ctx_create(C.byref(o), C.byref(h))
+        if devices is not None:
+            arr_d = (C.c_int * len(devices))(*[int(d) for d in devices])
+            rc = _ffi.lib().blu_ctx_create_multi(C.byref(o), arr_d, len(devices), C.byref(h))
+        else:
+            rc = _ffi.lib().blu_ctx_create(C.byref(o), C.byref(h))
         if rc != 0:
             _raise(rc, (_ffi.lib().blu_last_error(None) or b"").decode())
         self._h = h
         self.device = device
+        self.devices = list(devices) if devices is not None else [device]
+        self.text_refs = text_refs
 
     def _check(self, rc: int):
         if rc != 0:
@@ -288,16 +319,26 @@ class ConsensusEngine:
 
     def run_host(self, text: Union[bytes, int], nbytes: Optional[int] = None) -> ConsensusOutput:
         r = C.c_void_p()
+        keep = None
         if isinstance(text, (bytes, bytearray)):
             buf = C.create_string_buffer(bytes(text), len(text)) if len(text) else C.create_string_buffer(1)
+            keep = buf  # with text_refs the result's strings point into this buffer
             self._check(_ffi.lib().blu_consensus_run_host(self._h, C.addressof(buf), len(text), C.byref(r)))
         else:
             self._check(_ffi.lib().blu_consensus_run_host(self._h, int(text), int(nbytes), C.byref(r)))
-        return ConsensusOutput(self, r.value)
+        out = ConsensusOutput(self, r.value)
+        out._keep = keep
+        return out
 
     def run_device(self, dptr: int, nbytes: int, stream: int = 0) -> ConsensusOutput:
         r = C.c_void_p()
         self._check(_ffi.lib().blu_consensus_run_device(self._h, int(dptr), int(nbytes), int(stream) or None, C.byref(r)))
+        return ConsensusOutput(self, r.value)
+
+    def run_device_resident(self, dptr: int, nbytes: int, stream: int = 0) -> ConsensusOutput:
+        """Text in HBM -> records in HBM; `.download()` brings the result to the host."""
+        r = C.c_void_p()
+        self._check(_ffi.lib().blu_consensus_run_device_resident(self._h, int(dptr), int(nbytes), int(stream) or None, C.byref(r)))
         return ConsensusOutput(self, r.value)
 
     def timings(self) -> Dict[str, float]:
@@ -308,6 +349,11 @@ class ConsensusEngine:
     def measure_h2d(self, nbytes: int = 1 << 30) -> float:
         g = C.c_double()
         self._check(_ffi.lib().blu_ctx_measure_h2d(self._h, nbytes, C.byref(g)))
+        return g.value
+
+    def measure_d2h(self, nbytes: int = 1 << 30) -> float:
+        g = C.c_double()
+        self._check(_ffi.lib().blu_ctx_measure_d2h(self._h, nbytes, C.byref(g)))
         return g.value
 
     def close(self) -> None:
@@ -337,10 +383,10 @@ def shard_cuts(text: Union[bytes, int], n_shards: int, nbytes: Optional[int] = N
 
 def build_consensus_identities(blast_output: ParallelBlastOutput, taxonomies_file: str, taxon: Taxon, strategy: ConsensusStrategy,
                                use_taxid: Optional[bool] = None, custom_taxon_values: Optional[CustomTaxon] = None, *,
-                               device: int = 0) -> ConsensusOutput:
+                               device: int = 0, devices: Optional[Sequence[int]] = None) -> ConsensusOutput:
     """Drop-in for mod.rs:40-47.  Returns the results container (len() == number of ConsensusResult values);
     `.results()` gives the reference's result types, `.write()` is write_blutils_output."""
-    eng = ConsensusEngine(taxon, strategy, use_taxid, custom_taxon_values, device=device)
+    eng = ConsensusEngine(taxon, strategy, use_taxid, custom_taxon_values, device=device, devices=devices)
     eng.load_taxonomy(taxonomies_file)
     out = eng.run_file(blast_output.output_file)
     if blast_output.headers is not None:

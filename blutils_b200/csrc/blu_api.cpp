@@ -126,13 +126,70 @@ struct PinnedPool {
 
 }  // namespace
 
+namespace {
+
+// Result arrays on the device (records / beans / accession references).  A device-resident result takes the set it
+// was computed into with it and hands it back when it is freed, so back-to-back runs never wait for cudaMalloc.
+struct DeviceSet {
+    DevBuf<blu_record> rec;
+    DevBuf<blu_bean> beans;
+    DevBuf<blu_acc> accs;
+    void release() { rec.release(), beans.release(), accs.release(); }
+};
+
+struct DevicePool {
+    std::mutex mu;
+    std::vector<std::unique_ptr<DeviceSet>> free_list;
+    int device = 0;
+    bool closed = false;
+    std::unique_ptr<DeviceSet> acquire() {
+        std::lock_guard<std::mutex> g(mu);
+        if (free_list.empty()) return std::make_unique<DeviceSet>();
+        // the largest set: fewest reallocations
+        size_t best = 0;
+        for (size_t i = 1; i < free_list.size(); i++)
+            if (free_list[i]->rec.cap > free_list[best]->rec.cap) best = i;
+        auto s = std::move(free_list[best]);
+        free_list.erase(free_list.begin() + best);
+        return s;
+    }
+    void release(std::unique_ptr<DeviceSet> s) {
+        if (!s) return;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            if (!closed && free_list.size() < 4) {
+                free_list.push_back(std::move(s));
+                return;
+            }
+        }
+        int cur = 0;
+        cudaGetDevice(&cur);
+        cudaSetDevice(device);
+        s->release();
+        cudaSetDevice(cur);
+    }
+    void close() {
+        std::vector<std::unique_ptr<DeviceSet>> v;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            closed = true;
+            v.swap(free_list);
+        }
+        for (auto& s : v) s->release();
+    }
+};
+
+constexpr int kMaxRanges = 8;  // ranges of a resident table / event sets kept per context
+
+}  // namespace
+
 struct blu_ctx {
     blu_opts opts{};
     Cutoffs cut;
     int device = 0;
     int sms = 148;
     cudaStream_t stream = nullptr, copy_stream = nullptr, d2h_stream = nullptr;
-    cudaEvent_t ev[6]{};
+    cudaEvent_t ev[kMaxRanges][4]{};  // per range / chunk: before tile, after tile, after long-run, after the post-pass
     cudaEvent_t ev_h2d[2]{}, ev_free[2]{};
     std::shared_ptr<HostTaxonomy> tax;
     // device taxonomy
@@ -144,34 +201,79 @@ struct blu_ctx {
     LinTables dT{};
     // run buffers
     DevBuf<uint8_t> d_text[2];
-    DevBuf<blu_record> d_rec;
-    DevBuf<blu_bean> d_beans;
-    DevBuf<blu_acc> d_accs;
+    std::unique_ptr<DeviceSet> out;  // records / beans / accession references of the run in progress
     DevBuf<TopRowRaw> d_top;
     DevBuf<uint64_t> d_defer;
     DevBuf<uint8_t> d_pool;
-    DevBuf<unsigned long long> d_dup;
+    DevBuf<unsigned long long> d_dup, d_qhash;
+    DevBuf<TopRow> d_big_rows;
+    DevBuf<unsigned long long> d_big_cand;
     Counters* d_ctr = nullptr;
-    Counters* h_ctr = nullptr;  // pinned, two entries
+    Counters* h_snap = nullptr;  // pinned + mapped: kMaxRanges snapshots written by advance_kernel
+    Counters* d_snap = nullptr;  // device alias of h_snap
     std::shared_ptr<PinnedPool> pool = std::make_shared<PinnedPool>();
+    std::shared_ptr<DevicePool> dev_pool = std::make_shared<DevicePool>();
     std::string err;
     blu_timings tm{};
     uint64_t carry_bytes = 64ull << 20;
+    // output densities (per text byte) learnt from earlier runs / the probe: capacities are sized from them
+    double dens_rec = 0, dens_slot = 0, dens_bean = 0, dens_acc = 0, dens_pool = 0;
+    // a multi-device context owns one single-device context per GPU and nothing else
+    std::vector<std::unique_ptr<blu_ctx>> shards;
+    bool keep_hashes = false;  // a shard of a multi-device context keeps every record's id hash for the cross-shard duplicate check
+    bool is_multi() const { return !shards.empty(); }
 
     PinnedBuf acquire(size_t bytes) { return pool->acquire(bytes); }
 };
 
-struct blu_result {
+// One part of a result: what one GPU produced.
+struct ResultPartOwned {
     std::shared_ptr<PinnedPool> pinned;
+    PinnedBuf b_rec, b_beans, b_accs, b_pool;
+    const char* ext_strings = nullptr;  // BLU_OPT_TEXT_REFS: the caller's text the string references point into
+    uint64_t ext_len = 0;
+    uint64_t n_rec = 0, n_beans = 0, n_accs = 0, pool_len = 0;
+    // device-resident results
+    std::shared_ptr<DevicePool> dev_pool;
+    std::unique_ptr<DeviceSet> dev;
+    blu_ctx* ctx = nullptr;            // (download needs the context's streams and kernels)
+    const uint8_t* dtext = nullptr;    // the device text the references point into
+    uint64_t dtext_len = 0;
+    bool on_host = true;
+    const char* strings() const { return ext_strings ? ext_strings : (const char*)b_pool.p; }
+    uint64_t strings_len() const { return ext_strings ? ext_len : pool_len; }
+    void free_buffers() {
+        if (pinned) {
+            pinned->release(b_rec), pinned->release(b_beans), pinned->release(b_accs), pinned->release(b_pool);
+            b_rec = b_beans = b_accs = b_pool = PinnedBuf{};
+        }
+        if (dev_pool && dev) dev_pool->release(std::move(dev));
+    }
+};
+
+struct blu_result {
     std::shared_ptr<HostTaxonomy> tax;
     Cutoffs cut;
-    PinnedBuf b_rec, b_beans, b_accs, b_pool;
-    uint64_t n_rec = 0, n_slots = 0, pool_len = 0, n_rows = 0;
+    std::vector<ResultPartOwned> parts;
+    uint64_t n_rows = 0;
     std::vector<std::string> hitless;  // NoConsensusFound (mod.rs:84-102)
-    const blu_record* rec() const { return (const blu_record*)b_rec.p; }
-    const blu_bean* beans() const { return (const blu_bean*)b_beans.p; }
-    const blu_acc* accs() const { return (const blu_acc*)b_accs.p; }
-    const char* pool() const { return (const char*)b_pool.p; }
+    // concatenation of a multi-part result for the array accessors (built on first use)
+    mutable std::mutex merge_mu;
+    mutable bool merged = false;
+    mutable std::vector<blu_record> m_rec;
+    mutable std::vector<blu_bean> m_beans;
+    mutable std::vector<blu_acc> m_accs;
+    mutable std::string m_pool;
+    uint64_t n_rec() const {
+        uint64_t n = 0;
+        for (auto& p : parts) n += p.n_rec;
+        return n;
+    }
+    bool on_host() const {
+        for (auto& p : parts)
+            if (!p.on_host) return false;
+        return true;
+    }
 };
 
 namespace {
@@ -180,11 +282,15 @@ ResultView make_view(const blu_result* r) {
     ResultView v;
     v.tax = r->tax.get();
     v.cut = r->cut;
-    v.rec_ = r->rec();
-    v.beans_ = r->beans();
-    v.accs_ = r->accs();
-    v.pool_ = r->pool();
-    v.n_rec = r->n_rec;
+    for (auto& p : r->parts) {
+        ResultPart q;
+        q.rec = (const blu_record*)p.b_rec.p;
+        q.beans = (const blu_bean*)p.b_beans.p;
+        q.accs = (const blu_acc*)p.b_accs.p;
+        q.pool = p.strings();
+        q.n_rec = p.on_host ? p.n_rec : 0;
+        v.parts.push_back(q);
+    }
     v.hitless_ = &r->hitless;
     return v;
 }
@@ -232,7 +338,7 @@ const char* dev_err_text(uint32_t e) {
         case DE_ROOT_DISAGREE: return "top hits disagree at the first lineage level (reference: index underflow panic)";
         case DE_BITS_RANGE: return "bit score outside the i64 range";
         case DE_NUM_UNSUPPORTED: return "number outside the exactly-parsed range (more than 19 significant digits or |exponent| > 22)";
-        case DE_TOPGROUP_TOO_BIG: return "top bit-score group larger than 1024 rows";
+        case DE_TOPGROUP_TOO_BIG: return "top bit-score group larger than 8192 rows";
         case DE_CARRY_TOO_BIG: return "a single row does not fit the 60 KB window";
         default: return "internal device error";
     }
@@ -265,39 +371,78 @@ void upload_taxonomy(blu_ctx* c) {
     c->dT.hash_mask = T.hash_mask;
     c->dT.n_lin = (uint32_t)T.n_lin();
 }
-
 struct Caps {
-    size_t rec, slots, defer, pool;
+    size_t rec, slots, beans, accs, defer, pool;
 };
 
-inline uint64_t n_rec_of(const Counters& h) { return h.rec_slots >> 32; }
-inline uint64_t n_slots_of(const Counters& h) { return h.rec_slots & 0xFFFFFFFFull; }
+constexpr size_t kIdxMax = 0xFFFFFFF0ull;  // the record fields that index these arrays are 32-bit
 
-Caps initial_caps(uint64_t n_bytes) {
-    Caps c;
-    c.rec = n_bytes / 160 + 4096;
-    c.slots = n_bytes / 96 + 8192;
-    c.defer = c.rec;
-    c.pool = n_bytes / 24 + 65536;
-    return c;
+// Output capacities for n bytes of text: from the densities learnt on earlier runs / the probe, else from the
+// shortest rows the grammar allows for typical BLAST output.  An overflow is counted (never written) by the kernels;
+// the host then grows the arrays and runs again.
+Caps initial_caps(const blu_ctx* c, uint64_t n, bool want_pool) {
+    auto est = [&](double dens, double dflt_div, size_t slack) {
+        const double v = dens > 0 ? (double)n * dens * 1.3 : (double)n / dflt_div;
+        return (size_t)std::min<double>(v + (double)slack, (double)kIdxMax);
+    };
+    Caps k;
+    k.rec = est(c->dens_rec, 160, 4096);
+    k.slots = est(c->dens_slot, 96, 8192 + (size_t)kTileCtasPerSm * (size_t)c->sms * 2048);  // (+ the CTAs' slabs)
+    k.beans = est(c->dens_bean, 128, 8192);
+    k.accs = est(c->dens_acc, 128, 8192);
+    k.defer = std::max<size_t>(k.rec / 8, 65536);
+    k.pool = want_pool ? est(c->dens_pool, 24, 65536) : 0;
+    return k;
 }
 
 void ensure_out(blu_ctx* c, const Caps& k) {
-    c->d_rec.ensure(k.rec);
-    c->d_beans.ensure(k.slots);
-    c->d_accs.ensure(k.slots);
+    if (!c->out) c->out = c->dev_pool->acquire();
+    c->out->rec.ensure(k.rec);
+    c->out->beans.ensure(k.beans);
+    c->out->accs.ensure(k.accs);
     c->d_top.ensure(k.slots);
     c->d_defer.ensure(k.defer);
-    c->d_pool.ensure(k.pool);
+    if (k.pool) c->d_pool.ensure(k.pool);
+    size_t cap = 1024;
+    while (cap < 2 * k.rec) cap <<= 1;
+    c->d_dup.ensure(cap);
+    if (c->keep_hashes) c->d_qhash.ensure(k.rec);
+    c->d_big_rows.ensure((size_t)c->sms * kLongTopCap);
+    c->d_big_cand.ensure((size_t)c->sms * kLongTopCap);
 }
 
-void check_device_error(blu_ctx*, const Counters& h, uint64_t stream_base) {
-    if (!h.err_code) return;
-    std::string m = std::string(dev_err_text(h.err_code)) + " (near byte " + std::to_string(stream_base + h.err_off) + " of the blast output)";
-    if (h.err_code >= DE_INTERNAL) throw std::runtime_error(m);
-    if (h.err_code >= DE_NUM_UNSUPPORTED) throw UnsupportedErr(m);
+inline size_t dup_table_size(const Caps& k) {
+    size_t cap = 1024;
+    while (cap < 2 * k.rec) cap <<= 1;
+    return cap;
+}
+
+std::string dev_err_message(uint32_t code, uint64_t off) {
+    return std::string(dev_err_text(code)) + " (near byte " + std::to_string(off) + " of the blast output)";
+}
+
+[[noreturn]] void throw_device_error(uint32_t code, uint64_t off) {
+    const std::string m = dev_err_message(code, off);
+    if (code >= DE_INTERNAL) throw std::runtime_error(m);
+    if (code >= DE_NUM_UNSUPPORTED) throw UnsupportedErr(m);
     throw DataErr(m);
 }
+
+// Grammar-class errors abort the run wherever the row sits (the reference's CSV reader fails on it too).
+void check_fatal(const Counters& h, uint64_t stream_base) {
+    if (h.err_code) throw_device_error(h.err_code, stream_base + h.err_off);
+}
+
+// What a run leaves for its caller to decide on once the duplicate-id check is complete (a multi-device run merges
+// the shards' checks first): consensus-class errors are fatal only for a contiguous table.
+struct RunStatus {
+    uint32_t soft_code = 0;
+    uint64_t soft_off = 0;
+    bool dup_found = false;
+    void note_soft(const Counters& h, uint64_t stream_base) {
+        if (h.soft_code && !soft_code) soft_code = h.soft_code, soft_off = stream_base + h.soft_off;
+    }
+};
 
 // BLU_SYNC_DEBUG=1: synchronise behind every kernel so that a device fault is attributed to the kernel that caused it
 inline void dbg_sync(cudaStream_t s, const char* what) {
@@ -307,9 +452,30 @@ inline void dbg_sync(cudaStream_t s, const char* what) {
     if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
 }
 
-// Runs the kernels on one resident chunk.  rec_begin = number of records before this chunk.
-void launch_chunk(blu_ctx* c, const uint8_t* dtext, uint64_t begin, uint64_t end, bool final_chunk, const Caps& k, cudaStream_t s,
-                  uint32_t rec_begin_hint, bool time_it) {
+float ev_ms(cudaEvent_t a, cudaEvent_t b) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    return ms;
+}
+
+void reset_counters_async(blu_ctx* c, cudaStream_t s) {
+    CK(cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), s));
+    CK(cudaMemsetAsync(&c->d_ctr->tail_start, 0xFF, sizeof(unsigned long long), s));
+}
+
+// How the strings of a result are delivered.
+enum class Strings {
+    Pool,      // gathered into a string pool that is downloaded with the records
+    DeviceText // references into the device text (device-resident results)
+    ,
+    HostText   // references into the caller's host text (BLU_OPT_TEXT_REFS): buffer offsets are relocated by `delta`
+};
+
+// One range / chunk, all of it queued without a host round trip: tile kernel, long-run kernel (returns at once when
+// nothing was deferred), consensus, (gather,) duplicate-id check, and the one-thread kernel that advances the device-side
+// cursors and snapshots the counters into mapped host memory.  `begin` may be kBeginFromCounters.
+void launch_range(blu_ctx* c, const uint8_t* dtext, uint64_t begin, uint64_t end, bool final_chunk, const Caps& k, cudaStream_t s, int slot,
+                  Strings strings, long long delta) {
     RunParams p{};
     p.text = dtext;
     p.begin = begin;
@@ -317,46 +483,131 @@ void launch_chunk(blu_ctx* c, const uint8_t* dtext, uint64_t begin, uint64_t end
     p.final_chunk = final_chunk ? 1 : 0;
     p.strategy = c->opts.strategy;
     p.T = c->dT;
-    p.records = c->d_rec.p;
-    p.rec_cap = (uint32_t)std::min<size_t>(k.rec, 0xFFFFFFFFu);
-    p.beans = c->d_beans.p;
-    p.accs = c->d_accs.p;
+    p.records = c->out->rec.p;
+    p.rec_cap = k.rec;
     p.toprows = c->d_top.p;
-    p.slot_cap = (uint32_t)std::min<size_t>(k.slots, 0xFFFFFFFFu);
+    p.slot_cap = k.slots;
+    p.beans = c->out->beans.p;
+    p.bean_cap = k.beans;
+    p.accs = c->out->accs.p;
+    p.acc_cap = k.accs;
     p.defer = c->d_defer.p;
     p.defer_cap = (uint32_t)std::min<size_t>(k.defer, 0xFFFFFFFFu);
+    p.big_rows = c->d_big_rows.p;
+    p.big_cand = c->d_big_cand.p;
     p.ctr = c->d_ctr;
-    (void)rec_begin_hint;
-    if (time_it) CK(cudaEventRecord(c->ev[0], s));
+    cudaEvent_t* ev = c->ev[slot];
+    CK(cudaEventRecord(ev[0], s));
     CK(launch_tile_kernel(p, tile_kernel_grid(c->device), s));
     dbg_sync(s, "tile_kernel");
-    if (time_it) CK(cudaEventRecord(c->ev[1], s));
+    CK(cudaEventRecord(ev[1], s));
     CK(launch_longrun_kernel(p, c->sms, s));
     dbg_sync(s, "longrun_kernel");
-    if (time_it) CK(cudaEventRecord(c->ev[2], s));
-    c->tm.n_kernel_launches += 2;
+    CK(cudaEventRecord(ev[2], s));
+    PostParams q{};
+    q.records = c->out->rec.p;
+    q.rec_cap = k.rec;
+    q.toprows = c->d_top.p;
+    q.slot_cap = k.slots;
+    q.beans = c->out->beans.p;
+    q.bean_cap = k.beans;
+    q.accs = c->out->accs.p;
+    q.acc_cap = k.accs;
+    q.text = dtext;
+    q.text_end = end;
+    q.pool = strings == Strings::Pool ? c->d_pool.p : nullptr;
+    q.pool_cap = strings == Strings::Pool ? k.pool : 0;
+    q.T = c->dT;
+    q.strategy = c->opts.strategy;
+    q.ctr = c->d_ctr;
+    CK(launch_consensus_kernel(q, c->sms, s));
+    dbg_sync(s, "consensus_kernel");
+    if (strings == Strings::Pool) {
+        CK(launch_gather_kernel(q, c->sms, s));
+        dbg_sync(s, "gather_kernel");
+        c->tm.n_kernel_launches += 1;
+    }
+    DupParams d{};
+    d.records = c->out->rec.p;
+    d.rec_cap = k.rec;
+    d.beans = c->out->beans.p;
+    d.accs = c->out->accs.p;
+    d.strings = strings == Strings::Pool ? c->d_pool.p : dtext;
+    d.strings_len = strings == Strings::Pool ? k.pool : end;
+    d.table = c->d_dup.p;
+    d.mask = (uint32_t)(dup_table_size(k) - 1);
+    d.hashes = c->d_qhash.cap >= k.rec ? c->d_qhash.p : nullptr;
+    d.ref_delta = strings == Strings::HostText ? delta : 0;
+    d.ctr = c->d_ctr;
+    CK(launch_dup_kernel(d, c->sms, s));
+    dbg_sync(s, "dup_kernel");
+    AdvanceParams a{};
+    a.ctr = c->d_ctr;
+    a.rec_cap = k.rec;
+    a.range_end = end;
+    a.snapshot = c->d_snap + slot;
+    CK(launch_advance_kernel(a, s));
+    dbg_sync(s, "advance_kernel");
+    CK(cudaEventRecord(ev[3], s));
+    c->tm.n_kernel_launches += 5;
 }
 
-void reset_counters_async(blu_ctx* c, cudaStream_t s, bool whole) {
-    if (whole) {
-        CK(cudaMemsetAsync(c->d_ctr, 0, sizeof(Counters), s));
-    } else {
-        // per chunk: n_defer, work_ticket back to zero; keep the output counters
-        CK(cudaMemsetAsync(&c->d_ctr->n_defer, 0, sizeof(unsigned), s));
-        CK(cudaMemsetAsync(&c->d_ctr->work_ticket, 0, sizeof(unsigned), s));
+// Start of a run: output arrays, counters, the duplicate-id table.
+void begin_run(blu_ctx* c, const Caps& k, cudaStream_t s) {
+    ensure_out(c, k);
+    reset_counters_async(c, s);
+    CK(cudaMemsetAsync(c->d_dup.p, 0, dup_table_size(k) * sizeof(unsigned long long), s));
+}
+
+inline bool overflowed(const Counters& h, const Caps& k) {
+    return h.cap_overflow || h.rec_count > k.rec || h.slot_count > k.slots || h.bean_used > k.beans || h.acc_used > k.accs || h.n_defer > k.defer ||
+           (k.pool && h.pool_used > k.pool);
+}
+
+// `scale` = whole input / part of it the counters cover (>= 1): the cursors are cumulative over the chunks / ranges
+// processed so far, so the new capacity is extrapolated to the whole input -- otherwise a table of tiny rows in many
+// chunks needs one retry per chunk.  `n_bytes` bounds the extrapolation (a row has >= 26 bytes).
+void grow_caps(const Counters& h, Caps& k, double scale, uint64_t n_bytes) {
+    bool grew = false;
+    scale = std::max(1.0, scale);
+    auto want = [&](uint64_t seen, uint64_t slack, uint64_t bound) {
+        const double w = (double)seen * scale * 1.125 + (double)slack;
+        const double v = std::max<double>((double)seen + (double)slack, std::min<double>(w, (double)bound + (double)slack));
+        return (size_t)std::min<double>(v, (double)kIdxMax);
+    };
+    if (h.rec_count > k.rec) k.rec = want(h.rec_count, 1024, n_bytes / 26), grew = true;
+    if (h.slot_count > k.slots) k.slots = want(h.slot_count, 1024, n_bytes / 26 + (1u << 20)), grew = true;
+    if (h.bean_used > k.beans) k.beans = want(h.bean_used, 1024, n_bytes / 26), grew = true;
+    if (h.acc_used > k.accs) k.accs = want(h.acc_used, 1024, n_bytes / 26), grew = true;
+    if (h.n_defer > k.defer) k.defer = (size_t)h.n_defer + h.n_defer / 8 + 1024, grew = true;
+    if (k.pool && h.pool_used > k.pool) k.pool = want(h.pool_used, 4096, n_bytes), grew = true;
+    if (!grew) {  // overflow flagged but the counts look fine (a reservation raced past the cap): grow everything
+        auto dbl = [](size_t v) { return std::min<size_t>(v * 2, kIdxMax); };
+        k.rec = dbl(k.rec), k.slots = dbl(k.slots), k.beans = dbl(k.beans), k.accs = dbl(k.accs), k.defer *= 2;
+        if (k.pool) k.pool *= 2;
     }
-    CK(cudaMemsetAsync(&c->d_ctr->tail_start, 0xFF, sizeof(unsigned long long), s));
+    if (h.rec_count >= kIdxMax || h.slot_count >= kIdxMax || h.bean_used >= kIdxMax || h.acc_used >= kIdxMax)
+        throw UnsupportedErr("more than 2^32 queries / top rows in one device's share of the table (shard it over more devices)");
+}
+
+void learn_densities(blu_ctx* c, const Counters& h, uint64_t n) {
+    if (!n) return;
+    c->dens_rec = (double)h.rec_count / (double)n;
+    c->dens_slot = (double)h.slot_count / (double)n;
+    c->dens_bean = (double)h.bean_used / (double)n;
+    c->dens_acc = (double)h.acc_used / (double)n;
+    if (h.pool_used) c->dens_pool = (double)h.pool_used / (double)n;
 }
 
 // Incremental download of the finished part of the result arrays on the context's download stream, so that the
 // device->host copies of one range / chunk run under the kernels (and host->device copies) of the next one.
 struct Downloader {
     blu_ctx* c;
-    blu_result* r;
-    uint64_t rec_done = 0, slot_done = 0, pool_done = 0;
+    ResultPartOwned* r;
+    uint64_t rec_done = 0, bean_done = 0, acc_done = 0, pool_done = 0;
     uint64_t bytes = 0;
 
-    Downloader(blu_ctx* ctx, blu_result* res) : c(ctx), r(res) {}
+    Downloader(blu_ctx* ctx, ResultPartOwned* res) : c(ctx), r(res) { r->pinned = c->pool; }
 
     static void grow(blu_ctx* c, PinnedBuf& b, size_t need, size_t keep, cudaStream_t ds) {
         if (b.cap >= need && b.p) return;
@@ -369,140 +620,277 @@ struct Downloader {
         b = nb;
     }
     // capacity for at least these totals (called with estimates first, exact numbers at the end)
-    void reserve(uint64_t rec, uint64_t slots, uint64_t pool) {
+    void reserve(uint64_t rec, uint64_t beans, uint64_t accs, uint64_t pool) {
         cudaStream_t ds = c->d2h_stream;
         grow(c, r->b_rec, rec * sizeof(blu_record), rec_done * sizeof(blu_record), ds);
-        grow(c, r->b_beans, slots * sizeof(blu_bean), slot_done * sizeof(blu_bean), ds);
-        grow(c, r->b_accs, slots * sizeof(blu_acc), slot_done * sizeof(blu_acc), ds);
-        grow(c, r->b_pool, pool, pool_done, ds);
+        grow(c, r->b_beans, beans * sizeof(blu_bean), bean_done * sizeof(blu_bean), ds);
+        grow(c, r->b_accs, accs * sizeof(blu_acc), acc_done * sizeof(blu_acc), ds);
+        if (pool) grow(c, r->b_pool, pool, pool_done, ds);
     }
-    // everything up to the counters in `h` is final on the device (the compute stream has been synchronised)
+    // everything below the cursors of snapshot `h` is final on the device (its post-pass has completed)
     void push(const Counters& h) {
         cudaStream_t ds = c->d2h_stream;
-        const uint64_t rec = n_rec_of(h), slots = n_slots_of(h), pool = h.pool_used;
-        reserve(rec, slots, pool);
+        const uint64_t rec = h.post_done, beans = h.bean_used, accs = h.acc_used, pool = h.pool_used;
+        reserve(rec, beans, accs, pool);
         if (rec > rec_done)
-            CK(cudaMemcpyAsync((blu_record*)r->b_rec.p + rec_done, c->d_rec.p + rec_done, (rec - rec_done) * sizeof(blu_record),
-                               cudaMemcpyDeviceToHost, ds));
-        if (slots > slot_done) {
-            CK(cudaMemcpyAsync((blu_bean*)r->b_beans.p + slot_done, c->d_beans.p + slot_done, (slots - slot_done) * sizeof(blu_bean),
-                               cudaMemcpyDeviceToHost, ds));
-            CK(cudaMemcpyAsync((blu_acc*)r->b_accs.p + slot_done, c->d_accs.p + slot_done, (slots - slot_done) * sizeof(blu_acc),
-                               cudaMemcpyDeviceToHost, ds));
-        }
-        if (pool > pool_done)
-            CK(cudaMemcpyAsync((char*)r->b_pool.p + pool_done, c->d_pool.p + pool_done, pool - pool_done, cudaMemcpyDeviceToHost, ds));
-        bytes += (rec - rec_done) * sizeof(blu_record) + (slots - slot_done) * (sizeof(blu_bean) + sizeof(blu_acc)) + (pool - pool_done);
-        rec_done = rec, slot_done = slots, pool_done = pool;
+            CK(cudaMemcpyAsync((blu_record*)r->b_rec.p + rec_done, c->out->rec.p + rec_done, (rec - rec_done) * sizeof(blu_record), cudaMemcpyDeviceToHost, ds));
+        if (beans > bean_done)
+            CK(cudaMemcpyAsync((blu_bean*)r->b_beans.p + bean_done, c->out->beans.p + bean_done, (beans - bean_done) * sizeof(blu_bean), cudaMemcpyDeviceToHost, ds));
+        if (accs > acc_done)
+            CK(cudaMemcpyAsync((blu_acc*)r->b_accs.p + acc_done, c->out->accs.p + acc_done, (accs - acc_done) * sizeof(blu_acc), cudaMemcpyDeviceToHost, ds));
+        if (pool > pool_done) CK(cudaMemcpyAsync((char*)r->b_pool.p + pool_done, c->d_pool.p + pool_done, pool - pool_done, cudaMemcpyDeviceToHost, ds));
+        bytes += (rec - rec_done) * sizeof(blu_record) + (beans - bean_done) * sizeof(blu_bean) + (accs - acc_done) * sizeof(blu_acc) + (pool - pool_done);
+        rec_done = rec, bean_done = beans, acc_done = accs, pool_done = pool;
     }
     void finish(const Counters& h) {
         push(h);
         CK(cudaStreamSynchronize(c->d2h_stream));
-        r->n_rec = rec_done;
-        r->n_slots = slot_done;
-        r->pool_len = pool_done;
-        r->n_rows = h.n_rows;
+        r->n_rec = rec_done, r->n_beans = bean_done, r->n_accs = acc_done, r->pool_len = pool_done;
+        r->on_host = true;
         c->tm.d2h_bytes += bytes + sizeof(Counters);
-        c->tm.result_bytes = r->n_rec * sizeof(blu_record) + r->n_slots * (sizeof(blu_bean) + sizeof(blu_acc));
-        c->tm.n_queries = r->n_rec;
-        c->tm.n_rows = r->n_rows;
+        c->tm.result_bytes = rec_done * sizeof(blu_record) + bean_done * sizeof(blu_bean) + acc_done * sizeof(blu_acc);
+        c->tm.n_queries = rec_done;
+        c->tm.n_rows = h.n_rows;
     }
     void abandon() {  // retry with larger device capacities: drop what was downloaded
         cudaStreamSynchronize(c->d2h_stream);
-        rec_done = slot_done = pool_done = 0;
+        rec_done = bean_done = acc_done = pool_done = 0;
         bytes = 0;
     }
 };
 
-float ev_ms(cudaEvent_t a, cudaEvent_t b) {
-    float ms = 0;
-    cudaEventElapsedTime(&ms, a, b);
-    return ms;
-}
-
-// Post-pass on all records of the run: string gather for [rec_begin, rec_end) + (at the end) duplicate check.
-void launch_gather(blu_ctx* c, const uint8_t* dtext, uint64_t text_end, uint32_t rec_begin, uint32_t rec_end, const Caps& k, cudaStream_t s) {
-    {
-        // warp-per-query consensus over the top-row table the tile kernel produced for these records
-        ConsParams q{};
-        q.records = c->d_rec.p;
-        q.rec_begin = rec_begin;
-        q.rec_end = rec_end;
-        q.toprows = c->d_top.p;
-        q.beans = c->d_beans.p;
-        q.accs = c->d_accs.p;
-        q.text = dtext;
-        q.text_end = text_end;
-        q.T = c->dT;
-        q.strategy = c->opts.strategy;
-        q.ctr = c->d_ctr;
-        CK(launch_consensus_kernel(q, s));
-        dbg_sync(s, "consensus_kernel");
-        if (rec_end > rec_begin) c->tm.n_kernel_launches += 1;
-    }
-    GatherParams g{};
-    g.text = dtext;
-    g.records = c->d_rec.p;
-    g.accs = c->d_accs.p;
-    g.rec_begin = rec_begin;
-    g.rec_end = rec_end;
-    g.pool = c->d_pool.p;
-    g.pool_cap = k.pool;
-    g.ctr = c->d_ctr;
-    CK(launch_gather_kernel(g, s));
-    dbg_sync(s, "gather_kernel");
-    if (rec_end > rec_begin) c->tm.n_kernel_launches += 1;
-}
-
-void launch_dup(blu_ctx* c, uint32_t n_rec, cudaStream_t s) {
-    if (!n_rec) return;
-    size_t cap = 1024;
-    while (cap < 2ull * n_rec) cap <<= 1;
-    c->d_dup.ensure(cap);
-    CK(cudaMemsetAsync(c->d_dup.p, 0, cap * sizeof(unsigned long long), s));
-    DupParams d{};
-    d.records = c->d_rec.p;
-    d.n_rec = n_rec;
-    d.pool = c->d_pool.p;
-    d.pool_cap = c->d_pool.cap;
-    d.table = c->d_dup.p;
-    d.mask = (uint32_t)(cap - 1);
-    d.ctr = c->d_ctr;
-    CK(launch_dup_kernel(d, s));
-    dbg_sync(s, "dup_kernel");
-    c->tm.n_kernel_launches += 1;
-}
-
-// Tried and dropped (profiles/README.md): a one-thread kernel writing the counters to mapped host memory with the host
-// spinning on a sequence word, to avoid the copy engine and the stream-synchronise wake-up: no measurable difference.
-void read_counters(blu_ctx* c, cudaStream_t s) {
-    CK(cudaMemcpyAsync(c->h_ctr, c->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-}
-
-// `scale` = whole input / part of it the counters cover (>= 1): records, slots and pool bytes are cumulative over the
-// chunks / ranges processed so far, so the new capacity is extrapolated to the whole input -- otherwise a table of tiny
-// rows in many chunks needs one retry per chunk.  `n_bytes` bounds the extrapolation (a row has >= 26 bytes).
-bool grow_caps(const Counters& h, Caps& k, uint64_t defer_seen, double scale, uint64_t n_bytes) {
-    bool grew = false;
-    scale = std::max(1.0, scale);
-    auto want = [&](uint64_t seen, uint64_t slack, uint64_t bound) {
-        const double w = (double)seen * scale * 1.125 + (double)slack;
-        return (size_t)std::max<double>((double)seen + (double)slack, std::min<double>(w, (double)bound + (double)slack));
-    };
-    if (n_rec_of(h) > k.rec) k.rec = want(n_rec_of(h), 1024, n_bytes / 26), grew = true;
-    if (n_slots_of(h) > k.slots) k.slots = want(n_slots_of(h), 1024, n_bytes / 26), grew = true;
-    if (defer_seen > k.defer) k.defer = (size_t)defer_seen + defer_seen / 8 + 1024, grew = true;
-    if (h.pool_used > k.pool) k.pool = want(h.pool_used, 4096, n_bytes), grew = true;
-    if (!grew) {  // overflow flagged but counts look fine (reservation raced past the cap): grow everything
-        k.rec *= 2, k.slots *= 2, k.defer *= 2, k.pool *= 2;
-    }
-    return true;
-}
-
 void require_ready(blu_ctx* c) {
     if (!c->tax) throw std::invalid_argument("no taxonomy loaded (call blu_taxonomy_load_json first)");
 }
+
+// Output densities of a table this context has not seen the like of: the kernels run once over a small prefix (results
+// discarded), so that the arrays of the real run are sized for what the table holds instead of for the shortest rows the
+// grammar allows (1.5 GB of records for a 3.8 GB table; more than a B200 has for a 77 GB one).
+void probe_densities(blu_ctx* c, const uint8_t* dtext, uint64_t begin, uint64_t end, cudaStream_t s) {
+    const uint64_t len = end - begin;
+    if (len < (1u << 20)) return;
+    const blu_timings keep = c->tm;
+    Caps k = initial_caps(c, len, false);
+    begin_run(c, k, s);
+    launch_range(c, dtext, begin, end, false, k, s, 0, Strings::DeviceText, 0);
+    CK(cudaEventSynchronize(c->ev[0][3]));
+    const Counters h = c->h_snap[0];
+    c->tm = keep;
+    if (overflowed(h, k) || h.err_code || h.post_done < 64) return;  // (the real run reports whatever is wrong)
+    const uint64_t covered = h.next_begin > begin && h.next_begin <= end ? h.next_begin - begin : len;
+    learn_densities(c, h, covered);
+    c->dens_pool = c->dens_rec * 48.0 + c->dens_acc * 24.0;  // (ids + accessions; an underestimate is grown by the retry)
+}
+
+struct NonContiguous : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+// What a single-device entry point does with the status of its run.
+void settle(const RunStatus& st) {
+    if (st.dup_found) throw NonContiguous("a query id occurs in two non-adjacent groups of rows");
+    if (st.soft_code) throw_device_error(st.soft_code, st.soft_off);
+}
+
+std::vector<uint64_t> resident_ranges(uint64_t n) {
+    // Large resident tables are processed in a few query-aligned ranges so that the download of one range's records
+    // overlaps the kernels of the next.  Equal ranges measured best (tools/range_split.py, profiles/README.md).
+    // BLU_RANGE_FRACS="0.3,0.3,0.25,0.15" overrides the split (measurement knob).
+    std::vector<double> fracs(n >= (512ull << 20) ? 4 : (n >= (128ull << 20) ? 2 : 1), 1.0);
+    if (const char* ev = getenv("BLU_RANGE_FRACS")) {
+        std::vector<double> f;
+        for (const char* q = ev; *q;) {
+            char* e2 = nullptr;
+            double v = strtod(q, &e2);
+            if (e2 == q || !(v > 0)) break;
+            f.push_back(v);
+            q = *e2 == ',' ? e2 + 1 : e2;
+        }
+        if (!f.empty() && f.size() <= (size_t)kMaxRanges) fracs = f;
+    }
+    std::vector<uint64_t> range_end(fracs.size());
+    double tot = 0, acc = 0;
+    for (double f : fracs) tot += f;
+    for (size_t i = 0; i < fracs.size(); i++) {
+        acc += fracs[i];
+        const uint64_t e = (uint64_t)((double)n * (acc / tot));
+        range_end[i] = std::min<uint64_t>(n, (e + (uint64_t)kTile - 1) / (uint64_t)kTile * (uint64_t)kTile);
+    }
+    range_end.back() = n;
+    return range_end;
+}
+
+void check_device_text(const uint8_t* dtext, uint64_t n) {
+    if (n == 0) throw DataErr("empty blast output (the reference's CsvReader fails on an empty file)");
+    if (((uintptr_t)dtext & 15) != 0) throw std::invalid_argument("device text must be 16-byte aligned");
+}
+
+// --- text resident on the device, result downloaded -------------------------------------------------------------
+// Every range's kernels are queued up front -- a range starts where the previous one stopped (Counters.next_begin), the
+// post-pass takes its record range from the device counters -- so the GPU never waits for the host; the host trails
+// behind, reads each range's snapshot when its event fires and queues that range's download on the download stream.
+void run_device_download(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStream_t s, ResultPartOwned* r, RunStatus& st) {
+    require_ready(c);
+    check_device_text(dtext, n);
+    c->tm = blu_timings{};
+    if (c->dens_rec == 0 && n > (64ull << 20)) probe_densities(c, dtext, 0, std::min<uint64_t>(n, 32ull << 20), s);
+    Caps k = initial_caps(c, n, true);
+    const std::vector<uint64_t> range_end = resident_ranges(n);
+    const int n_ranges = (int)range_end.size();
+    Downloader dl(c, r);
+    for (int attempt = 0; attempt < 8; attempt++) {
+        begin_run(c, k, s);
+        for (int ri = 0; ri < n_ranges; ri++)
+            launch_range(c, dtext, ri == 0 ? 0 : kBeginFromCounters, range_end[ri], ri + 1 == n_ranges, k, s, ri, Strings::Pool, 0);
+        bool retry = false;
+        Counters h{};
+        double ms_tile = 0, ms_long = 0, ms_post = 0;
+        for (int ri = 0; ri < n_ranges; ri++) {
+            CK(cudaEventSynchronize(c->ev[ri][3]));
+            h = c->h_snap[ri];
+            ms_tile += ev_ms(c->ev[ri][0], c->ev[ri][1]);
+            ms_long += ev_ms(c->ev[ri][1], c->ev[ri][2]);
+            ms_post += ev_ms(c->ev[ri][2], c->ev[ri][3]);
+            c->tm.n_deferred_runs += h.n_defer;
+            if (overflowed(h, k)) {
+                grow_caps(h, k, (double)n / (double)std::max<uint64_t>(range_end[ri], 1), n);
+                retry = true;
+                break;
+            }
+            check_fatal(h, 0);
+            if (ri + 1 < n_ranges && !h.dup_found) {
+                if (ri == 0 && range_end[0] > 0) {
+                    // size the pinned result buffers from the density of the first range
+                    const double f = 1.15 * (double)n / (double)range_end[0];
+                    dl.reserve((uint64_t)(h.post_done * f) + 4096, (uint64_t)(h.bean_used * f) + 8192, (uint64_t)(h.acc_used * f) + 8192,
+                               (uint64_t)(h.pool_used * f) + 65536);
+                }
+                dl.push(h);  // runs on the download stream under the next ranges' kernels
+            }
+        }
+        if (retry) {
+            CK(cudaStreamSynchronize(s));  // the later ranges are still queued
+            dl.abandon();
+            c->tm = blu_timings{};
+            continue;
+        }
+        st.note_soft(h, 0);
+        st.dup_found = h.dup_found != 0;
+        if (st.dup_found) {
+            dl.abandon();
+            return;
+        }
+        if (h.post_done == 0) throw DataErr("the blast output holds no rows");
+        c->tm.ms_tile_kernel = ms_tile;
+        c->tm.ms_longrun_kernel = ms_long;
+        c->tm.ms_gather_kernel = ms_post;
+        c->tm.ms_total_device = ms_tile + ms_long + ms_post;
+        c->tm.text_bytes = n;
+        c->tm.taxonomy_bytes = c->tax->device_bytes();
+        c->tm.n_tile_launches = (uint64_t)n_ranges;
+        dl.finish(h);
+        learn_densities(c, h, n);
+        return;
+    }
+    throw std::runtime_error("output capacity did not converge");
+}
+
+// --- text resident on the device, result stays on the device ----------------------------------------------
+// One range, five launches, one host synchronisation; nothing but the counters crosses PCIe.
+void run_device_resident(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStream_t s, ResultPartOwned* r, RunStatus& st) {
+    require_ready(c);
+    check_device_text(dtext, n);
+    c->tm = blu_timings{};
+    if (c->dens_rec == 0 && n > (64ull << 20)) probe_densities(c, dtext, 0, std::min<uint64_t>(n, 32ull << 20), s);
+    Caps k = initial_caps(c, n, false);
+    for (int attempt = 0; attempt < 8; attempt++) {
+        begin_run(c, k, s);
+        launch_range(c, dtext, 0, n, true, k, s, 0, Strings::DeviceText, 0);
+        CK(cudaEventSynchronize(c->ev[0][3]));
+        const Counters h = c->h_snap[0];
+        if (overflowed(h, k)) {
+            grow_caps(h, k, 1.0, n);
+            c->tm = blu_timings{};
+            continue;
+        }
+        check_fatal(h, 0);
+        st.note_soft(h, 0);
+        st.dup_found = h.dup_found != 0;
+        if (!st.dup_found && h.post_done == 0) throw DataErr("the blast output holds no rows");
+        c->tm.ms_tile_kernel = ev_ms(c->ev[0][0], c->ev[0][1]);
+        c->tm.ms_longrun_kernel = ev_ms(c->ev[0][1], c->ev[0][2]);
+        c->tm.ms_gather_kernel = ev_ms(c->ev[0][2], c->ev[0][3]);
+        c->tm.ms_total_device = c->tm.ms_tile_kernel + c->tm.ms_longrun_kernel + c->tm.ms_gather_kernel;
+        c->tm.n_deferred_runs = h.n_defer;
+        c->tm.text_bytes = n;
+        c->tm.taxonomy_bytes = c->tax->device_bytes();
+        c->tm.n_tile_launches = 1;
+        c->tm.n_queries = h.post_done;
+        c->tm.n_rows = h.n_rows;
+        c->tm.d2h_bytes = sizeof(Counters);
+        c->tm.result_bytes = h.post_done * sizeof(blu_record) + h.bean_used * sizeof(blu_bean) + h.acc_used * sizeof(blu_acc);
+        r->dev = std::move(c->out);
+        r->dev_pool = c->dev_pool;
+        r->ctx = c;
+        r->dtext = dtext;
+        r->dtext_len = n;
+        r->n_rec = h.post_done, r->n_beans = h.bean_used, r->n_accs = h.acc_used;
+        r->on_host = false;
+        learn_densities(c, h, n);
+        return;
+    }
+    throw std::runtime_error("output capacity did not converge");
+}
+
+// Brings a device-resident part to the host: the referenced strings are gathered into a pool first (a counting pass of
+// the gather kernel sizes it), then records, beans, accession references and the pool are downloaded.
+void download_part(ResultPartOwned* r) {
+    if (r->on_host) return;
+    blu_ctx* c = r->ctx;
+    CK(cudaSetDevice(c->device));
+    cudaStream_t s = c->stream;
+    PostParams q{};
+    q.records = r->dev->rec.p;
+    q.rec_cap = r->n_rec;
+    q.beans = r->dev->beans.p;
+    q.bean_cap = r->n_beans;
+    q.accs = r->dev->accs.p;
+    q.acc_cap = r->n_accs;
+    q.text = r->dtext;
+    q.text_end = r->dtext_len;
+    q.ctr = c->d_ctr;
+    Counters hc{};
+    hc.rec_count = r->n_rec;
+    hc.tail_start = ~0ull;
+    CK(cudaMemcpyAsync(c->d_ctr, &hc, sizeof hc, cudaMemcpyHostToDevice, s));
+    q.pool = nullptr;  // counting pass
+    CK(launch_gather_kernel(q, c->sms, s));
+    Counters got{};
+    CK(cudaMemcpyAsync(&got, c->d_ctr, sizeof got, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    const uint64_t pool_len = got.pool_used;
+    c->d_pool.ensure(std::max<uint64_t>(pool_len, 64));
+    CK(cudaMemcpyAsync(c->d_ctr, &hc, sizeof hc, cudaMemcpyHostToDevice, s));
+    q.pool = c->d_pool.p;
+    q.pool_cap = pool_len;
+    CK(launch_gather_kernel(q, c->sms, s));
+    r->pinned = c->pool;
+    r->b_rec = c->acquire(std::max<uint64_t>(r->n_rec * sizeof(blu_record), 64));
+    r->b_beans = c->acquire(std::max<uint64_t>(r->n_beans * sizeof(blu_bean), 64));
+    r->b_accs = c->acquire(std::max<uint64_t>(r->n_accs * sizeof(blu_acc), 64));
+    r->b_pool = c->acquire(std::max<uint64_t>(pool_len, 64));
+    if (r->n_rec) CK(cudaMemcpyAsync(r->b_rec.p, r->dev->rec.p, r->n_rec * sizeof(blu_record), cudaMemcpyDeviceToHost, s));
+    if (r->n_beans) CK(cudaMemcpyAsync(r->b_beans.p, r->dev->beans.p, r->n_beans * sizeof(blu_bean), cudaMemcpyDeviceToHost, s));
+    if (r->n_accs) CK(cudaMemcpyAsync(r->b_accs.p, r->dev->accs.p, r->n_accs * sizeof(blu_acc), cudaMemcpyDeviceToHost, s));
+    if (pool_len) CK(cudaMemcpyAsync(r->b_pool.p, c->d_pool.p, pool_len, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(&got, c->d_ctr, sizeof got, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (got.cap_overflow) throw std::runtime_error("string pool of a device-resident result did not fit its counted size");
+    r->pool_len = pool_len;
+    r->dev_pool->release(std::move(r->dev));
+    r->on_host = true;
+}
+
 
 // Non-contiguous hit tables (the reference groups rows through a HashMap<String, Vec<_>>, mod.rs:145,192, so the
 // rows of one query need not be adjacent).  Rare (BLAST emits queries contiguously, blutils appends whole chunks),
@@ -544,337 +932,6 @@ std::string regroup_by_query(const char* text, uint64_t n) {
     return out;
 }
 
-struct NonContiguous : std::runtime_error {
-    using std::runtime_error::runtime_error;
-};
-
-// BLU_TIMELINE=1: device-side event timeline of one resident run (ms from its start), printed to stderr.  A debugging
-// aid for the overlap of result downloads with the next range's kernels; events are only created when it is on.
-struct Timeline {
-    struct Mark {
-        const char* what;
-        int range;
-        cudaEvent_t ev;
-        double host_ms;
-    };
-    bool on = getenv("BLU_TIMELINE") != nullptr;
-    std::vector<Mark> marks;
-    cudaEvent_t t0 = nullptr;
-    std::chrono::steady_clock::time_point h0;
-    void start(cudaStream_t s) {
-        if (!on) return;
-        cudaEventCreate(&t0);
-        cudaEventRecord(t0, s);
-        h0 = std::chrono::steady_clock::now();
-    }
-    void mark(const char* what, int range, cudaStream_t s) {
-        if (!on) return;
-        cudaEvent_t e;
-        cudaEventCreate(&e);
-        cudaEventRecord(e, s);
-        marks.push_back({what, range, e, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count()});
-    }
-    void host(const char* what, int range) {
-        if (!on) return;
-        marks.push_back({what, range, nullptr, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count()});
-    }
-    void dump() {
-        if (!on) return;
-        cudaDeviceSynchronize();
-        for (auto& m : marks) {
-            float ms = -1;
-            if (m.ev) cudaEventElapsedTime(&ms, t0, m.ev);
-            fprintf(stderr, "[timeline] range %d %-22s device %8.3f ms   host(issue) %8.3f ms\n", m.range, m.what, ms, m.host_ms);
-            if (m.ev) cudaEventDestroy(m.ev);
-        }
-        if (t0) cudaEventDestroy(t0);
-        marks.clear();
-    }
-};
-
-// --- text resident on the device ------------------------------------------------------------------------------
-void run_device_serial(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStream_t s, blu_result* r) {
-    require_ready(c);
-    if (n == 0) throw DataErr("empty blast output (the reference's CsvReader fails on an empty file)");
-    if (((uintptr_t)dtext & 15) != 0) throw std::invalid_argument("device text must be 16-byte aligned");
-    c->tm = blu_timings{};
-    Caps k = initial_caps(n);
-    // Large resident tables are processed in a few query-aligned ranges so that the download of one range's records
-    // overlaps the kernels of the next (the unfinished last query of a range simply starts the next range: the
-    // buffer is contiguous, nothing is copied).
-    // Equal ranges measured best (tools/range_split.py, profiles/README.md): the step is K_1 + ... + K_n + D_n + ~0.1 ms of
-    // host round trips per range; a smaller last range makes an earlier download spill past its kernels instead.
-    // BLU_RANGE_FRACS="0.3,0.3,0.25,0.15" overrides the split (measurement knob).
-    std::vector<double> fracs(n >= (512ull << 20) ? 4 : (n >= (128ull << 20) ? 2 : 1), 1.0);
-    if (const char* ev = getenv("BLU_RANGE_FRACS")) {
-        std::vector<double> f;
-        for (const char* q = ev; *q;) {
-            char* e2 = nullptr;
-            double v = strtod(q, &e2);
-            if (e2 == q || !(v > 0)) break;
-            f.push_back(v);
-            q = *e2 == ',' ? e2 + 1 : e2;
-        }
-        if (!f.empty() && f.size() <= 64) fracs = f;
-    }
-    const uint64_t n_ranges = fracs.size();
-    std::vector<uint64_t> range_end(n_ranges);
-    {
-        double tot = 0, acc = 0;
-        for (double f : fracs) tot += f;
-        for (uint64_t i = 0; i < n_ranges; i++) {
-            acc += fracs[i];
-            const uint64_t e = (uint64_t)((double)n * (acc / tot));
-            range_end[i] = std::min<uint64_t>(n, (e + (uint64_t)kTile - 1) / (uint64_t)kTile * (uint64_t)kTile);
-        }
-        range_end[n_ranges - 1] = n;
-    }
-    Downloader dl(c, r);
-    for (int attempt = 0; attempt < 8; attempt++) {
-        ensure_out(c, k);
-        reset_counters_async(c, s, true);
-        bool retry = false;
-        uint64_t begin = 0;
-        uint32_t rec_done = 0;
-        uint64_t defer_total = 0;
-        double ms_tile = 0, ms_long = 0, ms_post = 0;
-        uint64_t launches = 0;
-        Counters h{};
-        Timeline tl;
-        tl.start(s);
-        for (uint64_t ri = 0; ri < n_ranges && !retry; ri++) {
-            const bool final_range = ri + 1 == n_ranges;
-            const uint64_t end = range_end[ri];
-            if (end <= begin && !final_range) continue;
-            if (ri) reset_counters_async(c, s, false);
-            tl.mark("tile+longrun begin", (int)ri, s);
-            launch_chunk(c, dtext, begin, end, final_range, k, s, rec_done, true);
-            tl.mark("tile+longrun end", (int)ri, s);
-            launches++;
-            read_counters(c, s);
-            tl.host("counters #1 on host", (int)ri);
-            h = *c->h_ctr;
-            ms_tile += ev_ms(c->ev[0], c->ev[1]);
-            ms_long += ev_ms(c->ev[1], c->ev[2]);
-            defer_total = std::max<uint64_t>(defer_total, h.n_defer);
-            c->tm.n_deferred_runs += h.n_defer;
-            if (h.cap_overflow || n_rec_of(h) > k.rec || n_slots_of(h) > k.slots || h.n_defer > k.defer) {
-                grow_caps(h, k, h.n_defer, (double)n / (double)std::max<uint64_t>(end, 1), n);
-                retry = true;
-                break;
-            }
-            check_device_error(c, h, 0);
-            CK(cudaEventRecord(c->ev[3], s));
-            launch_gather(c, dtext, end, rec_done, (uint32_t)n_rec_of(h), k, s);
-            if (final_range) launch_dup(c, (uint32_t)n_rec_of(h), s);
-            CK(cudaEventRecord(c->ev[4], s));
-            tl.mark("consensus+gather end", (int)ri, s);
-            rec_done = (uint32_t)n_rec_of(h);
-            read_counters(c, s);
-            tl.host("counters #2 on host", (int)ri);
-            h = *c->h_ctr;
-            ms_post += ev_ms(c->ev[3], c->ev[4]);
-            if (h.cap_overflow || h.pool_used > k.pool) {
-                grow_caps(h, k, defer_total, (double)n / (double)std::max<uint64_t>(end, 1), n);
-                retry = true;
-                break;
-            }
-            check_device_error(c, h, 0);
-            if (!final_range) {
-                if (ri == 0 && end > 0) {
-                    // size the pinned result buffers from the density of the first range
-                    const double f = 1.15 * (double)n / (double)end;
-                    dl.reserve((uint64_t)(n_rec_of(h) * f) + 4096, (uint64_t)(n_slots_of(h) * f) + 8192, (uint64_t)(h.pool_used * f) + 65536);
-                }
-                tl.mark("download begin", (int)ri, c->d2h_stream);
-                dl.push(h);  // runs on the download stream under the next range's kernels
-                tl.mark("download end", (int)ri, c->d2h_stream);
-                begin = h.tail_start != ~0ull ? h.tail_start : end;
-            }
-        }
-        if (retry) {
-            dl.abandon();
-            c->tm = blu_timings{};
-            continue;
-        }
-        if (h.dup_found) {
-            dl.abandon();
-            throw NonContiguous("a query id occurs in two non-adjacent groups of rows");
-        }
-        if (n_rec_of(h) == 0) throw DataErr("the blast output holds no rows");
-        c->tm.ms_tile_kernel = ms_tile;
-        c->tm.ms_longrun_kernel = ms_long;
-        c->tm.ms_gather_kernel = ms_post;
-        c->tm.ms_total_device = ms_tile + ms_long + ms_post;
-        c->tm.text_bytes = n;
-        c->tm.taxonomy_bytes = c->tax->device_bytes();
-        c->tm.n_tile_launches = launches;
-        tl.mark("last download begin", (int)n_ranges - 1, c->d2h_stream);
-        dl.finish(h);
-        tl.mark("last download end", (int)n_ranges - 1, c->d2h_stream);
-        tl.host("run complete", (int)n_ranges - 1);
-        tl.dump();
-        return;
-    }
-    throw std::runtime_error("output capacity did not converge");
-}
-
-void run_device_pipelined(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStream_t s, blu_result* r) {
-    require_ready(c);
-    if (n == 0) throw DataErr("empty blast output (the reference's CsvReader fails on an empty file)");
-    if (((uintptr_t)dtext & 15) != 0) throw std::invalid_argument("device text must be 16-byte aligned");
-    c->tm = blu_timings{};
-    Caps k = initial_caps(n);
-    // Large resident tables are processed in a few query-aligned ranges so that the download of one range's records
-    // overlaps the kernels of the next (the unfinished last query of a range simply starts the next range: the
-    // buffer is contiguous, nothing is copied).
-    // Equal ranges measured best (tools/range_split.py, profiles/README.md): the step is K_1 + ... + K_n + D_n + ~0.1 ms of
-    // host round trips per range; a smaller last range makes an earlier download spill past its kernels instead.
-    // BLU_RANGE_FRACS="0.3,0.3,0.25,0.15" overrides the split (measurement knob).
-    std::vector<double> fracs(n >= (512ull << 20) ? 4 : (n >= (128ull << 20) ? 2 : 1), 1.0);
-    if (const char* ev = getenv("BLU_RANGE_FRACS")) {
-        std::vector<double> f;
-        for (const char* q = ev; *q;) {
-            char* e2 = nullptr;
-            double v = strtod(q, &e2);
-            if (e2 == q || !(v > 0)) break;
-            f.push_back(v);
-            q = *e2 == ',' ? e2 + 1 : e2;
-        }
-        if (!f.empty() && f.size() <= 64) fracs = f;
-    }
-    const uint64_t n_ranges = fracs.size();
-    std::vector<uint64_t> range_end(n_ranges);
-    {
-        double tot = 0, acc = 0;
-        for (double f : fracs) tot += f;
-        for (uint64_t i = 0; i < n_ranges; i++) {
-            acc += fracs[i];
-            const uint64_t e = (uint64_t)((double)n * (acc / tot));
-            range_end[i] = std::min<uint64_t>(n, (e + (uint64_t)kTile - 1) / (uint64_t)kTile * (uint64_t)kTile);
-        }
-        range_end[n_ranges - 1] = n;
-    }
-    Downloader dl(c, r);
-    for (int attempt = 0; attempt < 8; attempt++) {
-        ensure_out(c, k);
-        reset_counters_async(c, s, true);
-        bool retry = false;
-        uint32_t rec_done = 0;
-        uint64_t defer_total = 0;
-        double ms_tile = 0, ms_long = 0, ms_post = 0;
-        uint64_t launches = 0;
-        Counters h{}, h2{};
-        Timeline tl;
-        tl.start(s);
-        auto launch_range = [&](uint64_t ri, uint64_t begin) {
-            if (ri) reset_counters_async(c, s, false);
-            tl.mark("tile+longrun begin", (int)ri, s);
-            launch_chunk(c, dtext, begin, range_end[ri], ri + 1 == n_ranges, k, s, rec_done, true);
-            tl.mark("tile+longrun end", (int)ri, s);
-            launches++;
-        };
-        // The kernels of range i+1 are queued BEFORE the host looks at the post-pass of range i: the GPU goes from the
-        // gather of one range straight into the tile kernel of the next, and the download of range i still starts the
-        // moment its post-pass is done (ev[5] + a second pinned copy of the counters, taken between the two).
-        uint64_t ri = 0;
-        launch_range(0, 0);
-        for (;;) {
-            const bool final_range = ri + 1 == n_ranges;
-            const uint64_t end = range_end[ri];
-            read_counters(c, s);
-            tl.host("counters #1 on host", (int)ri);
-            h = c->h_ctr[0];
-            ms_tile += ev_ms(c->ev[0], c->ev[1]);
-            ms_long += ev_ms(c->ev[1], c->ev[2]);
-            defer_total = std::max<uint64_t>(defer_total, h.n_defer);
-            c->tm.n_deferred_runs += h.n_defer;
-            if (h.cap_overflow || n_rec_of(h) > k.rec || n_slots_of(h) > k.slots || h.n_defer > k.defer || h.pool_used > k.pool) {
-                grow_caps(h, k, h.n_defer, (double)n / (double)std::max<uint64_t>(end, 1), n);
-                retry = true;
-                break;
-            }
-            check_device_error(c, h, 0);
-            CK(cudaEventRecord(c->ev[3], s));
-            launch_gather(c, dtext, end, rec_done, (uint32_t)n_rec_of(h), k, s);
-            if (final_range) launch_dup(c, (uint32_t)n_rec_of(h), s);
-            CK(cudaEventRecord(c->ev[4], s));
-            tl.mark("consensus+gather end", (int)ri, s);
-            CK(cudaMemcpyAsync(&c->h_ctr[1], c->d_ctr, sizeof(Counters), cudaMemcpyDeviceToHost, s));
-            CK(cudaEventRecord(c->ev[5], s));
-            rec_done = (uint32_t)n_rec_of(h);
-            uint64_t next = ri;
-            if (!final_range) {
-                const uint64_t begin = h.tail_start != ~0ull ? h.tail_start : end;  // final after tile + long-run
-                next = ri + 1;
-                while (next + 1 < n_ranges && range_end[next] <= begin) next++;  // a query longer than a whole range
-                launch_range(next, begin);
-            }
-            CK(cudaEventSynchronize(c->ev[5]));
-            tl.host("counters #2 on host", (int)ri);
-            h2 = c->h_ctr[1];
-            ms_post += ev_ms(c->ev[3], c->ev[4]);
-            if (h2.cap_overflow || h2.pool_used > k.pool) {
-                grow_caps(h2, k, defer_total, (double)n / (double)std::max<uint64_t>(end, 1), n);
-                retry = true;
-                break;
-            }
-            check_device_error(c, h2, 0);
-            if (final_range) break;
-            if (ri == 0 && end > 0) {
-                // size the pinned result buffers from the density of the first range
-                const double f = 1.15 * (double)n / (double)end;
-                dl.reserve((uint64_t)(n_rec_of(h2) * f) + 4096, (uint64_t)(n_slots_of(h2) * f) + 8192, (uint64_t)(h2.pool_used * f) + 65536);
-            }
-            tl.mark("download begin", (int)ri, c->d2h_stream);
-            dl.push(h2);  // runs on the download stream under the next range's kernels
-            tl.mark("download end", (int)ri, c->d2h_stream);
-            ri = next;
-        }
-        if (retry) {
-            CK(cudaStreamSynchronize(s));  // the next range may already be running
-            dl.abandon();
-            c->tm = blu_timings{};
-            continue;
-        }
-        if (h2.dup_found) {
-            dl.abandon();
-            throw NonContiguous("a query id occurs in two non-adjacent groups of rows");
-        }
-        if (n_rec_of(h2) == 0) throw DataErr("the blast output holds no rows");
-        c->tm.ms_tile_kernel = ms_tile;
-        c->tm.ms_longrun_kernel = ms_long;
-        c->tm.ms_gather_kernel = ms_post;
-        c->tm.ms_total_device = ms_tile + ms_long + ms_post;
-        c->tm.text_bytes = n;
-        c->tm.taxonomy_bytes = c->tax->device_bytes();
-        c->tm.n_tile_launches = launches;
-        tl.mark("last download begin", (int)n_ranges - 1, c->d2h_stream);
-        dl.finish(h2);
-        tl.mark("last download end", (int)n_ranges - 1, c->d2h_stream);
-        tl.host("run complete", (int)n_ranges - 1);
-        tl.dump();
-        return;
-    }
-    throw std::runtime_error("output capacity did not converge");
-}
-
-// BLU_RESIDENT_SERIAL=1 selects the loop with two host round trips per range (A/B measurement).  On any failure nothing
-// may still be reading the caller's device text when the call returns.
-void run_device(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStream_t s, blu_result* r) {
-    static const bool serial = getenv("BLU_RESIDENT_SERIAL") != nullptr;
-    try {
-        if (serial)
-            run_device_serial(c, dtext, n, s, r);
-        else
-            run_device_pipelined(c, dtext, n, s, r);
-    } catch (...) {
-        cudaStreamSynchronize(s);
-        cudaStreamSynchronize(c->d2h_stream);
-        throw;
-    }
-}
-
 // --- where the streamed path takes the text of chunk `ci` from -------------------------------------------------
 struct ChunkSource {
     virtual ~ChunkSource() = default;
@@ -896,7 +953,7 @@ class FileSource : public ChunkSource {
     static constexpr uint64_t kRing = 3;
     blu_ctx* c_;
     int fd_;
-    uint64_t n_, chunk_, n_chunks_;
+    uint64_t base_, n_, chunk_, n_chunks_;  // the source is bytes [base_, base_ + n_) of the file
     int n_readers_;
     PinnedBuf buf_[kRing];
     std::mutex mu_;
@@ -910,7 +967,7 @@ class FileSource : public ChunkSource {
 
     bool read_span(char* dst, uint64_t off, uint64_t len, std::string& err) const {
         while (len) {
-            ssize_t got = pread(fd_, dst, (size_t)std::min<uint64_t>(len, 1ull << 30), (off_t)off);
+            ssize_t got = pread(fd_, dst, (size_t)std::min<uint64_t>(len, 1ull << 30), (off_t)(base_ + off));
             if (got < 0 && errno == EINTR) continue;
             if (got <= 0) {
                 err = got == 0 ? "the blast output shrank while it was read" : std::string("read error on the blast output: ") + strerror(errno);
@@ -981,9 +1038,12 @@ class FileSource : public ChunkSource {
     }
 
    public:
-    FileSource(blu_ctx* c, int fd, uint64_t n, uint64_t chunk) : c_(c), fd_(fd), n_(n), chunk_(chunk), n_chunks_((n + chunk - 1) / chunk) {
+    FileSource(blu_ctx* c, int fd, uint64_t base, uint64_t n, uint64_t chunk, int sharers = 1)
+        : c_(c), fd_(fd), base_(base), n_(n), chunk_(chunk), n_chunks_((n + chunk - 1) / chunk) {
+        // readers: the page-cache copy is the bound of this path, one thread moves ~5.6 GB/s; `sharers` = the
+        // file sources of a multi-device run that share the host's cores
         const unsigned hc = std::thread::hardware_concurrency();
-        n_readers_ = (int)std::min<unsigned>(8, std::max<unsigned>(1, hc ? hc : 4));
+        n_readers_ = (int)std::min<unsigned>(16, std::max<unsigned>(2, (hc ? hc : 8) / (unsigned)std::max(1, sharers)));
         if (const char* ev = getenv("BLU_READ_THREADS")) n_readers_ = std::max(1, std::min(64, atoi(ev)));
         const uint64_t used = std::min<uint64_t>(kRing, n_chunks_);
         try {
@@ -1030,7 +1090,8 @@ class FileSource : public ChunkSource {
 // --- text on the host: chunked, double-buffered H2D overlapped with the kernels --------------------------------
 inline uint64_t chunk_bytes_of(const blu_ctx* c, uint64_t dflt) { return c->opts.chunk_bytes ? ((c->opts.chunk_bytes + 127) & ~127ull) : dflt; }
 
-void run_host_chunks(blu_ctx* c, ChunkSource& src, uint64_t n, const uint64_t chunk, blu_result* r) {
+// `host_text` != nullptr: BLU_OPT_TEXT_REFS -- the result's strings stay references into that (caller-owned) text.
+void run_host_chunks(blu_ctx* c, ChunkSource& src, uint64_t n, const uint64_t chunk, ResultPartOwned* r, RunStatus& st, const char* host_text) {
     require_ready(c);
     if (n == 0) throw DataErr("empty blast output (the reference's CsvReader fails on an empty file)");
     c->tm = blu_timings{};
@@ -1041,19 +1102,18 @@ void run_host_chunks(blu_ctx* c, ChunkSource& src, uint64_t n, const uint64_t ch
     const uint64_t text_off = single ? 0 : carry;  // where H2D data lands inside a buffer
     c->d_text[0].ensure(buf_bytes);
     if (!single) c->d_text[1].ensure(buf_bytes);
-    Caps k = initial_caps(n);
+    const Strings strings = host_text ? Strings::HostText : Strings::Pool;
     cudaStream_t s = c->stream, cs = c->copy_stream;
     Downloader dl(c, r);
     auto t0 = std::chrono::steady_clock::now();
+    Caps k{};
+    bool have_caps = false;
     for (int attempt = 0; attempt < 8; attempt++) {
-        ensure_out(c, k);
-        reset_counters_async(c, s, true);
         bool retry = false;
-        uint64_t tail_len = 0;           // bytes carried from the previous chunk
-        uint32_t rec_done = 0;           // records already gathered
-        uint64_t defer_total = 0;
-        double ms_tile = 0, ms_long = 0, ms_gather = 0;
+        uint64_t tail_len = 0;  // bytes carried from the previous chunk
+        double ms_tile = 0, ms_long = 0, ms_post = 0;
         uint64_t launches = 0;
+        Counters h{};
         auto issue_h2d = [&](uint64_t ci) {
             const uint64_t off = ci * chunk, len = std::min(chunk, n - off);
             CK(cudaMemcpyAsync(c->d_text[ci & 1].p + text_off, src.acquire(ci), len, cudaMemcpyHostToDevice, cs));
@@ -1061,9 +1121,20 @@ void run_host_chunks(blu_ctx* c, ChunkSource& src, uint64_t n, const uint64_t ch
             c->tm.h2d_bytes += len;
         };
         issue_h2d(0);
+        if (!have_caps) {
+            // a table this context has not seen the like of: the first chunk's first megabytes tell how dense its output is
+            if (c->dens_rec == 0 && n > (64ull << 20)) {
+                CK(cudaStreamWaitEvent(s, c->ev_h2d[0], 0));
+                probe_densities(c, c->d_text[0].p, text_off, text_off + std::min<uint64_t>(std::min(chunk, n), 32ull << 20), s);
+            }
+            k = initial_caps(c, n, strings == Strings::Pool);
+            have_caps = true;
+        }
+        begin_run(c, k, s);
         for (uint64_t ci = 0; ci < n_chunks && !retry; ci++) {
             const uint64_t off = ci * chunk, len = std::min(chunk, n - off);
             const bool final_chunk = ci + 1 == n_chunks;
+            const int slot = (int)(ci % kMaxRanges);
             uint8_t* buf = c->d_text[ci & 1].p;
             CK(cudaStreamWaitEvent(s, c->ev_h2d[ci & 1], 0));
             if (tail_len) {
@@ -1073,53 +1144,39 @@ void run_host_chunks(blu_ctx* c, ChunkSource& src, uint64_t n, const uint64_t ch
                 CK(cudaMemcpyAsync(buf + text_off - tail_len, prev + prev_end - tail_len, tail_len, cudaMemcpyDeviceToDevice, s));
             }
             CK(cudaEventRecord(c->ev_free[(ci + 1) & 1], s));  // previous buffer no longer read after this point
-            if (ci) reset_counters_async(c, s, false);
             const uint64_t begin = text_off - tail_len, end = text_off + len;
-            launch_chunk(c, buf, begin, end, final_chunk, k, s, rec_done, true);
+            // buffer offset d of this chunk is byte off + d - text_off of the caller's text
+            launch_range(c, buf, begin, end, final_chunk, k, s, slot, strings, (long long)off - (long long)text_off);
             if (!final_chunk) {  // behind the launches: a file source may block here until the next chunk has been read
                 CK(cudaStreamWaitEvent(cs, c->ev_free[(ci + 1) & 1], 0));
                 issue_h2d(ci + 1);
             }
-            read_counters(c, s);
+            CK(cudaEventSynchronize(c->ev[slot][3]));
             src.release(ci);  // `s` waited for this chunk's copy, so it has completed
-            Counters h = *c->h_ctr;
-            ms_tile += ev_ms(c->ev[0], c->ev[1]);
-            ms_long += ev_ms(c->ev[1], c->ev[2]);
-            defer_total = std::max<uint64_t>(defer_total, h.n_defer);
-            if (h.cap_overflow || n_rec_of(h) > k.rec || n_slots_of(h) > k.slots || h.n_defer > k.defer) {
-                grow_caps(h, k, h.n_defer, (double)n / (double)(off + len), n);
+            h = c->h_snap[slot];
+            ms_tile += ev_ms(c->ev[slot][0], c->ev[slot][1]);
+            ms_long += ev_ms(c->ev[slot][1], c->ev[slot][2]);
+            ms_post += ev_ms(c->ev[slot][2], c->ev[slot][3]);
+            c->tm.n_deferred_runs += h.n_defer;
+            launches++;
+            if (overflowed(h, k)) {
+                grow_caps(h, k, (double)n / (double)(off + len), n);
                 retry = true;
                 break;
             }
-            check_device_error(c, h, off - text_off);  // err_off is in buffer coordinates
-            CK(cudaEventRecord(c->ev[3], s));
-            launch_gather(c, buf, end, rec_done, n_rec_of(h), k, s);
-            CK(cudaEventRecord(c->ev[4], s));
-            rec_done = n_rec_of(h);
+            check_fatal(h, off - text_off);  // err_off is in buffer coordinates
+            st.note_soft(h, off - text_off);
             if (!final_chunk) {
-                if (h.tail_start == ~0ull)
-                    tail_len = 0;
-                else {
-                    tail_len = end - h.tail_start;
-                    if (tail_len > carry) throw UnsupportedErr("a single query spans more than the 64 MiB carry buffer between streamed chunks");
+                tail_len = end - h.next_begin;  // (next_begin == end: nothing is carried)
+                if (tail_len > carry) throw UnsupportedErr("a single query spans more than the 64 MiB carry buffer between streamed chunks");
+                if (!h.dup_found) {
+                    if (ci == 0) {
+                        const double f = 1.15 * (double)n / (double)len;
+                        dl.reserve((uint64_t)(h.post_done * f) + 4096, (uint64_t)(h.bean_used * f) + 8192, (uint64_t)(h.acc_used * f) + 8192,
+                                   strings == Strings::Pool ? (uint64_t)(h.pool_used * f) + 65536 : 0);
+                    }
+                    dl.push(h);  // result download of this chunk runs beside the next chunks' host->device copies
                 }
-            }
-            read_counters(c, s);  // (also: gather must finish before this buffer is overwritten two chunks later)
-            ms_gather += ev_ms(c->ev[3], c->ev[4]);
-            c->tm.n_deferred_runs += h.n_defer;
-            launches++;
-            if (!final_chunk) {
-                const Counters hg = *c->h_ctr;
-                if (hg.cap_overflow || hg.pool_used > k.pool) {
-                    grow_caps(hg, k, defer_total, (double)n / (double)(off + len), n);
-                    retry = true;
-                    break;
-                }
-                if (ci == 0) {
-                    const double f = 1.15 * (double)n / (double)len;
-                    dl.reserve((uint64_t)(n_rec_of(hg) * f) + 4096, (uint64_t)(n_slots_of(hg) * f) + 8192, (uint64_t)(hg.pool_used * f) + 65536);
-                }
-                dl.push(hg);  // result download of this chunk runs beside the next chunks' host->device copies
             }
         }
         if (retry) {
@@ -1128,41 +1185,34 @@ void run_host_chunks(blu_ctx* c, ChunkSource& src, uint64_t n, const uint64_t ch
             dl.abandon();
             src.restart();
             c->tm = blu_timings{};
+            st = RunStatus{};
             continue;
         }
-        launch_dup(c, rec_done, s);
-        read_counters(c, s);
-        Counters h = *c->h_ctr;
-        if (h.cap_overflow || h.pool_used > k.pool) {
-            grow_caps(h, k, defer_total, 1.0, n);
+        st.dup_found = h.dup_found != 0;
+        if (st.dup_found) {
             dl.abandon();
-            src.restart();
-            c->tm = blu_timings{};
-            continue;
+            return;
         }
-        check_device_error(c, h, 0);
-        if (h.dup_found) {
-            dl.abandon();
-            throw NonContiguous("a query id occurs in two non-adjacent groups of rows");
-        }
-        if (n_rec_of(h) == 0) throw DataErr("the blast output holds no rows");
+        if (h.post_done == 0) throw DataErr("the blast output holds no rows");
         c->tm.ms_tile_kernel = ms_tile;
         c->tm.ms_longrun_kernel = ms_long;
-        c->tm.ms_gather_kernel = ms_gather;
+        c->tm.ms_gather_kernel = ms_post;
         c->tm.text_bytes = n;
         c->tm.taxonomy_bytes = c->tax->device_bytes();
         c->tm.n_tile_launches = launches;
         dl.finish(h);
+        if (host_text) r->ext_strings = host_text, r->ext_len = n;
         c->tm.ms_total_device = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        learn_densities(c, h, n);
         return;
     }
     throw std::runtime_error("output capacity did not converge");
 }
 
 // On any failure nothing may still be reading the caller's text (or a staging buffer) when the call returns.
-void run_host_source(blu_ctx* c, ChunkSource& src, uint64_t n, uint64_t chunk, blu_result* r) {
+void run_host_source(blu_ctx* c, ChunkSource& src, uint64_t n, uint64_t chunk, ResultPartOwned* r, RunStatus& st, const char* host_text) {
     try {
-        run_host_chunks(c, src, n, chunk, r);
+        run_host_chunks(c, src, n, chunk, r, st, host_text);
     } catch (...) {
         cudaStreamSynchronize(c->copy_stream);
         cudaStreamSynchronize(c->stream);
@@ -1171,10 +1221,251 @@ void run_host_source(blu_ctx* c, ChunkSource& src, uint64_t n, uint64_t chunk, b
     }
 }
 
-void run_host(blu_ctx* c, const char* text, uint64_t n, blu_result* r) {
+void run_host_single(blu_ctx* c, const char* text, uint64_t n, ResultPartOwned* r, RunStatus& st, bool text_refs) {
     const uint64_t chunk = chunk_bytes_of(c, 256ull << 20);
     MemorySource src(text, chunk);
-    run_host_source(c, src, n, chunk, r);
+    run_host_source(c, src, n, chunk, r, st, text_refs ? text : nullptr);
+}
+
+// ---- sharding ---------------------------------------------------------------------------------------
+// Byte access to a table that is either in memory or a file (read through a small window cache): the cut search only
+// ever looks at a few rows around each cut.
+struct ByteView {
+    const char* mem = nullptr;
+    int fd = -1;
+    uint64_t n = 0;
+    mutable std::vector<char> win;
+    mutable uint64_t win_lo = 0, win_hi = 0;
+    char at(uint64_t i) const {
+        if (mem) return mem[i];
+        if (i < win_lo || i >= win_hi) {
+            const uint64_t lo = i & ~((1ull << 16) - 1);
+            const uint64_t len = std::min<uint64_t>(1ull << 20, n - lo);
+            win.resize((size_t)len);
+            uint64_t got_total = 0;
+            while (got_total < len) {
+                ssize_t got = pread(fd, win.data() + got_total, (size_t)(len - got_total), (off_t)(lo + got_total));
+                if (got < 0 && errno == EINTR) continue;
+                if (got <= 0) throw IoErr("Unexpected error occurred on load table.");
+                got_total += (uint64_t)got;
+            }
+            win_lo = lo, win_hi = lo + len;
+        }
+        return win[(size_t)(i - win_lo)];
+    }
+};
+
+// cuts[0..n_shards]: ranges of roughly equal size that never split a query (every cut moves forward to the next query
+// boundary).  Valid for contiguous tables; a scattered table is caught by the duplicate-id check afterwards.
+void shard_cuts(const ByteView& v, int n_shards, uint64_t* cuts) {
+    const uint64_t n = v.n;
+    auto row_end = [&](uint64_t p) {  // position of the newline that ends the row containing p, or n
+        while (p < n && v.at(p) != '\n') p++;
+        return p;
+    };
+    auto next_row = [&](uint64_t p) {  // start of the next non-empty row after the row containing p
+        uint64_t q = row_end(p);
+        while (q < n && v.at(q) == '\n') q++;
+        return q;
+    };
+    auto same_first_field = [&](uint64_t a, uint64_t b) {
+        for (uint64_t i = 0;; i++) {
+            const bool ea = a + i >= n || v.at(a + i) == '\t' || v.at(a + i) == '\n';
+            const bool eb = b + i >= n || v.at(b + i) == '\t' || v.at(b + i) == '\n';
+            if (ea || eb) return ea && eb;
+            if (v.at(a + i) != v.at(b + i)) return false;
+        }
+    };
+    cuts[0] = 0;
+    cuts[n_shards] = n;
+    for (int k = 1; k < n_shards; k++) {
+        uint64_t p = std::max<uint64_t>(cuts[k - 1], n / (uint64_t)n_shards * (uint64_t)k);
+        if (p >= n) {
+            cuts[k] = n;
+            continue;
+        }
+        // first row start at/after p
+        if (p > 0 && v.at(p - 1) != '\n') p = next_row(p);
+        while (p < n && v.at(p) == '\n') p++;
+        if (p >= n) {
+            cuts[k] = n;
+            continue;
+        }
+        // previous non-empty row
+        if (p > 0) {
+            uint64_t q = p - 1;
+            while (q > 0 && v.at(q) == '\n') q--;
+            if (v.at(q) != '\n') {
+                uint64_t st = q;
+                while (st > 0 && v.at(st - 1) != '\n') st--;
+                while (p < n && same_first_field(st, p)) p = next_row(p);  // never split a query
+            }
+        }
+        cuts[k] = p;
+    }
+}
+
+// ---- one table over several GPUs ---------------------------------------------------------------------------------------
+// Cross-shard duplicate-id check: the 64-bit id hashes every shard's duplicate kernel left behind are copied to the first
+// device and inserted into one table there (8 bytes per query; the only data that ever moves between the GPUs).
+bool merged_duplicate_check(blu_ctx* c, const std::vector<uint64_t>& n_rec) {
+    uint64_t total = 0;
+    for (uint64_t v : n_rec) total += v;
+    if (total == 0) return false;
+    blu_ctx* c0 = c->shards[0].get();
+    CK(cudaSetDevice(c0->device));
+    DevBuf<unsigned long long> all, table;
+    struct Cleanup {
+        DevBuf<unsigned long long>&a, &b;
+        ~Cleanup() { a.release(), b.release(); }
+    } cleanup{all, table};
+    all.ensure(total);
+    size_t cap = 1024;
+    while (cap < 2 * total) cap <<= 1;
+    table.ensure(cap + 1);  // (+1: the flag)
+    CK(cudaMemsetAsync(table.p, 0, (cap + 1) * sizeof(unsigned long long), c0->stream));
+    uint64_t at = 0;
+    for (size_t i = 0; i < c->shards.size(); i++) {
+        if (!n_rec[i]) continue;
+        CK(cudaMemcpyPeerAsync(all.p + at, c0->device, c->shards[i]->d_qhash.p, c->shards[i]->device, n_rec[i] * sizeof(unsigned long long), c0->stream));
+        at += n_rec[i];
+    }
+    unsigned int* flag = reinterpret_cast<unsigned int*>(table.p + cap);
+    CK(launch_dup_merge_kernel(all.p, total, table.p, (uint32_t)(cap - 1), flag, c0->sms, c0->stream));
+    unsigned int found = 0;
+    CK(cudaMemcpyAsync(&found, flag, sizeof found, cudaMemcpyDeviceToHost, c0->stream));
+    CK(cudaStreamSynchronize(c0->stream));
+    return found != 0;
+}
+
+// Runs `work(i)` for every shard on its own host thread (each binds its GPU), rethrows the first failure in shard order.
+template <class F>
+void for_each_shard(blu_ctx* c, F&& work) {
+    const size_t N = c->shards.size();
+    std::vector<std::exception_ptr> errs(N);
+    std::vector<std::thread> th;
+    for (size_t i = 0; i < N; i++)
+        th.emplace_back([&, i] {
+            try {
+                if (cudaSetDevice(c->shards[i]->device) != cudaSuccess) throw CudaErr("cudaSetDevice failed");
+                work(i);
+            } catch (...) {
+                errs[i] = std::current_exception();
+            }
+        });
+    for (auto& t : th) t.join();
+    for (auto& e : errs)
+        if (e) std::rethrow_exception(e);
+}
+
+void aggregate_timings(blu_ctx* c, uint64_t n, double wall_ms) {
+    blu_timings t{};
+    for (auto& sh : c->shards) {
+        const blu_timings& u = sh->tm;
+        t.ms_tile_kernel = std::max(t.ms_tile_kernel, u.ms_tile_kernel);
+        t.ms_longrun_kernel = std::max(t.ms_longrun_kernel, u.ms_longrun_kernel);
+        t.ms_gather_kernel = std::max(t.ms_gather_kernel, u.ms_gather_kernel);
+        t.result_bytes += u.result_bytes;
+        t.taxonomy_bytes += u.taxonomy_bytes;
+        t.h2d_bytes += u.h2d_bytes, t.d2h_bytes += u.d2h_bytes;
+        t.n_queries += u.n_queries, t.n_rows += u.n_rows, t.n_deferred_runs += u.n_deferred_runs;
+        t.n_kernel_launches += u.n_kernel_launches;
+        t.n_tile_launches = std::max(t.n_tile_launches, u.n_tile_launches);
+    }
+    t.text_bytes = n;
+    t.ms_total_device = wall_ms;
+    c->tm = t;
+}
+
+// After all shards have run: the cross-shard duplicate check, then (for a contiguous table) the consensus-class errors.
+void settle_multi(blu_ctx* c, const std::vector<RunStatus>& st, const uint64_t* cuts, const std::vector<uint64_t>& n_rec) {
+    bool dup = false;
+    for (auto& s : st) dup |= s.dup_found;
+    if (!dup) dup = merged_duplicate_check(c, n_rec);
+    if (dup) throw NonContiguous("a query id occurs in two non-adjacent groups of rows");
+    for (size_t i = 0; i < st.size(); i++)
+        if (st[i].soft_code) throw_device_error(st[i].soft_code, cuts[i] + st[i].soft_off);
+}
+
+void run_host_multi(blu_ctx* c, const char* text, uint64_t n, blu_result* r, bool text_refs) {
+    if (n == 0) throw DataErr("empty blast output (the reference's CsvReader fails on an empty file)");
+    const size_t N = c->shards.size();
+    std::vector<uint64_t> cuts(N + 1);
+    ByteView v;
+    v.mem = text, v.n = n;
+    shard_cuts(v, (int)N, cuts.data());
+    r->parts.clear();
+    r->parts.resize(N);
+    std::vector<RunStatus> st(N);
+    auto t0 = std::chrono::steady_clock::now();
+    for_each_shard(c, [&](size_t i) {
+        c->shards[i]->tm = blu_timings{};
+        if (cuts[i + 1] > cuts[i]) run_host_single(c->shards[i].get(), text + cuts[i], cuts[i + 1] - cuts[i], &r->parts[i], st[i], text_refs);
+    });
+    std::vector<uint64_t> n_rec(N);
+    for (size_t i = 0; i < N; i++) n_rec[i] = st[i].dup_found ? 0 : r->parts[i].n_rec;
+    settle_multi(c, st, cuts.data(), n_rec);
+    aggregate_timings(c, n, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    r->n_rows = c->tm.n_rows;
+}
+
+void run_file_multi(blu_ctx* c, int fd, uint64_t n, blu_result* r) {
+    if (n == 0) throw DataErr("empty blast output (the reference's CsvReader fails on an empty file)");
+    const size_t N = c->shards.size();
+    std::vector<uint64_t> cuts(N + 1);
+    ByteView v;
+    v.fd = fd, v.n = n;
+    shard_cuts(v, (int)N, cuts.data());
+    r->parts.clear();
+    r->parts.resize(N);
+    std::vector<RunStatus> st(N);
+    auto t0 = std::chrono::steady_clock::now();
+    for_each_shard(c, [&](size_t i) {
+        blu_ctx* sh = c->shards[i].get();
+        sh->tm = blu_timings{};
+        const uint64_t len = cuts[i + 1] - cuts[i];
+        if (!len) return;
+        const uint64_t chunk = chunk_bytes_of(sh, 64ull << 20);
+        FileSource src(sh, fd, cuts[i], len, chunk, (int)N);
+        run_host_source(sh, src, len, chunk, &r->parts[i], st[i], nullptr);
+    });
+    std::vector<uint64_t> n_rec(N);
+    for (size_t i = 0; i < N; i++) n_rec[i] = st[i].dup_found ? 0 : r->parts[i].n_rec;
+    settle_multi(c, st, cuts.data(), n_rec);
+    aggregate_timings(c, n, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    r->n_rows = c->tm.n_rows;
+}
+
+std::unique_ptr<blu_result> new_result(blu_ctx* c) {
+    auto r = std::make_unique<blu_result>();
+    r->tax = c->is_multi() ? c->shards[0]->tax : c->tax;
+    r->cut = c->cut;
+    return r;
+}
+
+// the concatenation behind blu_result_records() & co. for a multi-part result
+void merge_parts(const blu_result* r) {
+    std::lock_guard<std::mutex> g(r->merge_mu);
+    if (r->merged) return;
+    uint64_t nr = 0, nb = 0, na = 0, np = 0;
+    for (auto& p : r->parts) nr += p.n_rec, nb += p.n_beans, na += p.n_accs, np += p.strings_len();
+    if (nb >= kIdxMax || na >= kIdxMax) throw UnsupportedErr("the concatenated result has more than 2^32 beans / accession references: read it part by part");
+    r->m_rec.reserve(nr), r->m_beans.reserve(nb), r->m_accs.reserve(na), r->m_pool.reserve(np);
+    for (auto& p : r->parts) {
+        const uint64_t b0 = r->m_beans.size(), a0 = r->m_accs.size(), s0 = r->m_pool.size();
+        const blu_record* rec = (const blu_record*)p.b_rec.p;
+        for (uint64_t i = 0; i < p.n_rec; i++) {
+            blu_record x = rec[i];
+            x.bean_base += (uint32_t)b0, x.acc_base += (uint32_t)a0, x.query_off += s0;
+            r->m_rec.push_back(x);
+        }
+        const blu_bean* bn = (const blu_bean*)p.b_beans.p;
+        r->m_beans.insert(r->m_beans.end(), bn, bn + p.n_beans);
+        const blu_acc* ac = (const blu_acc*)p.b_accs.p;
+        for (uint64_t i = 0; i < p.n_accs; i++) r->m_accs.push_back(blu_acc{ac[i].ref + (s0 << 16)});
+        if (p.strings_len()) r->m_pool.append(p.strings(), p.strings_len());
+    }
+    r->merged = true;
 }
 
 }  // namespace
@@ -1188,19 +1479,29 @@ int blu_abi_version(void) { return BLU_ABI_VERSION; }
 
 const char* blu_last_error(const blu_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
-int blu_ctx_create(const blu_opts* opts, blu_ctx** out) {
-    if (!opts || !out) return fail(nullptr, BLU_ERR_ARG, "null argument");
-    *out = nullptr;
+static int validate_opts(const blu_opts* opts) {
     if (opts->taxon < 0 || opts->taxon > 3) return fail(nullptr, BLU_ERR_ARG, "bad taxon");
     if (opts->strategy < 0 || opts->strategy > 1) return fail(nullptr, BLU_ERR_ARG, "bad strategy");
     if (opts->taxon == BLU_TAXON_CUSTOM && !opts->has_custom)
         return fail(nullptr, BLU_ERR_DATA, "Custom taxon values are required when the custom taxon option is selected.");
-    auto c = std::make_unique<blu_ctx>();
+    return BLU_OK;
+}
+
+static void fill_cutoffs(blu_ctx* c, const blu_opts* opts) {
     c->opts = *opts;
     c->cut.taxon = opts->taxon;
     c->cut.has_custom = opts->has_custom != 0;
     for (int i = 0; i < 8; i++) c->cut.custom[i] = opts->custom[i];
+}
+
+int blu_ctx_create(const blu_opts* opts, blu_ctx** out) {
+    if (!opts || !out) return fail(nullptr, BLU_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (int rc = validate_opts(opts)) return rc;
+    auto c = std::make_unique<blu_ctx>();
+    fill_cutoffs(c.get(), opts);
     c->device = opts->device;
+    c->dev_pool->device = opts->device;
     int rc = guarded(nullptr, [&] {
         make_backbone(c->cut);  // validates the custom values
         int n = 0;
@@ -1215,11 +1516,14 @@ int blu_ctx_create(const blu_opts* opts, blu_ctx** out) {
         CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
-        for (auto& e2 : c->ev) CK(cudaEventCreate(&e2));
+        for (auto& row : c->ev)
+            for (auto& e2 : row) CK(cudaEventCreate(&e2));
         for (auto& e2 : c->ev_h2d) CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
         for (auto& e2 : c->ev_free) CK(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
         CK(cudaMalloc((void**)&c->d_ctr, sizeof(Counters)));
-        CK(cudaHostAlloc((void**)&c->h_ctr, 2 * sizeof(Counters), cudaHostAllocDefault));  // [0]: read_counters, [1]: post-pass snapshot
+        // counter snapshots: written by advance_kernel straight into (mapped) host memory
+        CK(cudaHostAlloc((void**)&c->h_snap, kMaxRanges * sizeof(Counters), cudaHostAllocMapped | cudaHostAllocPortable));
+        CK(cudaHostGetDevicePointer((void**)&c->d_snap, c->h_snap, 0));
         CK(kernels_set_attributes());
     });
     if (rc != BLU_OK) {
@@ -1232,21 +1536,60 @@ int blu_ctx_create(const blu_opts* opts, blu_ctx** out) {
     return BLU_OK;
 }
 
+int blu_ctx_create_multi(const blu_opts* opts, const int* devices, int n_devices, blu_ctx** out) {
+    if (!opts || !out || !devices || n_devices < 1 || n_devices > 64) return fail(nullptr, BLU_ERR_ARG, "bad argument");
+    *out = nullptr;
+    if (int rc = validate_opts(opts)) return rc;
+    for (int i = 0; i < n_devices; i++)
+        for (int j = 0; j < i; j++)
+            if (devices[i] == devices[j]) return fail(nullptr, BLU_ERR_ARG, "a device is listed twice");
+    auto c = std::make_unique<blu_ctx>();
+    fill_cutoffs(c.get(), opts);
+    c->device = devices[0];
+    for (int i = 0; i < n_devices; i++) {
+        blu_opts o = *opts;
+        o.device = devices[i];
+        blu_ctx* sh = nullptr;
+        int rc = blu_ctx_create(&o, &sh);
+        if (rc != BLU_OK) {
+            std::string msg = g_create_error;
+            blu_ctx_destroy(c.release());
+            g_create_error = msg;
+            return rc;
+        }
+        sh->keep_hashes = true;
+        c->shards.emplace_back(sh);
+    }
+    *out = c.release();
+    return BLU_OK;
+}
+
+int blu_ctx_num_devices(const blu_ctx* c) { return !c ? 0 : (c->is_multi() ? (int)c->shards.size() : 1); }
+
 void blu_ctx_destroy(blu_ctx* c) {
     if (!c) return;
+    if (c->is_multi()) {
+        for (auto& sh : c->shards) blu_ctx_destroy(sh.release());
+        delete c;
+        return;
+    }
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
     if (c->d2h_stream) cudaStreamSynchronize(c->d2h_stream);
     c->d_lin_off.release(), c->d_lvl.release(), c->d_bean.release(), c->d_irank.release(), c->d_cut.release();
     c->d_rcls.release(), c->d_acls.release(), c->d_linok.release(), c->d_slots.release();
-    c->d_text[0].release(), c->d_text[1].release(), c->d_rec.release(), c->d_beans.release(), c->d_accs.release();
-    c->d_defer.release(), c->d_pool.release(), c->d_dup.release(), c->d_top.release();
+    c->d_text[0].release(), c->d_text[1].release();
+    if (c->out) c->out->release();
+    c->dev_pool->close();
+    c->d_defer.release(), c->d_pool.release(), c->d_dup.release(), c->d_top.release(), c->d_qhash.release();
+    c->d_big_rows.release(), c->d_big_cand.release();
     if (c->d_ctr) cudaFree(c->d_ctr);
-    if (c->h_ctr) cudaFreeHost(c->h_ctr);
+    if (c->h_snap) cudaFreeHost(c->h_snap);
     c->pool->close();
-    for (auto& e : c->ev)
-        if (e) cudaEventDestroy(e);
+    for (auto& row : c->ev)
+        for (auto& e : row)
+            if (e) cudaEventDestroy(e);
     for (auto& e : c->ev_h2d)
         if (e) cudaEventDestroy(e);
     for (auto& e : c->ev_free)
@@ -1271,15 +1614,26 @@ int blu_custom_cutoffs_from_file(const char* path, blu_opts* opts, char* err, si
     }
 }
 
+// the encoded lineage tables go to every GPU of the context (replicated: SURVEY 8e)
+static void install_taxonomy(blu_ctx* c, const std::shared_ptr<HostTaxonomy>& T) {
+    if (!c->is_multi()) {
+        CK(cudaSetDevice(c->device));
+        c->tax = T;
+        upload_taxonomy(c);
+        c->dens_rec = 0;  // (a different taxonomy usually comes with a different kind of table)
+        return;
+    }
+    c->tax = T;
+    for (auto& sh : c->shards) install_taxonomy(sh.get(), T);
+}
+
 int blu_taxonomy_load_arrays(blu_ctx* c, const int64_t* taxids, const uint64_t* off, const char* blob, uint64_t n) {
     if (!c || (n && (!taxids || !off || !blob))) return fail(c, BLU_ERR_ARG, "null argument");
     return guarded(c, [&] {
-        CK(cudaSetDevice(c->device));
         auto T = std::make_shared<HostTaxonomy>();
         static const uint64_t zero = 0;
         build_taxonomy(taxids, n ? off : &zero, blob, n, c->cut, *T);
-        c->tax = T;
-        upload_taxonomy(c);
+        install_taxonomy(c, T);
     });
 }
 
@@ -1298,7 +1652,6 @@ int blu_taxonomy_load_json_cached(blu_ctx* c, const char* path, const char* cach
     if (cache_state) *cache_state = 0;
     const std::string cpath = cache_path ? std::string(cache_path) : std::string(path) + ".blucache";
     return guarded(c, [&] {
-        CK(cudaSetDevice(c->device));
         const TaxCacheKey key = make_cache_key(path, c->opts.use_taxid != 0, c->cut);  // IoErr if the JSON is unreadable
         auto T = std::make_shared<HostTaxonomy>();
         int state = 1;
@@ -1316,31 +1669,76 @@ int blu_taxonomy_load_json_cached(blu_ctx* c, const char* path, const char* cach
                 state = -1;
             }
         }
-        c->tax = T;
-        upload_taxonomy(c);
+        install_taxonomy(c, T);
         if (cache_state) *cache_state = state;
     });
+}
+
+static void require_tax(blu_ctx* c) {
+    if (!c->tax) throw std::invalid_argument("no taxonomy loaded (call blu_taxonomy_load_json first)");
+}
+
+// host text -> result, on one or several GPUs; a scattered table is regrouped (data movement only) and run again
+static void run_host_any(blu_ctx* c, const char* text, uint64_t n, blu_result* r) {
+    const bool refs = (c->opts.flags & BLU_OPT_TEXT_REFS) != 0;
+    auto once = [&](const char* t, uint64_t len, bool text_refs) {
+        for (auto& p : r->parts) p.free_buffers();
+        r->parts.clear();
+        if (c->is_multi()) {
+            run_host_multi(c, t, len, r, text_refs);
+        } else {
+            CK(cudaSetDevice(c->device));
+            r->parts.resize(1);
+            RunStatus st;
+            run_host_single(c, t, len, &r->parts[0], st, text_refs);
+            settle(st);
+            r->n_rows = c->tm.n_rows;
+        }
+    };
+    try {
+        once(text, n, refs);
+    } catch (const NonContiguous&) {
+        const std::string re = regroup_by_query(text, n);
+        once(re.data(), re.size(), false);  // (the regrouped text is ours: its strings are copied into a pool)
+        c->tm.n_regrouped = 1;
+    }
 }
 
 int blu_consensus_run_device(blu_ctx* c, const void* dtext, uint64_t n, void* stream, blu_result** out) {
     if (!c || !out || (!dtext && n)) return fail(c, BLU_ERR_ARG, "null argument");
     *out = nullptr;
-    auto r = std::make_unique<blu_result>();
-    r->pinned = c->pool;
+    if (c->is_multi()) return fail(c, BLU_ERR_ARG, "device-resident text belongs to one GPU: use a single-device context");
+    std::unique_ptr<blu_result> r;
     int rc = guarded(c, [&] {
+        require_tax(c);
+        r = new_result(c);
         CK(cudaSetDevice(c->device));
-        r->tax = c->tax;
-        r->cut = c->cut;
+        cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
         try {
-            run_device(c, (const uint8_t*)dtext, n, stream ? (cudaStream_t)stream : c->stream, r.get());
+            r->parts.resize(1);
+            RunStatus st;
+            try {
+                run_device_download(c, (const uint8_t*)dtext, n, s, &r->parts[0], st);
+            } catch (...) {  // nothing may still be reading the caller's device text when the call returns
+                cudaStreamSynchronize(s);
+                cudaStreamSynchronize(c->d2h_stream);
+                throw;
+            }
+            settle(st);
+            r->n_rows = c->tm.n_rows;
         } catch (const NonContiguous&) {
             // regroup on the host (data movement only), then the normal streamed path
             std::string host(n, '\0');
             CK(cudaMemcpy(host.data(), dtext, n, cudaMemcpyDeviceToHost));
             std::string re = regroup_by_query(host.data(), n);
-            host.clear();
-            host.shrink_to_fit();
-            run_host(c, re.data(), re.size(), r.get());
+            std::string().swap(host);
+            for (auto& p : r->parts) p.free_buffers();
+            r->parts.clear();
+            r->parts.resize(1);
+            RunStatus st;
+            run_host_single(c, re.data(), re.size(), &r->parts[0], st, false);
+            settle(st);
+            r->n_rows = c->tm.n_rows;
             c->tm.n_regrouped = 1;
         }
     });
@@ -1352,22 +1750,72 @@ int blu_consensus_run_device(blu_ctx* c, const void* dtext, uint64_t n, void* st
     return BLU_OK;
 }
 
+int blu_consensus_run_device_resident(blu_ctx* c, const void* dtext, uint64_t n, void* stream, blu_result** out) {
+    if (!c || !out || (!dtext && n)) return fail(c, BLU_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (c->is_multi()) return fail(c, BLU_ERR_ARG, "device-resident text belongs to one GPU: use a single-device context");
+    std::unique_ptr<blu_result> r;
+    int rc = guarded(c, [&] {
+        require_tax(c);
+        r = new_result(c);
+        CK(cudaSetDevice(c->device));
+        cudaStream_t s = stream ? (cudaStream_t)stream : c->stream;
+        r->parts.resize(1);
+        RunStatus st;
+        try {
+            run_device_resident(c, (const uint8_t*)dtext, n, s, &r->parts[0], st);
+        } catch (...) {
+            cudaStreamSynchronize(s);
+            throw;
+        }
+        // a scattered table cannot stay device-resident (regrouping is host-side data movement): say so instead of guessing
+        if (st.dup_found)
+            throw UnsupportedErr("the table's queries are not contiguous: use blu_consensus_run_device / _host / _file, which regroup it");
+        settle(st);
+        r->n_rows = c->tm.n_rows;
+    });
+    if (rc != BLU_OK) {
+        blu_result_free(r.release());
+        return rc;
+    }
+    *out = r.release();
+    return BLU_OK;
+}
+
+const blu_record* blu_result_device_records(const blu_result* r) {
+    return (r && r->parts.size() == 1 && r->parts[0].dev) ? r->parts[0].dev->rec.p : nullptr;
+}
+const blu_bean* blu_result_device_beans(const blu_result* r, uint64_t* n) {
+    const bool ok = r && r->parts.size() == 1 && r->parts[0].dev;
+    if (n) *n = ok ? r->parts[0].n_beans : 0;
+    return ok ? r->parts[0].dev->beans.p : nullptr;
+}
+const blu_acc* blu_result_device_accessions(const blu_result* r, uint64_t* n) {
+    const bool ok = r && r->parts.size() == 1 && r->parts[0].dev;
+    if (n) *n = ok ? r->parts[0].n_accs : 0;
+    return ok ? r->parts[0].dev->accs.p : nullptr;
+}
+
+int blu_result_download(blu_result* r) {
+    if (!r) return BLU_ERR_ARG;
+    try {
+        for (auto& p : r->parts) download_part(&p);
+        return BLU_OK;
+    } catch (const CudaErr&) {
+        return BLU_ERR_CUDA;
+    } catch (const std::exception&) {
+        return BLU_ERR_INTERNAL;
+    }
+}
+
 int blu_consensus_run_host(blu_ctx* c, const char* text, uint64_t n, blu_result** out) {
     if (!c || !out || (!text && n)) return fail(c, BLU_ERR_ARG, "null argument");
     *out = nullptr;
-    auto r = std::make_unique<blu_result>();
-    r->pinned = c->pool;
+    std::unique_ptr<blu_result> r;
     int rc = guarded(c, [&] {
-        CK(cudaSetDevice(c->device));
-        r->tax = c->tax;
-        r->cut = c->cut;
-        try {
-            run_host(c, text, n, r.get());
-        } catch (const NonContiguous&) {
-            std::string re = regroup_by_query(text, n);
-            run_host(c, re.data(), re.size(), r.get());
-            c->tm.n_regrouped = 1;
-        }
+        require_tax(c);
+        r = new_result(c);
+        run_host_any(c, text, n, r.get());
     });
     if (rc != BLU_OK) {
         blu_result_free(r.release());
@@ -1391,19 +1839,25 @@ int blu_consensus_run_file(blu_ctx* c, const char* path, blu_result** out) {
     if (f.fd < 0 || fstat(f.fd, &st) != 0 || !S_ISREG(st.st_mode))
         return fail(c, BLU_ERR_IO, "Unexpected error occurred on load table.");  // mod.rs:357-364
     const uint64_t n = (uint64_t)st.st_size;
-    auto r = std::make_unique<blu_result>();
-    r->pinned = c->pool;
+    std::unique_ptr<blu_result> r;
     bool regroup = false;
     int rc = guarded(c, [&] {
-        CK(cudaSetDevice(c->device));
-        r->tax = c->tax;
-        r->cut = c->cut;
-        require_ready(c);
+        require_tax(c);
+        r = new_result(c);
         if (n == 0) throw DataErr("empty blast output (the reference's CsvReader fails on an empty file)");
         try {
-            const uint64_t chunk = chunk_bytes_of(c, 64ull << 20);
-            FileSource src(c, f.fd, n, chunk);
-            run_host_source(c, src, n, chunk, r.get());
+            if (c->is_multi()) {
+                run_file_multi(c, f.fd, n, r.get());
+            } else {
+                CK(cudaSetDevice(c->device));
+                const uint64_t chunk = chunk_bytes_of(c, 64ull << 20);
+                FileSource src(c, f.fd, 0, n, chunk);
+                r->parts.resize(1);
+                RunStatus rs;
+                run_host_source(c, src, n, chunk, &r->parts[0], rs, nullptr);
+                settle(rs);
+                r->n_rows = c->tm.n_rows;
+            }
         } catch (const NonContiguous&) {
             regroup = true;
         }
@@ -1419,12 +1873,15 @@ int blu_consensus_run_file(blu_ctx* c, const char* path, blu_result** out) {
             }
             std::string re = regroup_by_query(all.data(), n);
             std::string().swap(all);
-            blu_result_free(r.release());  // whatever the streamed attempt had downloaded
-            r = std::make_unique<blu_result>();
-            r->pinned = c->pool;
-            r->tax = c->tax;
-            r->cut = c->cut;
-            run_host(c, re.data(), re.size(), r.get());
+            const uint64_t keep_flags = c->opts.flags;
+            c->opts.flags &= ~(uint64_t)BLU_OPT_TEXT_REFS;  // (the regrouped text is ours)
+            try {
+                run_host_any(c, re.data(), re.size(), r.get());
+            } catch (...) {
+                c->opts.flags = keep_flags;
+                throw;
+            }
+            c->opts.flags = keep_flags;
             c->tm.n_regrouped = 1;
         });
     }
@@ -1437,10 +1894,13 @@ int blu_consensus_run_file(blu_ctx* c, const char* path, blu_result** out) {
 }
 
 int blu_result_add_headers(blu_result* r, const char* headers_nl, uint64_t len) {
-    if (!r) return BLU_ERR_ARG;
+    if (!r || !r->on_host()) return BLU_ERR_ARG;
     std::unordered_set<std::string_view> have;
-    have.reserve(r->n_rec * 2);
-    for (uint64_t i = 0; i < r->n_rec; i++) have.insert(std::string_view(r->pool() + r->rec()[i].query_off, r->rec()[i].query_len));
+    have.reserve(r->n_rec() * 2);
+    for (auto& p : r->parts) {
+        const blu_record* rec = (const blu_record*)p.b_rec.p;
+        for (uint64_t i = 0; i < p.n_rec; i++) have.insert(std::string_view(p.strings() + rec[i].query_off, rec[i].query_len));
+    }
     const char* p = headers_nl;
     const char* e = headers_nl + len;
     while (p < e) {
@@ -1453,24 +1913,63 @@ int blu_result_add_headers(blu_result* r, const char* headers_nl, uint64_t len) 
     return BLU_OK;
 }
 
-uint64_t blu_result_num_queries(const blu_result* r) { return r ? r->n_rec + r->hitless.size() : 0; }
+uint64_t blu_result_num_queries(const blu_result* r) { return r ? r->n_rec() + r->hitless.size() : 0; }
 uint64_t blu_result_num_rows(const blu_result* r) { return r ? r->n_rows : 0; }
-const blu_record* blu_result_records(const blu_result* r) { return r ? r->rec() : nullptr; }
-const blu_bean* blu_result_beans(const blu_result* r) { return r ? r->beans() : nullptr; }
-const blu_acc* blu_result_accessions(const blu_result* r) { return r ? r->accs() : nullptr; }
+uint64_t blu_result_num_beans(const blu_result* r) {
+    uint64_t n = 0;
+    if (r)
+        for (auto& p : r->parts) n += p.n_beans;
+    return n;
+}
+uint64_t blu_result_num_accessions(const blu_result* r) {
+    uint64_t n = 0;
+    if (r)
+        for (auto& p : r->parts) n += p.n_accs;
+    return n;
+}
+
+static bool host_arrays(const blu_result* r) {
+    if (!r || !r->on_host() || r->parts.empty()) return false;
+    if (r->parts.size() > 1) {
+        try {
+            merge_parts(r);
+        } catch (const std::exception&) {
+            return false;
+        }
+    }
+    return true;
+}
+const blu_record* blu_result_records(const blu_result* r) {
+    if (!host_arrays(r)) return nullptr;
+    return r->parts.size() == 1 ? (const blu_record*)r->parts[0].b_rec.p : r->m_rec.data();
+}
+const blu_bean* blu_result_beans(const blu_result* r) {
+    if (!host_arrays(r)) return nullptr;
+    return r->parts.size() == 1 ? (const blu_bean*)r->parts[0].b_beans.p : r->m_beans.data();
+}
+const blu_acc* blu_result_accessions(const blu_result* r) {
+    if (!host_arrays(r)) return nullptr;
+    return r->parts.size() == 1 ? (const blu_acc*)r->parts[0].b_accs.p : r->m_accs.data();
+}
 const char* blu_result_pool(const blu_result* r, uint64_t* len) {
-    if (len) *len = r ? r->pool_len : 0;
-    return r ? r->pool() : nullptr;
+    if (len) *len = 0;
+    if (!host_arrays(r)) return nullptr;
+    if (r->parts.size() == 1) {
+        if (len) *len = r->parts[0].strings_len();
+        return r->parts[0].strings();
+    }
+    if (len) *len = r->m_pool.size();
+    return r->m_pool.data();
 }
 
 uint64_t blu_result_checksum(const blu_result* r) {
-    if (!r) return 0;
+    if (!r || !r->on_host()) return 0;
     ResultView v = make_view(r);
     return view_checksum(&v);
 }
 
 int blu_result_to_jsonl(const blu_result* r, char** out, uint64_t* len) {
-    if (!r || !out || !len) return BLU_ERR_ARG;
+    if (!r || !out || !len || !r->on_host()) return BLU_ERR_ARG;
     try {
         ResultView v = make_view(r);
         std::string s = view_to_jsonl(&v);
@@ -1487,7 +1986,7 @@ int blu_result_to_jsonl(const blu_result* r, char** out, uint64_t* len) {
 }
 
 int blu_result_write(const blu_result* r, const char* path, int format, const char* run_id_in) {
-    if (!r || format < 0 || format > 2) return BLU_ERR_ARG;
+    if (!r || format < 0 || format > 2 || !r->on_host()) return BLU_ERR_ARG;
     try {
         ResultView v = make_view(r);
         return view_write(&v, path, format, run_id_in);
@@ -1497,7 +1996,7 @@ int blu_result_write(const blu_result* r, const char* path, int format, const ch
 }
 
 int blu_result_write_tabular(const blu_result* r, const char* path, const char* run_id) {
-    if (!r) return BLU_ERR_ARG;
+    if (!r || !r->on_host()) return BLU_ERR_ARG;
     try {
         ResultView v = make_view(r);
         return view_write_tabular(&v, path, run_id);
@@ -1521,12 +2020,7 @@ int blu_result_file_to_tabular(const char* in_path, const char* out_path, int in
 
 void blu_result_free(blu_result* r) {
     if (!r) return;
-    if (r->pinned) {
-        r->pinned->release(r->b_rec);
-        r->pinned->release(r->b_beans);
-        r->pinned->release(r->b_accs);
-        r->pinned->release(r->b_pool);
-    }
+    for (auto& p : r->parts) p.free_buffers();
     delete r;
 }
 
@@ -1538,8 +2032,9 @@ int blu_ctx_last_timings(const blu_ctx* c, blu_timings* out) {
     return BLU_OK;
 }
 
-int blu_ctx_measure_h2d(blu_ctx* c, uint64_t bytes, double* gbps) {
+static int measure_copy(blu_ctx* c, uint64_t bytes, double* gbps, bool to_device) {
     if (!c || !gbps || !bytes) return BLU_ERR_ARG;
+    if (c->is_multi()) c = c->shards[0].get();
     return guarded(c, [&] {
         CK(cudaSetDevice(c->device));
         void* h = nullptr;
@@ -1552,11 +2047,14 @@ int blu_ctx_measure_h2d(blu_ctx* c, uint64_t bytes, double* gbps) {
         memset(h, 1, bytes);
         double best = 0;
         for (int i = 0; i < 5; i++) {
-            cudaEventRecord(c->ev[0], c->stream);
-            cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream);
-            cudaEventRecord(c->ev[1], c->stream);
+            cudaEventRecord(c->ev[0][0], c->stream);
+            if (to_device)
+                cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream);
+            else
+                cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, c->stream);
+            cudaEventRecord(c->ev[0][1], c->stream);
             cudaStreamSynchronize(c->stream);
-            double ms = ev_ms(c->ev[0], c->ev[1]);
+            double ms = ev_ms(c->ev[0][0], c->ev[0][1]);
             if (ms > 0) best = std::max(best, bytes / ms / 1e6);
         }
         cudaFree(d);
@@ -1564,55 +2062,20 @@ int blu_ctx_measure_h2d(blu_ctx* c, uint64_t bytes, double* gbps) {
         *gbps = best;
     });
 }
+int blu_ctx_measure_h2d(blu_ctx* c, uint64_t bytes, double* gbps) { return measure_copy(c, bytes, gbps, true); }
+int blu_ctx_measure_d2h(blu_ctx* c, uint64_t bytes, double* gbps) { return measure_copy(c, bytes, gbps, false); }
 
 int blu_shard_cuts(const char* text, uint64_t n, int n_shards, uint64_t* cuts) {
     if (!cuts || n_shards < 1 || (!text && n)) return BLU_ERR_ARG;
-    auto first_field = [&](uint64_t p) {
-        const char* e = (const char*)memchr(text + p, '\n', n - p);
-        const uint64_t re = e ? (uint64_t)(e - text) : n;
-        const char* t = (const char*)memchr(text + p, '\t', re - p);
-        return std::string_view(text + p, t ? (size_t)(t - (text + p)) : (size_t)(re - p));
-    };
-    auto next_row = [&](uint64_t p) {  // start of the next non-empty row after the row containing p
-        const char* e = (const char*)memchr(text + p, '\n', n - p);
-        uint64_t q = e ? (uint64_t)(e - text) + 1 : n;
-        while (q < n && text[q] == '\n') q++;
-        return q;
-    };
-    cuts[0] = 0;
-    cuts[n_shards] = n;
-    for (int k = 1; k < n_shards; k++) {
-        uint64_t p = std::max<uint64_t>(cuts[k - 1], n / (uint64_t)n_shards * (uint64_t)k);
-        if (p >= n) {
-            cuts[k] = n;
-            continue;
-        }
-        // first row start at/after p
-        if (p > 0 && text[p - 1] != '\n') p = next_row(p);
-        while (p < n && text[p] == '\n') p++;
-        if (p >= n) {
-            cuts[k] = n;
-            continue;
-        }
-        // previous non-empty row
-        if (p > 0) {
-            uint64_t q = p - 1;
-            while (q > 0 && text[q] == '\n') q--;
-            if (text[q] != '\n') {
-                uint64_t st = q;
-                while (st > 0 && text[st - 1] != '\n') st--;
-                const std::string_view run = first_field(st);
-                while (p < n && first_field(p) == run) p = next_row(p);  // never split a query
-            }
-        }
-        cuts[k] = p;
-    }
+    ByteView v;
+    v.mem = text, v.n = n;
+    shard_cuts(v, n_shards, cuts);
     return BLU_OK;
 }
 
 void* blu_host_alloc(uint64_t bytes) {
     void* p = nullptr;
-    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) return nullptr;  // (portable: every GPU of a multi-device context copies from it)
     return p;
 }
 void blu_host_free(void* p) {

@@ -15,7 +15,7 @@ static void usage() {
             "Usage: blu [--log-level L] [--log-file F] [--log-format F] [-t|--threads N] blastn build-consensus <BLAST_OUT>\n"
             "           -t|--tax-file <FILE> --taxon <fungi|bacteria|eukaryotes|custom> --strategy <cautious|relaxed>\n"
             "           [-c|--custom-taxon-cutoff-file <FILE>] [-u|--use-taxid] [--blutils-out-file <FILE>]\n"
-            "           [--out-format <json|jsonl|yaml>] [--device N]\n"
+            "           [--out-format <json|jsonl|yaml>] [--device N | --devices N,M,...]\n"
             "       blu blastn build-tabular [BLU_RESULT|-] [-o|--output-file <FILE>] [-i|--input-format <json|jsonl>]\n");
 }
 
@@ -92,6 +92,7 @@ int main(int argc, char** argv) {
     std::string blast_out, tax_file, out_file, taxon, strategy, custom_file, fmt = "json";
     bool use_taxid = false, have_out = false;
     int device = 0;
+    std::vector<int> devices;  // --devices 0,1,...: the table is sharded by query range over these GPUs (one result)
     for (; i < a.size(); i++) {
         auto need = [&](const char* f) -> std::string {
             if (i + 1 >= a.size()) die(std::string("a value is required for '") + f + "'");
@@ -116,6 +117,16 @@ int main(int argc, char** argv) {
         }
         if (val("--taxon", taxon) || val("--strategy", strategy) || val("--out-format", fmt)) continue;
         if (val("--custom-taxon-cutoff-file", custom_file) || (a[i] == "-c" && (custom_file = need("-c"), true))) continue;
+        if (val("--devices", tmp)) {
+            for (size_t k = 0; k < tmp.size();) {
+                size_t e = tmp.find(',', k);
+                if (e == std::string::npos) e = tmp.size();
+                if (e > k) devices.push_back(atoi(tmp.substr(k, e - k).c_str()));
+                k = e + 1;
+            }
+            if (devices.empty()) die("--devices needs a comma-separated list of CUDA device ordinals");
+            continue;
+        }
         if (val("--device", tmp)) {
             device = atoi(tmp.c_str());
             continue;
@@ -178,7 +189,8 @@ int main(int argc, char** argv) {
     } else if (o.taxon == BLU_TAXON_CUSTOM)
         die("Custom taxon values are required when the custom taxon option is selected.");
     blu_ctx* ctx = nullptr;
-    if (blu_ctx_create(&o, &ctx) != BLU_OK) die(blu_last_error(nullptr));
+    if ((devices.empty() ? blu_ctx_create(&o, &ctx) : blu_ctx_create_multi(&o, devices.data(), (int)devices.size(), &ctx)) != BLU_OK)
+        die(blu_last_error(nullptr));
     // BLU_TAX_CACHE=1: binary side-car cache next to the taxonomy file; BLU_TAX_CACHE=<path>: that file.  An
     // environment variable, not a flag: the argument list stays the reference's (commands.rs:105-143).
     const char* tc = getenv("BLU_TAX_CACHE");

@@ -945,7 +945,8 @@ BLU_HD uint32_t heavy_parse_row_masked(const uint8_t* win, const uint64_t* tabw,
 }
 
 // ---- consensus --------------------------------------------------------------------------------------------------
-// Where the per-query output goes.  `beans`/`accs` point at this query's reserved slots (g of each).
+// Where the per-query output goes.  `beans`/`accs` point at this query's reserved entries (g of each; the caller has
+// stored their indices in rec->bean_base / rec->acc_base).
 struct QueryOut {
     blu_record* rec;
     blu_bean* beans;
@@ -1004,7 +1005,6 @@ BLU_HD uint32_t consensus_single(const TopRow& r, const LinTables& T, QueryOut o
     rec->perc_identity = r.pident;
     rec->ref_lineage = r.lin;
     rec->n_beans = 1;
-    rec->n_accessions = 1;
     rec->status = 1;
     rec->single_match = 1;
     rec->mutated = 0;
@@ -1015,9 +1015,7 @@ BLU_HD uint32_t consensus_single(const TopRow& r, const LinTables& T, QueryOut o
     out.beans[0].occurrences = 1;
     out.beans[0].acc_begin = 0;
     out.beans[0].n_acc = 1;
-    out.accs[0].off = r.acc_off;
-    out.accs[0].len = r.acc_len;
-    out.accs[0].pad = 0;
+    out.accs[0].ref = (r.acc_off << 16) | (uint64_t)r.acc_len;
     return DE_NONE;
 }
 
@@ -1169,9 +1167,7 @@ BLU_HD_NOINLINE uint32_t consensus_multi(const TopRow* rows, int g, const uint8_
                 const TopRow& q = rows[prev];
                 if (q.acc_len == r.acc_len && bytes_cmp(text + q.acc_off, q.acc_len, text + r.acc_off, r.acc_len) == 0) continue;
             }
-            out.accs[na].off = r.acc_off;
-            out.accs[na].len = r.acc_len;
-            out.accs[na].pad = 0;
+            out.accs[na].ref = (r.acc_off << 16) | (uint64_t)r.acc_len;
             na++;
             prev = order[s];
         }
@@ -1184,7 +1180,6 @@ BLU_HD_NOINLINE uint32_t consensus_multi(const TopRow* rows, int g, const uint8_
     rec->perc_identity = ref.pident;
     rec->ref_lineage = ref.lin;
     rec->n_beans = (uint32_t)nb;
-    rec->n_accessions = na;
     rec->status = 1;
     rec->single_match = 0;
     rec->bean_level = (int8_t)level;

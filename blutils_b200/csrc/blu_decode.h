@@ -19,26 +19,32 @@
 
 namespace blu {
 
-// Non-owning view of one result set.
+// One part of a result set: the records one GPU produced, with the arrays their indices refer to.
+struct ResultPart {
+    const blu_record* rec = nullptr;
+    const blu_bean* beans = nullptr;
+    const blu_acc* accs = nullptr;
+    const char* pool = nullptr;  // string base of this part: its string pool, or the text the references point into
+    uint64_t n_rec = 0;
+};
+
+// Non-owning view of one result set (a multi-device run has one part per GPU; nothing is concatenated to decode it).
 struct ResultView {
     const HostTaxonomy* tax = nullptr;
     Cutoffs cut;
-    const blu_record* rec_ = nullptr;
-    const blu_bean* beans_ = nullptr;
-    const blu_acc* accs_ = nullptr;
-    const char* pool_ = nullptr;
-    uint64_t n_rec = 0;
+    std::vector<ResultPart> parts;
     const std::vector<std::string>* hitless_ = nullptr;
-    const blu_record* rec() const { return rec_; }
-    const blu_bean* beans() const { return beans_; }
-    const blu_acc* accs() const { return accs_; }
-    const char* pool() const { return pool_; }
+    uint64_t n_rec() const {
+        uint64_t n = 0;
+        for (auto& p : parts) n += p.n_rec;
+        return n;
+    }
 };
 
 // ---------------------------------------------------------------------------------------------------------------
 // decoding: records -> the reference's JSON objects
 // ---------------------------------------------------------------------------------------------------------------
-inline std::string_view rec_query(const ResultView* r, const blu_record& rc) { return std::string_view(r->pool() + rc.query_off, rc.query_len); }
+inline std::string_view rec_query(const ResultPart& p, const blu_record& rc) { return std::string_view(p.pool + rc.query_off, rc.query_len); }
 
 // serde form of Option<LinnaeanRank> for max_allowed_rank (bbci.rs:22-30): DefaultRank -> the enum variant,
 // NonDefaultRank(name) -> Other(name) where name = rank.to_string()
@@ -63,7 +69,7 @@ struct Decoder {
         }
     }
     // `"taxon":{...}` object body (TaxonomyBean, taxonomy_bean.rs:5-17) in compact or pretty layout
-    void taxon(std::string& o, const blu_record& rc, bool pretty, int ind) const {
+    void taxon(std::string& o, const ResultPart& part, const blu_record& rc, bool pretty, int ind) const {
         const uint32_t lo = T.lin_off[rc.ref_lineage];
         auto nl = [&](int extra) {
             if (!pretty) return;
@@ -132,7 +138,7 @@ struct Decoder {
         o.push_back('[');
         std::string lineage;
         for (uint32_t b = 0; b < rc.n_beans; b++) {
-            const blu_bean& bn = r->beans()[rc.slot_base + b];
+            const blu_bean& bn = part.beans[rc.bean_base + b];
             const uint32_t bp = T.lin_off[bn.first_lineage] + rc.bean_level;
             if (b) o.push_back(',');
             nl(2);
@@ -164,10 +170,10 @@ struct Decoder {
             o += colon;
             o.push_back('[');
             for (uint32_t a = 0; a < bn.n_acc; a++) {
-                const blu_acc& ac = r->accs()[rc.slot_base + bn.acc_begin + a];
+                const blu_acc& ac = part.accs[rc.acc_base + bn.acc_begin + a];
                 if (a) o.push_back(',');
                 nl(4);
-                json_escape(o, std::string_view(r->pool() + ac.off, ac.len));
+                json_escape(o, std::string_view(part.pool + BLU_ACC_OFF(ac), BLU_ACC_LEN(ac)));
             }
             if (bn.n_acc) nl(3);
             o.push_back(']');
@@ -180,7 +186,7 @@ struct Decoder {
         o.push_back('}');
     }
     // one QueryWithConsensus object (consensus_result.rs:7-13); run_id empty -> field omitted (canonical form)
-    void object(std::string& o, std::string_view query, const blu_record* rc, const char* run_id, bool pretty, int ind) const {
+    void object(std::string& o, std::string_view query, const ResultPart* part, const blu_record* rc, const char* run_id, bool pretty, int ind) const {
         auto nl = [&](int extra) {
             if (!pretty) return;
             o.push_back('\n');
@@ -204,7 +210,7 @@ struct Decoder {
         o += "\"taxon\"";
         o += colon;
         if (rc)
-            taxon(o, *rc, pretty, ind + 1);
+            taxon(o, *part, *rc, pretty, ind + 1);
         else
             o += "null";
         nl(0);
@@ -215,15 +221,17 @@ struct Decoder {
 struct Entry {
     std::string_view query;
     const blu_record* rec;  // nullptr = NoConsensusFound
+    const ResultPart* part;
 };
 
 // write_blutils_output.rs:87-111: flatten + sort by query (bytewise)
 inline std::vector<Entry> sorted_entries(const ResultView* r) {
     std::vector<Entry> v;
-    v.reserve(r->n_rec + (r->hitless_ ? r->hitless_->size() : 0));
-    for (uint64_t i = 0; i < r->n_rec; i++) v.push_back({rec_query(r, r->rec()[i]), &r->rec()[i]});
+    v.reserve(r->n_rec() + (r->hitless_ ? r->hitless_->size() : 0));
+    for (auto& p : r->parts)
+        for (uint64_t i = 0; i < p.n_rec; i++) v.push_back({rec_query(p, p.rec[i]), &p.rec[i], &p});
     if (r->hitless_)
-        for (auto& h : *r->hitless_) v.push_back({std::string_view(h), nullptr});
+        for (auto& h : *r->hitless_) v.push_back({std::string_view(h), nullptr, nullptr});
     std::stable_sort(v.begin(), v.end(), [](const Entry& a, const Entry& b) { return a.query < b.query; });
     return v;
 }
@@ -334,22 +342,23 @@ inline uint64_t view_checksum(const ResultView* r) {
         }
         return h;
     };
-    parallel_ranges(r->n_rec, [&](unsigned, size_t a, size_t b) {
-        std::string line;
-        uint64_t sum = 0;
-        for (size_t i = a; i < b; i++) {
-            line.clear();
-            d.object(line, rec_query(r, r->rec()[i]), &r->rec()[i], nullptr, false, 0);
-            sum += fnv(line);
-        }
-        total += sum;
-    });
+    for (auto& p : r->parts)
+        parallel_ranges(p.n_rec, [&](unsigned, size_t a, size_t b) {
+            std::string line;
+            uint64_t sum = 0;
+            for (size_t i = a; i < b; i++) {
+                line.clear();
+                d.object(line, rec_query(p, p.rec[i]), &p, &p.rec[i], nullptr, false, 0);
+                sum += fnv(line);
+            }
+            total += sum;
+        });
     if (r->hitless_)
-    for (auto& h : *r->hitless_) {
-        std::string line;
-        d.object(line, h, nullptr, nullptr, false, 0);
-        total += fnv(line);
-    }
+        for (auto& h : *r->hitless_) {
+            std::string line;
+            d.object(line, h, nullptr, nullptr, nullptr, false, 0);
+            total += fnv(line);
+        }
     return total.load();
 }
 
@@ -361,7 +370,7 @@ inline std::string view_to_jsonl(const ResultView* r) {
     parallel_ranges(ent.size(), [&](unsigned t, size_t a, size_t b) {
         std::string& o = parts[t];
         for (size_t i = a; i < b; i++) {
-            d.object(o, ent[i].query, ent[i].rec, nullptr, false, 0);
+            d.object(o, ent[i].query, ent[i].part, ent[i].rec, nullptr, false, 0);
             o.push_back('\n');
         }
     });
@@ -408,7 +417,7 @@ inline int view_write(const ResultView* r, const char* path, int format, const c
             for (size_t i = 0; i < ent.size(); i++) {
                 if (i) o.push_back(',');
                 if (pretty) o += "\n    ";
-                d.object(o, ent[i].query, ent[i].rec, run_id.c_str(), pretty, 2);
+                d.object(o, ent[i].query, ent[i].part, ent[i].rec, run_id.c_str(), pretty, 2);
                 flush(false);
             }
             if (pretty)
@@ -418,7 +427,7 @@ inline int view_write(const ResultView* r, const char* path, int format, const c
         } else if (format == BLU_FORMAT_JSONL) {
             o += "null\n";  // serde_json::to_string(&config) with config = None
             for (size_t i = 0; i < ent.size(); i++) {
-                d.object(o, ent[i].query, ent[i].rec, run_id.c_str(), false, 0);
+                d.object(o, ent[i].query, ent[i].part, ent[i].rec, run_id.c_str(), false, 0);
                 o.push_back('\n');
                 flush(false);
             }
@@ -475,7 +484,7 @@ inline int view_write(const ResultView* r, const char* path, int format, const c
                 else
                     o += "\n    consensusBeans:\n";
                 for (uint32_t b = 0; b < rc.n_beans; b++) {
-                    const blu_bean& bn = r->beans()[rc.slot_base + b];
+                    const blu_bean& bn = en.part->beans[rc.bean_base + b];
                     const uint32_t bp = T.lin_off[bn.first_lineage] + rc.bean_level;
                     o += "    - rank: ";
                     yaml_str(o, T.ranks[T.pos_rank[bp]].full);
@@ -491,9 +500,9 @@ inline int view_write(const ResultView* r, const char* path, int format, const c
                     else
                         o += "\n      accessions:\n";
                     for (uint32_t a = 0; a < bn.n_acc; a++) {
-                        const blu_acc& ac = r->accs()[rc.slot_base + bn.acc_begin + a];
+                        const blu_acc& ac = en.part->accs[rc.acc_base + bn.acc_begin + a];
                         o += "      - ";
-                        yaml_str(o, std::string_view(r->pool() + ac.off, ac.len));
+                        yaml_str(o, std::string_view(en.part->pool + BLU_ACC_OFF(ac), BLU_ACC_LEN(ac)));
                         o.push_back('\n');
                     }
                 }
@@ -581,7 +590,7 @@ inline int view_write_tabular(const ResultView* r, const char* path, const char*
         o += "\tnull\tnull";
         piece_done();
         for (uint32_t b = 0; b < rc.n_beans; b++) {
-            const blu_bean& bn = r->beans()[rc.slot_base + b];
+            const blu_bean& bn = en.part->beans[rc.bean_base + b];
             const uint32_t bp = T.lin_off[bn.first_lineage] + rc.bean_level;
             o += run_id;
             o.push_back('\t');
@@ -598,9 +607,9 @@ inline int view_write_tabular(const ResultView* r, const char* path, const char*
             o += std::to_string(bn.occurrences);
             o.push_back('\t');
             for (uint32_t a = 0; a < bn.n_acc; a++) {
-                const blu_acc& ac = r->accs()[rc.slot_base + bn.acc_begin + a];
+                const blu_acc& ac = en.part->accs[rc.acc_base + bn.acc_begin + a];
                 if (a) o += ", ";
-                o.append(r->pool() + ac.off, ac.len);
+                o.append(en.part->pool + BLU_ACC_OFF(ac), BLU_ACC_LEN(ac));
             }
             piece_done();
         }

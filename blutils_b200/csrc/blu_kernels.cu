@@ -25,7 +25,6 @@ namespace blu {
 namespace {
 
 constexpr int kRowCap = kWin / 26 + 16;   // a valid row is >= 26 bytes (13 one-byte fields, 12 tabs, '\n')
-constexpr int kLongTopCap = 1024;         // largest top bit-score group the block path sorts
 constexpr int kLongThreads = 512;
 constexpr int kLongWarps = kLongThreads / 32;
 
@@ -63,8 +62,15 @@ __device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes)
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
+// grammar-class errors (a malformed row, a limit of this implementation hit while scanning): fatal wherever the row sits
 __device__ __forceinline__ void report(Counters* ctr, uint32_t err, unsigned long long off) {
     if (atomicCAS(&ctr->err_code, 0u, err) == 0u) ctr->err_off = off;
+}
+// consensus-class errors (join miss, unparsable lineage, root-level disagreement, empty adjusted taxonomy, a top row's number
+// outside the exactly-parsed range): what the reference only meets on the rows of a query's TOP group -- fatal once the
+// table is known to be contiguous (a fragment of a scattered query may have a different top group than the merged query)
+__device__ __forceinline__ void report_soft(Counters* ctr, uint32_t err, unsigned long long off) {
+    if (atomicCAS(&ctr->soft_code, 0u, err) == 0u) ctr->soft_off = off;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -83,7 +89,6 @@ struct WindowIndex {
     uint16_t endm[kChunks + 8];
     uint16_t row_s[kRowCap];
     uint16_t row_e[kRowCap + 1];
-    alignas(8) unsigned long long mbar;
     int n_starts, n_ends;
     int bad_byte;  // window offset of the first '"' / '\r' byte inside [qlo, qhi), or INT_MAX
     int warp_cnt[32];
@@ -102,18 +107,18 @@ struct WinGeom {
 
 // Stage [lo, lo+bytes) of the text into the window with TMA bulk copies.  All threads call; returns when the
 // bytes are visible.  `phase` is the barrier parity, flipped by the caller after every use.
-__device__ __forceinline__ void load_window(WindowIndex& W, const uint8_t* text, unsigned long long lo, int bytes, uint32_t& phase,
-                                            bool synced = false) {
+__device__ __forceinline__ void load_window(WindowIndex& W, unsigned long long* mbar, const uint8_t* text, unsigned long long lo, int bytes,
+                                            uint32_t& phase, bool synced = false) {
     if (!synced) __syncthreads();  // everyone is done with the previous contents
     if (threadIdx.x == 0) {
         fence_proxy_async();
-        mbar_expect_tx(&W.mbar, (uint32_t)bytes);
+        mbar_expect_tx(mbar, (uint32_t)bytes);
         for (int o = 0; o < bytes; o += 16384) {
             int n = bytes - o < 16384 ? bytes - o : 16384;
-            tma_bulk_g2s(W.win + o, text + lo + o, (uint32_t)n, &W.mbar);
+            tma_bulk_g2s(W.win + o, text + lo + o, (uint32_t)n, mbar);
         }
     }
-    while (!mbar_try_wait(&W.mbar, phase)) {
+    while (!mbar_try_wait(mbar, phase)) {
     }
     phase ^= 1;
 }
@@ -398,7 +403,7 @@ struct StreamSmem {
     int b_done;  // warps that have finished phase B of the current window
     int bad_byte, has_blank, crowded;
     int n_runs, next_run, n_skip, term, new_open;
-    uint32_t rec_base;
+    unsigned long long rec_base;
     uint32_t slot_cur, slot_end;  // the CTA's current slab of top-row slots: [slot_cur, slot_end) is free
     int rec_cnt;                  // record headers in rec_buf
     uint32_t slots_taken;         // slots this CTA has reserved in slabs so far (sizes the next slab)
@@ -576,9 +581,9 @@ __device__ __forceinline__ void write_record(blu_record* dst, const StagedRec& s
     rec.perc_identity = 0.0;
     rec.bit_score = (int64_t)sr.mx;
     rec.ref_lineage = 0;
-    rec.slot_base = sr.slot;
-    rec.n_beans = 0;
-    rec.n_accessions = sr.gtot;  // size of the top group until the consensus kernel overwrites it
+    rec.bean_base = sr.slot;     // first top-row slot / size of the top group until the consensus kernel has run
+    rec.n_beans = sr.gtot;
+    rec.acc_base = 0;
     rec.status = 2;              // waiting for the consensus kernel
     rec.single_match = 0;
     rec.mutated = 0;
@@ -595,17 +600,16 @@ __device__ __forceinline__ void flush_records(const RunParams& p, StreamSmem& S,
     const int n = S.rec_cnt < kRecBuf ? S.rec_cnt : kRecBuf;
     if (n == 0) return;
     if (tid == 0) {
-        const unsigned long long rs = atomicAdd(&p.ctr->rec_slots, (unsigned long long)n << 32);
-        const uint32_t rec_base = (uint32_t)(rs >> 32);
+        const unsigned long long rec_base = atomicAdd(&p.ctr->rec_count, (unsigned long long)n);
         S.rec_base = rec_base;
-        if ((unsigned long long)rec_base + (unsigned long long)n > p.rec_cap) {
+        if (rec_base + (unsigned long long)n > p.rec_cap) {
             S.out_ok = 0;
             p.ctr->cap_overflow = 1;
         }
     }
     __syncthreads();
     if (S.out_ok) {
-        const uint32_t rec_base = S.rec_base;
+        const unsigned long long rec_base = S.rec_base;
         for (int i = tid; i < n; i += kTileThreads) write_record(p.records + rec_base + i, S.rec_buf[i]);
     }
     __syncthreads();
@@ -613,14 +617,15 @@ __device__ __forceinline__ void flush_records(const RunParams& p, StreamSmem& S,
 }
 
 // One thread: describes the window that starts at `lo` in S.wd[buf] and asks the TMA unit for its bytes.
-__device__ __forceinline__ void describe_and_load(StreamSmem& S, int buf, const RunParams& p, unsigned long long lo, unsigned long long up) {
+__device__ __forceinline__ void describe_and_load(StreamSmem& S, int buf, const RunParams& p, unsigned long long p_begin, unsigned long long lo,
+                                                  unsigned long long up) {
     const int loaded = (int)(up - lo < (unsigned long long)kTile ? up - lo : (unsigned long long)kTile);
     WinDesc d;
     d.lo = lo;
     d.loaded = loaded;
     d.tend = (int)(p.end - lo < (unsigned long long)loaded ? p.end - lo : (unsigned long long)loaded);
-    const bool has_begin = lo <= p.begin;
-    d.vb = has_begin ? (int)(p.begin - lo) : 0;
+    const bool has_begin = lo <= p_begin;
+    d.vb = has_begin ? (int)(p_begin - lo) : 0;
     d.flags = (p.end <= lo + (unsigned long long)loaded ? 1 : 0) | (has_begin ? 2 : 0);
     S.wd[buf] = d;
     stream_issue_load(S, buf, p.text, lo, loaded);
@@ -659,15 +664,17 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
 #endif
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const unsigned FULL = 0xffffffffu;
-    if (p.end <= p.begin) return;
+    // a later range of a resident table starts where the previous one stopped (its open last query): no host round trip
+    const unsigned long long p_begin = p.begin == kBeginFromCounters ? p.ctr->next_begin : p.begin;
+    if (p.end <= p_begin) return;
     // ---- this CTA's segment --------------------------------------------------------------------------------------
-    const unsigned long long total = p.end - p.begin;
+    const unsigned long long total = p.end - p_begin;
     unsigned long long seg = (total + gridDim.x - 1) / gridDim.x;
     if (seg < 4ull * kTile) seg = 4ull * kTile;
-    const unsigned long long seg_lo = p.begin + (unsigned long long)blockIdx.x * seg;
+    const unsigned long long seg_lo = p_begin + (unsigned long long)blockIdx.x * seg;
     if (seg_lo >= p.end) return;
     const unsigned long long seg_hi = (seg_lo + seg < p.end) ? seg_lo + seg : p.end;
-    const unsigned long long b16 = p.begin & ~15ull;
+    const unsigned long long b16 = p_begin & ~15ull;
     const unsigned long long up = (p.end + 15ull) & ~15ull;
 
     if (tid == 0) {
@@ -682,16 +689,16 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
             // the CTA's first slab of top-row slots (about 40 per window of the segment, at most kSlotSlab)
             const unsigned long long est = ((seg_hi - seg_lo) / (unsigned long long)kTile + 1ull) * 40ull + (unsigned long long)kSlotLow;
             const uint32_t slab = est < (unsigned long long)kSlotSlab ? (uint32_t)est : kSlotSlab;
-            const unsigned long long rs = atomicAdd(&p.ctr->rec_slots, (unsigned long long)slab);
+            const unsigned long long rs = atomicAdd(&p.ctr->slot_count, (unsigned long long)slab);
             S.slot_cur = (uint32_t)rs;
             S.slot_end = (uint32_t)rs + slab;
             S.slots_taken = slab;
-        }
-        S.rec_cnt = 0;
-        S.out_ok = 1;
-        if ((unsigned long long)S.slot_end > (unsigned long long)p.slot_cap) {
-            S.out_ok = 0;
-            p.ctr->cap_overflow = 1;
+            S.rec_cnt = 0;
+            S.out_ok = 1;
+            if (rs + (unsigned long long)slab > p.slot_cap) {  // (slot_cap < 2^32: slot numbers fit the 32-bit fields)
+                S.out_ok = 0;
+                p.ctr->cap_overflow = 1;
+            }
         }
     }
     for (int i = tid; i < 7; i += kTileThreads) S.tabm[kUnits + i] = S.digm[kUnits + i] = S.nlm[kUnits + i] = 0u;
@@ -702,9 +709,9 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
     unsigned long long own_from = seg_lo;  // rows that start at or after this offset have not been processed yet
     int buf = 0;
     if (tid == 0) {
-        unsigned long long lo0 = seg_lo > p.begin + kBack ? (seg_lo - kBack) & ~15ull : b16;
+        unsigned long long lo0 = seg_lo > p_begin + kBack ? (seg_lo - kBack) & ~15ull : b16;
         if (lo0 < b16) lo0 = b16;
-        describe_and_load(S, 0, p, lo0, up);
+        describe_and_load(S, 0, p, p_begin, lo0, up);
     }
     __syncthreads();
 
@@ -835,7 +842,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
                 unsigned long long next_lo = lo;
                 if (progress) {
                     const unsigned long long la = lo + (unsigned long long)lc;
-                    next_lo = la > p.begin ? (la - 1) & ~15ull : b16;
+                    next_lo = la > p_begin ? (la - 1) & ~15ull : b16;
                     if (next_lo < b16) next_lo = b16;
                 }
                 const bool may_continue = progress && !covers_eof && next_lo > lo;
@@ -843,7 +850,7 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
                 S.geo.last_nl = last_nl;
                 S.geo.may_continue = may_continue ? 1 : 0;
                 if (n_complete == n_starts) S.row_s[n_starts] = (uint16_t)(last_nl + 1);  // sentinel: end of the last row
-                if (may_continue) describe_and_load(S, buf ^ 1, p, next_lo, up);
+                if (may_continue) describe_and_load(S, buf ^ 1, p, p_begin, next_lo, up);
             }
         }
         const uint64_t* tabw = reinterpret_cast<const uint64_t*>(S.tabm);
@@ -1070,9 +1077,9 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
                     if (g_tot > 0) {
                         slot = atomicAdd(&S.slot_cur, (uint32_t)g_tot);
                         if (slot + (uint32_t)g_tot > S.slot_end || slot + (uint32_t)g_tot < slot) {
-                            const unsigned long long rs = atomicAdd(&p.ctr->rec_slots, (unsigned long long)g_tot);
+                            const unsigned long long rs = atomicAdd(&p.ctr->slot_count, (unsigned long long)g_tot);
                             slot = (uint32_t)rs;
-                            if ((rs & 0xFFFFFFFFull) + (unsigned long long)g_tot > (unsigned long long)p.slot_cap) {
+                            if (rs + (unsigned long long)g_tot > p.slot_cap) {
                                 S.out_ok = 0;
                                 p.ctr->cap_overflow = 1;
                             }
@@ -1085,9 +1092,9 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
                         S.rec_buf[ri] = sr;
                     else {
                         // record buffer full (a window of very short queries): this record is reserved on its own
-                        const unsigned long long rs = atomicAdd(&p.ctr->rec_slots, 1ull << 32);
-                        if ((rs >> 32) < (unsigned long long)p.rec_cap)
-                            write_record(p.records + (rs >> 32), sr);
+                        const unsigned long long ri2 = atomicAdd(&p.ctr->rec_count, 1ull);
+                        if (ri2 < p.rec_cap)
+                            write_record(p.records + ri2, sr);
                         else
                             p.ctr->cap_overflow = 1;
                     }
@@ -1141,10 +1148,10 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
                 const unsigned long long est = (unsigned long long)(S.slots_taken / (uint32_t)win_idx + 8u) * left + (unsigned long long)kSlotLow;
                 const uint32_t slab = est < (unsigned long long)kSlotSlab ? (uint32_t)est : kSlotSlab;
                 S.slots_taken += slab;
-                const unsigned long long rs = atomicAdd(&p.ctr->rec_slots, (unsigned long long)slab);
+                const unsigned long long rs = atomicAdd(&p.ctr->slot_count, (unsigned long long)slab);
                 S.slot_cur = (uint32_t)rs;
                 S.slot_end = (uint32_t)rs + slab;
-                if ((rs & 0xFFFFFFFFull) + (unsigned long long)slab > (unsigned long long)p.slot_cap) {
+                if (rs + (unsigned long long)slab > p.slot_cap) {
                     S.out_ok = 0;
                     p.ctr->cap_overflow = 1;
                 }
@@ -1208,18 +1215,37 @@ __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(cons
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kQidCache = 256;  // bytes of the run's query id kept in shared memory
 
-struct LongSmem {
+// Sort-phase arrays of the block-parallel consensus (the window and its row tables are dead by then): all indices are
+// 16-bit (a top group holds at most kLongTopCap <= 65535 rows)
+struct LongSort {
+    uint16_t order[kLongTopCap];  // S: row numbers in the order of find_multi_taxa_consensus.rs:39-54
+    uint16_t bord[kLongTopCap];   // positions of S sorted by (bean key, position): one segment per bean, S order inside
+    uint16_t hb[kLongTopCap + 1]; // inclusive count of segment heads: bean number + 1
+    uint16_t kp[kLongTopCap + 1]; // exclusive count of kept accessions (Vec::dedup)
+    uint16_t st[kLongTopCap + 1]; // first position of every bean's segment
+    uint16_t bsort[kLongTopCap];  // beans in output order (occurrences desc, identifier asc)
+    uint16_t abeg[kLongTopCap];   // first accession of every bean, relative to the record's acc_base
+    uint16_t tmp[kLongTopCap + 1];
+    uint32_t key[kLongTopCap];    // bean key of every position of S
+};
+
+struct LongScanState {
     WindowIndex W;
     long long bits[kRowCap];
     uint8_t same[kRowCap];
-    unsigned long long cand_off[kLongTopCap];  // rows whose bit score equals the running maximum, in file order
-    uint32_t cand_len[kLongTopCap];
-    TopRow top[kLongTopCap];
-    uint16_t tmp[5 * kLongTopCap];
+};
+
+struct LongSmem {
+    union {
+        LongScanState scan;
+        LongSort sort;
+    };
+    alignas(8) unsigned long long mbar;  // (outside the union: its phase lives across runs)
     uint8_t qid[kQidCache];  // first field (+ its tab) of the run's first row
     long long red_max[kLongWarps];
     int red_cnt[kLongWarps];
     int red_first[kLongWarps];
+    int scan_tot[kLongWarps];
     int bcast[8];
     unsigned long long bcast64[4];
 };
@@ -1255,13 +1281,13 @@ struct LongScan {
 // Stages the window that starts at `cur`, indexes and parses its rows, and marks which rows belong to the run
 // whose first row starts at absolute offset `s`.
 __device__ LongScan long_scan(LongSmem& S, const RunParams& p, unsigned long long s, unsigned long long cur, uint32_t& phase, int qn) {
-    WindowIndex& W = S.W;
+    WindowIndex& W = S.scan.W;
     LongScan r;
     const unsigned long long lo = cur & ~15ull;
     WinGeom g = make_geom(lo, kWin, cur, p.end);
     __syncthreads();
     if (threadIdx.x == 0) W.bad_byte = INT_MAX;
-    load_window(W, p.text, lo, g.loaded, phase, true);
+    load_window(W, &S.mbar, p.text, lo, g.loaded, phase, true);
     if (threadIdx.x == 32) {
         // a long run continues right behind this window: pull the next one into L2 meanwhile
         const unsigned long long nb = lo + (unsigned long long)g.loaded;
@@ -1293,8 +1319,8 @@ __device__ LongScan long_scan(LongSmem& S, const RunParams& p, unsigned long lon
         }
         const bool sm = qn > 0 ? same_query_cached(W.win + st, len, S.qid, qn) : same_query(W.win + st, len, p.text, s, p.end);
         if (lr.err && sm) report(p.ctr, lr.err, lo + st);
-        S.bits[i] = lr.bits;
-        S.same[i] = sm;
+        S.scan.bits[i] = lr.bits;
+        S.scan.same[i] = sm;
         if (!sm && i < first_other) first_other = i;
     }
 #pragma unroll
@@ -1325,14 +1351,230 @@ __device__ LongScan long_scan(LongSmem& S, const RunParams& p, unsigned long lon
     return r;
 }
 
+// ---- block-wide primitives of the long-run kernel's consensus ----------------------------------------------------------
+// Bitonic sort of the 16-bit indices idx[0, n2) (n2 a power of two; the padding entries hold 0xFFFF and sort last) by a
+// strict total order `less`.  All threads of the CTA call.
+template <class Less>
+__device__ __forceinline__ void block_bitonic_u16(uint16_t* idx, int n2, Less less) {
+    for (int k = 2; k <= n2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int t = threadIdx.x; t < (n2 >> 1); t += kLongThreads) {
+                const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+                const int l = i | j;
+                const uint16_t x = idx[i], y = idx[l];
+                const bool up = (i & k) == 0;
+                // lt(u, v): u sorts in front of v
+                const uint16_t u = up ? y : x, v = up ? x : y;
+                const bool sw = u != 0xFFFFu && (v == 0xFFFFu || less((int)u, (int)v));
+                if (sw) {
+                    idx[i] = y;
+                    idx[l] = x;
+                }
+            }
+            __syncthreads();
+        }
+}
+
+// out[i] = f(0) + ... + f(i-1) for i in [0, n], out[n] = total (16-bit: totals stay below 65536).  All threads call.
+template <class F>
+__device__ __forceinline__ int block_excl_scan_u16(uint16_t* out, int n, F f, int* warp_tot) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (n + kLongThreads - 1) / kLongThreads;
+    const int b = tid * per < n ? tid * per : n, e = b + per < n ? b + per : n;
+    int sum = 0;
+    for (int i = b; i < e; i++) sum += f(i);
+    int inc = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += t;
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    int base = 0, total = 0;
+    for (int k = 0; k < kLongWarps; k++) {
+        if (k < warp) base += warp_tot[k];
+        total += warp_tot[k];
+    }
+    int run = base + inc - sum;
+    for (int i = b; i < e; i++) {
+        out[i] = (uint16_t)run;
+        run += f(i);
+    }
+    if (tid == 0) out[n] = (uint16_t)total;
+    __syncthreads();
+    return total;
+}
+
+__device__ __forceinline__ bool acc_equal(const TopRow& a, const TopRow& b, const uint8_t* text) {
+    return a.acc_len == b.acc_len && bytes_cmp(text + a.acc_off, a.acc_len, text + b.acc_off, b.acc_len) == 0;
+}
+
+// Block-parallel multi-taxa consensus of a top group of g >= 2 joined rows (file order, global scratch): the same result
+// as the serial consensus_multi() of blu_core.cuh (find_multi_taxa_consensus.rs:22-217, build_blast_consensus_identity.rs,
+// consensus_result.rs:65-88), computed with block-wide sorts and scans so that a group of thousands of rows (BASELINE
+// config C4 allows 5000 hits per query) costs a few hundred microseconds instead of a serial quadratic walk.
+// Returns the soft error (uniform), or DE_NONE after the record, its beans and accession references have been written.
+__device__ uint32_t long_consensus(LongSmem& S, const RunParams& p, const TopRow* rows, int g, unsigned long long s, uint32_t qlen,
+                                   unsigned long long nrows, long long mx) {
+    LongSort& Q = S.sort;
+    const LinTables& T = p.T;
+    const int tid = threadIdx.x, lane = tid & 31;
+    int n2 = 2;
+    while (n2 < g) n2 <<= 1;
+    // ---- S = the top group sorted by (lineage length, pident, align length, accession; file order)   fmtc.rs:39-54 ----
+    for (int i = tid; i < n2; i += kLongThreads) Q.order[i] = i < g ? (uint16_t)i : (uint16_t)0xFFFFu;
+    if (tid == 0) {
+        S.bcast[5] = INT_MAX;
+        S.bcast64[0] = 0ull;
+    }
+    __syncthreads();
+    block_bitonic_u16(Q.order, n2, [&](int a, int b) { return row_less(rows, p.text, a, b); });
+    const TopRow ref = rows[p.strategy == BLU_STRATEGY_CAUTIOUS ? Q.order[0] : Q.order[g - 1]];  // fmtc.rs:60-63
+    const int m = rows[Q.order[0]].lin_len;  // shortest lineage: levels >= m are never looked at
+    // ---- level walk (fmtc.rs:137-214): first level at which the level keys disagree; max pident folded from 0.0 ----------
+    {
+        const uint32_t lin0 = rows[0].lin;
+        const uint32_t o0 = T.lin_off[lin0];
+        int myd = INT_MAX;
+        double mypid = 0.0;
+        for (int r = tid; r < g; r += kLongThreads) {
+            const TopRow x = rows[r];
+            if (x.pident > mypid) mypid = x.pident;
+            if (x.lin != lin0) {
+                const uint32_t o = T.lin_off[x.lin];
+                for (int i = 0; i < m && i < myd; i++)
+                    if (T.lvl_key[o + i] != T.lvl_key[o0 + i]) {
+                        myd = i;
+                        break;
+                    }
+            }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const int od = __shfl_xor_sync(0xffffffffu, myd, d);
+            const double op = __shfl_xor_sync(0xffffffffu, mypid, d);
+            myd = od < myd ? od : myd;
+            mypid = op > mypid ? op : mypid;
+        }
+        if (lane == 0) {
+            if (myd != INT_MAX) atomicMin(&S.bcast[5], myd);
+            if (mypid > 0.0) atomicMax(&S.bcast64[0], (unsigned long long)__double_as_longlong(mypid));  // positive doubles order like their bits
+        }
+        __syncthreads();
+    }
+    const int diverge = S.bcast[5] == INT_MAX ? -1 : S.bcast[5];
+    if (diverge == 0) return DE_ROOT_DISAGREE;
+    double identity;
+    int idx, level;
+    bool single;
+    if (diverge > 0) {
+        identity = __longlong_as_double((long long)S.bcast64[0]), idx = diverge - 1, level = diverge, single = false;
+    } else {
+        identity = ref.pident, idx = m - 1, level = m - 1, single = true;
+    }
+    // ---- bean folding at `level` in S order (consensus_result.rs:65-88) ----------------------------------------------
+    for (int i = tid; i < n2; i += kLongThreads) {
+        Q.bord[i] = i < g ? (uint16_t)i : (uint16_t)0xFFFFu;
+        if (i < g) Q.key[i] = T.bean_key[T.lin_off[rows[Q.order[i]].lin] + level];
+    }
+    __syncthreads();
+    block_bitonic_u16(Q.bord, n2, [&](int a, int b) { return Q.key[a] != Q.key[b] ? Q.key[a] < Q.key[b] : a < b; });
+    // flags per position of `bord`: bit 0 = first of its bean, bit 1 = accession kept (Vec::dedup drops an accession equal
+    // to its predecessor in the bean's S-ordered list)
+    for (int i = tid; i < g; i += kLongThreads) {
+        const bool head = i == 0 || Q.key[Q.bord[i]] != Q.key[Q.bord[i - 1]];
+        const bool kept = head || !acc_equal(rows[Q.order[Q.bord[i]]], rows[Q.order[Q.bord[i - 1]]], p.text);
+        Q.tmp[i] = (uint16_t)((head ? 1 : 0) | (kept ? 2 : 0));
+    }
+    __syncthreads();
+    const int nb = block_excl_scan_u16(Q.hb, g, [&](int i) { return (int)(Q.tmp[i] & 1u); }, S.scan_tot);
+    const int nkept = block_excl_scan_u16(Q.kp, g, [&](int i) { return (int)((Q.tmp[i] >> 1) & 1u); }, S.scan_tot);
+    for (int i = tid; i < g; i += kLongThreads) {
+        const bool head = (Q.tmp[i] & 1u) != 0;
+        if (head) Q.st[Q.hb[i]] = (uint16_t)i;  // (hb is exclusive here: the bean's number)
+    }
+    if (tid == 0) Q.st[nb] = (uint16_t)g;
+    __syncthreads();
+    for (int i = tid; i < g; i += kLongThreads) Q.hb[i] = (uint16_t)(Q.hb[i] + (Q.tmp[i] & 1u));  // inclusive: bean number + 1
+    // ---- beans in output order: occurrences desc, identifier asc (bbci.rs:50-60), ties on the key id ----------------------
+    int nb2 = 2;
+    while (nb2 < nb) nb2 <<= 1;
+    for (int j = tid; j < nb2; j += kLongThreads) Q.bsort[j] = j < nb ? (uint16_t)j : (uint16_t)0xFFFFu;
+    __syncthreads();
+    block_bitonic_u16(Q.bsort, nb2, [&](int a, int b) {
+        const int oa = (int)Q.st[a + 1] - (int)Q.st[a], ob = (int)Q.st[b + 1] - (int)Q.st[b];
+        if (oa != ob) return oa > ob;
+        const uint32_t pa = T.lin_off[rows[Q.order[Q.bord[Q.st[a]]]].lin] + (uint32_t)level, pb = T.lin_off[rows[Q.order[Q.bord[Q.st[b]]]].lin] + (uint32_t)level;
+        const uint32_t ia = T.ident_rank[pa], ib = T.ident_rank[pb];
+        if (ia != ib) return ia < ib;
+        return Q.key[Q.bord[Q.st[a]]] < Q.key[Q.bord[Q.st[b]]];
+    });
+    // first accession of every bean: exclusive scan of the kept counts in output order, scattered back to bean numbers
+    block_excl_scan_u16(Q.tmp, nb, [&](int j) { const int bb = Q.bsort[j]; return (int)Q.kp[Q.st[bb + 1]] - (int)Q.kp[Q.st[bb]]; }, S.scan_tot);
+    for (int j = tid; j < nb; j += kLongThreads) Q.abeg[Q.bsort[j]] = Q.tmp[j];
+    // ---- output: one record, nb beans, nkept accession references, all compact --------------------------------------------
+    if (tid == 0) {
+        const unsigned long long ri = atomicAdd(&p.ctr->rec_count, 1ull);
+        const unsigned long long bb = atomicAdd(&p.ctr->bean_used, (unsigned long long)nb);
+        const unsigned long long ab = atomicAdd(&p.ctr->acc_used, (unsigned long long)nkept);
+        S.bcast64[1] = ri, S.bcast64[2] = bb, S.bcast64[3] = ab;
+        if (ri >= p.rec_cap || bb + (unsigned long long)nb > p.bean_cap || ab + (unsigned long long)nkept > p.acc_cap) {
+            p.ctr->cap_overflow = 1;
+            S.bcast64[1] = ~0ull;
+        }
+    }
+    __syncthreads();
+    if (S.bcast64[1] == ~0ull) return DE_NONE;  // the host grows the arrays and reruns
+    const unsigned long long ri = S.bcast64[1], bean_base = S.bcast64[2], acc_base = S.bcast64[3];
+    for (int j = tid; j < nb; j += kLongThreads) {
+        const int bb = Q.bsort[j];
+        blu_bean bn;
+        bn.first_lineage = rows[Q.order[Q.bord[Q.st[bb]]]].lin;
+        bn.occurrences = (uint32_t)((int)Q.st[bb + 1] - (int)Q.st[bb]);
+        bn.acc_begin = Q.abeg[bb];
+        bn.n_acc = (uint32_t)((int)Q.kp[Q.st[bb + 1]] - (int)Q.kp[Q.st[bb]]);
+        p.beans[bean_base + j] = bn;
+    }
+    for (int i = tid; i < g; i += kLongThreads)
+        if (Q.kp[i + 1] != Q.kp[i]) {
+            const int bb = (int)Q.hb[i] - 1;
+            const TopRow& x = rows[Q.order[Q.bord[i]]];
+            p.accs[acc_base + Q.abeg[bb] + (Q.kp[i] - Q.kp[Q.st[bb]])].ref = (x.acc_off << 16) | (unsigned long long)x.acc_len;
+        }
+    if (tid == 0) {
+        blu_record* rec = p.records + ri;
+        rec->query_off = s;
+        rec->query_len = qlen;
+        rec->n_rows = (uint32_t)nrows;
+        rec->bit_score = mx;
+        rec->perc_identity = ref.pident;
+        rec->ref_lineage = ref.lin;
+        rec->bean_base = (uint32_t)bean_base;
+        rec->n_beans = (uint32_t)nb;
+        rec->acc_base = (uint32_t)acc_base;
+        rec->status = 1;
+        rec->single_match = 0;
+        rec->bean_level = (int8_t)level;
+        rec->pad[0] = rec->pad[1] = 0;
+        apply_cutoffs(T, ref.lin, identity, single && nb == 1, idx, rec);
+    }
+    return DE_NONE;
+}
+
 __global__ void __launch_bounds__(kLongThreads, 1) longrun_kernel(const __grid_constant__ RunParams p) {
+    // (launched behind every tile kernel without a host round trip in between: nothing deferred -> nothing to do)
+    if (p.ctr->n_defer == 0) return;
     extern __shared__ __align__(128) uint8_t smem_raw[];
     LongSmem& S = *reinterpret_cast<LongSmem*>(smem_raw);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    if (tid == 0) mbar_init(&S.W.mbar, 1);
+    const unsigned long long p_begin = p.begin == kBeginFromCounters ? p.ctr->next_begin : p.begin;
+    if (tid == 0) mbar_init(&S.mbar, 1);
     __syncthreads();
     uint32_t phase = 0;
     const unsigned n_defer = p.ctr->n_defer < p.defer_cap ? p.ctr->n_defer : p.defer_cap;
+    TopRow* const rows = p.big_rows + (size_t)blockIdx.x * kLongTopCap;
+    unsigned long long* const cand = p.big_cand + (size_t)blockIdx.x * kLongTopCap;
 
     while (true) {
         __syncthreads();
@@ -1346,12 +1588,12 @@ __global__ void __launch_bounds__(kLongThreads, 1) longrun_kernel(const __grid_c
         if (entry & 1) {
             if (tid == 0) {
                 int head = 1;
-                if (s > p.begin) {
+                if (s > p_begin) {
                     long long q = (long long)s - 1;
-                    while (q >= (long long)p.begin && p.text[q] == '\n') q--;  // skip the newline(s) before s
-                    if (q >= (long long)p.begin) {
+                    while (q >= (long long)p_begin && p.text[q] == '\n') q--;  // skip the newline(s) before s
+                    if (q >= (long long)p_begin) {
                         long long st = q;
-                        while (st > (long long)p.begin && p.text[st - 1] != '\n') st--;
+                        while (st > (long long)p_begin && p.text[st - 1] != '\n') st--;
                         // compare first fields of rows at st and s
                         head = 0;
                         for (unsigned long long i = 0;; i++) {
@@ -1405,7 +1647,7 @@ __global__ void __launch_bounds__(kLongThreads, 1) longrun_kernel(const __grid_c
             // maximum of this window's rows of the run
             long long lm = LLONG_MIN;
             for (int i = tid; i < sc.d; i += kLongThreads) {
-                const long long b = S.bits[i];
+                const long long b = S.scan.bits[i];
                 lm = b > lm ? b : lm;
             }
 #pragma unroll
@@ -1424,7 +1666,7 @@ __global__ void __launch_bounds__(kLongThreads, 1) longrun_kernel(const __grid_c
             // append this window's rows with bits == mx, in file order
             for (int b0 = 0; b0 < sc.d; b0 += kLongThreads) {
                 const int i = b0 + tid;
-                const bool top = i < sc.d && S.bits[i] == mx;
+                const bool top = i < sc.d && S.scan.bits[i] == mx;
                 const unsigned bal = __ballot_sync(0xffffffffu, top);
                 if (lane == 0) S.red_cnt[warp] = __popc(bal);
                 __syncthreads();
@@ -1436,10 +1678,9 @@ __global__ void __launch_bounds__(kLongThreads, 1) longrun_kernel(const __grid_c
                 }
                 if (top) {
                     const long long pos = before + __popc(bal & ((1u << lane) - 1u));
-                    if (pos < kLongTopCap) {
-                        S.cand_off[pos] = lo + S.W.row_s[i];
-                        S.cand_len[pos] = (uint32_t)((int)S.W.row_e[i + sc.eskip] - (int)S.W.row_s[i]);
-                    }
+                    if (pos < kLongTopCap)
+                        cand[pos] = ((lo + S.scan.W.row_s[i]) << 16) |
+                                    (unsigned long long)(uint32_t)((int)S.scan.W.row_e[i + sc.eskip] - (int)S.scan.W.row_s[i]);  // (a row fits the window: < 65536 bytes)
                 }
                 cnt += total;
                 __syncthreads();
@@ -1466,53 +1707,79 @@ __global__ void __launch_bounds__(kLongThreads, 1) longrun_kernel(const __grid_c
             continue;
         }
         const int gcount = (int)cnt;
-        if (tid == 0) {
-            unsigned long long rs = atomicAdd(&p.ctr->rec_slots, (1ull << 32) | (unsigned long long)gcount);
-            S.bcast[2] = (int)(unsigned)(rs >> 32);
-            S.bcast[3] = (int)(unsigned)rs;
-        }
         // ---- join the top rows (read back from the text; they are few) -----------------------------------------------
-        int any_err = 0;
+        uint32_t my_err = 0;
+        unsigned long long my_off = 0;
         for (int i = tid; i < gcount; i += kLongThreads) {
-            const unsigned long long off = S.cand_off[i];
-            uint32_t err = heavy_parse_row(p.text + off, (int)S.cand_len[i], off, p.T, S.top[i]);
-            if (err) {
-                report(p.ctr, err, off);
-                any_err = 1;
+            const unsigned long long off = cand[i] >> 16;
+            const uint32_t err = heavy_parse_row(p.text + off, (int)(cand[i] & 0xFFFFull), off, p.T, rows[i]);
+            if (err && !my_err) my_err = err, my_off = off;
+        }
+        if (my_err) report_soft(p.ctr, my_err, my_off);
+        uint32_t soft = __syncthreads_or(my_err != 0) ? 1u : 0u;
+        uint32_t ql = 0;
+        if (qn > 0)
+            ql = (uint32_t)(qn - 1);
+        else
+            while (s + ql < p.end && p.text[s + ql] != '\t') ql++;
+        if (!soft && gcount > 1) {
+            const uint32_t ce = long_consensus(S, p, rows, gcount, s, ql, (unsigned long long)nrows, mx);
+            if (ce) {
+                if (tid == 0) report_soft(p.ctr, ce, s);
+                soft = 1;
             }
         }
-        any_err = __syncthreads_or(any_err);
-        const unsigned rec_i = (unsigned)S.bcast[2], slot = (unsigned)S.bcast[3];
-        if (rec_i >= p.rec_cap || slot + (unsigned)gcount > p.slot_cap) {
-            if (tid == 0) p.ctr->cap_overflow = 1;
-            continue;
-        }
-        if (any_err) {
-            if (tid == 0) p.records[rec_i].status = 0, p.records[rec_i].n_rows = 0, p.records[rec_i].query_len = 0, p.records[rec_i].n_accessions = 0;
-            continue;
-        }
-        if (tid == 0) {
-            blu_record* rec = p.records + rec_i;
-            QueryOut out{rec, p.beans + slot, p.accs + slot};
-            uint32_t ql = 0;
-            while (s + ql < p.end && p.text[s + ql] != '\t') ql++;
-            rec->query_off = s;
-            rec->query_len = ql;
-            rec->n_rows = (uint32_t)nrows;
-            rec->bit_score = mx;
-            rec->slot_base = slot;
-            rec->pad[0] = rec->pad[1] = 0;
-            uint32_t ce = gcount == 1 ? consensus_single(S.top[0], p.T, out)
-                                      : consensus_multi(S.top, gcount, p.text, p.T, p.strategy, S.tmp, out);
-            if (ce) report(p.ctr, ce, s);
+        if (tid == 0 && (soft || gcount == 1)) {
+            // a single top row, or a query whose consensus failed: the record is written here.  A failed query still leaves
+            // a record (status 0) so that the duplicate-id check sees its id: a fragment of a scattered query may fail
+            // although the merged query would not, and then the table is regrouped and run again.
+            const unsigned long long ri = atomicAdd(&p.ctr->rec_count, 1ull);
+            unsigned long long bb = 0, ab = 0;
+            if (!soft) {
+                bb = atomicAdd(&p.ctr->bean_used, 1ull);
+                ab = atomicAdd(&p.ctr->acc_used, 1ull);
+            }
+            if (ri >= p.rec_cap || bb + 1 > p.bean_cap || ab + 1 > p.acc_cap)
+                p.ctr->cap_overflow = 1;
+            else {
+                blu_record* rec = p.records + ri;
+                rec->query_off = s;
+                rec->query_len = ql;
+                rec->n_rows = (uint32_t)nrows;
+                rec->keep_mask = 0;
+                rec->perc_identity = 0.0;
+                rec->bit_score = mx;
+                rec->ref_lineage = 0;
+                rec->bean_base = (uint32_t)bb;
+                rec->n_beans = 0;
+                rec->acc_base = (uint32_t)ab;
+                rec->status = 0;
+                rec->single_match = rec->mutated = 0;
+                rec->reached_pos = 0, rec->allowed_pos = -1, rec->bean_level = 0;
+                rec->pad[0] = rec->pad[1] = 0;
+                if (!soft) {
+                    QueryOut out{rec, p.beans + bb, p.accs + ab};
+                    const uint32_t ce = consensus_single(rows[0], p.T, out);
+                    if (ce) {
+                        report_soft(p.ctr, ce, s);
+                        rec->status = 0, rec->n_beans = 0;
+                    }
+                }
+            }
         }
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// consensus kernel: one warp per query, lanes = rows of the top bit-score group (<= 32)
+// consensus kernel: W lanes per query (W = 8: four queries per warp; W = 32 for top groups of 9..32 rows), lanes = rows
+// of the top bit-score group
 //   find_multi_taxa_consensus.rs:39-214 + build_blast_consensus_identity.rs:9-105 + consensus_result.rs:65-88
-//   (same semantics as the serial consensus_multi() in blu_core.cuh, which the block path and the host tests use)
+//   (same semantics as the serial consensus_multi() in blu_core.cuh, which the host tests use, and as long_consensus())
+// Everything is written so that the four queries of a warp walk through the SAME instructions (loop bounds are the
+// warp-wide maxima, a query that is done is merely predicated off): top groups hold 1..8 rows in practice, so one
+// query per warp leaves most lanes idle (round 1: 928 warp-instructions per query at 15 active lanes).
+// Output is compact: a CTA adds up the beans / accession references of its 32 queries and reserves them with one atomic
+// each, so nothing but what the results need is ever downloaded.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ int cmp_u64(unsigned long long a, unsigned long long b) { return a < b ? -1 : (a > b ? 1 : 0); }
 
@@ -1533,124 +1800,61 @@ __device__ __forceinline__ int cmp_acc(unsigned long long a0, unsigned long long
     return (int)alen - (int)blen;
 }
 
-// rank selection for the reference lineage, lanes = lineage positions (two rounds cover the 64-position limit)
-__device__ __forceinline__ void warp_apply_cutoffs(const LinTables& T, uint32_t ref_lin, uint32_t o, int k, double identity, bool whole, int idx,
-                                                   blu_record* rec, int lane) {
-    unsigned long long ge = 0, notgt = 0;
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const int j = lane + 32 * h;
-        double c = 0.0;
-        const bool in = j < k;
-        if (in) c = T.cut[o + j];
-        const unsigned b_ge = __ballot_sync(0xffffffffu, in && identity >= c);     // linnaean_ranks.rs:208
-        const unsigned b_ng = __ballot_sync(0xffffffffu, in && !(identity > c));   // linnaean_ranks.rs:188
-        ge |= (unsigned long long)b_ge << (32 * h);
-        notgt |= (unsigned long long)b_ng << (32 * h);
-    }
-    if (lane == 0) {
-        const int allowed = notgt ? (__ffsll((long long)notgt) - 1) : -1;
-        unsigned long long mask = ge;
-        if (!whole) {
-            // keep the first idx+1 survivors: enumerate AFTER the filter, take_while(index <= bean_index)
-            unsigned long long m = 0, rest = ge;
-            for (int n = 0; n <= idx && rest; n++) {
-                unsigned long long low = rest & (~rest + 1);
-                m |= low;
-                rest ^= low;
-            }
-            mask = m;
-        }
-        const int last = mask ? 63 - __clzll((long long)mask) : -1;
-        rec->keep_mask = mask;
-        rec->allowed_pos = (int8_t)allowed;
-        rec->reached_pos = (int8_t)(last >= 0 ? last : idx);
-        rec->mutated = (allowed >= 0 && T.rank_cls[o + idx] != T.allowed_cls[o + allowed]) ? 1 : 0;
-        rec->ref_lineage = ref_lin;
-    }
-}
+constexpr int kConsThreads = 256;
+constexpr int kConsBatch = kConsThreads / 8;  // queries per CTA iteration of the narrow (8 lanes per query) pass
 
-__global__ void __launch_bounds__(256) consensus_kernel(const ConsParams p) {
+// What a lane holds once its query's consensus is computed; written out after the output space has been reserved.
+struct ConsLane {
+    // lane 0 of the group: the record
+    unsigned long long keep_mask;
+    double perc_identity;
+    uint32_t ref_lineage;
+    int nb, nkept;         // beans / kept accession references of the query (0: the query failed or is not this pass's)
+    int reached, allowed, level;
+    bool mutated, single, ok;
+    // every lane: its bean (leaders) and its accession reference (kept rows)
+    bool leader, keeps;
+    blu_bean bean;
+    int bean_idx, acc_idx;
+    unsigned long long acc_ref;
+};
+
+// `valid`: this group has a record to process in this pass; g = size of its top group (1..W), slot = its first top row.
+template <int W>
+__device__ __forceinline__ ConsLane cons_compute(const PostParams& p, bool valid, int g, unsigned long long slot, unsigned long long query_off, int lane) {
     const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const unsigned qi = p.rec_begin + (blockIdx.x * blockDim.x + threadIdx.x) / 32;
-    if (qi >= p.rec_end) return;
-    blu_record* rec = p.records + qi;
-    if (rec->status != 2) return;
     const LinTables& T = p.T;
-    const int g = (int)rec->n_accessions;
-    const unsigned slot = rec->slot_base;
-    const bool on = lane < g;
-    const unsigned act = g >= 32 ? FULL : ((1u << g) - 1u);
+    const int sl = lane & (W - 1);
+    const int gsh = lane & ~(W - 1);  // first lane of the group
+    const unsigned WM = W == 32 ? FULL : ((1u << (W & 31)) - 1u);
+    auto seg = [&](unsigned b) { return W == 32 ? b : ((b >> gsh) & WM); };
+    const unsigned ltm = (1u << sl) - 1u;
+    ConsLane o;
+    o.keep_mask = 0, o.perc_identity = 0.0, o.ref_lineage = 0, o.nb = 0, o.nkept = 0, o.reached = 0, o.allowed = -1, o.level = 0;
+    o.mutated = false, o.single = false, o.ok = false, o.leader = false, o.keeps = false, o.bean_idx = 0, o.acc_idx = 0, o.acc_ref = 0;
+    o.bean.first_lineage = 0, o.bean.occurrences = 0, o.bean.acc_begin = 0, o.bean.n_acc = 0;
+    const bool on = valid && sl < g;
+    // ---- the rows as the tile kernel left them: the join (left_join on subject_taxid == taxid, mod.rs:72-76) ------------
     TopRow r;
     r.pident = 0.0, r.alnlen = 0, r.acc_off = 0, r.lin = 0, r.acc_len = 0, r.lin_len = 0;
-    uint32_t pos0 = 0;
-    uint32_t jerr = 0;
+    uint32_t pos0 = 0, jerr = 0;
     if (on) {
-        // the row as the tile kernel left it -- a reference into the text: fields 1..4 are split and parsed here (the row was
-        // validated by the tile kernel), then the join (left_join on subject_taxid == taxid, mod.rs:72-76) probes the taxid table
-        const TopRowRaw raw = p.toprows[slot + lane];
-        unsigned long long off = raw.acc_off;
-        if (raw.dec_frac == kTopRowUnparsed) {
-            // a row of unusual shape: split and parsed here by the full parser (acc_off / acc_len are the row's)
+        const TopRowRaw raw = p.toprows[slot + sl];
+        const unsigned long long off = raw.acc_off;
+        if (raw.dec_frac == kTopRowUnparsed)  // a row of unusual shape: split and parsed here by the full parser (acc_off / acc_len are the ROW's)
             jerr = off + (unsigned long long)raw.acc_len <= p.text_end ? heavy_parse_row(p.text + off, (int)raw.acc_len, off, T, r) : (uint32_t)DE_INTERNAL;
-        } else
+        else
             jerr = join_top_row(raw, T, r);
         if (jerr)
-            report(p.ctr, jerr, off);
+            report_soft(p.ctr, jerr, off);
         else
             pos0 = T.lin_off[r.lin];
     }
-    if (__any_sync(FULL, jerr != 0)) {
-        // (the run is over: the host reports the error; the record is emptied so that the gather / duplicate kernels that
-        // are already queued behind this one do not follow accession slots that were never filled)
-        if (lane == 0) rec->status = 0, rec->n_accessions = 0;
-        return;
-    }
-    if (g == 1) {
-        // single match (find_single_query_consensus.rs:74-150)
-        const uint32_t o = __shfl_sync(FULL, pos0, 0);
-        const int k = __shfl_sync(FULL, (int)r.lin_len, 0);
-        const double pid = __shfl_sync(FULL, r.pident, 0);
-        unsigned long long mask = 0;
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const int j = lane + 32 * h;
-            const bool in = j < k;
-            double c = 0.0;
-            if (in) c = T.cut[o + j];
-            mask |= (unsigned long long)__ballot_sync(FULL, in && pid >= c) << (32 * h);
-        }
-        if (lane == 0) {
-            if (!mask) {
-                report(p.ctr, DE_EMPTY_ADJUSTED, rec->query_off);
-                rec->status = 0;
-                return;
-            }
-            const int last = 63 - __clzll((long long)mask);
-            rec->keep_mask = mask;
-            rec->perc_identity = r.pident;
-            rec->ref_lineage = r.lin;
-            rec->n_beans = 1;
-            rec->n_accessions = 1;
-            rec->single_match = 1;
-            rec->mutated = 0;
-            rec->reached_pos = (int8_t)last;
-            rec->allowed_pos = -1;
-            rec->bean_level = (int8_t)last;
-            blu_bean b;
-            b.first_lineage = r.lin, b.occurrences = 1, b.acc_begin = 0, b.n_acc = 1;
-            p.beans[slot] = b;
-            blu_acc a;
-            a.off = r.acc_off, a.len = r.acc_len, a.pad = 0;
-            p.accs[slot] = a;
-            rec->status = 1;
-        }
-        return;
-    }
+    bool failed = seg(__ballot_sync(FULL, jerr != 0)) != 0;
+    const bool live = valid && !failed;
     // ---- first 16 accession bytes as big-endian keys ---------------------------------------------------------------
     unsigned long long k0 = 0, k1 = 0;
-    if (on) {
+    if (on && !failed && g > 1) {
         // five aligned words cover the 16 bytes at any alignment (the row goes on for >= 20 bytes behind saccver, so the
         // reads stay inside the text); realigned by funnel shifts, byte-swapped to big-endian, bytes beyond the accession zeroed
         const unsigned n = r.acc_len;
@@ -1665,199 +1869,413 @@ __global__ void __launch_bounds__(256) consensus_kernel(const ConsParams p) {
         if (n < 8) k0 = n > 0 ? (k0 & (~0ull << (8u * (8u - n)))) : 0ull;
     }
     // ---- S = stable sort by (lineage length, pident, align length, accession)   fmtc.rs:39-54 ----------------------
-    int rank = 0;
-    for (int j = 0; j < g; j++) {
-        const int len_j = __shfl_sync(FULL, (int)r.lin_len, j);
-        const double pid_j = __shfl_sync(FULL, r.pident, j);
-        const long long aln_j = __shfl_sync(FULL, (long long)r.alnlen, j);
-        const unsigned long long k0_j = __shfl_sync(FULL, k0, j), k1_j = __shfl_sync(FULL, k1, j);
-        const unsigned alen_j = __shfl_sync(FULL, (unsigned)r.acc_len, j);
-        const unsigned long long off_j = __shfl_sync(FULL, (unsigned long long)r.acc_off, j);
-        bool lt;
-        if (len_j != (int)r.lin_len)
-            lt = len_j < (int)r.lin_len;
-        else if (pid_j < r.pident)
-            lt = true;
-        else if (pid_j > r.pident)
-            lt = false;
-        else if (aln_j != (long long)r.alnlen)
-            lt = aln_j < (long long)r.alnlen;
-        else {
-            const int c = on ? cmp_acc(k0_j, k1_j, alen_j, off_j, k0, k1, r.acc_len, r.acc_off, p.text) : 0;
-            lt = c < 0 || (c == 0 && j < lane);
-        }
-        if (on && j != lane && lt) rank++;
+    int gmax = live ? g : 0;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        const int t = __shfl_xor_sync(FULL, gmax, d);
+        gmax = t > gmax ? t : gmax;
     }
-    // move row of rank s into lane s
-    int src = lane;
-    for (int j = 0; j < g; j++) {
-        const int rj = __shfl_sync(FULL, rank, j);
-        if (rj == lane) src = j;
-    }
-    r.pident = __shfl_sync(FULL, r.pident, src);
-    r.alnlen = __shfl_sync(FULL, (long long)r.alnlen, src);
-    r.acc_off = __shfl_sync(FULL, (unsigned long long)r.acc_off, src);
-    r.lin = __shfl_sync(FULL, r.lin, src);
-    r.acc_len = (uint16_t)__shfl_sync(FULL, (unsigned)r.acc_len, src);
-    r.lin_len = (uint16_t)__shfl_sync(FULL, (unsigned)r.lin_len, src);
-    pos0 = __shfl_sync(FULL, pos0, src);
-    k0 = __shfl_sync(FULL, k0, src);
-    k1 = __shfl_sync(FULL, k1, src);
-    // ---- reference row + level walk (fmtc.rs:60-63,137-214) ----------------------------------------------------------
-    const int ref_lane = p.strategy == BLU_STRATEGY_CAUTIOUS ? 0 : g - 1;
-    const int m = __shfl_sync(FULL, (int)r.lin_len, 0);  // shortest lineage
-    const uint32_t lin0 = __shfl_sync(FULL, r.lin, 0);
-    int diverge = -1;
-    if (__ballot_sync(FULL, on && r.lin != lin0)) {
-        for (int i = 0; i < m; i++) {
-            uint32_t key = 0;
-            if (on) key = T.lvl_key[pos0 + i];
-            const uint32_t key0 = __shfl_sync(FULL, key, 0);
-            if (__ballot_sync(FULL, on && key != key0)) {
-                diverge = i;
-                break;
+    if (gmax > 1) {
+        int rank = 0;
+        for (int j = 0; j < gmax; j++) {
+            const int len_j = __shfl_sync(FULL, (int)r.lin_len, j, W);
+            const double pid_j = __shfl_sync(FULL, r.pident, j, W);
+            const long long aln_j = __shfl_sync(FULL, (long long)r.alnlen, j, W);
+            const unsigned long long k0_j = __shfl_sync(FULL, k0, j, W), k1_j = __shfl_sync(FULL, k1, j, W);
+            const unsigned alen_j = __shfl_sync(FULL, (unsigned)r.acc_len, j, W);
+            const unsigned long long off_j = __shfl_sync(FULL, (unsigned long long)r.acc_off, j, W);
+            if (on && live && j < g && j != sl) {
+                bool lt;
+                if (len_j != (int)r.lin_len)
+                    lt = len_j < (int)r.lin_len;
+                else if (pid_j < r.pident)
+                    lt = true;
+                else if (pid_j > r.pident)
+                    lt = false;
+                else if (aln_j != (long long)r.alnlen)
+                    lt = aln_j < (long long)r.alnlen;
+                else {
+                    const int c = cmp_acc(k0_j, k1_j, alen_j, off_j, k0, k1, r.acc_len, r.acc_off, p.text);
+                    lt = c < 0 || (c == 0 && j < sl);
+                }
+                if (lt) rank++;
             }
         }
-    }
-    if (diverge == 0) {
-        if (lane == 0) {
-            report(p.ctr, DE_ROOT_DISAGREE, rec->query_off);
-            rec->status = 0;
+        // move the row of rank s into lane s
+        int src = sl;
+        for (int j = 0; j < gmax; j++) {
+            const int rj = __shfl_sync(FULL, rank, j, W);
+            if (on && live && j < g && rj == sl) src = j;
         }
-        return;
+        r.pident = __shfl_sync(FULL, r.pident, src, W);
+        r.alnlen = __shfl_sync(FULL, (long long)r.alnlen, src, W);
+        r.acc_off = __shfl_sync(FULL, (unsigned long long)r.acc_off, src, W);
+        r.lin = __shfl_sync(FULL, r.lin, src, W);
+        r.acc_len = (uint16_t)__shfl_sync(FULL, (unsigned)r.acc_len, src, W);
+        r.lin_len = (uint16_t)__shfl_sync(FULL, (unsigned)r.lin_len, src, W);
+        pos0 = __shfl_sync(FULL, pos0, src, W);
+        k0 = __shfl_sync(FULL, k0, src, W);
+        k1 = __shfl_sync(FULL, k1, src, W);
+    }
+    // ---- reference row + level walk (fmtc.rs:60-63,137-214) ----------------------------------------------------------
+    const int ref_lane = p.strategy == BLU_STRATEGY_CAUTIOUS ? 0 : (g > 0 ? g - 1 : 0);
+    const int m = __shfl_sync(FULL, (int)r.lin_len, 0, W);  // shortest lineage
+    const uint32_t lin0 = __shfl_sync(FULL, r.lin, 0, W);
+    const unsigned dm = seg(__ballot_sync(FULL, on && r.lin != lin0));
+    const bool differ = live && g > 1 && dm != 0;
+    int diverge = -1;
+    {
+        int mmax = differ ? m : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const int t = __shfl_xor_sync(FULL, mmax, d);
+            mmax = t > mmax ? t : mmax;
+        }
+        for (int i0 = 0; i0 < mmax; i0 += 4) {
+            // four levels at a time: the loads go out together, then the votes
+            uint32_t key[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) key[u] = (on && differ && diverge < 0 && i0 + u < m) ? T.lvl_key[pos0 + i0 + u] : 0u;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const uint32_t key0 = __shfl_sync(FULL, key[u], 0, W);
+                const bool mism = on && differ && i0 + u < m && key[u] != key0;
+                const unsigned bm = seg(__ballot_sync(FULL, mism));
+                if (bm && diverge < 0) diverge = i0 + u;
+            }
+            if (__all_sync(FULL, !differ || diverge >= 0)) break;
+        }
+    }
+    if (live && diverge == 0) {
+        if (sl == 0) report_soft(p.ctr, DE_ROOT_DISAGREE, query_off);
+        failed = true;
     }
     double identity;
     int idx, level;
     bool single;
-    const double ref_pid = __shfl_sync(FULL, r.pident, ref_lane);
-    if (diverge > 0) {
-        double mx = on ? r.pident : 0.0;  // fold from 0.0 (fmtc.rs:182-185)
-        if (!(mx > 0.0)) mx = 0.0;
+    const double ref_pid = __shfl_sync(FULL, r.pident, ref_lane, W);
+    double mxp = on ? r.pident : 0.0;  // max pident of the group, folded from 0.0 (fmtc.rs:182-185)
+    if (!(mxp > 0.0)) mxp = 0.0;
 #pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            const double o = __shfl_xor_sync(FULL, mx, d);
-            mx = o > mx ? o : mx;
-        }
-        identity = mx, idx = diverge - 1, level = diverge, single = false;
-    } else {
-        identity = ref_pid, idx = m - 1, level = m - 1, single = true;
+    for (int d = W / 2; d > 0; d >>= 1) {
+        const double t = __shfl_xor_sync(FULL, mxp, d);
+        mxp = t > mxp ? t : mxp;
     }
+    if (diverge > 0)
+        identity = mxp, idx = diverge - 1, level = diverge, single = false;
+    else
+        identity = ref_pid, idx = m - 1, level = m - 1, single = true;
+    const bool go = valid && !failed;
     // ---- fold beans at `level` in S order (consensus_result.rs:65-88) -----------------------------------------------
-    uint32_t bkey = 0xFFFFFF00u + (uint32_t)lane, irank = 0;
-    if (on) {
+    unsigned long long mkey = 0x8000000000000000ull | (unsigned long long)lane;  // lanes without a row match nobody
+    uint32_t bkey = 0, irank = 0;
+    if (on && go) {
         bkey = T.bean_key[pos0 + level];
         irank = T.ident_rank[pos0 + level];
+        mkey = ((unsigned long long)(gsh + 1) << 32) | (unsigned long long)bkey;
     }
-    const unsigned grp = __match_any_sync(FULL, bkey) & act;
-    const unsigned below = grp & ((1u << lane) - 1u);
-    const bool leader = on && below == 0;
+    const unsigned grp = seg(__match_any_sync(FULL, mkey));  // (relative to the group's first lane)
+    const unsigned below = grp & ltm;
+    const bool leader = on && go && below == 0;
     const int occ = __popc(grp);
     // Vec::dedup: an accession equal to its predecessor in the bean's S-ordered list is dropped
-    const int pl = below ? 31 - __clz(below) : lane;
-    const unsigned long long pk0 = __shfl_sync(FULL, k0, pl), pk1 = __shfl_sync(FULL, k1, pl);
-    const unsigned plen = __shfl_sync(FULL, (unsigned)r.acc_len, pl);
-    const unsigned long long poff = __shfl_sync(FULL, (unsigned long long)r.acc_off, pl);
+    const int pl = below ? 31 - __clz(below) : sl;
+    const unsigned long long pk0 = __shfl_sync(FULL, k0, pl, W), pk1 = __shfl_sync(FULL, k1, pl, W);
+    const unsigned plen = __shfl_sync(FULL, (unsigned)r.acc_len, pl, W);
+    const unsigned long long poff = __shfl_sync(FULL, (unsigned long long)r.acc_off, pl, W);
     bool dropped = false;
-    if (on && below) dropped = plen == r.acc_len && cmp_acc(pk0, pk1, plen, poff, k0, k1, r.acc_len, r.acc_off, p.text) == 0;
-    const unsigned kept = __ballot_sync(FULL, on && !dropped);
+    if (on && go && below) dropped = plen == r.acc_len && cmp_acc(pk0, pk1, plen, poff, k0, k1, r.acc_len, r.acc_off, p.text) == 0;
+    const unsigned kept = seg(__ballot_sync(FULL, on && go && !dropped));
     const int nacc_bean = __popc(grp & kept);
-    const int my_idx = __popc(grp & kept & ((1u << lane) - 1u));
+    const int my_idx = __popc(grp & kept & ltm);
     // sort beans: occurrences desc, identifier asc (bbci.rs:50-60); deterministic tie-break on the key id
-    const unsigned lm = __ballot_sync(FULL, leader);
+    const unsigned lm = seg(__ballot_sync(FULL, leader));
     int brank = 0, acc_begin = 0;
-    for (unsigned rest = lm; rest;) {
-        const int j = __ffs(rest) - 1;
-        rest &= rest - 1;
-        const int occ_j = __shfl_sync(FULL, occ, j);
-        const uint32_t ir_j = __shfl_sync(FULL, irank, j), bk_j = __shfl_sync(FULL, bkey, j);
-        const int na_j = __shfl_sync(FULL, nacc_bean, j);
-        if (leader && j != lane) {
-            const bool better = occ_j != occ ? occ_j > occ : (ir_j != irank ? ir_j < irank : bk_j < bkey);
-            if (better) {
-                brank++;
-                acc_begin += na_j;
+    {
+        int jmax = go ? g : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const int t = __shfl_xor_sync(FULL, jmax, d);
+            jmax = t > jmax ? t : jmax;
+        }
+        for (int j = 0; j < jmax; j++) {
+            const int occ_j = __shfl_sync(FULL, occ, j, W);
+            const uint32_t ir_j = __shfl_sync(FULL, irank, j, W), bk_j = __shfl_sync(FULL, bkey, j, W);
+            const int na_j = __shfl_sync(FULL, nacc_bean, j, W);
+            if (leader && ((lm >> j) & 1u) && j != sl) {
+                const bool better = occ_j != occ ? occ_j > occ : (ir_j != irank ? ir_j < irank : bk_j < bkey);
+                if (better) {
+                    brank++;
+                    acc_begin += na_j;
+                }
             }
         }
     }
-    if (leader) {
-        blu_bean b;
-        b.first_lineage = r.lin, b.occurrences = (uint32_t)occ, b.acc_begin = (uint32_t)acc_begin, b.n_acc = (uint32_t)nacc_bean;
-        p.beans[slot + brank] = b;
-    }
-    const int my_begin = __shfl_sync(FULL, acc_begin, grp ? __ffs(grp) - 1 : 0);
-    if (on && !dropped) {
-        blu_acc a;
-        a.off = r.acc_off, a.len = r.acc_len, a.pad = 0;
-        p.accs[slot + my_begin + my_idx] = a;
-    }
+    const int my_begin = __shfl_sync(FULL, acc_begin, grp ? __ffs(grp) - 1 : 0, W);
     const int nb = __popc(lm);
-    // ---- rank selection on the reference lineage (bbci.rs:22-37,66-95) -----------------------------------------------
-    const uint32_t ref_lin = __shfl_sync(FULL, r.lin, ref_lane);
-    const uint32_t ref_o = __shfl_sync(FULL, pos0, ref_lane);
-    const int ref_k = __shfl_sync(FULL, (int)r.lin_len, ref_lane);
-    warp_apply_cutoffs(T, ref_lin, ref_o, ref_k, identity, single && nb == 1, idx, rec, lane);
-    if (lane == 0) {
-        rec->perc_identity = ref_pid;
-        rec->n_beans = (uint32_t)nb;
-        rec->n_accessions = (uint32_t)__popc(kept);
-        rec->single_match = 0;
-        rec->bean_level = (int8_t)level;
-        rec->status = 1;
+    // ---- rank selection on the reference lineage (bbci.rs:22-37,66-95; single match: fsqc.rs:74-150), lanes = positions --
+    const uint32_t ref_lin = __shfl_sync(FULL, r.lin, ref_lane, W);
+    const uint32_t ref_o = __shfl_sync(FULL, pos0, ref_lane, W);
+    const int ref_k = __shfl_sync(FULL, (int)r.lin_len, ref_lane, W);
+    unsigned long long ge = 0, notgt = 0;
+    {
+        int kmax = go ? ref_k : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const int t = __shfl_xor_sync(FULL, kmax, d);
+            kmax = t > kmax ? t : kmax;
+        }
+        for (int j0 = 0; j0 < kmax; j0 += W) {
+            const int j = j0 + sl;
+            const bool in = go && j < ref_k;
+            double c = 0.0;
+            if (in) c = T.cut[ref_o + j];
+            const unsigned b_ge = seg(__ballot_sync(FULL, in && identity >= c));    // linnaean_ranks.rs:208
+            const unsigned b_ng = seg(__ballot_sync(FULL, in && !(identity > c)));  // linnaean_ranks.rs:188
+            ge |= (unsigned long long)b_ge << j0;
+            notgt |= (unsigned long long)b_ng << j0;
+        }
+    }
+    if (go && g == 1 && !ge) {
+        if (sl == 0) report_soft(p.ctr, DE_EMPTY_ADJUSTED, query_off);
+        failed = true;
+    }
+    o.ok = valid && !failed;
+    if (!o.ok) return o;
+    o.leader = leader;
+    o.keeps = on && !dropped;
+    o.bean.first_lineage = r.lin, o.bean.occurrences = (uint32_t)occ, o.bean.acc_begin = (uint32_t)acc_begin, o.bean.n_acc = (uint32_t)nacc_bean;
+    o.bean_idx = brank;
+    o.acc_idx = my_begin + my_idx;
+    o.acc_ref = (r.acc_off << 16) | (unsigned long long)r.acc_len;
+    o.nb = nb;
+    o.nkept = __popc(kept);
+    o.ref_lineage = ref_lin;
+    o.level = level;
+    if (g == 1) {
+        const int last = 63 - __clzll((long long)ge);
+        o.keep_mask = ge, o.perc_identity = ref_pid, o.single = true, o.mutated = false, o.reached = last, o.allowed = -1, o.level = last;
+    } else {
+        const int allowed = notgt ? (__ffsll((long long)notgt) - 1) : -1;
+        unsigned long long mask = ge;
+        if (!(single && nb == 1)) {
+            // keep the first idx+1 survivors: enumerate AFTER the filter, take_while(index <= bean_index)
+            unsigned long long mk = 0, rest = ge;
+            for (int n = 0; n <= idx && rest; n++) {
+                const unsigned long long low = rest & (~rest + 1);
+                mk |= low;
+                rest ^= low;
+            }
+            mask = mk;
+        }
+        const int last = mask ? 63 - __clzll((long long)mask) : -1;
+        o.keep_mask = mask, o.perc_identity = ref_pid, o.single = false, o.allowed = allowed, o.reached = last >= 0 ? last : idx;
+        o.mutated = sl == 0 && allowed >= 0 && T.rank_cls[ref_o + idx] != T.allowed_cls[ref_o + allowed];
+    }
+    return o;
+}
+
+__device__ __forceinline__ void cons_write(const PostParams& p, blu_record* rec, const ConsLane& o, bool lane0, unsigned long long bean_base,
+                                           unsigned long long acc_base, bool space_ok) {
+    if (o.ok && space_ok) {
+        if (o.leader) p.beans[bean_base + o.bean_idx] = o.bean;
+        if (o.keeps) p.accs[acc_base + o.acc_idx].ref = o.acc_ref;
+    }
+    if (lane0) {
+        if (o.ok && space_ok) {
+            rec->keep_mask = o.keep_mask;
+            rec->perc_identity = o.perc_identity;
+            rec->ref_lineage = o.ref_lineage;
+            rec->bean_base = (uint32_t)bean_base;
+            rec->n_beans = (uint32_t)o.nb;
+            rec->acc_base = (uint32_t)acc_base;
+            rec->single_match = o.single ? 1 : 0;
+            rec->mutated = o.mutated ? 1 : 0;
+            rec->reached_pos = (int8_t)o.reached;
+            rec->allowed_pos = (int8_t)o.allowed;
+            rec->bean_level = (int8_t)o.level;
+            rec->status = 1;
+        } else {
+            // a failed query keeps its id (the duplicate-id check must see it) and owns no beans / accession references
+            rec->bean_base = 0, rec->n_beans = 0, rec->acc_base = 0;
+            rec->status = 0;
+        }
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// gather: query ids + accessions -> string pool
-// ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) gather_kernel(const GatherParams p) {
-    __shared__ unsigned long long warp_tot[8];
-    __shared__ unsigned long long base_sh;
+__global__ void __launch_bounds__(kConsThreads) consensus_kernel(const __grid_constant__ PostParams p) {
+    __shared__ int cnt_b[kConsBatch], cnt_a[kConsBatch];
+    __shared__ unsigned long long base_b, base_a;
+    __shared__ int space_ok_sh;
+    const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned i = p.rec_begin + blockIdx.x * blockDim.x + tid;
-    const bool live = i < p.rec_end;
-    unsigned long long bytes = 0;
-    blu_record* rec = nullptr;
-    unsigned rows = 0;
-    if (live) {
-        rec = p.records + i;
-        rows = rec->n_rows;
-        bytes = rec->query_len;
-        for (unsigned a = 0; a < rec->n_accessions; a++) bytes += p.accs[rec->slot_base + a].len;
-    }
-    unsigned long long inc = bytes;
+    const int sub = lane >> 3, sl8 = lane & 7;
+    if (p.ctr->cap_overflow) return;  // the tile kernel ran out of space: the host grows the arrays and reruns
+    const unsigned long long rb = p.ctr->post_done;
+    unsigned long long re = p.ctr->rec_count;
+    if (re > p.rec_cap) re = p.rec_cap;
+    unsigned long long rows_sum = 0;
+    for (unsigned long long base = rb + (unsigned long long)blockIdx.x * kConsBatch; base < re; base += (unsigned long long)gridDim.x * kConsBatch) {
+        // ---- narrow pass: 8 lanes per query -----------------------------------------------------------------------------
+        const unsigned long long qi = base + (unsigned long long)(warp * 4 + sub);
+        blu_record* rec = p.records + qi;
+        bool todo = false;
+        int g = 0;
+        unsigned long long slot = 0, qoff = 0;
+        if (qi < re) {
+            // (all eight lanes read the header: one sector)
+            const uint32_t st = rec->status;
+            if (sl8 == 0) rows_sum += rec->n_rows;
+            if (st == 2) {
+                todo = true;
+                g = (int)rec->n_beans;
+                slot = rec->bean_base;
+                qoff = rec->query_off;
+                if (slot + (unsigned long long)g > p.slot_cap) todo = false, g = 0;  // (cannot happen without cap_overflow)
+            }
+        }
+        const bool narrow = todo && g >= 1 && g <= 8;
+        const ConsLane o = cons_compute<8>(p, narrow, g, slot, qoff, lane);
+        if (sl8 == 0) {
+            cnt_b[warp * 4 + sub] = o.ok ? o.nb : 0;
+            cnt_a[warp * 4 + sub] = o.ok ? o.nkept : 0;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            const int vb = cnt_b[lane], va = cnt_a[lane];
+            int ib = vb, ia = va;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        unsigned long long t = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += t;
+            for (int d = 1; d < 32; d <<= 1) {
+                const int tb = __shfl_up_sync(FULL, ib, d), ta = __shfl_up_sync(FULL, ia, d);
+                if (lane >= d) ib += tb, ia += ta;
+            }
+            cnt_b[lane] = ib - vb;
+            cnt_a[lane] = ia - va;
+            if (lane == 31) {
+                const unsigned long long bb = ib ? atomicAdd(&p.ctr->bean_used, (unsigned long long)ib) : 0ull;
+                const unsigned long long ab = ia ? atomicAdd(&p.ctr->acc_used, (unsigned long long)ia) : 0ull;
+                base_b = bb, base_a = ab;
+                const bool fits = bb + (unsigned long long)ib <= p.bean_cap && ab + (unsigned long long)ia <= p.acc_cap;
+                space_ok_sh = fits ? 1 : 0;
+                if (!fits) p.ctr->cap_overflow = 1;
+            }
+        }
+        __syncthreads();
+        if (narrow) cons_write(p, rec, o, sl8 == 0, base_b + (unsigned long long)cnt_b[warp * 4 + sub], base_a + (unsigned long long)cnt_a[warp * 4 + sub], space_ok_sh != 0);
+        // ---- wide pass: top groups of 9..32 rows, one query per warp ------------------------------------------------------
+        unsigned wide = __ballot_sync(FULL, sl8 == 0 && todo && g > 8);
+        while (wide) {
+            const int src = __ffs(wide) - 1;
+            wide &= wide - 1;
+            const int gw = __shfl_sync(FULL, g, src);
+            const unsigned long long slotw = __shfl_sync(FULL, slot, src), qoffw = __shfl_sync(FULL, qoff, src);
+            const unsigned long long qiw = base + (unsigned long long)(warp * 4 + (src >> 3));
+            blu_record* recw = p.records + qiw;
+            if (gw > 32) {
+                if (lane == 0) {
+                    report(p.ctr, DE_INTERNAL, qoffw);
+                    recw->status = 0, recw->n_beans = 0;
+                }
+                continue;
+            }
+            const ConsLane ow = cons_compute<32>(p, true, gw, slotw, qoffw, lane);
+            unsigned long long bb = 0, ab = 0;
+            int fits = 1;
+            if (lane == 0 && ow.ok) {
+                bb = atomicAdd(&p.ctr->bean_used, (unsigned long long)ow.nb);
+                ab = atomicAdd(&p.ctr->acc_used, (unsigned long long)ow.nkept);
+                fits = bb + (unsigned long long)ow.nb <= p.bean_cap && ab + (unsigned long long)ow.nkept <= p.acc_cap;
+                if (!fits) p.ctr->cap_overflow = 1;
+            }
+            bb = __shfl_sync(FULL, bb, 0), ab = __shfl_sync(FULL, ab, 0), fits = __shfl_sync(FULL, fits, 0);
+            cons_write(p, recw, ow, lane == 0, bb, ab, fits != 0);
+        }
+        __syncthreads();  // cnt_* / base_* are rewritten by the next iteration
     }
-    if (lane == 31) warp_tot[warp] = inc;
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) rows += __shfl_xor_sync(0xffffffffu, rows, d);
-    if (lane == 0 && rows) atomicAdd(&p.ctr->n_rows, (unsigned long long)rows);
-    __syncthreads();
-    unsigned long long before = 0, total = 0;
-    for (int k = 0; k < 8; k++) {
-        if (k < warp) before += warp_tot[k];
-        total += warp_tot[k];
-    }
-    if (tid == 0) base_sh = total ? atomicAdd(&p.ctr->pool_used, total) : 0ull;
-    __syncthreads();
-    if (!live) return;
-    unsigned long long o = base_sh + before + inc - bytes;
-    if (base_sh + total > p.pool_cap) {
-        p.ctr->cap_overflow = 1;
-        return;
-    }
-    const uint8_t* src = p.text + rec->query_off;
-    for (unsigned k = 0; k < rec->query_len; k++) p.pool[o + k] = src[k];
-    rec->query_off = o;
-    o += rec->query_len;
-    for (unsigned a = 0; a < rec->n_accessions; a++) {
-        blu_acc& ac = p.accs[rec->slot_base + a];
-        const uint8_t* sa = p.text + ac.off;
-        for (unsigned k = 0; k < ac.len; k++) p.pool[o + k] = sa[k];
-        ac.off = o;
-        o += ac.len;
+    for (int d = 16; d > 0; d >>= 1) rows_sum += __shfl_xor_sync(FULL, rows_sum, d);
+    if (lane == 0 && rows_sum) atomicAdd(&p.ctr->n_rows, rows_sum);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// gather: query ids + accessions -> string pool (only for results that leave the device without their text)
+//   One warp per 32 records: lane = record for the lengths (a warp scan places the 32 records' strings back to back, one
+//   atomic reserves the pool space), then the whole warp copies string after string, a byte per lane: reads and writes
+//   of one string are one or two sectors instead of a byte-per-thread scatter.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ PostParams p) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    if (p.ctr->cap_overflow) return;
+    const unsigned long long rb = p.ctr->post_done;
+    unsigned long long re = p.ctr->rec_count;
+    if (re > p.rec_cap) re = p.rec_cap;
+    const unsigned long long wstride = (unsigned long long)gridDim.x * (blockDim.x >> 5) * 32ull;
+    for (unsigned long long base = rb + ((unsigned long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32ull; base < re; base += wstride) {
+        const unsigned long long i = base + lane;
+        const bool live = i < re;
+        blu_record* rec = p.records + i;
+        unsigned long long bytes = 0, qoff = 0, abase = 0;
+        uint32_t qlen = 0, nacc = 0;
+        if (live) {
+            qoff = rec->query_off, qlen = rec->query_len;
+            bytes = qlen;
+            if (rec->status == 1) {
+                abase = rec->acc_base;
+                const uint32_t nbn = rec->n_beans;
+                if (nbn) {
+                    const blu_bean lb = p.beans[(unsigned long long)rec->bean_base + nbn - 1];
+                    nacc = lb.acc_begin + lb.n_acc;  // the last bean's list ends the record's accession references
+                }
+                // (beans are stored in output order, their lists back to back: acc_begin is increasing)
+                for (uint32_t a = 0; a < nacc; a++) bytes += (uint32_t)(p.accs[abase + a].ref & 0xFFFFull);
+            }
+        }
+        unsigned long long inc = bytes;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t = __shfl_up_sync(FULL, inc, d);
+            if (lane >= d) inc += t;
+        }
+        const unsigned long long total = __shfl_sync(FULL, inc, 31);
+        unsigned long long wbase = 0;
+        if (lane == 31 && total) wbase = atomicAdd(&p.ctr->pool_used, total);
+        wbase = __shfl_sync(FULL, wbase, 31);
+        if (!p.pool) continue;  // counting pass: pool_used ends up as the size the pool needs
+        if (wbase + total > p.pool_cap) {
+            if (lane == 0) p.ctr->cap_overflow = 1;
+            continue;
+        }
+        const unsigned long long mine = wbase + inc - bytes;  // where this lane's record's strings start
+        // ---- copy, string by string, the whole warp on each --------------------------------------------------------------
+        uint32_t namax = nacc;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const uint32_t t = __shfl_xor_sync(FULL, namax, d);
+            namax = t > namax ? t : namax;
+        }
+        unsigned long long cur = mine;
+        for (int rr = 0; rr < 32; rr++) {
+            const unsigned long long so = __shfl_sync(FULL, qoff, rr), dst = __shfl_sync(FULL, cur, rr);
+            const uint32_t n = __shfl_sync(FULL, qlen, rr);
+            for (uint32_t k = lane; k < n; k += 32) p.pool[dst + k] = p.text[so + k];
+        }
+        if (live) rec->query_off = mine;
+        cur += qlen;
+        for (uint32_t a = 0; a < namax; a++) {
+            unsigned long long ref = 0;
+            if (a < nacc) ref = p.accs[abase + a].ref;
+            for (int rr = 0; rr < 32; rr++) {
+                const unsigned long long rf = __shfl_sync(FULL, ref, rr), dst = __shfl_sync(FULL, cur, rr);
+                const uint32_t n = (uint32_t)(rf & 0xFFFFull);
+                const unsigned long long so = rf >> 16;
+                for (uint32_t k = lane; k < n; k += 32) p.pool[dst + k] = p.text[so + k];
+            }
+            if (a < nacc) {
+                p.accs[abase + a].ref = (cur << 16) | (ref & 0xFFFFull);
+                cur += (uint32_t)(ref & 0xFFFFull);
+            }
+        }
     }
 }
 
@@ -1865,31 +2283,79 @@ __global__ void __launch_bounds__(256) gather_kernel(const GatherParams p) {
 // duplicate query detection (reference groups by a HashMap<String,_>, mod.rs:145,192: rows of one query need
 // not be contiguous).  A repeated id means the fast contiguous path is not applicable.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) dup_kernel(const DupParams p) {
-    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= p.n_rec) return;
-    const blu_record& r = p.records[i];
-    // (this kernel is queued behind the gather pass before the host has looked at its overflow flag: when the string pool
-    // was too small the ids were not moved and query_off still is a text offset)
-    if (r.query_off + (unsigned long long)r.query_len > p.pool_cap) return;
-    unsigned long long h = 0xcbf29ce484222325ull;
-    const uint8_t* q = p.pool + r.query_off;
-    for (unsigned k = 0; k < r.query_len; k++) {
-        h ^= q[k];
-        h *= 0x100000001b3ull;
-    }
-    h = mix64(h ^ r.query_len);
-    if (h == 0) h = 1;
-    unsigned slot = (unsigned)h & p.mask;
-    for (unsigned n = 0; n <= p.mask; n++) {
-        unsigned long long old = atomicCAS(p.table + slot, 0ull, h);
-        if (old == 0ull) return;
-        if (old == h) {
-            p.ctr->dup_found = 1;
-            return;
+__global__ void __launch_bounds__(256) dup_kernel(const __grid_constant__ DupParams p) {
+    if (p.ctr->cap_overflow) return;
+    const unsigned long long rb = p.ctr->post_done;
+    unsigned long long n = p.ctr->rec_count;
+    if (n > p.rec_cap) n = p.rec_cap;
+    for (unsigned long long i = rb + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        blu_record& r = p.records[i];
+        if (r.query_off + (unsigned long long)r.query_len > p.strings_len) continue;  // (a gather pass that overflowed: the host reruns)
+        unsigned long long h = 0xcbf29ce484222325ull;
+        const uint8_t* q = p.strings + r.query_off;
+        for (unsigned k = 0; k < r.query_len; k++) {
+            h ^= q[k];
+            h *= 0x100000001b3ull;
         }
-        slot = (slot + 1) & p.mask;
+        h = mix64(h ^ r.query_len);
+        if (h == 0) h = 1;
+        if (p.hashes) p.hashes[i] = h;
+        unsigned slot = (unsigned)h & p.mask;
+        for (unsigned t = 0; t <= p.mask; t++) {
+            const unsigned long long old = atomicCAS(p.table + slot, 0ull, h);
+            if (old == 0ull) break;
+            if (old == h) {
+                p.ctr->dup_found = 1;
+                break;
+            }
+            slot = (slot + 1) & p.mask;
+        }
+        if (p.ref_delta) {
+            r.query_off = (unsigned long long)((long long)r.query_off + p.ref_delta);
+            if (r.status == 1 && r.n_beans) {
+                const blu_bean lb = p.beans[(unsigned long long)r.bean_base + r.n_beans - 1];
+                const unsigned nacc = lb.acc_begin + lb.n_acc;
+                for (unsigned a = 0; a < nacc; a++) {
+                    blu_acc& ac = p.accs[(unsigned long long)r.acc_base + a];
+                    ac.ref = (unsigned long long)((long long)ac.ref + p.ref_delta * 65536);
+                }
+            }
+        }
     }
+}
+
+// Cross-device duplicate check of a multi-GPU run: the id hashes of all shards, inserted into one table.
+__global__ void __launch_bounds__(256) dup_merge_kernel(const unsigned long long* hashes, unsigned long long n, unsigned long long* table, uint32_t mask,
+                                                        unsigned int* dup_found) {
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long h = hashes[i];
+        unsigned slot = (unsigned)h & mask;
+        for (unsigned t = 0; t <= mask; t++) {
+            const unsigned long long old = atomicCAS(table + slot, 0ull, h);
+            if (old == 0ull) break;
+            if (old == h) {
+                *dup_found = 1;
+                break;
+            }
+            slot = (slot + 1) & mask;
+        }
+    }
+}
+
+// End of a range / chunk (one thread): see AdvanceParams.
+__global__ void advance_kernel(const AdvanceParams p) {
+    Counters* c = p.ctr;
+    unsigned long long n = c->rec_count;
+    if (n > p.rec_cap) n = p.rec_cap;
+    c->post_done = n;
+    c->next_begin = c->tail_start != ~0ull ? c->tail_start : p.range_end;
+    if (p.snapshot) {
+        *p.snapshot = *c;
+        __threadfence_system();
+    }
+    c->n_defer = 0;
+    c->work_ticket = 0;
+    c->tail_start = ~0ull;
 }
 
 }  // namespace
@@ -1919,24 +2385,32 @@ cudaError_t launch_longrun_kernel(const RunParams& p, int grid, cudaStream_t s) 
     return cudaGetLastError();
 }
 
-cudaError_t launch_consensus_kernel(const ConsParams& p, cudaStream_t s) {
-    if (p.rec_end <= p.rec_begin) return cudaSuccess;
-    const unsigned n = p.rec_end - p.rec_begin;  // one warp per record; two per CTA: the warps of a CTA finish at very different
-                                                 // times (top groups of 1..32 rows), and a slot is only refilled when its whole CTA is gone
-    consensus_kernel<<<(n + 1) / 2, 64, 0, s>>>(p);
+// The post-pass kernels take their record range from the device counters (no host round trip between the tile kernel
+// and them): fixed grids, grid-stride loops.
+cudaError_t launch_consensus_kernel(const PostParams& p, int sms, cudaStream_t s) {
+    consensus_kernel<<<sms * 8, kConsThreads, 0, s>>>(p);
     return cudaGetLastError();
 }
 
-cudaError_t launch_gather_kernel(const GatherParams& p, cudaStream_t s) {
-    if (p.rec_end <= p.rec_begin) return cudaSuccess;
-    unsigned n = p.rec_end - p.rec_begin;
-    gather_kernel<<<(n + 255) / 256, 256, 0, s>>>(p);
+cudaError_t launch_gather_kernel(const PostParams& p, int sms, cudaStream_t s) {
+    gather_kernel<<<sms * 8, 256, 0, s>>>(p);
     return cudaGetLastError();
 }
 
-cudaError_t launch_dup_kernel(const DupParams& p, cudaStream_t s) {
-    if (p.n_rec == 0) return cudaSuccess;
-    dup_kernel<<<(p.n_rec + 255) / 256, 256, 0, s>>>(p);
+cudaError_t launch_dup_kernel(const DupParams& p, int sms, cudaStream_t s) {
+    dup_kernel<<<sms * 8, 256, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dup_merge_kernel(const unsigned long long* hashes, unsigned long long n, unsigned long long* table, uint32_t mask,
+                                    unsigned int* dup_found, int sms, cudaStream_t s) {
+    if (!n) return cudaSuccess;
+    dup_merge_kernel<<<sms * 8, 256, 0, s>>>(hashes, n, table, mask, dup_found);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_advance_kernel(const AdvanceParams& p, cudaStream_t s) {
+    advance_kernel<<<1, 1, 0, s>>>(p);
     return cudaGetLastError();
 }
 

@@ -7,20 +7,33 @@
 
 namespace blu {
 
-// Device-side counters of one run (zeroed by the host before the first chunk).
+// Device-side counters of one run (zeroed by the host before the first chunk).  Every cursor is its own 64-bit word:
+// a reservation that overflows its capacity can never carry into a neighbouring count.
 struct Counters {
-    unsigned long long rec_slots;  // packed reservation counter: records << 32 | top-row slots
-    unsigned int n_defer;      // deferred runs of the current chunk
-    unsigned int err_code;     // first DevErr
-    unsigned long long err_off;    // byte offset (in the current device buffer) of the first error
-    unsigned long long tail_start; // !final chunks: start of the last (unfinished) run
-    unsigned long long pool_used;  // bytes of the string pool in use
-    unsigned int dup_found;    // a query id occurs in two separate runs
-    unsigned int cap_overflow; // some output capacity was exceeded (host grows and retries)
-    unsigned int work_ticket;  // dynamic work distribution of the long-run kernel
+    unsigned long long rec_count;   // record headers reserved by the tile / long-run kernels (dense)
+    unsigned long long slot_count;  // top-row slots reserved (CTA slabs: holes are allowed, the array is never downloaded)
+    unsigned long long bean_used;   // compact output cursors of the post-pass: beans, accession references, string pool
+    unsigned long long acc_used;
+    unsigned long long pool_used;
+    unsigned long long post_done;   // records [0, post_done) have been through the post-pass (consensus / gather)
+    unsigned long long next_begin;  // resident tables processed in ranges: where the next range starts
+    unsigned long long err_off;     // byte offset (in the current device buffer) of the first fatal error
+    unsigned long long soft_off;    // ... of the first consensus-class error
+    unsigned long long tail_start;  // !final chunks: start of the last (unfinished) run
+    unsigned long long n_rows;      // hit rows of the finished queries
+    unsigned int n_defer;       // deferred runs of the current chunk
+    unsigned int work_ticket;   // dynamic work distribution of the long-run kernel
+    unsigned int err_code;      // first grammar-class DevErr: the reference fails on such a row wherever it sits
+    unsigned int soft_code;     // first consensus-class DevErr (join / lineage / root disagreement / empty adjusted taxonomy):
+                                // fatal only once the table is known to be contiguous -- a fragment of a scattered query may
+                                // hit it although the merged query would not (the reference only parses the top group's rows)
+    unsigned int dup_found;     // a query id occurs in two separate runs
+    unsigned int cap_overflow;  // some output capacity was exceeded (host grows and retries)
+    unsigned int big_busy;      // (reserved)
     unsigned int pad;
-    unsigned long long n_rows; // hit rows of the finished queries (summed by the gather kernel)
 };
+
+constexpr uint64_t kBeginFromCounters = ~0ull;  // RunParams.begin: take the start of the range from Counters.next_begin
 
 struct RunParams {
     const uint8_t* text;   // device buffer (16-byte aligned, padded to a multiple of 128 bytes)
@@ -29,48 +42,64 @@ struct RunParams {
     int strategy;
     LinTables T;
     blu_record* records;
-    uint32_t rec_cap;
-    blu_bean* beans;
-    blu_acc* accs;
+    uint64_t rec_cap;
     TopRowRaw* toprows;    // top bit-score rows of every query (fields 1..4 folded to integers, or unparsed references;
                            // lineage not joined yet), slot-indexed
-    uint32_t slot_cap;
+    uint64_t slot_cap;
+    blu_bean* beans;       // compact outputs (the long-run kernel finishes its queries itself)
+    uint64_t bean_cap;
+    blu_acc* accs;
+    uint64_t acc_cap;
     uint64_t* defer;       // (offset << 1) | check_prev
     uint32_t defer_cap;
+    TopRow* big_rows;      // scratch of the long-run kernel: kLongTopCap joined top rows per CTA
+    unsigned long long* big_cand;  // ... and as many candidate references (offset << 16 | length)
     Counters* ctr;
 };
 
-struct ConsParams {
+// Post-pass over the records the tile kernel produced since the last post-pass: [ctr->post_done, ctr->rec_count).
+struct PostParams {
     blu_record* records;
-    uint32_t rec_begin, rec_end;
+    uint64_t rec_cap;
     const TopRowRaw* toprows;
-    uint64_t text_end;     // valid text is [0, text_end) of `text` (references beyond it are an internal error)
+    uint64_t slot_cap;
     blu_bean* beans;
+    uint64_t bean_cap;
     blu_acc* accs;
+    uint64_t acc_cap;
     const uint8_t* text;
+    uint64_t text_end;     // valid text is [0, text_end) of `text` (references beyond it are an internal error)
+    uint8_t* pool;         // string pool (gather kernel); nullptr: strings stay references into `text`
+    uint64_t pool_cap;
     LinTables T;
     int strategy;
     Counters* ctr;
 };
 
-struct GatherParams {
-    const uint8_t* text;
+// Duplicate-id check of the records produced since the last post-pass, [ctr->post_done, ctr->rec_count): their 64-bit id
+// hashes go into one open-addressing table that lives for the whole run.  The same pass relocates string references
+// that have to leave the device as offsets into the caller's host text (ref_delta != 0).
+struct DupParams {
     blu_record* records;
+    uint64_t rec_cap;
+    const blu_bean* beans;
     blu_acc* accs;
-    uint32_t rec_begin, rec_end;  // records produced by the current chunk
-    uint8_t* pool;
-    uint64_t pool_cap;
+    const uint8_t* strings;     // what blu_record.query_off refers to: the string pool, or the text when nothing was gathered
+    uint64_t strings_len;
+    unsigned long long* table;  // open addressing, 0 = empty
+    uint32_t mask;
+    unsigned long long* hashes; // optional: the 64-bit id hash of every record (multi-device runs merge them), or nullptr
+    long long ref_delta;        // added to every string offset after hashing (device-buffer -> caller's text coordinates)
     Counters* ctr;
 };
 
-struct DupParams {
-    const blu_record* records;
-    uint32_t n_rec;
-    const uint8_t* pool;
-    uint64_t pool_cap;          // bytes of `pool` (ids outside it: the gather pass overflowed, the host reruns with a larger pool)
-    unsigned long long* table;  // open addressing, 0 = empty
-    uint32_t mask;
+// End of a range / chunk: post_done <- rec_count, the per-range counters are reset (next_begin <- tail_start or range_end)
+// and the counters are copied to `snapshot` (mapped pinned host memory or device memory; may be nullptr).
+struct AdvanceParams {
     Counters* ctr;
+    uint64_t rec_cap;
+    uint64_t range_end;
+    Counters* snapshot;
 };
 
 // Geometry of the streaming tile kernel: every CTA walks one contiguous segment of the text in
@@ -93,9 +122,13 @@ constexpr int kWin = 60416;             // window of the block path (long-run ke
 int tile_kernel_grid(int device);
 cudaError_t launch_tile_kernel(const RunParams& p, int grid, cudaStream_t s);
 cudaError_t launch_longrun_kernel(const RunParams& p, int grid, cudaStream_t s);
-cudaError_t launch_consensus_kernel(const ConsParams& p, cudaStream_t s);
-cudaError_t launch_gather_kernel(const GatherParams& p, cudaStream_t s);
-cudaError_t launch_dup_kernel(const DupParams& p, cudaStream_t s);
+cudaError_t launch_consensus_kernel(const PostParams& p, int sms, cudaStream_t s);
+cudaError_t launch_gather_kernel(const PostParams& p, int sms, cudaStream_t s);
+cudaError_t launch_dup_kernel(const DupParams& p, int sms, cudaStream_t s);
+cudaError_t launch_advance_kernel(const AdvanceParams& p, cudaStream_t s);
+cudaError_t launch_dup_merge_kernel(const unsigned long long* hashes, unsigned long long n, unsigned long long* table, uint32_t mask,
+                                    unsigned int* dup_found, int sms, cudaStream_t s);
+constexpr int kLongTopCap = 8192;       // largest top bit-score group the block path handles (beyond: BLU_ERR_UNSUPPORTED)
 cudaError_t kernels_set_attributes();
 
 }  // namespace blu

@@ -42,15 +42,22 @@ class SynthWorkload:
         rc = self._l.blu_synth_hits(self._h, q_begin, n_queries, 1 if zipf else 0, hits, threads or (os.cpu_count() or 1), dst_ptr, cap,
                                     C.byref(ln), C.byref(nr))
         if rc == 2:
-            raise MemoryError(f"buffer too small: need {ln.value} bytes")
+            e = MemoryError(f"buffer too small: need {ln.value} bytes")
+            e.needed = ln.value
+            raise e
         if rc:
             raise RuntimeError("blu_synth_hits failed")
         return ln.value, nr.value
 
     def hits(self, q_begin: int, n_queries: int, hits: int, zipf: bool = False, threads: Optional[int] = None) -> bytes:
-        cap = n_queries * hits * 96 + 4096
+        cap = n_queries * (hits if not zipf else min(hits, 600)) * 96 + 4096
         buf = C.create_string_buffer(cap)
-        n, _ = self.hits_into(C.addressof(buf), cap, q_begin, n_queries, hits, zipf, threads)
+        try:
+            n, _ = self.hits_into(C.addressof(buf), cap, q_begin, n_queries, hits, zipf, threads)
+        except MemoryError as e:  # (Zipf tables: the size is only known once generated)
+            cap = int(getattr(e, "needed", 0)) + 4096
+            buf = C.create_string_buffer(cap)
+            n, _ = self.hits_into(C.addressof(buf), cap, q_begin, n_queries, hits, zipf, threads)
         return buf.raw[:n]
 
     def close(self):

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define BLU_ABI_VERSION 1
+#define BLU_ABI_VERSION 2
 
 /* Status codes.  The reference distinguishes `Err(MappedErrors)` (I/O-class: mod.rs:250-265,357-364) from
  * panics (every data-dependent failure: mod.rs:123,174-184,371; find_single_query_consensus.rs:59,115;
@@ -47,9 +47,14 @@ enum { BLU_FORMAT_JSON = 0, BLU_FORMAT_JSONL = 1, BLU_FORMAT_YAML = 2 };
 
 #define BLU_CUTOFF_ABSENT ((int32_t)-2147483647 - 1) /* Option::None of CustomTaxon's optional i16 fields */
 
+/* blu_opts.flags */
+#define BLU_OPT_TEXT_REFS 1u /* blu_consensus_run_host: query ids / accessions of the result stay (offset, length) references into
+                                the CALLER's text instead of being copied into a string pool (SURVEY 8b "Ownership"): nothing but
+                                records, beans and 8-byte accession references is downloaded.  The text must outlive the result. */
+
 /* The by-value arguments of build_consensus_identities (mod.rs:40-47) other than the two paths. */
 typedef struct blu_opts {
-    int32_t device;     /* CUDA device ordinal this context runs on */
+    int32_t device;     /* CUDA device ordinal this context runs on (blu_ctx_create_multi: ignored) */
     int32_t taxon;      /* BLU_TAXON_* */
     int32_t strategy;   /* BLU_STRATEGY_* */
     int32_t use_taxid;  /* Option<bool>: 1 -> numericLineage, 0 -> textLineage (mod.rs:287-291) */
@@ -57,25 +62,29 @@ typedef struct blu_opts {
     int32_t custom[8];  /* domain,kingdom,phylum,class,order,family,genus,species (taxon.rs:14-25); i16 range or
                            BLU_CUTOFF_ABSENT for the six optional ones */
     uint64_t chunk_bytes; /* streaming chunk for host input; 0 = default (256 MiB) */
-    uint64_t reserved[4];
+    uint64_t flags;       /* BLU_OPT_* */
+    uint64_t reserved[3];
 } blu_opts;
 
 typedef struct blu_ctx blu_ctx;
 typedef struct blu_result blu_result;
 
 /* Fixed-size consensus record, one per query, as produced on the device.
- * Strings live in the result's pool; lineage-derived strings are resolved through the context's taxonomy. */
+ * Strings are (offset, length) references into the result's string base (blu_result_pool: the string pool, or the
+ * caller's text with BLU_OPT_TEXT_REFS / device-resident results); lineage-derived strings are resolved through the
+ * context's taxonomy.  Beans and accession references are stored compactly (no holes): the beans of a record are
+ * beans[bean_base .. bean_base + n_beans), its accession references accessions[acc_base ..), bean by bean. */
 typedef struct blu_record {
-    uint64_t query_off;     /* offset of the query id in the string pool */
+    uint64_t query_off;     /* offset of the query id in the string base */
     uint32_t query_len;
     uint32_t n_rows;        /* hit rows of this query */
     uint64_t keep_mask;     /* bit j set: reference-lineage position j is part of the output `taxonomy` */
     double perc_identity;   /* TaxonomyBean.perc_identity, bit-for-bit the reference row's pident */
     int64_t bit_score;      /* truncated bit score (mod.rs:162,184); serialised as f64 */
     uint32_t ref_lineage;   /* index of the reference lineage in the loaded taxonomy */
-    uint32_t slot_base;     /* first bean / accession slot of this query */
+    uint32_t bean_base;     /* first bean of this query */
     uint32_t n_beans;
-    uint32_t n_accessions;
+    uint32_t acc_base;      /* first accession reference of this query */
     uint8_t status;         /* 1 = ConsensusFound; 0 = NoConsensusFound (hit-less header) */
     uint8_t single_match;
     uint8_t mutated;
@@ -88,15 +97,16 @@ typedef struct blu_record {
 typedef struct blu_bean {
     uint32_t first_lineage; /* lineage of the first (sorted) row carrying this bean: its `taxonomy` string */
     uint32_t occurrences;
-    uint32_t acc_begin;     /* relative to the record's slot_base */
+    uint32_t acc_begin;     /* relative to the record's acc_base */
     uint32_t n_acc;
 } blu_bean;
 
+/* accession reference: offset << 16 | length (an accession is at most 65535 bytes) */
 typedef struct blu_acc {
-    uint64_t off; /* offset in the string pool */
-    uint32_t len;
-    uint32_t pad;
+    uint64_t ref;
 } blu_acc;
+#define BLU_ACC_OFF(a) ((a).ref >> 16)
+#define BLU_ACC_LEN(a) ((uint32_t)((a).ref & 0xFFFFu))
 
 /* Stage timings of the last run (CUDA events, milliseconds) and byte counts, for bench.py's roofline. */
 typedef struct blu_timings {
@@ -115,6 +125,15 @@ typedef struct blu_timings {
 
 /* ---- context ------------------------------------------------------------------------------------------- */
 int blu_ctx_create(const blu_opts* opts, blu_ctx** out);
+/* One context over several GPUs of one box -- the reference's entry point consumes ONE hit table (mod.rs:40-47) and
+ * fans its queries out (mod.rs:104-128); here the table is sharded by query range over `n_devices` GPUs:
+ * blu_shard_cuts, one host worker thread + its own streams per GPU, lineage tables replicated, every GPU's result
+ * downloaded into its own part of ONE blu_result; no collective, no NCCL.  Every entry point that takes a blu_ctx
+ * accepts such a context (blu_consensus_run_device / _resident need a single-device one); opts->device is ignored.
+ * A table whose queries are not contiguous is detected across the shards (the 64-bit query-id hashes of all shards
+ * are merged on the first device) and regrouped like on one GPU. */
+int blu_ctx_create_multi(const blu_opts* opts, const int* devices, int n_devices, blu_ctx** out);
+int blu_ctx_num_devices(const blu_ctx* ctx);
 void blu_ctx_destroy(blu_ctx* ctx);
 /* Message of the last failing call on this context (or of the failing blu_ctx_create when ctx == NULL). */
 const char* blu_last_error(const blu_ctx* ctx);
@@ -139,6 +158,15 @@ int blu_consensus_run_host(blu_ctx* ctx, const char* text, uint64_t n_bytes, blu
 /* Text already resident in device memory of ctx's device.  `dtext` must be 16-byte aligned and readable up to
  * n_bytes rounded up to 128.  `stream` is a cudaStream_t (NULL = the context's own stream). */
 int blu_consensus_run_device(blu_ctx* ctx, const void* dtext, uint64_t n_bytes, void* stream, blu_result** out);
+/* Same, but the result stays in device memory ("text already in HBM -> records in HBM"): nothing but the
+ * counters crosses PCIe, strings stay (offset, length) references into `dtext`, no host round trip inside the call.
+ * blu_result_device_* give the device arrays; blu_result_download() brings them (and the referenced strings) to the
+ * host, after which every host-side accessor / writer works on the result.  `dtext` must stay valid until then. */
+int blu_consensus_run_device_resident(blu_ctx* ctx, const void* dtext, uint64_t n_bytes, void* stream, blu_result** out);
+const blu_record* blu_result_device_records(const blu_result* res);
+const blu_bean* blu_result_device_beans(const blu_result* res, uint64_t* n);
+const blu_acc* blu_result_device_accessions(const blu_result* res, uint64_t* n);
+int blu_result_download(blu_result* res);
 /* ParallelBlastOutput.output_file (parallel_blast_output.rs:3-7).  The file is streamed: parallel pread()s fill a ring of
  * three pinned staging buffers (opts.chunk_bytes each, default 64 MiB; BLU_READ_THREADS readers, default 8) while
  * earlier chunks are copied to the device and processed, so it never has to fit in host memory.  Only a table whose
@@ -151,10 +179,14 @@ int blu_result_add_headers(blu_result* res, const char* headers_nl, uint64_t len
 /* ---- results -------------------------------------------------------------------------------------------- */
 uint64_t blu_result_num_queries(const blu_result* res);
 uint64_t blu_result_num_rows(const blu_result* res);
+/* Host arrays of the result (the parts of a multi-device result are concatenated on the first call; the string
+ * references of such a result are relative to blu_result_pool of that same concatenation). */
 const blu_record* blu_result_records(const blu_result* res);
 const blu_bean* blu_result_beans(const blu_result* res);
 const blu_acc* blu_result_accessions(const blu_result* res);
 const char* blu_result_pool(const blu_result* res, uint64_t* len);
+uint64_t blu_result_num_beans(const blu_result* res);
+uint64_t blu_result_num_accessions(const blu_result* res);
 /* Order-independent 64-bit checksum of the canonical (runId-less) JSONL lines: sum of FNV-1a per line. */
 uint64_t blu_result_checksum(const blu_result* res);
 /* Canonical JSONL (one `{"query":..,"taxon":..}` object per line, sorted by query, no runId); caller frees
@@ -181,6 +213,8 @@ void blu_free(void* p);
 int blu_ctx_last_timings(const blu_ctx* ctx, blu_timings* out);
 /* Measured pinned host->device copy bandwidth (GB/s) on ctx's device, for the end-to-end ceiling. */
 int blu_ctx_measure_h2d(blu_ctx* ctx, uint64_t bytes, double* gbps);
+/* ... and device->host. */
+int blu_ctx_measure_d2h(blu_ctx* ctx, uint64_t bytes, double* gbps);
 
 /* Multi-GPU sharding: byte offsets cuts[0..n_shards] that split the table into n_shards ranges of
  * roughly equal size without ever splitting a query (cuts move forward to the next query boundary).  Valid for

@@ -176,18 +176,19 @@ extern "C" int blu_sim_run(const int64_t* taxids, const uint64_t* off, const cha
                     top.push_back(t);
                 }
             const size_t g = top.size();
-            if (g > 1024) return BLU_ERR_UNSUPPORTED;
+            if (g > 65535) return BLU_ERR_UNSUPPORTED;
             blu_record rec;
             memset(&rec, 0, sizeof rec);
             rec.query_off = rows[h].s;
             rec.query_len = (uint32_t)rows[h].qlen;
             rec.n_rows = (uint32_t)(e - h);
             rec.bit_score = mx;
-            rec.slot_base = (uint32_t)beans.size();
+            rec.bean_base = (uint32_t)beans.size();
+            rec.acc_base = (uint32_t)accs.size();
             beans.resize(beans.size() + g);
             accs.resize(accs.size() + g);
             scratch.assign(5 * g, 0);
-            QueryOut qo{&rec, beans.data() + rec.slot_base, accs.data() + rec.slot_base};
+            QueryOut qo{&rec, beans.data() + rec.bean_base, accs.data() + rec.acc_base};
             uint32_t ce = g == 1 ? consensus_single(top[0], L, qo) : consensus_multi(top.data(), (int)g, tx, L, strategy, scratch.data(), qo);
             if (ce) {
                 snprintf(err, errlen, "device error %u in query at byte %llu", ce, (unsigned long long)rows[h].s);
@@ -213,11 +214,13 @@ extern "C" int blu_sim_run(const int64_t* taxids, const uint64_t* off, const cha
         ResultView v;
         v.tax = &T;
         v.cut = cut;
-        v.rec_ = recs.data();
-        v.beans_ = beans.data();
-        v.accs_ = accs.data();
-        v.pool_ = text;
-        v.n_rec = recs.size();
+        ResultPart part;
+        part.rec = recs.data();
+        part.beans = beans.data();
+        part.accs = accs.data();
+        part.pool = text;
+        part.n_rec = recs.size();
+        v.parts.push_back(part);
         v.hitless_ = &hitless;
         std::string js = view_to_jsonl(&v);
         *out = (char*)malloc(js.size() + 1);

@@ -29,7 +29,7 @@ def test_header_symbols_exported():
     assert declared == bound, (declared ^ bound)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.blu_abi_version() == 1
+    assert lib.blu_abi_version() == 2
 
 
 def test_no_gpu_is_loud():
