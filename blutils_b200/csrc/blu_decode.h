@@ -268,63 +268,188 @@ inline std::string uuid_v4() {
     return s;
 }
 
-// serde_yaml 0.9 scalar rules needed for this schema (strings that would not round-trip as plain scalars are
-// single-quoted; everything else plain)
-inline void yaml_str(std::string& o, std::string_view s) {
-    auto plain_ok = [&]() {
-        if (s.empty()) return false;
-        static const char* special[] = {"null", "Null", "NULL", "~", "true", "True", "TRUE", "false", "False", "FALSE", "y", "Y", "n", "N",
-                                        "yes", "Yes", "YES", "no", "No", "NO", "on", "On", "ON", "off", "Off", "OFF"};
-        for (auto sp : special)
-            if (s == sp) return false;
-        char c0 = s[0];
-        if (strchr("-?:,[]{}#&*!|>'\"%@` ", c0)) return false;
-        if (s.back() == ' ' || s.back() == ':') return false;
-        bool numeric = true;
-        for (char ch : s)
-            if (!((ch >= '0' && ch <= '9') || ch == '.' || ch == '-' || ch == '+' || ch == 'e' || ch == 'E' || ch == '_')) numeric = false;
-        if (numeric) return false;
-        for (size_t i = 0; i < s.size(); i++) {
-            unsigned char ch = (unsigned char)s[i];
-            if (ch < 0x20 || ch == 0x7f) return false;
-            if (ch == ':' && i + 1 < s.size() && s[i + 1] == ' ') return false;
-            if (ch == '#' && i > 0 && s[i - 1] == ' ') return false;
-        }
-        return true;
-    };
-    if (plain_ok()) {
-        o.append(s);
-        return;
+// serde_yaml 0.9 string scalars (write_blutils_output.rs:216-248 serialises with serde_yaml::to_writer).  The crate is
+// not vendored under /root/reference: restated from its published behaviour (PARITY UNPINNED; the test oracle holds an
+// independent statement of the same rules, tests/test_yaml_scalars.py compares the two byte for byte):
+//   * single-quoted when the string would read back as another type (serde_yaml ser.rs serialize_str -> de.rs
+//     visit_untagged_scalar): empty, null / ~, true / false, integers (also 0x / 0o / 0b), floats (also .inf / .nan), or is a
+//     YAML 1.1 boolean (y, yes, n, no, on, off, any case);
+//   * else libyaml's emitter (yaml_emitter_analyze_scalar / select_scalar_style, block context): plain unless there is a
+//     leading / trailing space, a non-printable character, a leading indicator, "- " / "? " / ": " at the start, "---" / "...",
+//     ": " / trailing ":" / " #" inside; then single-quoted, double-quoted only for non-printable characters.
+inline bool yaml_digits_but_not_number(std::string_view s) {
+    if (!s.empty() && (s[0] == '+' || s[0] == '-')) s.remove_prefix(1);
+    if (s.size() <= 1 || s[0] != '0') return false;
+    for (size_t i = 1; i < s.size(); i++)
+        if (s[i] < '0' || s[i] > '9') return false;
+    return true;
+}
+
+inline bool yaml_fits_u128(std::string_view digits, int radix) {  // value of a valid digit string < 2^128
+    unsigned __int128 v = 0;
+    for (char ch : digits) {
+        const int d = ch <= '9' ? ch - '0' : (ch | 0x20) - 'a' + 10;
+        const unsigned __int128 lim = ~(unsigned __int128)0;
+        if (v > (lim - (unsigned)d) / (unsigned)radix) return false;
+        v = v * (unsigned)radix + (unsigned)d;
     }
-    bool ctl = false;
-    for (unsigned char ch : s) ctl |= ch < 0x20 || ch == 0x7f;
-    if (!ctl) {
+    return true;
+}
+
+inline bool yaml_int_like(std::string_view s) {
+    std::string_view body = s;
+    if (!body.empty() && (body[0] == '+' || body[0] == '-')) body.remove_prefix(1);
+    if (body.empty() || body[0] == '+' || body[0] == '-') return false;
+    if (body.size() >= 2 && body[0] == '0' && (body[1] == 'x' || body[1] == 'o' || body[1] == 'b')) {
+        const int radix = body[1] == 'x' ? 16 : body[1] == 'o' ? 8 : 2;
+        std::string_view rest = body.substr(2);
+        if (rest.empty()) return false;
+        for (char ch : rest) {
+            const bool ok = radix == 16 ? ((ch >= '0' && ch <= '9') || ((ch | 0x20) >= 'a' && (ch | 0x20) <= 'f')) : (ch >= '0' && ch < '0' + radix);
+            if (!ok) return false;
+        }
+        return yaml_fits_u128(rest, radix);
+    }
+    if (yaml_digits_but_not_number(s)) return false;
+    for (char ch : body)
+        if (ch < '0' || ch > '9') return false;
+    return yaml_fits_u128(body, 10);
+}
+
+inline bool yaml_float_like(std::string_view s) {
+    if (yaml_digits_but_not_number(s)) return false;
+    std::string_view u = s;
+    if (!u.empty() && u[0] == '+') {
+        u.remove_prefix(1);
+        if (!u.empty() && (u[0] == '+' || u[0] == '-')) return false;
+    }
+    if (u == ".inf" || u == ".Inf" || u == ".INF" || s == "-.inf" || s == "-.Inf" || s == "-.INF" || s == ".nan" || s == ".NaN" || s == ".NAN") return true;
+    // [+-]? (digits [. digits*] | . digits+) ([eE] [+-]? digits+)?
+    size_t i = 0;
+    if (i < u.size() && (u[i] == '+' || u[i] == '-')) i++;
+    size_t nint = 0, nfrac = 0;
+    while (i < u.size() && u[i] >= '0' && u[i] <= '9') i++, nint++;
+    if (i < u.size() && u[i] == '.') {
+        i++;
+        while (i < u.size() && u[i] >= '0' && u[i] <= '9') i++, nfrac++;
+    }
+    if (nint == 0 && nfrac == 0) return false;
+    if (i < u.size() && (u[i] == 'e' || u[i] == 'E')) {
+        i++;
+        if (i < u.size() && (u[i] == '+' || u[i] == '-')) i++;
+        size_t nexp = 0;
+        while (i < u.size() && u[i] >= '0' && u[i] <= '9') i++, nexp++;
+        if (nexp == 0) return false;
+    }
+    if (i != u.size()) return false;
+    const std::string z(u);
+    char* end = nullptr;
+    const double v = strtod(z.c_str(), &end);
+    return v - v == 0.0;  // finite (an overflowing literal reads back as a string)
+}
+
+inline bool yaml_printable(uint32_t cp) {
+    return cp == 0x0A || (cp >= 0x20 && cp <= 0x7E) || cp == 0x85 || (cp >= 0xA0 && cp <= 0xD7FF) || (cp >= 0xE000 && cp <= 0xFFFD && cp != 0xFEFF) ||
+           (cp >= 0x10000 && cp <= 0x10FFFF);
+}
+
+// next code point of a UTF-8 string (malformed bytes are returned as themselves, one at a time: they are not printable)
+inline uint32_t yaml_next_cp(std::string_view s, size_t& i) {
+    const unsigned char c = (unsigned char)s[i];
+    auto cont = [&](size_t k) { return i + k < s.size() && ((unsigned char)s[i + k] & 0xC0) == 0x80; };
+    if (c < 0x80) return i += 1, c;
+    if ((c & 0xE0) == 0xC0 && cont(1)) {
+        const uint32_t cp = ((c & 0x1Fu) << 6) | ((unsigned char)s[i + 1] & 0x3Fu);
+        return i += 2, cp;
+    }
+    if ((c & 0xF0) == 0xE0 && cont(1) && cont(2)) {
+        const uint32_t cp = ((c & 0x0Fu) << 12) | (((unsigned char)s[i + 1] & 0x3Fu) << 6) | ((unsigned char)s[i + 2] & 0x3Fu);
+        return i += 3, cp;
+    }
+    if ((c & 0xF8) == 0xF0 && cont(1) && cont(2) && cont(3)) {
+        const uint32_t cp = ((c & 0x07u) << 18) | (((unsigned char)s[i + 1] & 0x3Fu) << 12) | (((unsigned char)s[i + 2] & 0x3Fu) << 6) | ((unsigned char)s[i + 3] & 0x3Fu);
+        return i += 4, cp;
+    }
+    return i += 1, (uint32_t)c | 0x80000000u;
+}
+
+inline void yaml_str(std::string& o, std::string_view s) {
+    auto single = [&]() {
         o.push_back('\'');
         for (char ch : s) {
             if (ch == '\'') o.push_back('\'');
             o.push_back(ch);
         }
         o.push_back('\'');
+    };
+    std::string lower(s);
+    for (char& ch : lower)
+        if (ch >= 'A' && ch <= 'Z') ch = (char)(ch + 32);
+    static const char* ambiguous[] = {"y", "yes", "n", "no", "on", "off", "true", "false", "null", "~"};
+    bool amb = s.empty();
+    for (auto a : ambiguous) amb |= lower == a;
+    if (amb || yaml_int_like(s) || yaml_float_like(s)) return single();
+    bool special = false;
+    for (size_t i = 0; i < s.size();) {
+        const uint32_t cp = yaml_next_cp(s, i);
+        special |= !yaml_printable(cp) || cp == 0x0A;
+    }
+    if (special) {
+        o.push_back('"');
+        for (size_t i = 0; i < s.size();) {
+            const size_t at = i;
+            const uint32_t cp = yaml_next_cp(s, i);
+            const bool esc = !yaml_printable(cp) || cp == 0xFEFF || cp == 0x0A || cp == 0x0D || cp == 0x85 || cp == 0x2028 || cp == 0x2029 || cp == '"' || cp == '\\';
+            if (!esc) {
+                o.append(s.substr(at, i - at));
+                continue;
+            }
+            switch (cp) {
+                case 0: o += "\\0"; break;
+                case 7: o += "\\a"; break;
+                case 8: o += "\\b"; break;
+                case 9: o += "\\t"; break;
+                case 10: o += "\\n"; break;
+                case 11: o += "\\v"; break;
+                case 12: o += "\\f"; break;
+                case 13: o += "\\r"; break;
+                case 27: o += "\\e"; break;
+                case '"': o += "\\\""; break;
+                case '\\': o += "\\\\"; break;
+                case 0x85: o += "\\N"; break;
+                case 0xA0: o += "\\_"; break;
+                case 0x2028: o += "\\L"; break;
+                case 0x2029: o += "\\P"; break;
+                default: {
+                    char b[16];
+                    const uint32_t v = cp & 0x7FFFFFFFu;
+                    if (v <= 0xFF)
+                        snprintf(b, sizeof b, "\\x%02X", v);
+                    else if (v <= 0xFFFF)
+                        snprintf(b, sizeof b, "\\u%04X", v);
+                    else
+                        snprintf(b, sizeof b, "\\U%08X", v);
+                    o += b;
+                }
+            }
+        }
+        o.push_back('"');
         return;
     }
-    o.push_back('"');
-    for (unsigned char ch : s) {
-        switch (ch) {
-            case '"': o += "\\\""; break;
-            case '\\': o += "\\\\"; break;
-            case '\n': o += "\\n"; break;
-            case '\t': o += "\\t"; break;
-            case '\r': o += "\\r"; break;
-            default:
-                if (ch < 0x20 || ch == 0x7f) {
-                    char b[8];
-                    snprintf(b, sizeof b, "\\x%02x", ch);
-                    o += b;
-                } else
-                    o.push_back((char)ch);
+    bool block_ind = s.substr(0, 3) == "---" || s.substr(0, 3) == "...";
+    for (size_t i = 0; i < s.size(); i++) {
+        const char c = s[i];
+        const bool nxt_blank = i + 1 >= s.size() || s[i + 1] == ' ' || s[i + 1] == '\t';
+        if (i == 0) {
+            if (strchr("#,[]{}&*!|>'\"%@`", c)) block_ind = true;
+            if ((c == '?' || c == ':' || c == '-') && nxt_blank) block_ind = true;
+        } else {
+            if (c == ':' && nxt_blank) block_ind = true;
+            if (c == '#' && (s[i - 1] == ' ' || s[i - 1] == '\t')) block_ind = true;
         }
     }
-    o.push_back('"');
+    if (block_ind || s.front() == ' ' || s.back() == ' ') return single();
+    o.append(s);
 }
 
 inline void yaml_f64(std::string& o, double v) {  // serde_yaml: ryu, but integers print without ".0"?  No: serde_yaml keeps ryu's output

@@ -607,3 +607,133 @@ def results_to_tabular(results: List[dict], run_id: str, to_stdout: bool) -> str
                                   c["taxonomy"] if c["taxonomy"] is not None else "null", "null", "null", str(c["occurrences"]),
                                   ", ".join(c["accessions"])]) + end)
     return "".join(out)
+
+
+# --------------------------------------------------------------------------------------
+# serde_yaml 0.9 serialisation (write_blutils_output.rs:216-248: serde_yaml::to_writer of BlutilsOutput)
+#
+# serde_yaml is not vendored under /root/reference (core/Cargo.toml: serde_yaml = "0.9"): PARITY UNPINNED, restated from
+# the crate's published behaviour:
+#   * block style; a sequence that is a mapping value starts at the key's indentation ("- " under the key);
+#   * f64 through ryu (same text as serde_json), bool / null / integers plain;
+#   * a string is single-quoted when it would read back as another type (ser.rs serialize_str -> de.rs
+#     visit_untagged_scalar: empty, null / ~, true / false, integers incl. 0x / 0o / 0b, floats incl. .inf / .nan) or is one
+#     of the YAML 1.1 booleans (y, yes, n, no, on, off: "ambiguous" strings);
+#   * otherwise libyaml's emitter decides (yaml_emitter_analyze_scalar / select_scalar_style, block context): plain unless
+#     the string has a leading / trailing space, a non-printable character, starts with an indicator
+#     (# , [ ] { } & * ! | > ' " % @ `), with "- " / "? " / ": " (or is just that character), with "---" / "...", or contains
+#     ": " / a trailing ":" / " #"; then single-quoted ('' escapes '), double-quoted only for non-printable characters.
+# --------------------------------------------------------------------------------------
+_YAML11_BOOLS = {"y", "yes", "n", "no", "on", "off", "true", "false", "null", "~"}
+_FLOAT_RE = re.compile(r"[+-]?([0-9]+(\.[0-9]*)?|\.[0-9]+)([eE][+-]?[0-9]+)?\Z")
+
+
+def _digits_but_not_number(s: str) -> bool:
+    t = s[1:] if s[:1] in "+-" and s else s
+    return len(t) > 1 and t[0] == "0" and all("0" <= c <= "9" for c in t[1:])
+
+
+def _yaml_int_like(s: str) -> bool:
+    body = s[1:] if s[:1] in ("+", "-") else s
+    if not body or body[:1] in ("+", "-"):
+        return False
+    for pre, digits in (("0x", "0123456789abcdefABCDEF"), ("0o", "01234567"), ("0b", "01")):
+        if body.startswith(pre):
+            rest = body[2:]
+            return bool(rest) and all(c in digits for c in rest) and int(rest, {"0x": 16, "0o": 8, "0b": 2}[pre]) < (1 << 128)
+    if _digits_but_not_number(s):
+        return False
+    return all("0" <= c <= "9" for c in body) and int(body) < (1 << 128)
+
+
+def _yaml_float_like(s: str) -> bool:
+    if _digits_but_not_number(s):
+        return False
+    u = s[1:] if s.startswith("+") else s
+    if s.startswith("+") and u[:1] in ("+", "-"):
+        return False
+    if u in (".inf", ".Inf", ".INF") or s in ("-.inf", "-.Inf", "-.INF", ".nan", ".NaN", ".NAN"):
+        return True
+    if not _FLOAT_RE.match(u):
+        return False
+    try:
+        return math.isfinite(float(u))
+    except (ValueError, OverflowError):
+        return False
+
+
+def _yaml_printable(cp: int) -> bool:
+    return (cp == 0x0A or 0x20 <= cp <= 0x7E or cp == 0x85 or 0xA0 <= cp <= 0xD7FF or (0xE000 <= cp <= 0xFFFD and cp != 0xFEFF)
+            or 0x10000 <= cp <= 0x10FFFF)
+
+
+def yaml_str(s: str) -> str:
+    if s == "" or s in ("null", "Null", "NULL", "~", "true", "True", "TRUE", "false", "False", "FALSE") or _yaml_int_like(s) or _yaml_float_like(s) \
+            or s.lower() in _YAML11_BOOLS:
+        return "'" + s.replace("'", "''") + "'"
+    special = any(not _yaml_printable(ord(c)) or c == "\n" for c in s)
+    if special:
+        esc = {0: "\\0", 7: "\\a", 8: "\\b", 9: "\\t", 10: "\\n", 11: "\\v", 12: "\\f", 13: "\\r", 27: "\\e", 34: '\\"', 92: "\\\\", 0x85: "\\N",
+               0xA0: "\\_", 0x2028: "\\L", 0x2029: "\\P"}
+        out = ['"']
+        for c in s:
+            cp = ord(c)
+            if not _yaml_printable(cp) or cp in (0xFEFF, 0x0A, 0x0D, 0x85, 0x2028, 0x2029, 34, 92):
+                if cp in esc:
+                    out.append(esc[cp])
+                elif cp <= 0xFF:
+                    out.append("\\x%02X" % cp)
+                elif cp <= 0xFFFF:
+                    out.append("\\u%04X" % cp)
+                else:
+                    out.append("\\U%08X" % cp)
+            else:
+                out.append(c)
+        out.append('"')
+        return "".join(out)
+    block_ind = s.startswith("---") or s.startswith("...")
+    n = len(s)
+    for i, c in enumerate(s):
+        nxt_blank = i + 1 >= n or s[i + 1] in " \t"
+        if i == 0:
+            if c in "#,[]{}&*!|>'\"%@`":
+                block_ind = True
+            if c in "?:" and nxt_blank:
+                block_ind = True
+            if c == "-" and nxt_blank:
+                block_ind = True
+        else:
+            if c == ":" and nxt_blank:
+                block_ind = True
+            if c == "#" and s[i - 1] in " \t":
+                block_ind = True
+    if block_ind or s[0] == " " or s[-1] == " ":
+        return "'" + s.replace("'", "''") + "'"
+    return s
+
+
+def results_to_yaml(results: List[dict], run_id: str) -> str:
+    """serde_yaml::to_writer(BlutilsOutput { results, config: None }) (write_blutils_output.rs:216-248)."""
+    o: List[str] = []
+    o.append("results: []\n" if not results else "results:\n")
+    for r in results:
+        o.append("- runId: " + yaml_str(run_id) + "\n  query: " + yaml_str(r["query"]) + "\n")
+        t = r["taxon"]
+        if t is None:
+            o.append("  taxon: null\n")
+            continue
+        o.append("  taxon:\n    reachedRank: " + yaml_str(t["reachedRank"]) + "\n    maxAllowedRank: " +
+                 ("null" if t["maxAllowedRank"] is None else yaml_str(t["maxAllowedRank"])) + "\n    identifier: " + yaml_str(t["identifier"]) +
+                 "\n    percIdentity: " + ryu_f64(t["percIdentity"]) + "\n    bitScore: " + ryu_f64(t["bitScore"]) + "\n    taxonomy: " +
+                 yaml_str(t["taxonomy"]) + "\n    mutated: " + ("true" if t["mutated"] else "false") + "\n    singleMatch: " +
+                 ("true" if t["singleMatch"] else "false") + "\n")
+        beans = t["consensusBeans"]
+        o.append("    consensusBeans: []\n" if not beans else "    consensusBeans:\n")
+        for b in beans:
+            o.append("    - rank: " + yaml_str(b["rank"]) + "\n      identifier: " + yaml_str(b["identifier"]) + "\n      occurrences: " +
+                     str(b["occurrences"]) + "\n      taxonomy: " + yaml_str(b["taxonomy"]) + "\n")
+            o.append("      accessions: []\n" if not b["accessions"] else "      accessions:\n")
+            for a in b["accessions"]:
+                o.append("      - " + yaml_str(a) + "\n")
+    o.append("config: null\n")
+    return "".join(o)

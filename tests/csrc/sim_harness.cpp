@@ -242,6 +242,16 @@ extern "C" int blu_sim_run(const int64_t* taxids, const uint64_t* off, const cha
 
 extern "C" void blu_sim_free(char* p) { free(p); }
 
+// the product's serde_yaml string-scalar emitter (blu_decode.h yaml_str)
+extern "C" int blu_sim_yaml_str(const char* s, uint64_t n, char* out, int cap) {
+    std::string o;
+    yaml_str(o, std::string_view(s, (size_t)n));
+    if ((int)o.size() + 1 > cap) return -1;
+    memcpy(out, o.data(), o.size());
+    out[o.size()] = 0;
+    return (int)o.size();
+}
+
 // interpolation of the product's taxonomy encoder, for the KAT vectors
 extern "C" int blu_sim_interpolate(const char* ranks_nl, int taxon, int has_custom, const int32_t* custom8, double* out, int cap) {
     try {

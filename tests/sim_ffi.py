@@ -120,3 +120,15 @@ def taxonomy_cached(json_path: str, cache_path: str, use_taxid: bool = False, ta
     if rc:
         raise ValueError(err.value.decode())
     return state.value, ck.value
+
+
+def yaml_str(s: str) -> str:
+    """The product's serde_yaml string-scalar emitter (blu_decode.h yaml_str)."""
+    l = lib()
+    l.blu_sim_yaml_str.restype = C.c_int
+    l.blu_sim_yaml_str.argtypes = [C.c_char_p, C.c_uint64, C.c_char_p, C.c_int]
+    b = s.encode("utf-8")
+    out = C.create_string_buffer(8 * len(b) + 16)
+    n = l.blu_sim_yaml_str(b, len(b), out, len(out))
+    assert n >= 0
+    return out.raw[:n].decode("utf-8")
