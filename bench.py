@@ -200,6 +200,7 @@ def main():
     ap.add_argument("--host-gb", type=float, default=8.0, help="pinned host text kept per rank for the end-to-end arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--no-file-arm", action="store_true", help="skip the blu_consensus_run_file timing (the call the CLI makes)")
     args = ap.parse_args()
 
     cfg = dict(CONFIGS[args.config])
@@ -448,6 +449,28 @@ def main():
     e2e_q = sum_over_ranks(float(host_q * passes))
     e2e_rows = sum_over_ranks(float(host_rows * passes))
     e2e_bytes = sum_over_ranks(float(host_bytes * passes))
+    # ---------------- the same from a file (tmpfs), the call `blu blastn build-consensus` makes -------------------------------
+    e2e_file = None
+    if not args.no_file_arm and not streamed_only and os.path.isdir("/dev/shm"):
+        fpath = f"/dev/shm/blu_bench_{os.getpid()}_{rank}.out"
+        try:
+            with open(fpath, "wb") as fh:
+                fh.write((C.c_uint8 * host_bytes).from_address(pinned))
+            eng.run_file(fpath).close()
+            barrier()
+            t0 = time.perf_counter()
+            fsteps = max(1, min(args.steps, 3))
+            for _ in range(fsteps):
+                eng.run_file(fpath).close()
+            file_s = max_over_ranks(time.perf_counter() - t0) / fsteps
+            e2e_file = {"value": e2e_q / file_s, "unit": "queries/s", "ms_per_step": file_s * 1e3, "text_gb_per_s": e2e_bytes / file_s / 1e9,
+                        "what": "blu_consensus_run_file on a tmpfs copy of the same text (parallel pread ring -> pinned staging -> H2D)"}
+        finally:
+            try:
+                os.unlink(fpath)
+            except OSError:
+                pass
+        barrier()
     # pinned copy peaks: every rank alone is not what a multi-GPU box gives; all ranks copy at once behind a barrier
     barrier()
     h2d_c = eng.measure_h2d(1 << 30)
@@ -483,7 +506,7 @@ def main():
                                  "text resident in HBM -> consensus records resident in HBM (SURVEY 8d(i)); e2e and value_with_result_download include PCIe"),
             "hit_rows_per_s": total_rows / (ms_step * 1e-3),
             "text_gb_per_s": total_bytes / (ms_step * 1e-3) / 1e9,
-            "e2e": e2e, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "verified": verified,
+            "e2e": e2e, "e2e_file": e2e_file, "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "verified": verified,
         }
         line.update(line_extra)
         print(json.dumps(line))

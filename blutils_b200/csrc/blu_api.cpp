@@ -766,12 +766,12 @@ void run_device_download(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStrea
             ms_long += ev_ms(c->ev[ri][1], c->ev[ri][2]);
             ms_post += ev_ms(c->ev[ri][2], c->ev[ri][3]);
             c->tm.n_deferred_runs += h.n_defer;
+            check_fatal(h, 0);  // (before anything is done about a capacity: a malformed row is an error whatever else happened)
             if (overflowed(h, k)) {
                 grow_caps(h, k, (double)n / (double)std::max<uint64_t>(range_end[ri], 1), n);
                 retry = true;
                 break;
             }
-            check_fatal(h, 0);
             if (ri + 1 < n_ranges && !h.dup_found) {
                 if (ri == 0 && range_end[0] > 0) {
                     // size the pinned result buffers from the density of the first range
@@ -822,12 +822,12 @@ void run_device_resident(blu_ctx* c, const uint8_t* dtext, uint64_t n, cudaStrea
         launch_range(c, dtext, 0, n, true, k, s, 0, Strings::DeviceText, 0);
         CK(cudaEventSynchronize(c->ev[0][3]));
         const Counters h = c->h_snap[0];
+        check_fatal(h, 0);
         if (overflowed(h, k)) {
             grow_caps(h, k, 1.0, n);
             c->tm = blu_timings{};
             continue;
         }
-        check_fatal(h, 0);
         st.note_soft(h, 0);
         st.dup_found = h.dup_found != 0;
         if (!st.dup_found && h.post_done == 0) throw DataErr("the blast output holds no rows");
@@ -1173,12 +1173,12 @@ void run_host_chunks(blu_ctx* c, ChunkSource& src, uint64_t n, const uint64_t ch
             ms_post += ev_ms(c->ev[slot][2], c->ev[slot][3]);
             c->tm.n_deferred_runs += h.n_defer;
             launches++;
+            check_fatal(h, off - text_off);  // err_off is in buffer coordinates
             if (overflowed(h, k)) {
                 grow_caps(h, k, (double)n / (double)(off + len), n);
                 retry = true;
                 break;
             }
-            check_fatal(h, off - text_off);  // err_off is in buffer coordinates
             st.note_soft(h, off - text_off);
             if (!final_chunk) {
                 tail_len = end - h.next_begin;  // (next_begin == end: nothing is carried)

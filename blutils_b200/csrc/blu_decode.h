@@ -224,18 +224,6 @@ struct Entry {
     const ResultPart* part;
 };
 
-// write_blutils_output.rs:87-111: flatten + sort by query (bytewise)
-inline std::vector<Entry> sorted_entries(const ResultView* r) {
-    std::vector<Entry> v;
-    v.reserve(r->n_rec() + (r->hitless_ ? r->hitless_->size() : 0));
-    for (auto& p : r->parts)
-        for (uint64_t i = 0; i < p.n_rec; i++) v.push_back({rec_query(p, p.rec[i]), &p.rec[i], &p});
-    if (r->hitless_)
-        for (auto& h : *r->hitless_) v.push_back({std::string_view(h), nullptr, nullptr});
-    std::stable_sort(v.begin(), v.end(), [](const Entry& a, const Entry& b) { return a.query < b.query; });
-    return v;
-}
-
 inline unsigned host_threads() {
     unsigned n = std::thread::hardware_concurrency();
     return n ? std::min(n, 32u) : 4u;
@@ -250,6 +238,102 @@ void parallel_ranges(size_t n, F&& f) {
     }
     std::vector<std::thread> th;
     for (unsigned t = 0; t < nt; t++) th.emplace_back([&, t] { f(t, n * t / nt, n * (t + 1) / nt); });
+    for (auto& x : th) x.join();
+}
+
+// write_blutils_output.rs:87-111: flatten + sort by query (bytewise).  At 10^6 - 10^8 queries the sort of the ids is what the
+// writer waits for first: the entries are sorted in per-thread chunks and merged pairwise in parallel (stable:
+// equal ids keep their file order, like the reference's sort_by).
+inline std::vector<Entry> sorted_entries(const ResultView* r) {
+    std::vector<Entry> v;
+    v.reserve(r->n_rec() + (r->hitless_ ? r->hitless_->size() : 0));
+    for (auto& p : r->parts)
+        for (uint64_t i = 0; i < p.n_rec; i++) v.push_back({rec_query(p, p.rec[i]), &p.rec[i], &p});
+    if (r->hitless_)
+        for (auto& h : *r->hitless_) v.push_back({std::string_view(h), nullptr, nullptr});
+    auto less = [](const Entry& a, const Entry& b) { return a.query < b.query; };
+    const size_t n = v.size();
+    unsigned nt = (unsigned)std::min<size_t>(host_threads(), std::max<size_t>(1, n / 65536));
+    if (nt <= 1) {
+        std::stable_sort(v.begin(), v.end(), less);
+        return v;
+    }
+    std::vector<size_t> cut(nt + 1);
+    for (unsigned t = 0; t <= nt; t++) cut[t] = n * t / nt;
+    {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; t++) th.emplace_back([&, t] { std::stable_sort(v.begin() + cut[t], v.begin() + cut[t + 1], less); });
+        for (auto& x : th) x.join();
+    }
+    std::vector<Entry> aux(n);
+    std::vector<Entry>* src = &v;
+    std::vector<Entry>* dst = &aux;
+    while (cut.size() > 2) {
+        std::vector<size_t> ncut;
+        std::vector<std::thread> th;
+        for (size_t i = 0; i + 1 < cut.size(); i += 2) {
+            ncut.push_back(cut[i]);
+            if (i + 2 < cut.size()) {
+                const size_t a = cut[i], m = cut[i + 1], b = cut[i + 2];
+                th.emplace_back([=] { std::merge(src->begin() + a, src->begin() + m, src->begin() + m, src->begin() + b, dst->begin() + a, less); });
+            } else {
+                const size_t a = cut[i], b = cut[i + 1];
+                th.emplace_back([=] { std::copy(src->begin() + a, src->begin() + b, dst->begin() + a); });
+            }
+        }
+        ncut.push_back(n);
+        for (auto& x : th) x.join();
+        cut.swap(ncut);
+        std::swap(src, dst);
+    }
+    if (src != &v) v.swap(aux);
+    return v;
+}
+
+// Formats entries [0, n) with `emit(out, i)` on all host threads, blocks of entries at a time, and writes the blocks to `f` in
+// order while later ones are still being formatted.
+template <class Emit>
+void ordered_parallel_write(FILE* f, size_t n, Emit&& emit) {
+    const size_t B = 4096;
+    const size_t nblocks = (n + B - 1) / B;
+    const unsigned nt = (unsigned)std::min<size_t>(host_threads(), nblocks);
+    if (nt <= 1 || nblocks < 4) {
+        std::string o;
+        for (size_t i = 0; i < n; i++) {
+            emit(o, i);
+            if (o.size() > (8u << 20)) {
+                fwrite(o.data(), 1, o.size(), f);
+                o.clear();
+            }
+        }
+        fwrite(o.data(), 1, o.size(), f);
+        return;
+    }
+    std::vector<std::string> out(nblocks);
+    std::unique_ptr<std::atomic<int>[]> ready(new std::atomic<int>[nblocks]);
+    for (size_t b = 0; b < nblocks; b++) ready[b].store(0);
+    std::atomic<size_t> next{0}, written{0};
+    const size_t window = 4 * (size_t)nt;  // blocks formatted ahead of the writer: bounds the memory
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++)
+        th.emplace_back([&] {
+            for (;;) {
+                const size_t b = next.fetch_add(1);
+                if (b >= nblocks) return;
+                while (b >= written.load(std::memory_order_acquire) + window) std::this_thread::yield();
+                std::string& o = out[b];
+                o.reserve(B * 512);
+                const size_t e = std::min(n, (b + 1) * B);
+                for (size_t i = b * B; i < e; i++) emit(o, i);
+                ready[b].store(1, std::memory_order_release);
+            }
+        });
+    for (size_t b = 0; b < nblocks; b++) {
+        while (!ready[b].load(std::memory_order_acquire)) std::this_thread::yield();
+        fwrite(out[b].data(), 1, out[b].size(), f);
+        std::string().swap(out[b]);
+        written.store(b + 1, std::memory_order_release);
+    }
     for (auto& x : th) x.join();
 }
 
@@ -530,48 +614,38 @@ inline int view_write(const ResultView* r, const char* path, int format, const c
             if (!f) return BLU_ERR_IO;
         }
         const bool pretty = format == BLU_FORMAT_JSON && path != nullptr;  // to_string_pretty to a file, compact to stdout
-        std::string o;
-        auto flush = [&](bool force) {
-            if (o.size() > (8u << 20) || force) {
-                fwrite(o.data(), 1, o.size(), f);
-                o.clear();
-            }
-        };
+        auto put = [&](const char* t) { fwrite(t, 1, strlen(t), f); };
         if (format == BLU_FORMAT_JSON) {
-            o += pretty ? "{\n  \"results\": [" : "{\"results\":[";
-            for (size_t i = 0; i < ent.size(); i++) {
+            put(pretty ? "{\n  \"results\": [" : "{\"results\":[");
+            ordered_parallel_write(f, ent.size(), [&](std::string& o, size_t i) {
                 if (i) o.push_back(',');
                 if (pretty) o += "\n    ";
                 d.object(o, ent[i].query, ent[i].part, ent[i].rec, run_id.c_str(), pretty, 2);
-                flush(false);
-            }
+            });
             if (pretty)
-                o += ent.empty() ? "],\n  \"config\": null\n}" : "\n  ],\n  \"config\": null\n}";
+                put(ent.empty() ? "],\n  \"config\": null\n}" : "\n  ],\n  \"config\": null\n}");
             else
-                o += "],\"config\":null}";
+                put("],\"config\":null}");
         } else if (format == BLU_FORMAT_JSONL) {
-            o += "null\n";  // serde_json::to_string(&config) with config = None
-            for (size_t i = 0; i < ent.size(); i++) {
+            put("null\n");  // serde_json::to_string(&config) with config = None
+            ordered_parallel_write(f, ent.size(), [&](std::string& o, size_t i) {
                 d.object(o, ent[i].query, ent[i].part, ent[i].rec, run_id.c_str(), false, 0);
                 o.push_back('\n');
-                flush(false);
-            }
+            });
         } else {
             // serde_yaml 0.9 block style of BlutilsOutput{results, config}
             const HostTaxonomy& T = *r->tax;
-            if (ent.empty())
-                o += "results: []\n";
-            else
-                o += "results:\n";
-            std::string tmp;
-            for (auto& en : ent) {
+            put(ent.empty() ? "results: []\n" : "results:\n");
+            ordered_parallel_write(f, ent.size(), [&](std::string& o, size_t i) {
+                const Entry& en = ent[i];
+                std::string tmp;
                 o += "- runId: ";
-                o += run_id;
+                yaml_str(o, run_id);
                 o += "\n  query: ";
                 yaml_str(o, en.query);
                 if (!en.rec) {
                     o += "\n  taxon: null\n";
-                    continue;
+                    return;
                 }
                 const blu_record& rc = *en.rec;
                 const uint32_t lo = T.lin_off[rc.ref_lineage];
@@ -591,7 +665,6 @@ inline int view_write(const ResultView* r, const char* path, int format, const c
                 o += "\n    bitScore: ";
                 yaml_f64(o, (double)rc.bit_score);
                 o += "\n    taxonomy: ";
-                tmp.clear();
                 {
                     bool first = true;
                     for (int j = 0; j < T.lin_len(rc.ref_lineage); j++)
@@ -631,11 +704,9 @@ inline int view_write(const ResultView* r, const char* path, int format, const c
                         o.push_back('\n');
                     }
                 }
-                flush(false);
-            }
-            o += "config: null\n";
+            });
+            put("config: null\n");
         }
-        flush(true);
         if (path)
             fclose(f);
         else

@@ -20,13 +20,16 @@ pub struct blu_opts {
     pub has_custom: i32,
     pub custom: [i32; 8], // domain..species (CustomTaxon, taxon.rs:14-25)
     pub chunk_bytes: u64,
-    pub reserved: [u64; 4],
+    pub flags: u64,       // BLU_OPT_*
+    pub reserved: [u64; 3],
 }
 pub enum blu_ctx {}
 pub enum blu_result {}
 
 extern "C" {
+    pub fn blu_abi_version() -> c_int;
     pub fn blu_ctx_create(opts: *const blu_opts, out: *mut *mut blu_ctx) -> c_int;
+    pub fn blu_ctx_create_multi(opts: *const blu_opts, devices: *const c_int, n_devices: c_int, out: *mut *mut blu_ctx) -> c_int;
     pub fn blu_ctx_destroy(ctx: *mut blu_ctx);
     pub fn blu_last_error(ctx: *const blu_ctx) -> *const c_char;
     pub fn blu_custom_cutoffs_from_file(path: *const c_char, opts: *mut blu_opts, err: *mut c_char, errlen: size_t) -> c_int;
@@ -80,7 +83,37 @@ fn err_of(ctx: *const blu_ctx, rc: c_int) -> ConsensusError {
     if rc == BLU_ERR_IO { ConsensusError::Mapped(msg) } else { ConsensusError::Panic(msg) }
 }
 
-/// Same signature and argument meaning as the reference entry point (mod.rs:40-47).
+/// The reference entry point's signature, `Result<Vec<ConsensusResult>, MappedErrors>` included (mod.rs:40-47), without this
+/// crate depending on blul_core (which would be circular): the caller passes how one result object is decoded (serde, from
+/// the same JSON shape `QueryWithConsensus` serialises to; `taxon: null` = `NoConsensusFound`) and how an I/O-class failure
+/// becomes its error type.  Data-class failures panic, as the reference does (mod.rs:123).
+///
+/// ```ignore
+/// // blul_core::use_cases::build_consensus_identities, feature "b200"
+/// blu_consensus_sys::build_consensus_identities_as(blast_output.into(), taxonomies_file, taxon.into(), strategy.into(), use_taxid,
+///     custom_taxon_values.map(Into::into),
+///     |line| { let q: QueryWithConsensus = serde_json::from_str(line).unwrap();
+///              match q.taxon { Some(_) => ConsensusResult::ConsensusFound(q),
+///                              None => ConsensusResult::NoConsensusFound(QueryWithoutConsensus { query: q.query }) } },
+///     |msg| execution_err(msg))
+/// ```
+pub fn build_consensus_identities_as<R, E>(
+    blast_output: ParallelBlastOutput, taxonomies_file: &Path, taxon: Taxon, strategy: ConsensusStrategy,
+    use_taxid: Option<bool>, custom_taxon_values: Option<CustomTaxon>, decode: impl Fn(&str) -> R, io_err: impl Fn(String) -> E,
+) -> Result<Vec<R>, E> {
+    match build_consensus_identities(blast_output, taxonomies_file, taxon, strategy, use_taxid, custom_taxon_values) {
+        Ok(out) => Ok(out.jsonl().lines().map(|l| decode(l)).collect()),
+        Err(ConsensusError::Mapped(m)) => Err(io_err(m)),
+        Err(ConsensusError::Panic(m)) => panic!("Unexpected error on parse blast results: {m}"),
+    }
+}
+
+/// The GPUs the table is sharded over: `BLU_DEVICES=0,1,2,3` (one result either way); unset = device 0.
+fn devices_from_env() -> Vec<c_int> {
+    std::env::var("BLU_DEVICES").ok().map(|v| v.split(',').filter_map(|t| t.trim().parse().ok()).collect()).unwrap_or_default()
+}
+
+/// Same arguments as the reference entry point (mod.rs:40-47); returns the binary result container.
 pub fn build_consensus_identities(
     blast_output: ParallelBlastOutput, taxonomies_file: &Path, taxon: Taxon, strategy: ConsensusStrategy,
     use_taxid: Option<bool>, custom_taxon_values: Option<CustomTaxon>,
@@ -92,7 +125,11 @@ pub fn build_consensus_identities(
     }
     unsafe {
         let mut ctx = ptr::null_mut();
-        let rc = blu_ctx_create(&o, &mut ctx);
+        let devs = devices_from_env();
+        let rc = if devs.len() > 1 { blu_ctx_create_multi(&o, devs.as_ptr(), devs.len() as c_int, &mut ctx) } else {
+            if let Some(d) = devs.first() { o.device = *d; }
+            blu_ctx_create(&o, &mut ctx)
+        };
         if rc != BLU_OK { return Err(err_of(ptr::null(), rc)); }
         let tax = CString::new(taxonomies_file.to_str().unwrap()).unwrap();
         let rc = blu_taxonomy_load_json(ctx, tax.as_ptr());
