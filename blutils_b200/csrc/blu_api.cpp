@@ -207,7 +207,7 @@ struct blu_ctx {
     DevBuf<uint8_t> d_pool;
     DevBuf<unsigned long long> d_dup, d_qhash;
     DevBuf<TopRow> d_big_rows;
-    DevBuf<unsigned long long> d_big_cand, d_bail;
+    DevBuf<unsigned long long> d_big_cand;
     Counters* d_ctr = nullptr;
     Counters* h_snap = nullptr;  // pinned + mapped: kMaxRanges snapshots written by advance_kernel
     Counters* d_snap = nullptr;  // device alias of h_snap
@@ -387,7 +387,7 @@ Caps initial_caps(const blu_ctx* c, uint64_t n, bool want_pool) {
     };
     Caps k;
     k.rec = est(c->dens_rec, 160, 4096);
-    k.slots = est(c->dens_slot, 96, 8192 + (size_t)kWCtasPerSm * kWWarps * (size_t)c->sms * 512);  // (+ the warps' / CTAs' slabs)
+    k.slots = est(c->dens_slot, 96, 8192 + (size_t)kTileCtasPerSm * (size_t)c->sms * 2048);  // (+ the CTAs' slabs)
     k.beans = est(c->dens_bean, 128, 8192);
     k.accs = est(c->dens_acc, 128, 8192);
     k.defer = std::max<size_t>(k.rec / 8, 65536);
@@ -407,7 +407,6 @@ void ensure_out(blu_ctx* c, const Caps& k) {
     while (cap < 2 * k.rec) cap <<= 1;
     c->d_dup.ensure(cap);
     if (c->keep_hashes) c->d_qhash.ensure(k.rec);
-    c->d_bail.ensure(2 * (size_t)kWCtasPerSm * kWWarps * (size_t)c->sms);
     c->d_big_rows.ensure((size_t)c->sms * kLongTopCap);
     c->d_big_cand.ensure((size_t)c->sms * kLongTopCap);
 }
@@ -496,24 +495,11 @@ void launch_range(blu_ctx* c, const uint8_t* dtext, uint64_t begin, uint64_t end
     p.defer_cap = (uint32_t)std::min<size_t>(k.defer, 0xFFFFFFFFu);
     p.big_rows = c->d_big_rows.p;
     p.big_cand = c->d_big_cand.p;
-    p.bail = c->d_bail.p;
-    p.bail_cap = (uint32_t)(c->d_bail.cap / 2);
     p.ctr = c->d_ctr;
     cudaEvent_t* ev = c->ev[slot];
-    // BLU_TILE_CTA=1: the CTA-per-segment kernel of round 1 over the whole text (A/B measurements); default: the warp-streaming
-    // kernel, with the CTA kernel behind it for the segments whose rows are too long for a warp's windows (normally none)
-    static const bool cta_only = getenv("BLU_TILE_CTA") != nullptr;
     CK(cudaEventRecord(ev[0], s));
-    if (cta_only) {
-        CK(launch_tile_kernel(p, tile_kernel_grid(c->device), s));
-        dbg_sync(s, "tile_kernel");
-    } else {
-        CK(launch_wtile_kernel(p, wtile_kernel_grid(c->device), s));
-        dbg_sync(s, "wtile_kernel");
-        CK(launch_tile_kernel_list(p, tile_kernel_grid(c->device), s));
-        dbg_sync(s, "tile_kernel<list>");
-        c->tm.n_kernel_launches += 1;
-    }
+    CK(launch_tile_kernel(p, tile_kernel_grid(c->device), s));
+    dbg_sync(s, "tile_kernel");
     CK(cudaEventRecord(ev[1], s));
     CK(launch_longrun_kernel(p, c->sms, s));
     dbg_sync(s, "longrun_kernel");
@@ -1597,7 +1583,7 @@ void blu_ctx_destroy(blu_ctx* c) {
     if (c->out) c->out->release();
     c->dev_pool->close();
     c->d_defer.release(), c->d_pool.release(), c->d_dup.release(), c->d_top.release(), c->d_qhash.release();
-    c->d_big_rows.release(), c->d_big_cand.release(), c->d_bail.release();
+    c->d_big_rows.release(), c->d_big_cand.release();
     if (c->d_ctr) cudaFree(c->d_ctr);
     if (c->h_snap) cudaFreeHost(c->h_snap);
     c->pool->close();

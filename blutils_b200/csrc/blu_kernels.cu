@@ -1200,500 +1200,27 @@ __device__ __forceinline__ void tile_segment(const RunParams& p, StreamSmem& S, 
     __syncthreads();
 }
 
-// kFromList = false: the text [begin, end) is cut into gridDim.x segments, one per CTA.
-// kFromList = true:  the CTAs work through the segments the warp-streaming kernel could not finish (Counters.n_bail entries
-//                    of RunParams.bail: rows too long for its small windows); normally there are none.
-template <bool kFromList>
 __global__ void __launch_bounds__(kTileThreads, kTileCtasPerSm) tile_kernel(const __grid_constant__ RunParams p) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     StreamSmem& S = *reinterpret_cast<StreamSmem*>(smem_raw);
     // a later range of a resident table starts where the previous one stopped (its open last query): no host round trip
     const unsigned long long p_begin = p.begin == kBeginFromCounters ? p.ctr->next_begin : p.begin;
     if (p.end <= p_begin) return;
-    unsigned n_list = 0;
-    if (kFromList) {
-        n_list = p.ctr->n_bail < p.bail_cap ? p.ctr->n_bail : p.bail_cap;
-        if (blockIdx.x >= n_list) return;
-    }
+    // the text [begin, end) is cut into gridDim.x segments, one per CTA
+    const unsigned long long total = p.end - p_begin;
+    unsigned long long seg = (total + gridDim.x - 1) / gridDim.x;
+    if (seg < 4ull * kTile) seg = 4ull * kTile;
+    const unsigned long long seg_lo = p_begin + (unsigned long long)blockIdx.x * seg;
+    if (seg_lo >= p.end) return;
+    const unsigned long long seg_hi = (seg_lo + seg < p.end) ? seg_lo + seg : p.end;
     if (threadIdx.x == 0) {
         mbar_init(&S.mbar[0], 1);
         mbar_init(&S.mbar[1], 1);
     }
     __syncthreads();
     uint32_t ph0 = 0, ph1 = 0;
-    if (kFromList) {
-        for (unsigned i = blockIdx.x; i < n_list; i += gridDim.x) {
-            const unsigned long long lo = p.bail[2 * i], hi = p.bail[2 * i + 1];
-            if (lo < hi) tile_segment(p, S, p_begin, lo, hi, ph0, ph1);
-        }
-    } else {
-        const unsigned long long total = p.end - p_begin;
-        unsigned long long seg = (total + gridDim.x - 1) / gridDim.x;
-        if (seg < 4ull * kTile) seg = 4ull * kTile;
-        const unsigned long long seg_lo = p_begin + (unsigned long long)blockIdx.x * seg;
-        if (seg_lo >= p.end) return;
-        const unsigned long long seg_hi = (seg_lo + seg < p.end) ? seg_lo + seg : p.end;
-        tile_segment(p, S, p_begin, seg_lo, seg_hi, ph0, ph1);
-    }
+    tile_segment(p, S, p_begin, seg_lo, seg_hi, ph0, ph1);
 }
-
-// ---------------------------------------------------------------------------------------------------------------
-// warp-streaming tile kernel
-//
-// Same work and same ownership rules as tile_kernel above, but the unit that streams the text is ONE WARP, not a CTA:
-// every warp walks its own contiguous segment in windows of kWWin bytes (TMA bulk copies into the warp's two private
-// buffers, one mbarrier each), classifies a window's bytes, compacts its row starts with ballots, parses its rows one per
-// lane and folds them into the open query it carries -- all warp-synchronously.  There is no CTA-wide barrier anywhere, no
-// phase tables, no static assignment of runs to warps: round 1's kernel spent a third of its warp time waiting at its
-// three barriers per window (ncu: 2.5 of 7.3 resident warps per scheduler stalled on `barrier`) and left half its warps
-// without a query run in the run phase.  A pass is at most 32 rows (one per lane), so a pass's bit scores, head flags and
-// packed field positions live in registers; the open query's top rows (<= 32) are the only per-query state in shared
-// memory, and every query -- whether it fits a window or spans a hundred -- takes that one path.
-// A warp that meets a row too long for its small window hands the rest of its segment to tile_kernel (32 KB windows),
-// which is launched behind this kernel over the list of such segments and normally finds it empty.
-// ---------------------------------------------------------------------------------------------------------------
-constexpr int kWUnits = kWWin / 32 + 1;      // 32-byte units of a window (+1: the unit that can hold a virtual final newline)
-constexpr int kWRowCap = kWWin / 26 + 8;     // a valid row is >= 26 bytes
-constexpr int kWRecBuf = 16;                 // record headers a warp buffers before it reserves their place with one atomic
-constexpr uint32_t kWSlab = 128;             // top-row slots a warp reserves at a time
-
-struct WarpSmem {
-    alignas(128) uint8_t win[2][kWWin + 128];
-    alignas(8) uint32_t tabm[kWUnits + 7];
-    alignas(8) uint32_t digm[kWUnits + 7];
-    alignas(8) uint32_t nlm[kWUnits + 7];
-    uint16_t row_s[kWRowCap + 2];
-    TopRowRaw tops[kCarryTop];  // top rows of the open query so far
-    StagedRec rec_buf[kWRecBuf];
-    alignas(8) unsigned long long mbar[2];
-    int bad_byte;
-};
-
-static_assert((sizeof(WarpSmem) * kWWarps + 1024) * kWCtasPerSm <= 227 * 1024, "warp-streaming CTAs must fit one SM");
-
-// the open query a warp carries from pass to pass (warp-uniform registers)
-struct OpenQuery {
-    unsigned long long head_abs;
-    uint32_t qlen, nrows;
-    int32_t mx, g;
-    bool open, deferred;
-};
-
-// what a warp has reserved / buffered (warp-uniform registers)
-struct WarpOut {
-    uint32_t slot_cur, slot_end;
-    int rec_cnt;
-    bool ok;  // false: an output capacity was exceeded (the host grows the arrays and reruns)
-};
-
-__device__ __forceinline__ void w_flush_records(const RunParams& p, WarpSmem& S, WarpOut& W, int lane) {
-    const int n = W.rec_cnt;
-    if (n == 0) return;
-    unsigned long long base = 0;
-    if (lane == 0) base = atomicAdd(&p.ctr->rec_count, (unsigned long long)n);
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (base + (unsigned long long)n > p.rec_cap) {
-        W.ok = false;
-        if (lane == 0) p.ctr->cap_overflow = 1;
-    } else if (lane < n)
-        write_record(p.records + base + lane, S.rec_buf[lane]);
-    W.rec_cnt = 0;
-    __syncwarp();
-}
-
-// The open query ends: its record header is buffered, its top rows go from shared memory to their slots in HBM.
-__device__ __forceinline__ void w_finish(const RunParams& p, WarpSmem& S, OpenQuery& Q, WarpOut& W, int lane) {
-    const unsigned FULL = 0xffffffffu;
-    if (Q.deferred) {
-        if (lane == 0) push_defer(p, Q.head_abs, 0);
-        Q.open = false;
-        return;
-    }
-    const uint32_t g = (uint32_t)Q.g;
-    if (W.slot_cur + g > W.slot_end) {
-        const uint32_t slab = g > kWSlab ? g : kWSlab;
-        unsigned long long rs = 0;
-        if (lane == 0) rs = atomicAdd(&p.ctr->slot_count, (unsigned long long)slab);
-        rs = __shfl_sync(FULL, rs, 0);
-        if (rs + (unsigned long long)slab > p.slot_cap) {
-            W.ok = false;
-            if (lane == 0) p.ctr->cap_overflow = 1;
-        }
-        W.slot_cur = (uint32_t)rs;
-        W.slot_end = (uint32_t)rs + slab;
-    }
-    const uint32_t slot = W.slot_cur;
-    W.slot_cur += g;
-    __syncwarp();  // the tops were written by the lanes that parsed them
-    if (W.ok && (uint32_t)lane < g) p.toprows[slot + (uint32_t)lane] = S.tops[lane];
-    if (lane == 0) {
-        StagedRec sr;
-        sr.abs = Q.head_abs, sr.qlen = Q.qlen, sr.nrows = Q.nrows, sr.mx = Q.mx, sr.slot = slot, sr.gtot = g, sr.pad = 0;
-        S.rec_buf[W.rec_cnt] = sr;
-    }
-    W.rec_cnt++;
-    __syncwarp();
-    if (W.rec_cnt == kWRecBuf) w_flush_records(p, S, W, lane);
-    Q.open = false;
-}
-
-// exact byte-wise classification of one unit (text edges, non-ASCII bytes, the '"' / '\r' search): see classify_unit_slow
-__device__ __noinline__ uint32_t w_classify_unit_slow(WarpSmem& S, const uint8_t* w, int pos0, int vb, int tend, int virt_nl_at, bool publish) {
-    uint32_t nl = 0, tab = 0, dig = 0;
-    int bad = INT_MAX;
-    for (int k = 0; k < 32; k++) {
-        const int pos = pos0 + k;
-        if (pos < vb || pos >= tend) continue;
-        const uint32_t c = w[pos];
-        if (c == '\n') nl |= 1u << k;
-        if (c == '\t') tab |= 1u << k;
-        if (c - '0' <= 9u) dig |= 1u << k;
-        if ((c == '"' || c == '\r') && pos < bad) bad = pos;
-    }
-    if (bad != INT_MAX) atomicMin(&S.bad_byte, bad);
-    if (virt_nl_at >= pos0 && virt_nl_at < pos0 + 32) nl |= 1u << (virt_nl_at - pos0);
-    if (publish) {
-        const int u = pos0 >> 5;
-        S.tabm[u] = tab;
-        S.digm[u] = dig;
-        S.nlm[u] = nl;
-    }
-    return nl;
-}
-
-__device__ __noinline__ int w_row_end_search(const WarpSmem& S, int s, int limit) {
-    for (int u = s >> 5; (u << 5) <= limit; u++) {
-        uint32_t w = S.nlm[u];
-        if (u == (s >> 5)) w &= ~0u << (s & 31);
-        if (w) return (u << 5) + __ffs(w) - 1;
-    }
-    return limit;
-}
-
-__global__ void __launch_bounds__(kWWarps * 32, kWCtasPerSm) wtile_kernel(const __grid_constant__ RunParams p) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31, wic = threadIdx.x >> 5;
-    WarpSmem& S = reinterpret_cast<WarpSmem*>(smem_raw)[wic];
-    const uint32_t lt = (1u << lane) - 1u;
-    const unsigned long long p_begin = p.begin == kBeginFromCounters ? p.ctr->next_begin : p.begin;
-    if (p.end <= p_begin) return;
-    // ---- this warp's segment ---------------------------------------------------------------------------------------
-    const unsigned long long total = p.end - p_begin;
-    const unsigned long long n_warps = (unsigned long long)gridDim.x * kWWarps;
-    unsigned long long seg = (total + n_warps - 1) / n_warps;
-    if (seg < 4ull * kWWin) seg = 4ull * kWWin;
-    const unsigned long long seg_lo = p_begin + ((unsigned long long)blockIdx.x * kWWarps + (unsigned long long)wic) * seg;
-    if (seg_lo >= p.end) return;
-    const unsigned long long seg_hi = (seg_lo + seg < p.end) ? seg_lo + seg : p.end;
-    const unsigned long long b16 = p_begin & ~15ull;
-    const unsigned long long up = (p.end + 15ull) & ~15ull;
-    if (lane == 0) {
-        mbar_init(&S.mbar[0], 1);
-        mbar_init(&S.mbar[1], 1);
-        S.bad_byte = INT_MAX;
-    }
-    if (lane < 7) S.tabm[kWUnits + lane] = S.digm[kWUnits + lane] = S.nlm[kWUnits + lane] = 0u;
-    __syncwarp();
-    OpenQuery Q;
-    Q.head_abs = 0, Q.qlen = 0, Q.nrows = 0, Q.mx = INT32_MIN, Q.g = 0, Q.open = false, Q.deferred = false;
-    WarpOut W;
-    W.slot_cur = W.slot_end = 0, W.rec_cnt = 0, W.ok = true;
-    uint32_t ph0 = 0, ph1 = 0;
-    int buf = 0;
-    unsigned long long own_from = seg_lo;  // rows that start at or after this offset have not been processed yet
-    // the window being processed
-    unsigned long long lo = seg_lo > p_begin + kBack ? (seg_lo - kBack) & ~15ull : b16;
-    if (lo < b16) lo = b16;
-    auto window_bytes = [&](unsigned long long at) { return (int)(up - at < (unsigned long long)kWWin ? up - at : (unsigned long long)kWWin); };
-    if (lane == 0) {
-        const int n = window_bytes(lo);
-        fence_proxy_async();
-        mbar_expect_tx(&S.mbar[0], (uint32_t)n);
-        tma_bulk_g2s(S.win[0], p.text + lo, (uint32_t)n, &S.mbar[0]);
-    }
-    bool bail = false;
-
-    while (true) {
-        const uint8_t* const win = S.win[buf];
-        const int loaded = window_bytes(lo);
-        const int tend = (int)(p.end - lo < (unsigned long long)loaded ? p.end - lo : (unsigned long long)loaded);
-        const bool has_begin = lo <= p_begin;
-        const int vb = has_begin ? (int)(p_begin - lo) : 0;
-        const bool covers_eof = p.end <= lo + (unsigned long long)loaded;
-        {
-            uint32_t& ph = buf ? ph1 : ph0;
-            while (!mbar_try_wait(&S.mbar[buf], ph)) {
-            }
-            ph ^= 1;
-        }
-        // an unterminated last row of the input is closed by a virtual newline at `tend`
-        const bool virt_nl = p.final_chunk && covers_eof && tend > vb && win[tend - 1] != '\n';
-        const int scan_len = tend + (virt_nl ? 1 : 0);
-        const int n_units = (scan_len + 31) >> 5;
-        const bool interior = !has_begin && tend == kWWin && !virt_nl;
-
-        // ---- classify + row starts: 32 units (1 KB) per round, starts compacted straight into the row table --------------
-        int n_starts = 0, last_nl = -1;
-        uint32_t crowd = 0, blank = 0;
-        {
-            uint32_t carry_in = 0;
-            for (int base = 0; base < n_units; base += 32) {
-                const int u = base + lane;
-                const int pos0 = u << 5;
-                uint32_t nl = 0;
-                const bool live = u < n_units;
-                const bool edge = !interior && ((has_begin && pos0 <= vb) || pos0 + 32 > tend);  // first / last bytes of the text
-                if (live) {
-                    const uint4 v0 = *reinterpret_cast<const uint4*>(win + pos0);
-                    const uint4 v1 = *reinterpret_cast<const uint4*>(win + pos0 + 16);
-                    const uint32_t x[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-                    const uint32_t hi = (x[0] | x[1] | x[2] | x[3] | x[4] | x[5] | x[6] | x[7]) & 0x80808080u;
-                    if (__builtin_expect(edge || hi != 0, 0)) {
-                        nl = w_classify_unit_slow(S, win, pos0, vb, tend, virt_nl ? tend : -1, true);
-                    } else {
-                        // ASCII bytes: per-byte sums stay below 0x100, so plain 32-bit adds classify four bytes at once
-                        uint32_t fn[8], ft[8], fd[8], sus = 0;
-#pragma unroll
-                        for (int k = 0; k < 8; k++) {
-                            uint32_t tu = (x[k] ^ 0x09090909u) + 0x7F7F7F7Fu;  // bit 7 clear <=> tab
-                            uint32_t nu = (x[k] ^ 0x0A0A0A0Au) + 0x7F7F7F7Fu;  // bit 7 clear <=> newline
-                            asm("" : "+r"(tu));
-                            asm("" : "+r"(nu));
-                            const uint32_t ge30 = x[k] + 0x50505050u, ge3a = x[k] + 0x46464646u, ge23 = x[k] + 0x5D5D5D5Du;
-                            ft[k] = ~tu & 0x80808080u;
-                            fn[k] = ~nu & 0x80808080u;
-                            fd[k] = ge30 & ~ge3a & 0x80808080u;
-                            sus |= ~ge23 & tu & nu;  // below '#' and neither tab nor newline: look closer
-                        }
-                        nl = pack32(fn);
-                        S.tabm[u] = pack32(ft);
-                        S.digm[u] = pack32(fd);
-                        S.nlm[u] = nl;
-                        if (__builtin_expect((sus & 0x80808080u) != 0, 0)) w_classify_unit_slow(S, win, pos0, vb, tend, -1, false);  // exact '"' / '\r' search
-                    }
-                }
-                // row starts: a non-newline byte behind a newline (or behind the virtual newline in front of the text)
-                const uint32_t upv = __shfl_up_sync(FULL, nl, 1);
-                const uint32_t carry = lane == 0 ? carry_in : (upv >> 31);
-                carry_in = __shfl_sync(FULL, nl, 31) >> 31;
-                uint32_t prev = (nl << 1) | carry;
-                uint32_t st;
-                if (__builtin_expect(edge || (base == 0 && lane == 0), 0)) {
-                    // (the window's very first byte has no predecessor in the window: it starts a row only as the first byte of the
-                    // text; the look-behind guarantees that no owned row starts there otherwise)
-                    const uint32_t valid_lo = pos0 >= vb ? ~0u : (vb - pos0 >= 32 ? 0u : ~0u << (vb - pos0));
-                    const uint32_t valid_hi = pos0 + 32 <= tend ? ~0u : (tend <= pos0 ? 0u : ~0u >> (32 - (tend - pos0)));
-                    if (pos0 <= vb) prev &= valid_lo;  // the byte in front of vb is not text
-                    if (has_begin && vb >= pos0 && vb < pos0 + 32) prev |= 1u << (vb - pos0);
-                    st = prev & ~nl & valid_lo & valid_hi;
-                } else
-                    st = prev & ~nl;
-                if (!live) st = 0;
-                blank |= nl & prev;
-                // a valid row is >= 26 bytes: at most one start per 16 bytes, compacted with one ballot per half
-                const uint32_t sl = st & 0xFFFFu, sh = st >> 16;
-                crowd |= (sl & (sl - 1u)) | (sh & (sh - 1u));
-                const unsigned bl = __ballot_sync(FULL, sl != 0), bh = __ballot_sync(FULL, sh != 0);
-                int idx = n_starts + __popc(bl & lt) + __popc(bh & lt);
-                if (sl && idx < kWRowCap) S.row_s[idx] = (uint16_t)(pos0 + __ffs(sl) - 1);
-                if (sl) idx++;
-                if (sh && idx < kWRowCap) S.row_s[idx] = (uint16_t)(pos0 + 16 + __ffs(sh) - 1);
-                n_starts += __popc(bl) + __popc(bh);
-                // the last newline so far
-                const unsigned nb = __ballot_sync(FULL, nl != 0);
-                if (nb) {
-                    const int src = 31 - __clz(nb);
-                    const uint32_t wv = __shfl_sync(FULL, nl, src);
-                    last_nl = ((base + src) << 5) + 31 - __clz(wv);
-                }
-            }
-            crowd = __any_sync(FULL, crowd != 0) ? 1u : 0u;
-            blank = __any_sync(FULL, blank != 0) ? 1u : 0u;
-        }
-        if (lane < 4) S.tabm[n_units + lane] = S.digm[n_units + lane] = S.nlm[n_units + lane] = 0u;
-        __syncwarp();
-        if (crowd || n_starts > kWRowCap) {
-            // a row shorter than 16 bytes / more rows than 26-byte rows fit: malformed input
-            if (lane == 0) report(p.ctr, DE_BAD_FIELD_COUNT, lo);
-            break;  // (no copy in flight: the next window has not been requested)
-        }
-        if (lane == 0 && S.bad_byte != INT_MAX) {
-            report(p.ctr, DE_QUOTE_OR_CR, lo + (unsigned)S.bad_byte);
-            S.bad_byte = INT_MAX;
-        }
-        // ---- the window's geometry; the next window's bytes are requested before the rows are looked at ---------------------
-        const int last_start = n_starts > 0 ? (int)S.row_s[n_starts - 1] : -1;
-        const int n_complete = (n_starts > 0 && last_start > last_nl) ? n_starts - 1 : n_starts;
-        const int lc = n_complete > 0 ? (int)S.row_s[n_complete - 1] : -1;  // the last complete row: the look-behind row of the next window
-        const bool progress = lc >= 0 && lo + (unsigned long long)lc >= own_from;  // a complete row this warp had not seen yet
-        unsigned long long next_lo = lo;
-        if (progress) {
-            const unsigned long long la = lo + (unsigned long long)lc;
-            next_lo = la > p_begin ? (la - 1) & ~15ull : b16;
-            if (next_lo < b16) next_lo = b16;
-        }
-        const bool may_continue = progress && !covers_eof && next_lo > lo;
-        if (lane == 0) {
-            if (n_complete == n_starts) S.row_s[n_starts] = (uint16_t)(last_nl + 1);  // sentinel: end of the last row
-            if (may_continue) {
-                const int n = window_bytes(next_lo);
-                fence_proxy_async();
-                mbar_expect_tx(&S.mbar[buf ^ 1], (uint32_t)n);
-                tma_bulk_g2s(S.win[buf ^ 1], p.text + next_lo, (uint32_t)n, &S.mbar[buf ^ 1]);
-            }
-        }
-        __syncwarp();
-        const bool closes = covers_eof && p.final_chunk;  // the end of this window ends the open query
-        bool term = false;
-        // ---- passes of up to 32 rows: one row per lane ------------------------------------------------------------------------
-        for (int rb = 0; rb < n_complete && !term; rb += 32) {
-            const int r = rb + lane;
-            const bool live = r < n_complete;
-            bool head = false, parsed = false;
-            int s = 0, ql = 0, prv = -1;
-            int32_t b32 = INT32_MIN;
-            uint32_t info = 0;
-            bool ovf = false;
-            unsigned long long abs = 0;
-            if (live) {
-                s = S.row_s[r];
-                abs = lo + (unsigned long long)s;
-                if (abs >= own_from) {  // (else: look-behind row, seen by the previous window / owned by the previous segment)
-                    const int e = blank ? w_row_end_search(S, s, scan_len) : (int)S.row_s[r + 1] - 1;
-                    if (e < scan_len) {
-                        int64_t bits;
-                        if (!parse_row_lean(win, S.tabm, S.digm, s, e, bits, ql, info)) {
-                            const LightRow lr = parse_row_masked(win, reinterpret_cast<const uint64_t*>(S.tabm), reinterpret_cast<const uint64_t*>(S.digm), s, e);
-                            if (lr.err) report(p.ctr, lr.err, abs);
-                            bits = lr.bits;
-                            ql = lr.q_len;
-                            info = 0;
-                        }
-                        b32 = (int32_t)bits;
-                        ovf = (int64_t)b32 != bits;
-                        prv = r > 0 ? (int)S.row_s[r - 1] : -1;
-                        parsed = true;
-                    }
-                }
-            }
-            __syncwarp();  // the lanes part ways in the parser (evalue shapes, the rare full-grammar path): back together for the compare
-            if (parsed) {
-                if (prv < 0) {
-                    head = has_begin;  // first row of the text; else: predecessor not in the window
-                    if (!head) push_defer(p, abs, 1);  // the block path decides whether it starts a query
-                } else
-                    head = !same_qid_lean(win, S.tabm, s, ql, prv);
-            }
-            const unsigned pm = __ballot_sync(FULL, parsed);
-            unsigned hm = __ballot_sync(FULL, head);
-            // a query of the next segment starts in this pass: this warp's walk ends in front of it
-            const unsigned fm = __ballot_sync(FULL, head && abs >= seg_hi);
-            unsigned rows_m = pm;
-            if (fm) {
-                term = true;
-                const unsigned keep = (1u << (__ffs(fm) - 1)) - 1u;
-                rows_m &= keep;
-                hm &= keep;
-            }
-            // rows without a predecessor that are not heads for sure (handed to the block path) belong to nobody here
-            const unsigned orphan = __ballot_sync(FULL, parsed && prv < 0 && !head);
-            rows_m &= ~orphan;
-            // ---- fold the pass into queries: a segment of lanes per query -----------------------------------------------------
-            unsigned rest = rows_m;
-            while (rest) {
-                const int a = __ffs(rest) - 1;                         // first row of the segment
-                const unsigned above = hm & rest & ~((2u << a) - 1u);  // the next head behind it
-                const int bnd = above ? __ffs(above) - 1 : 32;
-                const unsigned seg_m = rest & (bnd >= 32 ? ~0u : ((1u << bnd) - 1u));
-                rest &= ~seg_m;
-                const bool starts = (hm >> a) & 1u;
-                if (starts) {
-                    if (Q.open) w_finish(p, S, Q, W, lane);
-                    Q.open = true, Q.deferred = false;
-                    Q.head_abs = __shfl_sync(FULL, abs, a);
-                    const int qlh = __shfl_sync(FULL, ql, a);
-                    Q.qlen = (uint32_t)qlh;
-                    Q.nrows = 0, Q.mx = INT32_MIN, Q.g = 0;
-                } else if (!Q.open)
-                    continue;  // rows in front of the segment's first query: the previous warp's
-                const bool in = (seg_m >> lane) & 1u;
-                const int mxp = __reduce_max_sync(FULL, in ? b32 : INT32_MIN);
-                if (__any_sync(FULL, in && ovf)) Q.deferred = true;
-                Q.nrows += (uint32_t)__popc(seg_m);
-                if (mxp > Q.mx) {
-                    Q.mx = mxp;
-                    Q.g = 0;
-                }
-                const unsigned tm = __ballot_sync(FULL, in && b32 == Q.mx);
-                const int gp = __popc(tm);
-                if (!Q.deferred && gp) {
-                    if (Q.g + gp > kCarryTop)
-                        Q.deferred = true;
-                    else {
-                        if ((tm >> lane) & 1u) {
-                            // fields 1..4 of a top row through the tab positions the row parser found: digit folds only; a row of any
-                            // other shape leaves unparsed (offset + length) and is split by the consensus kernel's full parser
-                            TopRowRaw ref;
-                            if (!top_row_from_info(win, s, info, lo, ref)) {
-                                const int e = blank ? w_row_end_search(S, s, scan_len) : (int)S.row_s[r + 1] - 1;
-                                ref.acc_off = lo + (unsigned long long)s;
-                                ref.acc_len = (uint32_t)(e - s);
-                                ref.taxid = 0, ref.alnlen = 0, ref.pident = 0.0;
-                                ref.dec_frac = kTopRowUnparsed;
-                            }
-                            S.tops[Q.g + __popc(tm & lt)] = ref;
-                        }
-                        Q.g += gp;
-                    }
-                }
-            }
-        }
-        // ---- where next? -----------------------------------------------------------------------------------------------
-        bool done = covers_eof || term;
-        if (term) {
-            if (Q.open) w_finish(p, S, Q, W, lane);
-        } else if (covers_eof && Q.open) {
-            if (closes)
-                w_finish(p, S, Q, W, lane);
-            else {
-                // the input continues in the next chunk: the whole query is carried over by the host
-                if (lane == 0) atomicMin(&p.ctr->tail_start, Q.head_abs);
-                Q.open = false;
-            }
-        }
-        if (!done && !Q.open && lo + (unsigned long long)(last_nl + 1) >= seg_hi) done = true;
-        if (!done && !may_continue) {
-            // no complete new row in a whole window: a row longer than this kernel stages.  The rest of the segment -- from the
-            // open query's first row -- goes to the kernel with the large windows.
-            bail = true;
-            done = true;
-        }
-        if (done) {
-            if (may_continue) {
-                // a copy into the other buffer is in flight: it must land before the warp exits
-                uint32_t& ph = (buf ^ 1) ? ph1 : ph0;
-                while (!mbar_try_wait(&S.mbar[buf ^ 1], ph)) {
-                }
-            }
-            break;
-        }
-        own_from = lo + (unsigned long long)(last_nl + 1);
-        lo = next_lo;
-        buf ^= 1;
-    }
-    if (bail && lane == 0) {
-        const unsigned long long from = Q.open ? Q.head_abs : own_from;
-        const unsigned i = atomicAdd(&p.ctr->n_bail, 1u);
-        if (i < p.bail_cap) {
-            p.bail[2 * i] = from;
-            p.bail[2 * i + 1] = seg_hi;
-        } else
-            p.ctr->cap_overflow = 1;
-    }
-    w_flush_records(p, S, W, lane);
-}
-
 
 // ---------------------------------------------------------------------------------------------------------------
 // long-run kernel: one CTA per deferred run
@@ -2285,8 +1812,7 @@ __device__ __forceinline__ int cmp_acc(unsigned long long a0, unsigned long long
     return (int)alen - (int)blen;
 }
 
-constexpr int kConsThreads = 256;
-constexpr int kConsBatch = kConsThreads / 8;  // queries per CTA iteration of the narrow (8 lanes per query) pass
+constexpr int kConsThreads = 128;
 
 // What a lane holds once its query's consensus is computed; written out after the output space has been reserved.
 struct ConsLane {
@@ -2560,122 +2086,155 @@ __device__ __forceinline__ ConsLane cons_compute(const PostParams& p, bool valid
     return o;
 }
 
-__device__ __forceinline__ void cons_write(const PostParams& p, blu_record* rec, const ConsLane& o, bool lane0, unsigned long long bean_base,
-                                           unsigned long long acc_base, bool space_ok) {
-    if (o.ok && space_ok) {
-        if (o.leader) p.beans[bean_base + o.bean_idx] = o.bean;
-        if (o.keeps) p.accs[acc_base + o.acc_idx].ref = o.acc_ref;
-    }
-    if (lane0) {
-        if (o.ok && space_ok) {
-            rec->keep_mask = o.keep_mask;
-            rec->perc_identity = o.perc_identity;
-            rec->ref_lineage = o.ref_lineage;
-            rec->bean_base = (uint32_t)bean_base;
-            rec->n_beans = (uint32_t)o.nb;
-            rec->acc_base = (uint32_t)acc_base;
-            rec->single_match = o.single ? 1 : 0;
-            rec->mutated = o.mutated ? 1 : 0;
-            rec->reached_pos = (int8_t)o.reached;
-            rec->allowed_pos = (int8_t)o.allowed;
-            rec->bean_level = (int8_t)o.level;
-            rec->status = 1;
-        } else {
-            // a failed query keeps its id (the duplicate-id check must see it) and owns no beans / accession references
-            rec->bean_base = 0, rec->n_beans = 0, rec->acc_base = 0;
-            rec->status = 0;
-        }
+// the record fields the consensus decides (everything but where its beans / accession references end up)
+__device__ __forceinline__ void cons_write_record(blu_record* rec, const ConsLane& o) {
+    if (o.ok) {
+        rec->keep_mask = o.keep_mask;
+        rec->perc_identity = o.perc_identity;
+        rec->ref_lineage = o.ref_lineage;
+        rec->n_beans = (uint32_t)o.nb;
+        rec->single_match = o.single ? 1 : 0;
+        rec->mutated = o.mutated ? 1 : 0;
+        rec->reached_pos = (int8_t)o.reached;
+        rec->allowed_pos = (int8_t)o.allowed;
+        rec->bean_level = (int8_t)o.level;
+        rec->status = 1;
+    } else {
+        // a failed query keeps its id (the duplicate-id check must see it) and owns no beans / accession references
+        rec->bean_base = 0, rec->n_beans = 0, rec->acc_base = 0;
+        rec->status = 0;
     }
 }
 
+constexpr int kConsWarps = kConsThreads / 32;
+constexpr int kConsBatch = 32;  // queries a warp finishes between two reservations of output space
+
+// per-warp staging of one batch's beans / accession references (a narrow query has at most 8 of each)
+struct ConsStage {
+    blu_bean beans[kConsBatch][8];
+    unsigned long long accs[kConsBatch][8];
+    int nb[kConsBatch], na[kConsBatch];
+};
+
 __global__ void __launch_bounds__(kConsThreads) consensus_kernel(const __grid_constant__ PostParams p) {
-    __shared__ int cnt_b[kConsBatch], cnt_a[kConsBatch];
-    __shared__ unsigned long long base_b, base_a;
-    __shared__ int space_ok_sh;
+    __shared__ ConsStage stage_all[kConsWarps];
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int sub = lane >> 3, sl8 = lane & 7;
+    ConsStage& St = stage_all[warp];
     if (p.ctr->cap_overflow) return;  // the tile kernel ran out of space: the host grows the arrays and reruns
     const unsigned long long rb = p.ctr->post_done;
     unsigned long long re = p.ctr->rec_count;
     if (re > p.rec_cap) re = p.rec_cap;
     unsigned long long rows_sum = 0;
-    for (unsigned long long base = rb + (unsigned long long)blockIdx.x * kConsBatch; base < re; base += (unsigned long long)gridDim.x * kConsBatch) {
-        // ---- narrow pass: 8 lanes per query -----------------------------------------------------------------------------
-        const unsigned long long qi = base + (unsigned long long)(warp * 4 + sub);
-        blu_record* rec = p.records + qi;
-        bool todo = false;
-        int g = 0;
-        unsigned long long slot = 0, qoff = 0;
-        if (qi < re) {
-            // (all eight lanes read the header: one sector)
-            const uint32_t st = rec->status;
-            if (sl8 == 0) rows_sum += rec->n_rows;
-            if (st == 2) {
-                todo = true;
-                g = (int)rec->n_beans;
-                slot = rec->bean_base;
-                qoff = rec->query_off;
-                if (slot + (unsigned long long)g > p.slot_cap) todo = false, g = 0;  // (cannot happen without cap_overflow)
-            }
-        }
-        const bool narrow = todo && g >= 1 && g <= 8;
-        const ConsLane o = cons_compute<8>(p, narrow, g, slot, qoff, lane);
-        if (sl8 == 0) {
-            cnt_b[warp * 4 + sub] = o.ok ? o.nb : 0;
-            cnt_a[warp * 4 + sub] = o.ok ? o.nkept : 0;
-        }
-        __syncthreads();
-        if (warp == 0) {
-            const int vb = cnt_b[lane], va = cnt_a[lane];
-            int ib = vb, ia = va;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int tb = __shfl_up_sync(FULL, ib, d), ta = __shfl_up_sync(FULL, ia, d);
-                if (lane >= d) ib += tb, ia += ta;
-            }
-            cnt_b[lane] = ib - vb;
-            cnt_a[lane] = ia - va;
-            if (lane == 31) {
-                const unsigned long long bb = ib ? atomicAdd(&p.ctr->bean_used, (unsigned long long)ib) : 0ull;
-                const unsigned long long ab = ia ? atomicAdd(&p.ctr->acc_used, (unsigned long long)ia) : 0ull;
-                base_b = bb, base_a = ab;
-                const bool fits = bb + (unsigned long long)ib <= p.bean_cap && ab + (unsigned long long)ia <= p.acc_cap;
-                space_ok_sh = fits ? 1 : 0;
-                if (!fits) p.ctr->cap_overflow = 1;
-            }
-        }
-        __syncthreads();
-        if (narrow) cons_write(p, rec, o, sl8 == 0, base_b + (unsigned long long)cnt_b[warp * 4 + sub], base_a + (unsigned long long)cnt_a[warp * 4 + sub], space_ok_sh != 0);
-        // ---- wide pass: top groups of 9..32 rows, one query per warp ------------------------------------------------------
-        unsigned wide = __ballot_sync(FULL, sl8 == 0 && todo && g > 8);
-        while (wide) {
-            const int src = __ffs(wide) - 1;
-            wide &= wide - 1;
-            const int gw = __shfl_sync(FULL, g, src);
-            const unsigned long long slotw = __shfl_sync(FULL, slot, src), qoffw = __shfl_sync(FULL, qoff, src);
-            const unsigned long long qiw = base + (unsigned long long)(warp * 4 + (src >> 3));
-            blu_record* recw = p.records + qiw;
-            if (gw > 32) {
-                if (lane == 0) {
-                    report(p.ctr, DE_INTERNAL, qoffw);
-                    recw->status = 0, recw->n_beans = 0;
+    const unsigned long long gw = (unsigned long long)blockIdx.x * kConsWarps + (unsigned long long)warp;
+    const unsigned long long wstride = (unsigned long long)gridDim.x * kConsWarps * kConsBatch;
+    // A warp finishes 32 queries (eight rounds of four, 8 lanes per query) into its staging area, reserves their output with
+    // one atomic per array and copies them out compactly: no CTA-wide barrier, one reservation per 32 queries.
+    for (unsigned long long base = rb + gw * kConsBatch; base < re; base += wstride) {
+        unsigned wide_any = 0;
+        for (int t = 0; t < kConsBatch / 4; t++) {
+            const int qslot = t * 4 + sub;
+            const unsigned long long qi = base + (unsigned long long)qslot;
+            blu_record* rec = p.records + qi;
+            bool todo = false;
+            int g = 0;
+            unsigned long long slot = 0, qoff = 0;
+            if (qi < re) {
+                const uint32_t st = rec->status;  // (all eight lanes read the header: one sector)
+                if (sl8 == 0) rows_sum += rec->n_rows;
+                if (st == 2) {
+                    todo = true;
+                    g = (int)rec->n_beans;
+                    slot = rec->bean_base;
+                    qoff = rec->query_off;
+                    if (slot + (unsigned long long)g > p.slot_cap) todo = false, g = 0;  // (cannot happen without cap_overflow)
                 }
-                continue;
             }
-            const ConsLane ow = cons_compute<32>(p, true, gw, slotw, qoffw, lane);
-            unsigned long long bb = 0, ab = 0;
-            int fits = 1;
-            if (lane == 0 && ow.ok) {
-                bb = atomicAdd(&p.ctr->bean_used, (unsigned long long)ow.nb);
-                ab = atomicAdd(&p.ctr->acc_used, (unsigned long long)ow.nkept);
-                fits = bb + (unsigned long long)ow.nb <= p.bean_cap && ab + (unsigned long long)ow.nkept <= p.acc_cap;
-                if (!fits) p.ctr->cap_overflow = 1;
+            const bool narrow = todo && g >= 1 && g <= 8;
+            wide_any |= __ballot_sync(FULL, sl8 == 0 && todo && g > 8) ? 1u << t : 0u;
+            const ConsLane o = cons_compute<8>(p, narrow, g, slot, qoff, lane);
+            if (o.ok && o.leader) St.beans[qslot][o.bean_idx] = o.bean;
+            if (o.ok && o.keeps) St.accs[qslot][o.acc_idx] = o.acc_ref;
+            if (sl8 == 0) {
+                St.nb[qslot] = o.ok ? o.nb : 0;
+                St.na[qslot] = o.ok ? o.nkept : 0;
+                if (narrow) cons_write_record(rec, o);
             }
-            bb = __shfl_sync(FULL, bb, 0), ab = __shfl_sync(FULL, ab, 0), fits = __shfl_sync(FULL, fits, 0);
-            cons_write(p, recw, ow, lane == 0, bb, ab, fits != 0);
         }
-        __syncthreads();  // cnt_* / base_* are rewritten by the next iteration
+        __syncwarp();
+        // ---- output space for the batch: lane = query -------------------------------------------------------------------------
+        const int vb = St.nb[lane], va = St.na[lane];
+        int ib = vb, ia = va;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int tb = __shfl_up_sync(FULL, ib, d), ta = __shfl_up_sync(FULL, ia, d);
+            if (lane >= d) ib += tb, ia += ta;
+        }
+        const int tot_b = __shfl_sync(FULL, ib, 31), tot_a = __shfl_sync(FULL, ia, 31);
+        unsigned long long bb = 0, ab = 0;
+        if (lane == 0) {
+            if (tot_b) bb = atomicAdd(&p.ctr->bean_used, (unsigned long long)tot_b);
+            if (tot_a) ab = atomicAdd(&p.ctr->acc_used, (unsigned long long)tot_a);
+        }
+        bb = __shfl_sync(FULL, bb, 0), ab = __shfl_sync(FULL, ab, 0);
+        const bool fits = bb + (unsigned long long)tot_b <= p.bean_cap && ab + (unsigned long long)tot_a <= p.acc_cap;
+        if (!fits && lane == 0) p.ctr->cap_overflow = 1;
+        const unsigned long long my_b = bb + (unsigned long long)(ib - vb), my_a = ab + (unsigned long long)(ia - va);
+        if (fits && vb > 0) {
+            blu_record* rec = p.records + base + (unsigned long long)lane;
+            rec->bean_base = (uint32_t)my_b;
+            rec->acc_base = (uint32_t)my_a;
+        }
+        if (fits) {
+            for (int t = 0; t < kConsBatch / 4; t++) {
+                const int qslot = t * 4 + sub;
+                const unsigned long long qb = __shfl_sync(FULL, my_b, qslot), qa = __shfl_sync(FULL, my_a, qslot);
+                const int nbq = __shfl_sync(FULL, vb, qslot), naq = __shfl_sync(FULL, va, qslot);
+                if (sl8 < nbq) p.beans[qb + sl8] = St.beans[qslot][sl8];
+                if (sl8 < naq) p.accs[qa + sl8].ref = St.accs[qslot][sl8];
+            }
+        }
+        __syncwarp();
+        // ---- top groups of 9..32 rows: one query per warp, its own reservation ------------------------------------------------
+        while (wide_any) {
+            const int t = __ffs(wide_any) - 1;
+            wide_any &= wide_any - 1;
+            for (int sb = 0; sb < 4; sb++) {
+                const unsigned long long qi = base + (unsigned long long)(t * 4 + sb);
+                if (qi >= re) break;
+                blu_record* rec = p.records + qi;
+                if (rec->status != 2) continue;
+                const int gw2 = (int)rec->n_beans;
+                const unsigned long long slotw = rec->bean_base, qoffw = rec->query_off;
+                if (gw2 <= 8) continue;
+                if (gw2 > 32 || slotw + (unsigned long long)gw2 > p.slot_cap) {
+                    if (lane == 0) {
+                        report(p.ctr, DE_INTERNAL, qoffw);
+                        rec->status = 0, rec->n_beans = 0;
+                    }
+                    continue;
+                }
+                const ConsLane ow = cons_compute<32>(p, true, gw2, slotw, qoffw, lane);
+                unsigned long long wb = 0, wa = 0;
+                int wfits = 1;
+                if (lane == 0 && ow.ok) {
+                    wb = atomicAdd(&p.ctr->bean_used, (unsigned long long)ow.nb);
+                    wa = atomicAdd(&p.ctr->acc_used, (unsigned long long)ow.nkept);
+                    wfits = wb + (unsigned long long)ow.nb <= p.bean_cap && wa + (unsigned long long)ow.nkept <= p.acc_cap;
+                    if (!wfits) p.ctr->cap_overflow = 1;
+                }
+                wb = __shfl_sync(FULL, wb, 0), wa = __shfl_sync(FULL, wa, 0), wfits = __shfl_sync(FULL, wfits, 0);
+                if (ow.ok && wfits) {
+                    if (ow.leader) p.beans[wb + ow.bean_idx] = ow.bean;
+                    if (ow.keeps) p.accs[wa + ow.acc_idx].ref = ow.acc_ref;
+                }
+                if (lane == 0) {
+                    cons_write_record(rec, ow);
+                    if (ow.ok && wfits) rec->bean_base = (uint32_t)wb, rec->acc_base = (uint32_t)wa;
+                }
+            }
+        }
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) rows_sum += __shfl_xor_sync(FULL, rows_sum, d);
@@ -2840,7 +2399,6 @@ __global__ void advance_kernel(const AdvanceParams p) {
     }
     c->n_defer = 0;
     c->work_ticket = 0;
-    c->n_bail = 0;
     c->tail_start = ~0ull;
 }
 
@@ -2850,11 +2408,7 @@ __global__ void advance_kernel(const AdvanceParams p) {
 // launchers
 // ---------------------------------------------------------------------------------------------------------------
 cudaError_t kernels_set_attributes() {
-    cudaError_t e = cudaFuncSetAttribute(tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamSmem));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamSmem));
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(wtile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(WarpSmem) * kWWarps));
+    cudaError_t e = cudaFuncSetAttribute(tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(StreamSmem));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(longrun_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(LongSmem));
 }
@@ -2866,24 +2420,7 @@ int tile_kernel_grid(int device) {
 }
 
 cudaError_t launch_tile_kernel(const RunParams& p, int grid, cudaStream_t s) {
-    tile_kernel<false><<<grid, kTileThreads, sizeof(StreamSmem), s>>>(p);
-    return cudaGetLastError();
-}
-
-// the segments the warp-streaming kernel handed over (normally none: the CTAs return at once)
-cudaError_t launch_tile_kernel_list(const RunParams& p, int grid, cudaStream_t s) {
-    tile_kernel<true><<<grid, kTileThreads, sizeof(StreamSmem), s>>>(p);
-    return cudaGetLastError();
-}
-
-int wtile_kernel_grid(int device) {
-    int sms = 148;
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    return kWCtasPerSm * sms;
-}
-
-cudaError_t launch_wtile_kernel(const RunParams& p, int grid, cudaStream_t s) {
-    wtile_kernel<<<grid, kWWarps * 32, sizeof(WarpSmem) * kWWarps, s>>>(p);
+    tile_kernel<<<grid, kTileThreads, sizeof(StreamSmem), s>>>(p);
     return cudaGetLastError();
 }
 
@@ -2895,7 +2432,7 @@ cudaError_t launch_longrun_kernel(const RunParams& p, int grid, cudaStream_t s) 
 // The post-pass kernels take their record range from the device counters (no host round trip between the tile kernel
 // and them): fixed grids, grid-stride loops.
 cudaError_t launch_consensus_kernel(const PostParams& p, int sms, cudaStream_t s) {
-    consensus_kernel<<<sms * 8, kConsThreads, 0, s>>>(p);
+    consensus_kernel<<<sms * 16, kConsThreads, 0, s>>>(p);
     return cudaGetLastError();
 }
 

@@ -29,7 +29,7 @@ struct Counters {
                                 // hit it although the merged query would not (the reference only parses the top group's rows)
     unsigned int dup_found;     // a query id occurs in two separate runs
     unsigned int cap_overflow;  // some output capacity was exceeded (host grows and retries)
-    unsigned int n_bail;        // segments the warp-streaming kernel handed to the kernel with the large windows
+    unsigned int pad0;
     unsigned int pad;
 };
 
@@ -52,8 +52,6 @@ struct RunParams {
     uint64_t acc_cap;
     uint64_t* defer;       // (offset << 1) | check_prev
     uint32_t defer_cap;
-    unsigned long long* bail;  // (from, segment end) pairs: what the warp-streaming kernel could not finish (rows too long for its windows)
-    uint32_t bail_cap;
     TopRow* big_rows;      // scratch of the long-run kernel: kLongTopCap joined top rows per CTA
     unsigned long long* big_cand;  // ... and as many candidate references (offset << 16 | length)
     Counters* ctr;
@@ -121,24 +119,7 @@ constexpr int kTileThreads = BLU_TILE_THREADS;
 constexpr int kTileCtasPerSm = BLU_TILE_CTAS;
 constexpr int kWin = 60416;             // window of the block path (long-run kernel)
 
-// Geometry of the warp-streaming tile kernel: every warp streams its own segment through two private windows.
-#ifndef BLU_WWIN_BYTES
-#define BLU_WWIN_BYTES 2048
-#endif
-#ifndef BLU_WWARPS
-#define BLU_WWARPS 4
-#endif
-#ifndef BLU_WCTAS
-#define BLU_WCTAS 7
-#endif
-constexpr int kWWin = BLU_WWIN_BYTES;   // bytes a warp stages per window
-constexpr int kWWarps = BLU_WWARPS;     // warps per CTA (they share nothing but the CTA's shared-memory allocation)
-constexpr int kWCtasPerSm = BLU_WCTAS;
-
 int tile_kernel_grid(int device);
-int wtile_kernel_grid(int device);
-cudaError_t launch_wtile_kernel(const RunParams& p, int grid, cudaStream_t s);
-cudaError_t launch_tile_kernel_list(const RunParams& p, int grid, cudaStream_t s);
 cudaError_t launch_tile_kernel(const RunParams& p, int grid, cudaStream_t s);
 cudaError_t launch_longrun_kernel(const RunParams& p, int grid, cudaStream_t s);
 cudaError_t launch_consensus_kernel(const PostParams& p, int sms, cudaStream_t s);
