@@ -2,9 +2,14 @@
 // the writer of `write_blutils_output` (reference core/src/use_cases/write_blutils_output.rs:33-250).
 // Header-only so that the C ABI (blu_api.cpp) and the test-only host simulation (tests/csrc) share it.
 #pragma once
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <atomic>
+#include <cerrno>
 #include <cstdio>
+#include <memory>
 #include <cstring>
 #include <filesystem>
 #include <random>
@@ -290,29 +295,74 @@ inline std::vector<Entry> sorted_entries(const ResultView* r) {
     return v;
 }
 
-// Formats entries [0, n) with `emit(out, i)` on all host threads, blocks of entries at a time, and writes the blocks to `f` in
-// order while later ones are still being formatted.
+// Formats entries [0, n) with `emit(out, i)` on all host threads, blocks of entries at a time.  To a regular file every
+// thread writes its own blocks with pwrite() at the offset its predecessors' sizes give it (the copy into the page cache is
+// what a single writer thread is bound by: ~2 GB/s); to a pipe / terminal the blocks are written in order by the caller's
+// thread while later ones are still being formatted.  Returns false on a write error.
 template <class Emit>
-void ordered_parallel_write(FILE* f, size_t n, Emit&& emit) {
+bool ordered_parallel_write(FILE* f, size_t n, Emit&& emit) {
     const size_t B = 4096;
     const size_t nblocks = (n + B - 1) / B;
     const unsigned nt = (unsigned)std::min<size_t>(host_threads(), nblocks);
     if (nt <= 1 || nblocks < 4) {
         std::string o;
+        bool ok = true;
         for (size_t i = 0; i < n; i++) {
             emit(o, i);
             if (o.size() > (8u << 20)) {
-                fwrite(o.data(), 1, o.size(), f);
+                ok &= fwrite(o.data(), 1, o.size(), f) == o.size();
                 o.clear();
             }
         }
-        fwrite(o.data(), 1, o.size(), f);
-        return;
+        ok &= fwrite(o.data(), 1, o.size(), f) == o.size();
+        return ok;
+    }
+    fflush(f);
+    const int fd = fileno(f);
+    struct stat st;
+    const bool seekable = fd >= 0 && fstat(fd, &st) == 0 && S_ISREG(st.st_mode);
+    std::atomic<size_t> next{0};
+    std::atomic<bool> failed{false};
+    if (seekable) {
+        const long long base_off = (long long)ftello(f);
+        std::unique_ptr<std::atomic<long long>[]> end_off(new std::atomic<long long>[nblocks]);
+        for (size_t b = 0; b < nblocks; b++) end_off[b].store(-1);
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; t++)
+            th.emplace_back([&] {
+                std::string o;
+                for (;;) {
+                    const size_t b = next.fetch_add(1);
+                    if (b >= nblocks) return;
+                    o.clear();
+                    o.reserve(B * 512);
+                    const size_t e = std::min(n, (b + 1) * B);
+                    for (size_t i = b * B; i < e; i++) emit(o, i);
+                    long long off = base_off;
+                    if (b) {
+                        while ((off = end_off[b - 1].load(std::memory_order_acquire)) < 0) std::this_thread::yield();
+                    }
+                    end_off[b].store(off + (long long)o.size(), std::memory_order_release);
+                    size_t done = 0;
+                    while (done < o.size()) {
+                        const ssize_t w = pwrite(fd, o.data() + done, o.size() - done, (off_t)(off + (long long)done));
+                        if (w < 0 && errno == EINTR) continue;
+                        if (w <= 0) {
+                            failed = true;
+                            break;
+                        }
+                        done += (size_t)w;
+                    }
+                }
+            });
+        for (auto& x : th) x.join();
+        if (failed) return false;
+        return fseeko(f, (off_t)end_off[nblocks - 1].load(), SEEK_SET) == 0;
     }
     std::vector<std::string> out(nblocks);
     std::unique_ptr<std::atomic<int>[]> ready(new std::atomic<int>[nblocks]);
     for (size_t b = 0; b < nblocks; b++) ready[b].store(0);
-    std::atomic<size_t> next{0}, written{0};
+    std::atomic<size_t> written{0};
     const size_t window = 4 * (size_t)nt;  // blocks formatted ahead of the writer: bounds the memory
     std::vector<std::thread> th;
     for (unsigned t = 0; t < nt; t++)
@@ -328,13 +378,15 @@ void ordered_parallel_write(FILE* f, size_t n, Emit&& emit) {
                 ready[b].store(1, std::memory_order_release);
             }
         });
+    bool ok = true;
     for (size_t b = 0; b < nblocks; b++) {
         while (!ready[b].load(std::memory_order_acquire)) std::this_thread::yield();
-        fwrite(out[b].data(), 1, out[b].size(), f);
+        ok &= fwrite(out[b].data(), 1, out[b].size(), f) == out[b].size();
         std::string().swap(out[b]);
         written.store(b + 1, std::memory_order_release);
     }
     for (auto& x : th) x.join();
+    return ok;
 }
 
 inline std::string uuid_v4() {
@@ -614,10 +666,11 @@ inline int view_write(const ResultView* r, const char* path, int format, const c
             if (!f) return BLU_ERR_IO;
         }
         const bool pretty = format == BLU_FORMAT_JSON && path != nullptr;  // to_string_pretty to a file, compact to stdout
+        bool wok = true;
         auto put = [&](const char* t) { fwrite(t, 1, strlen(t), f); };
         if (format == BLU_FORMAT_JSON) {
             put(pretty ? "{\n  \"results\": [" : "{\"results\":[");
-            ordered_parallel_write(f, ent.size(), [&](std::string& o, size_t i) {
+            wok &= ordered_parallel_write(f, ent.size(), [&](std::string& o, size_t i) {
                 if (i) o.push_back(',');
                 if (pretty) o += "\n    ";
                 d.object(o, ent[i].query, ent[i].part, ent[i].rec, run_id.c_str(), pretty, 2);
@@ -628,7 +681,7 @@ inline int view_write(const ResultView* r, const char* path, int format, const c
                 put("],\"config\":null}");
         } else if (format == BLU_FORMAT_JSONL) {
             put("null\n");  // serde_json::to_string(&config) with config = None
-            ordered_parallel_write(f, ent.size(), [&](std::string& o, size_t i) {
+            wok &= ordered_parallel_write(f, ent.size(), [&](std::string& o, size_t i) {
                 d.object(o, ent[i].query, ent[i].part, ent[i].rec, run_id.c_str(), false, 0);
                 o.push_back('\n');
             });
@@ -636,7 +689,7 @@ inline int view_write(const ResultView* r, const char* path, int format, const c
             // serde_yaml 0.9 block style of BlutilsOutput{results, config}
             const HostTaxonomy& T = *r->tax;
             put(ent.empty() ? "results: []\n" : "results:\n");
-            ordered_parallel_write(f, ent.size(), [&](std::string& o, size_t i) {
+            wok &= ordered_parallel_write(f, ent.size(), [&](std::string& o, size_t i) {
                 const Entry& en = ent[i];
                 std::string tmp;
                 o += "- runId: ";
@@ -708,10 +761,10 @@ inline int view_write(const ResultView* r, const char* path, int format, const c
             put("config: null\n");
         }
         if (path)
-            fclose(f);
+            wok &= fclose(f) == 0;
         else
             fflush(stdout);
-        return BLU_OK;
+        return wok ? BLU_OK : BLU_ERR_IO;
     }
 }
 
@@ -737,26 +790,24 @@ inline int view_write_tabular(const ResultView* r, const char* path, const char*
         if (dot != std::string::npos && (slash == std::string::npos || dot > slash)) target.resize(dot);
         target += ".tsv";
         std::remove(target.c_str());
-        f = fopen(target.c_str(), "ab");
+        f = fopen(target.c_str(), "wb");  // (the reference appends to a file it has just removed; pwrite needs a non-append descriptor)
         if (!f) return BLU_ERR_IO;
     }
-    std::string o;
-    auto piece_done = [&]() {
-        if (to_stdout) o.push_back('\n');
-        if (o.size() > (8u << 20)) {
-            fwrite(o.data(), 1, o.size(), f);
-            o.clear();
-        }
-    };
-    o += "run-id\tquery\ttype\trank\tidentifier\tperc-identity\tbit-score\ttaxonomy\tmutated\tsingle-match\toccurrences\taccessions";
-    piece_done();
-    std::string tmp;
-    for (auto& en : ent) {
+    {
+        std::string h = "run-id\tquery\ttype\trank\tidentifier\tperc-identity\tbit-score\ttaxonomy\tmutated\tsingle-match\toccurrences\taccessions";
+        if (to_stdout) h.push_back('\n');
+        fwrite(h.data(), 1, h.size(), f);
+    }
+    const bool ok = ordered_parallel_write(f, ent.size(), [&](std::string& o, size_t ei) {
+        const Entry& en = ent[ei];
+        auto piece_done = [&]() {
+            if (to_stdout) o.push_back('\n');
+        };
         if (!en.rec) {
             o.append(en.query);
             o += "\tnull\n";
             piece_done();
-            continue;
+            return;
         }
         const blu_record& rc = *en.rec;
         const uint32_t lo = T.lin_off[rc.ref_lineage];
@@ -809,13 +860,12 @@ inline int view_write_tabular(const ResultView* r, const char* path, const char*
             }
             piece_done();
         }
-    }
-    fwrite(o.data(), 1, o.size(), f);
+    });
     if (path)
         fclose(f);
     else
         fflush(stdout);
-    return BLU_OK;
+    return ok ? BLU_OK : BLU_ERR_IO;
 }
 
 }  // namespace blu
