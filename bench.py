@@ -405,7 +405,8 @@ def main():
             peaks = json.load(open(pth))
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "B200_PROFILING.md fallback 6650 GB/s"
-        algo_bytes = nbytes + res_bytes + tax_bytes  # B_text + B_out + B_tax per GPU
+        # B_text + B_out (+ B_tax, which the consensus kernel reads, not this one: reported beside, not added)
+        algo_bytes = nbytes + res_bytes
         traffic = None
         for name in ("r02_tile_kernel_traffic.json", "r01_tile_kernel_traffic.json"):
             tpath = os.path.join(ROOT, "profiles", name)
@@ -418,7 +419,7 @@ def main():
         achieved = algo_bytes / (tile_avg * 1e-3) / 1e9 if tile_avg > 0 else 0.0
         roof = {"bound": "hbm", "kernel": "tile_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": int(algo_bytes), "ms_per_launch": tile_avg,
-                "launches_per_step": 1, "kernel_share_of_step": tile_avg / dev_ms if dev_ms else None,
+                "launches_per_step": 1, "kernel_share_of_step": tile_avg / dev_ms if dev_ms else None, "taxonomy_bytes_not_counted": tax_bytes,
                 "ms_longrun_kernel": sum(long_ms) / len(long_ms), "ms_post_pass_kernels": sum(post_ms) / len(post_ms),
                 "whole_step_frac": (total_bytes / world) / (dev_ms * 1e-3) / 1e9 / peak if dev_ms else None}
     else:
