@@ -2109,42 +2109,19 @@ __device__ __forceinline__ void cons_write_record(blu_record* rec, const ConsLan
 constexpr int kConsWarps = kConsThreads / 32;
 constexpr int kConsBatch = 32;  // queries a warp finishes between two reservations of output space
 
-// per-warp staging of one batch's beans / accession references (a query of the staged classes has at most 8 of each)
+// per-warp staging of one batch's beans / accession references (a narrow query has at most 8 of each)
 struct ConsStage {
     blu_bean beans[kConsBatch][8];
     unsigned long long accs[kConsBatch][8];
     int nb[kConsBatch], na[kConsBatch];
-    uint8_t list4[kConsBatch], list8[kConsBatch];  // the batch's queries with top groups of 2..4 / 5..8 rows
 };
-
-// One round of the staged classes: W lanes per query, the queries taken from `list` (n of them), round `t`.
-template <int W>
-__device__ __forceinline__ void cons_round(const PostParams& p, ConsStage& St, const uint8_t* list, int n, int t, unsigned long long base, int g_l,
-                                           unsigned long long slot_l, unsigned long long qoff_l, int lane) {
-    const unsigned FULL = 0xffffffffu;
-    const int gid = lane / W, sl = lane & (W - 1);
-    const int pos = t * (32 / W) + gid;
-    const bool valid = pos < n;
-    const int q = valid ? (int)list[pos] : 0;  // the query's place in the batch == the lane that holds its header
-    const int g = __shfl_sync(FULL, g_l, q);
-    const unsigned long long slot = __shfl_sync(FULL, slot_l, q), qoff = __shfl_sync(FULL, qoff_l, q);
-    const ConsLane o = cons_compute<W>(p, valid, g, slot, qoff, lane);
-    if (o.ok && o.leader) St.beans[q][o.bean_idx] = o.bean;
-    if (o.ok && o.keeps) St.accs[q][o.acc_idx] = o.acc_ref;
-    if (valid && sl == 0) {
-        St.nb[q] = o.ok ? o.nb : 0;
-        St.na[q] = o.ok ? o.nkept : 0;
-        cons_write_record(p.records + base + (unsigned long long)q, o);
-    }
-}
 
 __global__ void __launch_bounds__(kConsThreads) consensus_kernel(const __grid_constant__ PostParams p) {
     __shared__ ConsStage stage_all[kConsWarps];
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t lt = (1u << lane) - 1u;
+    const int sub = lane >> 3, sl8 = lane & 7;
     ConsStage& St = stage_all[warp];
-    const LinTables& T = p.T;
     if (p.ctr->cap_overflow) return;  // the tile kernel ran out of space: the host grows the arrays and reruns
     const unsigned long long rb = p.ctr->post_done;
     unsigned long long re = p.ctr->rec_count;
@@ -2152,77 +2129,42 @@ __global__ void __launch_bounds__(kConsThreads) consensus_kernel(const __grid_co
     unsigned long long rows_sum = 0;
     const unsigned long long gw = (unsigned long long)blockIdx.x * kConsWarps + (unsigned long long)warp;
     const unsigned long long wstride = (unsigned long long)gridDim.x * kConsWarps * kConsBatch;
-    // A warp finishes 32 queries at a time.  Lane = query for the headers and for the single matches (half of all queries in
-    // practice: one lane each, no shuffles); the others by the size of their top group, 4 lanes per query (2..4 rows), 8 lanes
-    // (5..8 rows) or the whole warp (9..32 rows) -- a query costs what its top group needs, not what the largest one in the
-    // warp needs.  Beans / accession references are staged in shared memory, their output space is reserved with one atomic
-    // per array and batch, and they are copied out compactly: no CTA-wide barrier anywhere.
+    // A warp finishes 32 queries (eight rounds of four, 8 lanes per query) into its staging area, reserves their output with
+    // one atomic per array and copies them out compactly: no CTA-wide barrier, one reservation per 32 queries.
+    // (Measured and dropped, C2, per million queries: queries classed by top-group size with 4 / 8 / 32 lanes each 0.86 ms, single
+    // matches one lane per query with a serial cutoff loop 1.12 ms, against 0.65 ms for this uniform 8-lane version: three
+    // template instances triple the code and spill, and the lane-per-query header loads do not coalesce.)
     for (unsigned long long base = rb + gw * kConsBatch; base < re; base += wstride) {
-        // ---- headers: lane = query ----------------------------------------------------------------------------------------------
-        const unsigned long long qi = base + (unsigned long long)lane;
-        blu_record* rec = p.records + qi;
-        int g = 0, cls = 0;
-        unsigned long long slot = 0, qoff = 0;
-        if (qi < re) {
-            rows_sum += rec->n_rows;
-            if (rec->status == 2) {
-                g = (int)rec->n_beans;
-                slot = rec->bean_base;
-                qoff = rec->query_off;
-                if (g < 1 || slot + (unsigned long long)g > p.slot_cap)
-                    cls = 0;  // (cannot happen without cap_overflow)
-                else
-                    cls = g == 1 ? 1 : (g <= 4 ? 2 : (g <= 8 ? 3 : (g <= 32 ? 4 : 5)));
-            }
-        }
-        St.nb[lane] = 0, St.na[lane] = 0;
-        // ---- single matches (find_single_query_consensus.rs:74-150): entirely in the query's lane -----------------------------------
-        if (cls == 1) {
-            const TopRowRaw raw = p.toprows[slot];
-            TopRow r;
-            uint32_t jerr;
-            if (raw.dec_frac == kTopRowUnparsed)
-                jerr = raw.acc_off + (unsigned long long)raw.acc_len <= p.text_end ? heavy_parse_row(p.text + raw.acc_off, (int)raw.acc_len, raw.acc_off, T, r)
-                                                                                  : (uint32_t)DE_INTERNAL;
-            else
-                jerr = join_top_row(raw, T, r);
-            ConsLane o;
-            o.ok = false;
-            if (jerr)
-                report_soft(p.ctr, jerr, raw.acc_off);
-            else {
-                const uint32_t o0 = T.lin_off[r.lin];
-                const int k = r.lin_len;
-                unsigned long long mask = 0;
-                for (int j = 0; j < k; j++)
-                    if (r.pident >= T.cut[o0 + j]) mask |= 1ull << j;
-                if (!mask)
-                    report_soft(p.ctr, DE_EMPTY_ADJUSTED, qoff);
-                else {
-                    const int last = 63 - __clzll((long long)mask);
-                    o.ok = true, o.keep_mask = mask, o.perc_identity = r.pident, o.ref_lineage = r.lin, o.nb = 1, o.nkept = 1;
-                    o.single = true, o.mutated = false, o.reached = last, o.allowed = -1, o.level = last;
-                    blu_bean bn;
-                    bn.first_lineage = r.lin, bn.occurrences = 1, bn.acc_begin = 0, bn.n_acc = 1;
-                    St.beans[lane][0] = bn;
-                    St.accs[lane][0] = (r.acc_off << 16) | (unsigned long long)r.acc_len;
-                    St.nb[lane] = 1, St.na[lane] = 1;
+        unsigned wide_any = 0;
+        for (int t = 0; t < kConsBatch / 4; t++) {
+            const int qslot = t * 4 + sub;
+            const unsigned long long qi = base + (unsigned long long)qslot;
+            blu_record* rec = p.records + qi;
+            bool todo = false;
+            int g = 0;
+            unsigned long long slot = 0, qoff = 0;
+            if (qi < re) {
+                const uint32_t st = rec->status;  // (all eight lanes read the header: one sector)
+                if (sl8 == 0) rows_sum += rec->n_rows;
+                if (st == 2) {
+                    todo = true;
+                    g = (int)rec->n_beans;
+                    slot = rec->bean_base;
+                    qoff = rec->query_off;
+                    if (slot + (unsigned long long)g > p.slot_cap) todo = false, g = 0;  // (cannot happen without cap_overflow)
                 }
             }
-            cons_write_record(rec, o);
-        } else if (cls == 5) {
-            report(p.ctr, DE_INTERNAL, qoff);  // (the tile kernel hands top groups of more than 32 rows to the long-run kernel)
-            rec->status = 0, rec->n_beans = 0;
+            const bool narrow = todo && g >= 1 && g <= 8;
+            wide_any |= __ballot_sync(FULL, sl8 == 0 && todo && g > 8) ? 1u << t : 0u;
+            const ConsLane o = cons_compute<8>(p, narrow, g, slot, qoff, lane);
+            if (o.ok && o.leader) St.beans[qslot][o.bean_idx] = o.bean;
+            if (o.ok && o.keeps) St.accs[qslot][o.acc_idx] = o.acc_ref;
+            if (sl8 == 0) {
+                St.nb[qslot] = o.ok ? o.nb : 0;
+                St.na[qslot] = o.ok ? o.nkept : 0;
+                if (narrow) cons_write_record(rec, o);
+            }
         }
-        // ---- the other classes: their queries listed, W lanes per query ----------------------------------------------------------
-        const unsigned m4 = __ballot_sync(FULL, cls == 2), m8 = __ballot_sync(FULL, cls == 3);
-        unsigned m32 = __ballot_sync(FULL, cls == 4);
-        if (cls == 2) St.list4[__popc(m4 & lt)] = (uint8_t)lane;
-        if (cls == 3) St.list8[__popc(m8 & lt)] = (uint8_t)lane;
-        __syncwarp();
-        const int n4 = __popc(m4), n8 = __popc(m8);
-        for (int t = 0; t * 8 < n4; t++) cons_round<4>(p, St, St.list4, n4, t, base, g, slot, qoff, lane);
-        for (int t = 0; t * 4 < n8; t++) cons_round<8>(p, St, St.list8, n8, t, base, g, slot, qoff, lane);
         __syncwarp();
         // ---- output space for the batch: lane = query -------------------------------------------------------------------------
         const int vb = St.nb[lane], va = St.na[lane];
@@ -2242,13 +2184,12 @@ __global__ void __launch_bounds__(kConsThreads) consensus_kernel(const __grid_co
         const bool fits = bb + (unsigned long long)tot_b <= p.bean_cap && ab + (unsigned long long)tot_a <= p.acc_cap;
         if (!fits && lane == 0) p.ctr->cap_overflow = 1;
         const unsigned long long my_b = bb + (unsigned long long)(ib - vb), my_a = ab + (unsigned long long)(ia - va);
+        if (fits && vb > 0) {
+            blu_record* rec = p.records + base + (unsigned long long)lane;
+            rec->bean_base = (uint32_t)my_b;
+            rec->acc_base = (uint32_t)my_a;
+        }
         if (fits) {
-            if (vb > 0) {
-                rec->bean_base = (uint32_t)my_b;
-                rec->acc_base = (uint32_t)my_a;
-            }
-            // copy out: 8 lanes per query, four queries per step
-            const int sub = lane >> 3, sl8 = lane & 7;
             for (int t = 0; t < kConsBatch / 4; t++) {
                 const int qslot = t * 4 + sub;
                 const unsigned long long qb = __shfl_sync(FULL, my_b, qslot), qa = __shfl_sync(FULL, my_a, qslot);
@@ -2259,29 +2200,42 @@ __global__ void __launch_bounds__(kConsThreads) consensus_kernel(const __grid_co
         }
         __syncwarp();
         // ---- top groups of 9..32 rows: one query per warp, its own reservation ------------------------------------------------
-        while (m32) {
-            const int q = __ffs(m32) - 1;
-            m32 &= m32 - 1;
-            const int gw2 = __shfl_sync(FULL, g, q);
-            const unsigned long long slotw = __shfl_sync(FULL, slot, q), qoffw = __shfl_sync(FULL, qoff, q);
-            blu_record* recw = p.records + base + (unsigned long long)q;
-            const ConsLane ow = cons_compute<32>(p, true, gw2, slotw, qoffw, lane);
-            unsigned long long wb = 0, wa = 0;
-            int wfits = 1;
-            if (lane == 0 && ow.ok) {
-                wb = atomicAdd(&p.ctr->bean_used, (unsigned long long)ow.nb);
-                wa = atomicAdd(&p.ctr->acc_used, (unsigned long long)ow.nkept);
-                wfits = wb + (unsigned long long)ow.nb <= p.bean_cap && wa + (unsigned long long)ow.nkept <= p.acc_cap;
-                if (!wfits) p.ctr->cap_overflow = 1;
-            }
-            wb = __shfl_sync(FULL, wb, 0), wa = __shfl_sync(FULL, wa, 0), wfits = __shfl_sync(FULL, wfits, 0);
-            if (ow.ok && wfits) {
-                if (ow.leader) p.beans[wb + ow.bean_idx] = ow.bean;
-                if (ow.keeps) p.accs[wa + ow.acc_idx].ref = ow.acc_ref;
-            }
-            if (lane == 0) {
-                cons_write_record(recw, ow);
-                if (ow.ok && wfits) recw->bean_base = (uint32_t)wb, recw->acc_base = (uint32_t)wa;
+        while (wide_any) {
+            const int t = __ffs(wide_any) - 1;
+            wide_any &= wide_any - 1;
+            for (int sb = 0; sb < 4; sb++) {
+                const unsigned long long qi = base + (unsigned long long)(t * 4 + sb);
+                if (qi >= re) break;
+                blu_record* rec = p.records + qi;
+                if (rec->status != 2) continue;
+                const int gw2 = (int)rec->n_beans;
+                const unsigned long long slotw = rec->bean_base, qoffw = rec->query_off;
+                if (gw2 <= 8) continue;
+                if (gw2 > 32 || slotw + (unsigned long long)gw2 > p.slot_cap) {
+                    if (lane == 0) {
+                        report(p.ctr, DE_INTERNAL, qoffw);
+                        rec->status = 0, rec->n_beans = 0;
+                    }
+                    continue;
+                }
+                const ConsLane ow = cons_compute<32>(p, true, gw2, slotw, qoffw, lane);
+                unsigned long long wb = 0, wa = 0;
+                int wfits = 1;
+                if (lane == 0 && ow.ok) {
+                    wb = atomicAdd(&p.ctr->bean_used, (unsigned long long)ow.nb);
+                    wa = atomicAdd(&p.ctr->acc_used, (unsigned long long)ow.nkept);
+                    wfits = wb + (unsigned long long)ow.nb <= p.bean_cap && wa + (unsigned long long)ow.nkept <= p.acc_cap;
+                    if (!wfits) p.ctr->cap_overflow = 1;
+                }
+                wb = __shfl_sync(FULL, wb, 0), wa = __shfl_sync(FULL, wa, 0), wfits = __shfl_sync(FULL, wfits, 0);
+                if (ow.ok && wfits) {
+                    if (ow.leader) p.beans[wb + ow.bean_idx] = ow.bean;
+                    if (ow.keeps) p.accs[wa + ow.acc_idx].ref = ow.acc_ref;
+                }
+                if (lane == 0) {
+                    cons_write_record(rec, ow);
+                    if (ow.ok && wfits) rec->bean_base = (uint32_t)wb, rec->acc_base = (uint32_t)wa;
+                }
             }
         }
     }
