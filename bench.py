@@ -235,8 +235,7 @@ def main():
         w = SynthWorkload(cfg["taxa"], seed=seed)
         sample = min(q_rank, CPU_SAMPLE_Q if not cfg["zipf"] else CPU_SAMPLE_Q // 8)
         base, t = cpu_reference(cfg, w, w.lineages(False), sample, args.steps, min(args.warmup, 1))
-        config["reference_sample"] = base["sample"]
-        line = {"impl": "reference", "metric": "consensus_queries_per_s", "value": base["value"], "unit": "queries/s", "n_gpus": args.gpus,
+        line = {"impl": "reference", "run_info": {"reference_sample": base["sample"]}, "metric": "consensus_queries_per_s", "value": base["value"], "unit": "queries/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": scaling,
                 "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config, "cpu_baseline": base,
                 "hit_rows_per_s": base["rows_per_s"],
@@ -251,15 +250,16 @@ def main():
     from blutils_b200.synth import SynthWorkload
 
     torch.cuda.set_device(local_rank)
+    run_info = {}  # (what differs from run to run stays out of `config`: both arms print the same config)
     # keep this rank's threads and its pinned staging memory on the NUMA node of its GPU (one PCIe link per GPU)
     try:
         import pynvml
 
         pynvml.nvmlInit()
         pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
-        config["cpu_affinity"] = f"{len(os.sched_getaffinity(0))} cpus (NVML ideal affinity of GPU {local_rank})"
+        run_info["cpu_affinity"] = f"{len(os.sched_getaffinity(0))} cpus (NVML ideal affinity of GPU {local_rank})"
     except Exception as ex:  # noqa: BLE001
-        config["cpu_affinity"] = f"not set ({type(ex).__name__})"
+        run_info["cpu_affinity"] = f"not set ({type(ex).__name__})"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -308,7 +308,7 @@ def main():
         nbytes = nrows = 0
         host_q = max(1, min(q_rank, int(host_keep // (cfg["hits"] * 78))))
         host_bytes, host_rows = w.hits_into(pinned, cap, q_begin, host_q, cfg["hits"], zipf=cfg["zipf"])
-    config["generate_s"] = round(time.perf_counter() - t_gen, 1)
+    run_info["generate_s"] = round(time.perf_counter() - t_gen, 1)
 
     # custom cutoffs go through the YAML path (CustomTaxon::from_file semantics)
     custom = None
@@ -502,7 +502,7 @@ def main():
         line = {
             "metric": "consensus_queries_per_s", "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "u8",
-            "data": "synthetic", "config": config,
+            "data": "synthetic", "config": config, "run_info": run_info,
             "value_definition": ("end to end from pinned host text (C5 is a streamed configuration)" if streamed_only else
                                  "text resident in HBM -> consensus records resident in HBM (SURVEY 8d(i)); e2e and value_with_result_download include PCIe"),
             "hit_rows_per_s": total_rows / (ms_step * 1e-3),

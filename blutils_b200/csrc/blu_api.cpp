@@ -2045,18 +2045,23 @@ static int measure_copy(blu_ctx* c, uint64_t bytes, double* gbps, bool to_device
             throw CudaErr("cudaMalloc failed");
         }
         memset(h, 1, bytes);
-        double best = 0;
-        for (int i = 0; i < 5; i++) {
-            cudaEventRecord(c->ev[0][0], c->stream);
+        // sustained, not best-of: one warm-up copy, then enough back-to-back copies for ~6 GB, timed as a whole -- on a box where
+        // several GPUs copy at once a best-of figure picks the moments the others pause
+        auto copy = [&] {
             if (to_device)
                 cudaMemcpyAsync(d, h, bytes, cudaMemcpyHostToDevice, c->stream);
             else
                 cudaMemcpyAsync(h, d, bytes, cudaMemcpyDeviceToHost, c->stream);
-            cudaEventRecord(c->ev[0][1], c->stream);
-            cudaStreamSynchronize(c->stream);
-            double ms = ev_ms(c->ev[0][0], c->ev[0][1]);
-            if (ms > 0) best = std::max(best, bytes / ms / 1e6);
-        }
+        };
+        copy();
+        cudaStreamSynchronize(c->stream);
+        const int reps = (int)std::max<uint64_t>(2, (6ull << 30) / bytes);
+        cudaEventRecord(c->ev[0][0], c->stream);
+        for (int i = 0; i < reps; i++) copy();
+        cudaEventRecord(c->ev[0][1], c->stream);
+        cudaStreamSynchronize(c->stream);
+        const double ms = ev_ms(c->ev[0][0], c->ev[0][1]);
+        const double best = ms > 0 ? (double)bytes * reps / ms / 1e6 : 0;
         cudaFree(d);
         cudaFreeHost(h);
         *gbps = best;

@@ -211,7 +211,8 @@ void blu_result_free(blu_result* res);
 void blu_free(void* p);
 
 int blu_ctx_last_timings(const blu_ctx* ctx, blu_timings* out);
-/* Measured pinned host->device copy bandwidth (GB/s) on ctx's device, for the end-to-end ceiling. */
+/* Measured pinned host->device copy bandwidth (GB/s) on ctx's device, for the end-to-end ceiling: sustained over ~6 GB of
+ * back-to-back copies of `bytes` each (call it on every GPU at once to see what the box gives them together). */
 int blu_ctx_measure_h2d(blu_ctx* ctx, uint64_t bytes, double* gbps);
 /* ... and device->host. */
 int blu_ctx_measure_d2h(blu_ctx* ctx, uint64_t bytes, double* gbps);
