@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -964,8 +965,17 @@ class FileSource : public ChunkSource {
     bool stop_ = false;
     std::string error_;
     std::thread coordinator_;
+    const char* map_ = nullptr;  // BLU_FILE_MMAP=1: the source range of the file, mapped
+    uint64_t map_delta_ = 0, map_len_ = 0;
 
     bool read_span(char* dst, uint64_t off, uint64_t len, std::string& err) const {
+        if (map_) {
+            // the file's pages are mapped: one user-space copy (glibc switches to non-temporal stores for copies this large,
+            // so the pinned destination is not read for ownership first); a file that shrinks under us is a SIGBUS, which is
+            // why this path is opt-in (BLU_FILE_MMAP=1)
+            memcpy(dst, map_ + map_delta_ + off, (size_t)len);
+            return true;
+        }
         while (len) {
             ssize_t got = pread(fd_, dst, (size_t)std::min<uint64_t>(len, 1ull << 30), (off_t)(base_ + off));
             if (got < 0 && errno == EINTR) continue;
@@ -1045,12 +1055,23 @@ class FileSource : public ChunkSource {
         const unsigned hc = std::thread::hardware_concurrency();
         n_readers_ = (int)std::min<unsigned>(16, std::max<unsigned>(2, (hc ? hc : 8) / (unsigned)std::max(1, sharers)));
         if (const char* ev = getenv("BLU_READ_THREADS")) n_readers_ = std::max(1, std::min(64, atoi(ev)));
+        if (const char* ev = getenv("BLU_FILE_MMAP"); ev && *ev && *ev != '0' && n > 0) {
+            const uint64_t page = 4096, lo = base & ~(page - 1);
+            map_delta_ = base - lo;
+            map_len_ = map_delta_ + n;
+            void* m = mmap(nullptr, (size_t)map_len_, PROT_READ, MAP_SHARED, fd, (off_t)lo);
+            if (m != MAP_FAILED) {
+                map_ = (const char*)m;
+                madvise(m, (size_t)map_len_, MADV_SEQUENTIAL);
+            }
+        }
         const uint64_t used = std::min<uint64_t>(kRing, n_chunks_);
         try {
             for (uint64_t i = 0; i < used; i++) buf_[i] = c->acquire(std::min(chunk, n));
             coordinator_ = std::thread([this] { run(); });
         } catch (...) {  // a constructor that throws gets no destructor call
             for (auto& b : buf_) c_->pool->release(b);
+            if (map_) munmap((void*)map_, (size_t)map_len_);
             throw;
         }
     }
@@ -1062,6 +1083,7 @@ class FileSource : public ChunkSource {
         cv_.notify_all();
         coordinator_.join();
         for (auto& b : buf_) c_->pool->release(b);
+        if (map_) munmap((void*)map_, (size_t)map_len_);
     }
     const char* acquire(uint64_t ci) override {
         std::unique_lock<std::mutex> lk(mu_);
