@@ -82,6 +82,7 @@ SYMBOLS = [
     ("blu_ctx_measure_h2d", C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_double)]),
     ("blu_ctx_measure_d2h", C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_double)]),
     ("blu_shard_cuts", C.c_int, [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(C.c_uint64)]),
+    ("blu_shard_cuts_file", C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_uint64)]),
     ("blu_host_alloc", C.c_void_p, [C.c_uint64]),
     ("blu_host_free", None, [C.c_void_p]),
 ]

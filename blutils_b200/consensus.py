@@ -236,6 +236,13 @@ class ConsensusOutput:
         p = _ffi.lib().blu_result_records(self._h)
         return C.cast(p, C.POINTER(_ffi.blu_record * n)).contents if p else None
 
+    def query_ids(self) -> List[bytes]:
+        """The query id of every binary record, read through the string base (pool, or the caller's text with text_refs)."""
+        n = C.c_uint64()
+        base = _ffi.lib().blu_result_pool(self._h, C.byref(n))
+        recs = self.records()
+        return [] if recs is None else [C.string_at(base + r.query_off, r.query_len) for r in recs]
+
     def close(self) -> None:
         if self._h:
             _ffi.lib().blu_result_free(self._h)
@@ -378,6 +385,15 @@ def shard_cuts(text: Union[bytes, int], n_shards: int, nbytes: Optional[int] = N
         rc = _ffi.lib().blu_shard_cuts(int(text), int(nbytes), n_shards, cuts)
     if rc != 0:
         raise ValueError("blu_shard_cuts failed")
+    return list(cuts)
+
+
+def shard_cuts_file(path: str, n_shards: int) -> List[int]:
+    """shard_cuts for a table in a file: only the rows around every cut are read.  Host-only."""
+    cuts = (C.c_uint64 * (n_shards + 1))()
+    rc = _ffi.lib().blu_shard_cuts_file(os.fspath(path).encode(), n_shards, cuts)
+    if rc != 0:
+        raise MappedErrors("Unexpected error occurred on load table.")
     return list(cuts)
 
 

@@ -6,7 +6,6 @@
 #include <cuda_runtime.h>
 
 #include <fcntl.h>
-#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -265,6 +264,8 @@ struct blu_result {
     mutable std::vector<blu_bean> m_beans;
     mutable std::vector<blu_acc> m_accs;
     mutable std::string m_pool;
+    mutable const char* m_ext = nullptr;  // all parts reference the caller's text: the concatenation's string base is that text
+    mutable uint64_t m_ext_len = 0;
     uint64_t n_rec() const {
         uint64_t n = 0;
         for (auto& p : parts) n += p.n_rec;
@@ -965,17 +966,7 @@ class FileSource : public ChunkSource {
     bool stop_ = false;
     std::string error_;
     std::thread coordinator_;
-    const char* map_ = nullptr;  // BLU_FILE_MMAP=1: the source range of the file, mapped
-    uint64_t map_delta_ = 0, map_len_ = 0;
-
     bool read_span(char* dst, uint64_t off, uint64_t len, std::string& err) const {
-        if (map_) {
-            // the file's pages are mapped: one user-space copy (glibc switches to non-temporal stores for copies this large,
-            // so the pinned destination is not read for ownership first); a file that shrinks under us is a SIGBUS, which is
-            // why this path is opt-in (BLU_FILE_MMAP=1)
-            memcpy(dst, map_ + map_delta_ + off, (size_t)len);
-            return true;
-        }
         while (len) {
             ssize_t got = pread(fd_, dst, (size_t)std::min<uint64_t>(len, 1ull << 30), (off_t)(base_ + off));
             if (got < 0 && errno == EINTR) continue;
@@ -1051,27 +1042,17 @@ class FileSource : public ChunkSource {
     FileSource(blu_ctx* c, int fd, uint64_t base, uint64_t n, uint64_t chunk, int sharers = 1)
         : c_(c), fd_(fd), base_(base), n_(n), chunk_(chunk), n_chunks_((n + chunk - 1) / chunk) {
         // readers: the page-cache copy is the bound of this path, one thread moves ~5.6 GB/s; `sharers` = the
-        // file sources of a multi-device run that share the host's cores
+        // file sources of a multi-device run that share the host's cores.  (Measured and dropped: the file mmap'ed and copied
+        // into the ring with memcpy -- 26 / 29 GB/s with 8 / 16 threads against 30 / 39 GB/s for pread.)
         const unsigned hc = std::thread::hardware_concurrency();
         n_readers_ = (int)std::min<unsigned>(16, std::max<unsigned>(2, (hc ? hc : 8) / (unsigned)std::max(1, sharers)));
         if (const char* ev = getenv("BLU_READ_THREADS")) n_readers_ = std::max(1, std::min(64, atoi(ev)));
-        if (const char* ev = getenv("BLU_FILE_MMAP"); ev && *ev && *ev != '0' && n > 0) {
-            const uint64_t page = 4096, lo = base & ~(page - 1);
-            map_delta_ = base - lo;
-            map_len_ = map_delta_ + n;
-            void* m = mmap(nullptr, (size_t)map_len_, PROT_READ, MAP_SHARED, fd, (off_t)lo);
-            if (m != MAP_FAILED) {
-                map_ = (const char*)m;
-                madvise(m, (size_t)map_len_, MADV_SEQUENTIAL);
-            }
-        }
         const uint64_t used = std::min<uint64_t>(kRing, n_chunks_);
         try {
             for (uint64_t i = 0; i < used; i++) buf_[i] = c->acquire(std::min(chunk, n));
             coordinator_ = std::thread([this] { run(); });
         } catch (...) {  // a constructor that throws gets no destructor call
             for (auto& b : buf_) c_->pool->release(b);
-            if (map_) munmap((void*)map_, (size_t)map_len_);
             throw;
         }
     }
@@ -1083,7 +1064,6 @@ class FileSource : public ChunkSource {
         cv_.notify_all();
         coordinator_.join();
         for (auto& b : buf_) c_->pool->release(b);
-        if (map_) munmap((void*)map_, (size_t)map_len_);
     }
     const char* acquire(uint64_t ci) override {
         std::unique_lock<std::mutex> lk(mu_);
@@ -1290,13 +1270,20 @@ void shard_cuts(const ByteView& v, int n_shards, uint64_t* cuts) {
         while (q < n && v.at(q) == '\n') q++;
         return q;
     };
-    auto same_first_field = [&](uint64_t a, uint64_t b) {
-        for (uint64_t i = 0;; i++) {
-            const bool ea = a + i >= n || v.at(a + i) == '\t' || v.at(a + i) == '\n';
-            const bool eb = b + i >= n || v.at(b + i) == '\t' || v.at(b + i) == '\n';
-            if (ea || eb) return ea && eb;
-            if (v.at(a + i) != v.at(b + i)) return false;
+    auto first_field = [&](uint64_t a) {  // (copied out: the view of a file keeps one window, and the rows compared with it lie ahead)
+        std::string f;
+        for (uint64_t i = a; i < n; i++) {
+            const char ch = v.at(i);
+            if (ch == '\t' || ch == '\n') break;
+            f.push_back(ch);
         }
+        return f;
+    };
+    auto has_first_field = [&](uint64_t b, const std::string& f) {
+        for (size_t i = 0; i < f.size(); i++)
+            if (b + i >= n || v.at(b + i) != f[i]) return false;
+        const uint64_t e = b + f.size();
+        return e >= n || v.at(e) == '\t' || v.at(e) == '\n';
     };
     cuts[0] = 0;
     cuts[n_shards] = n;
@@ -1320,7 +1307,8 @@ void shard_cuts(const ByteView& v, int n_shards, uint64_t* cuts) {
             if (v.at(q) != '\n') {
                 uint64_t st = q;
                 while (st > 0 && v.at(st - 1) != '\n') st--;
-                while (p < n && same_first_field(st, p)) p = next_row(p);  // never split a query
+                const std::string run = first_field(st);
+                while (p < n && has_first_field(p, run)) p = next_row(p);  // never split a query
             }
         }
         cuts[k] = p;
@@ -1470,11 +1458,27 @@ void merge_parts(const blu_result* r) {
     std::lock_guard<std::mutex> g(r->merge_mu);
     if (r->merged) return;
     uint64_t nr = 0, nb = 0, na = 0, np = 0;
-    for (auto& p : r->parts) nr += p.n_rec, nb += p.n_beans, na += p.n_accs, np += p.strings_len();
-    if (nb >= kIdxMax || na >= kIdxMax) throw UnsupportedErr("the concatenated result has more than 2^32 beans / accession references: read it part by part");
-    r->m_rec.reserve(nr), r->m_beans.reserve(nb), r->m_accs.reserve(na), r->m_pool.reserve(np);
+    bool all_ext = true;
+    const char* ext_lo = nullptr;
+    const char* ext_hi = nullptr;
     for (auto& p : r->parts) {
-        const uint64_t b0 = r->m_beans.size(), a0 = r->m_accs.size(), s0 = r->m_pool.size();
+        nr += p.n_rec, nb += p.n_beans, na += p.n_accs, np += p.strings_len();
+        if (!p.n_rec) continue;
+        if (!p.ext_strings) {
+            all_ext = false;
+            continue;
+        }
+        if (!ext_lo || p.ext_strings < ext_lo) ext_lo = p.ext_strings;
+        if (!ext_hi || p.ext_strings + p.ext_len > ext_hi) ext_hi = p.ext_strings + p.ext_len;
+    }
+    all_ext = all_ext && ext_lo != nullptr;
+    if (nb >= kIdxMax || na >= kIdxMax) throw UnsupportedErr("the concatenated result has more than 2^32 beans / accession references: read it part by part");
+    r->m_rec.reserve(nr), r->m_beans.reserve(nb), r->m_accs.reserve(na);
+    if (!all_ext) r->m_pool.reserve(np);
+    for (auto& p : r->parts) {
+        if (!p.n_rec) continue;
+        // where this part's strings sit in the concatenation's string base
+        const uint64_t b0 = r->m_beans.size(), a0 = r->m_accs.size(), s0 = all_ext ? (uint64_t)(p.ext_strings - ext_lo) : r->m_pool.size();
         const blu_record* rec = (const blu_record*)p.b_rec.p;
         for (uint64_t i = 0; i < p.n_rec; i++) {
             blu_record x = rec[i];
@@ -1485,8 +1489,9 @@ void merge_parts(const blu_result* r) {
         r->m_beans.insert(r->m_beans.end(), bn, bn + p.n_beans);
         const blu_acc* ac = (const blu_acc*)p.b_accs.p;
         for (uint64_t i = 0; i < p.n_accs; i++) r->m_accs.push_back(blu_acc{ac[i].ref + (s0 << 16)});
-        if (p.strings_len()) r->m_pool.append(p.strings(), p.strings_len());
+        if (!all_ext && p.strings_len()) r->m_pool.append(p.strings(), p.strings_len());
     }
+    if (all_ext) r->m_ext = ext_lo, r->m_ext_len = (uint64_t)(ext_hi - ext_lo);
     r->merged = true;
 }
 
@@ -1980,6 +1985,10 @@ const char* blu_result_pool(const blu_result* r, uint64_t* len) {
         if (len) *len = r->parts[0].strings_len();
         return r->parts[0].strings();
     }
+    if (r->m_ext) {
+        if (len) *len = r->m_ext_len;
+        return r->m_ext;
+    }
     if (len) *len = r->m_pool.size();
     return r->m_pool.data();
 }
@@ -2098,6 +2107,26 @@ int blu_shard_cuts(const char* text, uint64_t n, int n_shards, uint64_t* cuts) {
     v.mem = text, v.n = n;
     shard_cuts(v, n_shards, cuts);
     return BLU_OK;
+}
+
+int blu_shard_cuts_file(const char* path, int n_shards, uint64_t* cuts) {
+    if (!path || !cuts || n_shards < 1) return BLU_ERR_ARG;
+    const int fd = open(path, O_RDONLY | O_CLOEXEC);
+    struct stat st;
+    if (fd < 0 || fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) {
+        if (fd >= 0) close(fd);
+        return BLU_ERR_IO;
+    }
+    int rc = BLU_OK;
+    try {
+        ByteView v;
+        v.fd = fd, v.n = (uint64_t)st.st_size;
+        shard_cuts(v, n_shards, cuts);
+    } catch (const std::exception&) {
+        rc = BLU_ERR_IO;
+    }
+    close(fd);
+    return rc;
 }
 
 void* blu_host_alloc(uint64_t bytes) {

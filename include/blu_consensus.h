@@ -222,6 +222,9 @@ int blu_ctx_measure_d2h(blu_ctx* ctx, uint64_t bytes, double* gbps);
  * contiguous tables (every query's rows adjacent), which is what BLAST and blutils' chunked appends
  * (run_parallel_blast.rs:97,146-151) produce.  Host-only; needs no GPU. */
 int blu_shard_cuts(const char* text, uint64_t n_bytes, int n_shards, uint64_t* cuts);
+/* The same for a file (what blu_consensus_run_file does on a multi-device context): only a few rows around every cut are
+ * read.  BLU_ERR_IO if the file cannot be opened / read. */
+int blu_shard_cuts_file(const char* path, int n_shards, uint64_t* cuts);
 
 /* Pinned host buffers (cudaHostAlloc) so callers can stage text for blu_consensus_run_host. */
 void* blu_host_alloc(uint64_t bytes);

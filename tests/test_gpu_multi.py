@@ -62,6 +62,7 @@ def test_sharded_table_equals_oracle(zipf, tmp_path):
             # the concatenated binary view: records of all parts, indices rebased
             recs = out.records()
             assert len(recs) == nq and all(r.status == 1 for r in recs)
+            assert sorted(out.query_ids()) == sorted(json.loads(l)["query"].encode() for l in want.decode().splitlines()), (devs, refs)
             t = eng.timings()
             assert int(t["n_queries"]) == nq and int(t["text_bytes"]) == len(text)
             out.close()
