@@ -74,6 +74,7 @@ SYMBOLS = [
     ("blu_result_num_accessions", C.c_uint64, [C.c_void_p]),
     ("blu_result_checksum", C.c_uint64, [C.c_void_p]),
     ("blu_result_to_jsonl", C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
+    ("blu_result_to_jsonl_head", C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]),
     ("blu_result_write", C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_char_p]),
     ("blu_result_write_tabular", C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
     ("blu_result_free", None, [C.c_void_p]),

@@ -177,15 +177,18 @@ class ConsensusOutput:
     def checksum(self) -> int:
         return _ffi.lib().blu_result_checksum(self._h)
 
-    def jsonl(self) -> bytes:
-        """Canonical JSONL: one {"query":..,"taxon":..} per line, sorted by query, no runId."""
+    def jsonl(self, head: Optional[int] = None) -> bytes:
+        """Canonical JSONL: one {"query":..,"taxon":..} per line, sorted by query, no runId.  `head`: only the first lines."""
         out = C.c_void_p()
         n = C.c_uint64()
-        rc = _ffi.lib().blu_result_to_jsonl(self._h, C.byref(out), C.byref(n))
+        if head is None:
+            rc = _ffi.lib().blu_result_to_jsonl(self._h, C.byref(out), C.byref(n))
+        else:
+            rc = _ffi.lib().blu_result_to_jsonl_head(self._h, int(head), C.byref(out), C.byref(n))
         if rc != 0:
             raise RuntimeError("blu_result_to_jsonl failed")
         try:
-            return C.string_at(out, n.value)
+            return bytes((C.c_char * n.value).from_address(out.value)) if n.value else b""  # (string_at takes an int: 2 GB limit)
         finally:
             _ffi.lib().blu_free(out)
 

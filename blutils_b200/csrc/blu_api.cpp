@@ -1999,11 +1999,11 @@ uint64_t blu_result_checksum(const blu_result* r) {
     return view_checksum(&v);
 }
 
-int blu_result_to_jsonl(const blu_result* r, char** out, uint64_t* len) {
+int blu_result_to_jsonl_head(const blu_result* r, uint64_t max_entries, char** out, uint64_t* len) {
     if (!r || !out || !len || !r->on_host()) return BLU_ERR_ARG;
     try {
         ResultView v = make_view(r);
-        std::string s = view_to_jsonl(&v);
+        std::string s = view_to_jsonl(&v, max_entries);
         char* buf = (char*)malloc(s.size() + 1);
         if (!buf) return BLU_ERR_INTERNAL;
         memcpy(buf, s.data(), s.size());
@@ -2015,6 +2015,8 @@ int blu_result_to_jsonl(const blu_result* r, char** out, uint64_t* len) {
         return BLU_ERR_INTERNAL;
     }
 }
+
+int blu_result_to_jsonl(const blu_result* r, char** out, uint64_t* len) { return blu_result_to_jsonl_head(r, ~0ull, out, len); }
 
 int blu_result_write(const blu_result* r, const char* path, int format, const char* run_id_in) {
     if (!r || format < 0 || format > 2 || !r->on_host()) return BLU_ERR_ARG;

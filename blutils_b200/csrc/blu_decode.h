@@ -624,9 +624,30 @@ inline uint64_t view_checksum(const ResultView* r) {
 }
 
 
-inline std::string view_to_jsonl(const ResultView* r) {
+// `max_entries` < number of entries: only the entries with the smallest query ids (partial sort), in order
+inline std::string view_to_jsonl(const ResultView* r, uint64_t max_entries = ~0ull) {
     Decoder d(r);
-    auto ent = sorted_entries(r);
+    std::vector<Entry> ent;
+    const uint64_t total = r->n_rec() + (r->hitless_ ? r->hitless_->size() : 0);
+    if (max_entries < total) {
+        ent.reserve(total);
+        for (auto& p : r->parts)
+            for (uint64_t i = 0; i < p.n_rec; i++) ent.push_back({rec_query(p, p.rec[i]), &p.rec[i], &p});
+        if (r->hitless_)
+            for (auto& h : *r->hitless_) ent.push_back({std::string_view(h), nullptr, nullptr});
+        // (ties keep their file order like the stable full sort: compare the position as the last key)
+        std::vector<uint64_t> idx(total);
+        for (uint64_t i = 0; i < total; i++) idx[i] = i;
+        std::partial_sort(idx.begin(), idx.begin() + (std::ptrdiff_t)max_entries, idx.end(), [&](uint64_t a, uint64_t b) {
+            const int c = ent[a].query.compare(ent[b].query);
+            return c != 0 ? c < 0 : a < b;
+        });
+        std::vector<Entry> head;
+        head.reserve(max_entries);
+        for (uint64_t i = 0; i < max_entries; i++) head.push_back(ent[idx[i]]);
+        ent.swap(head);
+    } else
+        ent = sorted_entries(r);
     std::vector<std::string> parts(host_threads());
     parallel_ranges(ent.size(), [&](unsigned t, size_t a, size_t b) {
         std::string& o = parts[t];

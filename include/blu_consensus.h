@@ -192,6 +192,9 @@ uint64_t blu_result_checksum(const blu_result* res);
 /* Canonical JSONL (one `{"query":..,"taxon":..}` object per line, sorted by query, no runId); caller frees
  * with blu_free. */
 int blu_result_to_jsonl(const blu_result* res, char** out, uint64_t* len);
+/* The first `max_entries` lines of the same (the entries with the smallest query ids): a check of a prefix of a large result
+ * need not format all of it. */
+int blu_result_to_jsonl_head(const blu_result* res, uint64_t max_entries, char** out, uint64_t* len);
 /* write_blutils_output (write_blutils_output.rs:33-250): path NULL -> stdout; run_id NULL -> fresh UUIDv4;
  * config is always `null` on this path (ports/cli/src/cmds/blast/mod.rs:139). */
 int blu_result_write(const blu_result* res, const char* path, int format, const char* run_id);

@@ -39,6 +39,8 @@ def test_device_resident_result(n_queries, hits, zipf):
         assert rec_ptr and beans_ptr and accs_ptr and nb >= nq and na >= nb
         assert int(eng.timings()["d2h_bytes"]) < 1024  # nothing but the counters crossed PCIe
         assert out.download().jsonl() == want
+        assert out.jsonl(head=37) == b"".join(want.splitlines(keepends=True)[:37])  # (what bench.py's in-run check reads)
+        assert out.jsonl(head=10 ** 9) == want
         out.close()
     # the download variant of the same call
     assert eng.run_device(t.data_ptr(), len(text), stream).jsonl() == want
