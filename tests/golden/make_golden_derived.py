@@ -5,8 +5,9 @@ The golden file holds results only (its BLAST table and taxonomy DB are not in t
 so it cannot be replayed end to end.  What it *does* pin is the arithmetic of
 interpolate_identities / get_rank_adjusted_by_identity / get_adjusted_taxonomy_by_identity /
 build_blast_consensus_identity / fold_consensus_list: each result is reduced to the fields those
-functions produce, accession lists are dropped (kept as counts), and identical reductions are
-de-duplicated with a multiplicity.  Run here (the reference is not present on the GPU box):
+functions produce (the accession list of every bean included: its order is the order of the sorted
+top group, find_multi_taxa_consensus.rs:39-54), and identical reductions are de-duplicated with a
+multiplicity.  Run here (the reference is not present on the GPU box):
 
     python tests/golden/make_golden_derived.py
 """
@@ -28,7 +29,8 @@ def main():
                                  "taxonomy", "mutated", "singleMatch")}
         red["consensusBeans"] = [
             {"rank": b["rank"], "identifier": b["identifier"], "occurrences": b["occurrences"],
-             "taxonomy": b["taxonomy"], "nAccessions": len(b["accessions"])} for b in t["consensusBeans"]]
+             "taxonomy": b["taxonomy"], "nAccessions": len(b["accessions"]), "accessions": b["accessions"]}
+            for b in t["consensusBeans"]]
         key = json.dumps(red, sort_keys=True)
         seen[key] = seen.get(key, 0) + 1
     with open(DST, "w") as f:

@@ -3,12 +3,17 @@ golden file pins the CUDA path itself, not only the Python restatement.
 
 The golden output holds results only (no BLAST table, no taxonomy DB).  Each result lists its consensus beans with
 their lineage (`taxonomy`), `occurrences` and the number of (deduplicated) accessions, plus percIdentity / bitScore.
-From that a top bit-score group is rebuilt: one lineage per bean (taxid = its index), `occurrences` rows per bean that
-all carry the result's percIdentity and bitScore, accession strings repeated so that Vec::dedup leaves `nAccessions`.
-Which row the reference used as reference row is not visible in the output, so every bean is tried as the preferred
-reference (its rows get the align length that sorts them first under `cautious` / last under `relaxed`,
+From that a top bit-score group is rebuilt: one lineage per bean (taxid = its index), one row per golden accession of the
+bean (the golden accession strings themselves), all carrying the result's percIdentity and bitScore.  The accession
+list of a bean is in the order of the sorted top group (lineage length, pident, align length, accession;
+find_multi_taxa_consensus.rs:39-54); pident per row is not visible, so the rows of a bean get increasing align lengths
+in the golden order -- the output must then list exactly the golden accessions in exactly the golden order.  The rows
+are written to the table in a shuffled order, so the order really comes from the sort.
+Which row the reference used as reference row is not visible in the output either, so every bean is tried as the
+preferred reference (its rows get the align lengths that sort them first under `cautious` / last under `relaxed`,
 find_multi_taxa_consensus.rs:39-63); a golden result is *pinned* when at least one variant reproduces every visible
-field of it."""
+field of it, accession lists included."""
+import random
 import json
 import os
 
@@ -33,6 +38,7 @@ def build(strategy: str):
             lin_id.setdefault(b["taxonomy"], len(lin_id) + 1)
     rows = []
     variants = {}
+    rng = random.Random(20261018)
     for gi, t in enumerate(golden):
         beans = t["consensusBeans"]
         pid = repr(float(t["percIdentity"]))
@@ -40,17 +46,20 @@ def build(strategy: str):
         for pref in range(len(beans)):
             q = f"g{gi:04d}_{pref:02d}"
             variants[q] = (gi, pref)
+            qrows = []
             for bi, b in enumerate(beans):
                 # the preferred bean's rows sort first (cautious: reference = first) / last (relaxed: reference = last) among
-                # lineages of equal length
+                # lineages of equal length; inside a bean the align length grows in the golden order of its accessions
                 if strategy == "cautious":
-                    aln = 100 if bi == pref else 200
+                    base = 100 if bi == pref else 2000
                 else:
-                    aln = 300 if bi == pref else 200
-                nacc, occ = b["nAccessions"], b["occurrences"]
-                for k in range(occ):
-                    acc = f"B{bi:02d}A{min(k, nacc - 1):03d}.1"  # the surplus rows repeat the last accession: dedup removes them
-                    rows.append(f"{q}\t{acc}\t{lin_id[b['taxonomy']]}\t{pid}\t{aln}\t0\t0\t1\t{aln}\t1\t{aln}\t0.0\t{bits}\n")
+                    base = 5000 if bi == pref else 2000
+                assert b["occurrences"] == len(b["accessions"]) < 100
+                for k, acc in enumerate(b["accessions"]):
+                    aln = base + k
+                    qrows.append(f"{q}\t{acc}\t{lin_id[b['taxonomy']]}\t{pid}\t{aln}\t0\t0\t1\t{aln}\t1\t{aln}\t0.0\t{bits}\n")
+            rng.shuffle(qrows)
+            rows += qrows
             # a lower-scoring hit that must not matter
             rows.append(f"{q}\tLOW.1\t{lin_id[beans[0]['taxonomy']]}\t80.0\t100\t0\t0\t1\t100\t1\t100\t0.0\t10\n")
     lineages = [None] * len(lin_id)
@@ -71,8 +80,8 @@ def score(results, variants, golden):
         t, g = r["taxon"], golden[gi]
         same = t is not None and all(t[k] == g[k] for k in FIELDS)
         if same:
-            gb = [(b["rank"], b["identifier"], b["occurrences"], b["taxonomy"], b["nAccessions"]) for b in g["consensusBeans"]]
-            tb = [(b["rank"], b["identifier"], b["occurrences"], b["taxonomy"], len(b["accessions"])) for b in t["consensusBeans"]]
+            gb = [(b["rank"], b["identifier"], b["occurrences"], b["taxonomy"], b["accessions"]) for b in g["consensusBeans"]]
+            tb = [(b["rank"], b["identifier"], b["occurrences"], b["taxonomy"], b["accessions"]) for b in t["consensusBeans"]]
             same = gb == tb
         if same:
             ok[gi] = True
