@@ -2114,12 +2114,23 @@ struct ConsStage {
     blu_bean beans[kConsBatch][8];
     unsigned long long accs[kConsBatch][8];
     int nb[kConsBatch], na[kConsBatch];
+    uint8_t list[kConsBatch];  // the batch's narrow queries (top groups of 1..8 rows) in the order of their top-group size
 };
 
-__global__ void __launch_bounds__(kConsThreads) consensus_kernel(const __grid_constant__ PostParams p) {
+#ifndef BLU_CONS_SORTED
+#define BLU_CONS_SORTED 1
+#endif
+
+// (64 registers, 8 CTAs = 32 warps per SM: the kernel waits on memory, occupancy decides -- measured per million queries:
+// 106 registers 0.92 ms, 95: 0.87, 80: 0.71, 72: 0.68, 64 (a few spills): 0.615)
+#ifndef BLU_CONS_MINB
+#define BLU_CONS_MINB 8
+#endif
+__global__ void __launch_bounds__(kConsThreads, BLU_CONS_MINB) consensus_kernel(const __grid_constant__ PostParams p) {
     __shared__ ConsStage stage_all[kConsWarps];
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t lt = (1u << lane) - 1u;
     const int sub = lane >> 3, sl8 = lane & 7;
     ConsStage& St = stage_all[warp];
     if (p.ctr->cap_overflow) return;  // the tile kernel ran out of space: the host grows the arrays and reruns
@@ -2129,40 +2140,59 @@ __global__ void __launch_bounds__(kConsThreads) consensus_kernel(const __grid_co
     unsigned long long rows_sum = 0;
     const unsigned long long gw = (unsigned long long)blockIdx.x * kConsWarps + (unsigned long long)warp;
     const unsigned long long wstride = (unsigned long long)gridDim.x * kConsWarps * kConsBatch;
-    // A warp finishes 32 queries (eight rounds of four, 8 lanes per query) into its staging area, reserves their output with
-    // one atomic per array and copies them out compactly: no CTA-wide barrier, one reservation per 32 queries.
-    // (Measured and dropped, C2, per million queries: queries classed by top-group size with 4 / 8 / 32 lanes each 0.86 ms, single
-    // matches one lane per query with a serial cutoff loop 1.12 ms, against 0.65 ms for this uniform 8-lane version: three
-    // template instances triple the code and spill, and the lane-per-query header loads do not coalesce.)
+    // A warp finishes 32 queries at a time: lane = query for the headers (all 32 records are requested at once), then rounds of
+    // four queries, 8 lanes per query, taken in the order of their top-group size -- the loops of a round run to the largest
+    // top group among its four queries, and half of all queries are single matches: sorted, they share rounds whose loops
+    // all collapse (0.615 instead of 0.646 ms per million queries).  Beans / accession references are staged in shared memory, their output space is reserved with one
+    // atomic per array and batch, and they are copied out compactly: no CTA-wide barrier anywhere.
     for (unsigned long long base = rb + gw * kConsBatch; base < re; base += wstride) {
-        unsigned wide_any = 0;
-        for (int t = 0; t < kConsBatch / 4; t++) {
-            const int qslot = t * 4 + sub;
-            const unsigned long long qi = base + (unsigned long long)qslot;
-            blu_record* rec = p.records + qi;
-            bool todo = false;
-            int g = 0;
-            unsigned long long slot = 0, qoff = 0;
-            if (qi < re) {
-                const uint32_t st = rec->status;  // (all eight lanes read the header: one sector)
-                if (sl8 == 0) rows_sum += rec->n_rows;
-                if (st == 2) {
-                    todo = true;
-                    g = (int)rec->n_beans;
-                    slot = rec->bean_base;
-                    qoff = rec->query_off;
-                    if (slot + (unsigned long long)g > p.slot_cap) todo = false, g = 0;  // (cannot happen without cap_overflow)
-                }
+        // ---- headers: lane = query ----------------------------------------------------------------------------------------------
+        const unsigned long long qi = base + (unsigned long long)lane;
+        blu_record* rec = p.records + qi;
+        int g = 0, cls = 0;  // cls 1: 1..8 rows, 2: 9..32 rows, 3: more (cannot come from the tile kernel)
+        unsigned long long slot = 0, qoff = 0;
+        if (qi < re) {
+            rows_sum += rec->n_rows;
+            if (rec->status == 2) {
+                g = (int)rec->n_beans;
+                slot = rec->bean_base;
+                qoff = rec->query_off;
+                if (g >= 1 && slot + (unsigned long long)g <= p.slot_cap) cls = g <= 8 ? 1 : (g <= 32 ? 2 : 3);  // (else: cannot happen without cap_overflow)
             }
-            const bool narrow = todo && g >= 1 && g <= 8;
-            wide_any |= __ballot_sync(FULL, sl8 == 0 && todo && g > 8) ? 1u << t : 0u;
-            const ConsLane o = cons_compute<8>(p, narrow, g, slot, qoff, lane);
-            if (o.ok && o.leader) St.beans[qslot][o.bean_idx] = o.bean;
-            if (o.ok && o.keeps) St.accs[qslot][o.acc_idx] = o.acc_ref;
-            if (sl8 == 0) {
-                St.nb[qslot] = o.ok ? o.nb : 0;
-                St.na[qslot] = o.ok ? o.nkept : 0;
-                if (narrow) cons_write_record(rec, o);
+        }
+        St.nb[lane] = 0, St.na[lane] = 0;
+        if (cls == 3) {
+            report(p.ctr, DE_INTERNAL, qoff);  // (the tile kernel hands top groups of more than 32 rows to the long-run kernel)
+            rec->status = 0, rec->n_beans = 0;
+        }
+        // ---- the narrow queries, listed by top-group size ------------------------------------------------------------------------
+        int n8 = 0;
+        {
+            int pos = 0;
+#pragma unroll
+            for (int k = 1; k <= 8; k++) {
+                const unsigned mk = __ballot_sync(FULL, cls == 1 && (BLU_CONS_SORTED ? g == k : k == 1));
+                if (BLU_CONS_SORTED ? k < g : false) pos += __popc(mk);
+                if (BLU_CONS_SORTED ? k == g : k == 1) pos += __popc(mk & lt);
+                n8 += __popc(mk);
+            }
+            if (cls == 1) St.list[pos] = (uint8_t)lane;
+        }
+        unsigned m32 = __ballot_sync(FULL, cls == 2);
+        __syncwarp();
+        for (int t = 0; t * 4 < n8; t++) {
+            const int at = t * 4 + sub;
+            const bool valid = at < n8;
+            const int q = valid ? (int)St.list[at] : 0;  // the query's place in the batch == the lane that holds its header
+            const int gq = __shfl_sync(FULL, g, q);
+            const unsigned long long slotq = __shfl_sync(FULL, slot, q), qoffq = __shfl_sync(FULL, qoff, q);
+            const ConsLane o = cons_compute<8>(p, valid, gq, slotq, qoffq, lane);
+            if (o.ok && o.leader) St.beans[q][o.bean_idx] = o.bean;
+            if (o.ok && o.keeps) St.accs[q][o.acc_idx] = o.acc_ref;
+            if (valid && sl8 == 0) {
+                St.nb[q] = o.ok ? o.nb : 0;
+                St.na[q] = o.ok ? o.nkept : 0;
+                cons_write_record(p.records + base + (unsigned long long)q, o);
             }
         }
         __syncwarp();
@@ -2184,12 +2214,12 @@ __global__ void __launch_bounds__(kConsThreads) consensus_kernel(const __grid_co
         const bool fits = bb + (unsigned long long)tot_b <= p.bean_cap && ab + (unsigned long long)tot_a <= p.acc_cap;
         if (!fits && lane == 0) p.ctr->cap_overflow = 1;
         const unsigned long long my_b = bb + (unsigned long long)(ib - vb), my_a = ab + (unsigned long long)(ia - va);
-        if (fits && vb > 0) {
-            blu_record* rec = p.records + base + (unsigned long long)lane;
-            rec->bean_base = (uint32_t)my_b;
-            rec->acc_base = (uint32_t)my_a;
-        }
         if (fits) {
+            if (vb > 0) {
+                rec->bean_base = (uint32_t)my_b;
+                rec->acc_base = (uint32_t)my_a;
+            }
+            // copy out: 8 lanes per query, four queries per step
             for (int t = 0; t < kConsBatch / 4; t++) {
                 const int qslot = t * 4 + sub;
                 const unsigned long long qb = __shfl_sync(FULL, my_b, qslot), qa = __shfl_sync(FULL, my_a, qslot);
@@ -2200,42 +2230,29 @@ __global__ void __launch_bounds__(kConsThreads) consensus_kernel(const __grid_co
         }
         __syncwarp();
         // ---- top groups of 9..32 rows: one query per warp, its own reservation ------------------------------------------------
-        while (wide_any) {
-            const int t = __ffs(wide_any) - 1;
-            wide_any &= wide_any - 1;
-            for (int sb = 0; sb < 4; sb++) {
-                const unsigned long long qi = base + (unsigned long long)(t * 4 + sb);
-                if (qi >= re) break;
-                blu_record* rec = p.records + qi;
-                if (rec->status != 2) continue;
-                const int gw2 = (int)rec->n_beans;
-                const unsigned long long slotw = rec->bean_base, qoffw = rec->query_off;
-                if (gw2 <= 8) continue;
-                if (gw2 > 32 || slotw + (unsigned long long)gw2 > p.slot_cap) {
-                    if (lane == 0) {
-                        report(p.ctr, DE_INTERNAL, qoffw);
-                        rec->status = 0, rec->n_beans = 0;
-                    }
-                    continue;
-                }
-                const ConsLane ow = cons_compute<32>(p, true, gw2, slotw, qoffw, lane);
-                unsigned long long wb = 0, wa = 0;
-                int wfits = 1;
-                if (lane == 0 && ow.ok) {
-                    wb = atomicAdd(&p.ctr->bean_used, (unsigned long long)ow.nb);
-                    wa = atomicAdd(&p.ctr->acc_used, (unsigned long long)ow.nkept);
-                    wfits = wb + (unsigned long long)ow.nb <= p.bean_cap && wa + (unsigned long long)ow.nkept <= p.acc_cap;
-                    if (!wfits) p.ctr->cap_overflow = 1;
-                }
-                wb = __shfl_sync(FULL, wb, 0), wa = __shfl_sync(FULL, wa, 0), wfits = __shfl_sync(FULL, wfits, 0);
-                if (ow.ok && wfits) {
-                    if (ow.leader) p.beans[wb + ow.bean_idx] = ow.bean;
-                    if (ow.keeps) p.accs[wa + ow.acc_idx].ref = ow.acc_ref;
-                }
-                if (lane == 0) {
-                    cons_write_record(rec, ow);
-                    if (ow.ok && wfits) rec->bean_base = (uint32_t)wb, rec->acc_base = (uint32_t)wa;
-                }
+        while (m32) {
+            const int q = __ffs(m32) - 1;
+            m32 &= m32 - 1;
+            const int gw2 = __shfl_sync(FULL, g, q);
+            const unsigned long long slotw = __shfl_sync(FULL, slot, q), qoffw = __shfl_sync(FULL, qoff, q);
+            blu_record* recw = p.records + base + (unsigned long long)q;
+            const ConsLane ow = cons_compute<32>(p, true, gw2, slotw, qoffw, lane);
+            unsigned long long wb = 0, wa = 0;
+            int wfits = 1;
+            if (lane == 0 && ow.ok) {
+                wb = atomicAdd(&p.ctr->bean_used, (unsigned long long)ow.nb);
+                wa = atomicAdd(&p.ctr->acc_used, (unsigned long long)ow.nkept);
+                wfits = wb + (unsigned long long)ow.nb <= p.bean_cap && wa + (unsigned long long)ow.nkept <= p.acc_cap;
+                if (!wfits) p.ctr->cap_overflow = 1;
+            }
+            wb = __shfl_sync(FULL, wb, 0), wa = __shfl_sync(FULL, wa, 0), wfits = __shfl_sync(FULL, wfits, 0);
+            if (ow.ok && wfits) {
+                if (ow.leader) p.beans[wb + ow.bean_idx] = ow.bean;
+                if (ow.keeps) p.accs[wa + ow.acc_idx].ref = ow.acc_ref;
+            }
+            if (lane == 0) {
+                cons_write_record(recw, ow);
+                if (ow.ok && wfits) recw->bean_base = (uint32_t)wb, recw->acc_base = (uint32_t)wa;
             }
         }
     }
