@@ -337,7 +337,12 @@ constexpr int kRounds = kTile / 1024;        // phase B works in rounds of 32 un
 constexpr int kSegCap = 32 * 2 + 4;           // row starts one round can find (<= 1 per 16 bytes, else malformed)
 constexpr int kSRowCap = kTile / 26 + 8;     // a valid row is >= 26 bytes
 constexpr int kRecFlush = 128;                // buffered record headers that trigger a flush (one global atomic)
-constexpr int kRecBuf = 256;                  // capacity of the record buffer (beyond: the run reserves its record itself)
+constexpr int kRecBuf = 176;                  // capacity of the record buffer (beyond: the run reserves its record itself)
+#ifndef BLU_TOPQ
+#define BLU_TOPQ 160
+#endif
+constexpr int kTopQCap = BLU_TOPQ;            // top rows of a window whose field parse is deferred to the next window (0: parse in the run phase)
+constexpr uint16_t kTopQEmpty = 0xFFFFu;      // TopQ::where of a slot a failed reservation left unfilled
 constexpr uint32_t kSlotSlab = 1024;          // top-row slots a CTA reserves at a time (one global atomic)
 constexpr uint32_t kSlotLow = 64;             // a new slab is fetched at the end of a window that leaves fewer free slots
 constexpr int kCarryTop = 32;                 // top rows of the open query kept in shared memory (beyond: block path)
@@ -368,6 +373,16 @@ struct StagedRec {
     uint32_t pad;
 };
 
+// A top row found by the run phase, to be split and parsed later: one warp does it for ALL runs of a window with full lanes
+// (next window, by the warp that has no rows) instead of every run's warp doing it for its own two or three rows.
+struct TopQ {
+    uint32_t dst;    // HBM: top-row slot; carry: index into its tops[]
+    uint32_t info;   // packed field positions of the row (parse_row_lean), 0: unknown
+    uint16_t s, e;   // the row in its window
+    uint16_t where;  // 0: p.toprows, 1 / 2: carry[0] / carry[1]
+    uint16_t pad;
+};
+
 struct WinDesc {  // what a window covers; written one window ahead, together with the request for its bytes
     unsigned long long lo;  // text offset of win[0] (16-byte aligned)
     int loaded, tend, vb;   // bytes staged; end / begin of the text inside the window
@@ -394,6 +409,9 @@ struct StreamSmem {
     uint32_t headw[(kSRowCap + kTileThreads) / 32 + 2];  // head flags, one bit per row (the row loop writes whole rounds)
     uint32_t runs[kSRowCap + 1];     // head rows in arrival order: row | id length << 16 (bit 15: continuation of the carried query)
     StagedRec rec_buf[kRecBuf];  // record headers of finished queries, waiting for the next flush
+    TopQ tq[kTopQCap > 0 ? kTopQCap : 1];
+    unsigned long long tq_lo;    // text offset of the window the queued rows belong to
+    int tq_cnt;
     uint16_t stage[kSWarps][32];
     CarryRun carry[2];
     alignas(8) unsigned long long mbar[2];
@@ -572,6 +590,30 @@ __device__ __forceinline__ void classify_round(StreamSmem& S, const uint8_t* win
     }
 }
 
+// Splits and parses the queued top rows of the window whose bytes are in `win` (fields 1..4 through the tab positions the row
+// phase found: digit folds only; a row of any other shape leaves unparsed -- offset + length -- and is split by the consensus
+// kernel's full parser) and writes them where the run phase said.  Entries [first, n) in steps of `stride`.
+__device__ __forceinline__ void drain_topq(const RunParams& p, StreamSmem& S, const uint8_t* win, int first, int stride) {
+    const int n = S.tq_cnt < kTopQCap ? S.tq_cnt : kTopQCap;
+    const unsigned long long lo = S.tq_lo;
+    const bool ok = S.out_ok != 0;
+    for (int i = first; i < n; i += stride) {
+        const TopQ d = S.tq[i];
+        if (d.where == kTopQEmpty) continue;
+        TopRowRaw ref;
+        if (!top_row_from_info(win, (int)d.s, d.info, lo, ref)) {
+            ref.acc_off = lo + (unsigned long long)d.s;
+            ref.acc_len = (uint32_t)((int)d.e - (int)d.s);
+            ref.taxid = 0, ref.alnlen = 0, ref.pident = 0.0;
+            ref.dec_frac = kTopRowUnparsed;
+        }
+        if (d.where == 0) {
+            if (ok) p.toprows[d.dst] = ref;
+        } else
+            S.carry[d.where - 1].tops[d.dst] = ref;
+    }
+}
+
 __device__ __forceinline__ void write_record(blu_record* dst, const StagedRec& sr) {
     blu_record rec;
     rec.query_off = sr.abs;
@@ -674,6 +716,7 @@ __device__ __forceinline__ void tile_segment(const RunParams& p, StreamSmem& S, 
         S.has_blank = S.crowded = 0;
         S.n_runs = S.next_run = S.n_skip = S.term = S.new_open = 0;
         S.b_done = 0;
+        S.tq_cnt = 0;
         {
             // the CTA's first slab of top-row slots (about 40 per window of the segment, at most kSlotSlab)
             const unsigned long long est = ((seg_hi - seg_lo) / (unsigned long long)kTile + 1ull) * 40ull + (unsigned long long)kSlotLow;
@@ -799,6 +842,13 @@ __device__ __forceinline__ void tile_segment(const RunParams& p, StreamSmem& S, 
         const int inc_i = lane < kRounds ? S.geo.inc[lane] : n_starts;
         const int nfirst_i = lane < kRounds ? S.geo.nfirst[lane] : -1, plast_i = lane < kRounds ? S.geo.plast[lane] : -1;
         if (warp == kSWarps - 1) {
+            if (kTopQCap > 0 && S.tq_cnt > 0) {
+                // the previous window's top rows: its bytes are still in the other buffer (the copy into it is requested below)
+                drain_topq(p, S, S.win[buf ^ 1], lane, 32);
+                __syncwarp();
+                if (lane == 0) S.tq_cnt = 0;
+                __syncwarp();
+            }
             // ---- last newline, last complete row, the next window (its bytes are requested now) ---------------------------
             const unsigned ne = __ballot_sync(FULL, c_i > 0);
             int last_start = __shfl_sync(FULL, lane < kRounds ? S.warp_last[lane] : -1, ne ? 31 - __clz(ne) : 0);
@@ -1096,25 +1146,53 @@ __device__ __forceinline__ void tile_segment(const RunParams& p, StreamSmem& S, 
             dst = __shfl_sync(FULL, dst, 0);
             n_old = __shfl_sync(FULL, n_old, 0);
             const bool ok = S.out_ok != 0;
-            // ---- the run's top rows of this window: field split + number parse, one lane each ----------------------------------
-            if (lane < g_part && (kind & (RK_EMIT | RK_OPEN))) {
-                const int r = S.stage[warp][lane];
-                const int s = S.row_s[r];
-                const int re = blank ? row_end_search(S, s, last_nl) : (int)S.row_s[r + 1] - 1;
-                // a top row leaves the tile kernel as a reference into the text: the consensus kernel splits and parses it
-                // fields 1..4 through the tab positions the row phase found: digit folds only, no second tab search; a row of any
-                // other shape leaves unparsed (offset + length) and is split by the consensus kernel's full parser
-                TopRowRaw ref;
-                if (!top_row_from_info(win, s, S.rowinfo[r], lo, ref)) {
-                    ref.acc_off = lo + (unsigned long long)s;
-                    ref.acc_len = (uint32_t)(re - s);
-                    ref.taxid = 0, ref.alnlen = 0, ref.pident = 0.0;
-                    ref.dec_frac = kTopRowUnparsed;
+            // ---- the run's top rows of this window: queued for the warp that parses all of the window's top rows at once ------------
+            if (g_part > 0 && (kind & (RK_EMIT | RK_OPEN))) {
+                int qbase = -1;
+                if (kTopQCap > 0) {
+                    if (lane == 0) {
+                        // no undo when the queue is full (an undo could land after another warp's successful reservation and take
+                        // that warp's entries out of the count): the count stays above the capacity until the queue is drained,
+                        // every later run of this window parses its rows itself, and the slots this reservation left unfilled
+                        // are marked empty below
+                        qbase = atomicAdd(&S.tq_cnt, g_part);
+                        if (qbase + g_part <= kTopQCap) S.tq_lo = lo;
+                    }
+                    qbase = __shfl_sync(FULL, qbase, 0);
+                    if (qbase + g_part > kTopQCap) {
+                        if (lane < g_part && qbase + lane < kTopQCap) S.tq[qbase + lane].where = kTopQEmpty;
+                        qbase = -1;
+                    }
                 }
-                if (kind & RK_EMIT) {
-                    if (ok) p.toprows[slot + (uint32_t)(dst + lane)] = ref;
-                } else
-                    S.carry[(kind & RK_NEWCARRY) ? (cur ^ 1) : cur].tops[-1 - dst + lane] = ref;
+                if (lane < g_part) {
+                    const int r = S.stage[warp][lane];
+                    const int s = S.row_s[r];
+                    const int re = blank ? row_end_search(S, s, last_nl) : (int)S.row_s[r + 1] - 1;
+                    const int carry_buf = (kind & RK_NEWCARRY) ? (cur ^ 1) : cur;
+                    if (qbase >= 0) {
+                        TopQ d;
+                        d.info = S.rowinfo[r];
+                        d.s = (uint16_t)s, d.e = (uint16_t)re;
+                        d.pad = 0;
+                        if (kind & RK_EMIT)
+                            d.where = 0, d.dst = slot + (uint32_t)(dst + lane);
+                        else
+                            d.where = (uint16_t)(1 + carry_buf), d.dst = (uint32_t)(-1 - dst + lane);
+                        S.tq[qbase + lane] = d;
+                    } else {
+                        TopRowRaw ref;
+                        if (!top_row_from_info(win, s, S.rowinfo[r], lo, ref)) {
+                            ref.acc_off = lo + (unsigned long long)s;
+                            ref.acc_len = (uint32_t)(re - s);
+                            ref.taxid = 0, ref.alnlen = 0, ref.pident = 0.0;
+                            ref.dec_frac = kTopRowUnparsed;
+                        }
+                        if (kind & RK_EMIT) {
+                            if (ok) p.toprows[slot + (uint32_t)(dst + lane)] = ref;
+                        } else
+                            S.carry[carry_buf].tops[-1 - dst + lane] = ref;
+                    }
+                }
             }
             RCLK(4)
             // a carried query that ends here: its earlier top rows go in front of this window's
@@ -1194,8 +1272,13 @@ __device__ __forceinline__ void tile_segment(const RunParams& p, StreamSmem& S, 
         printf("rcl %d warp %d windows %d | queue %lld head %lld stats %lld decide %lld parse %lld old %lld\n", blockIdx.x, warp, n_win, rc[0] / (n_win + 1), rc[1] / (n_win + 1),
                rc[2] / (n_win + 1), rc[3] / (n_win + 1), rc[4] / (n_win + 1), rc[5] / (n_win + 1));
 #endif
-    // ---- the record headers still in the buffer -------------------------------------------------------------------------
+    // ---- the last window's queued top rows (its bytes are still in `buf`), the record headers still in the buffer -----------
     __syncthreads();
+    if (kTopQCap > 0) {
+        drain_topq(p, S, S.win[buf], tid, kTileThreads);
+        __syncthreads();
+        if (tid == 0) S.tq_cnt = 0;
+    }
     flush_records(p, S, tid);
     __syncthreads();
 }

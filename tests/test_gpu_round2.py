@@ -179,3 +179,26 @@ def test_scattered_query_with_a_failing_fragment():
     assert out.jsonl() == want
     assert int(eng.timings()["n_regrouped"]) == 1
     eng.close()
+
+
+@pytest.mark.parametrize("group", [3, 20, 32])
+def test_windows_full_of_top_rows(group):
+    """Every row of every query ties on the top bit score: each 32 KB window holds several hundred top rows, far more than
+    the tile kernel's shared-memory queue of top rows to parse -- runs that do not fit parse their rows in place, the
+    others are parsed one window later (or at the end of the CTA's segment), and queries span window boundaries."""
+    rng = random.Random(77 + group)
+    n_taxa = 40
+    ids = list(range(1, n_taxa + 1))
+    lin = [f"d__bac;p__p{t % 3};c__c{t % 7};o__o{t % 11};f__f{t % 13};g__g{t % 17};s__s{t}" for t in ids]
+    rows = []
+    for q in range(4000):
+        t0 = rng.randrange(n_taxa)
+        for h in range(group):
+            t = ids[(t0 + (h % 3 if rng.random() < 0.5 else 0)) % n_taxa]
+            rows.append(_row(f"q{q:05d}", f"ACC{q}_{h}.1", t, f"{90 + (h * 7 + q) % 10}.{(q + h) % 100:02d}", 200 + h, "640"))
+    text = "".join(rows).encode()
+    want = _oracle(ids, lin, "bacteria", "relaxed").run_raw(text)[0]
+    eng = _engine("bacteria", "relaxed")
+    eng.load_taxonomy_arrays(ids, lin)
+    assert eng.run_host(text).jsonl() == want
+    eng.close()
