@@ -731,32 +731,18 @@ BLU_HD bool same_first_field(const uint8_t* win, const uint64_t* tabw, int a, in
     return true;
 }
 
-// Same test for the streaming kernel, which already knows the length `la` of the first field of the row at `a`:
-// the row at `b` must have its first tab at the same distance and the same bytes in front of it.
-BLU_HD bool same_qid_lean(const uint8_t* win, const uint32_t* tabw32, int a, int la, int b) {
-    if (la >= 32 || la < 4) {
-        // rare shapes: the first tab of b by the general search
-        int lb = 0;
-        while (true) {
-            const uint32_t t = bits_at(tabw32, b + lb);
-            if (t) {
-                lb += blu_ffs32(t);
-                break;
-            }
-            lb += 32;
-            if (lb > la) return false;
-        }
-        if (lb != la) return false;
-        for (int i = 0; i < la; i++)
+// Same test for the streaming kernel, which already knows the length `la` of the first field of the row at `a`: the
+// la + 1 bytes "id, tab" of the two rows must be equal.  (The id at `a` holds no tab, so equal bytes put b's first tab at
+// la as well; the row at `b` lies in front of `a` in the same window, so b + la stays inside it whatever b's length.)
+BLU_HD bool same_qid_lean(const uint8_t* win, const uint32_t* /*tabw32*/, int a, int la, int b) {
+    const int n = la + 1;
+    if (n < 4) {
+        for (int i = 0; i < n; i++)
             if (win[a + i] != win[b + i]) return false;
         return true;
     }
-    const uint32_t tb = bits_at(tabw32, b);
-    if ((tb & ((2u << la) - 1u)) != (1u << la)) return false;  // first tab of b exactly at la
-    uint32_t diff = 0;
-    int i = 0;
-    for (; i + 4 <= la; i += 4) diff |= load_u32_unaligned(win, a + i) ^ load_u32_unaligned(win, b + i);
-    if (i < la) diff |= load_u32_unaligned(win, a + la - 4) ^ load_u32_unaligned(win, b + la - 4);  // overlapping last word
+    uint32_t diff = load_u32_unaligned(win, a + n - 4) ^ load_u32_unaligned(win, b + n - 4);  // last word (may overlap the one before)
+    for (int i = 0; i + 4 < n; i += 4) diff |= load_u32_unaligned(win, a + i) ^ load_u32_unaligned(win, b + i);
     return diff == 0;
 }
 

@@ -32,6 +32,14 @@ constexpr int kLongWarps = kLongThreads / 32;
 // small PTX wrappers (TMA 1-D bulk copy + mbarrier)
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// One shared-memory atomic add, as written: atomicAdd() on shared memory is expanded by the compiler into a warp-aggregated
+// sequence (vote, leader election, popc, shuffle: ~12 instructions), which is pure overhead where a single lane -- or a lane
+// or two of a diverged warp -- executes it, as everywhere in the tile kernel.
+__device__ __forceinline__ uint32_t atoms_add(void* addr, uint32_t v) {
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(addr)), "r"(v) : "memory");
+    return old;
+}
 
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -580,8 +588,10 @@ __device__ __forceinline__ void classify_round(StreamSmem& S, const uint8_t* win
         if (sh) seg[idx] = (uint16_t)(pos0 + 16 + __ffs(sh) - 1);
         cnt += __popc(bl) + __popc(bh);
     }
-    if (__any_sync(FULL, blank != 0) && lane == 0) S.has_blank = 1;
-    if (__any_sync(FULL, crowd != 0) && lane == 0) S.crowded = 1;
+    if (__any_sync(FULL, (blank | crowd) != 0)) {  // (one vote on the common path)
+        if (__any_sync(FULL, blank != 0) && lane == 0) S.has_blank = 1;
+        if (__any_sync(FULL, crowd != 0) && lane == 0) S.crowded = 1;
+    }
     __syncwarp();
     if (lane == 0) {
         S.warp_cnt[round] = cnt;
@@ -794,7 +804,7 @@ __device__ __forceinline__ void tile_segment(const RunParams& p, StreamSmem& S, 
             __syncwarp();
             if (lane == 0) {
                 __threadfence_block();
-                ticket = atomicAdd(&S.b_done, 1);
+                ticket = (int)atoms_add(&S.b_done, 1u);
             }
             ticket = __shfl_sync(FULL, ticket, 0);
             if (ticket == kSWarps - 1) {
@@ -957,7 +967,7 @@ __device__ __forceinline__ void tile_segment(const RunParams& p, StreamSmem& S, 
                     head = !same_qid_lean(win, S.tabm, s, ql, prv);
                 if (head) {
                     if (abs < seg_hi) {
-                        const int i = atomicAdd(&S.n_runs, 1);
+                        const int i = (int)atoms_add(&S.n_runs, 1u);
                         S.runs[i] = (uint32_t)r | ((uint32_t)(ql > 0xFFFF ? 0xFFFF : ql) << 16);
                     } else
                         S.term = 1;  // a query of the next segment starts here: this CTA ends with this window
@@ -966,7 +976,7 @@ __device__ __forceinline__ void tile_segment(const RunParams& p, StreamSmem& S, 
             const unsigned hb = __ballot_sync(FULL, head);
             if (lane == 0) S.headw[r >> 5] = hb;
             const unsigned sb = __ballot_sync(FULL, skip);
-            if (sb && lane == 0) atomicAdd(&S.n_skip, __popc(sb));
+            if (sb && lane == 0) atoms_add(&S.n_skip, (uint32_t)__popc(sb));
         }
         PCLK(4)
         __syncthreads();
@@ -1113,7 +1123,7 @@ __device__ __forceinline__ void tile_segment(const RunParams& p, StreamSmem& S, 
                 if (kind & RK_EMIT) {
                     // top-row slots from the CTA's slab (or, when it is exhausted, straight from the global counter)
                     if (g_tot > 0) {
-                        slot = atomicAdd(&S.slot_cur, (uint32_t)g_tot);
+                        slot = atoms_add(&S.slot_cur, (uint32_t)g_tot);
                         if (slot + (uint32_t)g_tot > S.slot_end || slot + (uint32_t)g_tot < slot) {
                             const unsigned long long rs = atomicAdd(&p.ctr->slot_count, (unsigned long long)g_tot);
                             slot = (uint32_t)rs;
@@ -1125,7 +1135,7 @@ __device__ __forceinline__ void tile_segment(const RunParams& p, StreamSmem& S, 
                     }
                     StagedRec sr;
                     sr.abs = abs, sr.qlen = qlen, sr.nrows = nrows, sr.mx = mx, sr.gtot = (uint32_t)g_tot, sr.slot = slot, sr.pad = 0;
-                    const int ri = atomicAdd(&S.rec_cnt, 1);
+                    const int ri = (int)atoms_add(&S.rec_cnt, 1u);
                     if (ri < kRecBuf)
                         S.rec_buf[ri] = sr;
                     else {
@@ -1155,7 +1165,7 @@ __device__ __forceinline__ void tile_segment(const RunParams& p, StreamSmem& S, 
                         // that warp's entries out of the count): the count stays above the capacity until the queue is drained,
                         // every later run of this window parses its rows itself, and the slots this reservation left unfilled
                         // are marked empty below
-                        qbase = atomicAdd(&S.tq_cnt, g_part);
+                        qbase = (int)atoms_add(&S.tq_cnt, (uint32_t)g_part);
                         if (qbase + g_part <= kTopQCap) S.tq_lo = lo;
                     }
                     qbase = __shfl_sync(FULL, qbase, 0);
