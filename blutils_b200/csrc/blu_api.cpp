@@ -934,6 +934,51 @@ std::string regroup_by_query(const char* text, uint64_t n) {
     return out;
 }
 
+// The same regrouping on the GPU (blu_regroup.cu): the table -- uploaded first when it is host text -- is rewritten in HBM.
+// Used whenever the table, its regrouped copy and ~72 bytes per row fit the device; BLU_REGROUP_HOST=1 forces the host path.
+struct DevText {
+    uint8_t* p = nullptr;
+    uint64_t n = 0;
+    DevText() = default;
+    DevText(const DevText&) = delete;
+    DevText& operator=(const DevText&) = delete;
+    ~DevText() {
+        if (p) cudaFree(p);
+    }
+};
+
+bool regroup_gpu(blu_ctx* c, const char* h_text, const uint8_t* d_text, uint64_t n, cudaStream_t s, DevText& out) {
+    if (const char* ev = getenv("BLU_REGROUP_HOST"))
+        if (atoi(ev)) return false;
+    if (n == 0) return false;
+    CK(cudaSetDevice(c->device));
+    DevText in;
+    const auto t_begin = std::chrono::steady_clock::now();
+    (void)t_begin;
+    if (!d_text) {
+        size_t free_b = 0, total_b = 0;
+        CK(cudaMemGetInfo(&free_b, &total_b));
+        if (2.2 * (double)n + (double)(256ull << 20) > (double)free_b) return false;
+        if (cudaMalloc((void**)&in.p, n + 512) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        CK(cudaMemcpyAsync(in.p, h_text, n, cudaMemcpyHostToDevice, s));
+        d_text = in.p;
+    }
+    uint64_t rows = 0;
+    const bool trace = getenv("BLU_REGROUP_TRACE") != nullptr;
+    const auto t0 = t_begin;
+    if (trace) cudaStreamSynchronize(s);
+    const auto t1 = std::chrono::steady_clock::now();
+    const int rc = regroup_device(d_text, n, s, &out.p, &out.n, &rows);
+    if (trace)
+        fprintf(stderr, "[blu regroup] upload %.2f ms, regroup_device %.2f ms (%llu rows, rc %d)\n", std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count(), (unsigned long long)rows, rc);
+    if (rc < 0) throw CudaErr(std::string("regroup_device: ") + cudaGetErrorString((cudaError_t)(-rc)));
+    return rc == 0;
+}
+
 // --- where the streamed path takes the text of chunk `ci` from -------------------------------------------------
 struct ChunkSource {
     virtual ~ChunkSource() = default;
@@ -1705,29 +1750,67 @@ static void require_tax(blu_ctx* c) {
     if (!c->tax) throw std::invalid_argument("no taxonomy loaded (call blu_taxonomy_load_json first)");
 }
 
-// host text -> result, on one or several GPUs; a scattered table is regrouped (data movement only) and run again
-static void run_host_any(blu_ctx* c, const char* text, uint64_t n, blu_result* r) {
-    const bool refs = (c->opts.flags & BLU_OPT_TEXT_REFS) != 0;
-    auto once = [&](const char* t, uint64_t len, bool text_refs) {
-        for (auto& p : r->parts) p.free_buffers();
-        r->parts.clear();
-        if (c->is_multi()) {
-            run_host_multi(c, t, len, r, text_refs);
-        } else {
-            CK(cudaSetDevice(c->device));
-            r->parts.resize(1);
-            RunStatus st;
-            run_host_single(c, t, len, &r->parts[0], st, text_refs);
-            settle(st);
-            r->n_rows = c->tm.n_rows;
-        }
-    };
+// the regrouped table (device memory of ours) through the device-text path of a single-device context
+static void run_regrouped_device(blu_ctx* c, const DevText& dt, blu_result* r) {
+    for (auto& p : r->parts) p.free_buffers();
+    r->parts.clear();
+    r->parts.resize(1);
+    RunStatus st;
     try {
-        once(text, n, refs);
-    } catch (const NonContiguous&) {
+        run_device_download(c, dt.p, dt.n, c->stream, &r->parts[0], st);
+    } catch (...) {  // nothing may still be reading the regrouped text when it is freed
+        cudaStreamSynchronize(c->stream);
+        cudaStreamSynchronize(c->d2h_stream);
+        throw;
+    }
+    if (st.dup_found) throw std::runtime_error("a regrouped table is still not contiguous");
+    settle(st);
+    r->n_rows = c->tm.n_rows;
+}
+
+// host text -> result, on one or several GPUs
+static void run_host_once(blu_ctx* c, const char* t, uint64_t len, blu_result* r, bool text_refs) {
+    for (auto& p : r->parts) p.free_buffers();
+    r->parts.clear();
+    if (c->is_multi()) {
+        run_host_multi(c, t, len, r, text_refs);
+    } else {
+        CK(cudaSetDevice(c->device));
+        r->parts.resize(1);
+        RunStatus st;
+        run_host_single(c, t, len, &r->parts[0], st, text_refs);
+        settle(st);
+        r->n_rows = c->tm.n_rows;
+    }
+}
+
+// a scattered table in host memory: regrouped (data movement only; on the GPU when it fits, else on the host) and run.
+// The regrouped text is ours: the result's strings are copied into a pool.
+static void run_scattered_host(blu_ctx* c, const char* text, uint64_t n, blu_result* r) {
+    DevText dt;
+    if (regroup_gpu(c, text, nullptr, n, c->stream, dt)) {
+        if (c->is_multi()) {
+            // the shards start from host text: the regrouped table comes back once and is cut like any other
+            std::string re((size_t)dt.n, '\0');
+            CK(cudaMemcpy(re.data(), dt.p, dt.n, cudaMemcpyDeviceToHost));
+            cudaFree(dt.p);
+            dt.p = nullptr;
+            run_host_once(c, re.data(), re.size(), r, false);
+        } else
+            run_regrouped_device(c, dt, r);
+        c->tm.n_regrouped = 2;
+    } else {
         const std::string re = regroup_by_query(text, n);
-        once(re.data(), re.size(), false);  // (the regrouped text is ours: its strings are copied into a pool)
+        run_host_once(c, re.data(), re.size(), r, false);
         c->tm.n_regrouped = 1;
+    }
+}
+
+static void run_host_any(blu_ctx* c, const char* text, uint64_t n, blu_result* r) {
+    try {
+        run_host_once(c, text, n, r, (c->opts.flags & BLU_OPT_TEXT_REFS) != 0);
+    } catch (const NonContiguous&) {
+        run_scattered_host(c, text, n, r);
     }
 }
 
@@ -1754,6 +1837,12 @@ int blu_consensus_run_device(blu_ctx* c, const void* dtext, uint64_t n, void* st
             settle(st);
             r->n_rows = c->tm.n_rows;
         } catch (const NonContiguous&) {
+            DevText dt;
+            if (regroup_gpu(c, nullptr, (const uint8_t*)dtext, n, s, dt)) {
+                run_regrouped_device(c, dt, r.get());
+                c->tm.n_regrouped = 2;
+                return;
+            }
             // regroup on the host (data movement only), then the normal streamed path
             std::string host(n, '\0');
             CK(cudaMemcpy(host.data(), dtext, n, cudaMemcpyDeviceToHost));
@@ -1898,18 +1987,7 @@ int blu_consensus_run_file(blu_ctx* c, const char* path, blu_result** out) {
                 if (got <= 0) throw IoErr("Unexpected error occurred on load table.");
                 off += (uint64_t)got;
             }
-            std::string re = regroup_by_query(all.data(), n);
-            std::string().swap(all);
-            const uint64_t keep_flags = c->opts.flags;
-            c->opts.flags &= ~(uint64_t)BLU_OPT_TEXT_REFS;  // (the regrouped text is ours)
-            try {
-                run_host_any(c, re.data(), re.size(), r.get());
-            } catch (...) {
-                c->opts.flags = keep_flags;
-                throw;
-            }
-            c->opts.flags = keep_flags;
-            c->tm.n_regrouped = 1;
+            run_scattered_host(c, all.data(), n, r.get());
         });
     }
     if (rc != BLU_OK) {

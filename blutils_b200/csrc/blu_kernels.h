@@ -131,4 +131,10 @@ cudaError_t launch_dup_merge_kernel(const unsigned long long* hashes, unsigned l
 constexpr int kLongTopCap = 8192;       // largest top bit-score group the block path handles (beyond: BLU_ERR_UNSUPPORTED)
 cudaError_t kernels_set_attributes();
 
+// blu_regroup.cu: rewrites a non-contiguous hit table (device memory) with every query's rows adjacent -- queries in order of
+// first appearance, rows of a query in file order (the reference's HashMap grouping, mod.rs:145,192).  0: *d_out is the
+// cudaMalloc'ed regrouped text (the caller frees it); 1: not possible on the device (memory, >= 2^31 rows, two ids with one
+// hash): regroup on the host; < 0: -cudaError_t.
+int regroup_device(const uint8_t* d_text, uint64_t n, cudaStream_t s, uint8_t** d_out, uint64_t* out_n, uint64_t* n_rows_out);
+
 }  // namespace blu

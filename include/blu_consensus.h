@@ -118,7 +118,7 @@ typedef struct blu_timings {
     uint64_t text_bytes, result_bytes, taxonomy_bytes;
     uint64_t h2d_bytes, d2h_bytes;
     uint64_t n_queries, n_rows, n_deferred_runs, n_kernel_launches;
-    uint64_t n_regrouped; /* 1 when the table was non-contiguous and had to be regrouped by query first */
+    uint64_t n_regrouped; /* non-zero when the table was non-contiguous and was regrouped by query first: 2 = on the GPU, 1 = on the host */
     uint64_t n_tile_launches; /* tile_kernel launches of the run (ranges / streamed chunks); ms_tile_kernel is their sum */
     uint64_t reserved[2];
 } blu_timings;

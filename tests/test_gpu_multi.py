@@ -91,7 +91,7 @@ def test_scattered_table_across_shards():
         eng.load_taxonomy_arrays(ids, lin)
         out = eng.run_host(text)
         assert out.jsonl() == want, devs
-        assert int(eng.timings()["n_regrouped"]) == 1
+        assert int(eng.timings()["n_regrouped"]) == 2  # regrouped on the first GPU of the context
         out.close()
         eng.close()
 

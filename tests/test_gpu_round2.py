@@ -177,7 +177,7 @@ def test_scattered_query_with_a_failing_fragment():
     eng.load_taxonomy_arrays(ids, lin)
     out = eng.run_host(text)
     assert out.jsonl() == want
-    assert int(eng.timings()["n_regrouped"]) == 1
+    assert int(eng.timings()["n_regrouped"]) == 2  # regrouped on the GPU
     eng.close()
 
 
@@ -201,4 +201,81 @@ def test_windows_full_of_top_rows(group):
     eng = _engine("bacteria", "relaxed")
     eng.load_taxonomy_arrays(ids, lin)
     assert eng.run_host(text).jsonl() == want
+    eng.close()
+
+
+def _scattered_table(rng, n_queries, max_hits, n_taxa, blank_lines=False, final_newline=True):
+    """Rows of every query dealt out over the file in up to three far-apart fragments (file order inside a query kept)."""
+    ids = list(range(1, n_taxa + 1))
+    lin = [f"d__bac;p__p{t % 3};c__c{t % 7};o__o{t % 11};f__f{t % 13};g__g{t % 17};s__s{t}" for t in ids]
+    parts = [[], [], []]
+    for q in range(n_queries):
+        t0 = rng.randrange(n_taxa)
+        hits = rng.randint(1, max_hits)
+        for h in range(hits):
+            t = ids[(t0 + rng.choice([0, 0, 1, 2, 17])) % n_taxa]
+            bits = 900 - 10 * (h // 3) + (1 if rng.random() < 0.05 else 0)  # now and then the best row sits in a later fragment
+            row = _row(f"read_{q:06d}/1" if q % 7 else f"M0{q}:long:read:name:{q:09d}:abcdefgh", f"ACC{q}_{h}.{h % 3}", t,
+                       f"{88 + (h * 5 + q) % 12}.{(q + h) % 100:02d}", 150 + h, str(bits))
+            parts[min(2, rng.randrange(4))].append(row)
+    rows = parts[0] + parts[1] + parts[2]
+    if blank_lines:
+        for i in range(5, len(rows), 211):
+            rows[i] = "\n" + rows[i]
+    text = "".join(rows)
+    if not final_newline:
+        text = text[:-1]
+    return ids, lin, text.encode()
+
+
+@pytest.mark.parametrize("where", ["gpu", "host"])
+@pytest.mark.parametrize("shape", ["plain", "blank_lines", "no_final_newline", "big"])
+def test_scattered_tables_regrouped(where, shape, monkeypatch):
+    """Non-contiguous tables (the reference's HashMap grouping, mod.rs:145,192) through both regrouping paths: on the GPU
+    (blu_regroup.cu: row index, id hash table with byte-exact check, stable radix sort, copy) and on the host; host text,
+    device text and a file; against the oracle, which groups the way the reference does."""
+    import torch
+
+    if where == "host":
+        monkeypatch.setenv("BLU_REGROUP_HOST", "1")
+    else:
+        monkeypatch.delenv("BLU_REGROUP_HOST", raising=False)
+    rng = random.Random(len(shape) * 31 + 5)
+    ids, lin, text = _scattered_table(rng, 60_000 if shape == "big" else 700, 9, 60, blank_lines=shape == "blank_lines",
+                                      final_newline=shape != "no_final_newline")
+    want = _oracle(ids, lin, "bacteria", "relaxed").run_raw(text)[0]
+    eng = _engine("bacteria", "relaxed")
+    eng.load_taxonomy_arrays(ids, lin)
+    code = 2 if where == "gpu" else 1
+    out = eng.run_host(text)
+    assert out.jsonl() == want
+    assert int(eng.timings()["n_regrouped"]) == code
+    out.close()
+    t = _to_device(text)
+    out = eng.run_device(t.data_ptr(), len(text), torch.cuda.current_stream().cuda_stream)
+    assert out.jsonl() == want
+    assert int(eng.timings()["n_regrouped"]) == code
+    out.close()
+    # a contiguous table afterwards on the same context: nothing is regrouped
+    ids2, lin2, text2 = _synth_case(5000, 300, 20, seed=3)
+    eng2 = _engine("bacteria", "relaxed")
+    eng2.load_taxonomy_arrays(ids2, lin2)
+    eng2.run_host(text2).close()
+    assert int(eng2.timings()["n_regrouped"]) == 0
+    eng2.close()
+    eng.close()
+
+
+def test_scattered_table_from_a_file(tmp_path):
+    rng = random.Random(99)
+    ids, lin, text = _scattered_table(rng, 3000, 6, 40)
+    want = _oracle(ids, lin, "bacteria", "cautious").run_raw(text)[0]
+    path = tmp_path / "scattered.blast.out"
+    path.write_bytes(text)
+    eng = _engine("bacteria", "cautious")
+    eng.load_taxonomy_arrays(ids, lin)
+    out = eng.run_file(str(path))
+    assert out.jsonl() == want
+    assert int(eng.timings()["n_regrouped"]) == 2
+    out.close()
     eng.close()
