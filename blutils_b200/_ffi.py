@@ -58,6 +58,7 @@ SYMBOLS = [
     ("blu_consensus_run_host", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_void_p)]),
     ("blu_consensus_run_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_void_p)]),
     ("blu_consensus_run_device_resident", C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.POINTER(C.c_void_p)]),
+    ("blu_result_device_text", C.c_void_p, [C.c_void_p, C.POINTER(C.c_uint64)]),
     ("blu_result_device_records", C.c_void_p, [C.c_void_p]),
     ("blu_result_device_beans", C.c_void_p, [C.c_void_p, C.POINTER(C.c_uint64)]),
     ("blu_result_device_accessions", C.c_void_p, [C.c_void_p, C.POINTER(C.c_uint64)]),

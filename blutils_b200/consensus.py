@@ -233,6 +233,12 @@ class ConsensusOutput:
         return (l.blu_result_device_records(self._h), l.blu_result_device_beans(self._h, C.byref(nb)), nb.value,
                 l.blu_result_device_accessions(self._h, C.byref(na)), na.value)
 
+    def device_text(self):
+        """(ptr, n_bytes) of the device text the references of a device-resident result point into: the caller's text, or the
+        regrouped copy the library made of a non-contiguous table (owned by the result)."""
+        n = C.c_uint64()
+        return _ffi.lib().blu_result_device_text(self._h, C.byref(n)), n.value
+
     def records(self):
         """The binary records as a ctypes array (host results)."""
         n = _ffi.lib().blu_result_num_queries(self._h)

@@ -238,6 +238,7 @@ struct ResultPartOwned {
     std::unique_ptr<DeviceSet> dev;
     blu_ctx* ctx = nullptr;            // (download needs the context's streams and kernels)
     const uint8_t* dtext = nullptr;    // the device text the references point into
+    std::shared_ptr<uint8_t> owned_dtext;  // ... when it is the library's regrouped copy of a scattered table (freed with the result)
     uint64_t dtext_len = 0;
     bool on_host = true;
     const char* strings() const { return ext_strings ? ext_strings : (const char*)b_pool.p; }
@@ -1884,9 +1885,30 @@ int blu_consensus_run_device_resident(blu_ctx* c, const void* dtext, uint64_t n,
             cudaStreamSynchronize(s);
             throw;
         }
-        // a scattered table cannot stay device-resident (regrouping is host-side data movement): say so instead of guessing
-        if (st.dup_found)
-            throw UnsupportedErr("the table's queries are not contiguous: use blu_consensus_run_device / _host / _file, which regroup it");
+        if (st.dup_found) {
+            // a scattered table: regrouped in HBM (blu_regroup.cu); the result's references then point into that copy, which
+            // the result owns (blu_result_device_text)
+            DevText dt;
+            if (!regroup_gpu(c, nullptr, (const uint8_t*)dtext, n, s, dt))
+                throw UnsupportedErr("the table's queries are not contiguous and it cannot be regrouped on the device: use blu_consensus_run_device / _host / _file");
+            for (auto& p : r->parts) p.free_buffers();
+            r->parts.clear();
+            r->parts.resize(1);
+            RunStatus st2;
+            try {
+                run_device_resident(c, dt.p, dt.n, s, &r->parts[0], st2);
+            } catch (...) {
+                cudaStreamSynchronize(s);
+                throw;
+            }
+            if (st2.dup_found) throw std::runtime_error("a regrouped table is still not contiguous");
+            r->parts[0].owned_dtext = std::shared_ptr<uint8_t>(dt.p, [](uint8_t* q) { cudaFree(q); });
+            dt.p = nullptr;
+            settle(st2);
+            r->n_rows = c->tm.n_rows;
+            c->tm.n_regrouped = 2;
+            return;
+        }
         settle(st);
         r->n_rows = c->tm.n_rows;
     });
@@ -1898,6 +1920,11 @@ int blu_consensus_run_device_resident(blu_ctx* c, const void* dtext, uint64_t n,
     return BLU_OK;
 }
 
+const void* blu_result_device_text(const blu_result* r, uint64_t* n) {
+    const bool ok = r && r->parts.size() == 1 && r->parts[0].dev;
+    if (n) *n = ok ? r->parts[0].dtext_len : 0;
+    return ok ? r->parts[0].dtext : nullptr;
+}
 const blu_record* blu_result_device_records(const blu_result* r) {
     return (r && r->parts.size() == 1 && r->parts[0].dev) ? r->parts[0].dev->rec.p : nullptr;
 }

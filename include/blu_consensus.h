@@ -161,8 +161,11 @@ int blu_consensus_run_device(blu_ctx* ctx, const void* dtext, uint64_t n_bytes, 
 /* Same, but the result stays in device memory ("text already in HBM -> records in HBM"): nothing but the
  * counters crosses PCIe, strings stay (offset, length) references into `dtext`, no host round trip inside the call.
  * blu_result_device_* give the device arrays; blu_result_download() brings them (and the referenced strings) to the
- * host, after which every host-side accessor / writer works on the result.  `dtext` must stay valid until then. */
+ * host, after which every host-side accessor / writer works on the result.  `dtext` must stay valid until then.
+ * blu_result_device_text() is the text the references point into: `dtext` itself, or -- when the table's queries were not
+ * contiguous (timings.n_regrouped) -- the regrouped copy the library made in device memory, owned by the result. */
 int blu_consensus_run_device_resident(blu_ctx* ctx, const void* dtext, uint64_t n_bytes, void* stream, blu_result** out);
+const void* blu_result_device_text(const blu_result* res, uint64_t* n_bytes);
 const blu_record* blu_result_device_records(const blu_result* res);
 const blu_bean* blu_result_device_beans(const blu_result* res, uint64_t* n);
 const blu_acc* blu_result_device_accessions(const blu_result* res, uint64_t* n);

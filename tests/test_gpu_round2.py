@@ -279,3 +279,35 @@ def test_scattered_table_from_a_file(tmp_path):
     assert int(eng.timings()["n_regrouped"]) == 2
     out.close()
     eng.close()
+
+
+def test_scattered_table_device_resident():
+    """A non-contiguous table through the device-resident entry point: regrouped in HBM, the records stay on the device and
+    reference the regrouped copy (blu_result_device_text), which the result owns; downloaded afterwards it is the oracle's
+    result.  The caller's text may be released as soon as the call has returned."""
+    import torch
+
+    rng = random.Random(4711)
+    ids, lin, text = _scattered_table(rng, 5000, 8, 50)
+    want = _oracle(ids, lin, "bacteria", "relaxed").run_raw(text)[0]
+    eng = _engine("bacteria", "relaxed")
+    eng.load_taxonomy_arrays(ids, lin)
+    t = _to_device(text)
+    out = eng.run_device_resident(t.data_ptr(), len(text), torch.cuda.current_stream().cuda_stream)
+    assert int(eng.timings()["n_regrouped"]) == 2
+    ptr, n = out.device_text()
+    assert ptr and ptr != t.data_ptr() and n >= len(text)  # (every row newline-terminated; nothing else changes)
+    t.zero_()  # the result must not depend on the caller's text any more
+    torch.cuda.synchronize()
+    assert out.download().jsonl() == want
+    out.close()
+    # contiguous table: the references point into the caller's text
+    ids2, lin2, text2 = _synth_case(5000, 300, 20, seed=3)
+    eng2 = _engine("bacteria", "relaxed")
+    eng2.load_taxonomy_arrays(ids2, lin2)
+    t2 = _to_device(text2)
+    out2 = eng2.run_device_resident(t2.data_ptr(), len(text2), torch.cuda.current_stream().cuda_stream)
+    assert out2.device_text() == (t2.data_ptr(), len(text2))
+    out2.close()
+    eng2.close()
+    eng.close()
