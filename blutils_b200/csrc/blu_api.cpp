@@ -952,6 +952,10 @@ bool regroup_gpu(blu_ctx* c, const char* h_text, const uint8_t* d_text, uint64_t
     if (const char* ev = getenv("BLU_REGROUP_HOST"))
         if (atoi(ev)) return false;
     if (n == 0) return false;
+    if (c->is_multi()) {  // on the context's first GPU, with that shard's stream
+        c = c->shards[0].get();
+        s = c->stream;
+    }
     CK(cudaSetDevice(c->device));
     DevText in;
     const auto t_begin = std::chrono::steady_clock::now();
