@@ -1,4 +1,4 @@
-// blu_tabular.h -- `blu blastn build-tabular`: a blutils result file (JSON or JSONL) -> the 12-column TSV.  Host only.
+// blu_tabular.h -- `blu blastn build-tabular`: a blutils result file (JSON, JSONL or YAML) -> the 12-column TSV.  Host only.
 // Follows parse_consensus_as_tabular (reference core/src/use_cases/parse_consensus_as_tabular/mod.rs:15-173) and the
 // readers it uses (core/src/domain/dtos/file_or_stdin.rs:96-176), including their quirks:
 //   * the existence check looks at `<input with its extension replaced by .json>`, whatever the format (mod.rs:24-33);
@@ -7,7 +7,8 @@
 //   * to a file the pieces are written without line breaks, to stdout one println! per piece (see blu_decode.h).
 // Serde semantics restated: unknown fields are skipped, a duplicate field is an error, Option fields may be missing or
 // null, LinnaeanRank (de)serialises to the same string (`Other(String)` is untagged, linnaean_ranks.rs:14-29), f64
-// fields accept any JSON number.  YAML input is not supported (BLU_ERR_UNSUPPORTED).
+// fields accept any JSON number.  YAML input goes through blu_yaml_in.h (the block-style subset serde_yaml writes; anything
+// else of YAML is refused with BLU_ERR_UNSUPPORTED) with serde_yaml's scalar typing.
 #pragma once
 #include <climits>
 #include <cstdint>
@@ -24,6 +25,7 @@
 #include "../../include/blu_consensus.h"
 #include "blu_decode.h"
 #include "blu_json.h"
+#include "blu_yaml_in.h"
 
 namespace blu {
 
@@ -272,17 +274,90 @@ inline bool parse_config_run_id(JsonCursor& c, std::string& run_id) {
     return true;
 }
 
+// ---- the same structs from a YAML document (blu_yaml_in.h) -----------------------------------------------------------------
+inline const YNode* yaml_field(const YNode& m, const char* name) {
+    for (auto& kv : m.map)
+        if (kv.first == name) return kv.second.get();
+    return nullptr;
+}
+inline const YNode& yaml_need(const YNode& m, const char* name) {
+    const YNode* n = yaml_field(m, name);
+    if (!n) yaml_typed::bad(m, std::string("missing field `") + name + "`");
+    return *n;
+}
+inline void yaml_need_map(const YNode& n, const char* what) {
+    if (n.kind != YNode::Map) yaml_typed::bad(n, std::string("invalid type: expected struct ") + what);
+}
+inline bool yaml_opt_string(const YNode& m, const char* name, std::string& out) {
+    const YNode* n = yaml_field(m, name);
+    if (!n || yaml_typed::is_null(*n)) return false;
+    out = yaml_typed::as_str(*n, name);
+    return true;
+}
+inline std::string yaml_uuid(const YNode& n, const std::string& s) {
+    JsonCursor c(s.data(), s.size());
+    try {
+        return parse_uuid(c, s);
+    } catch (const JsonError&) {
+        yaml_typed::bad(n, "invalid UUID");
+    }
+}
+
+inline void yaml_bean(const YNode& n, TabBean& b) {
+    yaml_need_map(n, "ConsensusBean");
+    b.rank = yaml_typed::as_str(yaml_need(n, "rank"), "rank");
+    b.identifier = yaml_typed::as_str(yaml_need(n, "identifier"), "identifier");
+    const int64_t occ = yaml_typed::as_i64(yaml_need(n, "occurrences"), "occurrences");
+    if (occ < INT32_MIN || occ > INT32_MAX) yaml_typed::bad(n, "occurrences does not fit i32");
+    b.occurrences = (int32_t)occ;
+    b.has_taxonomy = yaml_opt_string(n, "taxonomy", b.taxonomy);
+    const YNode& acc = yaml_need(n, "accessions");
+    if (acc.kind != YNode::Seq) yaml_typed::bad(acc, "invalid type: expected a sequence for accessions");
+    for (auto& a : acc.seq) b.accessions.push_back(yaml_typed::as_str(*a, "accessions"));
+}
+
+inline void yaml_taxon(const YNode& n, TabTaxon& t) {
+    yaml_need_map(n, "TaxonomyBean");
+    t.reached_rank = yaml_typed::as_str(yaml_need(n, "reachedRank"), "reachedRank");
+    std::string tmp;
+    yaml_opt_string(n, "maxAllowedRank", tmp);  // Option<LinnaeanRank>: not printed
+    t.identifier = yaml_typed::as_str(yaml_need(n, "identifier"), "identifier");
+    t.perc_identity = yaml_typed::as_f64(yaml_need(n, "percIdentity"), "percIdentity");
+    t.bit_score = yaml_typed::as_f64(yaml_need(n, "bitScore"), "bitScore");
+    t.has_taxonomy = yaml_opt_string(n, "taxonomy", t.taxonomy);
+    t.mutated = yaml_typed::as_bool(yaml_need(n, "mutated"), "mutated");
+    t.single_match = yaml_typed::as_bool(yaml_need(n, "singleMatch"), "singleMatch");
+    const YNode* beans = yaml_field(n, "consensusBeans");
+    if (beans && !yaml_typed::is_null(*beans)) {
+        if (beans->kind != YNode::Seq) yaml_typed::bad(*beans, "invalid type: expected a sequence for consensusBeans");
+        t.has_beans = true;
+        for (auto& b : beans->seq) {
+            t.beans.emplace_back();
+            yaml_bean(*b, t.beans.back());
+        }
+    }
+}
+
+inline void yaml_result(const YNode& n, TabResult& r) {
+    yaml_need_map(n, "QueryWithConsensus");
+    std::string tmp;
+    if ((r.has_run_id = yaml_opt_string(n, "runId", tmp))) r.run_id = yaml_uuid(n, tmp);
+    r.query = yaml_typed::as_str(yaml_need(n, "query"), "query");
+    const YNode* t = yaml_field(n, "taxon");
+    if (t && !yaml_typed::is_null(*t)) {
+        r.has_taxon = true;
+        yaml_taxon(*t, r.taxon);
+    }
+}
+
 }  // namespace tabular_detail
 
-// Returns BLU_OK, BLU_ERR_IO (with `err` set: the reference's Err(MappedErrors)) or BLU_ERR_UNSUPPORTED (YAML input).
+// Returns BLU_OK, BLU_ERR_IO (with `err` set: the reference's Err(MappedErrors)) or BLU_ERR_UNSUPPORTED (YAML constructs outside
+// the subset blu_yaml_in.h reads).
 // in_path NULL or "-": stdin.  out_path NULL: stdout.  run_id_for_missing: used where neither a result nor the config
 // carries a run id (NULL: a fresh UUIDv4, as the reference).
 inline int result_file_to_tabular(const char* in_path, const char* out_path, int input_format, const char* run_id_for_missing, std::string& err) {
     using namespace tabular_detail;
-    if (input_format == BLU_FORMAT_YAML) {
-        err = "YAML input of build-tabular is not supported";
-        return BLU_ERR_UNSUPPORTED;
-    }
     const bool from_stdin = !in_path || std::string_view(in_path) == "-";
     std::string buf;
     if (from_stdin)
@@ -339,6 +414,24 @@ inline int result_file_to_tabular(const char* in_path, const char* out_path, int
             }
             c.end();
             if (!have_results) c.fail("missing field `results`");
+        } else if (input_format == BLU_FORMAT_YAML) {
+            YamlReader reader;
+            const std::unique_ptr<YNode> root = reader.parse(buf);
+            yaml_need_map(*root, "BlutilsOutput");
+            const YNode& rs = yaml_need(*root, "results");
+            if (rs.kind != YNode::Seq) yaml_typed::bad(rs, "invalid type: expected a sequence for results");
+            results.reserve(rs.seq.size());
+            for (auto& item : rs.seq) {
+                results.emplace_back();
+                yaml_result(*item, results.back());
+            }
+            const YNode* cfg = yaml_field(*root, "config");
+            if (cfg && !yaml_typed::is_null(*cfg)) {
+                yaml_need_map(*cfg, "BlastBuilder");
+                const YNode& id = yaml_need(*cfg, "runId");
+                cfg_run_id = yaml_uuid(id, yaml_typed::as_str(id, "runId"));
+                have_cfg = true;
+            }
         } else {
             size_t pos = 0;
             while (pos < buf.size()) {
@@ -362,6 +455,12 @@ inline int result_file_to_tabular(const char* in_path, const char* out_path, int
     } catch (const JsonError& e) {
         err = std::string(input_format == BLU_FORMAT_JSON ? "unable to parse content as JSON: " : "unable to parse line as JSON: ") + e.what();
         return BLU_ERR_IO;
+    } catch (const YamlError& e) {
+        err = std::string("unable to parse content as YAML: ") + e.what();
+        return BLU_ERR_IO;
+    } catch (const YamlUnsupported& e) {
+        err = e.what();
+        return BLU_ERR_UNSUPPORTED;
     }
     const std::string fallback = have_cfg ? cfg_run_id : (run_id_for_missing ? std::string(run_id_for_missing) : uuid_v4());
 

@@ -210,7 +210,8 @@ int blu_result_write_tabular(const blu_result* res, const char* path, const char
  * result file (BLU_FORMAT_JSON or BLU_FORMAT_JSONL; path NULL or "-" = stdin) and writes the same TSV (output_file NULL =
  * stdout, else extension forced to `.tsv`).  Needs no context and no GPU.  `run_id` is used where neither the result nor
  * the config carries one (NULL = a fresh UUIDv4, as the reference).  BLU_ERR_IO with the message in `err` mirrors the
- * reference's Err(MappedErrors); YAML input returns BLU_ERR_UNSUPPORTED. */
+ * reference's Err(MappedErrors); YAML input is read in the block style
+ * the writer produces (comments, any quoting, either sequence indentation); other YAML constructs return BLU_ERR_UNSUPPORTED. */
 int blu_result_file_to_tabular(const char* blu_result_path, const char* output_file, int input_format, const char* run_id, char* err,
                                size_t errlen);
 void blu_result_free(blu_result* res);

@@ -108,8 +108,6 @@ def test_errors(tmp_path):
         with pytest.raises(MappedErrors, match=what):
             _tab(str(bad), str(tmp_path / "o.tsv"))
     bad.write_text("{\"results\": []}")
-    with pytest.raises(Unsupported):
-        _tab(str(bad), None, "yaml")
     _tab(str(bad), str(tmp_path / "empty.tsv"))  # config may be missing (Option); no results -> header only
     assert (tmp_path / "empty.tsv").read_text() == po.results_to_tabular([], RUN_ID, to_stdout=False)
 
@@ -155,12 +153,10 @@ def test_cli_stdout_and_stdin(tmp_path):
     assert p.returncode == 101 and b"does not exist" in p.stderr
 
 
-def test_random_documents(tmp_path):
-    """Seeded random result documents (escapes, non-ASCII, surrogate pairs, float shapes, optional fields in any order) written by
-    Python's json module in both ASCII-escaped and raw UTF-8 form: same TSV as the oracle computes from the same objects."""
+def _random_results(seed, n=300):
     import random
 
-    rng = random.Random(20261018)
+    rng = random.Random(seed)
     alphabet = ["a", "Z", "0", " ", "_", "-", ".", ";", "\"", "\\", "/", "\t", "\n", "é", "ß", "漢", "𝔘", " ", "|", "'"]
 
     def word(lo=1, hi=12):
@@ -182,7 +178,7 @@ def test_random_documents(tmp_path):
         return dict(items)
 
     results = []
-    for i in range(300):
+    for i in range(n):
         if rng.random() < 0.15:
             results.append({"query": word(), "taxon": None})
             continue
@@ -195,6 +191,13 @@ def test_random_documents(tmp_path):
             "reachedRank": rng.choice(["domain", "family", "strain", word()]), "maxAllowedRank": rng.choice([None, "genus"]), "identifier": word(),
             "percIdentity": number(), "bitScore": number(), "taxonomy": rng.choice([None, "d__bac;" + word()]), "mutated": rng.random() < 0.5,
             "singleMatch": rng.random() < 0.5, "consensusBeans": beans}})
+    return rng, results, shuffled
+
+
+def test_random_documents(tmp_path):
+    """Seeded random result documents (escapes, non-ASCII, surrogate pairs, float shapes, optional fields in any order) written by
+    Python's json module in both ASCII-escaped and raw UTF-8 form: same TSV as the oracle computes from the same objects."""
+    rng, results, shuffled = _random_results(20261018)
     doc = {"config": None, "results": [shuffled(dict(r, runId=RUN_ID, taxon=shuffled(r["taxon"]) if r["taxon"] else None)) for r in results]}
     want = po.results_to_tabular(results, RUN_ID, to_stdout=False)
     for ascii_only in (True, False):
@@ -202,3 +205,169 @@ def test_random_documents(tmp_path):
         src.write_text(json.dumps(doc, ensure_ascii=ascii_only, indent=rng.choice([None, 1, 4])), encoding="utf-8")
         _tab(str(src), str(tmp_path / f"rand{int(ascii_only)}.tsv"))
         assert (tmp_path / f"rand{int(ascii_only)}.tsv").read_text(encoding="utf-8") == want
+
+
+# ---- YAML input (file_or_stdin.rs:113-130: serde_yaml::from_str::<BlutilsOutput>) ----------------------------------------------
+
+def _yaml_doc(results, run_id=RUN_ID, seq_indent=0, config="null"):
+    """The block style serde_yaml writes (pyoracle.results_to_yaml), with Option fields that are None as `null` and, optionally,
+    sequences indented below their key (the other common style)."""
+    def s(v):
+        return "null" if v is None else po.yaml_str(v)
+
+    si = " " * seq_indent
+    o = ["results: []\n" if not results else "results:\n"]
+    for r in results:
+        p = si + "  "
+        o.append(si + "- " + (("runId: " + s(run_id) + "\n" + p) if run_id else "") + "query: " + s(r["query"]) + "\n")
+        t = r["taxon"]
+        if t is None:
+            o.append(p + "taxon: null\n")
+            continue
+        q = p + "  "
+        o.append(p + "taxon:\n" + q + "reachedRank: " + s(t["reachedRank"]) + "\n" + q + "maxAllowedRank: " + s(t["maxAllowedRank"]) + "\n" + q +
+                 "identifier: " + s(t["identifier"]) + "\n" + q + "percIdentity: " + po.ryu_f64(t["percIdentity"]) + "\n" + q + "bitScore: " +
+                 po.ryu_f64(t["bitScore"]) + "\n" + q + "taxonomy: " + s(t["taxonomy"]) + "\n" + q + "mutated: " + ("true" if t["mutated"] else "false") +
+                 "\n" + q + "singleMatch: " + ("true" if t["singleMatch"] else "false") + "\n")
+        beans = t["consensusBeans"]
+        if beans is None:
+            o.append(q + "consensusBeans: null\n")
+            continue
+        o.append(q + "consensusBeans: []\n" if not beans else q + "consensusBeans:\n")
+        for b in beans:
+            bi = q + si
+            o.append(bi + "- rank: " + s(b["rank"]) + "\n" + bi + "  identifier: " + s(b["identifier"]) + "\n" + bi + "  occurrences: " +
+                     str(b["occurrences"]) + "\n" + bi + "  taxonomy: " + s(b["taxonomy"]) + "\n")
+            o.append(bi + "  accessions: []\n" if not b["accessions"] else bi + "  accessions:\n")
+            for a in b["accessions"]:
+                o.append(bi + "  " + si + "- " + s(a) + "\n")
+    o.append("config: " + config + "\n")
+    return "".join(o)
+
+
+@pytest.mark.parametrize("seq_indent", [0, 2])
+def test_yaml_input_mock_run(tmp_path, seq_indent):
+    """The YAML that build-consensus writes for the mock 16S run -> the same TSV as from its JSON."""
+    res = _results()
+    assert _yaml_doc(res) == po.results_to_yaml(res, RUN_ID)  # (the helper really is the writer's format)
+    src = tmp_path / "blutils.yaml"
+    (tmp_path / "blutils.json").write_text("{}")  # what the reference's existence check looks at (mod.rs:24-33)
+    src.write_text(_yaml_doc(res, seq_indent=seq_indent))
+    _tab(str(src), str(tmp_path / "t.tsv"), "yaml")
+    assert (tmp_path / "t.tsv").read_text() == po.results_to_tabular(res, RUN_ID, to_stdout=False)
+    # through the CLI, from stdin
+    cli = os.path.join(ROOT, "blutils_b200", "blu")
+    if os.path.exists(cli):
+        p = subprocess.run([cli, "blastn", "build-tabular", "--input-format", "yaml"], input=src.read_bytes(), stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                           timeout=60)
+        assert p.returncode == 0, p.stderr
+        assert p.stdout.decode() == po.results_to_tabular(res, RUN_ID, to_stdout=True)
+
+
+def test_yaml_input_random_documents(tmp_path):
+    """Random strings (quotes, escapes, non-ASCII, astral characters, YAML indicators, things that look like numbers / booleans /
+    null) through the writer's quoting rules (pyoracle.yaml_str) and back: the TSV is the one computed from the objects."""
+    rng, results, _ = _random_results(777, n=400)
+    tricky = ["null", "~", "true", "No", "0x1F", "1e3", "-.inf", "007", "- x", "a: b", "#c", "x #y", "'q'", "\"d\"", " lead", "trail ", "[a]", "{b}", "&a", "*a",
+              "!t", "|", ">", "%", "@", "`", "?", ": ", "---", "...", "a\tb", "\u00e9\u2028x", "\U0001d518", "back\\slash"]
+    for i, r in enumerate(results):
+        r["query"] = tricky[i % len(tricky)] if i % 3 == 0 else r["query"]
+        if r["taxon"] and i % 5 == 0:
+            r["taxon"]["identifier"] = tricky[(i // 5) % len(tricky)]
+    (tmp_path / "r.json").write_text("{}")
+    src = tmp_path / "r.yaml"
+    src.write_text(_yaml_doc(results), encoding="utf-8")
+    _tab(str(src), str(tmp_path / "r.tsv"), "yaml")
+    assert (tmp_path / "r.tsv").read_text(encoding="utf-8") == po.results_to_tabular(results, RUN_ID, to_stdout=False)
+
+
+def test_yaml_input_hand_edited(tmp_path):
+    """What a person does to such a file: comments, a document start, blank lines, other quoting, `~`, unknown keys, a config with
+    a run id, integers and exponents where floats are expected, deeper indentation."""
+    text = """# produced by blu, edited by hand
+---
+config:
+    runId: "11111111-2222-4333-8444-555555555555"   # used where a result has none
+    isConfig: true
+    anything: []
+
+results:
+    - query: 'q one'
+      extra: {}
+      taxon:
+          reachedRank: species-group
+          identifier: "x\ty \u00e9 \x41"
+          percIdentity: 1e2
+          bitScore: 845
+          taxonomy: ~
+          mutated: False
+          singleMatch: TRUE
+          consensusBeans:
+              - rank: Species
+                identifier: b
+                occurrences: 0x10
+                accessions: [ ]
+              - {}
+    - runId: 0b0e3c55-7a2f-4a61-9d4e-5f1c2a7b8c9d
+      query: q2
+      taxon: null
+    - query: "3"
+      runId: null
+      taxon:
+          reachedRank: genus
+          maxAllowedRank:
+          identifier: g
+          percIdentity: 97.125
+          bitScore: +.5
+          mutated: true
+          singleMatch: false
+...
+"""
+    (tmp_path / "h.json").write_text("{}")
+    src = tmp_path / "h.yaml"
+    from blutils_b200 import MappedErrors
+
+    src.write_text(text)
+    with pytest.raises(MappedErrors, match="missing field `rank`"):  # the `- {}` bean
+        _tab(str(src), str(tmp_path / "h.tsv"), "yaml")
+    src.write_text(text.replace("              - {}\n", ""))
+    _tab(str(src), str(tmp_path / "h.tsv"), "yaml")
+    got = (tmp_path / "h.tsv").read_text().split("\n")  # (to a file the pieces are written without line breaks: one long line)
+    want = po.results_to_tabular([
+        {"query": "q one", "taxon": {"reachedRank": "species-group", "maxAllowedRank": None, "identifier": "x\ty \u00e9 A", "percIdentity": 100.0, "bitScore": 845.0,
+                                     "taxonomy": None, "mutated": False, "singleMatch": True,
+                                     "consensusBeans": [{"rank": "Species", "identifier": "b", "occurrences": 16, "taxonomy": None, "accessions": []}]}},
+        {"query": "q2", "taxon": None},
+        {"query": "3", "taxon": {"reachedRank": "genus", "maxAllowedRank": None, "identifier": "g", "percIdentity": 97.125, "bitScore": 0.5, "taxonomy": None,
+                                 "mutated": True, "singleMatch": False, "consensusBeans": None}}], OTHER_ID, to_stdout=False)
+    assert "\n".join(got) == want
+
+
+def test_yaml_input_errors_and_refusals(tmp_path):
+    from blutils_b200 import MappedErrors, Unsupported
+
+    (tmp_path / "e.json").write_text("{}")
+    src = tmp_path / "e.yaml"
+    ok = "results:\n- query: q\n  taxon: null\nconfig: null\n"
+    src.write_text(ok)
+    _tab(str(src), str(tmp_path / "e.tsv"), "yaml")
+    for text, what in [("config: null\n", "missing field `results`"), ("results:\n- taxon: null\n", "missing field `query`"),
+                       ("results:\n- query: q\n  query: r\n", "duplicate entry"), ("results: 3\n", "expected a sequence"),
+                       ("results:\n- query: q\n  runId: nope\n", "invalid UUID"), ("results:\n- query: [a, b]\n", None),
+                       ("results:\n- query: q\n  taxon:\n    reachedRank: s\n    identifier: i\n    percIdentity: high\n", "expected a float"),
+                       ("results:\n- query: q\n  taxon:\n    reachedRank: s\n    identifier: i\n    percIdentity: 1\n    bitScore: 2\n    mutated: yes\n",
+                        "expected a boolean"),
+                       ("results:\n- query: \"a\\qb\"\n", "unknown escape"), ("results:\n\t- query: q\n", "tab"), ("- a\nb: c\n", "document end"),
+                       ("results:\n- query: q\n   taxon: null\n", "indentation")]:
+        src.write_text(text)
+        if what is None:
+            with pytest.raises(Unsupported):
+                _tab(str(src), str(tmp_path / "e.tsv"), "yaml")
+        else:
+            with pytest.raises(MappedErrors, match=what):
+                _tab(str(src), str(tmp_path / "e.tsv"), "yaml")
+    for text in ["results: &a []\n", "results: !!seq []\n", "results:\n- query: |\n    block\n", "results:\n- query: \"two\n    lines\"\n",
+                 "results: []\n---\nresults: []\n", "results:\n- query: *q\n", "? complex\n: key\n"]:
+        src.write_text(text)
+        with pytest.raises(Unsupported):
+            _tab(str(src), str(tmp_path / "e.tsv"), "yaml")
