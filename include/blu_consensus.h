@@ -207,7 +207,7 @@ int blu_result_write(const blu_result* res, const char* path, int format, const 
  * not writing line breaks between pieces in file mode. */
 int blu_result_write_tabular(const blu_result* res, const char* path, const char* run_id);
 /* `blu blastn build-tabular` proper (parse_consensus_as_tabular/mod.rs:15-173 + file_or_stdin.rs:96-176): reads a blutils
- * result file (BLU_FORMAT_JSON or BLU_FORMAT_JSONL; path NULL or "-" = stdin) and writes the same TSV (output_file NULL =
+ * result file (BLU_FORMAT_JSON, BLU_FORMAT_JSONL or BLU_FORMAT_YAML; path NULL or "-" = stdin) and writes the same TSV (output_file NULL =
  * stdout, else extension forced to `.tsv`).  Needs no context and no GPU.  `run_id` is used where neither the result nor
  * the config carries one (NULL = a fresh UUIDv4, as the reference).  BLU_ERR_IO with the message in `err` mirrors the
  * reference's Err(MappedErrors); YAML input is read in the block style
