@@ -16,7 +16,7 @@ static void usage() {
             "           -t|--tax-file <FILE> --taxon <fungi|bacteria|eukaryotes|custom> --strategy <cautious|relaxed>\n"
             "           [-c|--custom-taxon-cutoff-file <FILE>] [-u|--use-taxid] [--blutils-out-file <FILE>]\n"
             "           [--out-format <json|jsonl|yaml>] [--device N | --devices N,M,...]\n"
-            "       blu blastn build-tabular [BLU_RESULT|-] [-o|--output-file <FILE>] [-i|--input-format <json|jsonl>]\n");
+            "       blu blastn build-tabular [BLU_RESULT|-] [-o|--output-file <FILE>] [-i|--input-format <json|jsonl|yaml>]\n");
 }
 
 [[noreturn]] static void die(const std::string& m) {
