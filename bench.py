@@ -281,6 +281,15 @@ def main():
     def sum_over_ranks(x):
         return reduce(x, dist.ReduceOp.SUM if world > 1 else None)
 
+    def every_rank(x: float):
+        """x of every rank, in rank order (evidence for what bounds a multi-GPU number: the slowest rank sets the time)"""
+        if world == 1:
+            return [x]
+        t = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t[rank] = x
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(v) for v in t.tolist()]
+
     def min_over_ranks(x):
         return reduce(x, dist.ReduceOp.MIN if world > 1 else None)
 
@@ -444,7 +453,9 @@ def main():
             e2e_launches += int(tm["n_kernel_launches"])
             out.close()
     torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0) / e2e_steps
+    e2e_own = time.perf_counter() - t0
+    e2e_s = max_over_ranks(e2e_own) / e2e_steps
+    e2e_per_rank = every_rank(e2e_own / e2e_steps * 1e3)
     barrier()
     e2e_q = sum_over_ranks(float(host_q * passes))
     e2e_rows = sum_over_ranks(float(host_rows * passes))
@@ -478,6 +489,7 @@ def main():
     d2h_c = eng.measure_d2h(1 << 30)
     barrier()
     h2d_sum, d2h_sum = sum_over_ranks(h2d_c), sum_over_ranks(d2h_c)
+    h2d_per_rank = every_rank(h2d_c)
     if streamed_only:
         total_q, total_rows, total_bytes = e2e_q, e2e_rows, e2e_bytes
         launches = e2e_launches
@@ -491,6 +503,7 @@ def main():
                "ms_per_step": e2e_s * 1e3, "text_gb_per_s": e2e_bytes / e2e_s / 1e9, "hit_rows_per_s": e2e_rows / e2e_s,
                "pinned_h2d_concurrent_gb_per_s": h2d_sum, "pinned_d2h_concurrent_gb_per_s": d2h_sum,
                "frac_of_concurrent_h2d_peak": (e2e_bytes / e2e_s / 1e9) / h2d_sum if h2d_sum else None,
+               "per_rank_ms_per_step": [round(v, 2) for v in e2e_per_rank], "per_rank_pinned_h2d_concurrent_gb_per_s": [round(v, 1) for v in h2d_per_rank],
                "sample": (f"{host_q} queries ({host_bytes / 1e9:.2f} GB of text) per rank in pinned host memory" +
                           (f", streamed {passes} times per step = the rank's {q_rank}-query shard" if streamed_only else
                            ("" if host_q == q_rank else f" = the first part of the rank's {q_rank}-query shard (--host-gb)")))}
