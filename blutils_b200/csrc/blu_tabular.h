@@ -415,16 +415,14 @@ inline int result_file_to_tabular(const char* in_path, const char* out_path, int
             c.end();
             if (!have_results) c.fail("missing field `results`");
         } else if (input_format == BLU_FORMAT_YAML) {
-            YamlReader reader;
-            const std::unique_ptr<YNode> root = reader.parse(buf);
+            YamlReader reader;  // (the results are converted one by one as they are read: no tree of the whole file)
+            const std::unique_ptr<YNode> root = reader.parse(buf, "results", [&](const YNode& item) {
+                results.emplace_back();
+                yaml_result(item, results.back());
+            });
             yaml_need_map(*root, "BlutilsOutput");
             const YNode& rs = yaml_need(*root, "results");
             if (rs.kind != YNode::Seq) yaml_typed::bad(rs, "invalid type: expected a sequence for results");
-            results.reserve(rs.seq.size());
-            for (auto& item : rs.seq) {
-                results.emplace_back();
-                yaml_result(*item, results.back());
-            }
             const YNode* cfg = yaml_field(*root, "config");
             if (cfg && !yaml_typed::is_null(*cfg)) {
                 yaml_need_map(*cfg, "BlastBuilder");

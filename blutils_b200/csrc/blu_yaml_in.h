@@ -19,6 +19,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <memory>
 #include <stdexcept>
 #include <string>
@@ -52,6 +53,11 @@ class YamlReader {
     };
     std::vector<Line> lines_;
     size_t at_ = 0;
+    // streaming: the items of the block sequence under this root key are handed to the callback one by one and not kept
+    // (a result file holds millions of them; a tree of all of them would be several times the file)
+    std::string stream_key_;
+    std::function<void(const YNode&)> on_item_;
+    bool streaming_next_seq_ = false;
 
     [[noreturn]] static void fail(int line, const std::string& m) { throw YamlError(m + " at line " + std::to_string(line)); }
     [[noreturn]] static void refuse(int line, const std::string& m) { throw YamlUnsupported("YAML input: " + m + " at line " + std::to_string(line) + " is not supported by this reader"); }
@@ -239,12 +245,20 @@ class YamlReader {
     }
 
     // the node that starts at the current line, which is indented by exactly `indent`
-    std::unique_ptr<YNode> node(int indent) {
+    std::unique_ptr<YNode> node(int indent, bool root = false) {
         const Line first = lines_[at_];
+        const bool stream = streaming_next_seq_;  // (set by the root mapping for the value of the streamed key)
+        streaming_next_seq_ = false;
         if (is_seq_item(first.body)) {
             auto n = std::make_unique<YNode>();
             n->kind = YNode::Seq;
             n->line = first.no;
+            auto keep = [&](std::unique_ptr<YNode> item) {
+                if (stream)
+                    on_item_(*item);
+                else
+                    n->seq.push_back(std::move(item));
+            };
             while (at_ < lines_.size() && lines_[at_].indent == indent && is_seq_item(lines_[at_].body)) {
                 const Line cur = lines_[at_];
                 std::string_view rest = cur.body.substr(1);
@@ -254,15 +268,15 @@ class YamlReader {
                 if (rest.empty() || rest[0] == '#') {
                     at_++;
                     if (at_ < lines_.size() && lines_[at_].indent > indent)
-                        n->seq.push_back(node(lines_[at_].indent));
+                        keep(node(lines_[at_].indent));
                     else
-                        n->seq.push_back(null_node(cur.no));
+                        keep(null_node(cur.no));
                     continue;
                 }
                 // the item's content behaves like a line of its own, indented to where it starts
                 lines_[at_].indent = indent + 1 + (int)sp;
                 lines_[at_].body = rest;
-                n->seq.push_back(node(lines_[at_].indent));
+                keep(node(lines_[at_].indent));
             }
             if (at_ < lines_.size() && lines_[at_].indent > indent) fail(lines_[at_].no, "bad indentation of a sequence entry");
             return n;
@@ -281,13 +295,16 @@ class YamlReader {
                     if (kv.first == key) fail(cur.no, "duplicate entry with key \"" + key + "\"");
                 at_++;
                 std::unique_ptr<YNode> child;
+                const bool streamed = root && on_item_ && key == stream_key_;
                 if (!value.empty() && value[0] != '#')
                     child = inline_value(value, cur.no);
-                else if (at_ < lines_.size() && lines_[at_].indent > indent)
+                else if (at_ < lines_.size() && lines_[at_].indent > indent) {
+                    streaming_next_seq_ = streamed;
                     child = node(lines_[at_].indent);
-                else if (at_ < lines_.size() && lines_[at_].indent == indent && is_seq_item(lines_[at_].body))
+                } else if (at_ < lines_.size() && lines_[at_].indent == indent && is_seq_item(lines_[at_].body)) {
+                    streaming_next_seq_ = streamed;
                     child = node(indent);
-                else
+                } else
                     child = null_node(cur.no);
                 n->map.emplace_back(key, std::move(child));
             }
@@ -303,8 +320,12 @@ class YamlReader {
     }
 
 public:
-    // the document's root node (a null scalar for an empty document)
-    std::unique_ptr<YNode> parse(std::string_view text) {
+    // The document's root node (a null scalar for an empty document).  With `stream_key` the items of the block sequence
+    // under that key of the root mapping go to `on_item` as they are read and the returned tree holds an empty sequence there.
+    std::unique_ptr<YNode> parse(std::string_view text, const std::string& stream_key = std::string(), std::function<void(const YNode&)> on_item = nullptr) {
+        stream_key_ = stream_key;
+        on_item_ = std::move(on_item);
+        streaming_next_seq_ = false;
         lines_.clear();
         at_ = 0;
         int no = 0;
@@ -340,7 +361,7 @@ public:
             if (pos > text.size()) break;
         }
         if (lines_.empty()) return null_node(1);
-        auto root = node(lines_[0].indent);
+        auto root = node(lines_[0].indent, true);
         if (at_ < lines_.size()) fail(lines_[at_].no, "did not find expected <document end>");
         return root;
     }
