@@ -340,9 +340,14 @@ __device__ __forceinline__ void finish_geom(WindowIndex& W, WinGeom& g, bool fin
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kSWarps = kTileThreads / 32;
 constexpr int kUnits = kTile / 32 + 1;       // 32-byte units of a window (+1: the unit that can hold a virtual final newline)
-constexpr int kRounds = kTile / 1024;        // phase B works in rounds of 32 units = 1 KB (the extra unit of a virtual final
-                                             // newline goes to the last round)
-constexpr int kSegCap = 32 * 2 + 4;           // row starts one round can find (<= 1 per 16 bytes, else malformed)
+#ifndef BLU_ROUND_UNITS
+#define BLU_ROUND_UNITS 32
+#endif
+constexpr int kRoundUnits = BLU_ROUND_UNITS;  // phase B works in rounds of this many 32-byte units per warp (32: 1 KB, 64: 2 KB -- half as
+                                              // many rounds, so half the per-round bookkeeping); the extra unit of a virtual final
+                                              // newline goes to the last round
+constexpr int kRounds = kTile / (32 * kRoundUnits);
+constexpr int kSegCap = kRoundUnits * 2 + 4;  // row starts one round can find (<= 1 per 16 bytes, else malformed)
 constexpr int kSRowCap = kTile / 26 + 8;     // a valid row is >= 26 bytes
 constexpr int kRecFlush = 128;                // buffered record headers that trigger a flush (one global atomic)
 constexpr int kRecBuf = 176;                  // capacity of the record buffer (beyond: the run reserves its record itself)
@@ -357,7 +362,7 @@ constexpr int kCarryTop = 32;                 // top rows of the open query kept
 
 static_assert(kSRowCap < 0x8000, "row indices are 15-bit");
 static_assert(kTile % 32 == 0 && kTile + 128 < 65536, "window offsets are 16-bit");
-static_assert(kTile % 1024 == 0 && kRounds <= 32, "per-round tables are read by one warp");
+static_assert(kRoundUnits % 32 == 0 && kTile % (32 * kRoundUnits) == 0 && kRounds <= 32 && kRounds >= 1, "per-round tables are read by one warp");
 
 enum : uint32_t { RK_EMIT = 1, RK_DEFER = 2, RK_PSEUDO = 4, RK_OPEN = 8, RK_NEWCARRY = 16 };
 
@@ -786,11 +791,11 @@ __device__ __forceinline__ void tile_segment(const RunParams& p, StreamSmem& S, 
         {
             const bool interior = !has_begin && tend == kTile && !virt_nl;
             for (int rd = warp; rd < kRounds; rd += kSWarps) {
-                const int u0 = rd << 5;
+                const int u0 = rd * kRoundUnits;
                 if (interior)
-                    classify_round<true>(S, win, rd, u0, u0 + 32, 0, tend, false, false, lane);
+                    classify_round<true>(S, win, rd, u0, u0 + kRoundUnits, 0, tend, false, false, lane);
                 else {
-                    const int u1 = (rd == kRounds - 1 || u0 + 32 > n_units) ? n_units : u0 + 32;
+                    const int u1 = (rd == kRounds - 1 || u0 + kRoundUnits > n_units) ? n_units : u0 + kRoundUnits;
                     classify_round<false>(S, win, rd, u0, u1 > u0 ? u1 : u0, vb, tend, has_begin, virt_nl, lane);
                 }
             }
