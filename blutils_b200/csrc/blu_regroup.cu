@@ -185,7 +185,7 @@ __global__ void rg_len_kernel(const uint32_t* order, const uint32_t* len, uint32
 // one warp per row of the new order: copies the row and terminates it
 __global__ void rg_copy_kernel(const uint8_t* text, const uint64_t* row_off, const uint32_t* len, const uint32_t* order, const uint64_t* dst, uint32_t n_rows,
                                uint8_t* out) {
-    const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint64_t i = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // (64-bit: 32 threads per row)
     const int lane = threadIdx.x & 31;
     if (i >= n_rows) return;
     const uint32_t r = order[i];
@@ -232,8 +232,8 @@ struct Scratch {
 
 }  // namespace
 
-// 0: done (*d_out = cudaMalloc'ed regrouped text, padded; the caller frees it); 1: not possible here (memory, more than 2^32 - 2
-// rows, a row of 2 GB, two ids with one hash) -- the caller regroups on the host; < 0: a CUDA error (cudaError_t negated).
+// 0: done (*d_out = cudaMalloc'ed regrouped text, padded; the caller frees it); 1: not possible here (memory, 2^31 rows or
+// more, a row of 2 GB, two ids with one hash) -- the caller regroups on the host; < 0: a CUDA error (cudaError_t negated).
 int regroup_device(const uint8_t* d_text, uint64_t n, cudaStream_t s, uint8_t** d_out, uint64_t* out_n, uint64_t* n_rows_out) {
     *d_out = nullptr;
     *out_n = 0;
