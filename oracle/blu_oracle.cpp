@@ -211,6 +211,7 @@ struct Bean {
     std::string ident;
     std::string level_key;  // rank.to_string() + identifier (find_multi_taxa_consensus.rs:153-157)
     std::string bean_key;   // "{rank}__{identifier}" (consensus_result.rs:70-73)
+    uint32_t key_ord = 0;   // order of first appearance of bean_key in the taxonomy map (the tie-break of fold_beans)
 };
 
 struct Lineage {
@@ -483,9 +484,12 @@ static void fold_beans(const std::vector<std::pair<const Lineage*, const Row*>>&
         if (fb.accessions.empty() || fb.accessions.back() != r->acc) fb.accessions.push_back(r->acc);  // extend + dedup
         fb.occurrences++;
     }
+    // Full ties (same occurrences and identifier, different rank) leave the reference in HashMap order: non-deterministic there.
+    // Every implementation of this repository breaks them by the order in which the keys first appear in the taxonomy map.
     std::stable_sort(out.begin(), out.end(), [](const FoldBean& a, const FoldBean& b) {
         if (a.occurrences != b.occurrences) return a.occurrences > b.occurrences;
-        return a.bean->ident < b.bean->ident;
+        if (a.bean->ident != b.bean->ident) return a.bean->ident < b.bean->ident;
+        return a.bean->key_ord < b.bean->key_ord;
     });
 }
 
@@ -778,6 +782,11 @@ void* blu_oracle_create(const int64_t* taxids, const uint64_t* off, const char* 
         for (int t = 1; t < threads; t++) th.emplace_back(work, t);
         work(0);
         for (auto& x : th) x.join();
+        {
+            std::unordered_map<std::string_view, uint32_t> ord;
+            for (auto& L : H->lineages)
+                for (auto& bean : L.beans) bean.key_ord = ord.emplace(bean.bean_key, (uint32_t)ord.size()).first->second;
+        }
         return H.release();
     } catch (const std::exception& e) {
         snprintf(err, errlen, "%s", e.what());

@@ -306,7 +306,21 @@ def parse_blast(text: bytes) -> Dict[str, List[Row]]:
 # Consensus (find_single_query_consensus.rs, find_multi_taxa_consensus.rs,
 # build_blast_consensus_identity.rs, consensus_result.rs:48-88)
 # --------------------------------------------------------------------------------------
-def _fold_beans(beans: List[Tuple[Rank, str, str, str]]) -> List[dict]:
+def bean_key_order(tax: Dict[int, str]) -> Dict[str, int]:
+    """Order of first appearance of every "{rank}__{identifier}" key in the taxonomy map (lineages in map order, levels root to
+    leaf): the tie-break of _fold_beans."""
+    order: Dict[str, int] = {}
+    for s in tax.values():
+        try:
+            L = parse_lineage(s)
+        except DataError:
+            continue
+        for rank, ident in L:
+            order.setdefault(f"{rank_display(rank)}__{ident}", len(order))
+    return order
+
+
+def _fold_beans(beans: List[Tuple[Rank, str, str, str]], key_order: Optional[Dict[str, int]] = None) -> List[dict]:
     """ConsensusBean::fold_consensus_list (consensus_result.rs:65-88) + the sort at
     build_blast_consensus_identity.rs:50-60.  beans: (rank, identifier, taxonomy, accession)."""
     acc: Dict[str, dict] = {}
@@ -322,11 +336,13 @@ def _fold_beans(beans: List[Tuple[Rank, str, str, str]]) -> List[dict]:
                 d.append(x)
         b["accessions"] = d
         b["occurrences"] += 1
-    out = list(acc.values())
-    # full ties (same occurrences and identifier, different rank) are HashMap-order in the
-    # reference = non-deterministic; generators exclude them.  Here: first-seen order.
-    out.sort(key=lambda b: (-b["occurrences"], b["identifier"].encode("utf-8")))
-    return out
+    # Full ties (same occurrences and identifier, different rank) leave the reference in HashMap order: non-deterministic
+    # there.  Every implementation of this repository breaks them the same way: by the order in which the beans' keys first
+    # appear in the taxonomy map (the product's dictionary ids, blu_taxonomy.cpp); without a map, first-seen order.
+    keys = list(acc.keys())
+    out = sorted(range(len(keys)), key=lambda i: (-acc[keys[i]]["occurrences"], acc[keys[i]]["identifier"].encode("utf-8"),
+                                                  key_order.get(keys[i], 1 << 60) if key_order is not None else 0, i))
+    return [acc[keys[i]] for i in out]
 
 
 def _allowed(cut: List[float], identity: float) -> Optional[int]:
@@ -345,7 +361,7 @@ def _allowed_rank(ranks: Sequence[Rank], backbone, j: int) -> Rank:
     return ("O", rank_display(r))
 
 
-def _build(R, cut, backbone, identity, single, idx, beans, ref_row: Row) -> dict:
+def _build(R, cut, backbone, identity, single, idx, beans, ref_row: Row, key_order: Optional[Dict[str, int]] = None) -> dict:
     """build_blast_consensus_identity (build_blast_consensus_identity.rs:9-105)."""
     ranks = [b[0] for b in R]
     bean = R[idx]
@@ -356,7 +372,7 @@ def _build(R, cut, backbone, identity, single, idx, beans, ref_row: Row) -> dict
         ar = _allowed_rank(ranks, backbone, j)
         max_allowed = rank_full(ar)
         mutated = bean[0] != ar  # :35-37
-    folded = _fold_beans(beans)
+    folded = _fold_beans(beans, key_order)
     F = [R[k] for k in range(len(R)) if identity >= cut[k]]  # linnaean_ranks.rs:194-212
     if single and len(folded) == 1:
         A = F
@@ -377,7 +393,7 @@ def _build(R, cut, backbone, identity, single, idx, beans, ref_row: Row) -> dict
 
 
 def consensus_for_query(rows: List[Row], tax: Dict[int, str], backbone, strategy: str,
-                        lineage_cache: Optional[dict] = None) -> dict:
+                        lineage_cache: Optional[dict] = None, key_order: Optional[Dict[str, int]] = None) -> dict:
     """find_single_query_consensus.rs:17-173 -> taxon object (dict in serde field order)."""
     top = max(r.bits for r in rows)  # :28-50, only the first loop iteration is reachable
     G = [r for r in rows if r.bits == top]
@@ -440,9 +456,9 @@ def consensus_for_query(rows: List[Row], tax: Dict[int, str], backbone, strategy
             for _, r in tw:  # fold from 0.0 :182-185
                 if r.pident > mx:
                     mx = r.pident
-            out = _build(R, cut, backbone, mx, False, i - 1, beans, ref_row)
+            out = _build(R, cut, backbone, mx, False, i - 1, beans, ref_row, key_order)
             break
-        out = _build(R, cut, backbone, ref_row.pident, True, i, beans, ref_row)
+        out = _build(R, cut, backbone, ref_row.pident, True, i, beans, ref_row, key_order)
     assert out is not None
     return out
 
@@ -454,9 +470,10 @@ def build_consensus_identities(text: bytes, tax: Dict[int, str], taxon: str, str
     backbone = backbone_for(taxon, custom)
     groups = parse_blast(text)
     cache: dict = {}
+    key_order = bean_key_order(tax)
     res = []
     for q, rows in groups.items():
-        res.append({"query": q, "taxon": consensus_for_query(rows, tax, backbone, strategy, cache)})
+        res.append({"query": q, "taxon": consensus_for_query(rows, tax, backbone, strategy, cache, key_order)})
     if headers:
         for h in headers:  # mod.rs:91-100
             if h not in groups:

@@ -1,5 +1,6 @@
 """Round-2 GPU parity tests: device-resident results, text references, the block-parallel long-tail consensus,
 top groups of every size class, consensus-class errors on reused contexts and on scattered tables."""
+import json
 import random
 
 import pytest
@@ -311,3 +312,29 @@ def test_scattered_table_device_resident():
     out2.close()
     eng2.close()
     eng.close()
+
+
+@pytest.mark.parametrize("group", [2, 7, 20, 40])
+def test_fully_tied_beans(group):
+    """Two beans with the same identifier and the same number of occurrences under different rank names tie completely in
+    the reference's bean sort (build_blast_consensus_identity.rs:50-60), which leaves them in HashMap order.  Every
+    implementation here breaks the tie by the order in which the beans' keys first appear in the taxonomy map -- in the
+    8-lane, the 32-lane and the block-parallel consensus alike, and whichever way round the map lists them."""
+    lineages = {1: "d__bac;clade__x0;k__k0;p__p1", 2: "d__bac;species group__x0;k__k0;p__p2", 3: "d__bac;no rank__x0;k__k1", 4: "d__bac;k__k0"}
+    rows = []
+    for q in range(50):
+        for h in range(group):
+            rows.append(_row(f"q{q:03d}", f"A{q}_{h}.1", 1 + (h + q) % 3, "91.5", 300, "700"))
+        rows.append(_row(f"q{q:03d}", f"L{q}.1", 4, "80.0", 300, "100"))
+    text = "".join(rows).encode()
+    for order in ([1, 2, 3, 4], [3, 2, 1, 4], [2, 4, 3, 1]):
+        ids = order
+        lin = [lineages[i] for i in order]
+        for strategy in ("cautious", "relaxed"):
+            want = _oracle(ids, lin, "bacteria", strategy).run_raw(text)[0]
+            eng = _engine("bacteria", strategy)
+            eng.load_taxonomy_arrays(ids, lin)
+            assert eng.run_host(text).jsonl() == want, (order, strategy)
+            eng.close()
+    first = [json.loads(l)["taxon"]["consensusBeans"][0]["rank"] for l in want.decode().splitlines()[:1]]
+    assert first  # (the beans really are listed)

@@ -1,0 +1,218 @@
+"""Property tests (hypothesis) over generated lineage maps and hit groups, on the CPU:
+
+* three implementations of the path agree byte for byte on the canonical JSONL -- and on WHICH inputs are data errors:
+  oracle/pyoracle.py, oracle/blu_oracle.cpp and the product's device core compiled for the host (tests/csrc/sim_harness.cpp:
+  the same parse / top-group / consensus / cutoff functions the CUDA kernels call);
+* metamorphic properties the domain offers (build_consensus_identities/mod.rs:104-128 is an order-free per-query map, and only the
+  top bit-score group of a query is ever looked at, find_single_query_consensus.rs:17-173):
+    - the result of a query depends on its own rows only: queries can be reordered, tables can be cut at query boundaries and the
+      pieces' results concatenated;
+    - rows below the query's top bit score can be dropped, duplicated, permuted or given any mapped / unmapped taxid;
+    - a consensus taxonomy consists of levels of one of the top group's lineages, in order, from the root, cut in front of the first level -- among those every top lineage has -- at which two top rows
+      name different taxa, and a single-row top group is a single match.
+"""
+import json
+
+import pytest
+from hypothesis import HealthCheck, given, settings
+from hypothesis import strategies as st
+
+import pyoracle as po
+import sim_ffi
+from oracle_ffi import Oracle, OracleDataError
+
+RANKS = ["d", "k", "p", "c", "o", "f", "g", "s"]
+EXTRA = ["clade", "species group", "strain", "no rank", "subspecies"]
+
+
+@st.composite
+def lineage_maps(draw):
+    """A small tree: every lineage shares the domain (the reference aborts on root disagreement), ranks in Linnaean order with
+    optional non-Linnaean levels spliced in, identifiers from a tiny alphabet so that lineages share prefixes."""
+    n = draw(st.integers(2, 9))
+    lineages = []
+    for _ in range(n):
+        depth = draw(st.integers(2, len(RANKS)))
+        parts = ["d__bac"]
+        for r in RANKS[1:depth]:
+            if draw(st.integers(0, 9)) == 0:
+                # (the same identifier under two rank names at one level: two beans that tie completely -- the reference's order is
+                # its HashMap's there; the implementations of this repository agree on the taxonomy map's order)
+                parts.append(draw(st.sampled_from(EXTRA)) + "__x" + str(draw(st.integers(0, 2))))
+            parts.append(r + "__" + r + str(draw(st.integers(0, 2))))
+        if draw(st.integers(0, 5)) == 0:
+            parts.append("strain__st" + str(draw(st.integers(0, 3))))
+        lineages.append(";".join(parts))
+    taxids = draw(st.lists(st.integers(1, 10_000), min_size=n, max_size=n, unique=True))
+    return dict(zip(taxids, lineages))
+
+
+def _pident(draw):
+    whole = draw(st.integers(40, 100))
+    if whole == 100 or draw(st.booleans()):
+        return f"{whole}.000" if draw(st.booleans()) else str(whole)
+    return f"{whole}.{draw(st.integers(0, 999)):03d}"
+
+
+@st.composite
+def tables(draw, tax):
+    """queries: list of (id, rows); a row = (acc, taxid, pident, length, bitscore text).  Bit scores come from a few levels so
+    that top groups of several rows are common; one in ten is written with a decimal fraction (truncated by the reference)."""
+    ids = sorted(tax)
+    n_q = draw(st.integers(1, 6))
+    queries = []
+    for q in range(n_q):
+        rows = []
+        for h in range(draw(st.integers(1, 9))):
+            level = draw(st.integers(0, 3))
+            bits = 900 - 50 * level
+            bits_txt = f"{bits}.{draw(st.integers(0, 9))}" if draw(st.integers(0, 9)) == 0 else str(bits)
+            rows.append((f"AC{q}_{h}.{draw(st.integers(1, 3))}", draw(st.sampled_from(ids)), _pident(draw), draw(st.integers(50, 1500)), bits_txt))
+        queries.append((f"q{q:02d}_{draw(st.integers(0, 99))}", rows))
+    # distinct query ids (a repeated id would merge two groups: legal, but not what these properties talk about)
+    seen = set()
+    out = []
+    for qid, rows in queries:
+        while qid in seen:
+            qid += "x"
+        seen.add(qid)
+        out.append((qid, rows))
+    return out
+
+
+def _text(queries) -> bytes:
+    return "".join(f"{qid}\t{acc}\t{taxid}\t{pid}\t{ln}\t0\t0\t1\t{ln}\t1\t{ln}\t1e-50\t{bits}\n" for qid, rows in queries for acc, taxid, pid, ln, bits in rows).encode()
+
+
+def _three_ways(tax, text, taxon, strategy):
+    """canonical JSONL (bytes) or None when the reference would abort; asserts that the three implementations agree"""
+    ids = list(tax)
+    lin = [tax[i] for i in ids]
+    try:
+        a = po.results_to_jsonl(po.build_consensus_identities(text, tax, taxon, strategy, None)).encode()
+    except po.DataError:
+        a = None
+    try:
+        b = Oracle(ids, lin, taxon, strategy, None, threads=2).run_raw(text)[0]
+    except OracleDataError:
+        b = None
+    rc, c, _ = sim_ffi.run(ids, lin, taxon, strategy, text)
+    assert (a is None) == (b is None) == (rc != 0), (a is None, b is None, rc)
+    if a is not None:
+        assert a == b
+        assert a == c
+    return a
+
+
+def _by_query(jsonl: bytes):
+    return {json.loads(line)["query"]: line for line in jsonl.decode().splitlines()}
+
+
+COMMON = dict(max_examples=int(__import__("os").environ.get("BLU_HYP_EXAMPLES", "120")), deadline=None, suppress_health_check=[HealthCheck.too_slow, HealthCheck.data_too_large])
+
+
+@settings(**COMMON)
+@given(st.data())
+def test_three_implementations_agree(data):
+    tax = data.draw(lineage_maps())
+    queries = data.draw(tables(tax))
+    taxon = data.draw(st.sampled_from(["bacteria", "fungi", "eukaryotes"]))
+    strategy = data.draw(st.sampled_from(["cautious", "relaxed"]))
+    _three_ways(tax, _text(queries), taxon, strategy)
+
+
+@settings(**COMMON)
+@given(st.data())
+def test_a_query_depends_on_its_own_rows_only(data):
+    tax = data.draw(lineage_maps())
+    queries = data.draw(tables(tax))
+    strategy = data.draw(st.sampled_from(["cautious", "relaxed"]))
+    whole = _three_ways(tax, _text(queries), "bacteria", strategy)
+    if whole is None:
+        return
+    whole_q = _by_query(whole)
+    # any order of the queries; any cut at a query boundary, results concatenated (shard invariance)
+    perm = data.draw(st.permutations(queries))
+    assert _by_query(_three_ways(tax, _text(perm), "bacteria", strategy)) == whole_q
+    cut = data.draw(st.integers(0, len(queries)))
+    pieces = {}
+    for part in (queries[:cut], queries[cut:]):
+        if part:
+            pieces.update(_by_query(_three_ways(tax, _text(part), "bacteria", strategy)))
+    assert pieces == whole_q
+
+
+@settings(**COMMON)
+@given(st.data())
+def test_only_the_top_bit_score_group_matters(data):
+    tax = data.draw(lineage_maps())
+    queries = data.draw(tables(tax))
+    strategy = data.draw(st.sampled_from(["cautious", "relaxed"]))
+    whole = _three_ways(tax, _text(queries), "bacteria", strategy)
+    if whole is None:
+        return
+    changed = []
+    for qid, rows in queries:
+        top = max(int(float(r[4])) for r in rows)  # (the reference compares the TRUNCATED bit score, mod.rs:162,184)
+        keep, low = [r for r in rows if int(float(r[4])) == top], [r for r in rows if int(float(r[4])) != top]
+        mode = data.draw(st.sampled_from(["drop", "double", "permute", "unmapped"]))
+        if mode == "drop":
+            low = []
+        elif mode == "double":
+            low = low + low
+        elif mode == "permute":
+            low = list(data.draw(st.permutations(low)))
+        else:
+            low = [(a, 999_999, p, ln, b) for a, _t, p, ln, b in low]  # not in the map: only top-group rows are ever joined
+        # rows below the top score may sit anywhere among the top rows, whose own order stays
+        merged, ki, li = [], 0, 0
+        while ki < len(keep) or li < len(low):
+            take_low = li < len(low) and (ki >= len(keep) or data.draw(st.booleans()))
+            if take_low:
+                merged.append(low[li]); li += 1
+            else:
+                merged.append(keep[ki]); ki += 1
+        changed.append((qid, merged))
+    assert _by_query(_three_ways(tax, _text(changed), "bacteria", strategy)) == _by_query(whole)
+
+
+@settings(**COMMON)
+@given(st.data())
+def test_shape_of_a_consensus(data):
+    tax = data.draw(lineage_maps())
+    queries = data.draw(tables(tax))
+    strategy = data.draw(st.sampled_from(["cautious", "relaxed"]))
+    out = _three_ways(tax, _text(queries), "bacteria", strategy)
+    if out is None:
+        return
+    res = {json.loads(line)["query"]: json.loads(line) for line in out.decode().splitlines()}
+    assert sorted(res) == sorted(q for q, _ in queries)
+    for qid, rows in queries:
+        t = res[qid]["taxon"]
+        assert t is not None
+        top = max(int(float(r[4])) for r in rows)
+        group = [r for r in rows if int(float(r[4])) == top]
+        assert t["bitScore"] == float(top)
+        assert t["singleMatch"] == (len(group) == 1)
+        lineages = [tax[r[1]].replace("species group", "species-group").replace("no rank", "no-rank").split(";") for r in group]  # (ranks are slugified)
+        if t["taxonomy"] != "":  # ("" when the identity is below every cutoff: nothing of the lineage is kept)
+            got = t["taxonomy"].split(";")
+            # the levels of one of the top group's lineages, in order, that pass the identity filter (linnaean_ranks.rs:194-212
+            # filters level by level: a level can be dropped between two kept ones when a rank name occurs twice in a lineage)
+            def subsequence(a, l):
+                it = iter(l)
+                return all(x in it for x in a)
+            assert any(subsequence(got, l) and got[0] == l[0] for l in lineages), (got, lineages)
+        got = t["taxonomy"].split(";") if t["taxonomy"] else []
+        if len(group) > 1:
+            # Levels are compared only as deep as the SHORTEST top lineage reaches (find_multi_taxa_consensus.rs:137-214: a
+            # take_while over the length-ascending list ends at the first lineage that has ended).  A disagreement inside that
+            # range bounds the consensus; without one the reference lineage is kept as far as the identity allows.
+            shortest = min(len(l) for l in lineages)
+            i0 = next((i for i in range(shortest) if len({l[i] for l in lineages}) > 1), None)
+            if i0 is not None:
+                assert len(got) <= i0, (got, lineages)
+            beans = t["consensusBeans"]
+            assert beans is not None and sum(b["occurrences"] for b in beans) <= len(group)
+            keys = [(-b["occurrences"], b["identifier"]) for b in beans]
+            assert keys == sorted(keys)  # folded beans: occurrences descending, then identifier (consensus_result.rs:60-89)
