@@ -270,3 +270,30 @@ def test_the_input_grammar_three_ways(data):
     tax = {7: "d__bac;p__p1;c__c1", 12: "d__bac;p__p1;c__c2", 1500: "d__bac;p__p2"}
     text = data.draw(grammar_rows(sorted(tax)))
     _three_ways(tax, text, "bacteria", data.draw(st.sampled_from(["cautious", "relaxed"])), loud_limits=True)
+
+
+# ---- a9: the cutoff interpolation, the only floating-point arithmetic of the path -----------------------------------------------
+RANK_NAMES = ["d", "domain", "k", "kingdom", "p", "c", "class", "o", "order", "f", "g", "genus", "s", "species", "u", "clade", "species group", "species-group",
+              "strain", "no rank", "subspecies", "Subspecies", "superkingdom", "Forma  specialis", "serotype", " genus ", "GENUS", "x"]
+
+
+@settings(**COMMON)
+@given(st.lists(st.sampled_from(RANK_NAMES), min_size=1, max_size=24), st.sampled_from(["bacteria", "fungi", "eukaryotes", "custom"]),
+       st.lists(st.one_of(st.none(), st.integers(0, 100)), min_size=6, max_size=6), st.integers(0, 100), st.integers(0, 100))
+def test_cutoff_interpolation_matches_the_oracle(names, taxon, optional6, dom, spe):
+    """Rank vectors of any shape -- repeated names, ranks out of order, non-Linnaean names first / last / in runs, the NaN and
+    infinity cases of a zero-width window -- through the product's interpolate_cutoffs (host, f64), the C++ oracle and the Python
+    restatement of InterpolatedIdentity::interpolate_identities (linnaean_ranks.rs:220-383): bit-identical f64 values."""
+    import math
+
+    custom = None
+    if taxon == "custom":  # domain and species are required (taxon.rs:14-65), the six between them optional
+        keys = ["kingdom", "phylum", "class", "order", "family", "genus"]
+        custom = dict({"domain": dom, "species": spe}, **dict(zip(keys, optional6)))
+    want = po.interpolate([po.rank_from_str(n) for n in names], po.backbone_for(taxon, custom))
+    from oracle_ffi import interpolate as cpp_oracle_interpolate
+
+    for got in (sim_ffi.interpolate(names, taxon, custom), cpp_oracle_interpolate(names, taxon, custom)):
+        assert len(got) == len(want)
+        for g, w in zip(got, want):
+            assert (math.isnan(g) and math.isnan(w)) or (g == w and math.copysign(1.0, g) == math.copysign(1.0, w)), (names, taxon, custom, got, want)
