@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <functional>
 #include <unordered_set>
 #include <vector>
 
@@ -23,9 +24,10 @@ static int map_err(uint32_t e) {
     return BLU_ERR_DATA;
 }
 
-extern "C" int blu_sim_run(const int64_t* taxids, const uint64_t* off, const char* blob, uint64_t n, int taxon, int has_custom,
-                           const int32_t* custom8, int strategy, const char* text, uint64_t nbytes, const char* headers_nl, uint64_t headers_len,
-                           char** out, uint64_t* out_len, char* err, int errlen) {
+// The path on the host (device core + host taxonomy build), the finished result handed to `emit`.
+static int sim_run_impl(const int64_t* taxids, const uint64_t* off, const char* blob, uint64_t n, int taxon, int has_custom, const int32_t* custom8,
+                        int strategy, const char* text, uint64_t nbytes, const char* headers_nl, uint64_t headers_len,
+                        const std::function<void(const ResultView&)>& emit, char* err, int errlen) {
     try {
         Cutoffs cut;
         cut.taxon = taxon;
@@ -222,11 +224,7 @@ extern "C" int blu_sim_run(const int64_t* taxids, const uint64_t* off, const cha
         part.n_rec = recs.size();
         v.parts.push_back(part);
         v.hitless_ = &hitless;
-        std::string js = view_to_jsonl(&v);
-        *out = (char*)malloc(js.size() + 1);
-        memcpy(*out, js.data(), js.size());
-        (*out)[js.size()] = 0;
-        *out_len = js.size();
+        emit(v);
         return BLU_OK;
     } catch (const DataErr& e) {
         snprintf(err, errlen, "%s", e.what());
@@ -238,6 +236,36 @@ extern "C" int blu_sim_run(const int64_t* taxids, const uint64_t* off, const cha
         snprintf(err, errlen, "%s", e.what());
         return BLU_ERR_INTERNAL;
     }
+}
+
+extern "C" int blu_sim_run(const int64_t* taxids, const uint64_t* off, const char* blob, uint64_t n, int taxon, int has_custom,
+                           const int32_t* custom8, int strategy, const char* text, uint64_t nbytes, const char* headers_nl, uint64_t headers_len,
+                           char** out, uint64_t* out_len, char* err, int errlen) {
+    return sim_run_impl(taxids, off, blob, n, taxon, has_custom, custom8, strategy, text, nbytes, headers_nl, headers_len,
+                        [&](const ResultView& v) {
+                            std::string js = view_to_jsonl(&v);
+                            *out = (char*)malloc(js.size() + 1);
+                            memcpy(*out, js.data(), js.size());
+                            (*out)[js.size()] = 0;
+                            *out_len = js.size();
+                        },
+                        err, errlen);
+}
+
+// Same, the result written by the product's writers (blu_decode.h): format 0 / 1 / 2 = JSON / JSONL / YAML (write_blutils_output.rs),
+// 3 = the build-tabular TSV; path NULL = stdout.
+extern "C" int blu_sim_run_write(const int64_t* taxids, const uint64_t* off, const char* blob, uint64_t n, int taxon, int has_custom,
+                                 const int32_t* custom8, int strategy, const char* text, uint64_t nbytes, const char* out_path, int format,
+                                 const char* run_id, char* err, int errlen) {
+    int wrc = 0;
+    const int rc = sim_run_impl(taxids, off, blob, n, taxon, has_custom, custom8, strategy, text, nbytes, nullptr, 0,
+                                [&](const ResultView& v) { wrc = format == 3 ? view_write_tabular(&v, out_path, run_id) : view_write(&v, out_path, format, run_id); },
+                                err, errlen);
+    if (rc == BLU_OK && wrc != 0) {
+        snprintf(err, errlen, "writer failed (%d)", wrc);
+        return wrc;
+    }
+    return rc;
 }
 
 extern "C" void blu_sim_free(char* p) { free(p); }

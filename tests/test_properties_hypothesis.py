@@ -297,3 +297,45 @@ def test_cutoff_interpolation_matches_the_oracle(names, taxon, optional6, dom, s
         assert len(got) == len(want)
         for g, w in zip(got, want):
             assert (math.isnan(g) and math.isnan(w)) or (g == w and math.copysign(1.0, g) == math.copysign(1.0, w)), (names, taxon, custom, got, want)
+
+
+# ---- the writers: JSON / JSONL / YAML / TSV bytes of tables whose strings need escaping ------------------------------------------
+ODD = st.text(alphabet=st.sampled_from(list("abZ09 _-.;:#'\"\\/|&*!%@`?[]{},>~=") + ["é", "ß", "漢", "\U0001d518", " ", " ", "﻿", "\x7f", "\x01", "\x1b"]),
+              min_size=1, max_size=10)
+LOOKS_LIKE = st.sampled_from(["null", "~", "true", "False", "yes", "NO", "on", "0x1F", "0o17", "1e3", "-.inf", ".NaN", "007", "12", "-3", "+4", "1.5", "- x", "a: b", "x #y",
+                              " lead", "trail ", "---", "...", "? k", ": v", "[a]", "{b}", "&a", "*a", "!t", "|", ">", "%", "@", "`"])
+
+
+@settings(**COMMON)
+@given(st.data())
+def test_the_writers_escape_like_the_oracle(tmp_path_factory, data):
+    """Query ids and accessions made of quotes, backslashes, control characters, non-ASCII and astral characters, YAML indicators and
+    things that read as null / booleans / numbers: the product's pretty JSON, JSONL, YAML (serde_yaml 0.9 quoting) and build-tabular
+    TSV writers against the oracle's, byte for byte, on a table that goes through the whole host-compiled path."""
+    tax = {7: "d__bac;p__p1;c__c1", 12: "d__bac;p__p1;c__c2"}
+    ids = list(tax)
+    lin = [tax[i] for i in ids]
+    word = st.one_of(ODD, LOOKS_LIKE).filter(lambda w: "\t" not in w and "\n" not in w and "\r" not in w and '"' not in w)
+    n_q = data.draw(st.integers(1, 4))
+    qids = data.draw(st.lists(word, min_size=n_q, max_size=n_q, unique=True))
+    rows = []
+    for q in qids:
+        for h in range(data.draw(st.integers(1, 3))):
+            rows.append(f"{q}\t{data.draw(word)}\t{data.draw(st.sampled_from(ids))}\t{data.draw(st.sampled_from(['97.5', '100', '88.125']))}\t300\t0\t0\t1\t300\t1\t300\t1e-50\t640\n")
+    text = "".join(rows).encode("utf-8")
+    try:
+        res = po.build_consensus_identities(text, tax, "bacteria", "relaxed", None)
+    except po.DataError:
+        return  # (e.g. an id that is only blanks: the grammar property covers agreement on rejections)
+    run_id = "0b0e3c55-7a2f-4a61-9d4e-5f1c2a7b8c9d"
+    doc = {"results": [dict([("runId", run_id)] + list(r.items())) for r in res], "config": None}
+    want = {"json": po.to_json_pretty(doc), "jsonl": "null\n" + po.results_to_jsonl(res, run_id),  # (the config line, write_blutils_output.rs:165-175)
+            "yaml": po.results_to_yaml(res, run_id),
+            "tsv": po.results_to_tabular(res, run_id, to_stdout=False)}
+    d = tmp_path_factory.mktemp("w")
+    for fmt, expected in want.items():
+        path = str(d / ("out." + ("tsv" if fmt == "tsv" else fmt)))
+        rc = sim_ffi.run_write(ids, lin, "bacteria", "relaxed", text, path, fmt, run_id)
+        assert rc == 0, (fmt, rc)
+        got = open(path, "rb").read().decode("utf-8")
+        assert got == expected, (fmt, qids)
