@@ -371,3 +371,43 @@ def test_yaml_input_errors_and_refusals(tmp_path):
         src.write_text(text)
         with pytest.raises(Unsupported):
             _tab(str(src), str(tmp_path / "e.tsv"), "yaml")
+
+
+def test_yaml_input_property(tmp_path_factory):
+    """hypothesis: any strings (YAML indicators, quotes, escapes, non-ASCII, astral, control characters, number / boolean / null
+    look-alikes) through the writer's quoting rules and back through the reader: the TSV is the one computed from the objects."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    odd = st.text(alphabet=st.sampled_from(list("abZ09 _-.;:#'\"\\/|&*!%@`?[]{},>~=\t") + ["é", "漢", "\U0001d518", " ", " ", "﻿", "\x7f", "\x01", "\x1b", "\n"]),
+                  min_size=0, max_size=12)
+    looks = st.sampled_from(["null", "~", "true", "False", "yes", "0x1F", "0o17", "1e3", "-.inf", ".NaN", "007", "12", "-3", "+4", "1.5", "- x", "a: b", "x #y",
+                             " lead", "trail ", "---", "...", "? k", ": v", "[a]", "{b}", "&a", "*a", "!t", "|", ">", "%", "@", "`", ""])
+    word = st.one_of(odd, looks)
+    d = tmp_path_factory.mktemp("y")
+    (d / "p.json").write_text("{}")
+
+    @settings(max_examples=int(os.environ.get("BLU_HYP_EXAMPLES", "150")), deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.data())
+    def run(data):
+        results = []
+        for _ in range(data.draw(st.integers(1, 3))):
+            if data.draw(st.integers(0, 4)) == 0:
+                results.append({"query": data.draw(word), "taxon": None})
+                continue
+            beans = None
+            if data.draw(st.booleans()):
+                beans = [{"rank": data.draw(word), "identifier": data.draw(word), "occurrences": data.draw(st.integers(0, 2 ** 31 - 1)),
+                          "taxonomy": data.draw(st.one_of(st.none(), word)), "accessions": data.draw(st.lists(word, max_size=3))}
+                         for _ in range(data.draw(st.integers(0, 3)))]
+            results.append({"query": data.draw(word), "taxon": {
+                "reachedRank": data.draw(word), "maxAllowedRank": data.draw(st.one_of(st.none(), word)), "identifier": data.draw(word),
+                "percIdentity": data.draw(st.floats(0, 100, allow_nan=False)), "bitScore": data.draw(st.floats(0, 1e12, allow_nan=False)),
+                "taxonomy": data.draw(st.one_of(st.none(), word)), "mutated": data.draw(st.booleans()), "singleMatch": data.draw(st.booleans()),
+                "consensusBeans": beans}})
+        src = d / "p.yaml"
+        src.write_text(_yaml_doc(results, seq_indent=data.draw(st.sampled_from([0, 2]))), encoding="utf-8")
+        _tab(str(src), str(d / "p.tsv"), "yaml")
+        assert (d / "p.tsv").read_text(encoding="utf-8") == po.results_to_tabular(results, RUN_ID, to_stdout=False)
+
+    run()
