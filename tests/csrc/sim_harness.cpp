@@ -336,6 +336,31 @@ extern "C" long long blu_sim_read_taxonomy_json(const char* path, int use_taxid,
     }
 }
 
+// What the product's reader took from a `.blutils.json`: "taxid\0lineage\0" for every taxon, in file order (malloc'ed; the
+// lineage is the text or the numeric one, as build_consensus_identities/mod.rs:287-291 chooses by use_taxid).
+extern "C" int blu_sim_dump_taxonomy_json(const char* path, int use_taxid, char** out, uint64_t* out_len, char* err, int errlen) {
+    try {
+        std::vector<int64_t> ids;
+        std::vector<uint64_t> off;
+        std::string blob;
+        read_taxonomy_json(path, use_taxid != 0, ids, off, blob);
+        std::string o;
+        for (size_t i = 0; i < ids.size(); i++) {
+            o += std::to_string(ids[i]);
+            o.push_back('\0');
+            o.append(blob, off[i], off[i + 1] - off[i]);
+            o.push_back('\0');
+        }
+        *out = (char*)malloc(o.size() + 1);
+        memcpy(*out, o.data(), o.size());
+        *out_len = o.size();
+        return 0;
+    } catch (const std::exception& e) {
+        snprintf(err, errlen, "%s", e.what());
+        return 1;
+    }
+}
+
 // Side-car taxonomy cache of the product (same sequence as blu_taxonomy_load_json_cached, minus the upload):
 // *state = 1 loaded from the cache, 0 built + written, -1 built, not writable.  *checksum covers every field of the
 // resulting HostTaxonomy, so "loaded" and "built" can be compared.

@@ -106,6 +106,23 @@ def interpolate(ranks: Sequence[str], taxon: str, custom=None) -> List[float]:
     return [out[i] for i in range(n)]
 
 
+def dump_taxonomy_json(path: str, use_taxid: bool = False):
+    """[(taxid, lineage)] as the product's `.blutils.json` reader sees the file; IOError with its message when it rejects it."""
+    out, ol = C.c_void_p(), C.c_uint64()
+    err = C.create_string_buffer(512)
+    f = lib().blu_sim_dump_taxonomy_json
+    f.restype = C.c_int
+    f.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.c_char_p, C.c_int]
+    if f(path.encode(), 1 if use_taxid else 0, C.byref(out), C.byref(ol), err, 512) != 0:
+        raise IOError(err.value.decode(errors="replace"))
+    try:
+        raw = C.string_at(out, ol.value)
+    finally:
+        lib().blu_sim_free(out)
+    parts = raw.split(b"\0")[:-1]
+    return [(int(parts[i]), parts[i + 1].decode("utf-8")) for i in range(0, len(parts), 2)]
+
+
 def custom_cutoffs(path: str):
     out = (C.c_int32 * 8)()
     err = C.create_string_buffer(512)

@@ -339,3 +339,62 @@ def test_the_writers_escape_like_the_oracle(tmp_path_factory, data):
         assert rc == 0, (fmt, rc)
         got = open(path, "rb").read().decode("utf-8")
         assert got == expected, (fmt, qids)
+
+
+# ---- a3: the `.blutils.json` reader (hand-written pull parser) against Python's json ---------------------------------------------
+JSON_TEXT = st.text(alphabet=st.one_of(st.sampled_from(list("ab;_ -\"\\/\b\f\n\r\t{}[]:,") + ["é", "漢", "\U0001d518", "\x00", "\x1f", "\x7f", "퟿", "", "￿"]),
+                                       st.characters(blacklist_categories=("Cs",))), max_size=12)
+JUNK = st.recursive(st.one_of(st.none(), st.booleans(), st.integers(-10 ** 20, 10 ** 20), st.floats(allow_nan=False, allow_infinity=False), JSON_TEXT),
+                    lambda c: st.one_of(st.lists(c, max_size=3), st.dictionaries(JSON_TEXT, c, max_size=3)), max_leaves=8)
+
+
+@settings(**COMMON)
+@given(st.data())
+def test_taxonomy_json_reader_matches_python_json(tmp_path_factory, data):
+    """Schema-conforming `.blutils.json` documents (taxonomies_map.rs:6-32) with arbitrary strings -- every escape json.dumps can
+    produce, raw UTF-8, astral characters, control characters --, unknown fields holding arbitrary JSON at every level, keys in
+    any order, any whitespace: the product's reader (blu_taxonomy.cpp, the parser the GPU path's taxonomy comes through) yields
+    the (taxid, lineage) pairs Python's json module reads from the same bytes."""
+    import random as _random
+
+    rnd = _random.Random(data.draw(st.integers(0, 2 ** 32)))
+
+    def shuffled(d):
+        items = list(d.items())
+        rnd.shuffle(items)
+        return dict(items)
+
+    taxa = []
+    for _ in range(data.draw(st.integers(0, 5))):
+        t = {"taxid": data.draw(st.integers(0, 2 ** 53)), "rank": data.draw(JSON_TEXT), "numericLineage": data.draw(JSON_TEXT), "textLineage": data.draw(JSON_TEXT),
+             "accessions": [shuffled(dict({"accession": data.draw(JSON_TEXT), "oid": data.draw(JSON_TEXT)}, **data.draw(st.dictionaries(st.sampled_from(["x", "y"]), JUNK, max_size=1))))
+                            for _ in range(data.draw(st.integers(0, 2)))]}
+        if data.draw(st.booleans()):
+            t["futureField"] = data.draw(JUNK)
+        taxa.append(shuffled(t))
+    doc = {"blutilsVersion": data.draw(JSON_TEXT), "ignoreTaxids": data.draw(st.one_of(st.none(), st.lists(st.integers(0, 2 ** 40), max_size=3))),
+           "replaceRank": data.draw(st.one_of(st.none(), st.dictionaries(JSON_TEXT, JSON_TEXT, max_size=2))), "dropNonLinnaeanTaxonomies": data.draw(st.one_of(st.none(), st.booleans())),
+           "sourceDatabase": data.draw(JSON_TEXT), "taxonomies": taxa}
+    if data.draw(st.booleans()):
+        doc["somethingNew"] = data.draw(JUNK)
+    doc = shuffled(doc)
+    text = json.dumps(doc, ensure_ascii=data.draw(st.booleans()), indent=data.draw(st.sampled_from([None, 0, 2])),
+                      separators=data.draw(st.sampled_from([None, (",", ":"), (" , ", " : ")])))
+    path = str(tmp_path_factory.mktemp("j") / "t.blutils.json")
+    with open(path, "w", encoding="utf-8") as fh:
+        fh.write(text)
+    back = json.loads(text)
+    for use_taxid in (False, True):
+        want = [(t["taxid"], t["numericLineage" if use_taxid else "textLineage"]) for t in back["taxonomies"]]
+        if any("\x00" in lin for _, lin in want):
+            continue  # (the harness hands strings over NUL-separated)
+        assert sim_ffi.dump_taxonomy_json(path, use_taxid) == want
+    # a required field missing anywhere is an error, as it is for serde (mod.rs:261: from_str::<TaxonomiesMap>)
+    if taxa:
+        victim = data.draw(st.sampled_from(["taxid", "rank", "numericLineage", "textLineage", "accessions"]))
+        broken = json.loads(text)
+        del broken["taxonomies"][data.draw(st.integers(0, len(taxa) - 1))][victim]
+        with open(path, "w", encoding="utf-8") as fh:
+            json.dump(broken, fh)
+        with pytest.raises(IOError):
+            sim_ffi.dump_taxonomy_json(path)
