@@ -411,3 +411,65 @@ def test_yaml_input_property(tmp_path_factory):
         assert (d / "p.tsv").read_text(encoding="utf-8") == po.results_to_tabular(results, RUN_ID, to_stdout=False)
 
     run()
+
+
+def test_json_input_property(tmp_path_factory):
+    """hypothesis: result documents with any strings (every escape json.dumps produces, raw UTF-8, astral and control characters),
+    unknown fields holding arbitrary JSON, keys in any order, JSON and JSONL framing: the TSV is the one computed from the objects."""
+    import random as _random
+
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    text_s = st.text(alphabet=st.one_of(st.sampled_from(list("ab;_ -\"\\/\b\f\n\r\t{}[]:,") + ["é", "漢", "\U0001d518", "\x00", "\x1f", "\x7f", "퟿", "￿"]),
+                                        st.characters(blacklist_categories=("Cs",))), max_size=10)
+    junk = st.recursive(st.one_of(st.none(), st.booleans(), st.integers(-10 ** 20, 10 ** 20), st.floats(allow_nan=False, allow_infinity=False), text_s),
+                        lambda c: st.one_of(st.lists(c, max_size=3), st.dictionaries(text_s, c, max_size=3)), max_leaves=6)
+    d = tmp_path_factory.mktemp("jp")
+
+    @settings(max_examples=int(os.environ.get("BLU_HYP_EXAMPLES", "150")), deadline=None, suppress_health_check=list(HealthCheck))
+    @given(st.data())
+    def run(data):
+        rnd = _random.Random(data.draw(st.integers(0, 2 ** 32)))
+
+        def shuffled(x, extra=True):
+            items = list(x.items())
+            if extra and rnd.random() < 0.3:
+                items.append(("zzUnknown", data.draw(junk)))
+            rnd.shuffle(items)
+            return dict(items)
+
+        results = []
+        for _ in range(data.draw(st.integers(0, 3))):
+            if data.draw(st.integers(0, 4)) == 0:
+                results.append({"query": data.draw(text_s), "taxon": None})
+                continue
+            beans = None
+            if data.draw(st.booleans()):
+                beans = [{"rank": data.draw(text_s), "identifier": data.draw(text_s), "occurrences": data.draw(st.integers(-2 ** 31, 2 ** 31 - 1)),
+                          "taxonomy": data.draw(st.one_of(st.none(), text_s)), "accessions": data.draw(st.lists(text_s, max_size=3))}
+                         for _ in range(data.draw(st.integers(0, 3)))]
+            results.append({"query": data.draw(text_s), "taxon": {
+                "reachedRank": data.draw(text_s), "maxAllowedRank": data.draw(st.one_of(st.none(), text_s)), "identifier": data.draw(text_s),
+                "percIdentity": data.draw(st.floats(0, 100, allow_nan=False)), "bitScore": data.draw(st.one_of(st.floats(0, 1e15, allow_nan=False), st.integers(0, 10 ** 6))),
+                "taxonomy": data.draw(st.one_of(st.none(), text_s)), "mutated": data.draw(st.booleans()), "singleMatch": data.draw(st.booleans()),
+                "consensusBeans": beans}})
+        want = po.results_to_tabular([dict(r, taxon=dict(r["taxon"], bitScore=float(r["taxon"]["bitScore"])) if r["taxon"] else None) for r in results],
+                                     RUN_ID, to_stdout=False)
+        objs = [shuffled(dict(r, runId=RUN_ID, taxon=(shuffled(dict(r["taxon"], consensusBeans=[shuffled(b) for b in r["taxon"]["consensusBeans"]]
+                                                                                  if r["taxon"]["consensusBeans"] is not None else None)) if r["taxon"] else None)))
+                for r in results]
+        ascii_only = data.draw(st.booleans())
+        src = d / "r.json"
+        src.write_text(json.dumps(shuffled({"results": objs, "config": None}), ensure_ascii=ascii_only, indent=data.draw(st.sampled_from([None, 1, 3]))), encoding="utf-8")
+        _tab(str(src), str(d / "r.tsv"))
+        assert (d / "r.tsv").read_bytes().decode("utf-8") == want
+        # the same objects as JSONL (one compact object per line; strings with a raw newline cannot occur: json.dumps escapes them)
+        (d / "l.json").write_text("{}")
+        srcl = d / "l.jsonl"
+        srcl.write_text("".join(json.dumps(o, ensure_ascii=ascii_only) + "\n" for o in objs), encoding="utf-8")
+        if not any("isConfig" in json.dumps(o, ensure_ascii=ascii_only) for o in objs):  # (a line holding that word is taken for the config line)
+            _tab(str(srcl), str(d / "l.tsv"), "jsonl")
+            assert (d / "l.tsv").read_bytes().decode("utf-8") == want
+
+    run()
