@@ -84,7 +84,7 @@ def _text(queries) -> bytes:
     return "".join(f"{qid}\t{acc}\t{taxid}\t{pid}\t{ln}\t0\t0\t1\t{ln}\t1\t{ln}\t1e-50\t{bits}\n" for qid, rows in queries for acc, taxid, pid, ln, bits in rows).encode()
 
 
-def _three_ways(tax, text, taxon, strategy, loud_limits=False):
+def _three_ways(tax, text, taxon, strategy, loud_limits=False, custom=None, headers=None):
     """canonical JSONL (bytes) or None when the reference would abort; asserts that the three implementations agree.
     loud_limits: the product may answer BLU_ERR_UNSUPPORTED (5) where the oracles have a result -- its documented limits
     (numbers outside the exactly-parsed range; the host-compiled core has no regrouping of scattered
@@ -92,14 +92,14 @@ def _three_ways(tax, text, taxon, strategy, loud_limits=False):
     ids = list(tax)
     lin = [tax[i] for i in ids]
     try:
-        a = po.results_to_jsonl(po.build_consensus_identities(text, tax, taxon, strategy, None)).encode()
+        a = po.results_to_jsonl(po.build_consensus_identities(text, tax, taxon, strategy, custom, headers=headers)).encode()
     except po.DataError:
         a = None
     try:
-        b = Oracle(ids, lin, taxon, strategy, None, threads=2).run_raw(text)[0]
+        b = Oracle(ids, lin, taxon, strategy, custom, threads=2).run_raw(text, headers=headers)[0]
     except OracleDataError:
         b = None
-    rc, c, msg = sim_ffi.run(ids, lin, taxon, strategy, text)
+    rc, c, msg = sim_ffi.run(ids, lin, taxon, strategy, text, custom=custom, headers=headers)
     assert (a is None) == (b is None), (a is None, b is None)
     if loud_limits and rc == 5 and a is not None:
         event("product: loud limit (" + msg.split(" at ")[0] + ")")
@@ -123,9 +123,18 @@ COMMON = dict(max_examples=int(__import__("os").environ.get("BLU_HYP_EXAMPLES", 
 def test_three_implementations_agree(data):
     tax = data.draw(lineage_maps())
     queries = data.draw(tables(tax))
-    taxon = data.draw(st.sampled_from(["bacteria", "fungi", "eukaryotes"]))
+    taxon = data.draw(st.sampled_from(["bacteria", "fungi", "eukaryotes", "custom"]))
     strategy = data.draw(st.sampled_from(["cautious", "relaxed"]))
-    _three_ways(tax, _text(queries), taxon, strategy)
+    custom = None
+    if taxon == "custom":  # CustomTaxon (taxon.rs:14-65): domain and species required, the others optional
+        custom = {"domain": data.draw(st.integers(0, 100)), "species": data.draw(st.integers(0, 100))}
+        for k in ["kingdom", "phylum", "class", "order", "family", "genus"]:
+            custom[k] = data.draw(st.one_of(st.none(), st.integers(0, 100)))
+    # ParallelBlastOutput.headers (mod.rs:84-102): ids without hits become NoConsensusFound; ids with hits change nothing
+    headers = None
+    if data.draw(st.booleans()):
+        headers = data.draw(st.lists(st.one_of(st.sampled_from([q for q, _ in queries]), st.sampled_from(["nohit_1", "nohit 2", "é"])), max_size=5, unique=True))
+    _three_ways(tax, _text(queries), taxon, strategy, custom=custom, headers=headers or None)
 
 
 @settings(**COMMON)
