@@ -387,7 +387,8 @@ def test_yaml_input_property(tmp_path_factory):
     d = tmp_path_factory.mktemp("y")
     (d / "p.json").write_text("{}")
 
-    @settings(max_examples=int(os.environ.get("BLU_HYP_EXAMPLES", "150")), deadline=None, suppress_health_check=list(HealthCheck))
+    @settings(max_examples=int(os.environ.get("BLU_HYP_EXAMPLES", "150")), deadline=None, suppress_health_check=list(HealthCheck),
+              derandomize=not os.environ.get("BLU_HYP_RANDOM"), database=None)
     @given(st.data())
     def run(data):
         results = []
@@ -427,7 +428,8 @@ def test_json_input_property(tmp_path_factory):
                         lambda c: st.one_of(st.lists(c, max_size=3), st.dictionaries(text_s, c, max_size=3)), max_leaves=6)
     d = tmp_path_factory.mktemp("jp")
 
-    @settings(max_examples=int(os.environ.get("BLU_HYP_EXAMPLES", "150")), deadline=None, suppress_health_check=list(HealthCheck))
+    @settings(max_examples=int(os.environ.get("BLU_HYP_EXAMPLES", "150")), deadline=None, suppress_health_check=list(HealthCheck),
+              derandomize=not os.environ.get("BLU_HYP_RANDOM"), database=None)
     @given(st.data())
     def run(data):
         rnd = _random.Random(data.draw(st.integers(0, 2 ** 32)))
